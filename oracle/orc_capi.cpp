@@ -1,0 +1,259 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned; see orc_math.hpp header and DESIGN.md).
+//
+// C entry points over the CPU restatement so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// `--impl reference` leg can drive it through ctypes. The product never links or loads this library.
+#include <chrono>
+#include <cstdio>
+#include <omp.h>
+
+#include "orc_render.hpp"
+
+using namespace orc;
+
+namespace {
+thread_local std::string g_err;
+struct Handle {
+    Scene scene;
+};
+M4f mat16(const float *m) {
+    M4f r;
+    if (m) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[i][j] = m[4 * i + j];
+    return r;
+}
+Bitmap bitmap(const float *d, int w, int h, int c) {
+    Bitmap b;
+    b.w = w; b.h = h; b.c = c;
+    b.data.assign(d, d + (size_t)w * h * c);
+    return b;
+}
+template <class F> int guard(F &&f) {
+    try { f(); return 0; }
+    catch (const std::exception &e) { g_err = e.what(); return 1; }
+}
+Bitmap *bsdf_slot(Bsdf &b, int which) {
+    switch (which) {
+        case 0: return &b.reflectance;
+        case 1: return &b.alpha_u;
+        case 2: return &b.alpha_v;
+        case 3: return &b.eta;
+        case 4: return &b.k;
+        default: return &b.specular_reflectance;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char *orc_last_error() { return g_err.c_str(); }
+int orc_num_threads() { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+
+void *orc_scene_new() { return new Handle(); }
+void orc_scene_free(void *h) { delete (Handle *)h; }
+
+int orc_set_options(void *h, int w, int hh, int spp, int sppe, int sppse) {
+    Scene &s = ((Handle *)h)->scene;
+    s.opts.width = w; s.opts.height = hh; s.opts.spp = spp; s.opts.sppe = sppe; s.opts.sppse = sppse;
+    return 0;
+}
+// which: 0 reflectance(3) 1 alpha_u(1) 2 alpha_v(1) 3 eta(3) 4 k(3) 5 specular_reflectance(3)
+int orc_add_bsdf(void *h, int type) {
+    Scene &s = ((Handle *)h)->scene;
+    Bsdf b;
+    b.type = type;
+    s.bsdfs.push_back(b);
+    return (int)s.bsdfs.size() - 1;
+}
+int orc_set_bsdf_texture(void *h, int bsdf, int which, const float *data, int w, int hh) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        Bitmap *slot = bsdf_slot(s.bsdfs.at(bsdf), which);
+        *slot = bitmap(data, w, hh, slot->c);
+    });
+}
+int orc_set_bsdf_tangent(void *h, int bsdf, int which, const float *tang) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        Bitmap *slot = bsdf_slot(s.bsdfs.at(bsdf), which);
+        if (tang) slot->tang.assign(tang, tang + slot->data.size()); else slot->tang.clear();
+    });
+}
+int orc_add_mesh(void *h, int nv, int nf, const float *verts, const int *faces, int nuv, const float *uvs, const int *uv_faces,
+                 int face_normals, int enable_edges, int bsdf, const float *to_world) {
+    Scene &s = ((Handle *)h)->scene;
+    Mesh m;
+    m.nv = nv; m.nf = nf;
+    m.vraw.assign(verts, verts + 3 * (size_t)nv);
+    m.faces.assign(faces, faces + 3 * (size_t)nf);
+    m.has_uv = nuv > 0;
+    if (m.has_uv) { m.uvs.assign(uvs, uvs + 2 * (size_t)nuv); m.uv_faces.assign(uv_faces, uv_faces + 3 * (size_t)nf); }
+    m.face_normals = face_normals != 0;
+    m.enable_edges = enable_edges != 0;
+    m.bsdf = bsdf;
+    m.to_world_raw = mat16(to_world);
+    int rc = guard([&] { build_edge_list(m); });
+    if (rc) return -1;
+    s.meshes.push_back(std::move(m));
+    return (int)s.meshes.size() - 1;
+}
+int orc_set_mesh_vertices(void *h, int mesh, const float *verts) {
+    return guard([&] { Mesh &m = ((Handle *)h)->scene.meshes.at(mesh); m.vraw.assign(verts, verts + 3 * (size_t)m.nv); });
+}
+int orc_set_mesh_transform(void *h, int mesh, const float *mat, int left) {
+    return guard([&] { Mesh &m = ((Handle *)h)->scene.meshes.at(mesh); (left ? m.left : m.right) = mat16(mat); });
+}
+int orc_set_mesh_vertex_tangent(void *h, int mesh, const float *tang) {
+    return guard([&] {
+        Mesh &m = ((Handle *)h)->scene.meshes.at(mesh);
+        if (tang) m.vraw_t.assign(tang, tang + 3 * (size_t)m.nv); else m.vraw_t.clear();
+    });
+}
+int orc_set_mesh_transform_tangent(void *h, int mesh, const float *tang, int left) {
+    return guard([&] {
+        Mesh &m = ((Handle *)h)->scene.meshes.at(mesh);
+        M4f t;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) t.m[i][j] = tang ? tang[4 * i + j] : 0.f;
+        if (left) { m.left_t = t; m.has_left_t = tang != nullptr; } else { m.right_t = t; m.has_right_t = tang != nullptr; }
+    });
+}
+int orc_add_area_emitter(void *h, int mesh, const float *radiance) {
+    Scene &s = ((Handle *)h)->scene;
+    Emitter e;
+    e.type = EMITTER_AREA; e.mesh = mesh; e.radiance = V3f(radiance[0], radiance[1], radiance[2]);
+    s.emitters.push_back(e);
+    s.meshes.at(mesh).emitter = (int)s.emitters.size() - 1;
+    return (int)s.emitters.size() - 1;
+}
+int orc_add_envmap(void *h, int w, int hh, const float *rgb, float scale, const float *to_world) {
+    Scene &s = ((Handle *)h)->scene;
+    Emitter e;
+    e.type = EMITTER_ENVMAP;
+    e.env_radiance = bitmap(rgb, w, hh, 3);
+    e.env_scale = scale;
+    e.env_to_world_raw = mat16(to_world);
+    s.emitters.push_back(e);
+    s.emitter_env = (int)s.emitters.size() - 1;
+    return s.emitter_env;
+}
+int orc_set_envmap_transform(void *h, const float *left) {
+    return guard([&] { Scene &s = ((Handle *)h)->scene; s.emitters.at(s.emitter_env).env_left = mat16(left); });
+}
+int orc_add_sensor(void *h, float fov_x, float near_clip, float far_clip, const float *to_world) {
+    Scene &s = ((Handle *)h)->scene;
+    Sensor c;
+    c.fov_x = fov_x; c.near_clip = near_clip; c.far_clip = far_clip; c.to_world = mat16(to_world);
+    s.sensors.push_back(c);
+    return (int)s.sensors.size() - 1;
+}
+int orc_configure(void *h) { return guard([&] { ((Handle *)h)->scene.configure(); }); }
+
+// ---- introspection of configured tables (for parity tests of the product's configure kernels) ------------
+int orc_num_triangles(void *h) { return (int)((Handle *)h)->scene.tri.size(); }
+int orc_num_meshes(void *h) { return (int)((Handle *)h)->scene.meshes.size(); }
+// 22 floats per triangle: p0 e1 e2 n0 n1 n2 face_normal face_area (types.h:136-146)
+int orc_get_triangle_info(void *h, float *out) {
+    Scene &s = ((Handle *)h)->scene;
+    for (size_t i = 0; i < s.tri.size(); ++i) {
+        const auto &t = s.tri[i];
+        const V3<Dual> *v[7] = {&t.p0, &t.e1, &t.e2, &t.n0, &t.n1, &t.n2, &t.face_normal};
+        for (int k = 0; k < 7; ++k) for (int c = 0; c < 3; ++c) out[22 * i + 3 * k + c] = (*v[k])[c].v;
+        out[22 * i + 21] = t.face_area.v;
+    }
+    return 0;
+}
+int orc_mesh_num_edges(void *h, int mesh) { return (int)((Handle *)h)->scene.meshes.at(mesh).edges.size() / 5; }
+int orc_mesh_get_edges(void *h, int mesh, int *out) {
+    const auto &e = ((Handle *)h)->scene.meshes.at(mesh).edges;
+    std::copy(e.begin(), e.end(), out);
+    return 0;
+}
+int orc_num_sec_edges(void *h) { return (int)((Handle *)h)->scene.sec_edges.size(); }
+// 16 floats per secondary edge: p0 e1 n0 n1 p2 is_boundary (edge.h:50-65)
+int orc_get_sec_edges(void *h, float *out) {
+    Scene &s = ((Handle *)h)->scene;
+    for (size_t i = 0; i < s.sec_edges.size(); ++i) {
+        const auto &e = s.sec_edges[i];
+        const V3<Dual> *v[5] = {&e.p0, &e.e1, &e.n0, &e.n1, &e.p2};
+        for (int k = 0; k < 5; ++k) for (int c = 0; c < 3; ++c) out[16 * i + 3 * k + c] = (*v[k])[c].v;
+        out[16 * i + 15] = e.is_boundary ? 1.f : 0.f;
+    }
+    return 0;
+}
+int orc_num_primary_edges(void *h, int sensor) { return (int)((Handle *)h)->scene.sensors.at(sensor).edges.size(); }
+// 7 floats per primary edge: p0.xy p1.xy edge_normal.xy edge_length (edge.h:28-40)
+int orc_get_primary_edges(void *h, int sensor, float *out) {
+    const auto &ed = ((Handle *)h)->scene.sensors.at(sensor).edges;
+    for (size_t i = 0; i < ed.size(); ++i) {
+        out[7 * i + 0] = ed[i].p0.x.v; out[7 * i + 1] = ed[i].p0.y.v; out[7 * i + 2] = ed[i].p1.x.v; out[7 * i + 3] = ed[i].p1.y.v;
+        out[7 * i + 4] = ed[i].edge_normal.x; out[7 * i + 5] = ed[i].edge_normal.y; out[7 * i + 6] = ed[i].edge_length;
+    }
+    return 0;
+}
+// camera: sample_to_camera(16) world_to_sample(16) to_world(16) camera_pos(3) camera_dir(3) inv_area(1)
+int orc_get_sensor(void *h, int sensor, float *out) {
+    const Sensor &c = ((Handle *)h)->scene.sensors.at(sensor);
+    const M4<Dual> *m[3] = {&c.sample_to_camera, &c.world_to_sample, &c.to_world_d};
+    for (int k = 0; k < 3; ++k) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[16 * k + 4 * i + j] = m[k]->m[i][j].v;
+    for (int k = 0; k < 3; ++k) { out[48 + k] = c.camera_pos[k].v; out[51 + k] = c.camera_dir[k].v; }
+    out[54] = c.inv_area.v;
+    return 0;
+}
+
+// ---- RNG known-answer helpers ---------------------------------------------------------------------------
+void orc_pcg32_kat(uint64_t initstate, uint64_t initseq, int n, uint32_t *out) {
+    PCG32 r;
+    r.seed(initstate, initseq);
+    for (int i = 0; i < n; ++i) out[i] = r.next_uint32();
+}
+void orc_sampler_kat(uint64_t lane, int n, uint32_t *out_u32, float *out_f32) {
+    SamplerLane a = SamplerLane::make(lane), b = SamplerLane::make(lane);
+    for (int i = 0; i < n; ++i) { out_u32[i] = a.rng.next_uint32(); out_f32[i] = b.next_1d(); }
+}
+int orc_discrete_sample_reuse(const float *pmf, int n, const float *u_in, int m, int *idx, float *pdf, float *u_out) {
+    DiscreteDistribution d;
+    d.init(std::vector<float>(pmf, pmf + n));
+    for (int i = 0; i < m; ++i) { float u = u_in[i]; auto pr = d.sample_reuse(u); idx[i] = pr.first; pdf[i] = pr.second; u_out[i] = u; }
+    return 0;
+}
+
+// ---- closest hit (cuda/psdr_cuda.cu:9-45 contract: tri id, shape id, u, v; -1 on miss) -------------------------
+int orc_trace(void *h, int64_t n, const float *o, const float *d, const float *tmax, int *tri, int *shape, float *u, float *v, float *t, int brute) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        if (!s.ready) throw std::runtime_error("Input scene must be configured!");
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) {
+            Ray<float> r(V3f(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3f(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
+            r.tmax = tmax ? tmax[i] : kInf;
+            Hit hit = brute ? s.accel.closest_brute(r) : s.accel.closest(r);
+            tri[i] = hit.tri; shape[i] = hit.tri >= 0 ? s.tri_mesh[hit.tri] : -1;
+            u[i] = hit.u; v[i] = hit.v;
+            if (t) t[i] = hit.t;
+        }
+    });
+}
+
+// ---- integrators -------------------------------------------------------------------------------------------
+void *orc_integrator_new(int kind, int bsdf_samples, int light_samples, int hide_emitters, int field, int max_depth) {
+    Integrator *I = new Integrator();
+    I->kind = kind; I->bsdf_samples = bsdf_samples; I->light_samples = light_samples;
+    I->hide_emitters = hide_emitters != 0; I->field = field; I->max_depth = max_depth;
+    return I;
+}
+void orc_integrator_free(void *I) { delete (Integrator *)I; }
+int orc_render_c(void *h, void *I, int sensor, float *out) {
+    return guard([&] { renderC(*(Integrator *)I, ((Handle *)h)->scene, sensor, out); });
+}
+int orc_render_d(void *h, void *I, int sensor, float *out, float *out_t) {
+    return guard([&] { renderD(*(Integrator *)I, ((Handle *)h)->scene, sensor, out, out_t); });
+}
+int orc_preprocess_secondary_edges(void *h, void *I, int sensor, const int *reso4, int nrounds) {
+    return guard([&] { preprocess_secondary_edges(*(Integrator *)I, ((Handle *)h)->scene, sensor, reso4, nrounds); });
+}
+int orc_reseed(void *h) {   // drop sampler state so that the next configure() starts the streams afresh
+    Scene &s = ((Handle *)h)->scene;
+    for (auto &v : s.samplers) v.clear();
+    return 0;
+}
+
+}  // extern "C"
