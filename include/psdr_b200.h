@@ -1,0 +1,120 @@
+/* psdr_b200.h — C ABI of the B200-native path-space differentiable rendering hot path.
+ *
+ * This is the drop-in boundary for psdr-cuda's `Integrator::renderC / renderD` path. The reference has no C ABI or
+ * FFI of its own: its boundary is the pybind11 module `psdr_cuda` (src/psdr.cpp:41-295). Every entry point below
+ * cites the reference interface it stands behind; the pybind11 host layer of this repo (psdr_cuda_b200/host) binds
+ * exactly these, and INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every call returns 0 on success and a non-zero code on failure (never throws across the ABI);
+ * pb_last_error(ctx) returns the message (the reference raises psdr::Exception -> Python RuntimeError,
+ * include/misc/Exception.h:13-107). Pointers named h_* are host memory, d_* are device memory on the context's GPU.
+ * The context owns scene tables, BVH and wavefront buffers; the caller owns every image / gradient buffer it passes.
+ * One context per host thread and GPU; no global state. All work is enqueued on the context's stream and the call
+ * returns after the stream has been synchronised unless stated otherwise.
+ */
+#ifndef PSDR_B200_H
+#define PSDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+/* BSDF kinds / texture slots: src/scene/scene_loader.cpp:318-351 (diffuse, roughconductor) */
+enum { PB_BSDF_DIFFUSE = 0, PB_BSDF_ROUGHCONDUCTOR = 1 };
+enum { PB_TEX_REFLECTANCE = 0, PB_TEX_ALPHA_U = 1, PB_TEX_ALPHA_V = 2, PB_TEX_ETA = 3, PB_TEX_K = 4, PB_TEX_SPECULAR_REFLECTANCE = 5 };
+/* integrators: src/psdr.cpp:282-294 (+ the multi-bounce PathIntegrator BASELINE.json names; depth 1 == Direct(1,1)) */
+enum { PB_INTEG_DIRECT = 0, PB_INTEG_FIELD = 1, PB_INTEG_PATH = 2 };
+/* FieldExtractionIntegrator fields: src/integrator/field.cpp:38-52 */
+enum { PB_FIELD_SILHOUETTE = 0, PB_FIELD_POSITION, PB_FIELD_DEPTH, PB_FIELD_GEONORMAL, PB_FIELD_SHNORMAL, PB_FIELD_UV };
+/* mesh flags: Mesh::m_use_face_normals / m_enable_edges (include/psdr/shape/mesh.h) */
+enum { PB_MESH_FACE_NORMALS = 1, PB_MESH_ENABLE_EDGES = 2 };
+/* differentiable leaves: what a gradient segment refers to */
+enum { PB_PARAM_BSDF_TEXTURE = 0, PB_PARAM_MESH_VERTICES = 1 };
+
+typedef struct pb_integrator {
+    int kind;           /* PB_INTEG_* */
+    int bsdf_samples;   /* DirectIntegrator(bsdf_samples, light_samples): src/integrator/direct.cpp:30-32 */
+    int light_samples;
+    int hide_emitters;  /* DirectIntegrator.hide_emitters: src/psdr.cpp:294 */
+    int field;          /* PB_FIELD_* for PB_INTEG_FIELD */
+    int max_depth;      /* PB_INTEG_PATH: number of scattering events */
+} pb_integrator;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int pb_ctx_create(int device, pb_ctx **out);
+int pb_ctx_destroy(pb_ctx *ctx);
+const char *pb_last_error(pb_ctx *ctx);            /* ctx may be NULL: message of the last failed pb_ctx_create */
+int pb_version(void);
+/* lanes per wavefront batch (multiple of 1024); 0 restores the default. Tiling replaces the reference's
+ * "all W*H*spp lanes at once" (src/integrator/integrator.cpp:69-76). */
+int pb_ctx_set_batch(pb_ctx *ctx, int64_t lanes);
+/* multi-GPU: this context renders shard `rank` of `world` (pixel tiles for the interior term, lane ranges for the
+ * edge terms; RNG streams stay indexed by the global lane id). Default (0, 1). */
+int pb_ctx_set_shard(pb_ctx *ctx, int rank, int world);
+
+/* ---- scene description: what SceneLoader::load_scene builds (src/scene/scene_loader.cpp:208-242) ------------- */
+/* RenderOption: include/psdr/types.h:171-182, src/psdr.cpp:53-72 */
+int pb_scene_set_options(pb_ctx *ctx, int width, int height, int spp, int sppe, int sppse);
+/* PerspectiveCamera(fov_x, near, far) + to_world (row-major 4x4): src/sensor/perspective.cpp, src/psdr.cpp:222-224. Returns id >= 0. */
+int pb_scene_add_sensor(pb_ctx *ctx, float fov_x, float near_clip, float far_clip, const float h_to_world[16]);
+int pb_scene_set_sensor_transform(pb_ctx *ctx, int sensor, const float h_to_world[16]);
+/* Diffuse / RoughConductor with their default textures (src/bsdf/*.h). Returns id >= 0. */
+int pb_scene_add_bsdf(pb_ctx *ctx, int type);
+/* Bitmap data of one slot, interleaved [ (y*w + x)*C + c ], C = 1 (alpha_u/v) or 3: src/core/bitmap.cpp, src/psdr.cpp:102-120 */
+int pb_scene_set_bsdf_texture(pb_ctx *ctx, int bsdf, int slot, const float *h_data, int w, int h);
+/* Mesh::load result (src/shape/mesh.cpp:62-141): object-space vertices (xyz AoS), triangle indices, optional uvs. Returns id >= 0. */
+int pb_scene_add_mesh(pb_ctx *ctx, int num_vertices, int num_faces, const float *h_vertices, const int *h_faces, int num_uvs,
+                      const float *h_uvs, const int *h_uv_faces, int flags, int bsdf, const float h_to_world[16]);
+int pb_scene_set_mesh_vertices(pb_ctx *ctx, int mesh, const float *h_vertices);              /* Mesh.vertex_positions setter */
+int pb_scene_set_mesh_transform(pb_ctx *ctx, int mesh, const float h_mat[16], int left);     /* Mesh::set_transform, mesh.h:19-26 */
+/* AreaLight(radiance, mesh): src/emitter/area.cpp, src/psdr.cpp:230-231. Returns id >= 0. */
+int pb_scene_add_area_emitter(pb_ctx *ctx, int mesh, const float h_radiance[3]);
+/* Scene::configure: src/scene/scene.cpp:56-278 (sampler seeding rule, mesh preprocessing, emitter pmf, triangle table, BVH) */
+int pb_scene_configure(pb_ctx *ctx);
+/* forget sampler positions so that the next configure() restarts every stream (a fresh Scene in the reference) */
+int pb_scene_reseed(pb_ctx *ctx);
+int pb_scene_num_triangles(pb_ctx *ctx);
+/* configured tables, for inspection: 22 floats per triangle (p0 e1 e2 n0 n1 n2 face_normal area; types.h:136-146) */
+int pb_scene_get_triangle_info(pb_ctx *ctx, float *h_out);
+/* unique edges of a mesh, 5 ints each (v0 v1 f0 f1|-1 opposite vertex): src/shape/mesh.cpp:143-203, Mesh.edge_indices() */
+int pb_scene_mesh_num_edges(pb_ctx *ctx, int mesh);
+int pb_scene_mesh_get_edges(pb_ctx *ctx, int mesh, int *h_out);
+
+/* ---- hot path ------------------------------------------------------------------------------------------------- */
+/* Scene_OptiX::ray_intersect (src/scene/scene_optix.cpp:80-126, cuda/psdr_cuda.cu:9-45): n rays as 8 floats each
+ * (o.xyz, tmax, d.xyz, 0), hits as 4 x 32 bit each (tri id, shape id, u, v); d_t (optional) receives the distance. */
+int pb_trace(pb_ctx *ctx, int64_t n, const float *d_rays, void *d_hits, float *d_t);
+/* Integrator::renderC (src/integrator/integrator.cpp:13-29): d_image receives W*H*3 floats, pixel = y*W + x */
+int pb_render_c(pb_ctx *ctx, const pb_integrator *integ, int sensor, float *d_image);
+/* same call with host buffers: image copied back inside the call */
+int pb_render_c_host(pb_ctx *ctx, const pb_integrator *integ, int sensor, float *h_image);
+/* Integrator::renderD primal (src/integrator/integrator.cpp:32-60): the AD formulation's image; remembers the sampler
+ * positions so that pb_render_d_vjp replays the same paths */
+int pb_render_d(pb_ctx *ctx, const pb_integrator *integ, int sensor, float *d_image);
+
+/* ---- gradients (reverse mode: ek.backward + ek.gradient in the reference, docs/inverse_diff_render.rst:71-79) -- */
+/* mark a leaf as requiring a gradient (ek.set_requires_gradient); slot only for PB_PARAM_BSDF_TEXTURE */
+int pb_grad_require(pb_ctx *ctx, int param_kind, int id, int slot, int enable);
+/* layout of the flat fp32 gradient vector: number of segments, and per segment (kind, id, slot, offset, count) */
+int pb_grad_num_segments(pb_ctx *ctx);
+int pb_grad_segment(pb_ctx *ctx, int index, int *kind, int *id, int *slot, int64_t *offset, int64_t *count);
+int64_t pb_grad_size(pb_ctx *ctx);
+/* VJP of renderD: d_dLdI is W*H*3; accumulates (+=) into d_grad (pb_grad_size floats; the caller zeroes it).
+ * On several GPUs each rank holds a private d_grad and the caller all-reduces it once. */
+int pb_render_d_vjp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const float *d_dLdI, float *d_grad);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------------- */
+/* kernels launched by this context since creation, and the milliseconds the last render call spent in its traversal
+ * kernels (CUDA events on the context's stream) — bench.py's gpu_launches and roofline inputs */
+int64_t pb_stats_launches(pb_ctx *ctx);
+float pb_stats_last_trace_ms(pb_ctx *ctx);
+int64_t pb_stats_last_rays(pb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSDR_B200_H */

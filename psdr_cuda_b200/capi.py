@@ -1,0 +1,239 @@
+"""ctypes binding of include/psdr_b200.h (lib/libpsdr_b200.so) — the lowest Python layer of the product.
+
+torch is used only as the owner of device buffers (images, rays, gradients); every computation happens inside the
+shared library. There is no CPU fallback: creating a context without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libpsdr_b200.so")
+_lib = None
+
+BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR = 0, 1
+TEX = {"reflectance": 0, "alpha_u": 1, "alpha_v": 2, "eta": 3, "k": 4, "specular_reflectance": 5}
+INTEG_DIRECT, INTEG_FIELD, INTEG_PATH = 0, 1, 2
+FIELDS = {"silhouette": 0, "position": 1, "depth": 2, "geoNormal": 3, "shNormal": 4, "uv": 5}
+MESH_FACE_NORMALS, MESH_ENABLE_EDGES = 1, 2
+PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES = 0, 1
+
+SYMBOLS = [
+    "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard",
+    "pb_scene_set_options", "pb_scene_add_sensor", "pb_scene_set_sensor_transform", "pb_scene_add_bsdf", "pb_scene_set_bsdf_texture",
+    "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_configure",
+    "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
+    "pb_trace", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
+    "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays",
+]
+
+
+class Integrator(C.Structure):
+    _fields_ = [("kind", C.c_int), ("bsdf_samples", C.c_int), ("light_samples", C.c_int), ("hide_emitters", C.c_int),
+                ("field", C.c_int), ("max_depth", C.c_int)]
+
+
+def lib():
+    """Load the shared library; fail loudly if it has not been built (python -m psdr_cuda_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError("psdr_cuda_b200: %s is missing — run `python psdr_cuda_b200/build.py` (no CPU fallback exists)" % _LIB_PATH)
+        L = C.CDLL(_LIB_PATH)
+        L.pb_last_error.restype = C.c_char_p
+        L.pb_last_error.argtypes = [C.c_void_p]
+        L.pb_grad_size.restype = C.c_int64
+        L.pb_stats_launches.restype = C.c_int64
+        L.pb_stats_last_rays.restype = C.c_int64
+        L.pb_stats_last_trace_ms.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _dp(t):
+    """device pointer of a contiguous torch CUDA tensor"""
+    assert t.is_cuda and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def make_integrator(kind="direct", bsdf_samples=1, light_samples=1, hide_emitters=False, field="silhouette", max_depth=1):
+    k = {"direct": INTEG_DIRECT, "field": INTEG_FIELD, "path": INTEG_PATH}[kind]
+    return Integrator(k, bsdf_samples, light_samples, int(hide_emitters), FIELDS[field], max_depth)
+
+
+class Context:
+    def __init__(self, device=0):
+        L = lib()
+        h = C.c_void_p()
+        if L.pb_ctx_create(int(device), C.byref(h)) != 0:
+            raise RuntimeError(L.pb_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self.width = self.height = 0
+
+    def close(self):
+        if self.h is not None:
+            lib().pb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(lib().pb_last_error(self.h).decode())
+
+    def _id(self, rc):
+        if rc < 0:
+            raise RuntimeError(lib().pb_last_error(self.h).decode())
+        return rc
+
+    # --- scene description -----------------------------------------------------------------------------------
+    def set_options(self, width, height, spp, sppe=0, sppse=0):
+        self._chk(lib().pb_scene_set_options(self.h, width, height, spp, sppe, sppse))
+        self.width, self.height = width, height
+
+    def set_batch(self, lanes):
+        self._chk(lib().pb_ctx_set_batch(self.h, C.c_int64(lanes)))
+
+    def set_shard(self, rank, world):
+        self._chk(lib().pb_ctx_set_shard(self.h, rank, world))
+
+    def add_sensor(self, fov, near, far, to_world):
+        return self._id(lib().pb_scene_add_sensor(self.h, C.c_float(fov), C.c_float(near), C.c_float(far), _p(_f(to_world))))
+
+    def add_bsdf(self, type_):
+        return self._id(lib().pb_scene_add_bsdf(self.h, type_))
+
+    def set_bsdf_texture(self, bsdf, slot, data):
+        t = _f(data)
+        assert t.ndim == 3
+        self._chk(lib().pb_scene_set_bsdf_texture(self.h, bsdf, TEX[slot] if isinstance(slot, str) else slot, _p(t), t.shape[1], t.shape[0]))
+
+    def add_mesh(self, verts, faces, uvs=None, uv_faces=None, face_normals=False, enable_edges=True, bsdf=-1, to_world=None):
+        v, f = _f(verts), _i(faces)
+        has_uv = uvs is not None
+        u, uf = (_f(uvs), _i(uv_faces)) if has_uv else (None, None)
+        flags = (MESH_FACE_NORMALS if face_normals else 0) | (MESH_ENABLE_EDGES if enable_edges else 0)
+        tw = _f(to_world if to_world is not None else np.eye(4))
+        return self._id(lib().pb_scene_add_mesh(self.h, len(v), len(f), _p(v), _p(f), len(u) if has_uv else 0, _p(u), _p(uf), flags, bsdf, _p(tw)))
+
+    def set_mesh_vertices(self, mesh, verts):
+        self._chk(lib().pb_scene_set_mesh_vertices(self.h, mesh, _p(_f(verts))))
+
+    def set_mesh_transform(self, mesh, mat, left=True):
+        self._chk(lib().pb_scene_set_mesh_transform(self.h, mesh, _p(_f(mat)), int(left)))
+
+    def add_area_emitter(self, mesh, radiance):
+        return self._id(lib().pb_scene_add_area_emitter(self.h, mesh, _p(_f(radiance))))
+
+    def configure(self, reseed=False):
+        if reseed:
+            lib().pb_scene_reseed(self.h)
+        self._chk(lib().pb_scene_configure(self.h))
+
+    def load_description(self, desc, opts=None):
+        """Feed a scene-description dict (sensors / bsdfs / meshes / emitters / opts) through the C ABI."""
+        o = dict(desc["opts"])
+        if opts:
+            o.update(opts)
+        self.set_options(o["width"], o["height"], o["spp"], o.get("sppe", 0), o.get("sppse", 0))
+        for s in desc["sensors"]:
+            self.add_sensor(s["fov"], s["near"], s["far"], s["to_world"])
+        for b in desc["bsdfs"]:
+            bi = self.add_bsdf(b["type"])
+            for k in TEX:
+                if k in b:
+                    self.set_bsdf_texture(bi, k, b[k])
+        emitter_of = {e["mesh"]: e for e in desc["emitters"]}
+        for mi, m in enumerate(desc["meshes"]):
+            self.add_mesh(m["verts"], m["faces"], m.get("uvs"), m.get("uv_faces"), m["face_normals"], m["enable_edges"], m["bsdf"], m["to_world"])
+            if mi in emitter_of:
+                self.add_area_emitter(mi, emitter_of[mi]["radiance"])
+
+    # --- inspection --------------------------------------------------------------------------------------------
+    def triangle_info(self):
+        n = lib().pb_scene_num_triangles(self.h)
+        out = np.empty((n, 22), dtype=np.float32)
+        self._chk(lib().pb_scene_get_triangle_info(self.h, _p(out)))
+        return out
+
+    def mesh_edges(self, mesh):
+        n = self._id(lib().pb_scene_mesh_num_edges(self.h, mesh))
+        out = np.empty((n, 5), dtype=np.int32)
+        self._chk(lib().pb_scene_mesh_get_edges(self.h, mesh, _p(out)))
+        return out
+
+    # --- hot path ------------------------------------------------------------------------------------------------
+    def trace(self, rays):
+        """rays: (n, 8) float32 CUDA tensor (o.xyz, tmax, d.xyz, 0) -> (hits int32 (n,4) view pair, t)"""
+        import torch
+        n = rays.shape[0]
+        hits = torch.empty((n, 4), dtype=torch.int32, device=rays.device)
+        t = torch.empty(n, dtype=torch.float32, device=rays.device)
+        self._chk(lib().pb_trace(self.h, C.c_int64(n), _dp(rays), _dp(hits), _dp(t)))
+        return hits, t
+
+    def _image(self):
+        import torch
+        return torch.empty((self.height * self.width, 3), dtype=torch.float32, device="cuda:%d" % self.device)
+
+    def render_c(self, integ, sensor=0, out=None):
+        img = out if out is not None else self._image()
+        self._chk(lib().pb_render_c(self.h, C.byref(integ), sensor, _dp(img)))
+        return img
+
+    def render_c_host(self, integ, sensor=0, out=None):
+        img = out if out is not None else np.empty((self.height * self.width, 3), dtype=np.float32)
+        self._chk(lib().pb_render_c_host(self.h, C.byref(integ), sensor, _p(img)))
+        return img
+
+    def render_d(self, integ, sensor=0, out=None):
+        img = out if out is not None else self._image()
+        self._chk(lib().pb_render_d(self.h, C.byref(integ), sensor, _dp(img)))
+        return img
+
+    # --- gradients ---------------------------------------------------------------------------------------------
+    def grad_require(self, kind, id_, slot=0, enable=True):
+        self._chk(lib().pb_grad_require(self.h, kind, id_, TEX[slot] if isinstance(slot, str) else slot, int(enable)))
+
+    def grad_layout(self):
+        L = lib()
+        out = []
+        for i in range(L.pb_grad_num_segments(self.h)):
+            k, d, s = C.c_int(), C.c_int(), C.c_int()
+            off, cnt = C.c_int64(), C.c_int64()
+            self._chk(L.pb_grad_segment(self.h, i, C.byref(k), C.byref(d), C.byref(s), C.byref(off), C.byref(cnt)))
+            out.append(dict(kind=k.value, id=d.value, slot=s.value, offset=off.value, count=cnt.value))
+        return out
+
+    def grad_size(self):
+        return int(lib().pb_grad_size(self.h))
+
+    def render_d_vjp(self, integ, dLdI, sensor=0, grad=None):
+        import torch
+        if grad is None:
+            grad = torch.zeros(max(1, self.grad_size()), dtype=torch.float32, device=dLdI.device)
+        self._chk(lib().pb_render_d_vjp(self.h, C.byref(integ), sensor, _dp(dLdI.contiguous()), _dp(grad)))
+        return grad
+
+    # --- stats -------------------------------------------------------------------------------------------------
+    def stats(self):
+        L = lib()
+        return dict(launches=int(L.pb_stats_launches(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)))

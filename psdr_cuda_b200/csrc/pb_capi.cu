@@ -1,0 +1,626 @@
+// psdr-b200: implementation of the C ABI declared in include/psdr_b200.h.
+//
+// Host side of Scene::configure (src/scene/scene.cpp:56-278) and of Integrator::renderC/renderD
+// (src/integrator/integrator.cpp:13-95): owns the scene description, prepares the device tables, and drives the
+// wavefront kernels batch by batch on the context's stream.
+#include "../../include/psdr_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "pb_host.h"
+
+namespace pb {
+
+// ---- small host matrix helpers (fp32, op order as written: s = s + a*b from 0) ---------------------------------
+Mat4h matmul(const Mat4h &a, const Mat4h &b) {
+    Mat4h c;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < 4; ++k) s = s + a.m[4 * i + k] * b.m[4 * k + j];
+            c.m[4 * i + j] = s;
+        }
+    return c;
+}
+// Gauss-Jordan with partial pivoting in double, rounded once to fp32
+Mat4h inverse(const Mat4h &A) {
+    double a[4][8];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) { a[i][j] = A.m[4 * i + j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; ++c) {
+        int p = c;
+        for (int r = c + 1; r < 4; ++r) if (std::fabs(a[r][c]) > std::fabs(a[p][c])) p = r;
+        if (p != c) for (int j = 0; j < 8; ++j) std::swap(a[p][j], a[c][j]);
+        const double inv = 1.0 / a[c][c];
+        for (int j = 0; j < 8; ++j) a[c][j] *= inv;
+        for (int r = 0; r < 4; ++r) {
+            if (r == c) continue;
+            const double f = a[r][c];
+            for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    Mat4h R;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) R.m[4 * i + j] = (float)a[i][4 + j];
+    return R;
+}
+static Mat4 to_dev(const Mat4h &m) { Mat4 r; std::memcpy(r.m, m.m, sizeof(r.m)); return r; }
+static Mat4h from_ptr(const float *p) { Mat4h r = Mat4h::identity(); if (p) std::memcpy(r.m, p, sizeof(r.m)); return r; }
+
+// unique undirected edges in (min,max) order: (v0, v1, f0, f1|-1, opposite vertex of f0) — src/shape/mesh.cpp:143-203
+static void build_edges(HostMesh &m) {
+    struct Half { int lo, hi, face, opp; };
+    std::vector<Half> hs;
+    hs.reserve(3 * (size_t)m.nf);
+    for (int f = 0; f < m.nf; ++f)
+        for (int i = 0; i < 3; ++i) {
+            const int a = m.faces[3 * f + i], b = m.faces[3 * f + (i + 1) % 3], c = m.faces[3 * f + (i + 2) % 3];
+            hs.push_back({std::min(a, b), std::max(a, b), f, c});
+        }
+    std::stable_sort(hs.begin(), hs.end(), [](const Half &x, const Half &y) { return x.lo != y.lo ? x.lo < y.lo : x.hi < y.hi; });
+    m.edges.clear();
+    for (size_t i = 0; i < hs.size();) {
+        size_t j = i;
+        while (j < hs.size() && hs[j].lo == hs[i].lo && hs[j].hi == hs[i].hi) ++j;
+        const size_t cnt = j - i;
+        PB_ASSERT_MSG(cnt <= 2, "Edge shared by more than 2 faces");
+        PB_ASSERT_MSG(!(cnt == 2 && hs[i].face == hs[i + 1].face), "Duplicated faces");
+        const int e[5] = {hs[i].lo, hs[i].hi, hs[i].face, cnt == 2 ? hs[i + 1].face : -1, hs[i].opp};
+        m.edges.insert(m.edges.end(), e, e + 5);
+        i = j;
+    }
+}
+
+// vertex -> incident faces in the order the reference's three scatter_add passes visit them (mesh.cpp:34-37)
+static void build_csr(HostMesh &m) {
+    m.csr_off.assign(m.nv + 1, 0);
+    for (int i = 0; i < 3 * m.nf; ++i) m.csr_off[m.faces[i] + 1]++;
+    for (int v = 0; v < m.nv; ++v) m.csr_off[v + 1] += m.csr_off[v];
+    m.csr_face.resize(3 * (size_t)m.nf);
+    std::vector<int> cur(m.csr_off.begin(), m.csr_off.end() - 1);
+    for (int i = 0; i < 3; ++i)
+        for (int f = 0; f < m.nf; ++f) m.csr_face[cur[m.faces[3 * f + i]]++] = f;
+}
+
+// perspective.cpp:11-32
+static void configure_sensor(HostSensor &s, int W, int H) {
+    const float aspect = (float)W / (float)H;
+    const float *t = s.to_world.m;
+    const float det = t[0] * (t[5] * t[10] - t[6] * t[9]) - t[1] * (t[4] * t[10] - t[6] * t[8]) + t[2] * (t[4] * t[9] - t[5] * t[8]);
+    PB_ASSERT_MSG(std::fabs(det - 1.f) < kEpsilon, "Sensor transformation should not involve scaling!");
+    Mat4h sc = Mat4h::identity(), tr = Mat4h::identity(), pe = Mat4h::identity();
+    sc.m[0] = -0.5f; sc.m[5] = -0.5f * aspect;
+    tr.m[3] = -1.f; tr.m[7] = -1.f / aspect;
+    const float recip = 1.f / (s.far_clip - s.near_clip);
+    const float tn = std::tan(s.fov_x * .5f * kPi / 180.f), cot = 1.f / tn;
+    pe.m[0] = cot; pe.m[5] = cot; pe.m[10] = s.far_clip * recip; pe.m[15] = 0.f;
+    pe.m[11] = -s.near_clip * s.far_clip * recip; pe.m[14] = 1.f;
+    const Mat4h c2s = matmul(matmul(sc, tr), pe);
+    const Mat4h s2c = inverse(c2s);
+    const Mat4h w2s = matmul(c2s, inverse(s.to_world));
+    SensorRec &r = s.rec;
+    r.sample_to_camera = to_dev(s2c);
+    r.to_world = to_dev(s.to_world);
+    r.world_to_sample = to_dev(w2s);
+    r.camera_pos = transform_pos(r.to_world, f3(0.f));
+    r.camera_dir = transform_dir(r.to_world, f3(0.f, 0.f, 1.f));
+    const float3 v00 = transform_pos(r.sample_to_camera, f3(0.f, 0.f, 0.f)), v10 = transform_pos(r.sample_to_camera, f3(1.f, 0.f, 0.f)),
+                 v11 = transform_pos(r.sample_to_camera, f3(1.f, 1.f, 0.f)), vc = transform_pos(r.sample_to_camera, f3(.5f, .5f, 0.f));
+    r.inv_area = 1.f / (norm(v00 - v10) * norm(v11 - v10)) * squared_norm(vc);
+    r.width = W; r.height = H;
+}
+
+static cudaEvent_t get_event(pb_ctx *c, size_t idx) {
+    while (c->ev_pool.size() <= idx) {
+        cudaEvent_t e;
+        PB_CUDA(cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[idx];
+}
+
+static void configure(pb_ctx *c) {
+    PB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    PB_ASSERT_MSG(!c->meshes.empty(), "Missing meshes!");
+    PB_ASSERT_MSG(!c->sensors.empty(), "Missing sensor!");
+    PB_ASSERT_MSG(c->width > 0 && c->height > 0, "Invalid film size!");
+    // scene.cpp:65-79 — streams are re-seeded only when the lane count changes
+    const int spps[3] = {c->spp, c->sppe, c->sppse};
+    for (int k = 0; k < 3; ++k) {
+        if (spps[k] <= 0) continue;
+        const int64_t count = (int64_t)c->width * c->height * spps[k];
+        PB_ASSERT_MSG(count <= std::numeric_limits<int>::max(), "Too many samples (integrator.cpp:73-74)");
+        if (c->sampler_count[k] != count) { c->sampler_count[k] = count; c->sampler_offset[k] = 0; }
+    }
+    // meshes -> triangle table
+    int total = 0;
+    for (auto &m : c->meshes) { m.face_offset = total; total += m.nf; }
+    c->num_tri = total;
+    c->d_tri.reserve(std::max<size_t>(1, total) * sizeof(TriRec));
+    for (size_t i = 0; i < c->meshes.size(); ++i) {
+        HostMesh &m = c->meshes[i];
+        if (m.topo_dirty) {
+            m.d_faces.upload(m.faces, st);
+            m.d_csr_off.upload(m.csr_off, st);
+            m.d_csr_face.upload(m.csr_face, st);
+            if (m.flags & 2) { m.d_uvs.upload(m.uvs, st); m.d_uv_faces.upload(m.uv_faces, st); }
+            m.topo_dirty = false;
+        }
+        if (m.verts_dirty) { m.d_vraw.upload(m.verts, st); m.verts_dirty = false; }
+        m.d_vworld.reserve(3 * (size_t)m.nv * sizeof(float));
+        m.d_vnormal.reserve(3 * (size_t)m.nv * sizeof(float));
+        m.d_fcross.reserve((size_t)m.nf * sizeof(float4));
+        m.d_face_area.reserve((size_t)m.nf * sizeof(float));
+        m.to_world = matmul(matmul(m.left, m.raw), m.right);   // mesh.cpp:223
+        launch_mesh_preprocess(st, m.nv, m.nf, m.face_offset, (int)i, m.flags & 3, m.d_vraw.as<float>(), to_dev(m.to_world), m.d_faces.as<int>(),
+                               m.d_csr_off.as<int>(), m.d_csr_face.as<int>(), m.d_uvs.as<float>(), m.d_uv_faces.as<int>(), m.d_vworld.as<float>(),
+                               m.d_fcross.as<float4>(), m.d_vnormal.as<float>(), c->d_tri.as<TriRec>(), m.d_face_area.as<float>());
+        c->launches += 4;
+    }
+    c->h_tri.resize((size_t)total * 32);
+    if (total) PB_CUDA(cudaMemcpyAsync(c->h_tri.data(), c->d_tri.p, (size_t)total * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    // face-area pmf / cmf per emitter mesh (mesh.cpp:238-249): sequential fp32 sums, as the oracle
+    for (auto &m : c->meshes) {
+        if (m.emitter < 0) continue;
+        std::vector<float> cmf(m.nf);
+        float acc = 0.f;
+        for (int f = 0; f < m.nf; ++f) { acc += c->h_tri[(size_t)(m.face_offset + f) * 32 + 3]; cmf[f] = acc; }
+        m.total_area = acc; m.face_sum = acc;
+        m.inv_total_area = 1.f / acc;
+        m.d_face_cmf.upload(cmf, st);
+    }
+    // BVH over all triangles (replaces optixAccelBuild, optix.h:277-340)
+    {
+        std::vector<float> geo(9 * (size_t)total);
+        for (int t = 0; t < total; ++t)
+            for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) geo[9 * (size_t)t + 3 * k + a] = c->h_tri[(size_t)t * 32 + 4 * k + a];
+        std::vector<HostNode> nodes;
+        std::vector<int> order;
+        build_bvh(geo.data(), total, nodes, order);
+        std::vector<BvhNode> dn(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            const HostNode &n = nodes[i];
+            dn[i].a = make_float4(n.llo[0], n.llo[1], n.llo[2], n.lhi[0]);
+            dn[i].b = make_float4(n.lhi[1], n.lhi[2], n.rlo[0], n.rlo[1]);
+            dn[i].c = make_float4(n.rlo[2], n.rhi[0], n.rhi[1], n.rhi[2]);
+            float l, r;
+            std::memcpy(&l, &n.left, 4); std::memcpy(&r, &n.right, 4);
+            dn[i].d = make_float4(l, r, 0.f, 0.f);
+        }
+        c->d_nodes.upload(dn, st);
+        c->d_order.upload(order, st);
+        c->d_leaf.reserve(std::max<size_t>(1, order.size()) * sizeof(LeafTri));
+        if (total == 0) PB_CUDA(cudaMemsetAsync(c->d_leaf.p, 0, sizeof(LeafTri), st));
+        else launch_build_leaf_tris(st, total, c->d_order.as<int>(), c->d_tri.as<TriRec>(), c->d_leaf.as<LeafTri>());
+        c->launches += 1;
+        c->view.num_nodes = (int)dn.size();
+    }
+    // sensors
+    for (auto &s : c->sensors) configure_sensor(s, c->width, c->height);
+    // emitters (scene.cpp:183-196, area.cpp:10-17)
+    std::vector<EmitterRec> er(c->emitters.size());
+    if (!c->emitters.empty()) {
+        std::vector<float> w, cmf;
+        float acc = 0.f;
+        for (auto &e : c->emitters) {
+            const HostMesh &m = c->meshes[e.mesh];
+            e.sampling_weight = m.total_area * (e.radiance[0] * .2126f + e.radiance[1] * .7152f + e.radiance[2] * .0722f);
+            w.push_back(e.sampling_weight);
+            acc += e.sampling_weight;
+            cmf.push_back(acc);
+        }
+        c->emitter_sum = acc;
+        const float inv = 1.f / acc;
+        for (auto &e : c->emitters) e.sampling_weight *= inv;
+        c->d_emitter_pmf.upload(w, st);
+        c->d_emitter_cmf.upload(cmf, st);
+        for (size_t i = 0; i < er.size(); ++i) {
+            const HostEmitter &e = c->emitters[i];
+            const HostMesh &m = c->meshes[e.mesh];
+            EmitterRec &r = er[i];
+            std::memset(&r, 0, sizeof(r));
+            r.type = e.type; r.mesh = e.mesh; r.sampling_weight = e.sampling_weight;
+            r.radiance = f3(e.radiance[0], e.radiance[1], e.radiance[2]);
+            r.face_cmf = m.d_face_cmf.as<float>(); r.face_pmf = m.d_face_area.as<float>();
+            r.face_sum = m.face_sum; r.num_faces = m.nf; r.face_offset = m.face_offset;
+        }
+    }
+    c->d_emitters.upload(er, st);
+    // mesh + bsdf tables
+    std::vector<MeshRec> mr(c->meshes.size());
+    for (size_t i = 0; i < mr.size(); ++i) {
+        const HostMesh &m = c->meshes[i];
+        std::memset(&mr[i], 0, sizeof(MeshRec));
+        mr[i].bsdf = m.bsdf; mr[i].emitter = m.emitter; mr[i].inv_total_area = m.inv_total_area;
+        mr[i].face_offset = m.face_offset; mr[i].num_faces = m.nf; mr[i].flags = m.flags & 3;
+    }
+    c->d_meshes.upload(mr, st);
+    std::vector<BsdfRec> br(c->bsdfs.size());
+    for (size_t i = 0; i < br.size(); ++i) {
+        HostBsdf &b = c->bsdfs[i];
+        std::memset(&br[i], 0, sizeof(BsdfRec));
+        br[i].type = b.type;
+        for (int k = 0; k < TEX_COUNT; ++k) {
+            HostTexture &t = b.tex[k];
+            if (t.dirty) { t.d.upload(t.data, st); t.dirty = false; }
+            br[i].tex[k].data = t.d.as<float>(); br[i].tex[k].grad = nullptr;
+            br[i].tex[k].w = t.w; br[i].tex[k].h = t.h; br[i].tex[k].c = t.c;
+        }
+    }
+    c->d_bsdfs.upload(br, st);
+    PB_CUDA(cudaStreamSynchronize(st));
+    SceneView &V = c->view;
+    V.tri = c->d_tri.as<TriRec>(); V.leaf = c->d_leaf.as<LeafTri>(); V.nodes = c->d_nodes.as<BvhNode>();
+    V.meshes = c->d_meshes.as<MeshRec>(); V.bsdfs = c->d_bsdfs.as<BsdfRec>(); V.emitters = c->d_emitters.as<EmitterRec>();
+    V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
+    V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
+    V.emitter_env = -1;
+    // gradient layout
+    c->grad_segments.clear();
+    int64_t off = 0;
+    for (size_t i = 0; i < c->bsdfs.size(); ++i)
+        for (int k = 0; k < TEX_COUNT; ++k)
+            if (c->bsdfs[i].tex[k].requires_grad) {
+                const int64_t n = (int64_t)c->bsdfs[i].tex[k].data.size();
+                c->grad_segments.push_back({PB_PARAM_BSDF_TEXTURE, (int)i, k, off, n});
+                off += n;
+            }
+    for (size_t i = 0; i < c->meshes.size(); ++i)
+        if (c->meshes[i].requires_grad) {
+            const int64_t n = 3 * (int64_t)c->meshes[i].nv;
+            c->grad_segments.push_back({PB_PARAM_MESH_VERTICES, (int)i, 0, off, n});
+            off += n;
+        }
+    c->ready = true;
+    c->have_last_d = false;
+}
+
+struct Plan { int nbounce, nb, nl, draws; };
+static Plan make_plan(const pb_integrator &I) {
+    Plan p;
+    if (I.kind == PB_INTEG_DIRECT) {
+        PB_ASSERT_MSG(I.bsdf_samples >= 0 && I.light_samples >= 0 && I.bsdf_samples + I.light_samples > 0, "Invalid DirectIntegrator sample counts");
+        p.nbounce = 1; p.nb = I.bsdf_samples; p.nl = I.light_samples;
+    } else if (I.kind == PB_INTEG_PATH) {
+        PB_ASSERT_MSG(I.max_depth >= 1, "PathIntegrator needs max_depth >= 1");
+        p.nbounce = I.max_depth; p.nb = 1; p.nl = 1;
+    } else {
+        PB_ASSERT_MSG(I.kind == PB_INTEG_FIELD, "Unknown integrator kind");
+        p.nbounce = 0; p.nb = p.nl = 0;
+    }
+    p.draws = 2 + p.nbounce * (3 * p.nb + 2 * p.nl);
+    return p;
+}
+
+// interior term: integrator.cpp:64-95 over this shard's pixels, in batches
+static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float *d_image, bool ad) {
+    PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+    PB_ASSERT_MSG(sensor >= 0 && sensor < (int)c->sensors.size(), "Invalid sensor id!");
+    PB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t npix = (int64_t)c->width * c->height;
+    PB_CUDA(cudaMemsetAsync(d_image, 0, (size_t)npix * 3 * sizeof(float), st));
+    c->last_trace_ms = 0.f; c->last_rays = 0;
+    if (c->spp <= 0) { PB_CUDA(cudaStreamSynchronize(st)); return; }
+    const Plan plan = make_plan(I);
+    PB_ASSERT_MSG(I.kind == PB_INTEG_FIELD || !c->emitters.empty(), "No Emitter!");
+    const int64_t p0 = npix * c->rank / c->world, p1 = npix * (c->rank + 1) / c->world;
+    const int64_t lane_begin = p0 * c->spp, lane_end = p1 * c->spp;
+    const int R = std::max(1, plan.nb + plan.nl);
+    const int64_t B = std::min<int64_t>(c->batch, std::max<int64_t>(1024, lane_end - lane_begin));
+    c->d_hit0.reserve((size_t)B * sizeof(HitRec));
+    for (int k = 0; k < 2; ++k) { c->d_rays[k].reserve((size_t)B * R * sizeof(RayRec)); c->d_hits[k].reserve((size_t)B * R * sizeof(HitRec)); }
+    c->d_state.reserve((size_t)B * sizeof(PathState));
+    RenderParams P;
+    P.S = c->view; P.cam = c->sensors[sensor].rec;
+    P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
+    const uint64_t base = c->sampler_offset[0];
+    P.jump0 = make_jump(base);
+    size_t nev = 0;
+    for (int64_t start = lane_begin; start < lane_end; start += B) {
+        P.lane0 = start; P.n = (int)std::min<int64_t>(B, lane_end - start);
+        cudaEvent_t e0 = get_event(c, nev++), e1 = get_event(c, nev++);
+        PB_CUDA(cudaEventRecord(e0, st));
+        launch_primary(st, P, c->d_hit0.as<HitRec>());
+        PB_CUDA(cudaEventRecord(e1, st));
+        c->launches++; c->last_rays += P.n;
+        if (I.kind == PB_INTEG_FIELD) {
+            launch_field(st, P, I.field, c->d_hit0.as<HitRec>(), d_image);
+            c->launches++;
+            continue;
+        }
+        const HitRec *hit_cur = c->d_hit0.as<HitRec>();
+        const RayRec *prev_rays = nullptr;
+        for (int k = 0; k < plan.nbounce; ++k) {
+            BounceParams Bp;
+            Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
+            Bp.hide_emitters = I.hide_emitters; Bp.ad = ad ? 1 : 0;
+            Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
+            RayRec *rays = c->d_rays[k & 1].as<RayRec>();
+            HitRec *hits = c->d_hits[k & 1].as<HitRec>();
+            launch_shade(st, P, Bp, hit_cur, prev_rays, rays);
+            cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
+            PB_CUDA(cudaEventRecord(t0, st));
+            launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), rays, hits, nullptr);
+            PB_CUDA(cudaEventRecord(t1, st));
+            launch_resolve(st, P, Bp, hit_cur, prev_rays, hits, c->d_state.as<PathState>(), d_image);
+            c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl);
+            hit_cur = hits; prev_rays = rays;
+        }
+    }
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i + 1 < nev; i += 2) {
+        float ms = 0.f;
+        PB_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
+        c->last_trace_ms += ms;
+    }
+    c->sampler_offset[0] = base + plan.draws;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+static thread_local std::string g_create_error;
+
+template <class F> static int guard(pb_ctx *c, F &&f) {
+    try { f(); return 0; }
+    catch (const std::exception &e) { if (c) c->error = e.what(); else g_create_error = e.what(); return 1; }
+}
+template <class F> static int guard_id(pb_ctx *c, F &&f) {   // returns id >= 0 or -1
+    try { return f(); }
+    catch (const std::exception &e) { if (c) c->error = e.what(); return -1; }
+}
+
+extern "C" {
+
+int pb_version(void) { return 100; }
+
+int pb_ctx_create(int device, pb_ctx **out) {
+    *out = nullptr;
+    return guard(nullptr, [&] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw Error(std::string("psdr_b200 needs a CUDA device (no CPU fallback): ") + cudaGetErrorString(e));
+        PB_ASSERT_MSG(device >= 0 && device < count, "Invalid CUDA device index");
+        PB_CUDA(cudaSetDevice(device));
+        pb_ctx *c = new pb_ctx();
+        c->device = device;
+        PB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        *out = c;
+    });
+}
+int pb_ctx_destroy(pb_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+const char *pb_last_error(pb_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+int pb_ctx_set_batch(pb_ctx *c, int64_t lanes) {
+    return guard(c, [&] {
+        if (lanes <= 0) lanes = 1 << 20;
+        PB_ASSERT_MSG(lanes % 1024 == 0, "batch must be a multiple of 1024 lanes");
+        c->batch = lanes;
+    });
+}
+int pb_ctx_set_shard(pb_ctx *c, int rank, int world) {
+    return guard(c, [&] { PB_ASSERT_MSG(world >= 1 && rank >= 0 && rank < world, "Invalid shard"); c->rank = rank; c->world = world; });
+}
+
+int pb_scene_set_options(pb_ctx *c, int w, int h, int spp, int sppe, int sppse) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(w >= 0 && h >= 0 && spp >= 0 && sppe >= 0 && sppse >= 0, "Invalid render options");
+        c->width = w; c->height = h; c->spp = spp; c->sppe = sppe; c->sppse = sppse;
+        c->ready = false;
+    });
+}
+int pb_scene_add_sensor(pb_ctx *c, float fov_x, float near_clip, float far_clip, const float *to_world) {
+    return guard_id(c, [&] {
+        HostSensor s;
+        s.fov_x = fov_x; s.near_clip = near_clip; s.far_clip = far_clip; s.to_world = from_ptr(to_world);
+        c->sensors.push_back(s);
+        c->ready = false;
+        return (int)c->sensors.size() - 1;
+    });
+}
+int pb_scene_set_sensor_transform(pb_ctx *c, int sensor, const float *to_world) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(sensor >= 0 && sensor < (int)c->sensors.size(), "Invalid sensor id!");
+        c->sensors[sensor].to_world = from_ptr(to_world);
+        c->ready = false;
+    });
+}
+int pb_scene_add_bsdf(pb_ctx *c, int type) {
+    return guard_id(c, [&] {
+        PB_ASSERT_MSG(type == PB_BSDF_DIFFUSE || type == PB_BSDF_ROUGHCONDUCTOR, "Unsupported BSDF");
+        c->bsdfs.emplace_back();
+        HostBsdf &b = c->bsdfs.back();
+        b.type = type;
+        // defaults: diffuse.h:11-14, roughconductor.h:11-12
+        const float def3[TEX_COUNT] = {.5f, 0.f, 0.f, 0.f, 1.f, 1.f};
+        for (int k = 0; k < TEX_COUNT; ++k) {
+            const bool one = (k == TEX_ALPHA_U || k == TEX_ALPHA_V);
+            b.tex[k].c = one ? 1 : 3;
+            b.tex[k].data.assign(one ? 1 : 3, one ? .1f : def3[k]);
+        }
+        c->ready = false;
+        return (int)c->bsdfs.size() - 1;
+    });
+}
+int pb_scene_set_bsdf_texture(pb_ctx *c, int bsdf, int slot, const float *data, int w, int h) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(bsdf >= 0 && bsdf < (int)c->bsdfs.size(), "Invalid BSDF id");
+        PB_ASSERT_MSG(slot >= 0 && slot < TEX_COUNT && w >= 1 && h >= 1 && data, "Invalid texture");
+        HostTexture &t = c->bsdfs[bsdf].tex[slot];
+        t.w = w; t.h = h;
+        t.data.assign(data, data + (size_t)w * h * t.c);
+        t.dirty = true;
+        c->ready = false;
+    });
+}
+int pb_scene_add_mesh(pb_ctx *c, int nv, int nf, const float *verts, const int *faces, int nuv, const float *uvs, const int *uv_faces, int flags,
+                      int bsdf, const float *to_world) {
+    return guard_id(c, [&] {
+        PB_ASSERT_MSG(nv >= 0 && nf >= 0 && (nv == 0 || verts) && (nf == 0 || faces), "Invalid mesh buffers");
+        PB_ASSERT_MSG(bsdf >= -1 && bsdf < (int)c->bsdfs.size(), "Unknown BSDF id");
+        c->meshes.emplace_back();
+        HostMesh &m = c->meshes.back();
+        try {
+            m.nv = nv; m.nf = nf;
+            m.verts.assign(verts, verts + 3 * (size_t)nv);
+            m.faces.assign(faces, faces + 3 * (size_t)nf);
+            for (int i = 0; i < 3 * nf; ++i) PB_ASSERT_MSG(m.faces[i] >= 0 && m.faces[i] < nv, "Face index out of range");
+            const bool has_uv = nuv > 0 && uvs && uv_faces;
+            if (has_uv) {
+                m.uvs.assign(uvs, uvs + 2 * (size_t)nuv);
+                m.uv_faces.assign(uv_faces, uv_faces + 3 * (size_t)nf);
+                for (int i = 0; i < 3 * nf; ++i) PB_ASSERT_MSG(m.uv_faces[i] >= 0 && m.uv_faces[i] < nuv, "UV index out of range");
+            }
+            // device flags: bit0 face normals, bit1 has uv; bit2 keeps enable_edges on the host side
+            m.flags = ((flags & PB_MESH_FACE_NORMALS) ? 1 : 0) | (has_uv ? 2 : 0) | ((flags & PB_MESH_ENABLE_EDGES) ? 4 : 0);
+            m.bsdf = bsdf;
+            m.raw = from_ptr(to_world);
+            build_edges(m);
+            build_csr(m);
+        } catch (...) { c->meshes.pop_back(); throw; }
+        c->ready = false;
+        return (int)c->meshes.size() - 1;
+    });
+}
+int pb_scene_set_mesh_vertices(pb_ctx *c, int mesh, const float *verts) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size() && verts, "Invalid mesh id");
+        HostMesh &m = c->meshes[mesh];
+        m.verts.assign(verts, verts + 3 * (size_t)m.nv);
+        m.verts_dirty = true;
+        c->ready = false;
+    });
+}
+int pb_scene_set_mesh_transform(pb_ctx *c, int mesh, const float *mat, int left) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size(), "Invalid mesh id");
+        (left ? c->meshes[mesh].left : c->meshes[mesh].right) = from_ptr(mat);
+        c->ready = false;
+    });
+}
+int pb_scene_add_area_emitter(pb_ctx *c, int mesh, const float *radiance) {
+    return guard_id(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size() && radiance, "Invalid mesh id");
+        HostEmitter e;
+        e.type = EMITTER_AREA; e.mesh = mesh;
+        for (int k = 0; k < 3; ++k) e.radiance[k] = radiance[k];
+        c->emitters.push_back(e);
+        c->meshes[mesh].emitter = (int)c->emitters.size() - 1;
+        c->ready = false;
+        return (int)c->emitters.size() - 1;
+    });
+}
+int pb_scene_configure(pb_ctx *c) { return guard(c, [&] { configure(c); }); }
+int pb_scene_reseed(pb_ctx *c) {
+    for (int k = 0; k < 3; ++k) { c->sampler_count[k] = 0; c->sampler_offset[k] = 0; }
+    c->ready = false;
+    return 0;
+}
+int pb_scene_num_triangles(pb_ctx *c) { return c->num_tri; }
+int pb_scene_get_triangle_info(pb_ctx *c, float *out) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+        for (int t = 0; t < c->num_tri; ++t) {
+            const float *q = &c->h_tri[(size_t)t * 32];
+            float *o = out + 22 * (size_t)t;
+            for (int a = 0; a < 3; ++a) {
+                o[a] = q[a]; o[3 + a] = q[4 + a]; o[6 + a] = q[8 + a];              // p0 e1 e2
+                o[9 + a] = q[12 + a]; o[12 + a] = q[16 + a]; o[15 + a] = q[20 + a];  // n0 n1 n2
+                o[18 + a] = q[24 + a];                                              // face normal
+            }
+            o[21] = q[3];
+        }
+    });
+}
+int pb_scene_mesh_num_edges(pb_ctx *c, int mesh) {
+    if (mesh < 0 || mesh >= (int)c->meshes.size()) return -1;
+    return (int)c->meshes[mesh].edges.size() / 5;
+}
+int pb_scene_mesh_get_edges(pb_ctx *c, int mesh, int *out) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size(), "Invalid mesh id");
+        std::copy(c->meshes[mesh].edges.begin(), c->meshes[mesh].edges.end(), out);
+    });
+}
+
+int pb_trace(pb_ctx *c, int64_t n, const float *d_rays, void *d_hits, float *d_t) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+        PB_CUDA(cudaSetDevice(c->device));
+        cudaEvent_t e0 = get_event(c, 0), e1 = get_event(c, 1);
+        PB_CUDA(cudaEventRecord(e0, c->stream));
+        launch_trace(c->stream, c->view, n, reinterpret_cast<const RayRec *>(d_rays), reinterpret_cast<HitRec *>(d_hits), d_t);
+        PB_CUDA(cudaEventRecord(e1, c->stream));
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaStreamSynchronize(c->stream));
+        PB_CUDA(cudaEventElapsedTime(&c->last_trace_ms, e0, e1));
+        c->launches++; c->last_rays = n;
+    });
+}
+int pb_render_c(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
+    return guard(c, [&] { PB_ASSERT_MSG(I && d_image, "Null argument"); render_interior(c, *I, sensor, d_image, false); });
+}
+int pb_render_c_host(pb_ctx *c, const pb_integrator *I, int sensor, float *h_image) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(I && h_image, "Null argument");
+        const size_t bytes = (size_t)c->width * c->height * 3 * sizeof(float);
+        DevBuf img;
+        img.reserve(bytes);
+        render_interior(c, *I, sensor, img.as<float>(), false);
+        PB_CUDA(cudaMemcpy(h_image, img.p, bytes, cudaMemcpyDeviceToHost));
+    });
+}
+int pb_render_d(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(I && d_image, "Null argument");
+        const uint64_t off = c->sampler_offset[0];
+        render_interior(c, *I, sensor, d_image, true);
+        c->last_d_offset = off; c->have_last_d = true;
+    });
+}
+
+int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
+    return guard(c, [&] {
+        if (kind == PB_PARAM_BSDF_TEXTURE) {
+            PB_ASSERT_MSG(id >= 0 && id < (int)c->bsdfs.size() && slot >= 0 && slot < TEX_COUNT, "Invalid BSDF texture");
+            c->bsdfs[id].tex[slot].requires_grad = enable != 0;
+        } else if (kind == PB_PARAM_MESH_VERTICES) {
+            PB_ASSERT_MSG(id >= 0 && id < (int)c->meshes.size(), "Invalid mesh id");
+            c->meshes[id].requires_grad = enable != 0;
+        } else throw Error("Unknown parameter kind");
+        c->ready = false;
+    });
+}
+int pb_grad_num_segments(pb_ctx *c) { return (int)c->grad_segments.size(); }
+int pb_grad_segment(pb_ctx *c, int index, int *kind, int *id, int *slot, int64_t *offset, int64_t *count) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(index >= 0 && index < (int)c->grad_segments.size(), "Invalid segment");
+        const GradSegment &g = c->grad_segments[index];
+        *kind = g.kind; *id = g.id; *slot = g.slot; *offset = g.offset; *count = g.count;
+    });
+}
+int64_t pb_grad_size(pb_ctx *c) { return c->grad_segments.empty() ? 0 : c->grad_segments.back().offset + c->grad_segments.back().count; }
+int pb_render_d_vjp(pb_ctx *c, const pb_integrator *, int, const float *, float *) {
+    return guard(c, [&] { throw Error("pb_render_d_vjp: not implemented yet"); });
+}
+
+int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }
+float pb_stats_last_trace_ms(pb_ctx *c) { return c->last_trace_ms; }
+int64_t pb_stats_last_rays(pb_ctx *c) { return c->last_rays; }
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// psdr-b200: mesh preprocessing kernels — the device half of Scene::configure.
+//
+// Restates Mesh::configure / process_mesh (src/shape/mesh.cpp:19-51, 215-274) and the global triangle table build
+// (src/scene/scene.cpp:205-217). The reference scatter-adds face normals into vertices with atomics; here every vertex
+// gathers its incident faces through a CSR list laid out in the same (corner, face) order the oracle sums in, so the
+// result is deterministic and bit-identical to the CPU restatement, and the backward pass is a gather as well.
+#include "pb_kernels.h"
+
+namespace pb {
+
+__global__ void k_transform_vertices(int nv, const float *__restrict__ vraw, Mat4 to_world, float *__restrict__ vworld) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const float3 p = transform_pos(to_world, f3(vraw[3 * v], vraw[3 * v + 1], vraw[3 * v + 2]));
+    vworld[3 * v] = p.x; vworld[3 * v + 1] = p.y; vworld[3 * v + 2] = p.z;
+}
+
+// per face: unnormalised normal (cross) and its length -> fcross[4*f] = (cx, cy, cz, |c|)
+__global__ void k_face_cross(int nf, const float *__restrict__ vworld, const int *__restrict__ faces, float4 *__restrict__ fcross) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float3 p0 = f3(vworld[3 * i0], vworld[3 * i0 + 1], vworld[3 * i0 + 2]);
+    const float3 e1 = sub3_rn(f3(vworld[3 * i1], vworld[3 * i1 + 1], vworld[3 * i1 + 2]), p0);
+    const float3 e2 = sub3_rn(f3(vworld[3 * i2], vworld[3 * i2 + 1], vworld[3 * i2 + 2]), p0);
+    const float3 c = cross(e1, e2);
+    fcross[f] = make_float4(c.x, c.y, c.z, norm(c));
+}
+
+// per vertex: normalize(sum(cross) / sum(|cross|)) over incident faces in CSR order (mesh.cpp:32-38)
+__global__ void k_vertex_normals(int nv, const int *__restrict__ csr_off, const int *__restrict__ csr_face, const float4 *__restrict__ fcross,
+                                 float *__restrict__ vnormal) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    float3 acc = f3(0.f);
+    float w = 0.f;
+    for (int k = csr_off[v]; k < csr_off[v + 1]; ++k) {
+        const float4 c = fcross[csr_face[k]];
+        acc = f3(add_rn(acc.x, c.x), add_rn(acc.y, c.y), add_rn(acc.z, c.z));
+        w = add_rn(w, c.w);
+    }
+    const float3 n = normalize(f3(div_rn(acc.x, w), div_rn(acc.y, w), div_rn(acc.z, w)));
+    vnormal[3 * v] = n.x; vnormal[3 * v + 1] = n.y; vnormal[3 * v + 2] = n.z;
+}
+
+// assemble the 128-byte triangle records at their global offset + the face-area pmf of the mesh
+__global__ void k_assemble_triangles(int nf, int face_offset, int mesh_id, int flags, const float *__restrict__ vworld, const int *__restrict__ faces,
+                                     const float4 *__restrict__ fcross, const float *__restrict__ vnormal, const float *__restrict__ uvs,
+                                     const int *__restrict__ uv_faces, TriRec *__restrict__ tri, float *__restrict__ face_area) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float3 p0 = f3(vworld[3 * i0], vworld[3 * i0 + 1], vworld[3 * i0 + 2]);
+    const float3 e1 = sub3_rn(f3(vworld[3 * i1], vworld[3 * i1 + 1], vworld[3 * i1 + 2]), p0);
+    const float3 e2 = sub3_rn(f3(vworld[3 * i2], vworld[3 * i2 + 1], vworld[3 * i2 + 2]), p0);
+    const float4 c = fcross[f];
+    const float3 fn = f3(div_rn(c.x, c.w), div_rn(c.y, c.w), div_rn(c.z, c.w));
+    const float area = mul_rn(c.w, 0.5f);
+    float2 uv0 = make_float2(0.f, 0.f), uv1 = uv0, uv2 = uv0;
+    if (flags & 2) {
+        const int j0 = uv_faces[3 * f], j1 = uv_faces[3 * f + 1], j2 = uv_faces[3 * f + 2];
+        uv0 = make_float2(uvs[2 * j0], uvs[2 * j0 + 1]); uv1 = make_float2(uvs[2 * j1], uvs[2 * j1 + 1]); uv2 = make_float2(uvs[2 * j2], uvs[2 * j2 + 1]);
+    }
+    float4 *q = reinterpret_cast<float4 *>(tri + face_offset + f);
+    q[0] = make_float4(p0.x, p0.y, p0.z, area);
+    q[1] = make_float4(e1.x, e1.y, e1.z, __int_as_float(mesh_id));
+    q[2] = make_float4(e2.x, e2.y, e2.z, __int_as_float(flags));
+    q[3] = make_float4(vnormal[3 * i0], vnormal[3 * i0 + 1], vnormal[3 * i0 + 2], uv0.x);
+    q[4] = make_float4(vnormal[3 * i1], vnormal[3 * i1 + 1], vnormal[3 * i1 + 2], uv0.y);
+    q[5] = make_float4(vnormal[3 * i2], vnormal[3 * i2 + 1], vnormal[3 * i2 + 2], uv1.x);
+    q[6] = make_float4(fn.x, fn.y, fn.z, uv1.y);
+    q[7] = make_float4(uv2.x, uv2.y, 0.f, 0.f);
+    face_area[f] = area;
+}
+
+// leaf-ordered triangles for traversal: gather p0/e1/e2 by the BVH's triangle order
+__global__ void k_build_leaf_tris(int n, const int *__restrict__ order, const TriRec *__restrict__ tri, LeafTri *__restrict__ leaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = order[i];
+    const float4 *q = reinterpret_cast<const float4 *>(tri + t);
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    LeafTri l;
+    l.a = make_float4(q0.x, q0.y, q0.z, __int_as_float(t));
+    l.b = make_float4(q1.x, q1.y, q1.z, q1.w);   // w = mesh id
+    l.c = make_float4(q2.x, q2.y, q2.z, 0.f);
+    leaf[i] = l;
+}
+
+static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
+                            const int *faces, const int *csr_off, const int *csr_face, const float *uvs, const int *uv_faces, float *vworld,
+                            float4 *fcross, float *vnormal, TriRec *tri, float *face_area) {
+    if (nv > 0) k_transform_vertices<<<nblk(nv, 256), 256, 0, st>>>(nv, vraw, to_world, vworld);
+    if (nf > 0) k_face_cross<<<nblk(nf, 256), 256, 0, st>>>(nf, vworld, faces, fcross);
+    if (nv > 0) k_vertex_normals<<<nblk(nv, 256), 256, 0, st>>>(nv, csr_off, csr_face, fcross, vnormal);
+    if (nf > 0) k_assemble_triangles<<<nblk(nf, 256), 256, 0, st>>>(nf, face_offset, mesh_id, flags, vworld, faces, fcross, vnormal, uvs, uv_faces, tri, face_area);
+}
+
+void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf) {
+    if (n > 0) k_build_leaf_tris<<<nblk(n, 256), 256, 0, st>>>(n, order, tri, leaf);
+}
+
+}  // namespace pb

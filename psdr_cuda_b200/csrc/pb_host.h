@@ -1,0 +1,121 @@
+// psdr-b200: host-side context behind the C ABI (scene description, device tables, wavefront buffers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pb_bvh.h"
+#include "pb_kernels.h"
+
+namespace pb {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define PB_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) throw pb::Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); \
+    } while (0)
+#define PB_ASSERT_MSG(cond, msg) do { if (!(cond)) throw pb::Error(msg); } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    void reserve(size_t n) {   // grow-only
+        if (n <= bytes) return;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        PB_CUDA(cudaMalloc(&p, n ? n : 16));
+        bytes = n;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    template <class T> void upload(const std::vector<T> &v, cudaStream_t st) {
+        reserve(v.size() * sizeof(T));
+        if (!v.empty()) PB_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
+struct Mat4h {   // row-major
+    float m[16];
+    static Mat4h identity() { Mat4h r; for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.f : 0.f; return r; }
+};
+Mat4h matmul(const Mat4h &a, const Mat4h &b);
+Mat4h inverse(const Mat4h &a);
+
+struct HostTexture {
+    int w = 1, h = 1, c = 3;
+    std::vector<float> data;
+    DevBuf d;
+    bool dirty = true;
+    bool requires_grad = false;
+};
+struct HostBsdf {
+    int type = 0;
+    HostTexture tex[TEX_COUNT];
+};
+struct HostMesh {
+    int nv = 0, nf = 0, flags = 0, bsdf = -1, emitter = -1;
+    std::vector<float> verts, uvs;
+    std::vector<int> faces, uv_faces, edges, csr_off, csr_face;
+    Mat4h raw = Mat4h::identity(), left = Mat4h::identity(), right = Mat4h::identity();
+    bool verts_dirty = true, topo_dirty = true, requires_grad = false;
+    DevBuf d_vraw, d_faces, d_uvs, d_uv_faces, d_csr_off, d_csr_face, d_vworld, d_fcross, d_vnormal, d_face_area, d_face_cmf;
+    int face_offset = 0;
+    float total_area = 0.f, inv_total_area = 0.f, face_sum = 0.f;
+    Mat4h to_world = Mat4h::identity();
+};
+struct HostEmitter {
+    int type = 0, mesh = -1;
+    float radiance[3] = {0, 0, 0};
+    float sampling_weight = 0.f;
+};
+struct HostSensor {
+    float fov_x = 45.f, near_clip = 0.1f, far_clip = 1e4f;
+    Mat4h to_world = Mat4h::identity();
+    SensorRec rec;
+};
+struct GradSegment { int kind, id, slot; int64_t offset, count; };
+
+}  // namespace pb
+
+struct pb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    // description
+    int width = 0, height = 0, spp = 0, sppe = 0, sppse = 0;
+    std::vector<pb::HostSensor> sensors;
+    std::vector<pb::HostBsdf> bsdfs;
+    std::vector<pb::HostMesh> meshes;
+    std::vector<pb::HostEmitter> emitters;
+    // sharding / tiling
+    int rank = 0, world = 1;
+    int64_t batch = 1 << 20;
+    // samplers (scene.cpp:65-79): lane count the streams were seeded for and draws consumed so far
+    int64_t sampler_count[3] = {0, 0, 0};
+    uint64_t sampler_offset[3] = {0, 0, 0};
+    // configured device tables
+    bool ready = false;
+    int num_tri = 0;
+    pb::DevBuf d_tri, d_leaf, d_nodes, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
+    std::vector<float> h_tri;   // host copy of the triangle table (BVH build, inspection)
+    float emitter_sum = 0.f;
+    pb::SceneView view;
+    // wavefront buffers
+    pb::DevBuf d_hit0, d_rays[2], d_hits[2], d_state;
+    // replay info of the last renderD
+    uint64_t last_d_offset = 0;
+    bool have_last_d = false;
+    std::vector<pb::GradSegment> grad_segments;
+    // stats
+    int64_t launches = 0, last_rays = 0;
+    float last_trace_ms = 0.f;
+    std::vector<cudaEvent_t> ev_pool;
+};

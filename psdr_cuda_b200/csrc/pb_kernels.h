@@ -1,0 +1,46 @@
+// psdr-b200: host-callable launchers of the CUDA kernels (internal to the shared library; the public surface is
+// include/psdr_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pb_scene.cuh"
+
+namespace pb {
+
+// One scattering event of the interior integral. Direct(b,l) is a single event with (nb,nl) = (b,l);
+// the path integrator runs `max_depth` events with (1,1) and continues along BSDF ray 0.
+struct BounceParams {
+    int nb, nl;             // BSDF-sampled / emitter-sampled connections at this event (direct.cpp:67,119)
+    int depth;              // event index (0 = first hit of the camera ray)
+    int last;               // 1: this event writes the film
+    int carry;              // 1: path mode, keep throughput/radiance state between events
+    int hide_emitters;      // direct.h m_hide_emitters
+    int ad;                 // 1: the reference's AD formulation of the primal (direct.cpp:83-95), 0: renderC's
+    RngJump jump;           // stream position of this event's first draw
+};
+
+struct RenderParams {
+    SceneView S;
+    SensorRec cam;
+    int width, height, spp;
+    float inv_spp;
+    long long lane0;        // global lane id of the first lane of this batch
+    int n;                  // lanes in this batch
+    RngJump jump0;          // stream position of the pixel jitter
+};
+
+struct __align__(16) PathState { float4 thr, rad; };
+
+void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
+                            const int *faces, const int *csr_off, const int *csr_face, const float *uvs, const int *uv_faces, float *vworld,
+                            float4 *fcross, float *vnormal, TriRec *tri, float *face_area);
+void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
+
+void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
+void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
+void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, RayRec *rays_out);
+void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays,
+                    const HitRec *hits, PathState *state, float *film);
+void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film);
+
+}  // namespace pb

@@ -1,0 +1,250 @@
+// psdr-b200: wavefront kernels of the interior integral (primal): ray generation + primary trace, per-event shade
+// (sample BSDF / emitter, emit rays), generic trace, per-event resolve (MIS-weighted contributions, throughput update,
+// film accumulation).
+//
+// Restates Integrator::__render (src/integrator/integrator.cpp:64-95) and DirectIntegrator::__Li
+// (src/integrator/direct.cpp:47-163) as a fixed pipeline over RayRec/HitRec wavefront buffers. The sampler is
+// stateless: every kernel re-derives the lane's PCG32 stream from the global lane id and jumps to the position the
+// reference's lock-step wavefront would be at, so no RNG state is stored and a render can be replayed.
+#include "pb_kernels.h"
+#include "pb_shade.cuh"
+#include "pb_trace.cuh"
+
+namespace pb {
+
+__global__ void __launch_bounds__(128) k_trace(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
+                                               const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = ldg4(rp), b = ldg4(rp + 1);
+    const Hit h = trace_closest(nodes, leaf, f3(a), f3(b), a.w);
+    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    if (t_out) t_out[i] = h.t;
+}
+
+PB_D void lane_pixel_sample(const RenderParams &P, long long lane, float2 jitter, int &pix, float &sx, float &sy) {
+    pix = (int)(lane / P.spp);
+    const int x = pix % P.width, y = pix / P.width;
+    sx = div_rn(add_rn((float)x, jitter.x), (float)P.width);
+    sy = div_rn(add_rn((float)y, jitter.y), (float)P.height);
+}
+
+// integrator.cpp:76-85 + the first ray launch of direct.cpp:48
+__global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restrict__ hit0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const long long lane = P.lane0 + i;
+    Rng rng((uint64_t)lane, P.jump0);
+    const float2 j = rng.next_2d();
+    int pix; float sx, sy;
+    lane_pixel_sample(P, lane, j, pix, sx, sy);
+    float3 o, d;
+    sample_primary_ray(P.cam, sx, sy, o, d);
+    const Hit h = trace_closest(P.S.nodes, P.S.leaf, o, d, INFINITY);
+    reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+}
+
+struct Vertex { Its its; const BsdfRec *bsdf; bool active; };
+
+PB_D HitRec load_hit(const HitRec *p) {
+    const float4 h = ldg4(reinterpret_cast<const float4 *>(p));
+    HitRec r;
+    r.tri = __float_as_int(h.x); r.shape = __float_as_int(h.y); r.u = h.z; r.v = h.w;
+    return r;
+}
+PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax) {
+    float4 *q = reinterpret_cast<float4 *>(p);
+    q[0] = make_float4(o.x, o.y, o.z, tmax);
+    q[1] = make_float4(d.x, d.y, d.z, 0.f);
+}
+
+PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const HitRec *hit_cur, const RayRec *prev_rays) {
+    float3 origin;
+    if (B.depth == 0) origin = transform_pos(P.cam.to_world, f3(0.f));
+    else origin = f3(ldg4(reinterpret_cast<const float4 *>(prev_rays + i)));
+    Vertex v;
+    v.its = reconstruct_its(P.S, load_hit(hit_cur + i), origin);
+    v.active = v.its.valid;
+    v.bsdf = its_bsdf(P.S, v.its);
+    if (P.S.emitter_env >= 0) v.active = v.active && v.bsdf != nullptr;   // direct.cpp:54-57
+    return v;
+}
+
+// sample the connections of one scattering event and emit their rays (direct.cpp:69-76, 120-129)
+__global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
+                                               RayRec *__restrict__ rays_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
+    Rng rng((uint64_t)(P.lane0 + i), B.jump);
+    for (int j = 0; j < B.nb; ++j) {
+        const float3 s3 = rng.next_3d();
+        const BsdfSample bs = bsdf_sample(v.bsdf, v.its, s3, v.active);
+        const bool a1 = v.active && bs.valid;
+        store_ray(rays_out + (size_t)j * P.n + i, v.its.p, v.its.sh.to_world(bs.wo), a1 ? INFINITY : -1.f);
+    }
+    for (int j = 0; j < B.nl; ++j) {
+        const float2 s2 = rng.next_2d();
+        const PositionSample ps = sample_emitter_position(P.S, s2, v.active);
+        const bool a1 = v.active && ps.valid;
+        float3 wo = ps.p - v.its.p;
+        const float dist = safe_sqrt(squared_norm(wo));
+        wo = wo / dist;
+        store_ray(rays_out + (size_t)(B.nb + j) * P.n + i, v.its.p, wo, a1 ? INFINITY : -1.f);
+    }
+}
+
+// warp-segmented sum over lanes that share a pixel (spp consecutive lanes per pixel, integrator.cpp:76-77), then one
+// atomicAdd per segment instead of the reference's per-lane scatter_add (integrator.cpp:88)
+PB_D void film_accumulate(float *film, int pix, float3 val) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float x = __shfl_down_sync(full, val.x, o), y = __shfl_down_sync(full, val.y, o), z = __shfl_down_sync(full, val.z, o);
+        const int p2 = __shfl_down_sync(full, pix, o);
+        if (lane + o < 32 && p2 == pix) { val.x += x; val.y += y; val.z += z; }
+    }
+    const int prev = __shfl_up_sync(full, pix, 1);
+    if (pix >= 0 && (lane == 0 || prev != pix)) {
+        atomicAdd(film + 3 * (size_t)pix, val.x);
+        atomicAdd(film + 3 * (size_t)pix + 1, val.y);
+        atomicAdd(film + 3 * (size_t)pix + 2, val.z);
+    }
+}
+
+// direct.cpp:77-113 (BSDF-sampled connections) and 130-158 (emitter-sampled connections) for one scattering event
+__global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
+                                                 const HitRec *__restrict__ hits, PathState *__restrict__ state, float *__restrict__ film) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i < P.n;
+    int pix = -1;
+    float3 out = f3(0.f);
+    if (in_range) {
+        const long long lane = P.lane0 + i;
+        pix = (int)(lane / P.spp);
+        const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
+        const Its &its = v.its;
+        Rng rng((uint64_t)lane, B.jump);
+        float3 L = f3(0.f), w_cont = f3(0.f);
+        const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
+        for (int j = 0; j < B.nb; ++j) {
+            const float3 s3 = rng.next_3d();
+            const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
+            bool a1 = v.active && bs.valid;
+            const HitRec h1 = load_hit(hits + (size_t)j * P.n + i);
+            const Its its1 = reconstruct_its(P.S, h1, its.p);
+            a1 = a1 && its1.valid;
+            const bool cont = a1;
+            a1 = a1 && is_emitter(P.S, its1.shape);
+            if (a1 || (B.carry && j == 0 && cont)) {
+                float3 bsdf_val;
+                float pdf0;
+                if (B.ad) {   // direct.cpp:83-95
+                    float3 wo = its1.p - its.p;
+                    wo = wo / its1.t;
+                    bsdf_val = bsdf_eval(v.bsdf, its, its.sh.to_local(wo), true);
+                    const float G = fabsf(dot(its1.n, -wo)) / sqr(its1.t);
+                    pdf0 = bs.pdf * G;
+                    bsdf_val = bsdf_val * (G / pdf0);
+                } else {      // direct.cpp:96-106
+                    const float3 d1 = its.sh.to_world(bs.wo);
+                    bsdf_val = bsdf_eval(v.bsdf, its, bs.wo, true);
+                    const float G = fabsf(dot(its1.n, -d1)) / sqr(its1.t);
+                    pdf0 = bs.pdf * G;
+                    bsdf_val = bsdf_val / bs.pdf;
+                }
+                if (a1) {
+                    float weight = inv_nb;
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
+                    L += emitter_Le(P.S, its1, true) * bsdf_val * weight;
+                }
+                if (B.carry && j == 0 && cont) w_cont = bsdf_val;
+            }
+        }
+        for (int j = 0; j < B.nl; ++j) {
+            const float2 s2 = rng.next_2d();
+            const PositionSample ps = sample_emitter_position(P.S, s2, v.active);
+            bool a1 = v.active && ps.valid;
+            float3 wo = ps.p - its.p;
+            const float dist_sqr = squared_norm(wo);
+            const float dist = safe_sqrt(dist_sqr);
+            wo = wo / dist;
+            const HitRec h1 = load_hit(hits + (size_t)(B.nb + j) * P.n + i);
+            const Its its1 = reconstruct_its(P.S, h1, its.p);
+            a1 = a1 && its1.valid && (its1.t > dist - kShadowEpsilon) && is_emitter(P.S, its1.shape);
+            if (a1) {
+                const float G = fabsf(dot(its1.n, -wo)) / dist_sqr;
+                const float3 wo_local = its.sh.to_local(wo);
+                float3 bsdf_val = bsdf_eval(v.bsdf, its, wo_local, true);
+                const float pdf1 = bsdf_pdf(v.bsdf, its, wo_local, true) * G;
+                bsdf_val = bsdf_val * (G / ps.pdf);
+                float weight = inv_nl;
+                if (B.nb > 0) weight *= mis_weight(ps.pdf, pdf1);
+                L += emitter_Le(P.S, its1, true) * bsdf_val * weight;
+            }
+        }
+        float3 thr = f3(1.f), rad;
+        if (B.depth == 0) {
+            rad = B.hide_emitters ? f3(0.f) : emitter_Le(P.S, its, its.valid);   // direct.cpp:51
+        } else {
+            const float4 *sp = reinterpret_cast<const float4 *>(state + i);
+            thr = f3(sp[0]); rad = f3(sp[1]);
+        }
+        rad += thr * L;
+        if (B.last) {
+            out = zero_nonfinite(rad) * P.inv_spp;   // integrator.cpp:87-91
+        } else {
+            float4 *sp = reinterpret_cast<float4 *>(state + i);
+            const float3 t2 = thr * w_cont;
+            sp[0] = make_float4(t2.x, t2.y, t2.z, 0.f);
+            sp[1] = make_float4(rad.x, rad.y, rad.z, 0.f);
+        }
+    }
+    if (B.last) film_accumulate(film, pix, out);
+}
+
+// field.cpp:34-54
+__global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const HitRec *__restrict__ hit0, float *__restrict__ film) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int pix = -1;
+    float3 out = f3(0.f);
+    if (i < P.n) {
+        pix = (int)((P.lane0 + i) / P.spp);
+        const Its its = reconstruct_its(P.S, load_hit(hit0 + i), transform_pos(P.cam.to_world, f3(0.f)));
+        if (its.valid) {
+            switch (field) {
+                case FIELD_SILHOUETTE: out = f3(1.f); break;
+                case FIELD_POSITION: out = its.p; break;
+                case FIELD_DEPTH: out = f3(its.t); break;
+                case FIELD_GEONORMAL: out = its.n; break;
+                case FIELD_SHNORMAL: out = its.sh.n; break;
+                default: out = f3(its.uv.x, its.uv.y, 0.f); break;
+            }
+        }
+        out = zero_nonfinite(out) * P.inv_spp;
+    }
+    film_accumulate(film, pix, out);
+}
+
+static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out) {
+    if (n > 0) k_trace<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out);
+}
+void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0) {
+    if (P.n > 0) k_primary<<<nblk(P.n, 128), 128, 0, st>>>(P, hit0);
+}
+void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, RayRec *rays_out) {
+    if (P.n > 0) k_shade<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, rays_out);
+}
+void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays,
+                    const HitRec *hits, PathState *state, float *film) {
+    if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, hits, state, film);
+}
+void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film) {
+    if (P.n > 0) k_field<<<nblk(P.n, 256), 256, 0, st>>>(P, field, hit0, film);
+}
+
+}  // namespace pb

@@ -1,0 +1,88 @@
+// psdr-b200: device-side scene tables and wavefront records (the HBM layout).
+//
+// Replaces the reference's Enoki SoA arrays (include/psdr/types.h:136-146 TriangleInfo_, scene.h m_triangle_info /
+// m_triangle_uv / m_triangle_face_normals / m_meshes_cuda, cuda/psdr_cuda.h:3-14 Params) with 16-byte-aligned records
+// so that every gather and every wavefront read/write is a 128-bit access.
+#pragma once
+#include "pb_math.cuh"
+
+namespace pb {
+
+// ---- wavefront records ---------------------------------------------------------------------------
+struct __align__(16) RayRec {      // 32 B
+    float ox, oy, oz, tmax;        // tmax < 0  <=>  lane inactive (the ray is not traced)
+    float dx, dy, dz, pad;
+};
+struct __align__(16) HitRec {      // 16 B: what cuda/psdr_cuda.cu:36-45 writes (tri id, shape id, u, v); -1 on miss
+    int tri, shape;
+    float u, v;
+};
+
+// ---- triangle table: one 128-byte line per triangle, indexed by global triangle id -------------------------------
+// q[0] = p0.xyz, face_area     q[1] = e1.xyz, mesh id (int bits)   q[2] = e2.xyz, flags (bit0: face normals)
+// q[3] = n0.xyz, uv0.x         q[4] = n1.xyz, uv0.y                q[5] = n2.xyz, uv1.x
+// q[6] = face_normal.xyz, uv1.y                                    q[7] = uv2.x, uv2.y, -, -
+struct __align__(16) TriRec { float4 q[8]; };
+
+// triangles in BVH leaf order for the traversal kernel (48 B): p0.xyz,tri id | e1.xyz,- | e2.xyz,-
+struct __align__(16) LeafTri { float4 a, b, c; };
+
+// BVH2 node, 64 B: both children's boxes + child links.
+// a = (l.lo.x, l.lo.y, l.lo.z, l.hi.x)  b = (l.hi.y, l.hi.z, r.lo.x, r.lo.y)  c = (r.lo.z, r.hi.x, r.hi.y, r.hi.z)
+// d = (left, right, -, -) as int bits; child >= 0: inner node index; child < 0: leaf, v = ~child, first = v >> 3, count = (v & 7) + 1
+struct __align__(16) BvhNode { float4 a, b, c, d; };
+
+struct MeshRec {           // 32 B, per mesh
+    int bsdf, emitter;     // -1 = none
+    float inv_total_area;
+    int face_offset, num_faces;
+    int flags;             // bit0 face normals, bit1 has uv
+    int pad0, pad1;
+};
+enum { BSDF_DIFFUSE = 0, BSDF_ROUGHCONDUCTOR = 1 };
+enum { TEX_REFLECTANCE = 0, TEX_ALPHA_U, TEX_ALPHA_V, TEX_ETA, TEX_K, TEX_SPECULAR, TEX_COUNT };
+struct TexRef {            // texel data interleaved [pixel*C + c]
+    const float *data;
+    float *grad;           // gradient accumulation target (same layout) or nullptr
+    int w, h, c, pad;
+};
+struct BsdfRec {
+    int type, pad[3];
+    TexRef tex[TEX_COUNT];
+};
+enum { EMITTER_AREA = 0, EMITTER_ENVMAP = 1 };
+struct EmitterRec {
+    int type, mesh;
+    float sampling_weight, pad;
+    float3 radiance;
+    float pad2;
+    const float *face_cmf, *face_pmf;   // area pmf of the emitter's mesh (mesh.cpp:249)
+    float face_sum;
+    int num_faces, face_offset, pad3;
+};
+struct SensorRec {
+    Mat4 sample_to_camera, to_world, world_to_sample;
+    float3 camera_pos, camera_dir;
+    float inv_area;
+    int width, height;
+};
+
+struct SceneView {
+    const TriRec *tri;
+    const LeafTri *leaf;
+    const BvhNode *nodes;
+    const MeshRec *meshes;
+    const BsdfRec *bsdfs;
+    const EmitterRec *emitters;
+    const float *emitter_cmf, *emitter_pmf;   // scene.cpp:183-196
+    float emitter_sum;
+    int num_tri, num_nodes, num_meshes, num_bsdfs, num_emitters;
+    int emitter_env;
+};
+
+enum { INTEG_DIRECT = 0, INTEG_FIELD = 1, INTEG_PATH = 2 };
+enum { FIELD_SILHOUETTE = 0, FIELD_POSITION, FIELD_DEPTH, FIELD_GEONORMAL, FIELD_SHNORMAL, FIELD_UV };
+
+PB_D float4 ldg4(const float4 *p) { return __ldg(p); }
+
+}  // namespace pb
