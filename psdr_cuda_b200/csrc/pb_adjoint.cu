@@ -1,0 +1,176 @@
+// psdr-b200: reverse-mode (VJP) kernels of the interior integral.
+//
+// The reference differentiates DirectIntegrator::__Li<true> (src/integrator/direct.cpp:47-163) with Enoki's tape and
+// ek.backward; here each scattering event has a hand-written adjoint that replays the event from the stored hit
+// records (same RNG positions as the forward renderD) and scatters into the flat gradient vector.
+//
+// Per lane the forward radiance is  L = Le(x0) + sum_k T_k * L_k,  T_{k+1} = T_k * w_k  (L_k: the event's MIS-weighted
+// connections, w_k: its continuation weight). With the suffix  S_k = L_k + w_k * S_{k+1}  the sensitivity of L to the
+// parameters touched by event k is  T_k * (dL_k + dw_k * S_{k+1}); the adjoint kernels run k = D-1 .. 0 carrying S.
+#include "pb_trace.cuh"
+#include "pb_wavefront.cuh"
+
+namespace pb {
+
+constexpr int kMaxConstBsdf = 64;
+
+// adjoint of bsdf_eval w.r.t. its textures; `g` is dLoss/d(value). Constant (1x1) textures accumulate into the
+// thread-private `acc` (flushed per block), bitmap textures scatter with atomics (Bitmap::eval's backward,
+// src/core/bitmap.cpp:43-89: scatter_add into the four texels).
+PB_D void bsdf_eval_grad_tex(const BsdfRec *b, const Its &its, float3 wo, float3 g, float3 &acc) {
+    if (!b) return;
+    const float cos_i = its.wi.z, cos_o = wo.z;
+    if (!(cos_i > 0.f && cos_o > 0.f)) return;
+    if (b->type == BSDF_DIFFUSE) {
+        const TexRef &t = b->tex[TEX_REFLECTANCE];
+        if (!t.grad) return;
+        const float3 gr = g * (kInvPi * cos_o);
+        if (t.w == 1 && t.h == 1) { acc += gr; return; }
+        const TexTap tap = tex_tap(t, its.uv);
+        const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
+        const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            atomicAdd(t.grad + idx[k] * 3 + 0, gr.x * w[k]);
+            atomicAdd(t.grad + idx[k] * 3 + 1, gr.y * w[k]);
+            atomicAdd(t.grad + idx[k] * 3 + 2, gr.z * w[k]);
+        }
+    }
+    // TODO(roughconductor): alpha_u/alpha_v/eta/k/specular_reflectance adjoints
+}
+
+// block-level reduction of the per-thread constant-texture accumulators, keyed by BSDF id
+PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, float *s_acc) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < kMaxConstBsdf * 3; t += blockDim.x) s_acc[t] = 0.f;
+    __syncthreads();
+    const bool has = bsdf_id >= 0 && (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f);
+    unsigned remaining = __ballot_sync(full, has);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int key = __shfl_sync(full, bsdf_id, leader);
+        const unsigned grp = __ballot_sync(full, has && bsdf_id == key);
+        float3 v = (has && bsdf_id == key) ? acc : f3(0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v.x += __shfl_xor_sync(full, v.x, o); v.y += __shfl_xor_sync(full, v.y, o); v.z += __shfl_xor_sync(full, v.z, o);
+        }
+        if (lane == leader) {
+            if (key < kMaxConstBsdf) {
+                atomicAdd(s_acc + key * 3, v.x); atomicAdd(s_acc + key * 3 + 1, v.y); atomicAdd(s_acc + key * 3 + 2, v.z);
+            } else {
+                float *gp = S.bsdfs[key].tex[TEX_REFLECTANCE].grad;
+                atomicAdd(gp, v.x); atomicAdd(gp + 1, v.y); atomicAdd(gp + 2, v.z);
+            }
+        }
+        remaining &= ~grp;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kMaxConstBsdf * 3; t += blockDim.x) {
+        const float v = s_acc[t];
+        if (v != 0.f) {
+            const int b = t / 3;
+            if (b < S.num_bsdfs) { float *gp = S.bsdfs[b].tex[TEX_REFLECTANCE].grad; if (gp) atomicAdd(gp + (t - 3 * b), v); }
+        }
+    }
+}
+
+// adjoint of one scattering event (texture parameters). state_k: T_k and nothing else is read from it; suffix: S_{k+1}
+// in, S_k out; final_state.rad: the lane's forward radiance (decides which channels integrator.cpp:87 zeroed).
+__global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
+                                                 const HitRec *__restrict__ hits, const PathState *__restrict__ state_k,
+                                                 const PathState *__restrict__ final_state, float4 *__restrict__ suffix,
+                                                 const float *__restrict__ dLdI) {
+    __shared__ float s_acc[kMaxConstBsdf * 3];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 acc = f3(0.f);
+    int bsdf_id = -1;
+    if (i < P.n) {
+        int pix;
+        const long long lane = global_lane(P, i, pix);
+        const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
+        const Its &its = v.its;
+        bsdf_id = v.bsdf ? (int)(v.bsdf - P.S.bsdfs) : -1;
+        // loss adjoint of this lane's radiance
+        const float3 rad_final = f3(ldg4(reinterpret_cast<const float4 *>(final_state + i) + 1));
+        float3 g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
+        if (!isfinite(rad_final.x)) g.x = 0.f;
+        if (!isfinite(rad_final.y)) g.y = 0.f;
+        if (!isfinite(rad_final.z)) g.z = 0.f;
+        float3 T = f3(1.f);
+        if (B.depth > 0) T = f3(ldg4(reinterpret_cast<const float4 *>(state_k + i)));
+        const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
+        const float3 gL = g * T, gw = gL * S_next;
+        Rng rng((uint64_t)lane, B.jump);
+        float3 L = f3(0.f), w_cont = f3(0.f);
+        const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
+        for (int j = 0; j < B.nb; ++j) {
+            const float3 s3 = rng.next_3d();
+            const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
+            bool a1 = v.active && bs.valid;
+            const HitRec h1 = load_hit(hits + (size_t)j * P.n + i);
+            const Its its1 = reconstruct_its(P.S, h1, its.p);
+            a1 = a1 && its1.valid;
+            const bool cont = a1 && B.carry && j == 0;
+            a1 = a1 && is_emitter(P.S, its1.shape);
+            if (a1 || cont) {
+                float3 wo = its1.p - its.p;
+                wo = wo / its1.t;
+                const float3 wo_l = its.sh.to_local(wo);
+                const float3 f = bsdf_eval(v.bsdf, its, wo_l, true);
+                const float G = fabsf(dot(its1.n, -wo)) / sqr(its1.t);
+                const float pdf0 = bs.pdf * G;
+                const float scale = G / pdf0;
+                float3 gval = f3(0.f);
+                if (a1) {
+                    float weight = inv_nb;
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
+                    const float3 Le = emitter_Le(P.S, its1, true);
+                    L += Le * f * (scale * weight);
+                    gval += gL * Le * (scale * weight);
+                }
+                if (cont) { w_cont = f * scale; gval += gw * scale; }
+                bsdf_eval_grad_tex(v.bsdf, its, wo_l, gval, acc);
+            }
+        }
+        for (int j = 0; j < B.nl; ++j) {
+            const float2 s2 = rng.next_2d();
+            const PositionSample ps = sample_emitter_position(P.S, s2, v.active);
+            bool a1 = v.active && ps.valid;
+            float3 wo = ps.p - its.p;
+            const float dist_sqr = squared_norm(wo);
+            const float dist = safe_sqrt(dist_sqr);
+            wo = wo / dist;
+            const HitRec h1 = load_hit(hits + (size_t)(B.nb + j) * P.n + i);
+            const Its its1 = reconstruct_its(P.S, h1, its.p);
+            a1 = a1 && its1.valid && (its1.t > dist - kShadowEpsilon) && is_emitter(P.S, its1.shape);
+            if (a1) {
+                const float G = fabsf(dot(its1.n, -wo)) / dist_sqr;
+                const float3 wo_l = its.sh.to_local(wo);
+                const float3 f = bsdf_eval(v.bsdf, its, wo_l, true);
+                const float pdf1 = bsdf_pdf(v.bsdf, its, wo_l, true) * G;
+                float weight = inv_nl;
+                if (B.nb > 0) weight *= mis_weight(ps.pdf, pdf1);
+                const float3 Le = emitter_Le(P.S, its1, true);
+                const float scale = G / ps.pdf * weight;
+                L += Le * f * scale;
+                bsdf_eval_grad_tex(v.bsdf, its, wo_l, gL * Le * scale, acc);
+            }
+        }
+        if (B.depth > 0) {
+            const float3 Sk = L + w_cont * S_next;
+            suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
+        }
+    }
+    flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
+}
+
+static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, const HitRec *hits,
+                    const PathState *state_k, const PathState *final_state, float4 *suffix, const float *dLdI) {
+    if (P.n > 0) k_adjoint<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, hits, state_k, final_state, suffix, dLdI);
+}
+
+}  // namespace pb

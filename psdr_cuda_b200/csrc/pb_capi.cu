@@ -297,60 +297,95 @@ static Plan make_plan(const pb_integrator &I) {
     return p;
 }
 
-// interior term: integrator.cpp:64-95 over this shard's pixels, in batches
-static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float *d_image, bool ad) {
+enum Mode { MODE_C = 0, MODE_D = 1, MODE_VJP = 2 };
+
+// interior term: integrator.cpp:64-95 over this shard's samples, in batches. MODE_VJP replays the last renderD
+// (same stream positions), keeps every event's records and then runs the adjoint kernels in reverse event order.
+static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float *d_image, Mode mode, const float *d_dLdI = nullptr,
+                            float *d_grad = nullptr) {
     PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
     PB_ASSERT_MSG(sensor >= 0 && sensor < (int)c->sensors.size(), "Invalid sensor id!");
     PB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int64_t npix = (int64_t)c->width * c->height;
-    PB_CUDA(cudaMemsetAsync(d_image, 0, (size_t)npix * 3 * sizeof(float), st));
+    if (d_image) PB_CUDA(cudaMemsetAsync(d_image, 0, (size_t)npix * 3 * sizeof(float), st));
     c->last_trace_ms = 0.f; c->last_rays = 0;
-    if (c->spp <= 0) { PB_CUDA(cudaStreamSynchronize(st)); return; }
+    const int s0 = (int)((int64_t)c->spp * c->rank / c->world), s1 = (int)((int64_t)c->spp * (c->rank + 1) / c->world);
+    const int spp_local = s1 - s0;
     const Plan plan = make_plan(I);
+    const uint64_t base = (mode == MODE_VJP) ? c->last_d_offset : c->sampler_offset[0];
+    if (c->spp <= 0 || spp_local <= 0) {
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (mode != MODE_VJP && c->spp > 0) c->sampler_offset[0] = base + plan.draws;
+        return;
+    }
     PB_ASSERT_MSG(I.kind == PB_INTEG_FIELD || !c->emitters.empty(), "No Emitter!");
-    const int64_t p0 = npix * c->rank / c->world, p1 = npix * (c->rank + 1) / c->world;
-    const int64_t lane_begin = p0 * c->spp, lane_end = p1 * c->spp;
+    const int64_t total = npix * spp_local;
     const int R = std::max(1, plan.nb + plan.nl);
-    const int64_t B = std::min<int64_t>(c->batch, std::max<int64_t>(1024, lane_end - lane_begin));
+    const int64_t B = std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024);
+    const bool keep = (mode == MODE_VJP);
+    const int nbuf = keep ? std::max(1, plan.nbounce) : 2;
+    if ((int)c->d_rays.size() < nbuf) { c->d_rays.resize(nbuf); c->d_hits.resize(nbuf); }
+    if ((int)c->d_state.size() < nbuf + 1) c->d_state.resize(nbuf + 1);
     c->d_hit0.reserve((size_t)B * sizeof(HitRec));
-    for (int k = 0; k < 2; ++k) { c->d_rays[k].reserve((size_t)B * R * sizeof(RayRec)); c->d_hits[k].reserve((size_t)B * R * sizeof(HitRec)); }
-    c->d_state.reserve((size_t)B * sizeof(PathState));
+    for (int k = 0; k < nbuf; ++k) { c->d_rays[k].reserve((size_t)B * R * sizeof(RayRec)); c->d_hits[k].reserve((size_t)B * R * sizeof(HitRec)); }
+    for (int k = 0; k < nbuf + 1; ++k) c->d_state[k].reserve((size_t)B * sizeof(PathState));
+    if (keep) c->d_suffix.reserve((size_t)B * sizeof(float4));
     RenderParams P;
     P.S = c->view; P.cam = c->sensors[sensor].rec;
     P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
-    const uint64_t base = c->sampler_offset[0];
+    P.spp_local = spp_local; P.s0 = s0;
     P.jump0 = make_jump(base);
+    if (keep) {   // BSDF table whose textures point at their gradient segments
+        std::vector<BsdfRec> br(c->bsdfs.size());
+        PB_CUDA(cudaMemcpyAsync(br.data(), c->d_bsdfs.p, br.size() * sizeof(BsdfRec), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        for (const GradSegment &g : c->grad_segments)
+            if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;
+        c->d_bsdfs_grad.upload(br, st);
+        P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
+    }
     size_t nev = 0;
-    for (int64_t start = lane_begin; start < lane_end; start += B) {
-        P.lane0 = start; P.n = (int)std::min<int64_t>(B, lane_end - start);
+    for (int64_t start = 0; start < total; start += B) {
+        P.local0 = start; P.n = (int)std::min<int64_t>(B, total - start);
         cudaEvent_t e0 = get_event(c, nev++), e1 = get_event(c, nev++);
         PB_CUDA(cudaEventRecord(e0, st));
         launch_primary(st, P, c->d_hit0.as<HitRec>());
         PB_CUDA(cudaEventRecord(e1, st));
         c->launches++; c->last_rays += P.n;
         if (I.kind == PB_INTEG_FIELD) {
-            launch_field(st, P, I.field, c->d_hit0.as<HitRec>(), d_image);
-            c->launches++;
+            if (mode != MODE_VJP) { launch_field(st, P, I.field, c->d_hit0.as<HitRec>(), d_image); c->launches++; }
             continue;
         }
-        const HitRec *hit_cur = c->d_hit0.as<HitRec>();
-        const RayRec *prev_rays = nullptr;
+        std::vector<BounceParams> bps(plan.nbounce);
         for (int k = 0; k < plan.nbounce; ++k) {
-            BounceParams Bp;
+            BounceParams &Bp = bps[k];
             Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
-            Bp.hide_emitters = I.hide_emitters; Bp.ad = ad ? 1 : 0;
+            Bp.hide_emitters = I.hide_emitters; Bp.ad = (mode == MODE_C) ? 0 : 1;
             Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
-            RayRec *rays = c->d_rays[k & 1].as<RayRec>();
-            HitRec *hits = c->d_hits[k & 1].as<HitRec>();
-            launch_shade(st, P, Bp, hit_cur, prev_rays, rays);
+        }
+        auto hit_cur_of = [&](int k) { return k == 0 ? c->d_hit0.as<HitRec>() : c->d_hits[keep ? k - 1 : (k - 1) & 1].as<HitRec>(); };
+        auto prev_rays_of = [&](int k) { return k == 0 ? (const RayRec *)nullptr : c->d_rays[keep ? k - 1 : (k - 1) & 1].as<RayRec>(); };
+        for (int k = 0; k < plan.nbounce; ++k) {
+            const int slot = keep ? k : (k & 1);
+            RayRec *rays = c->d_rays[slot].as<RayRec>();
+            HitRec *hits = c->d_hits[slot].as<HitRec>();
+            launch_shade(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), rays);
             cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
             PB_CUDA(cudaEventRecord(t0, st));
             launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), rays, hits, nullptr);
             PB_CUDA(cudaEventRecord(t1, st));
-            launch_resolve(st, P, Bp, hit_cur, prev_rays, hits, c->d_state.as<PathState>(), d_image);
+            const int sin = keep ? k : (k & 1), sout = keep ? k + 1 : ((k + 1) & 1);
+            PathState *so = (bps[k].last && !keep) ? nullptr : c->d_state[sout].as<PathState>();
+            launch_resolve(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), hits, c->d_state[sin].as<PathState>(), so, d_image);
             c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl);
-            hit_cur = hits; prev_rays = rays;
+        }
+        if (keep) {
+            for (int k = plan.nbounce - 1; k >= 0; --k) {
+                launch_adjoint(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), c->d_hits[k].as<HitRec>(), c->d_state[k].as<PathState>(),
+                               c->d_state[plan.nbounce].as<PathState>(), c->d_suffix.as<float4>(), d_dLdI);
+                c->launches++;
+            }
         }
     }
     PB_CUDA(cudaGetLastError());
@@ -360,7 +395,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         PB_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
         c->last_trace_ms += ms;
     }
-    c->sampler_offset[0] = base + plan.draws;
+    if (mode != MODE_VJP) c->sampler_offset[0] = base + plan.draws;
 }
 
 }  // namespace pb
@@ -573,7 +608,7 @@ int pb_trace(pb_ctx *c, int64_t n, const float *d_rays, void *d_hits, float *d_t
     });
 }
 int pb_render_c(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
-    return guard(c, [&] { PB_ASSERT_MSG(I && d_image, "Null argument"); render_interior(c, *I, sensor, d_image, false); });
+    return guard(c, [&] { PB_ASSERT_MSG(I && d_image, "Null argument"); render_interior(c, *I, sensor, d_image, MODE_C); });
 }
 int pb_render_c_host(pb_ctx *c, const pb_integrator *I, int sensor, float *h_image) {
     return guard(c, [&] {
@@ -581,7 +616,7 @@ int pb_render_c_host(pb_ctx *c, const pb_integrator *I, int sensor, float *h_ima
         const size_t bytes = (size_t)c->width * c->height * 3 * sizeof(float);
         DevBuf img;
         img.reserve(bytes);
-        render_interior(c, *I, sensor, img.as<float>(), false);
+        render_interior(c, *I, sensor, img.as<float>(), MODE_C);
         PB_CUDA(cudaMemcpy(h_image, img.p, bytes, cudaMemcpyDeviceToHost));
     });
 }
@@ -589,7 +624,7 @@ int pb_render_d(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
     return guard(c, [&] {
         PB_ASSERT_MSG(I && d_image, "Null argument");
         const uint64_t off = c->sampler_offset[0];
-        render_interior(c, *I, sensor, d_image, true);
+        render_interior(c, *I, sensor, d_image, MODE_D);
         c->last_d_offset = off; c->have_last_d = true;
     });
 }
@@ -615,8 +650,16 @@ int pb_grad_segment(pb_ctx *c, int index, int *kind, int *id, int *slot, int64_t
     });
 }
 int64_t pb_grad_size(pb_ctx *c) { return c->grad_segments.empty() ? 0 : c->grad_segments.back().offset + c->grad_segments.back().count; }
-int pb_render_d_vjp(pb_ctx *c, const pb_integrator *, int, const float *, float *) {
-    return guard(c, [&] { throw Error("pb_render_d_vjp: not implemented yet"); });
+int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *d_dLdI, float *d_grad) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(I && d_dLdI && d_grad, "Null argument");
+        PB_ASSERT_MSG(c->have_last_d, "pb_render_d_vjp needs a preceding pb_render_d on the configured scene");
+        PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD, "FieldExtractionIntegrator has no parameter gradients in the interior term yet");
+        for (const GradSegment &g : c->grad_segments)
+            PB_ASSERT_MSG(g.kind == PB_PARAM_BSDF_TEXTURE && c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE,
+                          "pb_render_d_vjp: only diffuse reflectance gradients are implemented so far");
+        render_interior(c, *I, sensor, nullptr, MODE_VJP, d_dLdI, d_grad);
+    });
 }
 
 int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }

@@ -109,7 +109,8 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_hit0, d_rays[2], d_hits[2], d_state;
+    pb::DevBuf d_hit0, d_suffix, d_bsdfs_grad;
+    std::vector<pb::DevBuf> d_rays, d_hits, d_state;
     // replay info of the last renderD
     uint64_t last_d_offset = 0;
     bool have_last_d = false;

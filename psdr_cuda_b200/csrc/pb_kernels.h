@@ -24,7 +24,8 @@ struct RenderParams {
     SensorRec cam;
     int width, height, spp;
     float inv_spp;
-    long long lane0;        // global lane id of the first lane of this batch
+    long long local0;       // shard-local index of the first lane of this batch
+    int spp_local, s0;      // this shard owns samples [s0, s0 + spp_local) of every pixel
     int n;                  // lanes in this batch
     RngJump jump0;          // stream position of the pixel jitter
 };
@@ -40,7 +41,9 @@ void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, RayRec *rays_out);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays,
-                    const HitRec *hits, PathState *state, float *film);
+                    const HitRec *hits, const PathState *state_in, PathState *state_out, float *film);
+void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, const HitRec *hits,
+                    const PathState *state_k, const PathState *final_state, float4 *suffix, const float *dLdI);
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film);
 
 }  // namespace pb

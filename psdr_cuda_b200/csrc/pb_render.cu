@@ -9,6 +9,7 @@
 #include "pb_kernels.h"
 #include "pb_shade.cuh"
 #include "pb_trace.cuh"
+#include "pb_wavefront.cuh"
 
 namespace pb {
 
@@ -23,52 +24,20 @@ __global__ void __launch_bounds__(128) k_trace(const BvhNode *__restrict__ nodes
     if (t_out) t_out[i] = h.t;
 }
 
-PB_D void lane_pixel_sample(const RenderParams &P, long long lane, float2 jitter, int &pix, float &sx, float &sy) {
-    pix = (int)(lane / P.spp);
-    const int x = pix % P.width, y = pix / P.width;
-    sx = div_rn(add_rn((float)x, jitter.x), (float)P.width);
-    sy = div_rn(add_rn((float)y, jitter.y), (float)P.height);
-}
-
 // integrator.cpp:76-85 + the first ray launch of direct.cpp:48
 __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restrict__ hit0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const long long lane = P.lane0 + i;
+    int pix;
+    const long long lane = global_lane(P, i, pix);
     Rng rng((uint64_t)lane, P.jump0);
     const float2 j = rng.next_2d();
-    int pix; float sx, sy;
-    lane_pixel_sample(P, lane, j, pix, sx, sy);
+    float sx, sy;
+    lane_pixel_sample(P, pix, j, sx, sy);
     float3 o, d;
     sample_primary_ray(P.cam, sx, sy, o, d);
     const Hit h = trace_closest(P.S.nodes, P.S.leaf, o, d, INFINITY);
     reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
-}
-
-struct Vertex { Its its; const BsdfRec *bsdf; bool active; };
-
-PB_D HitRec load_hit(const HitRec *p) {
-    const float4 h = ldg4(reinterpret_cast<const float4 *>(p));
-    HitRec r;
-    r.tri = __float_as_int(h.x); r.shape = __float_as_int(h.y); r.u = h.z; r.v = h.w;
-    return r;
-}
-PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax) {
-    float4 *q = reinterpret_cast<float4 *>(p);
-    q[0] = make_float4(o.x, o.y, o.z, tmax);
-    q[1] = make_float4(d.x, d.y, d.z, 0.f);
-}
-
-PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const HitRec *hit_cur, const RayRec *prev_rays) {
-    float3 origin;
-    if (B.depth == 0) origin = transform_pos(P.cam.to_world, f3(0.f));
-    else origin = f3(ldg4(reinterpret_cast<const float4 *>(prev_rays + i)));
-    Vertex v;
-    v.its = reconstruct_its(P.S, load_hit(hit_cur + i), origin);
-    v.active = v.its.valid;
-    v.bsdf = its_bsdf(P.S, v.its);
-    if (P.S.emitter_env >= 0) v.active = v.active && v.bsdf != nullptr;   // direct.cpp:54-57
-    return v;
 }
 
 // sample the connections of one scattering event and emit their rays (direct.cpp:69-76, 120-129)
@@ -77,7 +46,8 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, c
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
-    Rng rng((uint64_t)(P.lane0 + i), B.jump);
+    int pix_unused;
+    Rng rng((uint64_t)global_lane(P, i, pix_unused), B.jump);
     for (int j = 0; j < B.nb; ++j) {
         const float3 s3 = rng.next_3d();
         const BsdfSample bs = bsdf_sample(v.bsdf, v.its, s3, v.active);
@@ -95,35 +65,16 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, c
     }
 }
 
-// warp-segmented sum over lanes that share a pixel (spp consecutive lanes per pixel, integrator.cpp:76-77), then one
-// atomicAdd per segment instead of the reference's per-lane scatter_add (integrator.cpp:88)
-PB_D void film_accumulate(float *film, int pix, float3 val) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float x = __shfl_down_sync(full, val.x, o), y = __shfl_down_sync(full, val.y, o), z = __shfl_down_sync(full, val.z, o);
-        const int p2 = __shfl_down_sync(full, pix, o);
-        if (lane + o < 32 && p2 == pix) { val.x += x; val.y += y; val.z += z; }
-    }
-    const int prev = __shfl_up_sync(full, pix, 1);
-    if (pix >= 0 && (lane == 0 || prev != pix)) {
-        atomicAdd(film + 3 * (size_t)pix, val.x);
-        atomicAdd(film + 3 * (size_t)pix + 1, val.y);
-        atomicAdd(film + 3 * (size_t)pix + 2, val.z);
-    }
-}
-
 // direct.cpp:77-113 (BSDF-sampled connections) and 130-158 (emitter-sampled connections) for one scattering event
 __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
-                                                 const HitRec *__restrict__ hits, PathState *__restrict__ state, float *__restrict__ film) {
+                                                 const HitRec *__restrict__ hits, const PathState *__restrict__ state_in,
+                                                 PathState *__restrict__ state_out, float *__restrict__ film) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i < P.n;
     int pix = -1;
     float3 out = f3(0.f);
     if (in_range) {
-        const long long lane = P.lane0 + i;
-        pix = (int)(lane / P.spp);
+        const long long lane = global_lane(P, i, pix);
         const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
         const Its &its = v.its;
         Rng rng((uint64_t)lane, B.jump);
@@ -189,20 +140,19 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
         if (B.depth == 0) {
             rad = B.hide_emitters ? f3(0.f) : emitter_Le(P.S, its, its.valid);   // direct.cpp:51
         } else {
-            const float4 *sp = reinterpret_cast<const float4 *>(state + i);
+            const float4 *sp = reinterpret_cast<const float4 *>(state_in + i);
             thr = f3(sp[0]); rad = f3(sp[1]);
         }
         rad += thr * L;
-        if (B.last) {
-            out = zero_nonfinite(rad) * P.inv_spp;   // integrator.cpp:87-91
-        } else {
-            float4 *sp = reinterpret_cast<float4 *>(state + i);
+        if (B.last) out = zero_nonfinite(rad) * P.inv_spp;   // integrator.cpp:87-91
+        if (state_out) {
+            float4 *sp = reinterpret_cast<float4 *>(state_out + i);
             const float3 t2 = thr * w_cont;
             sp[0] = make_float4(t2.x, t2.y, t2.z, 0.f);
             sp[1] = make_float4(rad.x, rad.y, rad.z, 0.f);
         }
     }
-    if (B.last) film_accumulate(film, pix, out);
+    if (B.last && film) film_accumulate(film, pix, out);
 }
 
 // field.cpp:34-54
@@ -211,7 +161,7 @@ __global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const 
     int pix = -1;
     float3 out = f3(0.f);
     if (i < P.n) {
-        pix = (int)((P.lane0 + i) / P.spp);
+        global_lane(P, i, pix);
         const Its its = reconstruct_its(P.S, load_hit(hit0 + i), transform_pos(P.cam.to_world, f3(0.f)));
         if (its.valid) {
             switch (field) {
@@ -240,8 +190,8 @@ void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B,
     if (P.n > 0) k_shade<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, rays_out);
 }
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays,
-                    const HitRec *hits, PathState *state, float *film) {
-    if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, hits, state, film);
+                    const HitRec *hits, const PathState *state_in, PathState *state_out, float *film) {
+    if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, hits, state_in, state_out, film);
 }
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film) {
     if (P.n > 0) k_field<<<nblk(P.n, 256), 256, 0, st>>>(P, field, hit0, film);

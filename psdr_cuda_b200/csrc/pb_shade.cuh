@@ -69,6 +69,40 @@ PB_D Its reconstruct_its(const SceneView &S, const HitRec &h, float3 ray_o) {
     return its;
 }
 
+// Scene::ray_intersect<true,false> — the solid-angle flavour renderD uses for the camera ray (scene.cpp:355-376):
+// (u,v,t) re-derived from the ray by Möller–Trumbore, p = o + t d, wi = to_local(-d)
+PB_D Its reconstruct_its_primary(const SceneView &S, const HitRec &h, float3 ray_o, float3 ray_d) {
+    Its its;
+    its.valid = h.tri >= 0;
+    its.tri = h.tri; its.shape = h.shape;
+    if (!its.valid) { its.t = 0.f; its.p = its.n = its.wi = f3(0.f); its.uv = make_float2(0.f, 0.f); return its; }
+    const float4 *q = reinterpret_cast<const float4 *>(S.tri + h.tri);
+    const float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2), q6 = ldg4(q + 6);
+    const int flags = __float_as_int(q2.w);
+    float u, v, t;
+    ray_intersect_triangle(f3(q0), f3(q1), f3(q2), ray_o, ray_d, u, v, t);
+    its.n = f3(q6);
+    float3 sh_n = its.n;
+    float4 q3, q4, q5;
+    if (!(flags & 1) || (flags & 2)) { q3 = ldg4(q + 3); q4 = ldg4(q + 4); q5 = ldg4(q + 5); }
+    if (!(flags & 1)) {
+        const float3 n0 = f3(q3), n1 = f3(q4), n2 = f3(q5);
+        sh_n = normalize(bilinear(n0, n1 - n0, n2 - n0, u, v));
+    }
+    its.p = f3(fma_rn(ray_d.x, t, ray_o.x), fma_rn(ray_d.y, t, ray_o.y), fma_rn(ray_d.z, t, ray_o.z));
+    its.t = t;
+    its.sh = Frame(sh_n);
+    its.wi = its.sh.to_local(-ray_d);
+    if (flags & 2) {
+        const float4 q7 = ldg4(q + 7);
+        const float u0x = q3.w, u0y = q4.w, u1x = q5.w, u1y = q6.w, u2x = q7.x, u2y = q7.y;
+        its.uv = make_float2(fma_rn(u1x - u0x, u, fma_rn(u2x - u0x, v, u0x)), fma_rn(u1y - u0y, u, fma_rn(u2y - u0y, v, u0y)));
+    } else {
+        its.uv = make_float2(0.f, 0.f);
+    }
+    return its;
+}
+
 // ---- textures (bitmap.cpp:43-89) ------------------------------------------------------------------------
 struct TexTap { int idx; float w0x, w1x, w0y, w1y; bool constant; };
 PB_D TexTap tex_tap(const TexRef &t, float2 uv, bool flip_v = true) {

@@ -1,0 +1,81 @@
+// psdr-b200: helpers shared by the wavefront kernels (lane mapping, record load/store, vertex reconstruction,
+// film accumulation).
+#pragma once
+#include "pb_kernels.h"
+#include "pb_shade.cuh"
+
+namespace pb {
+
+// shard-local lane index -> (pixel, global lane id). A shard owns samples [s0, s0 + spp_local) of every pixel, so the
+// global lane id (= RNG stream id, integrator.cpp:76) is pix*spp + s and results do not depend on the GPU count.
+PB_D long long global_lane(const RenderParams &P, int i, int &pix) {
+    const long long li = P.local0 + i;
+    pix = (int)(li / P.spp_local);
+    return (long long)pix * P.spp + P.s0 + (int)(li - (long long)pix * P.spp_local);
+}
+
+PB_D void lane_pixel_sample(const RenderParams &P, int pix, float2 jitter, float &sx, float &sy) {
+    const int x = pix % P.width, y = pix / P.width;
+    sx = div_rn(add_rn((float)x, jitter.x), (float)P.width);
+    sy = div_rn(add_rn((float)y, jitter.y), (float)P.height);
+}
+
+struct Vertex { Its its; const BsdfRec *bsdf; bool active; };
+
+PB_D HitRec load_hit(const HitRec *p) {
+    const float4 h = ldg4(reinterpret_cast<const float4 *>(p));
+    HitRec r;
+    r.tri = __float_as_int(h.x); r.shape = __float_as_int(h.y); r.u = h.z; r.v = h.w;
+    return r;
+}
+PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax) {
+    float4 *q = reinterpret_cast<float4 *>(p);
+    q[0] = make_float4(o.x, o.y, o.z, tmax);
+    q[1] = make_float4(d.x, d.y, d.z, 0.f);
+}
+
+PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const HitRec *hit_cur, const RayRec *prev_rays) {
+    Vertex v;
+    if (B.depth == 0) {
+        if (B.ad) {   // renderD: the camera hit is differentiated in solid-angle form (scene.cpp:355-376)
+            int pix;
+            const long long lane = global_lane(P, i, pix);
+            Rng rng((uint64_t)lane, P.jump0);
+            const float2 j = rng.next_2d();
+            float sx, sy;
+            lane_pixel_sample(P, pix, j, sx, sy);
+            float3 o, d;
+            sample_primary_ray(P.cam, sx, sy, o, d);
+            v.its = reconstruct_its_primary(P.S, load_hit(hit_cur + i), o, d);
+        } else {
+            v.its = reconstruct_its(P.S, load_hit(hit_cur + i), transform_pos(P.cam.to_world, f3(0.f)));
+        }
+    } else {
+        v.its = reconstruct_its(P.S, load_hit(hit_cur + i), f3(ldg4(reinterpret_cast<const float4 *>(prev_rays + i))));
+    }
+    v.active = v.its.valid;
+    v.bsdf = its_bsdf(P.S, v.its);
+    if (P.S.emitter_env >= 0) v.active = v.active && v.bsdf != nullptr;   // direct.cpp:54-57
+    return v;
+}
+
+// warp-segmented sum over lanes that share a pixel (spp consecutive lanes per pixel, integrator.cpp:76-77), then one
+// atomicAdd per segment instead of the reference's per-lane scatter_add (integrator.cpp:88)
+PB_D void film_accumulate(float *film, int pix, float3 val) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float x = __shfl_down_sync(full, val.x, o), y = __shfl_down_sync(full, val.y, o), z = __shfl_down_sync(full, val.z, o);
+        const int p2 = __shfl_down_sync(full, pix, o);
+        if (lane + o < 32 && p2 == pix) { val.x += x; val.y += y; val.z += z; }
+    }
+    const int prev = __shfl_up_sync(full, pix, 1);
+    if (pix >= 0 && (lane == 0 || prev != pix)) {
+        atomicAdd(film + 3 * (size_t)pix, val.x);
+        atomicAdd(film + 3 * (size_t)pix + 1, val.y);
+        atomicAdd(film + 3 * (size_t)pix + 2, val.z);
+    }
+}
+
+}  // namespace pb
