@@ -52,9 +52,12 @@ int pb_version(void);
 /* lanes per wavefront batch (multiple of 1024); 0 restores the default. Tiling replaces the reference's
  * "all W*H*spp lanes at once" (src/integrator/integrator.cpp:69-76). */
 int pb_ctx_set_batch(pb_ctx *ctx, int64_t lanes);
-/* multi-GPU: this context renders shard `rank` of `world` (pixel tiles for the interior term, lane ranges for the
- * edge terms; RNG streams stay indexed by the global lane id). Default (0, 1). */
+/* multi-GPU: this context renders shard `rank` of `world`: samples [spp*rank/world, spp*(rank+1)/world) of every pixel
+ * (lane ranges for the edge terms). RNG streams stay indexed by the global lane id, so the sum of the shards' images
+ * equals the single-GPU image up to fp32 summation order. Default (0, 1). */
 int pb_ctx_set_shard(pb_ctx *ctx, int rank, int world);
+/* run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream) instead of the context's own */
+int pb_ctx_set_stream(pb_ctx *ctx, void *cuda_stream);
 
 /* ---- scene description: what SceneLoader::load_scene builds (src/scene/scene_loader.cpp:208-242) ------------- */
 /* RenderOption: include/psdr/types.h:171-182, src/psdr.cpp:53-72 */
@@ -108,11 +111,14 @@ int64_t pb_grad_size(pb_ctx *ctx);
 int pb_render_d_vjp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const float *d_dLdI, float *d_grad);
 
 /* ---- instrumentation ---------------------------------------------------------------------------------------- */
-/* kernels launched by this context since creation, and the milliseconds the last render call spent in its traversal
- * kernels (CUDA events on the context's stream) — bench.py's gpu_launches and roofline inputs */
+/* kernels launched by this context since creation; for the last render / trace call: milliseconds spent in the k_trace
+ * launches (CUDA events on the context's stream), how many launches and rays that was, and the milliseconds of the
+ * fused raygen + primary-trace kernel — bench.py's gpu_launches and roofline inputs */
 int64_t pb_stats_launches(pb_ctx *ctx);
 float pb_stats_last_trace_ms(pb_ctx *ctx);
 int64_t pb_stats_last_rays(pb_ctx *ctx);
+int pb_stats_last_trace_launches(pb_ctx *ctx);
+float pb_stats_last_primary_ms(pb_ctx *ctx);
 
 #ifdef __cplusplus
 }

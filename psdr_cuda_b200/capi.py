@@ -20,12 +20,12 @@ MESH_FACE_NORMALS, MESH_ENABLE_EDGES = 1, 2
 PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES = 0, 1
 
 SYMBOLS = [
-    "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard",
+    "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream",
     "pb_scene_set_options", "pb_scene_add_sensor", "pb_scene_set_sensor_transform", "pb_scene_add_bsdf", "pb_scene_set_bsdf_texture",
     "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
-    "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays",
+    "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
 ]
 
 
@@ -47,6 +47,7 @@ def lib():
         L.pb_stats_launches.restype = C.c_int64
         L.pb_stats_last_rays.restype = C.c_int64
         L.pb_stats_last_trace_ms.restype = C.c_float
+        L.pb_stats_last_primary_ms.restype = C.c_float
         _lib = L
     return _lib
 
@@ -111,6 +112,10 @@ class Context:
 
     def set_batch(self, lanes):
         self._chk(lib().pb_ctx_set_batch(self.h, C.c_int64(lanes)))
+
+    def set_stream(self, cuda_stream):
+        """run on the caller's stream (int handle, e.g. torch.cuda.current_stream().cuda_stream; 0 = legacy default)"""
+        self._chk(lib().pb_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
 
     def set_shard(self, rank, world):
         self._chk(lib().pb_ctx_set_shard(self.h, rank, world))
@@ -236,4 +241,5 @@ class Context:
     # --- stats -------------------------------------------------------------------------------------------------
     def stats(self):
         L = lib()
-        return dict(launches=int(L.pb_stats_launches(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)))
+        return dict(launches=int(L.pb_stats_launches(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)),
+                    trace_launches=int(L.pb_stats_last_trace_launches(self.h)), primary_ms=float(L.pb_stats_last_primary_ms(self.h)))

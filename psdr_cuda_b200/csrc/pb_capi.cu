@@ -309,7 +309,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     cudaStream_t st = c->stream;
     const int64_t npix = (int64_t)c->width * c->height;
     if (d_image) PB_CUDA(cudaMemsetAsync(d_image, 0, (size_t)npix * 3 * sizeof(float), st));
-    c->last_trace_ms = 0.f; c->last_rays = 0;
+    c->last_trace_ms = 0.f; c->last_rays = 0; c->last_primary_ms = 0.f; c->last_trace_launches = 0;
     const int s0 = (int)((int64_t)c->spp * c->rank / c->world), s1 = (int)((int64_t)c->spp * (c->rank + 1) / c->world);
     const int spp_local = s1 - s0;
     const Plan plan = make_plan(I);
@@ -352,7 +352,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         PB_CUDA(cudaEventRecord(e0, st));
         launch_primary(st, P, c->d_hit0.as<HitRec>());
         PB_CUDA(cudaEventRecord(e1, st));
-        c->launches++; c->last_rays += P.n;
+        c->launches++;
         if (I.kind == PB_INTEG_FIELD) {
             if (mode != MODE_VJP) { launch_field(st, P, I.field, c->d_hit0.as<HitRec>(), d_image); c->launches++; }
             continue;
@@ -378,7 +378,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             const int sin = keep ? k : (k & 1), sout = keep ? k + 1 : ((k + 1) & 1);
             PathState *so = (bps[k].last && !keep) ? nullptr : c->d_state[sout].as<PathState>();
             launch_resolve(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), hits, c->d_state[sin].as<PathState>(), so, d_image);
-            c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl);
+            c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
         }
         if (keep) {
             for (int k = plan.nbounce - 1; k >= 0; --k) {
@@ -390,10 +390,14 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     }
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaStreamSynchronize(st));
-    for (size_t i = 0; i + 1 < nev; i += 2) {
-        float ms = 0.f;
-        PB_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
-        c->last_trace_ms += ms;
+    // event pairs: per batch one for the primary kernel, then one per k_trace launch
+    {
+        const size_t per_batch = 2 + 2 * (size_t)(I.kind == PB_INTEG_FIELD ? 0 : plan.nbounce);
+        for (size_t i = 0; i + 1 < nev; i += 2) {
+            float ms = 0.f;
+            PB_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
+            if (i % per_batch == 0) c->last_primary_ms += ms; else c->last_trace_ms += ms;
+        }
     }
     if (mode != MODE_VJP) c->sampler_offset[0] = base + plan.draws;
 }
@@ -436,7 +440,7 @@ int pb_ctx_destroy(pb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
@@ -604,7 +608,7 @@ int pb_trace(pb_ctx *c, int64_t n, const float *d_rays, void *d_hits, float *d_t
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaStreamSynchronize(c->stream));
         PB_CUDA(cudaEventElapsedTime(&c->last_trace_ms, e0, e1));
-        c->launches++; c->last_rays = n;
+        c->launches++; c->last_rays = n; c->last_trace_launches = 1; c->last_primary_ms = 0.f;
     });
 }
 int pb_render_c(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
@@ -665,5 +669,15 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
 int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }
 float pb_stats_last_trace_ms(pb_ctx *c) { return c->last_trace_ms; }
 int64_t pb_stats_last_rays(pb_ctx *c) { return c->last_rays; }
+float pb_stats_last_primary_ms(pb_ctx *c) { return c->last_primary_ms; }
+int pb_stats_last_trace_launches(pb_ctx *c) { return c->last_trace_launches; }
+int pb_ctx_set_stream(pb_ctx *c, void *stream) {
+    return guard(c, [&] {
+        PB_CUDA(cudaSetDevice(c->device));
+        PB_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+        c->stream = reinterpret_cast<cudaStream_t>(stream);
+    });
+}
 
 }  // extern "C"

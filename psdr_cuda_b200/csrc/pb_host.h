@@ -117,6 +117,8 @@ struct pb_ctx {
     std::vector<pb::GradSegment> grad_segments;
     // stats
     int64_t launches = 0, last_rays = 0;
-    float last_trace_ms = 0.f;
+    float last_trace_ms = 0.f, last_primary_ms = 0.f;
+    int last_trace_launches = 0;
+    bool own_stream = true;
     std::vector<cudaEvent_t> ev_pool;
 };

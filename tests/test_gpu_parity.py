@@ -1,0 +1,273 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and — at BASELINE.json's full size — through
+size-independent properties. Tolerances: indices / hit records bit-exact; images per-pixel L1 <= 1e-4 (BASELINE.json);
+gradients rtol 1e-3."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, scene_path
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLDEN, "cbox_bunny_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def desc():
+    from psdr_cuda_b200 import scene_io
+    return scene_io.load_scene_description(scene_path("cbox_bunny"))
+
+
+def make_ctx(desc, opts, grads=False):
+    from psdr_cuda_b200 import capi
+    ctx = capi.Context(0)
+    ctx.load_description(desc, opts)
+    if grads:
+        for b in range(len(desc["bsdfs"])):
+            ctx.grad_require(capi.PARAM_BSDF_TEXTURE, b, "reflectance")
+    ctx.configure()
+    return ctx
+
+
+def pixel_l1(a, b):
+    return np.abs(a - b).mean(axis=1)
+
+
+def test_extension_is_loaded_and_launches_kernels(desc):
+    from psdr_cuda_b200 import capi
+    ctx = make_ctx(desc, dict(width=16, height=16, spp=2, sppe=0, sppse=0))
+    before = ctx.stats()["launches"]
+    ctx.render_c(capi.make_integrator("direct"))
+    assert ctx.stats()["launches"] - before == 4          # primary, shade, trace, resolve
+    maps = open("/proc/self/maps").read()
+    assert "libpsdr_b200.so" in maps
+
+
+def test_configure_tables_bit_exact(desc, golden):
+    from oracle import orc
+    opts = dict(width=32, height=32, spp=4, sppe=0, sppse=0)
+    ctx = make_ctx(desc, opts)
+    osc = orc.Scene(orc.load_scene_description(scene_path("cbox_bunny")), opts)
+    osc.configure()
+    ti = ctx.triangle_info()
+    assert np.array_equal(ti.view(np.uint32), osc.triangle_info().view(np.uint32))
+    assert np.array_equal(ti[:8], golden["tri_info_first"]) and np.array_equal(ti[-8:], golden["tri_info_last"])
+    for m in range(7):
+        assert np.array_equal(ctx.mesh_edges(m), osc.mesh_edges(m))
+
+
+def test_trace_bit_exact_vs_golden_and_oracle(desc, golden):
+    from oracle import orc
+    opts = dict(width=32, height=32, spp=4, sppe=0, sppse=0)
+    ctx = make_ctx(desc, opts)
+    n = len(golden["trace_o"])
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, :3] = golden["trace_o"]; rays[:, 3] = np.inf; rays[:, 4:7] = golden["trace_d"]
+    hits, t = ctx.trace(torch.from_numpy(rays).cuda())
+    hits, t = hits.cpu().numpy(), t.cpu().numpy()
+    assert np.array_equal(hits[:, 0], golden["trace_tri"]) and np.array_equal(hits[:, 1], golden["trace_shape"])
+    assert np.array_equal(hits[:, 2].view(np.uint32), golden["trace_u"].view(np.uint32))
+    assert np.array_equal(hits[:, 3].view(np.uint32), golden["trace_v"].view(np.uint32))
+    assert np.array_equal(t.view(np.uint32), golden["trace_t"].view(np.uint32))
+    # edge cases: inactive lanes (tmax < 0) and finite tmax, empty launch
+    rays2 = rays.copy(); rays2[::2, 3] = -1.0; rays2[1::2, 3] = 60.0
+    h2, t2 = ctx.trace(torch.from_numpy(rays2).cuda())
+    h2, t2 = h2.cpu().numpy(), t2.cpu().numpy()
+    assert np.all(h2[::2, 0] == -1)
+    want = (golden["trace_tri"][1::2] >= 0) & (golden["trace_t"][1::2] < 60.0)
+    assert np.array_equal(h2[1::2, 0] >= 0, want)
+    h0, _ = ctx.trace(torch.zeros((0, 8), dtype=torch.float32, device="cuda"))
+    assert h0.shape[0] == 0
+    # a larger random set against the live oracle
+    osc = orc.Scene(orc.load_scene_description(scene_path("cbox_bunny")), opts)
+    osc.configure()
+    rng = np.random.default_rng(5)
+    m = 100000
+    o = np.stack([rng.uniform(-99, 99, m), rng.uniform(1, 199, m), rng.uniform(-99, 199, m)], 1).astype(np.float32)
+    d = rng.normal(size=(m, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[:100, 0] = 0.0                                   # axis-parallel components exercise the slab test's 1/0 handling
+    r = np.zeros((m, 8), np.float32); r[:, :3] = o; r[:, 3] = np.inf; r[:, 4:7] = d
+    hg, tg = ctx.trace(torch.from_numpy(r).cuda())
+    tri, shape, u, v, t = osc.trace(o, d)
+    hg = hg.cpu().numpy()
+    assert np.array_equal(hg[:, 0], tri) and np.array_equal(hg[:, 1], shape)
+    assert np.array_equal(hg[:, 2].view(np.uint32), u.view(np.uint32)) and np.array_equal(tg.cpu().numpy().view(np.uint32), t.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,kind,kw", [("direct11", "direct", dict(bsdf_samples=1, light_samples=1)), ("direct21", "direct", dict(bsdf_samples=2, light_samples=1)),
+                                          ("path3", "path", dict(max_depth=3)), ("field_depth", "field", dict(field="depth")), ("field_shn", "field", dict(field="shNormal"))])
+def test_renderC_vs_golden(desc, golden, name, kind, kw):
+    from psdr_cuda_b200 import capi
+    ctx = make_ctx(desc, dict(width=32, height=32, spp=4, sppe=0, sppse=0))
+    integ = capi.make_integrator(kind, **kw)
+    a = ctx.render_c(integ).cpu().numpy()
+    b = ctx.render_c(integ).cpu().numpy()          # second call continues the streams
+    scale = max(1.0, float(np.abs(golden["renderC_" + name]).max())) if kind == "field" else 1.0   # AOVs (depth ~1e3) are compared relatively
+    assert pixel_l1(a, golden["renderC_" + name]).max() <= 1e-4 * scale
+    assert pixel_l1(b, golden["renderC2_" + name]).max() <= 1e-4 * scale
+    host = np.empty_like(a)
+    ctx.configure(reseed=True)
+    ctx.render_c_host(integ, out=host)
+    assert np.array_equal(host, a)                 # same lanes, same batches -> same atomics order per pixel here
+
+
+def test_cfg1_direct_renderC_vs_oracle(desc):
+    # BASELINE.json configs[0]: DirectIntegrator renderC, cbox, 128x128, 16 spp
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    opts = dict(width=128, height=128, spp=16, sppe=0, sppse=0)
+    ctx = make_ctx(desc, opts)
+    osc = orc.Scene(orc.load_scene_description(scene_path("cbox_bunny")), opts)
+    osc.configure()
+    img = ctx.render_c(capi.make_integrator("direct")).cpu().numpy()
+    ref = orc.DirectIntegrator(1, 1).renderC(osc)
+    err = pixel_l1(img, ref)
+    assert np.mean(err > 1e-4) <= 1e-3, (err.max(), np.mean(err > 1e-4))
+    assert abs(img.mean() - ref.mean()) <= 1e-5 * ref.mean()
+
+
+def test_renderD_and_albedo_vjp_vs_oracle(desc, golden):
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    opts = dict(width=32, height=32, spp=4, sppe=0, sppse=0)
+    ctx = make_ctx(desc, opts, grads=True)
+    integ = capi.make_integrator("path", max_depth=3)
+    img = ctx.render_d(integ)
+    assert pixel_l1(img.cpu().numpy(), golden["renderD_path3"]).max() <= 1e-4
+    rng = np.random.default_rng(12345)
+    dLdI = rng.uniform(-1, 1, size=(32 * 32, 3)).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy()
+    layout = ctx.grad_layout()
+    assert [s["count"] for s in layout] == [3, 3, 3, 3] and ctx.grad_size() == 12
+    # <dLdI, J e_white> from the golden forward-mode image == sum of the three white-albedo gradient entries
+    want = float((dLdI.astype(np.float64) * golden["renderD_path3_dwhite"]).sum())
+    assert abs(g[0:3].sum() - want) <= 1e-3 * abs(want)
+    # full gradient against oracle JVPs, one per parameter
+    odesc = orc.load_scene_description(scene_path("cbox_bunny"))
+    ref = np.zeros(12)
+    for b in range(4):
+        for ch in range(3):
+            osc = orc.Scene(odesc, opts)
+            t = np.zeros((1, 1, 3), np.float32); t[0, 0, ch] = 1
+            osc.set_bsdf_tangent(b, "reflectance", t)
+            osc.configure()
+            ref[3 * b + ch] = float((dLdI.astype(np.float64) * orc.PathIntegrator(3).renderD(osc)[1]).sum())
+    assert np.linalg.norm(g - ref) <= 1e-3 * np.linalg.norm(ref)
+    assert np.all(np.abs(g - ref) <= 1e-3 * np.abs(ref).max())
+    # replaying the VJP gives the same gradient (up to fp32 atomics order); it accumulates into the buffer
+    g2 = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda(), grad=torch.from_numpy(g.copy()).cuda()).cpu().numpy()
+    assert np.allclose(g2, 2 * g, rtol=1e-4, atol=1e-5)
+
+
+def test_bitmap_texture_gradient_matches_oracle():
+    # a textured quad (uv-mapped) lit by a small emitter: exercises Bitmap::eval's bilinear taps and their scatter
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    rng = np.random.default_rng(3)
+    tex = rng.uniform(0.2, 0.9, size=(5, 7, 3)).astype(np.float32)
+    quad = dict(verts=np.array([[-1, 0, -1], [-1, 0, 1], [1, 0, 1], [1, 0, -1]], np.float32) * 2, faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                uvs=np.array([[0.05, 0.1], [0.1, 0.9], [0.95, 0.85], [0.9, 0.05]], np.float32), uv_faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                bsdf=0, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    light = dict(verts=np.array([[-.5, 3, -.5], [.5, 3, -.5], [.5, 3, .5], [-.5, 3, .5]], np.float32), faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                 bsdf=1, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    cam = orc.m_look_at(np.array([0, 4, 6], np.float32), np.array([0, 0, 0], np.float32), np.array([0, 1, 0], np.float32))
+    d = dict(opts=dict(width=24, height=24, spp=4, sppe=0, sppse=0), sensors=[dict(fov=40.0, near=0.1, far=1e4, to_world=cam)],
+             bsdfs=[dict(type=0, id="t", reflectance=tex), dict(type=0, id="k", reflectance=np.zeros((1, 1, 3), np.float32))],
+             meshes=[quad, light], emitters=[dict(mesh=1, radiance=np.array([30, 25, 20], np.float32))], envmap=None)
+    ctx = capi.Context(0)
+    ctx.load_description(d)
+    ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "reflectance")
+    ctx.configure()
+    integ = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+    osc = orc.Scene(d); osc.configure()
+    img = ctx.render_d(integ).cpu().numpy()
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().reshape(tex.shape)
+    ref_img, _ = orc.DirectIntegrator(1, 1).renderD(osc)
+    assert pixel_l1(img, ref_img).max() <= 1e-4
+    # directional derivatives for a few random texture directions
+    for k in range(3):
+        tdir = rng.normal(size=tex.shape).astype(np.float32)
+        o2 = orc.Scene(d); o2.set_bsdf_tangent(0, "reflectance", tdir); o2.configure()
+        _, dimg = orc.DirectIntegrator(1, 1).renderD(o2)
+        want = float((dLdI.astype(np.float64) * dimg).sum())
+        got = float((g.astype(np.float64) * tdir).sum())
+        assert abs(got - want) <= 1e-3 * max(abs(want), 1e-3), (got, want)
+
+
+def test_sample_shards_sum_to_the_full_image(desc):
+    from psdr_cuda_b200 import capi
+    opts = dict(width=64, height=64, spp=8, sppe=0, sppse=0)
+    integ = capi.make_integrator("path", max_depth=2)
+    full = make_ctx(desc, opts, grads=True)
+    img = full.render_d(integ)
+    dLdI = torch.ones_like(img)
+    g = full.render_d_vjp(integ, dLdI).cpu().numpy()
+    acc, gacc = np.zeros((64 * 64, 3), np.float32), np.zeros(12, np.float32)
+    for r in range(3):
+        ctx = capi.Context(0)
+        ctx.load_description(desc, opts)
+        for b in range(4):
+            ctx.grad_require(capi.PARAM_BSDF_TEXTURE, b, "reflectance")
+        ctx.set_shard(r, 3)
+        ctx.configure()
+        acc += ctx.render_d(integ).cpu().numpy()
+        gacc += ctx.render_d_vjp(integ, dLdI).cpu().numpy()
+    assert pixel_l1(acc, img.cpu().numpy()).max() <= 1e-5
+    assert np.allclose(gacc, g, rtol=1e-4, atol=1e-4)
+
+
+def test_full_size_properties(desc):
+    # BASELINE.json configs[1] size (512x512 / 256 spp): batch-size invariance, linearity in the emitter radiance,
+    # gradient = image/albedo identity for a path of depth 1 restricted to one wall colour
+    from psdr_cuda_b200 import capi
+    opts = dict(width=512, height=512, spp=256, sppe=0, sppse=0)
+    integ = capi.make_integrator("direct")
+    ctx = make_ctx(desc, opts, grads=True)
+    a = ctx.render_c(integ)
+    ctx.set_batch(1 << 18)
+    ctx.configure(reseed=True)
+    b = ctx.render_c(integ)
+    assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max())
+    assert bool(torch.isfinite(a).all()) and float(a.min()) >= 0.0
+    # doubling the radiance doubles the image exactly (same paths, power-of-two scale)
+    import copy
+    d2 = copy.deepcopy(desc)
+    d2["emitters"][0]["radiance"] = d2["emitters"][0]["radiance"] * 2
+    ctx2 = make_ctx(d2, opts)
+    ctx2.set_batch(1 << 18)
+    c = ctx2.render_c(integ)
+    assert float((c - 2 * b).abs().max()) <= 1e-5 * float(c.abs().max())
+    # Direct(1,1): every non-emitted term carries exactly one albedo factor of the first hit, so
+    # sum_k albedo_k * dI/dalbedo_k == I - Le  (Euler's identity for a degree-1 homogeneous function)
+    ctx.configure(reseed=True)
+    img = ctx.render_d(integ)
+    dLdI = torch.ones_like(img)
+    g = ctx.render_d_vjp(integ, dLdI).cpu().numpy()
+    albedo = np.concatenate([bs["reflectance"].reshape(3) for bs in desc["bsdfs"]])
+    hide = capi.make_integrator("direct", hide_emitters=True)
+    ctx.configure(reseed=True)
+    no_le = ctx.render_c(hide)
+    assert abs(float((g * albedo).sum()) - float(no_le.double().sum())) <= 2e-3 * float(no_le.double().sum())
+
+
+def test_errors_surface_as_runtime_error(desc):
+    from psdr_cuda_b200 import capi
+    ctx = capi.Context(0)
+    ctx.load_description(desc, dict(width=8, height=8, spp=1, sppe=0, sppse=0))
+    with pytest.raises(RuntimeError, match="must be configured"):
+        ctx.render_c(capi.make_integrator("direct"))
+    ctx.configure()
+    with pytest.raises(RuntimeError, match="Invalid sensor id"):
+        ctx.render_c(capi.make_integrator("direct"), sensor=3)
+    with pytest.raises(RuntimeError, match="preceding pb_render_d"):
+        ctx.render_d_vjp(capi.make_integrator("direct"), torch.ones((64, 3), device="cuda"))
+    with pytest.raises(RuntimeError):
+        ctx.add_mesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 5]], np.int32))
