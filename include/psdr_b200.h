@@ -56,6 +56,10 @@ int pb_ctx_set_batch(pb_ctx *ctx, int64_t lanes);
  * (lane ranges for the edge terms). RNG streams stay indexed by the global lane id, so the sum of the shards' images
  * equals the single-GPU image up to fp32 summation order. Default (0, 1). */
 int pb_ctx_set_shard(pb_ctx *ctx, int rank, int world);
+/* pb_render_d keeps every event's hit records / vertex positions / throughputs of the whole shard (352 B per lane for a
+ * depth-5 path) when they fit in `bytes` (default 64 GiB of the 180 GB HBM3e), so that pb_render_d_vjp runs only the
+ * adjoint kernels; otherwise the VJP re-traces the forward pass batch by batch. 0 disables retention. */
+int pb_ctx_set_retain_limit(pb_ctx *ctx, int64_t bytes);
 /* run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream) instead of the context's own */
 int pb_ctx_set_stream(pb_ctx *ctx, void *cuda_stream);
 
@@ -119,6 +123,10 @@ float pb_stats_last_trace_ms(pb_ctx *ctx);
 int64_t pb_stats_last_rays(pb_ctx *ctx);
 int pb_stats_last_trace_launches(pb_ctx *ctx);
 float pb_stats_last_primary_ms(pb_ctx *ctx);
+
+/* ---- debugging / tuning hooks (not part of the reference surface) ---------------------------------------------- */
+int pb_debug_set(pb_ctx *ctx, const char *key, int64_t value);                         /* "trace_variant": 0..3 */
+int pb_debug_ray_buffer(pb_ctx *ctx, int event, void **d_rays, int64_t *bytes);        /* rays kept by the last VJP batch */
 
 #ifdef __cplusplus
 }

@@ -20,12 +20,13 @@ MESH_FACE_NORMALS, MESH_ENABLE_EDGES = 1, 2
 PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES = 0, 1
 
 SYMBOLS = [
-    "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream",
+    "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream", "pb_ctx_set_retain_limit",
     "pb_scene_set_options", "pb_scene_add_sensor", "pb_scene_set_sensor_transform", "pb_scene_add_bsdf", "pb_scene_set_bsdf_texture",
     "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
+    "pb_debug_set", "pb_debug_ray_buffer",
 ]
 
 
@@ -112,6 +113,9 @@ class Context:
 
     def set_batch(self, lanes):
         self._chk(lib().pb_ctx_set_batch(self.h, C.c_int64(lanes)))
+
+    def set_retain_limit(self, nbytes):
+        self._chk(lib().pb_ctx_set_retain_limit(self.h, C.c_int64(nbytes)))
 
     def set_stream(self, cuda_stream):
         """run on the caller's stream (int handle, e.g. torch.cuda.current_stream().cuda_stream; 0 = legacy default)"""
@@ -237,6 +241,14 @@ class Context:
             grad = torch.zeros(max(1, self.grad_size()), dtype=torch.float32, device=dLdI.device)
         self._chk(lib().pb_render_d_vjp(self.h, C.byref(integ), sensor, _dp(dLdI.contiguous()), _dp(grad)))
         return grad
+
+    def debug_set(self, key, value):
+        self._chk(lib().pb_debug_set(self.h, key.encode(), C.c_int64(value)))
+
+    def debug_ray_buffer(self, event):
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._chk(lib().pb_debug_ray_buffer(self.h, event, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
 
     # --- stats -------------------------------------------------------------------------------------------------
     def stats(self):

@@ -76,12 +76,10 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, floa
     }
 }
 
-// adjoint of one scattering event (texture parameters). state_k: T_k and nothing else is read from it; suffix: S_{k+1}
-// in, S_k out; final_state.rad: the lane's forward radiance (decides which channels integrator.cpp:87 zeroed).
-__global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
-                                                 const HitRec *__restrict__ hits, const PathState *__restrict__ state_k,
-                                                 const PathState *__restrict__ final_state, float4 *__restrict__ suffix,
-                                                 const float *__restrict__ dLdI) {
+// adjoint of one scattering event (texture parameters). E.thr_in: T_k; suffix: S_{k+1} in, S_k out; E.rad: the lane's
+// final forward radiance (decides which channels integrator.cpp:87 zeroed).
+__global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
+    const HitRec *__restrict__ hits = E.hits;
     __shared__ float s_acc[kMaxConstBsdf * 3];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float3 acc = f3(0.f);
@@ -89,17 +87,17 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
     if (i < P.n) {
         int pix;
         const long long lane = global_lane(P, i, pix);
-        const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
+        const Vertex v = load_vertex(P, B, i, E);
         const Its &its = v.its;
         bsdf_id = v.bsdf ? (int)(v.bsdf - P.S.bsdfs) : -1;
         // loss adjoint of this lane's radiance
-        const float3 rad_final = f3(ldg4(reinterpret_cast<const float4 *>(final_state + i) + 1));
+        const float3 rad_final = f3(ldg4(E.rad + i));
         float3 g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
         if (!isfinite(rad_final.x)) g.x = 0.f;
         if (!isfinite(rad_final.y)) g.y = 0.f;
         if (!isfinite(rad_final.z)) g.z = 0.f;
         float3 T = f3(1.f);
-        if (B.depth > 0) T = f3(ldg4(reinterpret_cast<const float4 *>(state_k + i)));
+        if (B.depth > 0) T = f3(ldg4(E.thr_in + i));
         const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
         const float3 gL = g * T, gw = gL * S_next;
         Rng rng((uint64_t)lane, B.jump);
@@ -168,9 +166,8 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
-void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, const HitRec *hits,
-                    const PathState *state_k, const PathState *final_state, float4 *suffix, const float *dLdI) {
-    if (P.n > 0) k_adjoint<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, hits, state_k, final_state, suffix, dLdI);
+void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI) {
+    if (P.n > 0) k_adjoint<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E, suffix, dLdI);
 }
 
 }  // namespace pb

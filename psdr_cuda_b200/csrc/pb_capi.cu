@@ -278,6 +278,7 @@ static void configure(pb_ctx *c) {
         }
     c->ready = true;
     c->have_last_d = false;
+    c->retained_valid = false;
 }
 
 struct Plan { int nbounce, nb, nl, draws; };
@@ -299,8 +300,22 @@ static Plan make_plan(const pb_integrator &I) {
 
 enum Mode { MODE_C = 0, MODE_D = 1, MODE_VJP = 2 };
 
-// interior term: integrator.cpp:64-95 over this shard's samples, in batches. MODE_VJP replays the last renderD
-// (same stream positions), keeps every event's records and then runs the adjoint kernels in reverse event order.
+static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t ray_lanes) {
+    if ((int)S.pos.size() < nslots) { S.pos.resize(nslots); S.hits.resize(nslots); }
+    if ((int)S.thr.size() < nslots + 1) S.thr.resize(nslots + 1);
+    S.hit0.reserve((size_t)lanes * sizeof(HitRec));
+    S.rad.reserve((size_t)lanes * sizeof(float4));
+    S.rays.reserve((size_t)ray_lanes * R * sizeof(RayRec));
+    for (int k = 0; k < nslots; ++k) { S.pos[k].reserve((size_t)lanes * sizeof(float4)); S.hits[k].reserve((size_t)lanes * R * sizeof(HitRec)); }
+    for (int k = 0; k < nslots + 1; ++k) S.thr[k].reserve((size_t)lanes * sizeof(float4));
+}
+
+// interior term: integrator.cpp:64-95 over this shard's samples, in batches.
+//   MODE_C / MODE_D   forward render (renderC's / renderD's formulation of the primal). MODE_D additionally retains every
+//                     event's hit records, vertex positions and throughputs for the whole shard when they fit
+//                     pb_ctx_set_retain_limit (352 B per lane for a depth-5 path), so that the VJP needs no re-tracing.
+//   MODE_VJP          adjoint kernels in reverse event order over the retained records; if nothing was retained the
+//                     forward pass is replayed batch by batch first (same stream positions as the last renderD).
 static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float *d_image, Mode mode, const float *d_dLdI = nullptr,
                             float *d_grad = nullptr) {
     PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
@@ -314,6 +329,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     const int spp_local = s1 - s0;
     const Plan plan = make_plan(I);
     const uint64_t base = (mode == MODE_VJP) ? c->last_d_offset : c->sampler_offset[0];
+    if (mode == MODE_D) c->retained_valid = false;
     if (c->spp <= 0 || spp_local <= 0) {
         PB_CUDA(cudaStreamSynchronize(st));
         if (mode != MODE_VJP && c->spp > 0) c->sampler_offset[0] = base + plan.draws;
@@ -323,20 +339,28 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     const int64_t total = npix * spp_local;
     const int R = std::max(1, plan.nb + plan.nl);
     const int64_t B = std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024);
-    const bool keep = (mode == MODE_VJP);
-    const int nbuf = keep ? std::max(1, plan.nbounce) : 2;
-    if ((int)c->d_rays.size() < nbuf) { c->d_rays.resize(nbuf); c->d_hits.resize(nbuf); }
-    if ((int)c->d_state.size() < nbuf + 1) c->d_state.resize(nbuf + 1);
-    c->d_hit0.reserve((size_t)B * sizeof(HitRec));
-    for (int k = 0; k < nbuf; ++k) { c->d_rays[k].reserve((size_t)B * R * sizeof(RayRec)); c->d_hits[k].reserve((size_t)B * R * sizeof(HitRec)); }
-    for (int k = 0; k < nbuf + 1; ++k) c->d_state[k].reserve((size_t)B * sizeof(PathState));
-    if (keep) c->d_suffix.reserve((size_t)B * sizeof(float4));
+    const int D = std::max(1, plan.nbounce);
+    const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (16 + 16 * R + 16));
+    const bool field = (I.kind == PB_INTEG_FIELD);
+    // which store, and whether the forward pass has to run
+    bool use_retained = false, run_forward = true;
+    if (mode == MODE_D && !field && !c->grad_segments.empty() && retain_bytes <= c->retain_limit) use_retained = true;
+    if (mode == MODE_VJP) {
+        if (c->retained_valid && c->retained_kind == I.kind && c->retained_nb == plan.nb && c->retained_nl == plan.nl &&
+            c->retained_nbounce == plan.nbounce && c->retained_sensor == sensor && c->retained_hide == I.hide_emitters) {
+            use_retained = true; run_forward = false;
+        }
+    }
+    const bool keep = use_retained || mode == MODE_VJP;   // every event has its own slot
+    EventStore &S = use_retained ? c->retained : c->scratch;
+    size_store(S, use_retained ? total : B, keep ? D : 2, R, B);
+    if (mode == MODE_VJP) c->d_suffix.reserve((size_t)B * sizeof(float4));
     RenderParams P;
     P.S = c->view; P.cam = c->sensors[sensor].rec;
     P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
     P.spp_local = spp_local; P.s0 = s0;
     P.jump0 = make_jump(base);
-    if (keep) {   // BSDF table whose textures point at their gradient segments
+    if (mode == MODE_VJP) {   // BSDF table whose textures point at their gradient segments
         std::vector<BsdfRec> br(c->bsdfs.size());
         PB_CUDA(cudaMemcpyAsync(br.data(), c->d_bsdfs.p, br.size() * sizeof(BsdfRec), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
@@ -345,45 +369,55 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         c->d_bsdfs_grad.upload(br, st);
         P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
     }
+    std::vector<BounceParams> bps(plan.nbounce);
+    for (int k = 0; k < plan.nbounce; ++k) {
+        BounceParams &Bp = bps[k];
+        Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
+        Bp.hide_emitters = I.hide_emitters; Bp.ad = (mode == MODE_C) ? 0 : 1;
+        Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
+    }
     size_t nev = 0;
     for (int64_t start = 0; start < total; start += B) {
         P.local0 = start; P.n = (int)std::min<int64_t>(B, total - start);
-        cudaEvent_t e0 = get_event(c, nev++), e1 = get_event(c, nev++);
-        PB_CUDA(cudaEventRecord(e0, st));
-        launch_primary(st, P, c->d_hit0.as<HitRec>());
-        PB_CUDA(cudaEventRecord(e1, st));
-        c->launches++;
-        if (I.kind == PB_INTEG_FIELD) {
-            if (mode != MODE_VJP) { launch_field(st, P, I.field, c->d_hit0.as<HitRec>(), d_image); c->launches++; }
-            continue;
+        const size_t off = use_retained ? (size_t)start : 0;
+        HitRec *hit0 = S.hit0.as<HitRec>() + off;
+        auto event = [&](int k) {
+            const int sl = keep ? k : (k & 1), sp = keep ? k - 1 : ((k - 1) & 1);
+            EventBuffers E;
+            E.hit_cur = (k == 0) ? hit0 : S.hits[sp].as<HitRec>() + off * R;
+            E.prev_pos = (k == 0) ? nullptr : S.pos[sp].as<float4>() + off;
+            E.pos = S.pos[sl].as<float4>() + off;
+            E.rays = S.rays.as<RayRec>();
+            E.hits = S.hits[sl].as<HitRec>() + off * R;
+            E.thr_in = (k == 0) ? nullptr : S.thr[keep ? k : (k & 1)].as<float4>() + off;
+            E.thr_out = bps[k].last ? nullptr : S.thr[keep ? k + 1 : ((k + 1) & 1)].as<float4>() + off;
+            E.rad = S.rad.as<float4>() + off;
+            return E;
+        };
+        if (run_forward) {
+            cudaEvent_t e0 = get_event(c, nev++), e1 = get_event(c, nev++);
+            PB_CUDA(cudaEventRecord(e0, st));
+            launch_primary(st, P, hit0);
+            PB_CUDA(cudaEventRecord(e1, st));
+            c->launches++;
+            if (field) {
+                if (mode != MODE_VJP) { launch_field(st, P, I.field, hit0, d_image); c->launches++; }
+                continue;
+            }
+            for (int k = 0; k < plan.nbounce; ++k) {
+                const EventBuffers E = event(k);
+                launch_shade(st, P, bps[k], E);
+                cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
+                PB_CUDA(cudaEventRecord(t0, st));
+                launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr);
+                PB_CUDA(cudaEventRecord(t1, st));
+                launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
+                c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
+            }
         }
-        std::vector<BounceParams> bps(plan.nbounce);
-        for (int k = 0; k < plan.nbounce; ++k) {
-            BounceParams &Bp = bps[k];
-            Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
-            Bp.hide_emitters = I.hide_emitters; Bp.ad = (mode == MODE_C) ? 0 : 1;
-            Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
-        }
-        auto hit_cur_of = [&](int k) { return k == 0 ? c->d_hit0.as<HitRec>() : c->d_hits[keep ? k - 1 : (k - 1) & 1].as<HitRec>(); };
-        auto prev_rays_of = [&](int k) { return k == 0 ? (const RayRec *)nullptr : c->d_rays[keep ? k - 1 : (k - 1) & 1].as<RayRec>(); };
-        for (int k = 0; k < plan.nbounce; ++k) {
-            const int slot = keep ? k : (k & 1);
-            RayRec *rays = c->d_rays[slot].as<RayRec>();
-            HitRec *hits = c->d_hits[slot].as<HitRec>();
-            launch_shade(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), rays);
-            cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
-            PB_CUDA(cudaEventRecord(t0, st));
-            launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), rays, hits, nullptr);
-            PB_CUDA(cudaEventRecord(t1, st));
-            const int sin = keep ? k : (k & 1), sout = keep ? k + 1 : ((k + 1) & 1);
-            PathState *so = (bps[k].last && !keep) ? nullptr : c->d_state[sout].as<PathState>();
-            launch_resolve(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), hits, c->d_state[sin].as<PathState>(), so, d_image);
-            c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
-        }
-        if (keep) {
+        if (mode == MODE_VJP) {
             for (int k = plan.nbounce - 1; k >= 0; --k) {
-                launch_adjoint(st, P, bps[k], hit_cur_of(k), prev_rays_of(k), c->d_hits[k].as<HitRec>(), c->d_state[k].as<PathState>(),
-                               c->d_state[plan.nbounce].as<PathState>(), c->d_suffix.as<float4>(), d_dLdI);
+                launch_adjoint(st, P, bps[k], event(k), c->d_suffix.as<float4>(), d_dLdI);
                 c->launches++;
             }
         }
@@ -392,12 +426,16 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     PB_CUDA(cudaStreamSynchronize(st));
     // event pairs: per batch one for the primary kernel, then one per k_trace launch
     {
-        const size_t per_batch = 2 + 2 * (size_t)(I.kind == PB_INTEG_FIELD ? 0 : plan.nbounce);
+        const size_t per_batch = 2 + 2 * (size_t)(field ? 0 : plan.nbounce);
         for (size_t i = 0; i + 1 < nev; i += 2) {
             float ms = 0.f;
             PB_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
             if (i % per_batch == 0) c->last_primary_ms += ms; else c->last_trace_ms += ms;
         }
+    }
+    if (mode == MODE_D && use_retained) {
+        c->retained_valid = true; c->retained_kind = I.kind; c->retained_nb = plan.nb; c->retained_nl = plan.nl;
+        c->retained_nbounce = plan.nbounce; c->retained_sensor = sensor; c->retained_hide = I.hide_emitters;
     }
     if (mode != MODE_VJP) c->sampler_offset[0] = base + plan.draws;
 }
@@ -666,6 +704,22 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
     });
 }
 
+int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
+    return guard(c, [&] {
+        if (std::strcmp(key, "trace_variant") == 0) pb::g_trace_variant = (int)value;
+        else if (std::strcmp(key, "trace_blocks_per_sm") == 0) pb::g_trace_blocks_per_sm = (int)value;
+        else throw Error(std::string("Unknown debug key: ") + key);
+    });
+}
+/* scratch ray buffer (the rays of the last event traced by the last batch): (nb+nl)*n RayRecs */
+int pb_debug_ray_buffer(pb_ctx *c, int event, void **d_rays, int64_t *bytes) {
+    return guard(c, [&] {
+        (void)event;
+        EventStore &S = c->retained_valid ? c->retained : c->scratch;
+        *d_rays = S.rays.p; *bytes = (int64_t)S.rays.bytes;
+    });
+}
+int pb_ctx_set_retain_limit(pb_ctx *c, int64_t bytes) { c->retain_limit = bytes; c->retained_valid = false; return 0; }
 int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }
 float pb_stats_last_trace_ms(pb_ctx *c) { return c->last_trace_ms; }
 int64_t pb_stats_last_rays(pb_ctx *c) { return c->last_rays; }

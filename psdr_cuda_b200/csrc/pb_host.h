@@ -82,6 +82,11 @@ struct HostSensor {
     SensorRec rec;
 };
 struct GradSegment { int kind, id, slot; int64_t offset, count; };
+// per-event wavefront records, either one batch worth (scratch) or the whole shard (retained for the VJP)
+struct EventStore {
+    DevBuf hit0, rad, rays;
+    std::vector<DevBuf> pos, hits, thr;
+};
 
 }  // namespace pb
 
@@ -109,8 +114,11 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_hit0, d_suffix, d_bsdfs_grad;
-    std::vector<pb::DevBuf> d_rays, d_hits, d_state;
+    pb::DevBuf d_suffix, d_bsdfs_grad;
+    pb::EventStore scratch, retained;
+    int64_t retain_limit = (int64_t)64 << 30;
+    bool retained_valid = false;
+    int retained_kind = 0, retained_nb = 0, retained_nl = 0, retained_nbounce = 0, retained_sensor = 0, retained_hide = 0;
     // replay info of the last renderD
     uint64_t last_d_offset = 0;
     bool have_last_d = false;

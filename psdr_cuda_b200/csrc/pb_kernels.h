@@ -30,20 +30,30 @@ struct RenderParams {
     RngJump jump0;          // stream position of the pixel jitter
 };
 
-struct __align__(16) PathState { float4 thr, rad; };
+// device buffers of one scattering event for one batch of n lanes (R = nb + nl rays per lane)
+struct EventBuffers {
+    const HitRec *hit_cur;   // [n]   hit that created this event's vertex
+    const float4 *prev_pos;  // [n]   position of the previous vertex (origin of the ray that found hit_cur); unused at depth 0
+    float4 *pos;             // [n]   this vertex' position, written by k_shade
+    RayRec *rays;            // [R*n] rays of this event (scratch, ray j of lane i at j*n + i)
+    HitRec *hits;            // [R*n] their hits
+    const float4 *thr_in;    // [n]   throughput T_k (.w != 0: the path is dead); unused at depth 0
+    float4 *thr_out;         // [n]   T_{k+1}; may be null on the last event
+    float4 *rad;             // [n]   radiance accumulated so far (in/out)
+};
 
 void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
                             const int *faces, const int *csr_off, const int *csr_face, const float *uvs, const int *uv_faces, float *vworld,
                             float4 *fcross, float *vnormal, TriRec *tri, float *face_area);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
+extern int g_trace_blocks_per_sm;
+extern int g_trace_variant;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
-void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, RayRec *rays_out);
-void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays,
-                    const HitRec *hits, const PathState *state_in, PathState *state_out, float *film);
-void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, const HitRec *hits,
-                    const PathState *state_k, const PathState *final_state, float4 *suffix, const float *dLdI);
+void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
+void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);
+void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI);
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film);
 
 }  // namespace pb

@@ -6,6 +6,8 @@
 // (src/integrator/direct.cpp:47-163) as a fixed pipeline over RayRec/HitRec wavefront buffers. The sampler is
 // stateless: every kernel re-derives the lane's PCG32 stream from the global lane id and jumps to the position the
 // reference's lock-step wavefront would be at, so no RNG state is stored and a render can be replayed.
+#include <algorithm>
+
 #include "pb_kernels.h"
 #include "pb_shade.cuh"
 #include "pb_trace.cuh"
@@ -22,6 +24,149 @@ __global__ void __launch_bounds__(128) k_trace(const BvhNode *__restrict__ nodes
     const Hit h = trace_closest(nodes, leaf, f3(a), f3(b), a.w);
     reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
     if (t_out) t_out[i] = h.t;
+}
+
+__global__ void __launch_bounds__(128) k_trace_ww(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
+                                                  const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = ldg4(rp), b = ldg4(rp + 1);
+    const Hit h = trace_closest_ww(nodes, leaf, f3(a), f3(b), a.w);
+    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    if (t_out) t_out[i] = h.t;
+}
+
+// Block-local regrouping: the 256 rays of a block are counting-sorted in shared memory by (active, direction bin) so
+// that each warp traverses rays that point the same way and inactive lanes collect in warps that exit at once.
+// Only the thread<->ray assignment changes; every ray's hit is written back to its own slot.
+template <bool WW>
+__global__ void __launch_bounds__(256) k_trace_sorted(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
+                                                      const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
+    constexpr int NB = 65;   // 64 direction bins + inactive
+    __shared__ int s_count[NB + 1];
+    __shared__ float4 s_ray[2][256];
+    __shared__ unsigned short s_src[256];
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * 256;
+    const long long i = base + tid;
+    if (tid < NB + 1) s_count[tid] = 0;
+    __syncthreads();
+    float4 a = make_float4(0.f, 0.f, 0.f, -1.f), b = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (i < n) { const float4 *rp = reinterpret_cast<const float4 *>(rays + i); a = ldg4(rp); b = ldg4(rp + 1); }
+    const int key = (a.w > 0.f) ? direction_bin(f3(b)) : 64;
+    const int rank = atomicAdd(&s_count[key], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < NB; ++k) { const int c = s_count[k]; s_count[k] = acc; acc += c; }
+    }
+    __syncthreads();
+    const int pos = s_count[key] + rank;
+    s_ray[0][pos] = a; s_ray[1][pos] = b; s_src[pos] = (unsigned short)tid;
+    __syncthreads();
+    const float4 ra = s_ray[0][tid], rb = s_ray[1][tid];
+    const long long dst = base + s_src[tid];
+    if (dst >= n) return;
+    const Hit h = WW ? trace_closest_ww(nodes, leaf, f3(ra), f3(rb), ra.w) : trace_closest(nodes, leaf, f3(ra), f3(rb), ra.w);
+    reinterpret_cast<float4 *>(hits)[dst] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    if (t_out) t_out[dst] = h.t;
+}
+
+// Persistent traversal with dynamic ray fetch (Aila & Laine 2009): a warp keeps its lanes busy by handing a new ray to
+// every lane whose ray has terminated, as soon as fewer than kFetchThreshold lanes are still traversing. Ray lengths in
+// this workload differ by an order of magnitude (12 wall triangles vs a 69k-triangle bunny), which is what starves the
+// one-ray-per-thread kernels of SIMD lanes.
+constexpr int kFetchThreshold = 20;
+
+__global__ void __launch_bounds__(128) k_trace_dynamic(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
+                                                       const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out,
+                                                       unsigned long long *__restrict__ counter) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float3 o = f3(0.f), d = f3(0.f);
+    float ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
+    Hit best;
+    best.tri = -1; best.shape = -1; best.u = best.v = -1.f; best.t = 0.f;
+    int stack[64];
+    int sp = 0;
+    int node = kTraverseDone;
+    long long ray_idx = -1;
+    while (true) {
+        // retire finished rays and fetch new ones
+        const bool idle = (node == kTraverseDone);
+        if (idle && ray_idx >= 0) {
+            if (best.tri < 0) best.t = INFINITY;
+            reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(__int_as_float(best.tri), __int_as_float(best.shape), best.u, best.v);
+            if (t_out) t_out[ray_idx] = best.t;
+            ray_idx = -1;
+        }
+        const unsigned m = __ballot_sync(full, idle);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(full, base, leader);
+            if (idle) {
+                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
+                if (idx < n) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + idx);
+                    const float4 a = ldg4(rp), b = ldg4(rp + 1);
+                    o = f3(a); d = f3(b); tmax = a.w;
+                    ix = clamp_idir(d.x); iy = clamp_idir(d.y); iz = clamp_idir(d.z);
+                    best.tri = -1; best.shape = -1; best.u = best.v = -1.f; best.t = tmax;
+                    sp = 0;
+                    ray_idx = idx;
+                    node = (tmax > 0.f) ? 0 : kTraverseDone;   // inactive lanes are retired on the next round
+                }
+            }
+        }
+        if (__all_sync(full, ray_idx < 0)) break;
+        while (node != kTraverseDone) {
+            if (node >= 0) {
+                const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+                const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2), l = ldg4(np + 3);
+                float t0, t1;
+                t0 = (a.x - o.x) * ix; t1 = (a.w - o.x) * ix;
+                float ln = fminf(t0, t1), lf = fmaxf(t0, t1);
+                t0 = (a.y - o.y) * iy; t1 = (b.x - o.y) * iy;
+                ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+                t0 = (a.z - o.z) * iz; t1 = (b.y - o.z) * iz;
+                ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+                t0 = (b.z - o.x) * ix; t1 = (c.y - o.x) * ix;
+                float rn = fminf(t0, t1), rf = fmaxf(t0, t1);
+                t0 = (b.w - o.y) * iy; t1 = (c.z - o.y) * iy;
+                rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+                t0 = (c.x - o.z) * iz; t1 = (c.w - o.z) * iz;
+                rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+                const bool hl = fmaxf(ln, 0.f) <= fminf(lf, best.t), hr = fmaxf(rn, 0.f) <= fminf(rf, best.t);
+                int cl = __float_as_int(l.x), cr = __float_as_int(l.y);
+                if (hl && hr) {
+                    if (rn < ln) { int t = cl; cl = cr; cr = t; }
+                    stack[sp++] = cr;
+                    node = cl;
+                } else if (hl) node = cl;
+                else if (hr) node = cr;
+                else node = sp ? stack[--sp] : kTraverseDone;
+            } else {
+                const int v = ~node;
+                const int first = v >> 3, cnt = (v & 7) + 1;
+                for (int i = 0; i < cnt; ++i) {
+                    const float4 *tp = reinterpret_cast<const float4 *>(leaf + first + i);
+                    const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                    float u, w, t;
+                    ray_intersect_triangle(f3(ta), f3(tb), f3(tc), o, d, u, w, t);
+                    const int id = __float_as_int(ta.w);
+                    if (u >= 0.f && w >= 0.f && add_rn(u, w) <= 1.f && t > kRayEpsilon && t < tmax &&
+                        (t < best.t || (t == best.t && (best.tri < 0 || id < best.tri)))) {
+                        best.t = t; best.u = u; best.v = w; best.tri = id; best.shape = __float_as_int(tb.w);
+                    }
+                }
+                node = sp ? stack[--sp] : kTraverseDone;
+            }
+            if (__popc(__activemask()) < kFetchThreshold) break;
+        }
+    }
 }
 
 // integrator.cpp:76-85 + the first ray launch of direct.cpp:48
@@ -41,11 +186,12 @@ __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restr
 }
 
 // sample the connections of one scattering event and emit their rays (direct.cpp:69-76, 120-129)
-__global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
-                                               RayRec *__restrict__ rays_out) {
+__global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, EventBuffers E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
+    RayRec *__restrict__ rays_out = E.rays;
+    const Vertex v = load_vertex(P, B, i, E);
+    E.pos[i] = make_float4(v.its.p.x, v.its.p.y, v.its.p.z, 0.f);
     int pix_unused;
     Rng rng((uint64_t)global_lane(P, i, pix_unused), B.jump);
     for (int j = 0; j < B.nb; ++j) {
@@ -66,16 +212,15 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, c
 }
 
 // direct.cpp:77-113 (BSDF-sampled connections) and 130-158 (emitter-sampled connections) for one scattering event
-__global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B, const HitRec *__restrict__ hit_cur, const RayRec *__restrict__ prev_rays,
-                                                 const HitRec *__restrict__ hits, const PathState *__restrict__ state_in,
-                                                 PathState *__restrict__ state_out, float *__restrict__ film) {
+__global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B, EventBuffers E, float *__restrict__ film) {
+    const HitRec *__restrict__ hits = E.hits;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i < P.n;
     int pix = -1;
     float3 out = f3(0.f);
     if (in_range) {
         const long long lane = global_lane(P, i, pix);
-        const Vertex v = load_vertex(P, B, i, hit_cur, prev_rays);
+        const Vertex v = load_vertex(P, B, i, E);
         const Its &its = v.its;
         Rng rng((uint64_t)lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
@@ -140,17 +285,16 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
         if (B.depth == 0) {
             rad = B.hide_emitters ? f3(0.f) : emitter_Le(P.S, its, its.valid);   // direct.cpp:51
         } else {
-            const float4 *sp = reinterpret_cast<const float4 *>(state_in + i);
-            thr = f3(sp[0]); rad = f3(sp[1]);
+            thr = f3(ldg4(E.thr_in + i)); rad = f3(E.rad[i]);
         }
         rad += thr * L;
         if (B.last) out = zero_nonfinite(rad) * P.inv_spp;   // integrator.cpp:87-91
-        if (state_out) {
-            float4 *sp = reinterpret_cast<float4 *>(state_out + i);
+        if (E.thr_out) {
             const float3 t2 = thr * w_cont;
-            sp[0] = make_float4(t2.x, t2.y, t2.z, 0.f);
-            sp[1] = make_float4(rad.x, rad.y, rad.z, 0.f);
+            const bool dead = !(t2.x != 0.f || t2.y != 0.f || t2.z != 0.f);   // also true when there is no continuation
+            E.thr_out[i] = make_float4(t2.x, t2.y, t2.z, dead ? 1.f : 0.f);
         }
+        if (E.rad) E.rad[i] = make_float4(rad.x, rad.y, rad.z, 0.f);
     }
     if (B.last && film) film_accumulate(film, pix, out);
 }
@@ -180,18 +324,33 @@ __global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const 
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
+int g_trace_blocks_per_sm = 8;
+int g_trace_variant = 4;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out) {
-    if (n > 0) k_trace<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out);
+    if (n <= 0) return;
+    switch (g_trace_variant) {
+        case 0: k_trace<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 1: k_trace_ww<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 2: k_trace_sorted<false><<<nblk(n, 256), 256, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 3: k_trace_sorted<true><<<nblk(n, 256), 256, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        default: {
+            static unsigned long long *counter = nullptr;   // one per process; launches on a stream are ordered
+            if (!counter) cudaMalloc(&counter, sizeof(unsigned long long));
+            cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+            const unsigned blocks = (unsigned)std::min<long long>((n + 127) / 128, 148LL * g_trace_blocks_per_sm);
+            k_trace_dynamic<<<blocks, 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out, counter);
+            break;
+        }
+    }
 }
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0) {
     if (P.n > 0) k_primary<<<nblk(P.n, 128), 128, 0, st>>>(P, hit0);
 }
-void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays, RayRec *rays_out) {
-    if (P.n > 0) k_shade<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, rays_out);
+void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E) {
+    if (P.n > 0) k_shade<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
 }
-void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const HitRec *hit_cur, const RayRec *prev_rays,
-                    const HitRec *hits, const PathState *state_in, PathState *state_out, float *film) {
-    if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, hit_cur, prev_rays, hits, state_in, state_out, film);
+void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film) {
+    if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E, film);
 }
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film) {
     if (P.n > 0) k_field<<<nblk(P.n, 256), 256, 0, st>>>(P, field, hit0, film);

@@ -23,7 +23,7 @@ template <int STACK = 64>
 PB_D Hit trace_closest(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, float3 o, float3 d, float tmax) {
     Hit best;
     best.tri = -1; best.shape = -1; best.u = -1.f; best.v = -1.f; best.t = tmax;
-    if (!(tmax > 0.f)) return best;
+    if (!(tmax > 0.f)) { best.t = INFINITY; return best; }
     const float ix = clamp_idir(d.x), iy = clamp_idir(d.y), iz = clamp_idir(d.z);
     int stack[STACK];
     int sp = 0;
@@ -75,6 +75,84 @@ PB_D Hit trace_closest(const BvhNode *__restrict__ nodes, const LeafTri *__restr
     }
     if (best.tri < 0) best.t = INFINITY;
     return best;
+}
+
+
+// while-while variant: every thread first descends inner nodes until it holds a leaf, then intersects leaves; the two
+// phases no longer serialise against each other inside a warp (Aila & Laine 2009).
+constexpr int kTraverseDone = (int)0x80000000;
+
+template <int STACK = 64>
+PB_D Hit trace_closest_ww(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, float3 o, float3 d, float tmax) {
+    Hit best;
+    best.tri = -1; best.shape = -1; best.u = -1.f; best.v = -1.f; best.t = tmax;
+    if (!(tmax > 0.f)) { best.t = INFINITY; return best; }
+    const float ix = clamp_idir(d.x), iy = clamp_idir(d.y), iz = clamp_idir(d.z);
+    int stack[STACK];
+    int sp = 0;
+    int node = 0;
+    while (node != kTraverseDone) {
+        while (node >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2), l = ldg4(np + 3);
+            float t0, t1;
+            t0 = (a.x - o.x) * ix; t1 = (a.w - o.x) * ix;
+            float ln = fminf(t0, t1), lf = fmaxf(t0, t1);
+            t0 = (a.y - o.y) * iy; t1 = (b.x - o.y) * iy;
+            ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+            t0 = (a.z - o.z) * iz; t1 = (b.y - o.z) * iz;
+            ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+            t0 = (b.z - o.x) * ix; t1 = (c.y - o.x) * ix;
+            float rn = fminf(t0, t1), rf = fmaxf(t0, t1);
+            t0 = (b.w - o.y) * iy; t1 = (c.z - o.y) * iy;
+            rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+            t0 = (c.x - o.z) * iz; t1 = (c.w - o.z) * iz;
+            rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+            const bool hl = fmaxf(ln, 0.f) <= fminf(lf, best.t), hr = fmaxf(rn, 0.f) <= fminf(rf, best.t);
+            int cl = __float_as_int(l.x), cr = __float_as_int(l.y);
+            if (hl && hr) {
+                if (rn < ln) { int t = cl; cl = cr; cr = t; }
+                stack[sp++] = cr;
+                node = cl;
+            } else if (hl) node = cl;
+            else if (hr) node = cr;
+            else node = sp ? stack[--sp] : kTraverseDone;
+        }
+        while (node < 0 && node != kTraverseDone) {
+            const int v = ~node;
+            const int first = v >> 3, cnt = (v & 7) + 1;
+            for (int i = 0; i < cnt; ++i) {
+                const float4 *tp = reinterpret_cast<const float4 *>(leaf + first + i);
+                const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                float u, w, t;
+                ray_intersect_triangle(f3(ta), f3(tb), f3(tc), o, d, u, w, t);
+                const int id = __float_as_int(ta.w);
+                if (u >= 0.f && w >= 0.f && add_rn(u, w) <= 1.f && t > kRayEpsilon && t < tmax &&
+                    (t < best.t || (t == best.t && (best.tri < 0 || id < best.tri)))) {
+                    best.t = t; best.u = u; best.v = w; best.tri = id; best.shape = __float_as_int(tb.w);
+                }
+            }
+            node = sp ? stack[--sp] : kTraverseDone;
+        }
+    }
+    if (best.tri < 0) best.t = INFINITY;
+    return best;
+}
+
+// 6-bit direction bin (octahedral map, 8x8, Morton order) used to regroup the rays of a block into coherent warps
+PB_D int direction_bin(float3 d) {
+    const float inv = 1.f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float px = d.x * inv, py = d.y * inv;
+    if (d.z < 0.f) {
+        const float qx = (1.f - fabsf(py)) * (px >= 0.f ? 1.f : -1.f), qy = (1.f - fabsf(px)) * (py >= 0.f ? 1.f : -1.f);
+        px = qx; py = qy;
+    }
+    int ux = min(7, max(0, (int)((px * .5f + .5f) * 8.f))), uy = min(7, max(0, (int)((py * .5f + .5f) * 8.f)));
+    // interleave 3+3 bits
+    int m = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) m |= (((ux >> b) & 1) << (2 * b)) | (((uy >> b) & 1) << (2 * b + 1));
+    return m;
 }
 
 }  // namespace pb

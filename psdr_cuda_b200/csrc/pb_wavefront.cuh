@@ -34,7 +34,8 @@ PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax) {
     q[1] = make_float4(d.x, d.y, d.z, 0.f);
 }
 
-PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const HitRec *hit_cur, const RayRec *prev_rays) {
+PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const EventBuffers &E) {
+    const HitRec *hit_cur = E.hit_cur;
     Vertex v;
     if (B.depth == 0) {
         if (B.ad) {   // renderD: the camera hit is differentiated in solid-angle form (scene.cpp:355-376)
@@ -51,7 +52,9 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
             v.its = reconstruct_its(P.S, load_hit(hit_cur + i), transform_pos(P.cam.to_world, f3(0.f)));
         }
     } else {
-        v.its = reconstruct_its(P.S, load_hit(hit_cur + i), f3(ldg4(reinterpret_cast<const float4 *>(prev_rays + i))));
+        HitRec h = load_hit(hit_cur + i);
+        if (ldg4(E.thr_in + i).w != 0.f) h.tri = -1;   // dead path (zero throughput or no continuation): nothing downstream can contribute
+        v.its = reconstruct_its(P.S, h, f3(ldg4(E.prev_pos + i)));
     }
     v.active = v.its.valid;
     v.bsdf = its_bsdf(P.S, v.its);
