@@ -7,6 +7,7 @@
 // Per lane the forward radiance is  L = Le(x0) + sum_k T_k * L_k,  T_{k+1} = T_k * w_k  (L_k: the event's MIS-weighted
 // connections, w_k: its continuation weight). With the suffix  S_k = L_k + w_k * S_{k+1}  the sensitivity of L to the
 // parameters touched by event k is  T_k * (dL_k + dw_k * S_{k+1}); the adjoint kernels run k = D-1 .. 0 carrying S.
+#include "pb_adjoint_math.cuh"
 #include "pb_trace.cuh"
 #include "pb_wavefront.cuh"
 
@@ -37,6 +38,34 @@ PB_D void bsdf_eval_grad_tex(const BsdfRec *b, const Its &its, float3 wo, float3
         }
     }
     // TODO(roughconductor): alpha_u/alpha_v/eta/k/specular_reflectance adjoints
+}
+
+// scatter one triangle's adjoint into the triangle-table gradient (only meshes that require a gradient carry bit3)
+PB_D void tri_grad_scatter(float *tg, int tri, const TriGrad &g) {
+    float *p = tg + (size_t)tri * kTriGradStride;
+    const float v[22] = {g.p0.x, g.p0.y, g.p0.z, g.e1.x, g.e1.y, g.e1.z, g.e2.x, g.e2.y, g.e2.z, g.n0.x, g.n0.y, g.n0.z,
+                         g.n1.x, g.n1.y, g.n1.z, g.n2.x, g.n2.y, g.n2.z, g.fn.x, g.fn.y, g.fn.z, g.area};
+#pragma unroll
+    for (int k = 0; k < 22; ++k) if (v[k] != 0.f) atomicAdd(p + k, v[k]);
+}
+struct TriFull { float3 p0, e1, e2, n0, n1, n2, fn; float area; int flags; };
+PB_D TriFull load_tri_full(const SceneView &S, int tri) {
+    const float4 *q = reinterpret_cast<const float4 *>(S.tri + tri);
+    const float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2), q3 = ldg4(q + 3), q4 = ldg4(q + 4), q5 = ldg4(q + 5), q6 = ldg4(q + 6);
+    TriFull t;
+    t.p0 = f3(q0); t.area = q0.w; t.e1 = f3(q1); t.e2 = f3(q2); t.flags = __float_as_int(q2.w);
+    t.n0 = f3(q3); t.n1 = f3(q4); t.n2 = f3(q5); t.fn = f3(q6);
+    return t;
+}
+// adjoint of a path-space point q = p0 + u e1 + v e2 with face normal / Jacobian J = A/detach(A) (scene.cpp:306,326-342,
+// mesh.cpp:317-328): g_q, g_n, g_J -> the triangle's record
+PB_D void point_on_triangle_scatter(const SceneView &S, int tri, float u, float v, float3 g_q, float3 g_n, float g_J) {
+    const float4 *q = reinterpret_cast<const float4 *>(S.tri + tri);
+    const float4 q0 = ldg4(q), q2 = ldg4(q + 2);
+    if (!(__float_as_int(q2.w) & 8)) return;
+    TriGrad g;
+    g.p0 = g_q; g.e1 = g_q * u; g.e2 = g_q * v; g.fn = g_n; g.area = g_J / q0.w;
+    tri_grad_scatter(S.tri_grad, tri, g);
 }
 
 // block-level reduction of the per-thread constant-texture accumulators, keyed by BSDF id
@@ -103,6 +132,8 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
         Rng rng((uint64_t)lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
+        const bool geom = P.S.tri_grad != nullptr && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
+        float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
             const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
@@ -130,6 +161,23 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 }
                 if (cont) { w_cont = f * scale; gval += gw * scale; }
                 bsdf_eval_grad_tex(v.bsdf, its, wo_l, gval, acc);
+                if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
+                    // value = K * (cos_o G J) with K = rho/pi * (Le weight gL + gw) / pdf0   (diffuse: pdf0 and the MIS weight are detached)
+                    const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
+                    float3 kk = f3(0.f);
+                    if (a1) {
+                        float weight = inv_nb;
+                        if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
+                        kk += gL * emitter_Le(P.S, its1, true) * weight;
+                    }
+                    if (cont) kk += gw;
+                    const float gc = pdot(kk, rho) * kInvPi / pdf0;
+                    if (gc != 0.f) {
+                        const ConnGrad cg = connection_vjp(its.p, its1.p, its.sh.n, its1.n, 1.f, gc);
+                        g_p += cg.p; g_shn += cg.sh_n;
+                        point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, cg.q, cg.n_q, cg.J);
+                    }
+                }
             }
         }
         for (int j = 0; j < B.nl; ++j) {
@@ -154,11 +202,37 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
                 bsdf_eval_grad_tex(v.bsdf, its, wo_l, gL * Le * scale, acc);
+                if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
+                    const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
+                    const float gc = pdot(gL * Le, rho) * kInvPi * weight / ps.pdf;
+                    if (gc != 0.f) {
+                        const ConnGrad cg = connection_vjp(its.p, ps.p, its.sh.n, its1.n, 1.f, gc);
+                        g_p += cg.p; g_shn += cg.sh_n;
+                        point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, cg.q, f3(0.f), cg.J);     // sampled point + its Jacobian (mesh.cpp:317-328)
+                        point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, f3(0.f), cg.n_q, 0.f);   // normal of the triangle the shadow ray hit
+                    }
+                }
             }
         }
         if (B.depth > 0) {
             const float3 Sk = L + w_cont * S_next;
             suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
+        }
+        if (geom) {   // chain the vertex adjoints into its triangle (scene.cpp:326-376)
+            const TriFull t = load_tri_full(P.S, its.tri);
+            if (t.flags & 8) {
+                TriGrad tg;
+                float gu = 0.f, gv = 0.f;
+                if (t.flags & 1) tg.fn += g_shn;
+                else shading_normal_vjp(t.n0, t.n1, t.n2, v.h.u, v.h.v, g_shn, tg, gu, gv);
+                if (B.depth == 0) {   // solid-angle form: (u, v, t) come from the differentiable ray/triangle test, p = o + t d
+                    const RayTriGrad r = ray_intersect_triangle_vjp(t.p0, t.e1, t.e2, v.ro, v.rd, gu, gv, pdot(g_p, v.rd));
+                    tg.p0 += r.p0; tg.e1 += r.e1; tg.e2 += r.e2;
+                } else {              // path-space form: barycentrics are frozen, the point rides the triangle
+                    tg.p0 += g_p; tg.e1 += g_p * v.h.u; tg.e2 += g_p * v.h.v;
+                }
+                tri_grad_scatter(P.S.tri_grad, its.tri, tg);
+            }
         }
     }
     flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);

@@ -11,6 +11,7 @@
 #include <limits>
 #include <numeric>
 
+#include "pb_adjoint_math.cuh"
 #include "pb_host.h"
 
 namespace pb {
@@ -81,8 +82,13 @@ static void build_csr(HostMesh &m) {
     for (int v = 0; v < m.nv; ++v) m.csr_off[v + 1] += m.csr_off[v];
     m.csr_face.resize(3 * (size_t)m.nf);
     std::vector<int> cur(m.csr_off.begin(), m.csr_off.end() - 1);
+    m.csr_slot.resize(3 * (size_t)m.nf);
     for (int i = 0; i < 3; ++i)
-        for (int f = 0; f < m.nf; ++f) m.csr_face[cur[m.faces[3 * f + i]]++] = f;
+        for (int f = 0; f < m.nf; ++f) {
+            const int k = cur[m.faces[3 * f + i]]++;
+            m.csr_face[k] = f;
+            m.csr_slot[k] = 3 * f + i;
+        }
 }
 
 // perspective.cpp:11-32
@@ -147,6 +153,7 @@ static void configure(pb_ctx *c) {
             m.d_faces.upload(m.faces, st);
             m.d_csr_off.upload(m.csr_off, st);
             m.d_csr_face.upload(m.csr_face, st);
+            m.d_csr_slot.upload(m.csr_slot, st);
             if (m.flags & 2) { m.d_uvs.upload(m.uvs, st); m.d_uv_faces.upload(m.uv_faces, st); }
             m.topo_dirty = false;
         }
@@ -156,7 +163,7 @@ static void configure(pb_ctx *c) {
         m.d_fcross.reserve((size_t)m.nf * sizeof(float4));
         m.d_face_area.reserve((size_t)m.nf * sizeof(float));
         m.to_world = matmul(matmul(m.left, m.raw), m.right);   // mesh.cpp:223
-        launch_mesh_preprocess(st, m.nv, m.nf, m.face_offset, (int)i, m.flags & 3, m.d_vraw.as<float>(), to_dev(m.to_world), m.d_faces.as<int>(),
+        launch_mesh_preprocess(st, m.nv, m.nf, m.face_offset, (int)i, (m.flags & 3) | (m.requires_grad ? 8 : 0), m.d_vraw.as<float>(), to_dev(m.to_world), m.d_faces.as<int>(),
                                m.d_csr_off.as<int>(), m.d_csr_face.as<int>(), m.d_uvs.as<float>(), m.d_uv_faces.as<int>(), m.d_vworld.as<float>(),
                                m.d_fcross.as<float4>(), m.d_vnormal.as<float>(), c->d_tri.as<TriRec>(), m.d_face_area.as<float>());
         c->launches += 4;
@@ -260,6 +267,7 @@ static void configure(pb_ctx *c) {
     V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
     V.emitter_env = -1;
+    V.tri_grad = nullptr;
     // gradient layout
     c->grad_segments.clear();
     int64_t off = 0;
@@ -368,6 +376,19 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;
         c->d_bsdfs_grad.upload(br, st);
         P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
+        bool any_geom = false;
+        for (const GradSegment &g : c->grad_segments) any_geom = any_geom || g.kind == PB_PARAM_MESH_VERTICES;
+        if (any_geom) {
+            c->d_tri_grad.reserve((size_t)std::max(1, c->num_tri) * kTriGradStride * sizeof(float));
+            PB_CUDA(cudaMemsetAsync(c->d_tri_grad.p, 0, (size_t)std::max(1, c->num_tri) * kTriGradStride * sizeof(float), st));
+            P.S.tri_grad = c->d_tri_grad.as<float>();
+            for (const GradSegment &g : c->grad_segments)
+                if (g.kind == PB_PARAM_MESH_VERTICES) {
+                    HostMesh &m = c->meshes[g.id];
+                    m.d_gworld.reserve(3 * (size_t)m.nv * sizeof(float));
+                    PB_CUDA(cudaMemsetAsync(m.d_gworld.p, 0, 3 * (size_t)m.nv * sizeof(float), st));
+                }
+        }
     }
     std::vector<BounceParams> bps(plan.nbounce);
     for (int k = 0; k < plan.nbounce; ++k) {
@@ -421,6 +442,18 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 c->launches++;
             }
         }
+    }
+    if (mode == MODE_VJP && P.S.tri_grad) {   // triangle-table adjoint -> object-space vertex gradients (mesh.cpp:19-51,215-231 backward)
+        for (const GradSegment &g : c->grad_segments)
+            if (g.kind == PB_PARAM_MESH_VERTICES) {
+                HostMesh &m = c->meshes[g.id];
+                m.d_gnsum.reserve(3 * (size_t)m.nv * sizeof(float));
+                m.d_gcorner.reserve(9 * (size_t)m.nf * sizeof(float));
+                launch_mesh_backward(st, m.nv, m.nf, m.face_offset, m.d_csr_off.as<int>(), m.d_csr_slot.as<int>(), m.d_fcross.as<float4>(),
+                                     m.d_vworld.as<float>(), m.d_faces.as<int>(), m.d_vraw.as<float>(), to_dev(m.to_world), c->d_tri_grad.as<float>(),
+                                     m.d_gworld.as<float>(), m.d_gnsum.as<float>(), m.d_gcorner.as<float>(), d_grad + g.offset);
+                c->launches += 3;
+            }
     }
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaStreamSynchronize(st));
@@ -698,8 +731,8 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
         PB_ASSERT_MSG(c->have_last_d, "pb_render_d_vjp needs a preceding pb_render_d on the configured scene");
         PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD, "FieldExtractionIntegrator has no parameter gradients in the interior term yet");
         for (const GradSegment &g : c->grad_segments)
-            PB_ASSERT_MSG(g.kind == PB_PARAM_BSDF_TEXTURE && c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE,
-                          "pb_render_d_vjp: only diffuse reflectance gradients are implemented so far");
+            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || (c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE),
+                          "pb_render_d_vjp: texture gradients are implemented for diffuse reflectance only so far");
         render_interior(c, *I, sensor, nullptr, MODE_VJP, d_dLdI, d_grad);
     });
 }

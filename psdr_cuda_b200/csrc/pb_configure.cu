@@ -4,6 +4,7 @@
 // (src/scene/scene.cpp:205-217). The reference scatter-adds face normals into vertices with atomics; here every vertex
 // gathers its incident faces through a CSR list laid out in the same (corner, face) order the oracle sums in, so the
 // result is deterministic and bit-identical to the CPU restatement, and the backward pass is a gather as well.
+#include "pb_adjoint_math.cuh"
 #include "pb_kernels.h"
 
 namespace pb {
@@ -87,7 +88,84 @@ __global__ void k_build_leaf_tris(int n, const int *__restrict__ order, const Tr
     leaf[i] = l;
 }
 
+// ---- backward of the mesh preprocessing (mesh.cpp:19-51, 215-231): triangle-table adjoint -> vertex adjoints -------------
+// csr_slot[k] = 3*face + corner for the k-th (vertex, incident face) pair, same order as the forward gather.
+
+// per vertex: adjoint of the (unnormalised) normal sum A_v = sum_f c_f from the adjoints of n0/n1/n2 of its faces
+__global__ void k_mesh_bwd_vertex_normal(int nv, int face_offset, const int *__restrict__ csr_off, const int *__restrict__ csr_slot,
+                                         const float4 *__restrict__ fcross, const float *__restrict__ tri_grad, float *__restrict__ g_nsum) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    float3 acc = f3(0.f), gn = f3(0.f);
+    float w = 0.f;
+    for (int k = csr_off[v]; k < csr_off[v + 1]; ++k) {
+        const int slot = csr_slot[k], f = slot / 3, corner = slot - 3 * f;
+        const float4 c = fcross[f];
+        acc += f3(c); w += c.w;
+        const float *g = tri_grad + (size_t)(face_offset + f) * kTriGradStride + 9 + 3 * corner;
+        gn += f3(g[0], g[1], g[2]);
+    }
+    float3 gA = f3(0.f);
+    if (w > 0.f && (gn.x != 0.f || gn.y != 0.f || gn.z != 0.f)) gA = normalize_vjp(acc * (1.f / w), gn) * (1.f / w);
+    g_nsum[3 * v] = gA.x; g_nsum[3 * v + 1] = gA.y; g_nsum[3 * v + 2] = gA.z;
+}
+
+// per face: adjoints of its three corners from the adjoints of p0/e1/e2/face normal/area and the vertex-normal sums
+__global__ void k_mesh_bwd_face(int nf, int face_offset, const float *__restrict__ vworld, const int *__restrict__ faces,
+                                const float *__restrict__ tri_grad, const float *__restrict__ g_nsum, float *__restrict__ g_corner) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float3 p0 = f3(vworld[3 * i0], vworld[3 * i0 + 1], vworld[3 * i0 + 2]);
+    const float3 e1 = f3(vworld[3 * i1], vworld[3 * i1 + 1], vworld[3 * i1 + 2]) - p0;
+    const float3 e2 = f3(vworld[3 * i2], vworld[3 * i2 + 1], vworld[3 * i2 + 2]) - p0;
+    const float *g = tri_grad + (size_t)(face_offset + f) * kTriGradStride;
+    const float3 g_p0 = f3(g[0], g[1], g[2]);
+    float3 g_e1 = f3(g[3], g[4], g[5]), g_e2 = f3(g[6], g[7], g[8]);
+    const float3 g_fn = f3(g[18], g[19], g[20]);
+    const float g_area = g[21];
+    const float3 g_cn = f3(g_nsum[3 * i0] + g_nsum[3 * i1] + g_nsum[3 * i2], g_nsum[3 * i0 + 1] + g_nsum[3 * i1 + 1] + g_nsum[3 * i2 + 1],
+                           g_nsum[3 * i0 + 2] + g_nsum[3 * i1 + 2] + g_nsum[3 * i2 + 2]);
+    face_vjp(e1, e2, g_fn, g_area, g_cn, g_e1, g_e2);
+    const float3 c0 = g_p0 - g_e1 - g_e2;
+    float *o = g_corner + 9 * (size_t)f;
+    o[0] = c0.x; o[1] = c0.y; o[2] = c0.z; o[3] = g_e1.x; o[4] = g_e1.y; o[5] = g_e1.z; o[6] = g_e2.x; o[7] = g_e2.y; o[8] = g_e2.z;
+}
+
+// per vertex: gather the corner adjoints (+ the direct world-space adjoint from the boundary terms), pull back through
+// transform_pos (mesh.cpp:223-231) and accumulate into the gradient segment of the object-space vertex positions
+__global__ void k_mesh_bwd_vertex(int nv, const int *__restrict__ csr_off, const int *__restrict__ csr_slot, const float *__restrict__ g_corner,
+                                  const float *__restrict__ g_world_direct, const float *__restrict__ vraw, Mat4 M, float *__restrict__ grad_out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    float3 gw = f3(g_world_direct[3 * v], g_world_direct[3 * v + 1], g_world_direct[3 * v + 2]);
+    for (int k = csr_off[v]; k < csr_off[v + 1]; ++k) {
+        const float *c = g_corner + 3 * (size_t)csr_slot[k];
+        gw += f3(c[0], c[1], c[2]);
+    }
+    // p = t.xyz / t.w, t = M (x, 1)
+    const float3 x = f3(vraw[3 * v], vraw[3 * v + 1], vraw[3 * v + 2]);
+    float t[4];
+    for (int i = 0; i < 4; ++i) t[i] = M.m[4 * i] * x.x + M.m[4 * i + 1] * x.y + M.m[4 * i + 2] * x.z + M.m[4 * i + 3];
+    const float3 p = f3(t[0] / t[3], t[1] / t[3], t[2] / t[3]);
+    const float gt[4] = {gw.x / t[3], gw.y / t[3], gw.z / t[3], -pdot(gw, p) / t[3]};
+    for (int j = 0; j < 3; ++j) {
+        float acc = 0.f;
+        for (int i = 0; i < 4; ++i) acc += M.m[4 * i + j] * gt[i];
+        grad_out[3 * v + j] += acc;
+    }
+}
+
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+void launch_mesh_backward(cudaStream_t st, int nv, int nf, int face_offset, const int *csr_off, const int *csr_slot, const float4 *fcross,
+                          const float *vworld, const int *faces, const float *vraw, const Mat4 &to_world, const float *tri_grad,
+                          const float *g_world_direct, float *g_nsum, float *g_corner, float *grad_out) {
+    if (nv <= 0 || nf <= 0) return;
+    k_mesh_bwd_vertex_normal<<<nblk(nv, 256), 256, 0, st>>>(nv, face_offset, csr_off, csr_slot, fcross, tri_grad, g_nsum);
+    k_mesh_bwd_face<<<nblk(nf, 256), 256, 0, st>>>(nf, face_offset, vworld, faces, tri_grad, g_nsum, g_corner);
+    k_mesh_bwd_vertex<<<nblk(nv, 256), 256, 0, st>>>(nv, csr_off, csr_slot, g_corner, g_world_direct, vraw, to_world, grad_out);
+}
 
 void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
                             const int *faces, const int *csr_off, const int *csr_face, const float *uvs, const int *uv_faces, float *vworld,

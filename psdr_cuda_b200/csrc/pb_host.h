@@ -63,10 +63,11 @@ struct HostBsdf {
 struct HostMesh {
     int nv = 0, nf = 0, flags = 0, bsdf = -1, emitter = -1;
     std::vector<float> verts, uvs;
-    std::vector<int> faces, uv_faces, edges, csr_off, csr_face;
+    std::vector<int> faces, uv_faces, edges, csr_off, csr_face, csr_slot;
     Mat4h raw = Mat4h::identity(), left = Mat4h::identity(), right = Mat4h::identity();
     bool verts_dirty = true, topo_dirty = true, requires_grad = false;
-    DevBuf d_vraw, d_faces, d_uvs, d_uv_faces, d_csr_off, d_csr_face, d_vworld, d_fcross, d_vnormal, d_face_area, d_face_cmf;
+    DevBuf d_vraw, d_faces, d_uvs, d_uv_faces, d_csr_off, d_csr_face, d_csr_slot, d_vworld, d_fcross, d_vnormal, d_face_area, d_face_cmf;
+    DevBuf d_gworld, d_gnsum, d_gcorner;   // VJP scratch: direct world-space vertex adjoint, normal-sum adjoint, per-corner adjoint
     int face_offset = 0;
     float total_area = 0.f, inv_total_area = 0.f, face_sum = 0.f;
     Mat4h to_world = Mat4h::identity();
@@ -114,7 +115,7 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad;
     pb::EventStore scratch, retained;
     int64_t retain_limit = (int64_t)64 << 30;
     bool retained_valid = false;

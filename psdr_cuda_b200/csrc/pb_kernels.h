@@ -45,6 +45,9 @@ struct EventBuffers {
 void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
                             const int *faces, const int *csr_off, const int *csr_face, const float *uvs, const int *uv_faces, float *vworld,
                             float4 *fcross, float *vnormal, TriRec *tri, float *face_area);
+void launch_mesh_backward(cudaStream_t st, int nv, int nf, int face_offset, const int *csr_off, const int *csr_slot, const float4 *fcross,
+                          const float *vworld, const int *faces, const float *vraw, const Mat4 &to_world, const float *tri_grad,
+                          const float *g_world_direct, float *g_nsum, float *g_corner, float *grad_out);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_trace_blocks_per_sm;

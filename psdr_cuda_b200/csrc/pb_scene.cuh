@@ -19,7 +19,7 @@ struct __align__(16) HitRec {      // 16 B: what cuda/psdr_cuda.cu:36-45 writes 
 };
 
 // ---- triangle table: one 128-byte line per triangle, indexed by global triangle id -------------------------------
-// q[0] = p0.xyz, face_area     q[1] = e1.xyz, mesh id (int bits)   q[2] = e2.xyz, flags (bit0: face normals)
+// q[0] = p0.xyz, face_area     q[1] = e1.xyz, mesh id (int bits)   q[2] = e2.xyz, flags (bit0 face normals, bit1 has uv, bit3 mesh requires grad)
 // q[3] = n0.xyz, uv0.x         q[4] = n1.xyz, uv0.y                q[5] = n2.xyz, uv1.x
 // q[6] = face_normal.xyz, uv1.y                                    q[7] = uv2.x, uv2.y, -, -
 struct __align__(16) TriRec { float4 q[8]; };
@@ -78,6 +78,7 @@ struct SceneView {
     float emitter_sum;
     int num_tri, num_nodes, num_meshes, num_bsdfs, num_emitters;
     int emitter_env;
+    float *tri_grad;        // VJP only: kTriGradStride floats per triangle (adjoint of the triangle table), or nullptr
 };
 
 enum { INTEG_DIRECT = 0, INTEG_FIELD = 1, INTEG_PATH = 2 };

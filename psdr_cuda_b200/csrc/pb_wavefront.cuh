@@ -20,7 +20,7 @@ PB_D void lane_pixel_sample(const RenderParams &P, int pix, float2 jitter, float
     sy = div_rn(add_rn((float)y, jitter.y), (float)P.height);
 }
 
-struct Vertex { Its its; const BsdfRec *bsdf; bool active; };
+struct Vertex { Its its; const BsdfRec *bsdf; bool active; HitRec h; float3 ro, rd; };
 
 PB_D HitRec load_hit(const HitRec *p) {
     const float4 h = ldg4(reinterpret_cast<const float4 *>(p));
@@ -47,14 +47,20 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
             lane_pixel_sample(P, pix, j, sx, sy);
             float3 o, d;
             sample_primary_ray(P.cam, sx, sy, o, d);
-            v.its = reconstruct_its_primary(P.S, load_hit(hit_cur + i), o, d);
+            v.h = load_hit(hit_cur + i);
+            v.ro = o; v.rd = d;
+            v.its = reconstruct_its_primary(P.S, v.h, o, d);
         } else {
-            v.its = reconstruct_its(P.S, load_hit(hit_cur + i), transform_pos(P.cam.to_world, f3(0.f)));
+            v.h = load_hit(hit_cur + i);
+            v.ro = transform_pos(P.cam.to_world, f3(0.f)); v.rd = f3(0.f);
+            v.its = reconstruct_its(P.S, v.h, v.ro);
         }
     } else {
         HitRec h = load_hit(hit_cur + i);
         if (ldg4(E.thr_in + i).w != 0.f) h.tri = -1;   // dead path (zero throughput or no continuation): nothing downstream can contribute
-        v.its = reconstruct_its(P.S, h, f3(ldg4(E.prev_pos + i)));
+        v.h = h;
+        v.ro = f3(ldg4(E.prev_pos + i)); v.rd = f3(0.f);
+        v.its = reconstruct_its(P.S, h, v.ro);
     }
     v.active = v.its.valid;
     v.bsdf = its_bsdf(P.S, v.its);
