@@ -42,6 +42,7 @@ typedef struct pb_integrator {
     int hide_emitters;  /* DirectIntegrator.hide_emitters: src/psdr.cpp:294 */
     int field;          /* PB_FIELD_* for PB_INTEG_FIELD */
     int max_depth;      /* PB_INTEG_PATH: number of scattering events */
+    int use_guiding;    /* use the grid built by pb_preprocess_secondary_edges for this sensor (DirectIntegrator::m_warpper) */
 } pb_integrator;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -103,6 +104,10 @@ int pb_render_c_host(pb_ctx *ctx, const pb_integrator *integ, int sensor, float 
  * positions so that pb_render_d_vjp replays the same paths */
 int pb_render_d(pb_ctx *ctx, const pb_integrator *integ, int sensor, float *d_image);
 
+/* DirectIntegrator::preprocess_secondary_edges (src/integrator/direct.cpp:166-204, src/psdr.cpp:285): builds the guiding grid
+ * resolution[0..2] cells x resolution[3] samples per cell x nrounds over the secondary-edge sample space of `sensor` */
+int pb_preprocess_secondary_edges(pb_ctx *ctx, int sensor, const int resolution[4], int nrounds);
+
 /* ---- gradients (reverse mode: ek.backward + ek.gradient in the reference, docs/inverse_diff_render.rst:71-79) -- */
 /* mark a leaf as requiring a gradient (ek.set_requires_gradient); slot only for PB_PARAM_BSDF_TEXTURE */
 int pb_grad_require(pb_ctx *ctx, int param_kind, int id, int slot, int enable);
@@ -111,6 +116,8 @@ int pb_grad_num_segments(pb_ctx *ctx);
 int pb_grad_segment(pb_ctx *ctx, int index, int *kind, int *id, int *slot, int64_t *offset, int64_t *count);
 int64_t pb_grad_size(pb_ctx *ctx);
 /* VJP of renderD: d_dLdI is W*H*3; accumulates (+=) into d_grad (pb_grad_size floats; the caller zeroes it).
+ * Includes the primary-edge term when sppe > 0 and the secondary-edge term when sppse > 0 (src/integrator/integrator.cpp:41-47);
+ * both exist only in the derivative, so they are evaluated here and not in pb_render_d.
  * On several GPUs each rank holds a private d_grad and the caller all-reduces it once. */
 int pb_render_d_vjp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const float *d_dLdI, float *d_grad);
 

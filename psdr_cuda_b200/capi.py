@@ -24,7 +24,7 @@ SYMBOLS = [
     "pb_scene_set_options", "pb_scene_add_sensor", "pb_scene_set_sensor_transform", "pb_scene_add_bsdf", "pb_scene_set_bsdf_texture",
     "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
-    "pb_trace", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
+    "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
     "pb_debug_set", "pb_debug_ray_buffer",
 ]
@@ -32,7 +32,7 @@ SYMBOLS = [
 
 class Integrator(C.Structure):
     _fields_ = [("kind", C.c_int), ("bsdf_samples", C.c_int), ("light_samples", C.c_int), ("hide_emitters", C.c_int),
-                ("field", C.c_int), ("max_depth", C.c_int)]
+                ("field", C.c_int), ("max_depth", C.c_int), ("use_guiding", C.c_int)]
 
 
 def lib():
@@ -71,9 +71,9 @@ def _dp(t):
     return C.c_void_p(t.data_ptr())
 
 
-def make_integrator(kind="direct", bsdf_samples=1, light_samples=1, hide_emitters=False, field="silhouette", max_depth=1):
+def make_integrator(kind="direct", bsdf_samples=1, light_samples=1, hide_emitters=False, field="silhouette", max_depth=1, use_guiding=False):
     k = {"direct": INTEG_DIRECT, "field": INTEG_FIELD, "path": INTEG_PATH}[kind]
-    return Integrator(k, bsdf_samples, light_samples, int(hide_emitters), FIELDS[field], max_depth)
+    return Integrator(k, bsdf_samples, light_samples, int(hide_emitters), FIELDS[field], max_depth, int(use_guiding))
 
 
 class Context:
@@ -217,6 +217,11 @@ class Context:
         img = out if out is not None else self._image()
         self._chk(lib().pb_render_d(self.h, C.byref(integ), sensor, _dp(img)))
         return img
+
+    def preprocess_secondary_edges(self, sensor, resolution, nrounds=1):
+        r = _i(resolution)
+        assert r.shape == (4,)
+        self._chk(lib().pb_preprocess_secondary_edges(self.h, sensor, _p(r), nrounds))
 
     # --- gradients ---------------------------------------------------------------------------------------------
     def grad_require(self, kind, id_, slot=0, enable=True):

@@ -7,7 +7,6 @@
 // Per lane the forward radiance is  L = Le(x0) + sum_k T_k * L_k,  T_{k+1} = T_k * w_k  (L_k: the event's MIS-weighted
 // connections, w_k: its continuation weight). With the suffix  S_k = L_k + w_k * S_{k+1}  the sensitivity of L to the
 // parameters touched by event k is  T_k * (dL_k + dw_k * S_{k+1}); the adjoint kernels run k = D-1 .. 0 carrying S.
-#include "pb_adjoint_math.cuh"
 #include "pb_trace.cuh"
 #include "pb_wavefront.cuh"
 
@@ -38,34 +37,6 @@ PB_D void bsdf_eval_grad_tex(const BsdfRec *b, const Its &its, float3 wo, float3
         }
     }
     // TODO(roughconductor): alpha_u/alpha_v/eta/k/specular_reflectance adjoints
-}
-
-// scatter one triangle's adjoint into the triangle-table gradient (only meshes that require a gradient carry bit3)
-PB_D void tri_grad_scatter(float *tg, int tri, const TriGrad &g) {
-    float *p = tg + (size_t)tri * kTriGradStride;
-    const float v[22] = {g.p0.x, g.p0.y, g.p0.z, g.e1.x, g.e1.y, g.e1.z, g.e2.x, g.e2.y, g.e2.z, g.n0.x, g.n0.y, g.n0.z,
-                         g.n1.x, g.n1.y, g.n1.z, g.n2.x, g.n2.y, g.n2.z, g.fn.x, g.fn.y, g.fn.z, g.area};
-#pragma unroll
-    for (int k = 0; k < 22; ++k) if (v[k] != 0.f) atomicAdd(p + k, v[k]);
-}
-struct TriFull { float3 p0, e1, e2, n0, n1, n2, fn; float area; int flags; };
-PB_D TriFull load_tri_full(const SceneView &S, int tri) {
-    const float4 *q = reinterpret_cast<const float4 *>(S.tri + tri);
-    const float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2), q3 = ldg4(q + 3), q4 = ldg4(q + 4), q5 = ldg4(q + 5), q6 = ldg4(q + 6);
-    TriFull t;
-    t.p0 = f3(q0); t.area = q0.w; t.e1 = f3(q1); t.e2 = f3(q2); t.flags = __float_as_int(q2.w);
-    t.n0 = f3(q3); t.n1 = f3(q4); t.n2 = f3(q5); t.fn = f3(q6);
-    return t;
-}
-// adjoint of a path-space point q = p0 + u e1 + v e2 with face normal / Jacobian J = A/detach(A) (scene.cpp:306,326-342,
-// mesh.cpp:317-328): g_q, g_n, g_J -> the triangle's record
-PB_D void point_on_triangle_scatter(const SceneView &S, int tri, float u, float v, float3 g_q, float3 g_n, float g_J) {
-    const float4 *q = reinterpret_cast<const float4 *>(S.tri + tri);
-    const float4 q0 = ldg4(q), q2 = ldg4(q + 2);
-    if (!(__float_as_int(q2.w) & 8)) return;
-    TriGrad g;
-    g.p0 = g_q; g.e1 = g_q * u; g.e2 = g_q * v; g.fn = g_n; g.area = g_J / q0.w;
-    tri_grad_scatter(S.tri_grad, tri, g);
 }
 
 // block-level reduction of the per-thread constant-texture accumulators, keyed by BSDF id

@@ -128,6 +128,98 @@ static cudaEvent_t get_event(pb_ctx *c, size_t idx) {
     return c->ev_pool[idx];
 }
 
+// Primary-edge list of every sensor (perspective.cpp:39-111) and the global secondary-edge table (mesh.cpp:251-264,
+// scene.cpp:219-235). Host code over the downloaded world-space vertices and the triangle table; the cmfs are
+// sequential fp32 sums like the oracle's.
+static void configure_edges(pb_ctx *c) {
+    cudaStream_t st = c->stream;
+    const bool need_prim = c->sppe > 0, need_sec = c->sppse > 0;
+    std::vector<const float *> vw_ptrs(c->meshes.size());
+    for (size_t i = 0; i < c->meshes.size(); ++i) vw_ptrs[i] = c->meshes[i].d_vworld.as<float>();
+    c->d_mesh_vworld.upload(vw_ptrs, st);
+    for (auto &s : c->sensors) { s.num_prim = 0; s.prim_sum = 0.f; }
+    c->num_sec = 0; c->sec_sum = 0.f;
+    if (!need_prim && !need_sec) return;
+    std::vector<std::vector<float>> vworld(c->meshes.size());
+    for (size_t i = 0; i < c->meshes.size(); ++i) {
+        HostMesh &m = c->meshes[i];
+        if (!(m.flags & 4)) continue;
+        vworld[i].resize(3 * (size_t)m.nv);
+        if (m.nv) PB_CUDA(cudaMemcpyAsync(vworld[i].data(), m.d_vworld.p, vworld[i].size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    auto tri_p0 = [&](int t) { const float *q = &c->h_tri[(size_t)t * 32]; return f3(q[0], q[1], q[2]); };
+    auto tri_fn = [&](int t) { const float *q = &c->h_tri[(size_t)t * 32 + 24]; return f3(q[0], q[1], q[2]); };
+    auto vert = [&](size_t mi, int v) { const float *q = &vworld[mi][3 * (size_t)v]; return f3(q[0], q[1], q[2]); };
+    if (need_prim) {
+        for (auto &s : c->sensors) {
+            std::vector<PrimEdgeRec> recs;
+            const float3 cam = s.rec.camera_pos;
+            for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
+                const HostMesh &m = c->meshes[mi];
+                if (!(m.flags & 4)) continue;
+                size_t kept = 0;
+                for (size_t e = 0; e < m.edges.size(); e += 5) {
+                    const int *ed = &m.edges[e];
+                    const bool interior = ed[3] >= 0;
+                    const float3 e0 = normalize(cam - tri_p0(m.face_offset + ed[2])), n0 = tri_fn(m.face_offset + ed[2]);
+                    float3 e1 = f3(0.f), n1 = f3(0.f);
+                    if (interior) { e1 = normalize(cam - tri_p0(m.face_offset + ed[3])); n1 = tri_fn(m.face_offset + ed[3]); }
+                    bool keep;
+                    if (m.flags & 1) keep = !(interior && ((dot(e0, n0) < kEpsilon && dot(e1, n1) < kEpsilon) || dot(n0, n1) > 1.f - kEpsilon));
+                    else keep = !interior || ((dot(e0, n0) > kEpsilon) != (dot(e1, n1) > kEpsilon));
+                    if (!keep) continue;
+                    ++kept;
+                    const float3 q0 = transform_pos(s.rec.world_to_sample, vert(mi, ed[0])), q1 = transform_pos(s.rec.world_to_sample, vert(mi, ed[1]));
+                    PrimEdgeRec r;
+                    r.p0x = q0.x; r.p0y = q0.y; r.p1x = q1.x; r.p1y = q1.y;
+                    const float ex = q1.x - q0.x, ey = q1.y - q0.y;
+                    const float len = sqrt_rn(fma_rn(ex, ex, mul_rn(ey, ey)));
+                    r.nx = -(ey / len); r.ny = ex / len; r.len = len; r.pad = 0.f;
+                    r.mesh = (int)mi; r.v0 = ed[0]; r.v1 = ed[1]; r.pad2 = 0;
+                    recs.push_back(r);
+                }
+                PB_ASSERT_MSG(kept > 0, "A mesh with enabled edges contributes no primary edge (perspective.cpp:67)");
+            }
+            std::vector<float> pmf(recs.size()), cmf(recs.size());
+            float acc = 0.f;
+            for (size_t i = 0; i < recs.size(); ++i) { pmf[i] = recs[i].len; acc += pmf[i]; cmf[i] = acc; }
+            s.num_prim = (int)recs.size(); s.prim_sum = acc;
+            s.d_prim.upload(recs, st); s.d_prim_pmf.upload(pmf, st); s.d_prim_cmf.upload(cmf, st);
+        }
+    }
+    if (need_sec) {
+        std::vector<SecEdgeRec> recs;
+        std::vector<float> pmf, cmf;
+        float acc = 0.f;
+        for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
+            const HostMesh &m = c->meshes[mi];
+            if (!(m.flags & 4)) continue;
+            for (size_t e = 0; e < m.edges.size(); e += 5) {
+                const int *ed = &m.edges[e];
+                const bool boundary = ed[3] < 0;
+                const float3 p0 = vert(mi, ed[0]), e1 = vert(mi, ed[1]) - p0, n0 = tri_fn(m.face_offset + ed[2]);
+                const float3 n1 = boundary ? f3(0.f) : tri_fn(m.face_offset + ed[3]), p2 = vert(mi, ed[4]);
+                if (!(dot(n0, n1) < 1.f - kEdgeEpsilon)) continue;   // mesh.cpp:262-263
+                SecEdgeRec r;
+                float fm, f0, f1;
+                const int im = (int)mi;
+                std::memcpy(&fm, &im, 4); std::memcpy(&f0, &ed[0], 4); std::memcpy(&f1, &ed[1], 4);
+                r.a = make_float4(p0.x, p0.y, p0.z, boundary ? 1.f : 0.f);
+                r.b = make_float4(e1.x, e1.y, e1.z, fm);
+                r.c = make_float4(n0.x, n0.y, n0.z, f0);
+                r.d = make_float4(n1.x, n1.y, n1.z, f1);
+                r.e = make_float4(p2.x, p2.y, p2.z, 0.f);
+                recs.push_back(r);
+                const float len = norm(e1);
+                pmf.push_back(len); acc += len; cmf.push_back(acc);
+            }
+        }
+        c->num_sec = (int)recs.size(); c->sec_sum = acc;
+        c->d_sec.upload(recs, st); c->d_sec_pmf.upload(pmf, st); c->d_sec_cmf.upload(cmf, st);
+    }
+}
+
 static void configure(pb_ctx *c) {
     PB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -268,6 +360,7 @@ static void configure(pb_ctx *c) {
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
     V.emitter_env = -1;
     V.tri_grad = nullptr;
+    configure_edges(c);
     // gradient layout
     c->grad_segments.clear();
     int64_t off = 0;
@@ -308,6 +401,26 @@ static Plan make_plan(const pb_integrator &I) {
 
 enum Mode { MODE_C = 0, MODE_D = 1, MODE_VJP = 2 };
 
+struct Plan;
+static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const Plan &plan, const RenderParams &Pbase, const float *d_dLdI, size_t *nev);
+
+static EdgeParams make_edge_params(pb_ctx *c, int sensor, const GuideGrid *guide) {
+    EdgeParams Q;
+    std::memset(&Q, 0, sizeof(Q));
+    const HostSensor &s = c->sensors[sensor];
+    Q.prim = s.d_prim.as<PrimEdgeRec>(); Q.prim_cmf = s.d_prim_cmf.as<float>(); Q.prim_pmf = s.d_prim_pmf.as<float>();
+    Q.prim_sum = s.prim_sum; Q.num_prim = s.num_prim;
+    Q.sec = c->d_sec.as<SecEdgeRec>(); Q.sec_cmf = c->d_sec_cmf.as<float>(); Q.sec_pmf = c->d_sec_pmf.as<float>();
+    Q.sec_sum = c->sec_sum; Q.num_sec = c->num_sec;
+    if (guide && guide->ready) {
+        Q.guide_cmf = guide->d_cmf.as<float>(); Q.guide_pmf = guide->d_pmf.as<float>(); Q.guide_sum = guide->sum; Q.guide_cells = guide->cells;
+    }
+    if (guide) for (int k = 0; k < 3; ++k) Q.guide_res[k] = guide->res[k];
+    Q.mesh_gworld = c->d_mesh_gworld.as<float *>();
+    Q.mesh_vworld = c->d_mesh_vworld.as<const float *>();
+    return Q;
+}
+
 static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t ray_lanes) {
     if ((int)S.pos.size() < nslots) { S.pos.resize(nslots); S.hits.resize(nslots); }
     if ((int)S.thr.size() < nslots + 1) S.thr.resize(nslots + 1);
@@ -316,6 +429,143 @@ static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t 
     S.rays.reserve((size_t)ray_lanes * R * sizeof(RayRec));
     for (int k = 0; k < nslots; ++k) { S.pos[k].reserve((size_t)lanes * sizeof(float4)); S.hits[k].reserve((size_t)lanes * R * sizeof(HitRec)); }
     for (int k = 0; k < nslots + 1; ++k) S.thr[k].reserve((size_t)lanes * sizeof(float4));
+}
+
+// the three ray launches + evaluation of the secondary-edge estimator for one batch (direct.cpp:225-316)
+static void secondary_edge_batch(pb_ctx *c, const RenderParams &P, const EdgeParams &Q, const float *d_dLdI, float inv_sppse, float *guide_out, int guide_spc) {
+    cudaStream_t st = c->stream;
+    EventStore &S = c->scratch;
+    RayRec *rays = S.rays.as<RayRec>();
+    HitRec *hits = S.hits[0].as<HitRec>();
+    RayRec *cam_rays = c->d_edge_rays.as<RayRec>();
+    HitRec *cam_hits = S.hit0.as<HitRec>();
+    launch_edge_secondary_rays(st, P, Q, rays, guide_spc);
+    launch_trace(st, c->view, 2 * (int64_t)P.n, rays, hits, nullptr);
+    launch_edge_secondary_camera(st, P, Q, rays, hits, cam_rays, guide_spc);
+    launch_trace(st, c->view, (int64_t)P.n, cam_rays, cam_hits, nullptr);
+    launch_edge_secondary_eval(st, P, Q, rays, hits, cam_rays, cam_hits, d_dLdI, inv_sppse, guide_out, guide_spc);
+    c->launches += 5;
+}
+
+// boundary terms of renderD in reverse mode (integrator.cpp:98-119, direct.cpp:207-221); lanes are sharded by index range
+static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const Plan &plan, const RenderParams &Pbase, const float *d_dLdI, size_t *) {
+    cudaStream_t st = c->stream;
+    const int64_t npix = (int64_t)c->width * c->height;
+    const bool field = (I.kind == PB_INTEG_FIELD);
+    // per-mesh world-space vertex adjoint buffers
+    std::vector<float *> gw(c->meshes.size(), nullptr);
+    for (const GradSegment &g : c->grad_segments)
+        if (g.kind == PB_PARAM_MESH_VERTICES) gw[g.id] = c->meshes[g.id].d_gworld.as<float>();
+    c->d_mesh_gworld.upload(gw, st);
+    const GuideGrid *guide = (I.use_guiding && sensor < (int)c->guides.size()) ? &c->guides[sensor] : nullptr;
+    const EdgeParams Q = make_edge_params(c, sensor, guide);
+    const int R = std::max(2, plan.nb + plan.nl);
+    const int64_t B = c->batch;
+    size_store(c->scratch, B, 2, R, B);
+    c->d_edge_rays.reserve((size_t)B * sizeof(RayRec));
+    c->d_edge_rad.reserve((size_t)B * sizeof(float4));
+    RenderParams P = Pbase;
+    P.spp = 1; P.spp_local = 1; P.s0 = 0; P.inv_spp = 1.f;
+    EventStore &S = c->scratch;
+    // ---- primary edges
+    if (c->sppe > 0 && Q.num_prim > 0) {
+        const int64_t N = npix * c->sppe;
+        const int64_t l0 = N * c->rank / c->world, l1 = N * (c->rank + 1) / c->world;
+        const uint64_t base = c->last_d_offset_e;
+        const uint64_t per_event = 3 * plan.nb + 2 * plan.nl, per_li = (uint64_t)plan.nbounce * per_event;
+        P.jump0 = make_jump(base);
+        for (int64_t start = l0; start < l1; start += B) {
+            P.local0 = start; P.n = (int)std::min<int64_t>(B, l1 - start);
+            for (int side = 0; side < 2; ++side) {   // side 0 = ray_p is evaluated first (operand order)
+                HitRec *hit0 = S.hit0.as<HitRec>();
+                launch_edge_primary_rays(st, P, Q, side, hit0);
+                c->launches++;
+                if (field) {
+                    launch_field(st, P, I.field, hit0, nullptr, S.rad.as<float4>());
+                    c->launches++;
+                } else {
+                    for (int k = 0; k < plan.nbounce; ++k) {
+                        BounceParams Bp;
+                        Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
+                        Bp.hide_emitters = I.hide_emitters; Bp.ad = 0;
+                        Bp.jump = make_jump(base + 1 + (uint64_t)side * per_li + (uint64_t)k * per_event);
+                        EventBuffers E;
+                        E.hit_cur = (k == 0) ? hit0 : S.hits[(k - 1) & 1].as<HitRec>();
+                        E.prev_pos = (k == 0) ? nullptr : S.pos[(k - 1) & 1].as<float4>();
+                        E.pos = S.pos[k & 1].as<float4>();
+                        E.rays = S.rays.as<RayRec>();
+                        E.hits = S.hits[k & 1].as<HitRec>();
+                        E.thr_in = (k == 0) ? nullptr : S.thr[k & 1].as<float4>();
+                        E.thr_out = Bp.last ? nullptr : S.thr[(k + 1) & 1].as<float4>();
+                        E.rad = S.rad.as<float4>();
+                        launch_shade(st, P, Bp, E);
+                        launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr);
+                        launch_resolve(st, P, Bp, E, nullptr);
+                        c->launches += 3;
+                    }
+                }
+                if (side == 0) PB_CUDA(cudaMemcpyAsync(c->d_edge_rad.p, S.rad.p, (size_t)P.n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+            }
+            launch_edge_primary_grad(st, P, Q, c->d_edge_rad.as<float4>(), S.rad.as<float4>(), d_dLdI, 1.f / (float)c->sppe);
+            c->launches++;
+        }
+    }
+    // ---- secondary edges (the base Integrator / FieldExtractionIntegrator has none: integrator.h:24)
+    if (c->sppse > 0 && Q.num_sec > 0 && !field) {
+        const int64_t N = npix * c->sppse;
+        const int64_t l0 = N * c->rank / c->world, l1 = N * (c->rank + 1) / c->world;
+        P.jump0 = make_jump(c->last_d_offset_s);
+        for (int64_t start = l0; start < l1; start += B) {
+            P.local0 = start; P.n = (int)std::min<int64_t>(B, l1 - start);
+            secondary_edge_batch(c, P, Q, d_dLdI, 1.f / (float)c->sppse, nullptr, 0);
+        }
+    }
+}
+
+// DirectIntegrator::preprocess_secondary_edges (direct.cpp:166-204): guiding grid over the 3-D secondary-edge sample space
+static void preprocess_secondary_edges(pb_ctx *c, int sensor, const int *reso, int nrounds) {
+    PB_ASSERT_MSG(nrounds > 0, "nrounds must be positive");
+    PB_ASSERT_MSG(c->ready, "Scene needs to be configured!");
+    PB_ASSERT_MSG(sensor >= 0 && sensor < (int)c->sensors.size(), "Invalid sensor id!");
+    PB_ASSERT_MSG(c->sppse > 0 && c->num_sec > 0, "preprocess_secondary_edges needs sppse > 0 and at least one secondary edge");
+    PB_ASSERT_MSG(reso[0] > 0 && reso[1] > 0 && reso[2] > 0 && reso[3] > 0, "Invalid guiding resolution");
+    PB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if ((int)c->guides.size() < (int)c->sensors.size()) c->guides.resize(c->sensors.size());
+    GuideGrid &G = c->guides[sensor];
+    const int64_t cells = (int64_t)reso[0] * reso[1] * reso[2];
+    const int64_t N = cells * reso[3];
+    PB_ASSERT_MSG(N <= std::numeric_limits<int>::max(), "Too many guiding samples");
+    for (int k = 0; k < 3; ++k) G.res[k] = reso[k];
+    G.cells = (int)cells; G.ready = false;
+    G.d_pmf.reserve((size_t)cells * sizeof(float));
+    PB_CUDA(cudaMemsetAsync(G.d_pmf.p, 0, (size_t)cells * sizeof(float), st));
+    std::vector<float *> gw(c->meshes.size(), nullptr);
+    c->d_mesh_gworld.upload(gw, st);
+    const EdgeParams Q = make_edge_params(c, sensor, &G);
+    const int64_t B = c->batch;
+    size_store(c->scratch, B, 2, 2, B);
+    c->d_edge_rays.reserve((size_t)B * sizeof(RayRec));
+    RenderParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.S = c->view; P.cam = c->sensors[sensor].rec;
+    P.width = c->width; P.height = c->height; P.spp = 1; P.spp_local = 1; P.s0 = 0; P.inv_spp = 1.f;
+    for (int j = 0; j < nrounds; ++j) {
+        P.jump0 = make_jump(3 * (uint64_t)j);   // a private sampler seeded with arange(N) (direct.cpp:185-186)
+        for (int64_t start = 0; start < N; start += B) {
+            P.local0 = start; P.n = (int)std::min<int64_t>(B, N - start);
+            secondary_edge_batch(c, P, Q, nullptr, 1.f, G.d_pmf.as<float>(), reso[3]);
+        }
+    }
+    std::vector<float> pmf((size_t)cells), cmf((size_t)cells);
+    PB_CUDA(cudaMemcpyAsync(pmf.data(), G.d_pmf.p, (size_t)cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    float acc = 0.f;
+    for (int64_t i = 0; i < cells; ++i) { if (nrounds > 1) pmf[i] /= (float)nrounds; acc += pmf[i]; cmf[i] = acc; }
+    G.sum = acc;
+    G.d_pmf.upload(pmf, st); G.d_cmf.upload(cmf, st);
+    PB_CUDA(cudaStreamSynchronize(st));
+    G.ready = acc > 0.f;
 }
 
 // interior term: integrator.cpp:64-95 over this shard's samples, in batches.
@@ -338,18 +588,24 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     const Plan plan = make_plan(I);
     const uint64_t base = (mode == MODE_VJP) ? c->last_d_offset : c->sampler_offset[0];
     if (mode == MODE_D) c->retained_valid = false;
-    if (c->spp <= 0 || spp_local <= 0) {
+    const bool field = (I.kind == PB_INTEG_FIELD);
+    if ((c->spp <= 0 || spp_local <= 0) && mode != MODE_VJP) {
         PB_CUDA(cudaStreamSynchronize(st));
-        if (mode != MODE_VJP && c->spp > 0) c->sampler_offset[0] = base + plan.draws;
+        if (c->spp > 0) c->sampler_offset[0] = base + plan.draws;
+        if (mode == MODE_D) {   // the edge samplers still advance (integrator.cpp:41-47)
+            const uint64_t per_li = (uint64_t)plan.nbounce * (3 * plan.nb + 2 * plan.nl);
+            c->last_d_offset_e = c->sampler_offset[1]; c->last_d_offset_s = c->sampler_offset[2];
+            if (c->sppe > 0 && c->sensors[sensor].num_prim > 0) c->sampler_offset[1] += 1 + 2 * per_li;
+            if (c->sppse > 0 && !field) c->sampler_offset[2] += 3;
+        }
         return;
     }
-    PB_ASSERT_MSG(I.kind == PB_INTEG_FIELD || !c->emitters.empty(), "No Emitter!");
-    const int64_t total = npix * spp_local;
+    PB_ASSERT_MSG(field || !c->emitters.empty(), "No Emitter!");
+    const int64_t total = (c->spp > 0 && spp_local > 0) ? npix * spp_local : 0;
     const int R = std::max(1, plan.nb + plan.nl);
-    const int64_t B = std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024);
+    const int64_t B = std::max<int64_t>(1024, std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024));
     const int D = std::max(1, plan.nbounce);
     const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (16 + 16 * R + 16));
-    const bool field = (I.kind == PB_INTEG_FIELD);
     // which store, and whether the forward pass has to run
     bool use_retained = false, run_forward = true;
     if (mode == MODE_D && !field && !c->grad_segments.empty() && retain_bytes <= c->retain_limit) use_retained = true;
@@ -397,8 +653,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         Bp.hide_emitters = I.hide_emitters; Bp.ad = (mode == MODE_C) ? 0 : 1;
         Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
     }
-    size_t nev = 0;
-    for (int64_t start = 0; start < total; start += B) {
+    size_t nev = 0, nev_edge = 0;
+    for (int64_t start = 0; start < total && !(field && mode == MODE_VJP); start += B) {
         P.local0 = start; P.n = (int)std::min<int64_t>(B, total - start);
         const size_t off = use_retained ? (size_t)start : 0;
         HitRec *hit0 = S.hit0.as<HitRec>() + off;
@@ -422,7 +678,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             PB_CUDA(cudaEventRecord(e1, st));
             c->launches++;
             if (field) {
-                if (mode != MODE_VJP) { launch_field(st, P, I.field, hit0, d_image); c->launches++; }
+                if (mode != MODE_VJP) { launch_field(st, P, I.field, hit0, d_image, nullptr); c->launches++; }
                 continue;
             }
             for (int k = 0; k < plan.nbounce; ++k) {
@@ -443,6 +699,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             }
         }
     }
+    if (mode == MODE_VJP && P.S.tri_grad) run_edge_terms(c, I, sensor, plan, P, d_dLdI, &nev_edge);
     if (mode == MODE_VJP && P.S.tri_grad) {   // triangle-table adjoint -> object-space vertex gradients (mesh.cpp:19-51,215-231 backward)
         for (const GradSegment &g : c->grad_segments)
             if (g.kind == PB_PARAM_MESH_VERTICES) {
@@ -471,6 +728,12 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         c->retained_nbounce = plan.nbounce; c->retained_sensor = sensor; c->retained_hide = I.hide_emitters;
     }
     if (mode != MODE_VJP) c->sampler_offset[0] = base + plan.draws;
+    if (mode == MODE_D) {   // integrator.cpp:41-47: renderD also consumes the two edge samplers
+        const uint64_t per_li = (uint64_t)plan.nbounce * (3 * plan.nb + 2 * plan.nl);
+        c->last_d_offset_e = c->sampler_offset[1]; c->last_d_offset_s = c->sampler_offset[2];
+        if (c->sppe > 0 && c->sensors[sensor].num_prim > 0) c->sampler_offset[1] += 1 + 2 * per_li;
+        if (c->sppse > 0 && !field) c->sampler_offset[2] += 3;
+    }
 }
 
 }  // namespace pb
@@ -538,7 +801,7 @@ int pb_scene_add_sensor(pb_ctx *c, float fov_x, float near_clip, float far_clip,
     return guard_id(c, [&] {
         HostSensor s;
         s.fov_x = fov_x; s.near_clip = near_clip; s.far_clip = far_clip; s.to_world = from_ptr(to_world);
-        c->sensors.push_back(s);
+        c->sensors.push_back(std::move(s));
         c->ready = false;
         return (int)c->sensors.size() - 1;
     });
@@ -704,6 +967,10 @@ int pb_render_d(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
     });
 }
 
+int pb_preprocess_secondary_edges(pb_ctx *c, int sensor, const int *resolution, int nrounds) {
+    return guard(c, [&] { PB_ASSERT_MSG(resolution, "Null argument"); preprocess_secondary_edges(c, sensor, resolution, nrounds); });
+}
+
 int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
     return guard(c, [&] {
         if (kind == PB_PARAM_BSDF_TEXTURE) {
@@ -729,7 +996,8 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
     return guard(c, [&] {
         PB_ASSERT_MSG(I && d_dLdI && d_grad, "Null argument");
         PB_ASSERT_MSG(c->have_last_d, "pb_render_d_vjp needs a preceding pb_render_d on the configured scene");
-        PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD, "FieldExtractionIntegrator has no parameter gradients in the interior term yet");
+        PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD || I->field == PB_FIELD_SILHOUETTE,
+                      "FieldExtractionIntegrator: only the silhouette field (zero interior derivative) has gradients so far");
         for (const GradSegment &g : c->grad_segments)
             PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || (c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE),
                           "pb_render_d_vjp: texture gradients are implemented for diffuse reflectance only so far");

@@ -81,6 +81,17 @@ struct HostSensor {
     float fov_x = 45.f, near_clip = 0.1f, far_clip = 1e4f;
     Mat4h to_world = Mat4h::identity();
     SensorRec rec;
+    // primary-edge list (perspective.cpp:39-111)
+    int num_prim = 0;
+    float prim_sum = 0.f;
+    DevBuf d_prim, d_prim_pmf, d_prim_cmf;
+};
+struct GuideGrid {   // HyperCubeDistribution3f of DirectIntegrator::m_warpper (direct.cpp:166-204)
+    int res[3] = {0, 0, 0};
+    int cells = 0;
+    float sum = 0.f;
+    bool ready = false;
+    DevBuf d_pmf, d_cmf;
 };
 struct GradSegment { int kind, id, slot; int64_t offset, count; };
 // per-event wavefront records, either one batch worth (scratch) or the whole shard (retained for the VJP)
@@ -116,6 +127,12 @@ struct pb_ctx {
     pb::SceneView view;
     // wavefront buffers
     pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad;
+    // boundary terms
+    int num_sec = 0;
+    float sec_sum = 0.f;
+    pb::DevBuf d_sec, d_sec_pmf, d_sec_cmf, d_mesh_vworld, d_mesh_gworld, d_edge_rays, d_edge_rad;
+    std::vector<pb::GuideGrid> guides;
+    uint64_t last_d_offset_e = 0, last_d_offset_s = 0;
     pb::EventStore scratch, retained;
     int64_t retain_limit = (int64_t)64 << 30;
     bool retained_valid = false;

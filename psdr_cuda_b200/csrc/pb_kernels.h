@@ -57,6 +57,12 @@ void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);
 void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI);
-void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film);
+void launch_edge_primary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, int side, HitRec *hit0);
+void launch_edge_primary_grad(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const float4 *rad_p, const float4 *rad_n, const float *dLdI, float inv_sppe);
+void launch_edge_secondary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, RayRec *rays, int guide_spc);
+void launch_edge_secondary_camera(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const RayRec *rays, const HitRec *hits, RayRec *cam_rays, int guide_spc);
+void launch_edge_secondary_eval(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const RayRec *rays, const HitRec *hits, const RayRec *cam_rays,
+                                const HitRec *cam_hits, const float *dLdI, float inv_sppse, float *guide_out, int guide_spc);
+void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film, float4 *rad_out);
 
 }  // namespace pb

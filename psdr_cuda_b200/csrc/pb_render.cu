@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
 }
 
 // field.cpp:34-54
-__global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const HitRec *__restrict__ hit0, float *__restrict__ film) {
+__global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const HitRec *__restrict__ hit0, float *__restrict__ film, float4 *__restrict__ rad_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int pix = -1;
     float3 out = f3(0.f);
@@ -317,9 +317,10 @@ __global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const 
                 default: out = f3(its.uv.x, its.uv.y, 0.f); break;
             }
         }
+        if (rad_out) rad_out[i] = make_float4(out.x, out.y, out.z, 0.f);
         out = zero_nonfinite(out) * P.inv_spp;
     }
-    film_accumulate(film, pix, out);
+    if (film) film_accumulate(film, pix, out);
 }
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -352,8 +353,8 @@ void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B,
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film) {
     if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E, film);
 }
-void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film) {
-    if (P.n > 0) k_field<<<nblk(P.n, 256), 256, 0, st>>>(P, field, hit0, film);
+void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film, float4 *rad_out) {
+    if (P.n > 0) k_field<<<nblk(P.n, 256), 256, 0, st>>>(P, field, hit0, film, rad_out);
 }
 
 }  // namespace pb

@@ -67,6 +67,18 @@ struct SensorRec {
     int width, height;
 };
 
+// primary (camera-silhouette) edge, 48 B: projected endpoints, unit normal, length (edge.h:28-40) + who owns it
+struct __align__(16) PrimEdgeRec { float p0x, p0y, p1x, p1y; float nx, ny, len, pad; int mesh, v0, v1, pad2; };
+// secondary edge, 80 B (edge.h:50-65): p0|boundary flag, e1|mesh, n0|v0, n1|v1, p2|-
+struct __align__(16) SecEdgeRec { float4 a, b, c, d, e; };
+struct EdgeParams {
+    const PrimEdgeRec *prim; const float *prim_cmf, *prim_pmf; float prim_sum; int num_prim;
+    const SecEdgeRec *sec; const float *sec_cmf, *sec_pmf; float sec_sum; int num_sec;
+    const float *guide_cmf, *guide_pmf; float guide_sum; int guide_cells; int guide_res[3];   // direct.cpp:166-204 (null: no guiding)
+    float *const *mesh_gworld;          // per mesh: world-space vertex adjoint buffer (nullptr if the mesh needs no gradient)
+    const float *const *mesh_vworld;    // per mesh: world-space vertex positions
+};
+
 struct SceneView {
     const TriRec *tri;
     const LeafTri *leaf;

@@ -286,3 +286,98 @@ def test_errors_surface_as_runtime_error(desc):
         ctx.render_d_vjp(capi.make_integrator("direct"), torch.ones((64, 3), device="cuda"))
     with pytest.raises(RuntimeError):
         ctx.add_mesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 5]], np.int32))
+
+
+# ---- vertex-position gradients: interior geometry terms + primary / secondary boundary terms (BASELINE.json configs[2]) ----
+def _vertex_grad_case(scene, opts, kind, kw, mesh, guide=None, trials=3, rtol=1e-3):
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    rng = np.random.default_rng(2718)
+    pdesc = scene_io.load_scene_description(scene_path(scene))
+    odesc = orc.load_scene_description(scene_path(scene))
+    W, H = opts["width"], opts["height"]
+    dLdI = rng.uniform(-1, 1, size=(W * H, 3)).astype(np.float32)
+    ctx = capi.Context(0)
+    ctx.load_description(pdesc, opts)
+    ctx.grad_require(capi.PARAM_MESH_VERTICES, mesh)
+    ctx.configure()
+    integ = capi.make_integrator(kind, use_guiding=guide is not None, **kw)
+    if kind == "direct":
+        oi = orc.DirectIntegrator(kw.get("bsdf_samples", 1), kw.get("light_samples", 1))
+    elif kind == "path":
+        oi = orc.PathIntegrator(kw["max_depth"])
+    else:
+        oi = orc.FieldExtractionIntegrator(kw["field"])
+    if guide is not None:
+        ctx.preprocess_secondary_edges(0, guide[0], guide[1])
+    ctx.render_d(integ)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().reshape(-1, 3)
+    nv = len(odesc["meshes"][mesh]["verts"])
+    assert g.shape == (nv, 3) and np.isfinite(g).all() and np.abs(g).max() > 0
+    scale = None
+    for trial in range(trials):
+        u = np.tile(np.array([[1.0, 0.5, -0.3]], np.float32), (nv, 1)) if trial == 0 else rng.normal(size=(nv, 3)).astype(np.float32)
+        osc = orc.Scene(odesc, opts)
+        osc.set_mesh_vertex_tangent(mesh, u)
+        osc.configure()
+        if guide is not None:
+            oi.preprocess_secondary_edges(osc, 0, guide[0], guide[1])
+        _, dimg = oi.renderD(osc)
+        want = float((dLdI.astype(np.float64) * dimg).sum())     # <dL/dI, J u> by the oracle's forward mode
+        got = float((g.astype(np.float64) * u).sum())            # <J^T dL/dI, u> by the CUDA reverse mode
+        scale = max(abs(want), scale or 0.0)
+        assert abs(got - want) <= rtol * max(abs(want), 0.05 * scale), (trial, got, want)
+    ctx.close()
+
+
+def test_vertex_gradients_interior_only():
+    o = dict(width=48, height=48, spp=8, sppe=0, sppse=0)
+    _vertex_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1), 1)     # smooth-normal bunny
+    _vertex_grad_case("cbox_bunny", o, "path", dict(max_depth=3), 1)
+    _vertex_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1), 0)     # the emitter quad
+    _vertex_grad_case("cbox_bunny", o, "path", dict(max_depth=3), 5)                           # a face-normal wall
+
+
+def test_vertex_gradients_primary_edges_only():
+    _vertex_grad_case("bunny", dict(width=64, height=64, spp=0, sppe=16, sppse=0), "field", dict(field="silhouette"), 0)   # examples/config.py bunny_silhouette
+    _vertex_grad_case("cbox_bunny", dict(width=48, height=48, spp=0, sppe=8, sppse=0), "direct", dict(bsdf_samples=1, light_samples=1), 1)
+    _vertex_grad_case("cbox_bunny", dict(width=48, height=48, spp=0, sppe=8, sppse=0), "path", dict(max_depth=2), 1)
+
+
+def test_vertex_gradients_secondary_edges_only():
+    o = dict(width=48, height=48, spp=0, sppe=0, sppse=32)
+    _vertex_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1), 1)
+    _vertex_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1), 0)     # flows through the emitter triangle
+    _vertex_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1), 2)     # flows through the shaded triangle (floor)
+
+
+def test_vertex_gradients_guided_secondary_edges():
+    _vertex_grad_case("cbox_bunny", dict(width=48, height=48, spp=0, sppe=0, sppse=16), "direct", dict(bsdf_samples=1, light_samples=1), 1,
+                      guide=([200, 4, 4, 2], 2))
+
+
+def test_vertex_gradients_all_terms_cfg3_small():
+    # configs[2] at test size: PathIntegrator renderD with vertex-position gradients, interior + primary + secondary
+    o = dict(width=48, height=48, spp=8, sppe=8, sppse=8)
+    _vertex_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1), 1)
+    _vertex_grad_case("cbox_bunny", o, "path", dict(max_depth=3), 1)
+
+
+def test_vertex_and_albedo_gradients_together_and_sharded():
+    from psdr_cuda_b200 import capi, scene_io
+    desc = scene_io.load_scene_description(scene_path("cbox_bunny"))
+    opts = dict(width=32, height=32, spp=6, sppe=6, sppse=6)
+    integ = capi.make_integrator("direct")
+    def grads(rank, world):
+        ctx = capi.Context(0)
+        ctx.load_description(desc, opts)
+        ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "reflectance")
+        ctx.grad_require(capi.PARAM_MESH_VERTICES, 1)
+        ctx.set_shard(rank, world)
+        ctx.configure()
+        img = ctx.render_d(integ)
+        return ctx.render_d_vjp(integ, torch.ones_like(img)).cpu().numpy(), ctx.grad_layout()
+    full, layout = grads(0, 1)
+    assert [s["kind"] for s in layout] == [capi.PARAM_BSDF_TEXTURE, capi.PARAM_MESH_VERTICES] and layout[1]["count"] == 3 * 34817
+    parts = sum(grads(r, 3)[0] for r in range(3))
+    assert np.linalg.norm(parts - full) <= 1e-4 * np.linalg.norm(full)
