@@ -133,7 +133,8 @@ float pb_stats_last_primary_ms(pb_ctx *ctx);
 
 /* ---- debugging / tuning hooks (not part of the reference surface) ---------------------------------------------- */
 int pb_debug_set(pb_ctx *ctx, const char *key, int64_t value);                         /* "trace_variant": 0..3 */
-int pb_debug_ray_buffer(pb_ctx *ctx, int event, void **d_rays, int64_t *bytes);        /* rays kept by the last VJP batch */
+int pb_debug_ray_buffer(pb_ctx *ctx, int event, void **d_rays, int64_t *bytes);
+int pb_debug_retained_rad(pb_ctx *ctx, void **d_rad, int64_t *bytes);                  /* per-lane radiance kept by pb_render_d */        /* rays kept by the last VJP batch */
 
 #ifdef __cplusplus
 }

@@ -247,6 +247,29 @@ int orc_render_c(void *h, void *I, int sensor, float *out) {
 int orc_render_d(void *h, void *I, int sensor, float *out, float *out_t) {
     return guard([&] { renderD(*(Integrator *)I, ((Handle *)h)->scene, sensor, out, out_t); });
 }
+// debugging aid: radiance of one interior lane of a freshly seeded sampler (stream position 0), C or D formulation
+int orc_debug_lane(void *h, void *Iv, int sensor, int64_t lane, int ad, float *out3) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        const Integrator &I = *(Integrator *)Iv;
+        const RenderOption &o = s.opts;
+        SamplerLane smp = SamplerLane::make((uint64_t)lane);
+        int pix = (int)(lane / o.spp);
+        V2f j = smp.next_2d();
+        float bx = (float)(pix % o.width), by = (float)(pix / o.width);
+        if (ad) {
+            V2<Dual> smpl(Dual((bx + j.x) / (float)o.width), Dual((by + j.y) / (float)o.height));
+            Ray<Dual> ray = s.sensors[sensor].sample_primary_ray<Dual>(smpl);
+            V3<Dual> v = Li<Dual>(I, s, smp, ray);
+            for (int k = 0; k < 3; ++k) out3[k] = v[k].v;
+        } else {
+            V2f smpl((bx + j.x) / (float)o.width, (by + j.y) / (float)o.height);
+            Ray<float> ray = s.sensors[sensor].sample_primary_ray<float>(smpl);
+            V3f v = Li<float>(I, s, smp, ray);
+            for (int k = 0; k < 3; ++k) out3[k] = v[k];
+        }
+    });
+}
 int orc_preprocess_secondary_edges(void *h, void *I, int sensor, const int *reso4, int nrounds) {
     return guard([&] { preprocess_secondary_edges(*(Integrator *)I, ((Handle *)h)->scene, sensor, reso4, nrounds); });
 }

@@ -26,7 +26,7 @@ SYMBOLS = [
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
-    "pb_debug_set", "pb_debug_ray_buffer",
+    "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad",
 ]
 
 

@@ -1020,6 +1020,13 @@ int pb_debug_ray_buffer(pb_ctx *c, int event, void **d_rays, int64_t *bytes) {
         *d_rays = S.rays.p; *bytes = (int64_t)S.rays.bytes;
     });
 }
+/* retained per-lane radiance of the last pb_render_d (float4 per lane), for debugging */
+int pb_debug_retained_rad(pb_ctx *c, void **d_rad, int64_t *bytes) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->retained_valid, "nothing retained");
+        *d_rad = c->retained.rad.p; *bytes = (int64_t)c->retained.rad.bytes;
+    });
+}
 int pb_ctx_set_retain_limit(pb_ctx *c, int64_t bytes) { c->retain_limit = bytes; c->retained_valid = false; return 0; }
 int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }
 float pb_stats_last_trace_ms(pb_ctx *c) { return c->last_trace_ms; }

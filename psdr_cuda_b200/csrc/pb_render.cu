@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
         const Its &its = v.its;
         Rng rng((uint64_t)lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
+        bool has_cont = false;
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
                     if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
                     L += emitter_Le(P.S, its1, true) * bsdf_val * weight;
                 }
-                if (B.carry && j == 0 && cont) w_cont = bsdf_val;
+                if (B.carry && j == 0 && cont) { w_cont = bsdf_val; has_cont = true; }
             }
         }
         for (int j = 0; j < B.nl; ++j) {
@@ -291,7 +292,10 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
         if (B.last) out = zero_nonfinite(rad) * P.inv_spp;   // integrator.cpp:87-91
         if (E.thr_out) {
             const float3 t2 = thr * w_cont;
-            const bool dead = !(t2.x != 0.f || t2.y != 0.f || t2.z != 0.f);   // also true when there is no continuation
+            // A path without a continuation is dead. A zero-throughput path contributes nothing either, but its deeper
+            // events still enter the derivative w.r.t. whatever made the throughput zero (d(rho X)/d rho = X at rho = 0),
+            // so it is only dropped by renderC.
+            const bool dead = !has_cont || (!B.ad && !(t2.x != 0.f || t2.y != 0.f || t2.z != 0.f));
             E.thr_out[i] = make_float4(t2.x, t2.y, t2.z, dead ? 1.f : 0.f);
         }
         if (E.rad) E.rad[i] = make_float4(rad.x, rad.y, rad.z, 0.f);
