@@ -149,6 +149,8 @@ def run_ours(args):
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     if args.batch:
         ctx.set_batch(args.batch)
+    if args.trace_variant >= 0:
+        ctx.debug_set("trace_variant", args.trace_variant)
     ctx.configure()
     integ = capi.make_integrator("path", max_depth=DEPTH)
     npix = W * H
@@ -277,6 +279,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace-variant", type=int, default=-1, help="debug: traversal kernel variant (default: library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

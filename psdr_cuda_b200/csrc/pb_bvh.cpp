@@ -123,10 +123,12 @@ struct Builder {
     }
 };
 
-void pad_box(float *lo, float *hi) {
+// pad = 1e-4 relative to the coordinate (rounded ray/triangle test vs exact boxes) + 2.5e-7 of the scene extent (error of
+// the fused slab test for ray origins inside the scene, pb_trace.cuh)
+void pad_box(float *lo, float *hi, float extent) {
     for (int k = 0; k < 3; ++k) {
         if (!(hi[k] < std::numeric_limits<float>::max())) continue;
-        float pad = 1e-4f * std::max(1.f, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+        float pad = 1e-4f * std::max(1.f, std::max(std::fabs(lo[k]), std::fabs(hi[k]))) + 2.5e-7f * extent;
         lo[k] -= pad; hi[k] += pad;
     }
 }
@@ -161,7 +163,9 @@ void build_bvh(const float *p0e1e2, int n, std::vector<HostNode> &nodes, std::ve
             B.nodes.push_back(root);
         }
     }
-    for (auto &nd : B.nodes) { pad_box(nd.llo, nd.lhi); pad_box(nd.rlo, nd.rhi); }
+    float extent = 0.f;
+    for (const Box &b : tb) for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+    for (auto &nd : B.nodes) { pad_box(nd.llo, nd.lhi, extent); pad_box(nd.rlo, nd.rhi, extent); }
     nodes.swap(B.nodes);
     order.swap(B.order);
 }

@@ -119,6 +119,19 @@ static void configure_sensor(HostSensor &s, int W, int H) {
     r.width = W; r.height = H;
 }
 
+// all wavefront ray launches go through here: sorted (variant 7) or in lane order (debug variants)
+static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits) {
+    if (g_trace_variant == 7) {
+        c->d_sort_hist.reserve(8192 * sizeof(unsigned));
+        c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
+        launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
+                            f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>());
+        c->launches += 3;
+    } else {
+        launch_trace(c->stream, c->view, n, rays, hits, nullptr);
+    }
+}
+
 static cudaEvent_t get_event(pb_ctx *c, size_t idx) {
     while (c->ev_pool.size() <= idx) {
         cudaEvent_t e;
@@ -275,6 +288,16 @@ static void configure(pb_ctx *c) {
     }
     // BVH over all triangles (replaces optixAccelBuild, optix.h:277-340)
     {
+        for (int k = 0; k < 3; ++k) { c->scene_lo[k] = std::numeric_limits<float>::max(); c->scene_hi[k] = -std::numeric_limits<float>::max(); }
+        for (int t = 0; t < total; ++t) {
+            const float *q = &c->h_tri[(size_t)t * 32];
+            for (int a = 0; a < 3; ++a) {
+                const float v0 = q[a], v1 = q[a] + q[4 + a], v2 = q[a] + q[8 + a];
+                c->scene_lo[a] = std::min(c->scene_lo[a], std::min(v0, std::min(v1, v2)));
+                c->scene_hi[a] = std::max(c->scene_hi[a], std::max(v0, std::max(v1, v2)));
+            }
+        }
+        if (total == 0) for (int k = 0; k < 3; ++k) { c->scene_lo[k] = 0.f; c->scene_hi[k] = 1.f; }
         std::vector<float> geo(9 * (size_t)total);
         for (int t = 0; t < total; ++t)
             for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) geo[9 * (size_t)t + 3 * k + a] = c->h_tri[(size_t)t * 32 + 4 * k + a];
@@ -440,9 +463,9 @@ static void secondary_edge_batch(pb_ctx *c, const RenderParams &P, const EdgePar
     RayRec *cam_rays = c->d_edge_rays.as<RayRec>();
     HitRec *cam_hits = S.hit0.as<HitRec>();
     launch_edge_secondary_rays(st, P, Q, rays, guide_spc);
-    launch_trace(st, c->view, 2 * (int64_t)P.n, rays, hits, nullptr);
+    trace_wavefront(c, 2 * (int64_t)P.n, rays, hits);
     launch_edge_secondary_camera(st, P, Q, rays, hits, cam_rays, guide_spc);
-    launch_trace(st, c->view, (int64_t)P.n, cam_rays, cam_hits, nullptr);
+    trace_wavefront(c, (int64_t)P.n, cam_rays, cam_hits);
     launch_edge_secondary_eval(st, P, Q, rays, hits, cam_rays, cam_hits, d_dLdI, inv_sppse, guide_out, guide_spc);
     c->launches += 5;
 }
@@ -499,7 +522,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.thr_out = Bp.last ? nullptr : S.thr[(k + 1) & 1].as<float4>();
                         E.rad = S.rad.as<float4>();
                         launch_shade(st, P, Bp, E);
-                        launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr);
+                        trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits);
                         launch_resolve(st, P, Bp, E, nullptr);
                         c->launches += 3;
                     }
@@ -686,7 +709,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 launch_shade(st, P, bps[k], E);
                 cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
                 PB_CUDA(cudaEventRecord(t0, st));
-                launch_trace(st, c->view, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr);
+                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits);
                 PB_CUDA(cudaEventRecord(t1, st));
                 launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
                 c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;

@@ -126,7 +126,8 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_sort_hist, d_sort_perm;
+    float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     // boundary terms
     int num_sec = 0;
     float sec_sum = 0.f;

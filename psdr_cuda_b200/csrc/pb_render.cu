@@ -37,6 +37,18 @@ __global__ void __launch_bounds__(128) k_trace_ww(const BvhNode *__restrict__ no
     if (t_out) t_out[i] = h.t;
 }
 
+template <bool FMA_SLAB>
+__global__ void __launch_bounds__(128) k_trace_spec(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
+                                                    const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = ldg4(rp), b = ldg4(rp + 1);
+    const Hit h = trace_closest_spec<FMA_SLAB>(nodes, leaf, f3(a), f3(b), a.w, b.w);
+    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    if (t_out) t_out[i] = h.t;
+}
+
 // Block-local regrouping: the 256 rays of a block are counting-sorted in shared memory by (active, direction bin) so
 // that each warp traverses rays that point the same way and inactive lanes collect in warps that exit at once.
 // Only the thread<->ray assignment changes; every ray's hit is written back to its own slot.
@@ -207,7 +219,10 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
         float3 wo = ps.p - v.its.p;
         const float dist = safe_sqrt(squared_norm(wo));
         wo = wo / dist;
-        store_ray(rays_out + (size_t)(B.nb + j) * P.n + i, v.its.p, wo, a1 ? INFINITY : -1.f);
+        // The connection is valid iff the closest hit lies beyond dist - ShadowEpsilon and is an emitter (direct.cpp:130-131):
+        // nothing past the sampled point can change that, and any closer hit decides it, so the ray is bounded and
+        // flagged as an occlusion query.
+        store_ray(rays_out + (size_t)(B.nb + j) * P.n + i, v.its.p, wo, a1 ? fmaf(dist, 1e-5f, dist) + 2e-3f : -1.f, dist - kShadowEpsilon);
     }
 }
 
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 int g_trace_blocks_per_sm = 8;
-int g_trace_variant = 4;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
+int g_trace_variant = 7;   // 7: counting-sorted + compacted wavefront (pb_sort.cu) for render calls; pb_trace uses the speculative kernel   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out) {
     if (n <= 0) return;
     switch (g_trace_variant) {
@@ -338,6 +353,9 @@ void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec
         case 1: k_trace_ww<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
         case 2: k_trace_sorted<false><<<nblk(n, 256), 256, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
         case 3: k_trace_sorted<true><<<nblk(n, 256), 256, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 5: k_trace_spec<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 6: k_trace_spec<true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 7: k_trace_spec<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
         default: {
             static unsigned long long *counter = nullptr;   // one per process; launches on a stream are ordered
             if (!counter) cudaMalloc(&counter, sizeof(unsigned long long));

@@ -139,6 +139,100 @@ PB_D Hit trace_closest_ww(const BvhNode *__restrict__ nodes, const LeafTri *__re
     return best;
 }
 
+// Speculative while-while traversal (Aila & Laine 2009, "postponed leaf"): a lane that reaches a leaf parks it and keeps
+// descending inner nodes until every lane of the warp has parked one, then the warp tests triangles together. The ncu
+// source view of the plain loop shows why: the triangle test is 30 % of the warp-instructions at 5 of 32 lanes active.
+//   FMA_SLAB  box test as fma(lo, 1/d, -o/d) (12 FFMA instead of 12 FADD + 12 FMUL). Its rounding error in world units is
+//             2^-24 |o|, covered by the box padding when ray origins lie inside the scene (wavefront rays do; the
+//             camera / user rays of pb_trace may not and use the subtract-multiply form).
+//   t_occ > 0 occlusion query: stop as soon as any hit closer than t_occ is known (shadow rays only need to know that
+//             the emitter sample is blocked; direct.cpp:130-131).
+// The triangle test rejects on the sign of the unnormalised barycentrics before paying for the division; survivors run
+// the exact utils.h:67-77 arithmetic, so accepted hits are bit-identical to the oracle's.
+template <bool FMA_SLAB, int STACK = 64>
+PB_D Hit trace_closest_spec(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, float3 o, float3 d, float tmax, float t_occ) {
+    Hit best;
+    best.tri = -1; best.shape = -1; best.u = -1.f; best.v = -1.f; best.t = tmax;
+    if (!(tmax > 0.f)) { best.t = INFINITY; return best; }
+    float ix = clamp_idir(d.x), iy = clamp_idir(d.y), iz = clamp_idir(d.z);
+    float ox = o.x, oy = o.y, oz = o.z;
+    if (FMA_SLAB) {
+        ix = fminf(fmaxf(ix, -1e30f), 1e30f); iy = fminf(fmaxf(iy, -1e30f), 1e30f); iz = fminf(fmaxf(iz, -1e30f), 1e30f);
+        ox = o.x * ix; oy = o.y * iy; oz = o.z * iz;
+    }
+    int stack[STACK];
+    int sp = 0;
+    int node = 0, parked = 0;   // parked: a leaf code (< 0) waiting to be intersected, 0 = none
+    while (node != kTraverseDone) {
+        bool searching = true;
+        while (node >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2), l = ldg4(np + 3);
+            float t0, t1;
+#define PB_SLAB(lo, hi, oc, ic) if (FMA_SLAB) { t0 = fmaf(lo, ic, -oc); t1 = fmaf(hi, ic, -oc); } else { t0 = (lo - oc) * ic; t1 = (hi - oc) * ic; }
+            PB_SLAB(a.x, a.w, ox, ix)
+            float ln = fminf(t0, t1), lf = fmaxf(t0, t1);
+            PB_SLAB(a.y, b.x, oy, iy)
+            ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+            PB_SLAB(a.z, b.y, oz, iz)
+            ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+            PB_SLAB(b.z, c.y, ox, ix)
+            float rn = fminf(t0, t1), rf = fmaxf(t0, t1);
+            PB_SLAB(b.w, c.z, oy, iy)
+            rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+            PB_SLAB(c.x, c.w, oz, iz)
+            rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+#undef PB_SLAB
+            const bool hl = fmaxf(ln, 0.f) <= fminf(lf, best.t), hr = fmaxf(rn, 0.f) <= fminf(rf, best.t);
+            int cl = __float_as_int(l.x), cr = __float_as_int(l.y);
+            if (hl && hr) {
+                if (rn < ln) { int t = cl; cl = cr; cr = t; }
+                stack[sp++] = cr;
+                node = cl;
+            } else if (hl) node = cl;
+            else if (hr) node = cr;
+            else node = sp ? stack[--sp] : kTraverseDone;
+            if (node < 0 && node != kTraverseDone && parked == 0) {   // first leaf: park it, keep descending
+                searching = false;
+                parked = node;
+                node = sp ? stack[--sp] : kTraverseDone;
+            }
+            if (__ballot_sync(__activemask(), searching) == 0) break;
+        }
+        while (parked < 0) {
+            const int v = ~parked;
+            const int first = v >> 3, cnt = (v & 7) + 1;
+            for (int i = 0; i < cnt; ++i) {
+                const float4 *tp = reinterpret_cast<const float4 *>(leaf + first + i);
+                const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                const float3 p0 = f3(ta), e1 = f3(tb), e2 = f3(tc);
+                // unnormalised barycentrics with the oracle's op order; sign-only early outs (guarded against underflow of u, v)
+                const float3 h = cross(d, e2);
+                const float a = dot(e1, h);
+                const float3 sv = sub3_rn(o, p0);
+                const float U = dot(sv, h);
+                const bool guard = fabsf(a) <= 1e18f;
+                if (guard && U * a < 0.f && fabsf(U) >= 1e-20f) continue;
+                const float3 q = cross(sv, e1);
+                const float V = dot(d, q);
+                if (guard && V * a < 0.f && fabsf(V) >= 1e-20f) continue;
+                const float f = div_rn(1.f, a);
+                const float u = mul_rn(f, U), w = mul_rn(f, V), t = mul_rn(f, dot(e2, q));
+                const int id = __float_as_int(ta.w);
+                if (u >= 0.f && w >= 0.f && add_rn(u, w) <= 1.f && t > kRayEpsilon && t < tmax &&
+                    (t < best.t || (t == best.t && (best.tri < 0 || id < best.tri)))) {
+                    best.t = t; best.u = u; best.v = w; best.tri = id; best.shape = __float_as_int(tb.w);
+                }
+            }
+            if (best.t <= t_occ) { node = kTraverseDone; break; }   // occluded: nothing else matters
+            parked = 0;
+            if (node < 0 && node != kTraverseDone) { parked = node; node = sp ? stack[--sp] : kTraverseDone; }
+        }
+    }
+    if (best.tri < 0) best.t = INFINITY;
+    return best;
+}
+
 // 6-bit direction bin (octahedral map, 8x8, Morton order) used to regroup the rays of a block into coherent warps
 PB_D int direction_bin(float3 d) {
     const float inv = 1.f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));

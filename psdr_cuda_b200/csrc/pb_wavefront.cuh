@@ -29,10 +29,10 @@ PB_D HitRec load_hit(const HitRec *p) {
     r.tri = __float_as_int(h.x); r.shape = __float_as_int(h.y); r.u = h.z; r.v = h.w;
     return r;
 }
-PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax) {
+PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax, float t_occ = 0.f) {
     float4 *q = reinterpret_cast<float4 *>(p);
     q[0] = make_float4(o.x, o.y, o.z, tmax);
-    q[1] = make_float4(d.x, d.y, d.z, 0.f);
+    q[1] = make_float4(d.x, d.y, d.z, t_occ);   // t_occ > 0: occlusion query, any hit closer than t_occ ends the traversal
 }
 
 PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const EventBuffers &E) {

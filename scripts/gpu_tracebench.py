@@ -8,25 +8,23 @@ ctx = capi.Context(0)
 ctx.load_description(desc, dict(width=512, height=16, spp=256, sppe=0, sppse=0))
 for b in range(4): ctx.grad_require(capi.PARAM_BSDF_TEXTURE, b, "reflectance")
 ctx.configure()
-integ = capi.make_integrator("path", max_depth=5)
 B = 1 << 20
 ctx.set_batch(B)
-img = ctx.render_d(integ)
-ctx.render_d_vjp(integ, torch.ones_like(img))
 bufs = []
 for k in range(5):
+    ctx.configure(reseed=True)
+    ctx.render_c(capi.make_integrator("path", max_depth=k + 1))
     ptr, nbytes = ctx.debug_ray_buffer(k)
     n = 2 * B
     t = torch.empty((n, 8), dtype=torch.float32, device="cuda")
     ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(n * 32), 3)
     bufs.append(t)
-    act = (t[:, 3] > 0).float().mean().item()
     print("event", k, "active fraction bsdf %.3f light %.3f" % ((t[:B, 3] > 0).float().mean().item(), (t[B:, 3] > 0).float().mean().item()))
 ref = {}
 runs = []
 for v in variants:
     if v == 4:
-        runs += [(4, 4), (4, 8), (4, 12), (4, 16)]
+        runs += [(4, 8)]
     else:
         runs.append((v, 8))
 for v, bps in runs:
@@ -39,7 +37,11 @@ for v, bps in runs:
             hits, tt = ctx.trace(r)
             key = (k, part)
             if key not in ref: ref[key] = (hits.clone(), tt.clone())
-            else: assert torch.equal(hits, ref[key][0]) and torch.equal(tt.view(torch.int32), ref[key][1].view(torch.int32)), (v, key)
+            elif v < 5: assert torch.equal(hits, ref[key][0]) and torch.equal(tt.view(torch.int32), ref[key][1].view(torch.int32)), (v, key)
+            else:   # occlusion queries may stop at a different (closer-than-t_occ) hit: compare where no early-out applies
+                same = (hits == ref[key][0]).all(dim=1)
+                occl = (tt <= r[:, 7]) & (r[:, 7] > 0)
+                assert bool((same | occl).all()), (v, key, int((~(same | occl)).sum()))
             ms = []
             for _ in range(5):
                 ctx.trace(r); ms.append(ctx.stats()["trace_ms"])

@@ -6,19 +6,15 @@ variants = [int(v) for v in sys.argv[1].split(",")]
 desc = scene_io.load_scene_description('tests/data/scenes/cbox_bunny.xml')
 ctx = capi.Context(0)
 ctx.load_description(desc, dict(width=512, height=16, spp=256, sppe=0, sppse=0))
-for b in range(4): ctx.grad_require(capi.PARAM_BSDF_TEXTURE, b, "reflectance")
 ctx.configure()
-integ = capi.make_integrator("path", max_depth=5)
 B = 1 << 20
 ctx.set_batch(B)
 ctx.debug_set("trace_variant", 0)
-img = ctx.render_d(integ)
-ctx.render_d_vjp(integ, torch.ones_like(img))
+ctx.render_c(capi.make_integrator("path", max_depth=2))
 ptr, nbytes = ctx.debug_ray_buffer(1)
 t = torch.empty((2 * B, 8), dtype=torch.float32, device="cuda")
 ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(2 * B * 32), 3)
 torch.cuda.synchronize()
-print("PROFILE_START")
 for v in variants:
     ctx.debug_set("trace_variant", v)
     for _ in range(2):
