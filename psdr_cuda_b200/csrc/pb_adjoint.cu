@@ -25,6 +25,7 @@ PB_D void bsdf_eval_grad_tex(const BsdfRec *b, const Its &its, float3 wo, float3
         const TexRef &t = b->tex[TEX_REFLECTANCE];
         if (!t.grad) return;
         const float3 gr = g * (kInvPi * cos_o);
+        if (!finite3(gr)) return;   // degenerate sample (e.g. zero pdf): no contribution rather than a poisoned gradient
         if (t.w == 1 && t.h == 1) { acc += gr; return; }
         const TexTap tap = tex_tap(t, its.uv);
         const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
@@ -143,9 +144,9 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                     }
                     if (cont) kk += gw;
                     const float gc = pdot(kk, rho) * kInvPi / pdf0;
-                    if (gc != 0.f) {
+                    if (gc != 0.f && isfinite(gc)) {
                         const ConnGrad cg = connection_vjp(its.p, its1.p, its.sh.n, its1.n, 1.f, gc);
-                        g_p += cg.p; g_shn += cg.sh_n;
+                        if (finite3(cg.p) && finite3(cg.sh_n)) { g_p += cg.p; g_shn += cg.sh_n; }
                         point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, cg.q, cg.n_q, cg.J);
                     }
                 }
@@ -176,9 +177,9 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
                     const float gc = pdot(gL * Le, rho) * kInvPi * weight / ps.pdf;
-                    if (gc != 0.f) {
+                    if (gc != 0.f && isfinite(gc)) {
                         const ConnGrad cg = connection_vjp(its.p, ps.p, its.sh.n, its1.n, 1.f, gc);
-                        g_p += cg.p; g_shn += cg.sh_n;
+                        if (finite3(cg.p) && finite3(cg.sh_n)) { g_p += cg.p; g_shn += cg.sh_n; }
                         point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, cg.q, f3(0.f), cg.J);     // sampled point + its Jacobian (mesh.cpp:317-328)
                         point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, f3(0.f), cg.n_q, 0.f);   // normal of the triangle the shadow ray hit
                     }

@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(128) k_edge_primary_rays(RenderParams P, EdgeP
     reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
 }
 
-PB_D void atomic_add3(float *p, float3 v) { atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); }
+PB_D void atomic_add3(float *p, float3 v) {
+    if (!finite3(v)) return;   // degenerate samples must not poison the gradient
+    atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z);
+}
 
 // integrator.cpp:111-117: value = x_dot_n * (L_n - L_p) / pdf / sppe; only x_dot_n carries a derivative. Its adjoint goes
 // through the two projected endpoints (perspective.cpp:85-96) back to the world-space vertices of the edge.

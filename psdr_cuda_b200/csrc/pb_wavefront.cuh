@@ -94,6 +94,11 @@ PB_D void tri_grad_scatter(float *tg, int tri, const TriGrad &g) {
     const float v[22] = {g.p0.x, g.p0.y, g.p0.z, g.e1.x, g.e1.y, g.e1.z, g.e2.x, g.e2.y, g.e2.z, g.n0.x, g.n0.y, g.n0.z,
                          g.n1.x, g.n1.y, g.n1.z, g.n2.x, g.n2.y, g.n2.z, g.fn.x, g.fn.y, g.fn.z, g.area};
 #pragma unroll
+    bool ok = true;   // a degenerate sample (zero-length connection, zero pdf) must not poison the whole gradient
+#pragma unroll
+    for (int k = 0; k < 22; ++k) ok = ok && isfinite(v[k]);
+    if (!ok) return;
+#pragma unroll
     for (int k = 0; k < 22; ++k) if (v[k] != 0.f) atomicAdd(p + k, v[k]);
 }
 struct TriFull { float3 p0, e1, e2, n0, n1, n2, fn; float area; int flags; };
