@@ -81,6 +81,12 @@ int pb_scene_set_mesh_vertices(pb_ctx *ctx, int mesh, const float *h_vertices); 
 int pb_scene_set_mesh_transform(pb_ctx *ctx, int mesh, const float h_mat[16], int left);     /* Mesh::set_transform, mesh.h:19-26 */
 /* AreaLight(radiance, mesh): src/emitter/area.cpp, src/psdr.cpp:230-231. Returns id >= 0. */
 int pb_scene_add_area_emitter(pb_ctx *ctx, int mesh, const float h_radiance[3]);
+/* EnvironmentMap(file) + scale + to_world (src/emitter/envmap.cpp, src/psdr.cpp:233-238, scene_loader.cpp:291-315): lat-long RGB
+ * radiance, interleaved. Must be added before the area emitters to keep the reference's emitter order. At configure the
+ * context appends the 12-triangle bounding mesh the envmap radiates from (src/scene/scene.cpp:135-180). Returns id >= 0. */
+int pb_scene_add_envmap(pb_ctx *ctx, int w, int h, const float *h_rgb, float scale, const float h_to_world[16]);
+int pb_scene_set_envmap_transform(pb_ctx *ctx, const float h_left[16]);   /* EnvironmentMap::set_transform, envmap.h:18-21 */
+int pb_scene_num_meshes(pb_ctx *ctx);                                      /* Scene.num_meshes (includes the bounding mesh) */
 /* Scene::configure: src/scene/scene.cpp:56-278 (sampler seeding rule, mesh preprocessing, emitter pmf, triangle table, BVH) */
 int pb_scene_configure(pb_ctx *ctx);
 /* forget sampler positions so that the next configure() restarts every stream (a fresh Scene in the reference) */

@@ -22,7 +22,7 @@ PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES = 0, 1
 SYMBOLS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream", "pb_ctx_set_retain_limit",
     "pb_scene_set_options", "pb_scene_add_sensor", "pb_scene_set_sensor_transform", "pb_scene_add_bsdf", "pb_scene_set_bsdf_texture",
-    "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_configure",
+    "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_add_envmap", "pb_scene_set_envmap_transform", "pb_scene_num_meshes", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
@@ -152,6 +152,15 @@ class Context:
     def add_area_emitter(self, mesh, radiance):
         return self._id(lib().pb_scene_add_area_emitter(self.h, mesh, _p(_f(radiance))))
 
+    def add_envmap(self, radiance, scale=1.0, to_world=None):
+        r = _f(radiance)
+        assert r.ndim == 3 and r.shape[2] == 3
+        tw = _f(to_world if to_world is not None else np.eye(4))
+        return self._id(lib().pb_scene_add_envmap(self.h, r.shape[1], r.shape[0], _p(r), C.c_float(scale), _p(tw)))
+
+    def set_envmap_transform(self, left):
+        self._chk(lib().pb_scene_set_envmap_transform(self.h, _p(_f(left))))
+
     def configure(self, reseed=False):
         if reseed:
             lib().pb_scene_reseed(self.h)
@@ -170,6 +179,9 @@ class Context:
             for k in TEX:
                 if k in b:
                     self.set_bsdf_texture(bi, k, b[k])
+        if desc.get("envmap") is not None:      # the reference loads the env emitter before the shapes (scene_loader.cpp:222-230)
+            e = desc["envmap"]
+            self.add_envmap(e["radiance"], e["scale"], e["to_world"])
         emitter_of = {e["mesh"]: e for e in desc["emitters"]}
         for mi, m in enumerate(desc["meshes"]):
             self.add_mesh(m["verts"], m["faces"], m.get("uvs"), m.get("uv_faces"), m["face_normals"], m["enable_edges"], m["bsdf"], m["to_world"])

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 float3 gval = f3(0.f);
                 if (a1) {
                     float weight = inv_nb;
-                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
                     const float3 Le = emitter_Le(P.S, its1, true);
                     L += Le * f * (scale * weight);
                     gval += gL * Le * (scale * weight);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                     float3 kk = f3(0.f);
                     if (a1) {
                         float weight = inv_nb;
-                        if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
+                        if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
                         kk += gL * emitter_Le(P.S, its1, true) * weight;
                     }
                     if (cont) kk += gw;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
         }
         for (int j = 0; j < B.nl; ++j) {
             const float2 s2 = rng.next_2d();
-            const PositionSample ps = sample_emitter_position(P.S, s2, v.active);
+            const PositionSample ps = sample_emitter_position(P.S, v.its.p, s2, v.active);
             bool a1 = v.active && ps.valid;
             float3 wo = ps.p - its.p;
             const float dist_sqr = squared_norm(wo);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                     if (gc != 0.f && isfinite(gc)) {
                         const ConnGrad cg = connection_vjp(its.p, ps.p, its.sh.n, its1.n, 1.f, gc);
                         if (finite3(cg.p) && finite3(cg.sh_n)) { g_p += cg.p; g_shn += cg.sh_n; }
-                        point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, cg.q, f3(0.f), cg.J);     // sampled point + its Jacobian (mesh.cpp:317-328)
+                        if (ps.tri >= 0) point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, cg.q, f3(0.f), cg.J);     // sampled point + its Jacobian (mesh.cpp:317-328); envmap samples are detached (envmap.cpp:72-95)
                         point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, f3(0.f), cg.n_q, 0.f);   // normal of the triangle the shadow ray hit
                     }
                 }

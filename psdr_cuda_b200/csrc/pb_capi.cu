@@ -91,6 +91,49 @@ static void build_csr(HostMesh &m) {
         }
 }
 
+// Bitmap<3>::eval on the host (bitmap.cpp:43-89), used for the envmap cell masses (envmap.cpp:17-21)
+static float3 host_tex_eval3(const HostTexture &t, float u, float v, bool flip_v) {
+    const float *d = t.data.data();
+    if (t.w == 1 && t.h == 1) return f3(d[0], d[1], d[2]);
+    if (flip_v) v = -v;
+    u -= std::floor(u); v -= std::floor(v);
+    u *= (float)(t.w - 1); v *= (float)(t.h - 1);
+    int px = (int)std::floor(u), py = (int)std::floor(v);
+    const float w1x = u - (float)px, w1y = v - (float)py, w0x = 1.f - w1x, w0y = 1.f - w1y;
+    px = std::min(px, t.w - 2); py = std::min(py, t.h - 2);
+    const int i = py * t.w + px;
+    float o[3];
+    for (int k = 0; k < 3; ++k) {
+        const float v00 = d[i * 3 + k], v10 = d[(i + 1) * 3 + k], v01 = d[(i + t.w) * 3 + k], v11 = d[(i + t.w + 1) * 3 + k];
+        const float a = fmaf(w0x, v00, w1x * v10), b = fmaf(w0x, v01, w1x * v11);
+        o[k] = fmaf(w0y, a, w1y * b);
+    }
+    return f3(o[0], o[1], o[2]);
+}
+
+// EnvironmentMap::configure (envmap.cpp:10-26): luminance * sin(theta) mass of every cell of the 2(w-1) x 2(h-1) grid
+static void configure_envmap_distribution(pb_ctx *c, HostEmitter &e) {
+    if (!e.env_dirty) return;
+    const int w = e.env_radiance.w, h = e.env_radiance.h;
+    PB_ASSERT_MSG(w > 1 && h > 1, "Environment map must be larger than 1x1");
+    const int rx = (w - 1) << 1, ry = (h - 1) << 1;
+    e.env_res[0] = rx; e.env_res[1] = ry;
+    const float ux = 1.f / (float)rx, uy = 1.f / (float)ry;
+    std::vector<float> pmf((size_t)rx * ry), cmf((size_t)rx * ry);
+    for (int i = 0; i < rx; ++i)
+        for (int j = 0; j < ry; ++j) {
+            const float3 col = host_tex_eval3(e.env_radiance, ((float)i + .5f) * ux, ((float)j + .5f) * uy, false);
+            const float theta = ((float)j + .5f) * (kPi / (float)ry);
+            pmf[(size_t)i * ry + j] = (col.x * .2126f + col.y * .7152f + col.z * .0722f) * std::sin(theta);
+        }
+    float acc = 0.f;
+    for (size_t k = 0; k < pmf.size(); ++k) { acc += pmf[k]; cmf[k] = acc; }
+    e.env_sum = acc;
+    e.d_env_pmf.upload(pmf, c->stream); e.d_env_cmf.upload(cmf, c->stream);
+    e.env_radiance.d.upload(e.env_radiance.data, c->stream);
+    e.env_dirty = false;
+}
+
 // perspective.cpp:11-32
 static void configure_sensor(HostSensor &s, int W, int H) {
     const float aspect = (float)W / (float)H;
@@ -247,12 +290,29 @@ static void configure(pb_ctx *c) {
         PB_ASSERT_MSG(count <= std::numeric_limits<int>::max(), "Too many samples (integrator.cpp:73-74)");
         if (c->sampler_count[k] != count) { c->sampler_count[k] = count; c->sampler_offset[k] = 0; }
     }
+    // sensors first: the camera positions are part of the scene box the envmap radiates from (scene.cpp:104-119)
+    for (auto &s : c->sensors) configure_sensor(s, c->width, c->height);
+    // environment lighting: (re)create the bounding mesh as the last mesh (scene.cpp:135-180)
+    if (c->has_bound_mesh) { c->meshes.pop_back(); c->has_bound_mesh = false; }
+    if (c->emitter_env >= 0) {
+        c->meshes.emplace_back();
+        HostMesh &b = c->meshes.back();
+        static const int face_data[3][12] = {{0, 0, 1, 1, 2, 2, 0, 0, 0, 0, 4, 4}, {1, 3, 5, 7, 3, 7, 5, 4, 2, 6, 7, 6}, {3, 2, 7, 3, 7, 6, 1, 5, 6, 4, 5, 7}};
+        b.nv = 8; b.nf = 12; b.flags = 1; b.bsdf = -1; b.emitter = c->emitter_env;
+        b.verts.assign(24, 0.f);
+        b.faces.resize(36);
+        for (int f = 0; f < 12; ++f) for (int j = 0; j < 3; ++j) b.faces[3 * f + j] = face_data[j][f];
+        build_edges(b);
+        build_csr(b);
+        c->emitters[c->emitter_env].mesh = (int)c->meshes.size() - 1;
+        c->has_bound_mesh = true;
+    }
     // meshes -> triangle table
     int total = 0;
     for (auto &m : c->meshes) { m.face_offset = total; total += m.nf; }
     c->num_tri = total;
     c->d_tri.reserve(std::max<size_t>(1, total) * sizeof(TriRec));
-    for (size_t i = 0; i < c->meshes.size(); ++i) {
+    auto preprocess = [&](size_t i) {
         HostMesh &m = c->meshes[i];
         if (m.topo_dirty) {
             m.d_faces.upload(m.faces, st);
@@ -272,10 +332,37 @@ static void configure(pb_ctx *c) {
                                m.d_csr_off.as<int>(), m.d_csr_face.as<int>(), m.d_uvs.as<float>(), m.d_uv_faces.as<int>(), m.d_vworld.as<float>(),
                                m.d_fcross.as<float4>(), m.d_vnormal.as<float>(), c->d_tri.as<TriRec>(), m.d_face_area.as<float>());
         c->launches += 4;
-    }
+    };
+    const size_t num_regular = c->meshes.size() - (c->has_bound_mesh ? 1 : 0);
+    for (size_t i = 0; i < num_regular; ++i) preprocess(i);
     c->h_tri.resize((size_t)total * 32);
-    if (total) PB_CUDA(cudaMemcpyAsync(c->h_tri.data(), c->d_tri.p, (size_t)total * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
+    const int regular_tris = total - (c->has_bound_mesh ? 12 : 0);
+    if (regular_tris) PB_CUDA(cudaMemcpyAsync(c->h_tri.data(), c->d_tri.p, (size_t)regular_tris * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
+    if (c->has_bound_mesh) {
+        // scene box: all vertices + camera positions, upper initialised to the smallest positive float (scene.cpp:88-89 quirk),
+        // grown by 5 % of its smallest extent (scene.cpp:136-137)
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<float>::max(); hi[k] = std::numeric_limits<float>::min(); }
+        for (int t = 0; t < regular_tris; ++t) {
+            const float *q = &c->h_tri[(size_t)t * 32];
+            for (int a = 0; a < 3; ++a)
+                for (float v : {q[a], q[a] + q[4 + a], q[a] + q[8 + a]}) { lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
+        }
+        for (auto &s : c->sensors) {
+            const float p[3] = {s.rec.camera_pos.x, s.rec.camera_pos.y, s.rec.camera_pos.z};
+            for (int a = 0; a < 3; ++a) { lo[a] = p[a] < lo[a] ? p[a] : lo[a]; hi[a] = p[a] > hi[a] ? p[a] : hi[a]; }
+        }
+        float margin = (hi[0] - lo[0]) * 0.05f;
+        for (int a = 1; a < 3; ++a) margin = std::min(margin, (hi[a] - lo[a]) * 0.05f);
+        for (int a = 0; a < 3; ++a) { lo[a] -= margin; hi[a] += margin; c->env_lower[a] = lo[a]; c->env_upper[a] = hi[a]; }
+        HostMesh &b = c->meshes.back();
+        for (int i = 0; i < 8; ++i) for (int j = 0; j < 3; ++j) b.verts[3 * i + j] = (i & (1 << j)) ? hi[j] : lo[j];
+        b.verts_dirty = true;
+        preprocess(c->meshes.size() - 1);
+        PB_CUDA(cudaMemcpyAsync(c->h_tri.data() + (size_t)regular_tris * 32, c->d_tri.as<TriRec>() + regular_tris, 12 * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+    }
     // face-area pmf / cmf per emitter mesh (mesh.cpp:238-249): sequential fp32 sums, as the oracle
     for (auto &m : c->meshes) {
         if (m.emitter < 0) continue;
@@ -322,16 +409,15 @@ static void configure(pb_ctx *c) {
         c->launches += 1;
         c->view.num_nodes = (int)dn.size();
     }
-    // sensors
-    for (auto &s : c->sensors) configure_sensor(s, c->width, c->height);
-    // emitters (scene.cpp:183-196, area.cpp:10-17)
+    // emitters (scene.cpp:183-196, area.cpp:10-17; the envmap keeps its default weight 1, emitter.h:27)
     std::vector<EmitterRec> er(c->emitters.size());
     if (!c->emitters.empty()) {
         std::vector<float> w, cmf;
         float acc = 0.f;
         for (auto &e : c->emitters) {
             const HostMesh &m = c->meshes[e.mesh];
-            e.sampling_weight = m.total_area * (e.radiance[0] * .2126f + e.radiance[1] * .7152f + e.radiance[2] * .0722f);
+            if (e.type == EMITTER_AREA) e.sampling_weight = m.total_area * (e.radiance[0] * .2126f + e.radiance[1] * .7152f + e.radiance[2] * .0722f);
+            else { configure_envmap_distribution(c, e); e.sampling_weight = 1.f; }
             w.push_back(e.sampling_weight);
             acc += e.sampling_weight;
             cmf.push_back(acc);
@@ -350,6 +436,15 @@ static void configure(pb_ctx *c) {
             r.radiance = f3(e.radiance[0], e.radiance[1], e.radiance[2]);
             r.face_cmf = m.d_face_cmf.as<float>(); r.face_pmf = m.d_face_area.as<float>();
             r.face_sum = m.face_sum; r.num_faces = m.nf; r.face_offset = m.face_offset;
+            if (e.type == EMITTER_ENVMAP) {
+                r.env_radiance.data = e.env_radiance.d.as<float>(); r.env_radiance.grad = nullptr;
+                r.env_radiance.w = e.env_radiance.w; r.env_radiance.h = e.env_radiance.h; r.env_radiance.c = 3;
+                r.env_scale = e.env_scale; r.env_res_x = e.env_res[0]; r.env_res_y = e.env_res[1]; r.env_cells = e.env_res[0] * e.env_res[1];
+                const Mat4h tw = matmul(e.env_left, e.env_raw);   // envmap.cpp:23
+                r.env_to_world = to_dev(tw); r.env_from_world = to_dev(inverse(tw));
+                r.env_lower = f3(c->env_lower[0], c->env_lower[1], c->env_lower[2]); r.env_upper = f3(c->env_upper[0], c->env_upper[1], c->env_upper[2]);
+                r.env_sum = e.env_sum; r.env_cmf = e.d_env_cmf.as<float>(); r.env_pmf = e.d_env_pmf.as<float>();
+            }
         }
     }
     c->d_emitters.upload(er, st);
@@ -381,7 +476,7 @@ static void configure(pb_ctx *c) {
     V.meshes = c->d_meshes.as<MeshRec>(); V.bsdfs = c->d_bsdfs.as<BsdfRec>(); V.emitters = c->d_emitters.as<EmitterRec>();
     V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
-    V.emitter_env = -1;
+    V.emitter_env = c->emitter_env;
     V.tri_grad = nullptr;
     configure_edges(c);
     // gradient layout
@@ -915,12 +1010,37 @@ int pb_scene_add_area_emitter(pb_ctx *c, int mesh, const float *radiance) {
         HostEmitter e;
         e.type = EMITTER_AREA; e.mesh = mesh;
         for (int k = 0; k < 3; ++k) e.radiance[k] = radiance[k];
-        c->emitters.push_back(e);
+        c->emitters.push_back(std::move(e));
         c->meshes[mesh].emitter = (int)c->emitters.size() - 1;
         c->ready = false;
         return (int)c->emitters.size() - 1;
     });
 }
+int pb_scene_add_envmap(pb_ctx *c, int w, int h, const float *rgb, float scale, const float *to_world) {
+    return guard_id(c, [&] {
+        PB_ASSERT_MSG(c->emitter_env < 0, "A scene is only allowed to have one envmap!");
+        PB_ASSERT_MSG(rgb && w > 1 && h > 1, "Invalid environment map");
+        PB_ASSERT_MSG(!c->has_bound_mesh, "internal: bounding mesh present");
+        c->emitters.emplace_back();
+        HostEmitter &e = c->emitters.back();
+        e.type = EMITTER_ENVMAP;
+        e.env_radiance.w = w; e.env_radiance.h = h; e.env_radiance.c = 3;
+        e.env_radiance.data.assign(rgb, rgb + (size_t)w * h * 3);
+        e.env_scale = scale;
+        e.env_raw = from_ptr(to_world);
+        c->emitter_env = (int)c->emitters.size() - 1;
+        c->ready = false;
+        return c->emitter_env;
+    });
+}
+int pb_scene_set_envmap_transform(pb_ctx *c, const float *left) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->emitter_env >= 0, "No environment map");
+        c->emitters[c->emitter_env].env_left = from_ptr(left);
+        c->ready = false;
+    });
+}
+int pb_scene_num_meshes(pb_ctx *c) { return (int)c->meshes.size(); }
 int pb_scene_configure(pb_ctx *c) { return guard(c, [&] { configure(c); }); }
 int pb_scene_reseed(pb_ctx *c) {
     for (int k = 0; k < 3; ++k) { c->sampler_count[k] = 0; c->sampler_offset[k] = 0; }

@@ -155,7 +155,7 @@ PB_D BoundarySample sample_boundary_segment_direct(const SceneView &S, const Edg
     r.edge = normalize(r.info.e1);
     r.edge2 = r.info.p2 - r.info.p0;
     pdf0 = div_rn(pdf0, norm(r.info.e1));
-    const PositionSample ps2 = sample_emitter_position(S, make_float2(sample3.y, sample3.z), true);
+    const PositionSample ps2 = sample_emitter_position(S, r.p0, make_float2(sample3.y, sample3.z), true);
     r.p2 = ps2.p; r.n = ps2.n; r.light_tri = ps2.tri; r.ls = ps2.s; r.lt = ps2.t;
     float3 e = r.p2 - r.p0;
     const float dist_sqr = squared_norm(e);

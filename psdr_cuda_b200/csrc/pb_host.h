@@ -76,6 +76,14 @@ struct HostEmitter {
     int type = 0, mesh = -1;
     float radiance[3] = {0, 0, 0};
     float sampling_weight = 0.f;
+    // environment map (envmap.h)
+    HostTexture env_radiance;
+    float env_scale = 1.f;
+    Mat4h env_raw = Mat4h::identity(), env_left = Mat4h::identity();
+    bool env_dirty = true;
+    int env_res[2] = {0, 0};
+    float env_sum = 0.f;
+    DevBuf d_env_pmf, d_env_cmf;
 };
 struct HostSensor {
     float fov_x = 45.f, near_clip = 0.1f, far_clip = 1e4f;
@@ -112,6 +120,8 @@ struct pb_ctx {
     std::vector<pb::HostBsdf> bsdfs;
     std::vector<pb::HostMesh> meshes;
     std::vector<pb::HostEmitter> emitters;
+    int emitter_env = -1;          // index of the environment emitter (scene.h m_emitter_env)
+    bool has_bound_mesh = false;   // the last mesh is the envmap's bounding box (scene.cpp:135-180)
     // sharding / tiling
     int rank = 0, world = 1;
     int64_t batch = 1 << 20;
@@ -128,6 +138,7 @@ struct pb_ctx {
     // wavefront buffers
     pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_sort_hist, d_sort_perm;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
+    float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms
     int num_sec = 0;
     float sec_sum = 0.f;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
     }
     for (int j = 0; j < B.nl; ++j) {
         const float2 s2 = rng.next_2d();
-        const PositionSample ps = sample_emitter_position(P.S, s2, v.active);
+        const PositionSample ps = sample_emitter_position(P.S, v.its.p, s2, v.active);
         const bool a1 = v.active && ps.valid;
         float3 wo = ps.p - v.its.p;
         const float dist = safe_sqrt(squared_norm(wo));
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
                 }
                 if (a1) {
                     float weight = inv_nb;
-                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its1, true));
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
                     L += emitter_Le(P.S, its1, true) * bsdf_val * weight;
                 }
                 if (B.carry && j == 0 && cont) { w_cont = bsdf_val; has_cont = true; }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B,
         }
         for (int j = 0; j < B.nl; ++j) {
             const float2 s2 = rng.next_2d();
-            const PositionSample ps = sample_emitter_position(P.S, s2, v.active);
+            const PositionSample ps = sample_emitter_position(P.S, v.its.p, s2, v.active);
             bool a1 = v.active && ps.valid;
             float3 wo = ps.p - its.p;
             const float dist_sqr = squared_norm(wo);

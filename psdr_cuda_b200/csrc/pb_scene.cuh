@@ -59,6 +59,15 @@ struct EmitterRec {
     const float *face_cmf, *face_pmf;   // area pmf of the emitter's mesh (mesh.cpp:249)
     float face_sum;
     int num_faces, face_offset, pad3;
+    // environment map (envmap.h): lat-long radiance bitmap, scale, rotation, the scene box it radiates from, and the
+    // luminance*sin(theta) cell distribution over 2(w-1) x 2(h-1) cells (last dimension fastest)
+    TexRef env_radiance;
+    float env_scale;
+    int env_res_x, env_res_y, env_cells;
+    Mat4 env_to_world, env_from_world;
+    float3 env_lower; float pad4;
+    float3 env_upper; float env_sum;
+    const float *env_cmf, *env_pmf;
 };
 struct SensorRec {
     Mat4 sample_to_camera, to_world, world_to_sample;

@@ -270,38 +270,97 @@ PB_D BsdfSample bsdf_sample(const BsdfRec *b, const Its &its, float3 smp, bool a
 
 // ---- emitters --------------------------------------------------------------------------------------------------
 PB_D bool is_emitter(const SceneView &S, int shape) { return shape >= 0 && S.meshes[shape].emitter >= 0; }
-PB_D float3 emitter_Le(const SceneView &S, const Its &its, bool active) {   // intersection.h:36-38, area.cpp:20-29
+
+PB_D float safe_acos(float x) { return acosf(fminf(fmaxf(x, -1.f), 1.f)); }
+
+// EnvironmentMap::eval_direction (envmap.cpp:42-58): world direction -> lat-long lookup (no v flip) * scale
+PB_D float3 env_eval_direction(const EmitterRec &em, float3 wi_world) {
+    const float3 v = transform_dir(em.env_from_world, wi_world);
+    float2 uv = make_float2(atan2f(v.x, -v.z) * kInvTwoPi, safe_acos(v.y) * kInvPi);
+    uv.x -= floorf(uv.x); uv.y -= floorf(uv.y);
+    return tex_eval3(em.env_radiance, uv, false) * em.env_scale;
+}
+
+PB_D float3 emitter_Le(const SceneView &S, const Its &its, bool active) {   // intersection.h:36-38
     if (!active || !its.valid) return f3(0.f);
     const int e = S.meshes[its.shape].emitter;
     if (e < 0) return f3(0.f);
     const EmitterRec &em = S.emitters[e];
-    return its.wi.z > 0.f ? em.radiance : f3(0.f);
+    if (em.type == EMITTER_AREA) return its.wi.z > 0.f ? em.radiance : f3(0.f);   // area.cpp:20-29
+    return env_eval_direction(em, -its.sh.to_world(its.wi));                      // envmap.cpp:29-39
 }
+
+// utils.h:129-145: exit point of a ray that starts inside the scene box
+PB_D void ray_intersect_scene_aabb(float3 o, float3 d, float3 lo, float3 hi, float &t, float3 &n, float &G) {
+    const float3 t1 = f3((lo.x - o.x) / d.x, (lo.y - o.y) / d.y, (lo.z - o.z) / d.z), t2 = f3((hi.x - o.x) / d.x, (hi.y - o.y) / d.y, (hi.z - o.z) / d.z);
+    const float3 t2p = f3(t1.x > t2.x ? t1.x : t2.x, t1.y > t2.y ? t1.y : t2.y, t1.z > t2.z ? t1.z : t2.z);
+    int idx = 0;
+    t = t2p.x;
+    if (t2p.y < t) { t = t2p.y; idx = 1; }
+    if (t2p.z < t) { t = t2p.z; idx = 2; }
+    n = f3(0.f);
+    const float sg = -copysignf(1.f, getc(d, idx));
+    if (idx == 0) n.x = sg; else if (idx == 1) n.y = sg; else n.z = sg;
+    G = dot(n, -d) * (1.f / sqr(t));
+}
+
 struct PositionSample { float3 p, n; float pdf; int tri; float s, t; bool valid; };
-PB_D PositionSample sample_emitter_position(const SceneView &S, float2 smp, bool active) {   // scene.cpp:427-447
+PB_D PositionSample sample_emitter_position(const SceneView &S, float3 ref_p, float2 smp, bool active) {   // scene.cpp:427-447
     PositionSample r;
     int ei = 0;
     float emitter_pdf = 1.f;
     if (S.num_emitters > 1) ei = sample_reuse(S.emitter_cmf, S.emitter_pmf, S.num_emitters, S.emitter_sum, smp.y, emitter_pdf);
     const EmitterRec &em = S.emitters[ei];
-    // mesh.cpp:306-330
-    float face_pdf;
-    const int f = sample_reuse(em.face_cmf, em.face_pmf, em.num_faces, em.face_sum, smp.x, face_pdf);
-    const float2 st = square_to_uniform_triangle(smp.x, smp.y);
-    r.tri = em.face_offset + f;
-    r.s = st.x; r.t = st.y;
-    const TriGeom g = load_tri_geom(S, r.tri);
-    r.p = bilinear(g.p0, g.e1, g.e2, st.x, st.y);
-    r.n = g.fn;
-    r.pdf = S.meshes[em.mesh].inv_total_area * emitter_pdf;
+    if (em.type == EMITTER_AREA) {   // mesh.cpp:306-330
+        float face_pdf;
+        const int f = sample_reuse(em.face_cmf, em.face_pmf, em.num_faces, em.face_sum, smp.x, face_pdf);
+        const float2 st = square_to_uniform_triangle(smp.x, smp.y);
+        r.tri = em.face_offset + f;
+        r.s = st.x; r.t = st.y;
+        const TriGeom g = load_tri_geom(S, r.tri);
+        r.p = bilinear(g.p0, g.e1, g.e2, st.x, st.y);
+        r.n = g.fn;
+        r.pdf = S.meshes[em.mesh].inv_total_area * emitter_pdf;
+    } else {                          // envmap.cpp:72-111
+        float pdf;
+        const int cell = sample_reuse(em.env_cmf, em.env_pmf, em.env_cells, em.env_sum, smp.y, pdf);
+        const int cy = cell % em.env_res_y, cx = cell / em.env_res_y;
+        const float sx = (smp.x + (float)cx) * (1.f / (float)em.env_res_x), sy = (smp.y + (float)cy) * (1.f / (float)em.env_res_y);
+        pdf *= (float)em.env_cells;
+        const float theta = sy * kPi, phi = sx * kTwoPi;
+        float st, ct, sp, cp;
+        sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+        float3 d = f3(sp * st, ct, -(cp * st));   // sphdir(theta, phi) = (cp st, sp st, ct) permuted to (y, z, -x)
+        const float inv_sin_theta = 1.f / safe_sqrt(fmaxf(sqr(d.x) + sqr(d.z), sqr(kEpsilon)));
+        if (pdf > kEpsilon) pdf *= inv_sin_theta * (.5f / sqr(kPi));
+        d = transform_dir(em.env_to_world, d);
+        float t, G;
+        ray_intersect_scene_aabb(ref_p, d, em.env_lower, em.env_upper, t, r.n, G);
+        r.p = ref_p + d * t;
+        r.pdf = pdf * G * emitter_pdf;
+        r.tri = -1; r.s = r.t = 0.f;
+    }
     r.valid = active;
     return r;
 }
-PB_D float emitter_position_pdf(const SceneView &S, const Its &its, bool active) {   // scene.cpp:451-453, area.cpp:58-62
+PB_D float emitter_position_pdf(const SceneView &S, float3 ref_p, const Its &its, bool active) {   // scene.cpp:451-453
     if (!active || !its.valid) return 0.f;
     const MeshRec &m = S.meshes[its.shape];
     if (m.emitter < 0) return 0.f;
-    return S.emitters[m.emitter].sampling_weight * m.inv_total_area;
+    const EmitterRec &em = S.emitters[m.emitter];
+    if (em.type == EMITTER_AREA) return em.sampling_weight * m.inv_total_area;   // area.cpp:58-62
+    // envmap.cpp:125-143 (no sampling_weight factor)
+    float3 d = its.p - ref_p;
+    const float dist2 = squared_norm(d);
+    d = d / safe_sqrt(dist2);
+    const float G = fabsf(dot(d, its.n)) / dist2;
+    d = transform_dir(em.env_from_world, d);
+    const float factor = G * (1.f / safe_sqrt(fmaxf(sqr(d.x) + sqr(d.z), sqr(kEpsilon)))) * (.5f / sqr(kPi));
+    float u = atan2f(d.x, -d.z) * kInvTwoPi, v = safe_acos(d.y) * kInvPi;
+    u -= floorf(u); v -= floorf(v);
+    const int ix = (int)floorf(u * (float)em.env_res_x), iy = (int)floorf(v * (float)em.env_res_y);
+    if (!(ix >= 0 && ix < em.env_res_x && iy >= 0 && iy < em.env_res_y)) return 0.f;
+    return (__ldg(em.env_pmf + ix * em.env_res_y + iy) / em.env_sum) * (float)em.env_cells * factor;
 }
 
 // ---- sensor (perspective.cpp:120-127) -------------------------------------------------------------------------------

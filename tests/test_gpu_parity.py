@@ -384,3 +384,29 @@ def test_vertex_and_albedo_gradients_together_and_sharded():
     assert [s["kind"] for s in layout] == [capi.PARAM_BSDF_TEXTURE, capi.PARAM_MESH_VERTICES] and layout[1]["count"] == 3 * 34817
     parts = sum(grads(r, 3)[0] for r in range(3))
     assert np.linalg.norm(parts - full) <= 1e-4 * np.linalg.norm(full)
+
+
+# ---- rough conductor + environment map (BASELINE.json configs[4] scene family), multi-emitter and tree scenes: primal parity ----
+@pytest.mark.parametrize("scene,w,h", [("bunny_env", 64, 64), ("bunny_env_2", 64, 36), ("cbox_bunny_mutiemitter", 48, 48), ("tree", 48, 48)])
+def test_other_fixture_scenes_renderC_renderD(scene, w, h):
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    opts = dict(width=w, height=h, spp=8, sppe=0, sppse=0)
+    pdesc = scene_io.load_scene_description(scene_path(scene))
+    odesc = orc.load_scene_description(scene_path(scene))
+    for kind, kw in (("direct", dict(bsdf_samples=1, light_samples=1)), ("direct", dict(bsdf_samples=2, light_samples=0)),
+                     ("direct", dict(bsdf_samples=0, light_samples=2)), ("path", dict(max_depth=3))):
+        osc = orc.Scene(odesc, opts)
+        osc.configure()
+        ctx = capi.Context(0)
+        ctx.load_description(pdesc, opts)
+        ctx.configure()
+        # Scene::configure products incl. the envmap's bounding mesh (scene.cpp:135-180) are bit-identical
+        assert np.array_equal(osc.triangle_info().view(np.uint32), ctx.triangle_info().view(np.uint32))
+        oi = orc.DirectIntegrator(kw["bsdf_samples"], kw["light_samples"]) if kind == "direct" else orc.PathIntegrator(kw["max_depth"])
+        integ = capi.make_integrator(kind, **kw)
+        # the alpha = 0.05 conductor amplifies last-ulp differences of sin/cos/atan2: allow a few more outlier pixels there
+        outl = 5e-3 if scene == "bunny_env" else 2e-3
+        assert_image_parity(ctx.render_c(integ).cpu().numpy(), oi.renderC(osc), outliers=outl)
+        assert_image_parity(ctx.render_d(integ).cpu().numpy(), oi.renderD(osc)[0], outliers=outl)
+        ctx.close()
