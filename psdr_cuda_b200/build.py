@@ -54,5 +54,23 @@ def build_core(force=False, verbose=False):
     return out
 
 
+def build_host(force=False):
+    """pybind11 host module psdr_cuda/_psdr_host*.so (g++), linked against lib/libpsdr_b200.so through an $ORIGIN rpath"""
+    import sysconfig
+    import pybind11
+    core = build_core()
+    out_dir = os.path.join(HERE, "compat", "psdr_cuda")
+    out = os.path.join(out_dir, "_psdr_host" + sysconfig.get_config_var("EXT_SUFFIX"))
+    srcs = [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))] + [os.path.join(ROOT, "include", "psdr_b200.h")]
+    if not force and not _stale(out, srcs + [core]):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden",
+           "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+           os.path.join(HERE, "host", "psdr_module.cpp"), "-o", out, "-L" + LIB, "-lpsdr_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_core(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

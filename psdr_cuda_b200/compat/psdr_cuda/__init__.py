@@ -1,0 +1,162 @@
+"""`import psdr_cuda` — the reference's module name (src/psdr.cpp:41) on top of the B200-native hot path.
+
+The compiled host layer `_psdr_host` (pybind11, C++) owns scene ingest, the scene objects and the calls into the C ABI;
+this file adds what is Python-side in this design: device results come back as torch CUDA tensors, and `renderD` is a
+torch.autograd node whose backward is `pb_render_d_vjp` (the reference returns Enoki autodiff arrays and relies on
+`ek.backward`; Enoki is not a dependency here).
+
+    scene = psdr_cuda.Scene(); scene.load_file("scenes/cbox_bunny.xml")
+    albedo = scene.parameter("BSDF[id=white]", "reflectance")        # torch leaf, requires_grad
+    verts  = scene.parameter("Mesh[1]", "vertex_positions")
+    scene.configure()
+    img = psdr_cuda.PathIntegrator(5).renderD(scene, 0)                # (H*W, 3) CUDA tensor attached to the graph
+    img.square().mean().backward(); albedo.grad, verts.grad
+
+Put this directory's parent (psdr_cuda_b200/compat) on sys.path, or `import psdr_cuda_b200.compat` once.
+"""
+import os
+
+import numpy as np
+
+from . import _psdr_host as _h
+from ._psdr_host import (AreaLight, BitmapD, DiffuseBSDF, EnvironmentMap, Mesh, Object, PerspectiveCamera, RenderOption,  # noqa: F401
+                         RoughConductorBSDF)
+
+Bitmap1fD = Bitmap3fD = BitmapD
+
+
+def _read_exr(path, channels):
+    """EXR decode for textures / environment maps (the reference uses tinyexr, src/core/bitmap_loader.cpp:13-53)"""
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise RuntimeError("Failed to load EXR: " + path)
+    img = img.astype(np.float32)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    else:
+        img = img[:, :, [2, 1, 0] + list(range(3, img.shape[2]))]
+    return np.ascontiguousarray(img[:, :, :channels])
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("psdr_cuda needs a CUDA device: there is no CPU fallback")
+    return torch
+
+
+class Scene(_h.Scene):
+    """Scene (src/psdr.cpp:269-278) + a registry of differentiable parameters held as torch leaves."""
+
+    def __init__(self, device=0):
+        super().__init__(device)
+        self._device = device
+        self._params = {}   # (key, field) -> torch leaf
+
+    def parameter(self, key, field, requires_grad=True):
+        """torch leaf mirroring `param_map[key].<field>` (e.g. ("BSDF[id=white]", "reflectance"), ("Mesh[1]", "vertex_positions")).
+        Edit it in place / through an optimiser; `configure()` pushes the current value into the scene."""
+        torch = _torch()
+        obj = self.param_map[key]
+        value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
+        t = torch.tensor(np.asarray(value), dtype=torch.float32, device="cuda:%d" % self._device, requires_grad=requires_grad)
+        self._params[(key, field)] = t
+        return t
+
+    def configure(self):
+        for (key, field), t in self._params.items():
+            obj = self.param_map[key]
+            val = t.detach().cpu().numpy()
+            if field == "vertex_positions":
+                obj.vertex_positions = val
+                obj.requires_grad = bool(t.requires_grad)
+            else:
+                bm = getattr(obj, field)
+                bm.data = val
+                bm.requires_grad = bool(t.requires_grad)
+        if self._params or True:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    self.set_stream(torch.cuda.current_stream(self._device).cuda_stream)
+            except ImportError:
+                pass
+        super().configure()
+
+    def _leaves_in_layout_order(self):
+        """registered leaves matched to the segments of the flat gradient vector"""
+        canon = {}
+        pm = self.param_map
+        for (key, field), t in self._params.items():
+            obj = pm[key]
+            for k2, o2 in pm.items():
+                if o2 is obj or (o2.type_name() == obj.type_name() and o2.id == obj.id and o2.id != "" and k2.split("[")[0] == key.split("[")[0]):
+                    canon[(k2, field)] = t
+            canon[(key, field)] = t
+        out = []
+        for key, field, off, cnt in self.grad_layout():
+            out.append((canon.get((key, field)), off, cnt))
+        return out
+
+
+def _image_tensor(scene):
+    torch = _torch()
+    return torch.empty((scene.opts.height * scene.opts.width, 3), dtype=torch.float32, device="cuda:%d" % scene._device)
+
+
+class _IntegratorMixin:
+    def renderC(self, scene, sensor_id=0):
+        """Integrator.renderC (src/integrator/integrator.cpp:13-29) -> (H*W, 3) CUDA tensor, pixel = y*W + x"""
+        img = _image_tensor(scene)
+        self._render_c(scene, sensor_id, img.data_ptr())
+        return img
+
+    def renderD(self, scene, sensor_id=0):
+        """Integrator.renderD (src/integrator/integrator.cpp:32-60) -> image attached to torch.autograd; backward() runs the
+        reverse-mode kernels (interior + boundary terms) and fills .grad of the registered parameters"""
+        torch = _torch()
+        segs = scene._leaves_in_layout_order()
+        leaves = [t for t, _, _ in segs if t is not None and t.requires_grad]
+        integ = self
+
+        class _RenderD(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *inputs):
+                img = _image_tensor(scene)
+                integ._render_d(scene, sensor_id, img.data_ptr())
+                return img
+
+            @staticmethod
+            def backward(ctx, g):
+                grad = torch.zeros(max(1, scene.grad_size()), dtype=torch.float32, device=g.device)
+                g = g.contiguous().float()
+                integ._render_d_vjp(scene, sensor_id, g.data_ptr(), grad.data_ptr())
+                try:
+                    from psdr_cuda_b200 import dist as _dist
+                    _dist.all_reduce_sum_(grad)
+                except ImportError:
+                    pass
+                outs = []
+                for t, off, cnt in segs:
+                    if t is not None and t.requires_grad:
+                        outs.append(grad[off:off + cnt].view_as(t))
+                return tuple(outs)
+
+        return _RenderD.apply(*leaves) if leaves else _RenderD.apply()
+
+
+class DirectIntegrator(_IntegratorMixin, _h.DirectIntegrator):
+    pass
+
+
+class PathIntegrator(_IntegratorMixin, _h.PathIntegrator):
+    pass
+
+
+class FieldExtractionIntegrator(_IntegratorMixin, _h.FieldExtractionIntegrator):
+    pass
+
+
+Integrator = _h.Integrator

@@ -1,0 +1,670 @@
+// psdr-b200 host layer: the pybind11 module behind `import psdr_cuda` — C++ host code over the C ABI of
+// include/psdr_b200.h, mirroring the Python-visible surface of the reference's module (src/psdr.cpp:41-295):
+// RenderOption, Scene (load_file / load_string / configure / opts / num_sensors / num_meshes / param_map), Mesh,
+// DiffuseBSDF, RoughConductorBSDF, Bitmap1fD / Bitmap3fD, PerspectiveCamera, AreaLight, EnvironmentMap and the
+// integrators (DirectIntegrator, FieldExtractionIntegrator, + PathIntegrator) with renderC / renderD.
+//
+// Differences that are deliberate: arrays cross the boundary as numpy arrays / raw device pointers instead of Enoki
+// arrays (Enoki is not a dependency; psdr_cuda/__init__.py wraps device results as torch tensors and wires renderD into
+// torch.autograd); scene ingest (XML subset + OBJ) is implemented here without pugixml / tinyobj.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <unistd.h>
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+
+#include "../../include/psdr_b200.h"
+#include "pb_xml.h"
+
+namespace py = pybind11;
+using namespace pbhost;
+using farray = py::array_t<float, py::array::c_style | py::array::forcecast>;
+using iarray = py::array_t<int, py::array::c_style | py::array::forcecast>;
+
+namespace {
+
+struct Mat4 {
+    float m[16];
+    Mat4() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.f : 0.f; }
+};
+Mat4 operator*(const Mat4 &a, const Mat4 &b) {
+    Mat4 c;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < 4; ++k) s = s + a.m[4 * i + k] * b.m[4 * k + j];
+            c.m[4 * i + j] = s;
+        }
+    return c;
+}
+farray mat_to_numpy(const Mat4 &m) {
+    farray a({4, 4});
+    std::memcpy(a.mutable_data(), m.m, sizeof(m.m));
+    return a;
+}
+Mat4 mat_from_numpy(const farray &a) {
+    if (a.ndim() != 2 || a.shape(0) != 4 || a.shape(1) != 4) throw std::runtime_error("expected a 4x4 matrix");
+    Mat4 m;
+    std::memcpy(m.m, a.data(), sizeof(m.m));
+    return m;
+}
+
+// ---- transform.h:14-79 ---------------------------------------------------------------------------------------------
+Mat4 m_translate(float x, float y, float z) { Mat4 m; m.m[3] = x; m.m[7] = y; m.m[11] = z; return m; }
+Mat4 m_scale(float x, float y, float z) { Mat4 m; m.m[0] = x; m.m[5] = y; m.m[10] = z; return m; }
+Mat4 m_rotate(float x, float y, float z, float angle_deg) {
+    const float ang = angle_deg * 3.14159265358979323846f / 180.f;
+    const float s = (float)std::sin((double)ang), c = (float)std::cos((double)ang), k = 1.f - c;
+    Mat4 m;
+    m.m[0] = x * x * k + c;     m.m[1] = x * y * k - z * s; m.m[2] = x * z * k + y * s;
+    m.m[4] = y * x * k + z * s; m.m[5] = y * y * k + c;     m.m[6] = y * z * k - x * s;
+    m.m[8] = z * x * k - y * s; m.m[9] = z * y * k + x * s; m.m[10] = z * z * k + c;
+    return m;
+}
+void norm3(float *v) { const float n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int k = 0; k < 3; ++k) v[k] /= n; }
+void cross3(const float *a, const float *b, float *o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+Mat4 m_look_at(const float *origin, const float *target, const float *up) {
+    float dir[3] = {target[0] - origin[0], target[1] - origin[1], target[2] - origin[2]}, left[3], new_up[3];
+    norm3(dir);
+    cross3(up, dir, left); norm3(left);
+    cross3(dir, left, new_up);
+    Mat4 m;
+    for (int i = 0; i < 3; ++i) { m.m[4 * i] = left[i]; m.m[4 * i + 1] = new_up[i]; m.m[4 * i + 2] = dir[i]; m.m[4 * i + 3] = origin[i]; }
+    return m;
+}
+
+std::vector<float> parse_vector(const std::string &str, size_t n, bool allow_short = false) {   // scene_loader.cpp:23-52
+    std::vector<float> v;
+    std::string tok;
+    for (size_t i = 0; i <= str.size(); ++i) {
+        const char ch = i < str.size() ? str[i] : ',';
+        if (ch == ',' || ch == ' ' || ch == '\t' || ch == '\n') { if (!tok.empty()) { v.push_back((float)std::atof(tok.c_str())); tok.clear(); } }
+        else tok.push_back(ch);
+    }
+    if (v.size() > n) throw std::runtime_error("Vector too long: [" + str + "]");
+    if (v.size() < n) {
+        if (!allow_short) throw std::runtime_error("Vector too short: [" + str + "]");
+        const float fill = v.empty() ? 0.f : v.back();
+        v.resize(n, fill);
+    }
+    return v;
+}
+
+Mat4 load_transform(const XmlNode *node) {   // scene_loader.cpp:80-127: left-multiplied in document order
+    Mat4 result;
+    if (!node) return result;
+    const std::string nm = node->attr("name");
+    if (nm != "to_world" && nm != "toWorld") throw std::runtime_error("Invalid transformation name: " + nm);
+    for (auto &op : node->children) {
+        Mat4 t;
+        if (op->name == "translate") t = m_translate(op->attr_float("x", 0.f), op->attr_float("y", 0.f), op->attr_float("z", 0.f));
+        else if (op->name == "rotate") t = m_rotate(op->attr_float("x", 0.f), op->attr_float("y", 0.f), op->attr_float("z", 0.f), op->attr_float("angle", 0.f));
+        else if (op->name == "scale") t = m_scale(op->attr_float("x", 1.f), op->attr_float("y", 1.f), op->attr_float("z", 1.f));
+        else if (op->name == "look_at" || op->name == "lookAt" || op->name == "lookat") {
+            auto o = parse_vector(op->attr("origin"), 3), tg = parse_vector(op->attr("target"), 3), up = parse_vector(op->attr("up"), 3);
+            t = m_look_at(o.data(), tg.data(), up.data());
+        } else if (op->name == "matrix") {
+            auto v = parse_vector(op->attr("value"), 16);
+            std::memcpy(t.m, v.data(), sizeof(t.m));
+        } else throw std::runtime_error("Unsupported transformation: " + op->name);
+        result = t * result;
+    }
+    return result;
+}
+
+// ---- Python-visible objects ------------------------------------------------------------------------------------------
+struct Object {
+    std::string id;
+    virtual ~Object() = default;
+    virtual std::string type_name() const = 0;
+    virtual std::string to_string() const { return type_name() + (id.empty() ? "" : "[id=" + id + "]"); }
+};
+
+struct Bitmap {   // Bitmap1fD / Bitmap3fD (src/core/bitmap.cpp, src/psdr.cpp:102-120)
+    int channels = 3, width = 1, height = 1;
+    std::vector<float> data;   // interleaved
+    bool dirty = true, requires_grad = false;
+    explicit Bitmap(int c = 3, float v = 0.f) : channels(c), data(c, v) {}
+    void fill(const std::vector<float> &v) { width = height = 1; data = v; data.resize(channels, v.empty() ? 0.f : v.back()); dirty = true; }
+    farray get_data() const {
+        farray a(std::vector<py::ssize_t>{(py::ssize_t)width * height, (py::ssize_t)channels});
+        std::memcpy(a.mutable_data(), data.data(), data.size() * sizeof(float));
+        return a;
+    }
+    void set_data(const farray &a) {
+        if ((size_t)a.size() != (size_t)width * height * channels) {
+            if (a.size() == channels) { width = height = 1; }
+            else throw std::runtime_error("Bitmap.data: size does not match resolution (set resolution first)");
+        }
+        data.assign(a.data(), a.data() + a.size());
+        dirty = true;
+    }
+};
+
+struct BSDF : Object { int index = -1; };
+struct Diffuse : BSDF {
+    Bitmap reflectance{3, .5f};
+    std::string type_name() const override { return "DiffuseBSDF"; }
+};
+struct RoughConductor : BSDF {
+    Bitmap alpha_u{1, .1f}, alpha_v{1, .1f}, eta{3, 0.f}, k{3, 1.f}, specular_reflectance{3, 1.f};
+    std::string type_name() const override { return "RoughConductorBSDF"; }
+};
+
+struct Mesh : Object {
+    int index = -1, bsdf = -1, emitter = -1;
+    std::vector<float> verts, uvs;
+    std::vector<int> faces, uv_faces;
+    bool use_face_normals = false, enable_edges = true, requires_grad = false;
+    bool verts_dirty = false, transform_dirty = false;
+    Mat4 to_world_raw, to_world_left, to_world_right;
+    int nv() const { return (int)verts.size() / 3; }
+    int nf() const { return (int)faces.size() / 3; }
+    std::string type_name() const override { return "Mesh"; }
+
+    void load(const std::string &path) {   // Mesh::load (mesh.cpp:62-141): positions, texcoords, fan-triangulated faces
+        std::ifstream in(path);
+        if (!in) throw std::runtime_error("Failed to load OBJ from: " + path);
+        verts.clear(); uvs.clear(); faces.clear(); uv_faces.clear();
+        std::string line;
+        std::vector<int> cv, ct;
+        while (std::getline(in, line)) {
+            if (line.size() < 2) continue;
+            if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
+                const char *p = line.c_str() + 1; char *e;
+                for (int k = 0; k < 3; ++k) { verts.push_back(std::strtof(p, &e)); p = e; }
+            } else if (line[0] == 'v' && line[1] == 't') {
+                const char *p = line.c_str() + 2; char *e;
+                for (int k = 0; k < 2; ++k) { uvs.push_back(std::strtof(p, &e)); p = e; }
+            } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+                cv.clear(); ct.clear();
+                std::istringstream ss(line.substr(1));
+                std::string tok;
+                while (ss >> tok) {
+                    int vi = 0, ti = 0;
+                    const size_t s1 = tok.find('/');
+                    vi = std::atoi(tok.substr(0, s1).c_str());
+                    if (s1 != std::string::npos) {
+                        const size_t s2 = tok.find('/', s1 + 1);
+                        const std::string t = tok.substr(s1 + 1, s2 == std::string::npos ? std::string::npos : s2 - s1 - 1);
+                        if (!t.empty()) ti = std::atoi(t.c_str());
+                    }
+                    cv.push_back(vi > 0 ? vi - 1 : nv() + vi);
+                    ct.push_back(ti > 0 ? ti - 1 : (ti < 0 ? (int)uvs.size() / 2 + ti : -1));
+                }
+                for (size_t k = 2; k < cv.size(); ++k) {
+                    faces.insert(faces.end(), {cv[0], cv[k - 1], cv[k]});
+                    uv_faces.insert(uv_faces.end(), {ct[0], ct[k - 1], ct[k]});
+                }
+            }
+        }
+        if (verts.empty()) throw std::runtime_error("Failed to load OBJ from: " + path);
+        if (uvs.empty()) uv_faces.clear();
+    }
+    farray get_vertices() const {
+        farray a(std::vector<py::ssize_t>{(py::ssize_t)nv(), 3});
+        std::memcpy(a.mutable_data(), verts.data(), verts.size() * sizeof(float));
+        return a;
+    }
+    void set_vertices(const farray &a) {
+        if ((size_t)a.size() != verts.size()) throw std::runtime_error("vertex_positions: wrong size");
+        verts.assign(a.data(), a.data() + a.size());
+        verts_dirty = true;
+    }
+    iarray get_faces() const {
+        iarray a(std::vector<py::ssize_t>{(py::ssize_t)nf(), 3});
+        std::memcpy(a.mutable_data(), faces.data(), faces.size() * sizeof(int));
+        return a;
+    }
+    void dump(const std::string &fname) const {   // Mesh::dump (mesh.cpp:354-418): object-space OBJ
+        std::ofstream out(fname);
+        if (!out) throw std::runtime_error("Failed to open: " + fname);
+        for (int v = 0; v < nv(); ++v) out << "v " << verts[3 * v] << " " << verts[3 * v + 1] << " " << verts[3 * v + 2] << "\n";
+        for (size_t t = 0; t + 1 < uvs.size(); t += 2) out << "vt " << uvs[t] << " " << uvs[t + 1] << "\n";
+        for (int f = 0; f < nf(); ++f) {
+            out << "f";
+            for (int k = 0; k < 3; ++k) {
+                out << " " << faces[3 * f + k] + 1;
+                if (!uv_faces.empty()) out << "/" << uv_faces[3 * f + k] + 1;
+            }
+            out << "\n";
+        }
+    }
+};
+
+struct Sensor : Object {
+    float fov_x = 45.f, near_clip = 0.1f, far_clip = 1e4f;
+    Mat4 to_world;
+    bool dirty = false;
+    std::string type_name() const override { return "PerspectiveCamera"; }
+};
+struct Emitter : Object {};
+struct AreaLight : Emitter {
+    float radiance[3] = {0, 0, 0};
+    int mesh = -1;
+    std::string type_name() const override { return "AreaLight"; }
+};
+struct EnvironmentMap : Emitter {
+    Bitmap radiance{3, 0.f};
+    float scale = 1.f;
+    Mat4 to_world_raw, to_world_left;
+    bool transform_dirty = false;
+    std::string type_name() const override { return "AreaLight"; }   // sic: envmap.h:58
+};
+
+struct RenderOption {   // types.h:171-182, psdr.cpp:53-72
+    int width = 0, height = 0, spp = 0, sppe = 0, sppse = 0, log_level = 1;
+    RenderOption() = default;
+    RenderOption(int w, int h, int s) : width(w), height(h), spp(s), sppe(s), sppse(s) {}
+    RenderOption(int w, int h, int s, int se) : width(w), height(h), spp(s), sppe(se), sppse(se) {}
+    RenderOption(int w, int h, int s, int se, int sse) : width(w), height(h), spp(s), sppe(se), sppse(sse) {}
+};
+
+std::string find_file(const std::string &name, const std::string &xml_dir) {
+    std::vector<std::string> trial = {name};
+    std::string d = xml_dir;
+    for (int up = 0; up < 5 && !d.empty(); ++up) {
+        trial.push_back(d + "/" + name);
+        const size_t s = d.find_last_of('/');
+        if (s == std::string::npos || s == 0) break;
+        d = d.substr(0, s);
+    }
+    for (auto &t : trial) { std::ifstream f(t); if (f.good()) return t; }
+    throw std::runtime_error("Failed to load file: " + name);
+}
+
+class Scene {
+public:
+    pb_ctx *ctx = nullptr;
+    RenderOption opts;
+    std::vector<std::shared_ptr<Sensor>> sensors;
+    std::vector<std::shared_ptr<BSDF>> bsdfs;
+    std::vector<std::shared_ptr<Mesh>> meshes;
+    std::vector<std::shared_ptr<Emitter>> emitters;
+    std::shared_ptr<EnvironmentMap> envmap;
+    std::map<std::string, std::shared_ptr<Object>> param_map;
+    bool loaded = false, uploaded = false, configured = false;
+
+    // device < 0: description only (ingest and inspection work, configure / render need a context)
+    explicit Scene(int device = 0) { if (device >= 0 && pb_ctx_create(device, &ctx)) throw std::runtime_error(pb_last_error(nullptr)); }
+    ~Scene() { if (ctx) pb_ctx_destroy(ctx); }
+    Scene(const Scene &) = delete;
+    void check(int rc) const { if (rc) throw std::runtime_error(pb_last_error(ctx)); }
+    int check_id(int rc) const { if (rc < 0) throw std::runtime_error(pb_last_error(ctx)); return rc; }
+
+    void load_file(const std::string &fname, bool auto_configure) {
+        std::ifstream in(fname);
+        if (!in) throw std::runtime_error("XML parsing failed");
+        std::stringstream ss;
+        ss << in.rdbuf();
+        std::string dir = ".";
+        const size_t s = fname.find_last_of('/');
+        if (s != std::string::npos) dir = fname.substr(0, s);
+        if (!dir.empty() && dir[0] != '/') {
+            char buf[4096];
+            if (getcwd(buf, sizeof(buf))) dir = std::string(buf) + "/" + dir;
+        }
+        load_xml(ss.str(), dir, auto_configure);
+    }
+    void load_string(const std::string &xml, bool auto_configure) { load_xml(xml, "", auto_configure); }
+
+    void load_texture(const XmlNode *node, Bitmap &bm, const std::string &xml_dir) {   // scene_loader.cpp:158-170
+        if (node->name == "texture") {
+            if (node->attr("type") != "bitmap") throw std::runtime_error("Unsupported texture type: " + node->attr("type"));
+            const XmlNode *fn = node->child("string");
+            if (!fn || fn->attr("name") != "filename") throw std::runtime_error("Failed to retrieve bitmap filename");
+            load_exr(find_file(fn->attr("value"), xml_dir), bm);
+        } else if (bm.channels == 1) {
+            bm.fill({std::stof(node->attr("value"))});
+        } else if (node->name == "float") {
+            const float v = std::stof(node->attr("value"));
+            bm.fill({v, v, v});
+        } else if (node->name == "rgb") {
+            bm.fill(parse_vector(node->attr("value"), 3, true));
+        } else throw std::runtime_error("Unsupported RGB type: " + node->name);
+    }
+    static void load_exr(const std::string &path, Bitmap &bm) {   // bitmap_loader.cpp:13-53; decoding is delegated to Python (cv2)
+        py::object img = py::module_::import("psdr_cuda").attr("_read_exr")(path, bm.channels);
+        farray a = img.cast<farray>();
+        bm.height = (int)a.shape(0); bm.width = (int)a.shape(1);
+        bm.data.assign(a.data(), a.data() + a.size());
+        bm.dirty = true;
+    }
+
+    void load_xml(const std::string &text, const std::string &xml_dir, bool auto_configure) {   // scene_loader.cpp:208-242
+        if (loaded) throw std::runtime_error("Scene already loaded!");
+        XmlParser parser(text);
+        std::unique_ptr<XmlNode> doc = parser.parse();
+        const XmlNode *root = doc->child("scene");
+        if (!root) throw std::runtime_error("XML parsing failed");
+        for (const XmlNode *node : root->all("sensor")) {
+            const XmlNode *film = node->child("film"), *sampler = node->child("sampler");
+            if (sensors.empty()) {
+                if (!film) throw std::runtime_error("Missing film node");
+                if (!sampler) throw std::runtime_error("Missing sampler node");
+                const XmlNode *w = film->named({"width"}), *h = film->named({"height"});
+                if (!w) throw std::runtime_error("Missing child node: width");
+                if (!h) throw std::runtime_error("Missing child node: height");
+                opts.width = std::stoi(w->attr("value")); opts.height = std::stoi(h->attr("value"));
+                const XmlNode *cnt = sampler->child("integer");
+                opts.spp = opts.sppe = opts.sppse = cnt ? std::stoi(cnt->attr("value")) : 0;
+            } else {
+                if (film) throw std::runtime_error("Duplicate film node");
+                if (sampler) throw std::runtime_error("Duplicate sampler node");
+            }
+            if (node->attr("type") != "perspective") throw std::runtime_error("Unsupported sensor: " + node->attr("type"));
+            auto s = std::make_shared<Sensor>();
+            s->to_world = load_transform(node->child("transform"));
+            const XmlNode *fov = node->named({"fov"});
+            if (!fov) throw std::runtime_error("Missing child node: fov");
+            s->fov_x = std::stof(fov->attr("value"));
+            if (const XmlNode *ax = node->named({"fov_axis", "fovAxis"})) if (ax->attr("value") != "x") throw std::runtime_error("Unsupported fov-axis: " + ax->attr("value"));
+            if (const XmlNode *n = node->named({"near_clip", "nearClip"})) s->near_clip = n->attr_float("value", 0.1f);
+            if (const XmlNode *n = node->named({"far_clip", "farClip"})) s->far_clip = n->attr_float("value", 1e4f);
+            sensors.push_back(s);
+        }
+        for (const XmlNode *node : root->all("bsdf")) {
+            const std::string id = node->attr("id"), type = node->attr("type");
+            if (id.empty()) throw std::runtime_error("BSDF must have an id");
+            std::shared_ptr<BSDF> b;
+            if (type == "diffuse") {
+                auto d = std::make_shared<Diffuse>();
+                const XmlNode *r = node->named({"reflectance"});
+                if (!r) throw std::runtime_error("Missing child node: reflectance");
+                load_texture(r, d->reflectance, xml_dir);
+                b = d;
+            } else if (type == "roughconductor") {
+                auto r = std::make_shared<RoughConductor>();
+                const XmlNode *alpha = node->named({"alpha"}), *eta = node->named({"eta"}), *k = node->named({"k"});
+                if (!alpha) throw std::runtime_error("Missing child node: alpha");
+                if (!eta) throw std::runtime_error("Missing child node: eta");
+                if (!k) throw std::runtime_error("Missing child node: k");
+                load_texture(alpha, r->alpha_u, xml_dir); load_texture(alpha, r->alpha_v, xml_dir);
+                load_texture(eta, r->eta, xml_dir); load_texture(k, r->k, xml_dir);
+                b = r;
+            } else throw std::runtime_error("Unsupported BSDF: " + type);
+            b->id = id; b->index = (int)bsdfs.size();
+            if (param_map.count("BSDF[id=" + id + "]")) throw std::runtime_error("Duplicate BSDF id: " + id);
+            param_map["BSDF[" + std::to_string(bsdfs.size()) + "]"] = b;
+            param_map["BSDF[id=" + id + "]"] = b;
+            bsdfs.push_back(b);
+        }
+        for (const XmlNode *node : root->all("emitter")) {
+            if (node->attr("type") != "envmap") throw std::runtime_error("Unsupported emitter: " + node->attr("type"));
+            if (envmap) throw std::runtime_error("A scene is only allowed to have one envmap!");
+            const XmlNode *fn = node->child("string");
+            if (!fn || fn->attr("name") != "filename") throw std::runtime_error("Failed to retrieve bitmap filename");
+            auto e = std::make_shared<EnvironmentMap>();
+            load_exr(find_file(fn->attr("value"), xml_dir), e->radiance);
+            if (const XmlNode *sc = node->named({"scale"})) e->scale = sc->attr_float("value", 1.f);
+            e->to_world_raw = load_transform(node->child("transform"));
+            envmap = e;
+            emitters.push_back(e);
+        }
+        for (const XmlNode *node : root->all("shape")) {
+            if (node->attr("type") != "obj") throw std::runtime_error("Unsupported shape: " + node->attr("type"));
+            const XmlNode *fn = node->child("string");
+            if (!fn || fn->attr("name") != "filename") throw std::runtime_error("Missing mesh filename");
+            auto m = std::make_shared<Mesh>();
+            m->load(find_file(fn->attr("value"), xml_dir));
+            const XmlNode *ref = node->child("ref");
+            if (!ref) throw std::runtime_error("Missing BSDF reference");
+            if (node->child("bsdf")) throw std::runtime_error("BSDFs declared under shapes are not supported.");
+            auto it = param_map.find("BSDF[id=" + ref->attr("id") + "]");
+            if (it == param_map.end()) throw std::runtime_error("Unknown BSDF id: " + ref->attr("id"));
+            m->bsdf = std::static_pointer_cast<BSDF>(it->second)->index;
+            if (const XmlNode *f = node->named({"face_normals", "faceNormals"})) m->use_face_normals = (f->attr("value") == "true");
+            m->id = node->attr("id");
+            m->to_world_raw = load_transform(node->child("transform"));
+            m->index = (int)meshes.size();
+            if (const XmlNode *em = node->child("emitter")) {
+                if (em->attr("type") != "area") throw std::runtime_error("Unsupported emitter: " + em->attr("type"));
+                const XmlNode *rad = em->named({"radiance"});
+                if (!rad) throw std::runtime_error("Missing child node: radiance");
+                auto a = std::make_shared<AreaLight>();
+                std::vector<float> v = rad->name == "float" ? std::vector<float>(3, std::stof(rad->attr("value"))) : parse_vector(rad->attr("value"), 3, true);
+                for (int k = 0; k < 3; ++k) a->radiance[k] = v[k];
+                a->mesh = m->index;
+                m->emitter = (int)emitters.size();
+                emitters.push_back(a);
+            }
+            meshes.push_back(m);
+        }
+        auto add_all = [&](auto &arr, const char *name) {   // build_param_map, scene_loader.cpp:187-205
+            for (size_t i = 0; i < arr.size(); ++i) {
+                param_map[std::string(name) + "[" + std::to_string(i) + "]"] = arr[i];
+                if (!arr[i]->id.empty()) {
+                    const std::string key = std::string(name) + "[id=" + arr[i]->id + "]";
+                    if (param_map.count(key)) throw std::runtime_error("Duplicate id: " + arr[i]->id);
+                    param_map[key] = arr[i];
+                }
+            }
+        };
+        add_all(meshes, "Mesh"); add_all(emitters, "Emitter"); add_all(sensors, "Sensor");
+        loaded = true;
+        if (auto_configure) configure();
+    }
+
+    static int tex_slot(const RoughConductor &, int k) { return k; }
+    void push_bitmap(int bsdf, int slot, Bitmap &b) {
+        if (b.dirty) { check(pb_scene_set_bsdf_texture(ctx, bsdf, slot, b.data.data(), b.width, b.height)); b.dirty = false; }
+        check(pb_grad_require(ctx, PB_PARAM_BSDF_TEXTURE, bsdf, slot, b.requires_grad ? 1 : 0));
+    }
+
+    void configure() {   // Scene::configure (scene.cpp:56-278): mirror the (possibly edited) objects into the context, then configure it
+        if (!loaded) throw std::runtime_error("Scene not loaded yet!");
+        if (!ctx) throw std::runtime_error("psdr_b200 needs a CUDA device (no CPU fallback): this Scene was created without a context");
+        check(pb_scene_set_options(ctx, opts.width, opts.height, opts.spp, opts.sppe, opts.sppse));
+        if (!uploaded) {
+            for (auto &s : sensors) check_id(pb_scene_add_sensor(ctx, s->fov_x, s->near_clip, s->far_clip, s->to_world.m));
+            for (auto &b : bsdfs) check_id(pb_scene_add_bsdf(ctx, dynamic_cast<Diffuse *>(b.get()) ? PB_BSDF_DIFFUSE : PB_BSDF_ROUGHCONDUCTOR));
+            if (envmap) check_id(pb_scene_add_envmap(ctx, envmap->radiance.width, envmap->radiance.height, envmap->radiance.data.data(), envmap->scale, envmap->to_world_raw.m));
+            for (auto &m : meshes) {
+                const int flags = (m->use_face_normals ? PB_MESH_FACE_NORMALS : 0) | (m->enable_edges ? PB_MESH_ENABLE_EDGES : 0);
+                check_id(pb_scene_add_mesh(ctx, m->nv(), m->nf(), m->verts.data(), m->faces.data(), (int)m->uvs.size() / 2, m->uvs.empty() ? nullptr : m->uvs.data(),
+                                           m->uv_faces.empty() ? nullptr : m->uv_faces.data(), flags, m->bsdf, m->to_world_raw.m));
+                if (m->emitter >= 0) check_id(pb_scene_add_area_emitter(ctx, m->index, std::static_pointer_cast<AreaLight>(emitters[m->emitter])->radiance));
+                m->verts_dirty = false;
+            }
+            uploaded = true;
+        }
+        for (auto &s : sensors) if (s->dirty) { check(pb_scene_set_sensor_transform(ctx, (int)(&s - &sensors[0]), s->to_world.m)); s->dirty = false; }
+        for (auto &b : bsdfs) {
+            if (auto *d = dynamic_cast<Diffuse *>(b.get())) push_bitmap(b->index, PB_TEX_REFLECTANCE, d->reflectance);
+            else if (auto *r = dynamic_cast<RoughConductor *>(b.get())) {
+                push_bitmap(b->index, PB_TEX_ALPHA_U, r->alpha_u); push_bitmap(b->index, PB_TEX_ALPHA_V, r->alpha_v);
+                push_bitmap(b->index, PB_TEX_ETA, r->eta); push_bitmap(b->index, PB_TEX_K, r->k);
+                push_bitmap(b->index, PB_TEX_SPECULAR_REFLECTANCE, r->specular_reflectance);
+            }
+        }
+        for (auto &m : meshes) {
+            if (m->verts_dirty) { check(pb_scene_set_mesh_vertices(ctx, m->index, m->verts.data())); m->verts_dirty = false; }
+            if (m->transform_dirty) {
+                check(pb_scene_set_mesh_transform(ctx, m->index, m->to_world_left.m, 1));
+                check(pb_scene_set_mesh_transform(ctx, m->index, m->to_world_right.m, 0));
+                m->transform_dirty = false;
+            }
+            check(pb_grad_require(ctx, PB_PARAM_MESH_VERTICES, m->index, 0, m->requires_grad ? 1 : 0));
+        }
+        if (envmap && envmap->transform_dirty) { check(pb_scene_set_envmap_transform(ctx, envmap->to_world_left.m)); envmap->transform_dirty = false; }
+        check(pb_scene_configure(ctx));
+        configured = true;
+    }
+
+    // gradient vector layout as (param_map key, field, offset, count)
+    py::list grad_layout() const {
+        py::list out;
+        const int n = pb_grad_num_segments(ctx);
+        static const char *slots[] = {"reflectance", "alpha_u", "alpha_v", "eta", "k", "specular_reflectance"};
+        for (int i = 0; i < n; ++i) {
+            int kind, id, slot; int64_t off, cnt;
+            check(pb_grad_segment(ctx, i, &kind, &id, &slot, &off, &cnt));
+            if (kind == PB_PARAM_BSDF_TEXTURE) out.append(py::make_tuple("BSDF[" + std::to_string(id) + "]", std::string(slots[slot]), off, cnt));
+            else out.append(py::make_tuple("Mesh[" + std::to_string(id) + "]", std::string("vertex_positions"), off, cnt));
+        }
+        return out;
+    }
+    std::string to_string() const {
+        std::ostringstream oss;
+        oss << "Scene[\n  # Sensors\n";
+        for (auto &s : sensors) oss << "  " << s->to_string() << "\n";
+        oss << "\n  # BSDFs\n";
+        for (auto &b : bsdfs) oss << "  " << b->to_string() << "\n";
+        oss << "\n  # Meshes\n";
+        for (auto &m : meshes) oss << "  " << m->to_string() << "\n";
+        oss << "]";
+        return oss.str();
+    }
+};
+
+struct Integrator {
+    pb_integrator desc{PB_INTEG_DIRECT, 1, 1, 0, 0, 1, 0};
+    virtual ~Integrator() = default;
+    void require_ready(const Scene &s) const { if (!s.configured) throw std::runtime_error("Input scene must be configured!"); }
+    // images are written into caller-provided device memory (W*H*3 floats); psdr_cuda/__init__.py allocates torch tensors
+    void render_c(Scene &s, int sensor, uintptr_t d_image) const { require_ready(s); s.check(pb_render_c(s.ctx, &desc, sensor, reinterpret_cast<float *>(d_image))); }
+    void render_d(Scene &s, int sensor, uintptr_t d_image) const { require_ready(s); s.check(pb_render_d(s.ctx, &desc, sensor, reinterpret_cast<float *>(d_image))); }
+    void render_d_vjp(Scene &s, int sensor, uintptr_t d_dLdI, uintptr_t d_grad) const {
+        require_ready(s);
+        s.check(pb_render_d_vjp(s.ctx, &desc, sensor, reinterpret_cast<const float *>(d_dLdI), reinterpret_cast<float *>(d_grad)));
+    }
+    farray render_c_numpy(Scene &s, int sensor) const {
+        require_ready(s);
+        farray img(std::vector<py::ssize_t>{(py::ssize_t)s.opts.width * s.opts.height, 3});
+        s.check(pb_render_c_host(s.ctx, &desc, sensor, img.mutable_data()));
+        return img;
+    }
+    void preprocess_secondary_edges(Scene &s, int sensor, const iarray &reso, int nrounds) {
+        if (reso.size() != 4) throw std::runtime_error("resolution must have 4 entries");
+        s.check(pb_preprocess_secondary_edges(s.ctx, sensor, reso.data(), nrounds));
+        desc.use_guiding = 1;
+    }
+};
+struct DirectIntegrator : Integrator {
+    DirectIntegrator(int b, int l) {
+        if (!(b >= 0 && l >= 0 && b + l > 0)) throw std::runtime_error("Invalid DirectIntegrator sample counts");
+        desc.kind = PB_INTEG_DIRECT; desc.bsdf_samples = b; desc.light_samples = l;
+    }
+};
+struct PathIntegrator : Integrator {
+    explicit PathIntegrator(int depth) { if (depth < 1) throw std::runtime_error("PathIntegrator needs max_depth >= 1"); desc.kind = PB_INTEG_PATH; desc.max_depth = depth; }
+};
+struct FieldExtractionIntegrator : Integrator {
+    explicit FieldExtractionIntegrator(const std::string &field) {
+        static const std::map<std::string, int> f = {{"silhouette", PB_FIELD_SILHOUETTE}, {"position", PB_FIELD_POSITION}, {"depth", PB_FIELD_DEPTH},
+                                                     {"geoNormal", PB_FIELD_GEONORMAL}, {"shNormal", PB_FIELD_SHNORMAL}, {"uv", PB_FIELD_UV}};
+        auto it = f.find(field);
+        if (it == f.end()) throw std::runtime_error("Unknown field: " + field);
+        desc.kind = PB_INTEG_FIELD; desc.field = it->second;
+    }
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_psdr_host, m) {
+    m.doc() = "psdr-b200 host layer (pybind11 over the C ABI of include/psdr_b200.h)";
+    m.def("abi_version", &pb_version);
+
+    py::class_<Object, std::shared_ptr<Object>>(m, "Object")
+        .def("type_name", &Object::type_name)
+        .def_readonly("id", &Object::id)
+        .def("__repr__", &Object::to_string);
+
+    py::class_<RenderOption>(m, "RenderOption")
+        .def(py::init<>()).def(py::init<int, int, int>()).def(py::init<int, int, int, int>()).def(py::init<int, int, int, int, int>())
+        .def_readwrite("width", &RenderOption::width).def_readwrite("height", &RenderOption::height).def_readwrite("spp", &RenderOption::spp)
+        .def_readwrite("sppe", &RenderOption::sppe).def_readwrite("sppse", &RenderOption::sppse).def_readwrite("log_level", &RenderOption::log_level)
+        .def("__repr__", [](const RenderOption &o) {
+            std::ostringstream s;
+            s << "RenderOption[width = " << o.width << ", height = " << o.height << ", spp = " << o.spp << ", sppe = " << o.sppe << ", sppse = " << o.sppse << "]";
+            return s.str();
+        });
+
+    auto bitmap = [&](const char *name) {
+        return py::class_<Bitmap>(m, name)
+            .def_property("data", &Bitmap::get_data, &Bitmap::set_data)
+            .def_property("resolution", [](const Bitmap &b) { return py::make_tuple(b.width, b.height); },
+                          [](Bitmap &b, std::pair<int, int> r) { b.width = r.first; b.height = r.second; b.data.assign((size_t)b.width * b.height * b.channels, 0.f); b.dirty = true; })
+            .def_readwrite("requires_grad", &Bitmap::requires_grad)
+            .def_readonly("channels", &Bitmap::channels);
+    };
+    bitmap("BitmapD");
+
+    py::class_<BSDF, Object, std::shared_ptr<BSDF>>(m, "BSDF");
+    py::class_<Diffuse, BSDF, std::shared_ptr<Diffuse>>(m, "DiffuseBSDF")
+        .def_property_readonly("reflectance", [](Diffuse &d) -> Bitmap & { return d.reflectance; }, py::return_value_policy::reference_internal);
+    py::class_<RoughConductor, BSDF, std::shared_ptr<RoughConductor>>(m, "RoughConductorBSDF")
+        .def_property_readonly("alpha_u", [](RoughConductor &d) -> Bitmap & { return d.alpha_u; }, py::return_value_policy::reference_internal)
+        .def_property_readonly("alpha_v", [](RoughConductor &d) -> Bitmap & { return d.alpha_v; }, py::return_value_policy::reference_internal)
+        .def_property_readonly("eta", [](RoughConductor &d) -> Bitmap & { return d.eta; }, py::return_value_policy::reference_internal)
+        .def_property_readonly("k", [](RoughConductor &d) -> Bitmap & { return d.k; }, py::return_value_policy::reference_internal)
+        .def_property_readonly("specular_reflectance", [](RoughConductor &d) -> Bitmap & { return d.specular_reflectance; }, py::return_value_policy::reference_internal);
+
+    py::class_<Sensor, Object, std::shared_ptr<Sensor>>(m, "PerspectiveCamera")
+        .def_property("to_world", [](const Sensor &s) { return mat_to_numpy(s.to_world); }, [](Sensor &s, const farray &a) { s.to_world = mat_from_numpy(a); s.dirty = true; })
+        .def_readonly("fov_x", &Sensor::fov_x).def_readonly("near_clip", &Sensor::near_clip).def_readonly("far_clip", &Sensor::far_clip);
+
+    py::class_<Emitter, Object, std::shared_ptr<Emitter>>(m, "Emitter");
+    py::class_<AreaLight, Emitter, std::shared_ptr<AreaLight>>(m, "AreaLight")
+        .def_property_readonly("radiance", [](const AreaLight &a) { return py::make_tuple(a.radiance[0], a.radiance[1], a.radiance[2]); });
+    py::class_<EnvironmentMap, Emitter, std::shared_ptr<EnvironmentMap>>(m, "EnvironmentMap")
+        .def_property_readonly("radiance", [](EnvironmentMap &e) -> Bitmap & { return e.radiance; }, py::return_value_policy::reference_internal)
+        .def_readonly("scale", &EnvironmentMap::scale)
+        .def_property_readonly("to_world", [](const EnvironmentMap &e) { return mat_to_numpy(e.to_world_left * e.to_world_raw); })
+        .def("set_transform", [](EnvironmentMap &e, const farray &a) { e.to_world_left = mat_from_numpy(a); e.transform_dirty = true; });
+
+    py::class_<Mesh, Object, std::shared_ptr<Mesh>>(m, "Mesh")
+        .def_property_readonly("num_vertices", &Mesh::nv)
+        .def_property_readonly("num_faces", &Mesh::nf)
+        .def_property("vertex_positions", &Mesh::get_vertices, &Mesh::set_vertices)
+        .def_property_readonly("face_indices", &Mesh::get_faces)
+        .def_property_readonly("to_world_raw", [](const Mesh &x) { return mat_to_numpy(x.to_world_raw); })
+        .def_readonly("bsdf_index", &Mesh::bsdf)
+        .def_readonly("emitter_index", &Mesh::emitter)
+        .def_property_readonly("has_uv", [](const Mesh &x) { return !x.uvs.empty(); })
+        .def_readwrite("enable_edges", &Mesh::enable_edges)
+        .def_readwrite("use_face_normals", &Mesh::use_face_normals)
+        .def_readwrite("requires_grad", &Mesh::requires_grad)
+        .def_property_readonly("to_world", [](const Mesh &x) { return mat_to_numpy(x.to_world_left * x.to_world_raw * x.to_world_right); })
+        .def("set_transform", [](Mesh &x, const farray &a, bool set_left) { (set_left ? x.to_world_left : x.to_world_right) = mat_from_numpy(a); x.transform_dirty = true; },
+             py::arg("mat"), py::arg("set_left") = true)   // mesh.h:19-26
+        .def("append_transform", [](Mesh &x, const farray &a, bool append_left) {   // mesh.h:28-35
+                 if (append_left) x.to_world_left = mat_from_numpy(a) * x.to_world_left; else x.to_world_right = x.to_world_right * mat_from_numpy(a);
+                 x.transform_dirty = true;
+             }, py::arg("mat"), py::arg("append_left") = true)
+        .def("dump", &Mesh::dump);
+
+    py::class_<Scene>(m, "Scene")
+        .def(py::init<int>(), py::arg("device") = 0)
+        .def("load_file", &Scene::load_file, py::arg("file_name"), py::arg("auto_configure") = true)
+        .def("load_string", &Scene::load_string, py::arg("scene_xml"), py::arg("auto_configure") = true)
+        .def("configure", &Scene::configure)
+        .def_readwrite("opts", &Scene::opts)
+        .def_property_readonly("num_sensors", [](const Scene &s) { return (int)s.sensors.size(); })
+        .def_property_readonly("num_meshes", [](const Scene &s) { return s.configured ? pb_scene_num_meshes(s.ctx) : (int)s.meshes.size(); })
+        .def_property_readonly("param_map", [](Scene &s) { py::dict d; for (auto &kv : s.param_map) d[py::str(kv.first)] = py::cast(kv.second); return d; })
+        .def("grad_layout", &Scene::grad_layout)
+        .def("grad_size", [](const Scene &s) { return (int64_t)pb_grad_size(s.ctx); })
+        .def("set_shard", [](Scene &s, int rank, int world) { s.check(pb_ctx_set_shard(s.ctx, rank, world)); })
+        .def("set_stream", [](Scene &s, uintptr_t stream) { s.check(pb_ctx_set_stream(s.ctx, reinterpret_cast<void *>(stream))); })
+        .def("stats_launches", [](const Scene &s) { return (int64_t)pb_stats_launches(s.ctx); })
+        .def("__repr__", &Scene::to_string);
+
+    py::class_<Integrator>(m, "Integrator")
+        .def("_render_c", &Integrator::render_c)
+        .def("_render_d", &Integrator::render_d)
+        .def("_render_d_vjp", &Integrator::render_d_vjp)
+        .def("renderC_numpy", &Integrator::render_c_numpy, py::arg("scene"), py::arg("sensor_id") = 0)
+        .def("preprocess_secondary_edges", &Integrator::preprocess_secondary_edges, py::arg("scene"), py::arg("sensor_id"), py::arg("resolution"), py::arg("nrounds") = 1)
+        .def_property("hide_emitters", [](const Integrator &i) { return i.desc.hide_emitters != 0; }, [](Integrator &i, bool v) { i.desc.hide_emitters = v ? 1 : 0; });
+    py::class_<DirectIntegrator, Integrator>(m, "DirectIntegrator").def(py::init<int, int>(), py::arg("bsdf_samples") = 1, py::arg("light_samples") = 1);
+    py::class_<PathIntegrator, Integrator>(m, "PathIntegrator").def(py::init<int>(), py::arg("max_depth") = 5);
+    py::class_<FieldExtractionIntegrator, Integrator>(m, "FieldExtractionIntegrator").def(py::init<std::string>(), py::arg("field"));
+}

@@ -29,4 +29,6 @@ def cbox_desc():
 @pytest.fixture(scope="session")
 def native_lib():
     from psdr_cuda_b200 import build
-    return build.build_core()
+    core = build.build_core()
+    build.build_host()
+    return core

@@ -1,0 +1,20 @@
+"""CPU test: the reverse-mode building blocks of csrc/pb_adjoint_math.cuh (normalize, ray/triangle, connection factor,
+shading normal, face normal/area) against central finite differences. Host-compiled with nvcc; no GPU needed."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_adjoint_helpers_match_finite_differences(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "adjoint_check")
+    subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "adjoint_check.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "adjoint_check: ok" in out.stdout, out.stdout[-2000:]

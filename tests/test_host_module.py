@@ -1,0 +1,136 @@
+"""The pybind11 host layer (`import psdr_cuda`): CPU tests of its C++ scene ingest against the oracle's loader and of the
+reference-facing class surface; GPU tests of renderC / renderD + torch.autograd against the ctypes path."""
+import numpy as np
+import pytest
+
+from conftest import scene_path
+
+
+@pytest.fixture(scope="module")
+def psdr_cuda(native_lib):
+    import psdr_cuda_b200.compat  # noqa: F401
+    import psdr_cuda as m
+    return m
+
+
+def test_surface_matches_reference_names(psdr_cuda):
+    # src/psdr.cpp:48-294
+    for name in ("Scene", "RenderOption", "Mesh", "DiffuseBSDF", "RoughConductorBSDF", "PerspectiveCamera", "AreaLight", "EnvironmentMap",
+                 "Bitmap1fD", "Bitmap3fD", "Integrator", "DirectIntegrator", "FieldExtractionIntegrator", "PathIntegrator"):
+        assert hasattr(psdr_cuda, name), name
+    o = psdr_cuda.RenderOption(64, 48, 4)
+    assert (o.width, o.height, o.spp, o.sppe, o.sppse) == (64, 48, 4, 4, 4)
+    o = psdr_cuda.RenderOption(64, 48, 4, 2, 1)
+    assert (o.sppe, o.sppse) == (2, 1)
+    o.spp = 9
+    assert o.spp == 9
+    d = psdr_cuda.DirectIntegrator(2, 3)
+    d.hide_emitters = True
+    assert d.hide_emitters
+    with pytest.raises(RuntimeError):
+        psdr_cuda.DirectIntegrator(0, 0)
+    with pytest.raises(RuntimeError):
+        psdr_cuda.FieldExtractionIntegrator("nonsense")
+
+
+@pytest.mark.parametrize("name", ["cbox_bunny", "cbox_bunny_mutiemitter", "bunny", "tree", "bunny_env", "bunny_env_2"])
+def test_cpp_loader_matches_oracle_loader(psdr_cuda, name):
+    from oracle import orc
+    ref = orc.load_scene_description(scene_path(name))
+    sc = psdr_cuda.Scene(-1)                    # description only: no CUDA context needed for ingest
+    sc.load_file(scene_path(name), False)
+    assert sc.num_meshes == len(ref["meshes"]) and sc.num_sensors == len(ref["sensors"])
+    assert (sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse) == tuple(ref["opts"][k] for k in ("width", "height", "spp", "sppe", "sppse"))
+    pm = sc.param_map
+    for i, m in enumerate(ref["meshes"]):
+        o = pm["Mesh[%d]" % i]
+        assert o.type_name() == "Mesh" and o.num_vertices == len(m["verts"]) and o.num_faces == len(m["faces"])
+        assert np.array_equal(o.vertex_positions, m["verts"]) and np.array_equal(o.face_indices, m["faces"])
+        assert np.array_equal(o.to_world_raw, m["to_world"]) and o.bsdf_index == m["bsdf"] and o.use_face_normals == m["face_normals"]
+    for i, b in enumerate(ref["bsdfs"]):
+        o = pm["BSDF[%d]" % i]
+        assert pm["BSDF[id=%s]" % b["id"]].id == b["id"]
+        if b["type"] == 0:
+            assert o.type_name() == "DiffuseBSDF" and np.array_equal(o.reflectance.data.reshape(-1), b["reflectance"].reshape(-1))
+        else:
+            assert o.type_name() == "RoughConductorBSDF" and np.array_equal(o.alpha_u.data.reshape(-1), b["alpha_u"].reshape(-1))
+            assert np.array_equal(o.eta.data.reshape(-1), b["eta"].reshape(-1)) and np.array_equal(o.k.data.reshape(-1), b["k"].reshape(-1))
+    for i, s in enumerate(ref["sensors"]):
+        o = pm["Sensor[%d]" % i]
+        assert np.array_equal(o.to_world, s["to_world"]) and o.fov_x == np.float32(s["fov"])
+    if ref["envmap"] is not None:
+        e = pm["Emitter[0]"]
+        assert e.type_name() == "AreaLight"      # sic, include/psdr/emitter/envmap.h:58
+        assert np.array_equal(e.radiance.data.reshape(ref["envmap"]["radiance"].shape), ref["envmap"]["radiance"])
+        assert e.scale == np.float32(ref["envmap"]["scale"])
+
+
+def test_loader_error_messages(psdr_cuda):
+    sc = psdr_cuda.Scene(-1)
+    with pytest.raises(RuntimeError, match="XML parsing failed"):
+        sc.load_string("<scene", False)
+    with pytest.raises(RuntimeError, match="Unsupported BSDF"):
+        psdr_cuda.Scene(-1).load_string("<scene><bsdf type='plastic' id='x'/></scene>", False)
+    with pytest.raises(RuntimeError, match="BSDF must have an id"):
+        psdr_cuda.Scene(-1).load_string("<scene><bsdf type='diffuse'><rgb name='reflectance' value='1'/></bsdf></scene>", False)
+    sc = psdr_cuda.Scene(-1)
+    sc.load_file(scene_path("bunny"), False)
+    with pytest.raises(RuntimeError, match="already loaded"):
+        sc.load_file(scene_path("bunny"), False)
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        sc.configure()                           # no context, no CPU fallback
+    with pytest.raises(RuntimeError, match="must be configured"):
+        psdr_cuda.DirectIntegrator(1, 1).renderC_numpy(sc, 0)
+
+
+def test_mesh_transform_semantics(psdr_cuda):
+    # mesh.h:19-35: set_transform overwrites left (default), append_transform pre-multiplies left / post-multiplies right
+    sc = psdr_cuda.Scene(-1)
+    sc.load_file(scene_path("bunny"), False)
+    m = sc.param_map["Mesh[0]"]
+    raw = m.to_world_raw
+    T = np.eye(4, dtype=np.float32); T[0, 3] = 2
+    S = np.diag(np.array([2, 2, 2, 1], np.float32))
+    m.set_transform(T)
+    assert np.allclose(m.to_world, T @ raw)
+    m.append_transform(S)
+    assert np.allclose(m.to_world, S @ T @ raw)
+    m.append_transform(S, False)
+    assert np.allclose(m.to_world, S @ T @ raw @ S)
+
+
+@pytest.mark.gpu
+def test_psdr_cuda_module_renders_and_differentiates(psdr_cuda):
+    torch = pytest.importorskip("torch")
+    from psdr_cuda_b200 import capi, scene_io
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path("cbox_bunny"), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse = 48, 48, 4, 4, 4
+    albedo = sc.parameter("BSDF[id=white]", "reflectance")
+    verts = sc.parameter("Mesh[1]", "vertex_positions")
+    sc.configure()
+    integ = psdr_cuda.PathIntegrator(2)
+    img_c = integ.renderC(sc, 0)
+    img = integ.renderD(sc, 0)
+    assert img.shape == (48 * 48, 3) and img.requires_grad
+    w = torch.linspace(0.5, 1.5, img.numel(), device=img.device).view_as(img)
+    (img * w).sum().backward()
+    assert albedo.grad is not None and verts.grad is not None and verts.grad.shape == (34817, 3)
+    # same thing through the ctypes binding
+    ctx = capi.Context(0)
+    ctx.load_description(scene_io.load_scene_description(scene_path("cbox_bunny")), dict(width=48, height=48, spp=4, sppe=4, sppse=4))
+    ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "reflectance")
+    ctx.grad_require(capi.PARAM_MESH_VERTICES, 1)
+    ctx.configure()
+    ci = capi.make_integrator("path", max_depth=2)
+    ref_c = ctx.render_c(ci)
+    ref_d = ctx.render_d(ci)
+    g = ctx.render_d_vjp(ci, w.contiguous())
+    assert torch.equal(img_c, ref_c) and torch.equal(img.detach(), ref_d)
+    assert torch.allclose(albedo.grad.reshape(-1), g[:3], rtol=1e-4, atol=1e-5)
+    assert (verts.grad.reshape(-1) - g[3:]).norm() <= 1e-4 * g[3:].norm()
+    # an optimisation step moves the parameter and the next configure() picks it up (examples/utils/adam.py flow)
+    with torch.no_grad():
+        albedo -= 0.1 * albedo.grad / albedo.grad.abs().max()
+    sc.configure()
+    assert not torch.equal(integ.renderC(sc, 0), img_c)
