@@ -151,6 +151,9 @@ def run_ours(args):
         ctx.set_batch(args.batch)
     if args.trace_variant >= 0:
         ctx.debug_set("trace_variant", args.trace_variant)
+    for kv in args.debug:
+        k, v = kv.split("=")
+        ctx.debug_set(k, int(v))
     ctx.configure()
     integ = capi.make_integrator("path", max_depth=DEPTH)
     npix = W * H
@@ -267,7 +270,7 @@ def run_ours(args):
 
 
 def ctx_batch_mb(args):
-    lanes = args.batch if args.batch else (1 << 20)
+    lanes = args.batch if args.batch else (1 << 24)
     return lanes * (16 + 2 * 2 * (32 + 16) + 2 * 32) / 1e6
 
 
@@ -280,6 +283,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace-variant", type=int, default=-1, help="debug: traversal kernel variant (default: library default)")
+    ap.add_argument("--debug", action="append", default=[], help="debug: key=value passed to pb_debug_set")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -165,7 +165,7 @@ static void configure_sensor(HostSensor &s, int W, int H) {
 // all wavefront ray launches go through here: sorted (variant 7) or in lane order (debug variants)
 static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits) {
     if (g_trace_variant == 7) {
-        c->d_sort_hist.reserve(8192 * sizeof(unsigned));
+        c->d_sort_hist.reserve(40000 * sizeof(unsigned));
         c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
         launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
                             f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>());
@@ -402,6 +402,12 @@ static void configure(pb_ctx *c) {
             dn[i].d = make_float4(l, r, 0.f, 0.f);
         }
         c->d_nodes.upload(dn, st);
+        {
+            std::vector<HostNode4> n4;
+            collapse_bvh4(nodes, n4);
+            static_assert(sizeof(HostNode4) == sizeof(BvhNode4), "BVH4 node layout");
+            c->d_nodes4.upload(n4, st);
+        }
         c->d_order.upload(order, st);
         c->d_leaf.reserve(std::max<size_t>(1, order.size()) * sizeof(LeafTri));
         if (total == 0) PB_CUDA(cudaMemsetAsync(c->d_leaf.p, 0, sizeof(LeafTri), st));
@@ -472,7 +478,7 @@ static void configure(pb_ctx *c) {
     c->d_bsdfs.upload(br, st);
     PB_CUDA(cudaStreamSynchronize(st));
     SceneView &V = c->view;
-    V.tri = c->d_tri.as<TriRec>(); V.leaf = c->d_leaf.as<LeafTri>(); V.nodes = c->d_nodes.as<BvhNode>();
+    V.tri = c->d_tri.as<TriRec>(); V.leaf = c->d_leaf.as<LeafTri>(); V.nodes = c->d_nodes.as<BvhNode>(); V.nodes4 = c->d_nodes4.as<BvhNode4>();
     V.meshes = c->d_meshes.as<MeshRec>(); V.bsdfs = c->d_bsdfs.as<BsdfRec>(); V.emitters = c->d_emitters.as<EmitterRec>();
     V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
@@ -899,7 +905,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 const char *pb_last_error(pb_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
 int pb_ctx_set_batch(pb_ctx *c, int64_t lanes) {
     return guard(c, [&] {
-        if (lanes <= 0) lanes = 1 << 20;
+        if (lanes <= 0) lanes = 1 << 24;
         PB_ASSERT_MSG(lanes % 1024 == 0, "batch must be a multiple of 1024 lanes");
         c->batch = lanes;
     });
@@ -1152,6 +1158,9 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
     return guard(c, [&] {
         if (std::strcmp(key, "trace_variant") == 0) pb::g_trace_variant = (int)value;
         else if (std::strcmp(key, "trace_blocks_per_sm") == 0) pb::g_trace_blocks_per_sm = (int)value;
+        else if (std::strcmp(key, "trace_smem") == 0) pb::g_trace_smem = (int)value;
+        else if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
+        else if (std::strcmp(key, "trace_smem_nodes") == 0) pb::g_trace_smem_nodes = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);
     });
 }

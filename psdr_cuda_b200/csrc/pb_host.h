@@ -124,14 +124,14 @@ struct pb_ctx {
     bool has_bound_mesh = false;   // the last mesh is the envmap's bounding box (scene.cpp:135-180)
     // sharding / tiling
     int rank = 0, world = 1;
-    int64_t batch = 1 << 20;
+    int64_t batch = 1 << 24;   // 16 Mi lanes: large wavefronts sort into more coherent bins
     // samplers (scene.cpp:65-79): lane count the streams were seeded for and draws consumed so far
     int64_t sampler_count[3] = {0, 0, 0};
     uint64_t sampler_offset[3] = {0, 0, 0};
     // configured device tables
     bool ready = false;
     int num_tri = 0;
-    pb::DevBuf d_tri, d_leaf, d_nodes, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
+    pb::DevBuf d_tri, d_leaf, d_nodes, d_nodes4, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
     std::vector<float> h_tri;   // host copy of the triangle table (BVH build, inspection)
     float emitter_sum = 0.f;
     pb::SceneView view;

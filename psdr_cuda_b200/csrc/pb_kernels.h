@@ -51,6 +51,9 @@ void launch_mesh_backward(cudaStream_t st, int nv, int nf, int face_offset, cons
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_trace_blocks_per_sm;
+extern int g_sort_mode;
+extern int g_trace_smem;
+extern int g_trace_smem_nodes;
 extern int g_trace_variant;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm);

@@ -49,6 +49,18 @@ __global__ void __launch_bounds__(128) k_trace_spec(const BvhNode *__restrict__ 
     if (t_out) t_out[i] = h.t;
 }
 
+template <bool FMA_SLAB>
+__global__ void __launch_bounds__(128) k_trace_bvh4(const BvhNode4 *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
+                                                    const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = ldg4(rp), b = ldg4(rp + 1);
+    const Hit h = trace_closest_bvh4<FMA_SLAB>(nodes, leaf, f3(a), f3(b), a.w, b.w);
+    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    if (t_out) t_out[i] = h.t;
+}
+
 // Block-local regrouping: the 256 rays of a block are counting-sorted in shared memory by (active, direction bin) so
 // that each warp traverses rays that point the same way and inactive lanes collect in warps that exit at once.
 // Only the thread<->ray assignment changes; every ray's hit is written back to its own slot.
@@ -356,6 +368,8 @@ void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec
         case 5: k_trace_spec<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
         case 6: k_trace_spec<true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
         case 7: k_trace_spec<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
+        case 8: k_trace_bvh4<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes4, S.leaf, n, rays, hits, t_out); break;
+        case 9: k_trace_bvh4<true><<<nblk(n, 128), 128, 0, st>>>(S.nodes4, S.leaf, n, rays, hits, t_out); break;
         default: {
             static unsigned long long *counter = nullptr;   // one per process; launches on a stream are ordered
             if (!counter) cudaMalloc(&counter, sizeof(unsigned long long));

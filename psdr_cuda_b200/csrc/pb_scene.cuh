@@ -32,6 +32,10 @@ struct __align__(16) LeafTri { float4 a, b, c; };
 // d = (left, right, -, -) as int bits; child >= 0: inner node index; child < 0: leaf, v = ~child, first = v >> 3, count = (v & 7) + 1
 struct __align__(16) BvhNode { float4 a, b, c, d; };
 
+// BVH4 node, 128 B = one line: the four children's boxes in SoA form (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4]),
+// child links (int bits; 0x80000000 = absent), padding. Built by collapsing the binary tree (pb_bvh.cpp).
+struct __align__(16) BvhNode4 { float4 lox, loy, loz, hix, hiy, hiz, child, pad; };
+
 struct MeshRec {           // 32 B, per mesh
     int bsdf, emitter;     // -1 = none
     float inv_total_area;
@@ -92,6 +96,7 @@ struct SceneView {
     const TriRec *tri;
     const LeafTri *leaf;
     const BvhNode *nodes;
+    const BvhNode4 *nodes4;
     const MeshRec *meshes;
     const BsdfRec *bsdfs;
     const EmitterRec *emitters;

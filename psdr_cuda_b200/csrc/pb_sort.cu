@@ -13,20 +13,46 @@
 
 namespace pb {
 
-constexpr int kSortBins = 4096;   // 6 bits direction (octahedral 8x8, Morton) x 6 bits origin cell (4x4x4, Morton)
+int g_sort_mode = 0;
+int g_trace_smem_nodes = 512;
+int g_trace_smem = 0;   // stage the top of the BVH in shared memory (persistent blocks) for the sorted wavefront trace
+
+constexpr int kSortBins = 4096;   // 6 bits direction (octahedral 8x8, Morton) x 6 bits origin cell (4x4x4, Morton); finer keys measured slower
+
+__constant__ int c_sort_mode = 0;   // 0: 6 bits direction + 6 bits origin cell; 1: 8 + 3 (+ray kind); 2: 9 bits direction + 3 bits cell
+
+PB_D int direction_bin_n(float3 d, int n) {   // octahedral n x n grid, row-major
+    const float inv = 1.f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float px = d.x * inv, py = d.y * inv;
+    if (d.z < 0.f) {
+        const float qx = (1.f - fabsf(py)) * (px >= 0.f ? 1.f : -1.f), qy = (1.f - fabsf(px)) * (py >= 0.f ? 1.f : -1.f);
+        px = qx; py = qy;
+    }
+    const int ux = min(n - 1, max(0, (int)((px * .5f + .5f) * (float)n))), uy = min(n - 1, max(0, (int)((py * .5f + .5f) * (float)n)));
+    return ((uy & 1) ? (n - 1 - ux) : ux) + uy * n;   // boustrophedon rows keep neighbouring bins adjacent
+}
 
 PB_D int sort_key(float4 a, float4 b, float3 lo, float3 inv_ext) {
     if (!(a.w > 0.f)) return kSortBins;
-    const int db = direction_bin(f3(b));
-    const int cx = min(3, max(0, (int)((a.x - lo.x) * inv_ext.x * 4.f)));
-    const int cy = min(3, max(0, (int)((a.y - lo.y) * inv_ext.y * 4.f)));
-    const int cz = min(3, max(0, (int)((a.z - lo.z) * inv_ext.z * 4.f)));
-    const int cell = (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2) | ((cx & 2) << 2) | ((cy & 2) << 3) | ((cz & 2) << 4);
-    return (db << 6) | cell;
+    if (c_sort_mode == 0) {
+        const int db = direction_bin(f3(b));
+        const int cx = min(3, max(0, (int)((a.x - lo.x) * inv_ext.x * 4.f)));
+        const int cy = min(3, max(0, (int)((a.y - lo.y) * inv_ext.y * 4.f)));
+        const int cz = min(3, max(0, (int)((a.z - lo.z) * inv_ext.z * 4.f)));
+        int cell = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) cell |= (((cx >> k) & 1) << (3 * k)) | (((cy >> k) & 1) << (3 * k + 1)) | (((cz >> k) & 1) << (3 * k + 2));
+        return (db << 6) | cell;
+    }
+    const int cx = min(1, max(0, (int)((a.x - lo.x) * inv_ext.x * 2.f))), cy = min(1, max(0, (int)((a.y - lo.y) * inv_ext.y * 2.f))),
+              cz = min(1, max(0, (int)((a.z - lo.z) * inv_ext.z * 2.f)));
+    const int cell = cx | (cy << 1) | (cz << 2);
+    if (c_sort_mode == 1) return (((b.w > 0.f) ? 1 : 0) << 11) | (direction_bin_n(f3(b), 16) << 3) | cell;
+    return min(kSortBins - 1, (direction_bin_n(f3(b), 22) << 3) | cell);
 }
 
-__global__ void __launch_bounds__(256) k_sort_hist(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ hist) {
-    __shared__ unsigned s_hist[kSortBins + 1];
+__global__ void __launch_bounds__(1024) k_sort_hist(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ hist) {
+    extern __shared__ unsigned s_hist[];
     for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -42,7 +68,7 @@ __global__ void __launch_bounds__(256) k_sort_hist(long long n, const RayRec *__
 __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist) {
     __shared__ unsigned s_part[1024];
     const int t = threadIdx.x;
-    constexpr int per = (kSortBins + 1 + 1023) / 1024;   // 5
+    constexpr int per = (kSortBins + 1 + 1023) / 1024;
     unsigned v[per], sum = 0;
     for (int k = 0; k < per; ++k) { const int idx = t * per + k; v[k] = idx <= kSortBins ? hist[idx] : 0u; sum += v[k]; }
     s_part[t] = sum;
@@ -61,21 +87,34 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist)
     }
 }
 
-__global__ void __launch_bounds__(256) k_sort_scatter(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ cursor,
-                                                      unsigned *__restrict__ perm, HitRec *__restrict__ hits) {
+// Scatter with block-level aggregation: lanes rank themselves inside the block with shared-memory atomics, then one
+// global atomic per (block, non-empty bin) reserves the block's range. Rays arrive in pixel order, so the lanes in flight
+// at any moment share an origin cell and hammer ~64 counters; per-lane global atomics serialised on them.
+__global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ cursor,
+                                                       unsigned *__restrict__ perm, HitRec *__restrict__ hits) {
+    extern __shared__ unsigned s_cnt[];
+    for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) s_cnt[t] = 0;
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const int key = sort_key(ldg4(rp), ldg4(rp + 1), lo, inv_ext);
-    if (key == kSortBins) {   // inactive lane: a miss, and no thread of the traversal kernel is spent on it
-        reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);
-        return;
+    int key = kSortBins;
+    unsigned rank = 0;
+    if (i < n) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+        key = sort_key(ldg4(rp), ldg4(rp + 1), lo, inv_ext);
+        if (key == kSortBins) reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);   // inactive lane: a miss
+        else rank = atomicAdd(&s_cnt[key], 1u);
     }
-    perm[atomicAdd(cursor + key, 1u)] = (unsigned)i;
+    __syncthreads();
+    for (int t = threadIdx.x; t < kSortBins; t += blockDim.x) {
+        const unsigned c = s_cnt[t];
+        if (c) s_cnt[t] = atomicAdd(cursor + t, c);
+    }
+    __syncthreads();
+    if (key != kSortBins) perm[s_cnt[key] + rank] = (unsigned)i;
 }
 
-template <bool FMA_SLAB>
-__global__ void __launch_bounds__(128) k_trace_perm(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
+template <bool FMA_SLAB, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_trace_perm(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
                                                     const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= __ldg(n_active)) return;
@@ -86,18 +125,57 @@ __global__ void __launch_bounds__(128) k_trace_perm(const BvhNode *__restrict__ 
     reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
 }
 
+// persistent blocks (one per SM, 1024 threads, 192 KiB of shared memory for the top of the tree) over the sorted rays
+template <bool FMA_SLAB>
+__global__ void __launch_bounds__(1024, 1) k_trace_perm_smem(const BvhNode *__restrict__ nodes, int num_nodes, const LeafTri *__restrict__ leaf,
+                                                             const unsigned *__restrict__ n_active, const unsigned *__restrict__ perm,
+                                                             const RayRec *__restrict__ rays, HitRec *__restrict__ hits, int cap) {
+    extern __shared__ float4 s_nodes[];
+    const int top = stage_top_nodes(s_nodes, nodes, num_nodes, cap);
+    const unsigned n = __ldg(n_active);
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned i = __ldg(perm + j);
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+        const float4 a = ldg4(rp), b = ldg4(rp + 1);
+        const Hit h = trace_closest_smem<FMA_SLAB>(s_nodes, top, cap, nodes, leaf, f3(a), f3(b), a.w, b.w);
+        reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    }
+}
+
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 // hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm) {
     if (n <= 0) return;
+    static int mode_set = -1;
+    if (mode_set != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); mode_set = g_sort_mode; }
     const float3 inv_ext = f3(1.f / fmaxf(hi.x - lo.x, 1e-20f), 1.f / fmaxf(hi.y - lo.y, 1e-20f), 1.f / fmaxf(hi.z - lo.z, 1e-20f));
-    cudaMemsetAsync(hist, 0, (kSortBins + 2) * sizeof(unsigned), st);
-    k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 256), 148 * 8), 256, 0, st>>>(n, rays, lo, inv_ext, hist);
+    cudaMemsetAsync(hist, 0, (kSortBins + 2) * sizeof(unsigned), st);   // hist must hold kSortBins + 2 counters
+    const int cnt_bytes = (kSortBins + 1) * (int)sizeof(unsigned);
+    static bool sort_attr = false;
+    if (!sort_attr) {
+        cudaFuncSetAttribute(k_sort_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, cnt_bytes);
+        cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, cnt_bytes);
+        sort_attr = true;
+    }
+    k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist);
     k_sort_scan<<<1, 1024, 0, st>>>(hist);
-    k_sort_scatter<<<nblk(n, 256), 256, 0, st>>>(n, rays, lo, inv_ext, hist, perm, hits);
+    k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist, perm, hits);
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
-    k_trace_perm<true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+    if (g_trace_smem) {
+        static bool attr_set = false;
+        const int cap = std::min(kTopNodes, std::max(32, g_trace_smem_nodes));
+        const int smem = cap * 64;
+        if (!attr_set) { cudaFuncSetAttribute(k_trace_perm_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopNodes * 64); attr_set = true; }
+        k_trace_perm_smem<true><<<148, 1024, smem, st>>>(S.nodes, S.num_nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits, cap);
+    } else {
+        switch (g_trace_blocks_per_sm) {
+            case 10: k_trace_perm<true, 10><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
+            case 12: k_trace_perm<true, 12><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
+            case 16: k_trace_perm<true, 16><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
+            default: k_trace_perm<true, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
+        }
+    }
 }
 
 }  // namespace pb
