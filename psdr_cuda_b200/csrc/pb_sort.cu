@@ -118,11 +118,12 @@ __global__ void __launch_bounds__(128, MINB) k_trace_perm(const BvhNode *__restr
                                                     const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= __ldg(n_active)) return;
-    const unsigned i = __ldg(perm + j);
+    const unsigned i = __ldcs(perm + j);
+    // rays and hits stream through once: evict-first hints keep the BVH and the triangle tables resident in L2
     const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const float4 a = ldg4(rp), b = ldg4(rp + 1);
+    const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
     const Hit h = trace_closest_spec<FMA_SLAB>(nodes, leaf, f3(a), f3(b), a.w, b.w);
-    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
 }
 
 // persistent blocks (one per SM, 1024 threads, 192 KiB of shared memory for the top of the tree) over the sorted rays
