@@ -127,6 +127,12 @@ int64_t pb_grad_size(pb_ctx *ctx);
  * On several GPUs each rank holds a private d_grad and the caller all-reduces it once. */
 int pb_render_d_vjp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const float *d_dLdI, float *d_grad);
 
+/* forward mode (ek.forward + ek.gradient(image) in the reference, examples/run_test.py:126-129): d_tangent is a flat vector with the
+ * layout of the gradient vector (the direction in parameter space), d_dimage receives the W*H*3 derivative image. Needs a
+ * preceding pb_render_d like the VJP. Implemented by running the adjoint kernels once per colour channel with a unit seed and
+ * contracting each local gradient with the tangent of what it refers to. */
+int pb_render_d_jvp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const float *d_tangent, float *d_dimage);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------------- */
 /* kernels launched by this context since creation; for the last render / trace call: milliseconds spent in the k_trace
  * launches (CUDA events on the context's stream), how many launches and rays that was, and the milliseconds of the

@@ -147,6 +147,25 @@ class _IntegratorMixin:
         return _RenderD.apply(*leaves) if leaves else _RenderD.apply()
 
 
+    def forward(self, scene, tangents, sensor_id=0):
+        """Forward mode (ek.forward(P) + ek.gradient(image) in examples/run_test.py:126-129): `tangents` maps registered
+        parameters (the tensors returned by scene.parameter) to tangent tensors of the same shape; returns (image, d image).
+        Unlisted parameters get a zero tangent."""
+        torch = _torch()
+        img = _image_tensor(scene)
+        self._render_d(scene, sensor_id, img.data_ptr())
+        flat = torch.zeros(max(1, scene.grad_size()), dtype=torch.float32, device=img.device)
+        for t, off, cnt in scene._leaves_in_layout_order():
+            if t is None:
+                continue
+            for p, tan in tangents.items():
+                if p is t:
+                    flat[off:off + cnt] = tan.to(flat.device, torch.float32).reshape(-1)
+        dimg = torch.empty_like(img)
+        self._render_d_jvp(scene, sensor_id, flat.data_ptr(), dimg.data_ptr())
+        return img, dimg
+
+
 class DirectIntegrator(_IntegratorMixin, _h.DirectIntegrator):
     pass
 

@@ -17,7 +17,7 @@ constexpr int kMaxConstBsdf = 64;
 // adjoint of bsdf_eval w.r.t. its textures; `g` is dLoss/d(value). Constant (1x1) textures accumulate into the
 // thread-private `acc` (flushed per block), bitmap textures scatter with atomics (Bitmap::eval's backward,
 // src/core/bitmap.cpp:43-89: scatter_add into the four texels).
-PB_D void bsdf_eval_grad_tex(const BsdfRec *b, const Its &its, float3 wo, float3 g, float3 &acc) {
+PB_D void bsdf_eval_grad_tex(const SceneView &S, const BsdfRec *b, const Its &its, float3 wo, float3 g, float3 &acc) {
     if (!b) return;
     const float cos_i = its.wi.z, cos_o = wo.z;
     if (!(cos_i > 0.f && cos_o > 0.f)) return;
@@ -30,6 +30,14 @@ PB_D void bsdf_eval_grad_tex(const BsdfRec *b, const Its &its, float3 wo, float3
         const TexTap tap = tex_tap(t, its.uv);
         const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
         const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
+        if (S.tri_tangent) {   // forward mode: t.grad holds the texture's tangent
+            float sacc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                sacc += w[k] * (gr.x * __ldg(t.grad + idx[k] * 3) + gr.y * __ldg(t.grad + idx[k] * 3 + 1) + gr.z * __ldg(t.grad + idx[k] * 3 + 2));
+            jvp_add(S, sacc);
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             atomicAdd(t.grad + idx[k] * 3 + 0, gr.x * w[k]);
@@ -93,7 +101,9 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
         bsdf_id = v.bsdf ? (int)(v.bsdf - P.S.bsdfs) : -1;
         // loss adjoint of this lane's radiance
         const float3 rad_final = f3(ldg4(E.rad + i));
-        float3 g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
+        float3 g;
+        if (P.S.tri_tangent) g = f3(P.S.jvp_channel == 0 ? 1.f : 0.f, P.S.jvp_channel == 1 ? 1.f : 0.f, P.S.jvp_channel == 2 ? 1.f : 0.f) * P.inv_spp;
+        else g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
         if (!isfinite(rad_final.x)) g.x = 0.f;
         if (!isfinite(rad_final.y)) g.y = 0.f;
         if (!isfinite(rad_final.z)) g.z = 0.f;
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
         Rng rng((uint64_t)lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
-        const bool geom = P.S.tri_grad != nullptr && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
+        const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                     gval += gL * Le * (scale * weight);
                 }
                 if (cont) { w_cont = f * scale; gval += gw * scale; }
-                bsdf_eval_grad_tex(v.bsdf, its, wo_l, gval, acc);
+                bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gval, acc);
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     // value = K * (cos_o G J) with K = rho/pi * (Le weight gL + gw) / pdf0   (diffuse: pdf0 and the MIS weight are detached)
                     const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 const float3 Le = emitter_Le(P.S, its1, true);
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
-                bsdf_eval_grad_tex(v.bsdf, its, wo_l, gL * Le * scale, acc);
+                bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gL * Le * scale, acc);
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
                     const float gc = pdot(gL * Le, rho) * kInvPi * weight / ps.pdf;
@@ -203,9 +213,22 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 } else {              // path-space form: barycentrics are frozen, the point rides the triangle
                     tg.p0 += g_p; tg.e1 += g_p * v.h.u; tg.e2 += g_p * v.h.v;
                 }
-                tri_grad_scatter(P.S.tri_grad, its.tri, tg);
+                tri_grad_scatter(P.S, its.tri, tg);
             }
         }
+    }
+    if (P.S.tri_tangent) {   // forward mode (uniform over the grid): constant-texture part, then the lane total goes to the derivative image
+        int pix = -1;
+        float total = 0.f;
+        if (i < P.n) {
+            if (bsdf_id >= 0) {
+                const TexRef &t = P.S.bsdfs[bsdf_id].tex[TEX_REFLECTANCE];
+                if (t.grad && t.w == 1 && t.h == 1) jvp_add(P.S, acc.x * __ldg(t.grad) + acc.y * __ldg(t.grad + 1) + acc.z * __ldg(t.grad + 2));
+            }
+            if (B.depth == 0) { global_lane(P, i, pix); total = P.S.jvp_acc[i]; }
+        }
+        if (B.depth == 0) film_accumulate1(P.S.jvp_image, pix, P.S.jvp_channel, total);
+        return;
     }
     flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
 }

@@ -484,6 +484,7 @@ static void configure(pb_ctx *c) {
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
     V.emitter_env = c->emitter_env;
     V.tri_grad = nullptr;
+    V.tri_tangent = nullptr; V.jvp_acc = nullptr; V.jvp_image = nullptr; V.jvp_channel = 0;
     configure_edges(c);
     // gradient layout
     c->grad_segments.clear();
@@ -523,7 +524,7 @@ static Plan make_plan(const pb_integrator &I) {
     return p;
 }
 
-enum Mode { MODE_C = 0, MODE_D = 1, MODE_VJP = 2 };
+enum Mode { MODE_C = 0, MODE_D = 1, MODE_VJP = 2, MODE_JVP = 3 };
 
 struct Plan;
 static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const Plan &plan, const RenderParams &Pbase, const float *d_dLdI, size_t *nev);
@@ -555,6 +556,11 @@ static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t 
     for (int k = 0; k < nslots + 1; ++k) S.thr[k].reserve((size_t)lanes * sizeof(float4));
 }
 
+static bool any_geom_jvp(const pb_ctx *c) {
+    for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_MESH_VERTICES) return true;
+    return false;
+}
+
 // the three ray launches + evaluation of the secondary-edge estimator for one batch (direct.cpp:225-316)
 static void secondary_edge_batch(pb_ctx *c, const RenderParams &P, const EdgeParams &Q, const float *d_dLdI, float inv_sppse, float *guide_out, int guide_spc) {
     cudaStream_t st = c->stream;
@@ -567,8 +573,18 @@ static void secondary_edge_batch(pb_ctx *c, const RenderParams &P, const EdgePar
     trace_wavefront(c, 2 * (int64_t)P.n, rays, hits);
     launch_edge_secondary_camera(st, P, Q, rays, hits, cam_rays, guide_spc);
     trace_wavefront(c, (int64_t)P.n, cam_rays, cam_hits);
-    launch_edge_secondary_eval(st, P, Q, rays, hits, cam_rays, cam_hits, d_dLdI, inv_sppse, guide_out, guide_spc);
-    c->launches += 5;
+    if (P.S.tri_tangent) {
+        RenderParams Pc = P;
+        for (int ch = 0; ch < 3; ++ch) {
+            Pc.S.jvp_channel = ch;
+            launch_edge_secondary_eval(st, Pc, Q, rays, hits, cam_rays, cam_hits, d_dLdI, inv_sppse, guide_out, guide_spc);
+            c->launches++;
+        }
+    } else {
+        launch_edge_secondary_eval(st, P, Q, rays, hits, cam_rays, cam_hits, d_dLdI, inv_sppse, guide_out, guide_spc);
+        c->launches++;
+    }
+    c->launches += 4;
 }
 
 // boundary terms of renderD in reverse mode (integrator.cpp:98-119, direct.cpp:207-221); lanes are sharded by index range
@@ -584,11 +600,13 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
     const GuideGrid *guide = (I.use_guiding && sensor < (int)c->guides.size()) ? &c->guides[sensor] : nullptr;
     const EdgeParams Q = make_edge_params(c, sensor, guide);
     const int R = std::max(2, plan.nb + plan.nl);
-    const int64_t B = c->batch;
+    const int64_t max_lanes = npix * std::max(c->sppe, c->sppse);
+    const int64_t B = std::max<int64_t>(1024, std::min<int64_t>(c->batch, ((max_lanes + 1023) / 1024) * 1024));
     size_store(c->scratch, B, 2, R, B);
     c->d_edge_rays.reserve((size_t)B * sizeof(RayRec));
     c->d_edge_rad.reserve((size_t)B * sizeof(float4));
     RenderParams P = Pbase;
+    if (P.S.tri_tangent) { c->d_jvp_acc.reserve((size_t)B * sizeof(float)); P.S.jvp_acc = c->d_jvp_acc.as<float>(); }
     P.spp = 1; P.spp_local = 1; P.s0 = 0; P.inv_spp = 1.f;
     EventStore &S = c->scratch;
     // ---- primary edges
@@ -630,8 +648,17 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                 }
                 if (side == 0) PB_CUDA(cudaMemcpyAsync(c->d_edge_rad.p, S.rad.p, (size_t)P.n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
             }
-            launch_edge_primary_grad(st, P, Q, c->d_edge_rad.as<float4>(), S.rad.as<float4>(), d_dLdI, 1.f / (float)c->sppe);
-            c->launches++;
+            if (P.S.tri_tangent) {
+                RenderParams Pc = P;
+                for (int ch = 0; ch < 3; ++ch) {
+                    Pc.S.jvp_channel = ch;
+                    launch_edge_primary_grad(st, Pc, Q, c->d_edge_rad.as<float4>(), S.rad.as<float4>(), d_dLdI, 1.f / (float)c->sppe);
+                    c->launches++;
+                }
+            } else {
+                launch_edge_primary_grad(st, P, Q, c->d_edge_rad.as<float4>(), S.rad.as<float4>(), d_dLdI, 1.f / (float)c->sppe);
+                c->launches++;
+            }
         }
     }
     // ---- secondary edges (the base Integrator / FieldExtractionIntegrator has none: integrator.h:24)
@@ -700,12 +727,17 @@ static void preprocess_secondary_edges(pb_ctx *c, int sensor, const int *reso, i
 //                     forward pass is replayed batch by batch first (same stream positions as the last renderD).
 static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float *d_image, Mode mode, const float *d_dLdI = nullptr,
                             float *d_grad = nullptr) {
+    // MODE_JVP: d_grad is the (read-only) flat tangent vector and d_image the W*H*3 derivative image; everything else follows MODE_VJP
+    const bool jvp = (mode == MODE_JVP);
+    float *d_dimage = jvp ? d_image : nullptr;
+    if (jvp) mode = MODE_VJP;
     PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
     PB_ASSERT_MSG(sensor >= 0 && sensor < (int)c->sensors.size(), "Invalid sensor id!");
     PB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int64_t npix = (int64_t)c->width * c->height;
     if (d_image) PB_CUDA(cudaMemsetAsync(d_image, 0, (size_t)npix * 3 * sizeof(float), st));
+    if (jvp) d_image = nullptr;
     c->last_trace_ms = 0.f; c->last_rays = 0; c->last_primary_ms = 0.f; c->last_trace_launches = 0;
     const int s0 = (int)((int64_t)c->spp * c->rank / c->world), s1 = (int)((int64_t)c->spp * (c->rank + 1) / c->world);
     const int spp_local = s1 - s0;
@@ -753,7 +785,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         PB_CUDA(cudaMemcpyAsync(br.data(), c->d_bsdfs.p, br.size() * sizeof(BsdfRec), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
         for (const GradSegment &g : c->grad_segments)
-            if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;
+            if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;   // forward mode: the tangent, read only
         c->d_bsdfs_grad.upload(br, st);
         P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
         bool any_geom = false;
@@ -768,6 +800,27 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                     m.d_gworld.reserve(3 * (size_t)m.nv * sizeof(float));
                     PB_CUDA(cudaMemsetAsync(m.d_gworld.p, 0, 3 * (size_t)m.nv * sizeof(float), st));
                 }
+        }
+        if (jvp) {   // forward mode: tangent of the triangle table from the vertex tangents (mesh.cpp:19-51,215-231 in forward mode)
+            const size_t tt_bytes = (size_t)std::max(1, c->num_tri) * kTriGradStride * sizeof(float);
+            c->d_tri_tangent.reserve(tt_bytes);
+            PB_CUDA(cudaMemsetAsync(c->d_tri_tangent.p, 0, tt_bytes, st));
+            for (const GradSegment &g : c->grad_segments)
+                if (g.kind == PB_PARAM_MESH_VERTICES) {
+                    HostMesh &m = c->meshes[g.id];
+                    m.d_fcross_t.reserve((size_t)m.nf * sizeof(float4));
+                    m.d_vnormal_t.reserve(3 * (size_t)m.nv * sizeof(float));
+                    launch_mesh_tangent(st, m.nv, m.nf, m.face_offset, m.d_vraw.as<float>(), d_grad + g.offset, to_dev(m.to_world), m.d_vworld.as<float>(),
+                                        m.d_faces.as<int>(), m.d_csr_off.as<int>(), m.d_csr_face.as<int>(), m.d_fcross.as<float4>(), m.d_gworld.as<float>(),
+                                        m.d_fcross_t.as<float4>(), m.d_vnormal_t.as<float>(), c->d_tri_tangent.as<float>());
+                    c->launches += 4;
+                }
+            c->d_jvp_acc.reserve((size_t)B * sizeof(float));
+            P.S.tri_grad = nullptr;
+            P.S.tri_tangent = c->d_tri_tangent.as<float>();
+            P.S.jvp_acc = c->d_jvp_acc.as<float>();
+            P.S.jvp_image = d_dimage;
+            P.S.jvp_channel = 0;
         }
     }
     std::vector<BounceParams> bps(plan.nbounce);
@@ -817,13 +870,16 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             }
         }
         if (mode == MODE_VJP) {
-            for (int k = plan.nbounce - 1; k >= 0; --k) {
-                launch_adjoint(st, P, bps[k], event(k), c->d_suffix.as<float4>(), d_dLdI);
-                c->launches++;
+            for (int ch = 0; ch < (jvp ? 3 : 1); ++ch) {   // forward mode: one pass per colour channel with a unit seed
+                if (jvp) { P.S.jvp_channel = ch; PB_CUDA(cudaMemsetAsync(c->d_jvp_acc.p, 0, (size_t)P.n * sizeof(float), st)); }
+                for (int k = plan.nbounce - 1; k >= 0; --k) {
+                    launch_adjoint(st, P, bps[k], event(k), c->d_suffix.as<float4>(), d_dLdI);
+                    c->launches++;
+                }
             }
         }
     }
-    if (mode == MODE_VJP && P.S.tri_grad) run_edge_terms(c, I, sensor, plan, P, d_dLdI, &nev_edge);
+    if (mode == MODE_VJP && (P.S.tri_grad || (jvp && any_geom_jvp(c)))) run_edge_terms(c, I, sensor, plan, P, d_dLdI, &nev_edge);
     if (mode == MODE_VJP && P.S.tri_grad) {   // triangle-table adjoint -> object-space vertex gradients (mesh.cpp:19-51,215-231 backward)
         for (const GradSegment &g : c->grad_segments)
             if (g.kind == PB_PARAM_MESH_VERTICES) {
@@ -1180,6 +1236,18 @@ int pb_debug_retained_rad(pb_ctx *c, void **d_rad, int64_t *bytes) {
     });
 }
 int pb_ctx_set_retain_limit(pb_ctx *c, int64_t bytes) { c->retain_limit = bytes; c->retained_valid = false; return 0; }
+int pb_render_d_jvp(pb_ctx *c, const pb_integrator *I, int sensor, const float *d_tangent, float *d_dimage) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(I && d_tangent && d_dimage, "Null argument");
+        PB_ASSERT_MSG(c->have_last_d, "pb_render_d_jvp needs a preceding pb_render_d on the configured scene");
+        PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD || I->field == PB_FIELD_SILHOUETTE,
+                      "FieldExtractionIntegrator: only the silhouette field (zero interior derivative) has derivatives so far");
+        for (const GradSegment &g : c->grad_segments)
+            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || (c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE),
+                          "pb_render_d_jvp: texture derivatives are implemented for diffuse reflectance only so far");
+        render_interior(c, *I, sensor, d_dimage, MODE_JVP, nullptr, const_cast<float *>(d_tangent));
+    });
+}
 int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }
 float pb_stats_last_trace_ms(pb_ctx *c) { return c->last_trace_ms; }
 int64_t pb_stats_last_rays(pb_ctx *c) { return c->last_rays; }

@@ -156,7 +156,76 @@ __global__ void k_mesh_bwd_vertex(int nv, const int *__restrict__ csr_off, const
     }
 }
 
+// ---- forward mode of the mesh preprocessing: vertex tangents -> tangent of the triangle table ---------------------------------
+__global__ void k_mesh_tan_vertices(int nv, const float *__restrict__ vraw, const float *__restrict__ vraw_t, Mat4 M, float *__restrict__ vworld_t) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const float3 x = f3(vraw[3 * v], vraw[3 * v + 1], vraw[3 * v + 2]), u = f3(vraw_t[3 * v], vraw_t[3 * v + 1], vraw_t[3 * v + 2]);
+    float t[4], dt[4];
+    for (int i = 0; i < 4; ++i) {
+        t[i] = M.m[4 * i] * x.x + M.m[4 * i + 1] * x.y + M.m[4 * i + 2] * x.z + M.m[4 * i + 3];
+        dt[i] = M.m[4 * i] * u.x + M.m[4 * i + 1] * u.y + M.m[4 * i + 2] * u.z;
+    }
+    for (int k = 0; k < 3; ++k) vworld_t[3 * v + k] = (dt[k] - (t[k] / t[3]) * dt[3]) / t[3];
+}
+// per face: tangent of the unnormalised normal c = e1 x e2 and of its length -> fcross_t = (dc, d|c|)
+__global__ void k_mesh_tan_faces(int nf, const float *__restrict__ vworld, const float *__restrict__ vworld_t, const int *__restrict__ faces,
+                                 float4 *__restrict__ fcross_t) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    auto ld = [](const float *a, int i) { return f3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); };
+    const float3 p0 = ld(vworld, i0), e1 = ld(vworld, i1) - p0, e2 = ld(vworld, i2) - p0;
+    const float3 dp0 = ld(vworld_t, i0), de1 = ld(vworld_t, i1) - dp0, de2 = ld(vworld_t, i2) - dp0;
+    const float3 c = pcross(e1, e2), dc = pcross(de1, e2) + pcross(e1, de2);
+    fcross_t[f] = make_float4(dc.x, dc.y, dc.z, pdot(c, dc) / sqrtf(pdot(c, c)));
+}
+__global__ void k_mesh_tan_vnormals(int nv, const int *__restrict__ csr_off, const int *__restrict__ csr_face, const float4 *__restrict__ fcross,
+                                    const float4 *__restrict__ fcross_t, float *__restrict__ vnormal_t) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    float3 A = f3(0.f), dA = f3(0.f);
+    float w = 0.f, dw = 0.f;
+    for (int k = csr_off[v]; k < csr_off[v + 1]; ++k) {
+        const float4 c = fcross[csr_face[k]], dc = fcross_t[csr_face[k]];
+        A += f3(c); w += c.w; dA += f3(dc); dw += dc.w;
+    }
+    float3 dn = f3(0.f);
+    if (w > 0.f) {
+        const float3 B = A * (1.f / w), dB = (dA - B * dw) * (1.f / w);
+        const float len = sqrtf(pdot(B, B));
+        const float3 n = B * (1.f / len);
+        dn = (dB - n * pdot(n, dB)) * (1.f / len);
+    }
+    vnormal_t[3 * v] = dn.x; vnormal_t[3 * v + 1] = dn.y; vnormal_t[3 * v + 2] = dn.z;
+}
+__global__ void k_mesh_tan_assemble(int nf, int face_offset, const float *__restrict__ vworld_t, const int *__restrict__ faces, const float4 *__restrict__ fcross,
+                                    const float4 *__restrict__ fcross_t, const float *__restrict__ vnormal_t, float *__restrict__ tri_tangent) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    auto ld = [](const float *a, int i) { return f3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); };
+    const float3 dp0 = ld(vworld_t, i0), de1 = ld(vworld_t, i1) - dp0, de2 = ld(vworld_t, i2) - dp0;
+    const float4 c = fcross[f], dc = fcross_t[f];
+    const float3 fn = f3(c) * (1.f / c.w);
+    const float3 dfn = (f3(dc) - fn * pdot(fn, f3(dc))) * (1.f / c.w);
+    float *o = tri_tangent + (size_t)(face_offset + f) * kTriGradStride;
+    const float3 rows[7] = {dp0, de1, de2, ld(vnormal_t, i0), ld(vnormal_t, i1), ld(vnormal_t, i2), dfn};
+    for (int k = 0; k < 7; ++k) { o[3 * k] = rows[k].x; o[3 * k + 1] = rows[k].y; o[3 * k + 2] = rows[k].z; }
+    o[21] = 0.5f * dc.w; o[22] = 0.f; o[23] = 0.f;
+}
+
 static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+void launch_mesh_tangent(cudaStream_t st, int nv, int nf, int face_offset, const float *vraw, const float *vraw_t, const Mat4 &to_world, const float *vworld,
+                         const int *faces, const int *csr_off, const int *csr_face, const float4 *fcross, float *vworld_t, float4 *fcross_t, float *vnormal_t,
+                         float *tri_tangent) {
+    if (nv <= 0 || nf <= 0) return;
+    k_mesh_tan_vertices<<<nblk(nv, 256), 256, 0, st>>>(nv, vraw, vraw_t, to_world, vworld_t);
+    k_mesh_tan_faces<<<nblk(nf, 256), 256, 0, st>>>(nf, vworld, vworld_t, faces, fcross_t);
+    k_mesh_tan_vnormals<<<nblk(nv, 256), 256, 0, st>>>(nv, csr_off, csr_face, fcross, fcross_t, vnormal_t);
+    k_mesh_tan_assemble<<<nblk(nf, 256), 256, 0, st>>>(nf, face_offset, vworld_t, faces, fcross, fcross_t, vnormal_t, tri_tangent);
+}
 
 void launch_mesh_backward(cudaStream_t st, int nv, int nf, int face_offset, const int *csr_off, const int *csr_slot, const float4 *fcross,
                           const float *vworld, const int *faces, const float *vraw, const Mat4 &to_world, const float *tri_grad,

@@ -56,9 +56,13 @@ __global__ void __launch_bounds__(128) k_edge_primary_rays(RenderParams P, EdgeP
     reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
 }
 
-PB_D void atomic_add3(float *p, float3 v) {
-    if (!finite3(v)) return;   // degenerate samples must not poison the gradient
-    atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z);
+// adjoint of a world-space vertex: reverse mode adds it to the mesh's vertex-adjoint buffer; forward mode (the buffer then
+// holds the vertex tangents) returns its dot product with the tangent
+PB_D float vertex_adjoint(const SceneView &S, float *buf, int v, float3 g) {
+    if (!finite3(g)) return 0.f;   // degenerate samples must not poison the gradient
+    if (S.tri_tangent) return g.x * buf[3 * v] + g.y * buf[3 * v + 1] + g.z * buf[3 * v + 2];
+    atomicAdd(buf + 3 * v, g.x); atomicAdd(buf + 3 * v + 1, g.y); atomicAdd(buf + 3 * v + 2, g.z);
+    return 0.f;
 }
 
 // integrator.cpp:111-117: value = x_dot_n * (L_n - L_p) / pdf / sppe; only x_dot_n carries a derivative. Its adjoint goes
@@ -75,13 +79,16 @@ __global__ void __launch_bounds__(256) k_edge_primary_grad(RenderParams P, EdgeP
     float *gworld = Q.mesh_gworld[es.rec.mesh];
     if (!gworld) return;
     const float3 delta = f3(rad_n[i]) - f3(rad_p[i]);
+    const bool jvp = P.S.tri_tangent != nullptr;
     float w = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float v = es.x_dot_n * (getc(delta, c) / es.pdf);
-        if (isfinite(v)) w += __ldg(dLdI + 3 * (size_t)es.idx + c) * (getc(delta, c) / es.pdf) * inv_sppe;
+        const float seed = jvp ? (c == P.S.jvp_channel ? 1.f : 0.f) : __ldg(dLdI + 3 * (size_t)es.idx + c);
+        if (isfinite(v)) w += seed * (getc(delta, c) / es.pdf) * inv_sppe;
     }
     if (w == 0.f) return;
+    float jsum = 0.f;
     // x_dot_n = p_ . n,  p_ = (1-s) q0 + s q1,  q = (M (v,1)).xy / (M (v,1)).w
     const float gq[2][2] = {{w * es.rec.nx * (1.f - es.s), w * es.rec.ny * (1.f - es.s)}, {w * es.rec.nx * es.s, w * es.rec.ny * es.s}};
     const float qv[2][2] = {{es.rec.p0x, es.rec.p0y}, {es.rec.p1x, es.rec.p1y}};
@@ -94,8 +101,9 @@ __global__ void __launch_bounds__(256) k_edge_primary_grad(RenderParams P, EdgeP
         const float tw = M[12] * x.x + M[13] * x.y + M[14] * x.z + M[15];
         const float gt0 = gq[e][0] / tw, gt1 = gq[e][1] / tw, gt3 = -(gq[e][0] * qv[e][0] + gq[e][1] * qv[e][1]) / tw;
         const float3 gx = f3(M[0] * gt0 + M[4] * gt1 + M[12] * gt3, M[1] * gt0 + M[5] * gt1 + M[13] * gt3, M[2] * gt0 + M[6] * gt1 + M[14] * gt3);
-        atomic_add3(gworld + 3 * vid[e], gx);
+        jsum += vertex_adjoint(P.S, gworld, vid[e], gx);
     }
+    if (jvp && jsum != 0.f && isfinite(jsum)) atomicAdd(P.S.jvp_image + 3 * (size_t)es.idx + P.S.jvp_channel, jsum);
 }
 
 // ---- secondary edges ---------------------------------------------------------------------------------------------------
@@ -286,6 +294,7 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
     ray_intersect_triangle(te.p0, te.e1, te.e2, x1, sd, u, v, t);
     const float3 u2 = te.p0 + te.e1 * u + te.e2 * v;
     const float nv = pdot(n, u2);
+    const bool jvp = P.S.tri_tangent != nullptr;
     float W = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -293,14 +302,15 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
         if (isfinite(prim)) {
             float wv = getc(value0, c) * inv_sppse;
             if (guide_pdf > kEpsilon) wv /= guide_pdf;
-            W += __ldg(dLdI + 3 * (size_t)sds.pixel + c) * wv;
+            W += (jvp ? (c == P.S.jvp_channel ? 1.f : 0.f) : __ldg(dLdI + 3 * (size_t)sds.pixel + c)) * wv;
         }
     }
-    if (W == 0.f || !P.S.tri_grad) return;
+    if (W == 0.f || !geom_mode(P.S)) return;
+    if (jvp) P.S.jvp_acc[i] = 0.f;
     // d(n . u2): only (u, v) carry derivatives
     const float3 g_u2 = n * W;
     const RayTriGrad rt = ray_intersect_triangle_vjp(te.p0, te.e1, te.e2, x1, sd, pdot(g_u2, te.e1), pdot(g_u2, te.e2), 0.f);
-    if (te.flags & 8) { TriGrad g; g.p0 = rt.p0; g.e1 = rt.e1; g.e2 = rt.e2; tri_grad_scatter(P.S.tri_grad, h2.tri, g); }
+    if (te.flags & 8) { TriGrad g; g.p0 = rt.p0; g.e1 = rt.e1; g.e2 = rt.e2; tri_grad_scatter(P.S, h2.tri, g); }
     const float3 g_x = normalize_vjp(sd_raw, rt.d);           // sd = normalize(p0 - x1)
     const float3 g_x1 = rt.o - g_x, g_p0 = g_x;
     // x1 = cam_o + t_c cam_d with t_c from the camera ray's triangle (scene.cpp:357,366)
@@ -310,14 +320,19 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
         if (__float_as_int(q2.w) & 8) {
             const RayTriGrad rc = ray_intersect_triangle_vjp(f3(q0), f3(q1), f3(q2), cam_o, cam_d, 0.f, 0.f, pdot(g_x1, cam_d));
             TriGrad g; g.p0 = rc.p0; g.e1 = rc.e1; g.e2 = rc.e2;
-            tri_grad_scatter(P.S.tri_grad, hc.tri, g);
+            tri_grad_scatter(P.S, hc.tri, g);
         }
     }
     // edge point p0 = (1-s) v0 + s v1
     float *gworld = Q.mesh_gworld[bss.info.mesh];
+    float jsum = 0.f;
     if (gworld) {
-        atomic_add3(gworld + 3 * bss.info.v0, g_p0 * (1.f - bss.s));
-        atomic_add3(gworld + 3 * bss.info.v1, g_p0 * bss.s);
+        jsum += vertex_adjoint(P.S, gworld, bss.info.v0, g_p0 * (1.f - bss.s));
+        jsum += vertex_adjoint(P.S, gworld, bss.info.v1, g_p0 * bss.s);
+    }
+    if (jvp) {
+        jsum += P.S.jvp_acc[i];
+        if (jsum != 0.f && isfinite(jsum)) atomicAdd(P.S.jvp_image + 3 * (size_t)sds.pixel + P.S.jvp_channel, jsum);
     }
 }
 

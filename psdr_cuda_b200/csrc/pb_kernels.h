@@ -48,6 +48,9 @@ void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, in
 void launch_mesh_backward(cudaStream_t st, int nv, int nf, int face_offset, const int *csr_off, const int *csr_slot, const float4 *fcross,
                           const float *vworld, const int *faces, const float *vraw, const Mat4 &to_world, const float *tri_grad,
                           const float *g_world_direct, float *g_nsum, float *g_corner, float *grad_out);
+void launch_mesh_tangent(cudaStream_t st, int nv, int nf, int face_offset, const float *vraw, const float *vraw_t, const Mat4 &to_world, const float *vworld,
+                         const int *faces, const int *csr_off, const int *csr_face, const float4 *fcross, float *vworld_t, float4 *fcross_t, float *vnormal_t,
+                         float *tri_tangent);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_trace_blocks_per_sm;

@@ -105,6 +105,12 @@ struct SceneView {
     int num_tri, num_nodes, num_meshes, num_bsdfs, num_emitters;
     int emitter_env;
     float *tri_grad;        // VJP only: kTriGradStride floats per triangle (adjoint of the triangle table), or nullptr
+    // forward mode (JVP): the same adjoint kernels run once per colour channel with a unit seed; instead of scattering a
+    // local gradient they dot it with the tangent of what it refers to and add the result to the lane's accumulator
+    const float *tri_tangent;   // kTriGradStride floats per triangle: tangent of the triangle table, or nullptr (reverse mode)
+    float *jvp_acc;             // one float per lane of the batch
+    int jvp_channel;            // colour channel of this pass
+    float *jvp_image;           // W*H*3 derivative image
 };
 
 enum { INTEG_DIRECT = 0, INTEG_FIELD = 1, INTEG_PATH = 2 };

@@ -89,18 +89,43 @@ PB_D void film_accumulate(float *film, int pix, float3 val) {
 }
 
 // scatter one triangle's adjoint into the triangle-table gradient (only meshes that require a gradient carry bit3)
-PB_D void tri_grad_scatter(float *tg, int tri, const TriGrad &g) {
-    float *p = tg + (size_t)tri * kTriGradStride;
+PB_D bool geom_mode(const SceneView &S) { return S.tri_grad != nullptr || S.tri_tangent != nullptr; }
+PB_D void jvp_add(const SceneView &S, float v) {
+    if (isfinite(v)) S.jvp_acc[blockIdx.x * blockDim.x + threadIdx.x] += v;   // every wavefront kernel maps thread -> lane this way
+}
+PB_D void tri_grad_scatter(const SceneView &S, int tri, const TriGrad &g) {
     const float v[22] = {g.p0.x, g.p0.y, g.p0.z, g.e1.x, g.e1.y, g.e1.z, g.e2.x, g.e2.y, g.e2.z, g.n0.x, g.n0.y, g.n0.z,
                          g.n1.x, g.n1.y, g.n1.z, g.n2.x, g.n2.y, g.n2.z, g.fn.x, g.fn.y, g.fn.z, g.area};
-#pragma unroll
     bool ok = true;   // a degenerate sample (zero-length connection, zero pdf) must not poison the whole gradient
 #pragma unroll
     for (int k = 0; k < 22; ++k) ok = ok && isfinite(v[k]);
     if (!ok) return;
+    if (S.tri_tangent) {   // forward mode: <local gradient, tangent of the triangle record>
+        const float *t = S.tri_tangent + (size_t)tri * kTriGradStride;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 22; ++k) if (v[k] != 0.f) s = fmaf(v[k], __ldg(t + k), s);
+        jvp_add(S, s);
+        return;
+    }
+    float *p = S.tri_grad + (size_t)tri * kTriGradStride;
 #pragma unroll
     for (int k = 0; k < 22; ++k) if (v[k] != 0.f) atomicAdd(p + k, v[k]);
 }
+// scalar version of film_accumulate for one channel of the derivative image
+PB_D void film_accumulate1(float *img, int pix, int channel, float val) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float x = __shfl_down_sync(full, val, o);
+        const int p2 = __shfl_down_sync(full, pix, o);
+        if (lane + o < 32 && p2 == pix) val += x;
+    }
+    const int prev = __shfl_up_sync(full, pix, 1);
+    if (pix >= 0 && (lane == 0 || prev != pix) && val != 0.f) atomicAdd(img + 3 * (size_t)pix + channel, val);
+}
+
 struct TriFull { float3 p0, e1, e2, n0, n1, n2, fn; float area; int flags; };
 PB_D TriFull load_tri_full(const SceneView &S, int tri) {
     const float4 *q = reinterpret_cast<const float4 *>(S.tri + tri);
@@ -118,7 +143,7 @@ PB_D void point_on_triangle_scatter(const SceneView &S, int tri, float u, float 
     if (!(__float_as_int(q2.w) & 8)) return;
     TriGrad g;
     g.p0 = g_q; g.e1 = g_q * u; g.e2 = g_q * v; g.fn = g_n; g.area = g_J / q0.w;
-    tri_grad_scatter(S.tri_grad, tri, g);
+    tri_grad_scatter(S, tri, g);
 }
 
 }  // namespace pb

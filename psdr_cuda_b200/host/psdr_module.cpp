@@ -535,6 +535,10 @@ struct Integrator {
         require_ready(s);
         s.check(pb_render_d_vjp(s.ctx, &desc, sensor, reinterpret_cast<const float *>(d_dLdI), reinterpret_cast<float *>(d_grad)));
     }
+    void render_d_jvp(Scene &s, int sensor, uintptr_t d_tangent, uintptr_t d_dimage) const {
+        require_ready(s);
+        s.check(pb_render_d_jvp(s.ctx, &desc, sensor, reinterpret_cast<const float *>(d_tangent), reinterpret_cast<float *>(d_dimage)));
+    }
     farray render_c_numpy(Scene &s, int sensor) const {
         require_ready(s);
         farray img(std::vector<py::ssize_t>{(py::ssize_t)s.opts.width * s.opts.height, 3});
@@ -661,6 +665,7 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def("_render_c", &Integrator::render_c)
         .def("_render_d", &Integrator::render_d)
         .def("_render_d_vjp", &Integrator::render_d_vjp)
+        .def("_render_d_jvp", &Integrator::render_d_jvp)
         .def("renderC_numpy", &Integrator::render_c_numpy, py::arg("scene"), py::arg("sensor_id") = 0)
         .def("preprocess_secondary_edges", &Integrator::preprocess_secondary_edges, py::arg("scene"), py::arg("sensor_id"), py::arg("resolution"), py::arg("nrounds") = 1)
         .def_property("hide_emitters", [](const Integrator &i) { return i.desc.hide_emitters != 0; }, [](Integrator &i, bool v) { i.desc.hide_emitters = v ? 1 : 0; });

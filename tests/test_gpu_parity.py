@@ -410,3 +410,52 @@ def test_other_fixture_scenes_renderC_renderD(scene, w, h):
         assert_image_parity(ctx.render_c(integ).cpu().numpy(), oi.renderC(osc), outliers=outl)
         assert_image_parity(ctx.render_d(integ).cpu().numpy(), oi.renderD(osc)[0], outliers=outl)
         ctx.close()
+
+
+# ---- forward mode (ek.forward in the reference's examples): derivative images against the oracle's duals, pixel by pixel ----
+@pytest.mark.parametrize("label,opts,kind,kw,what", [
+    ("interior-albedo", dict(width=48, height=48, spp=8, sppe=0, sppse=0), "path", dict(max_depth=3), "albedo"),
+    ("interior-translate", dict(width=48, height=48, spp=8, sppe=0, sppse=0), "direct", dict(bsdf_samples=1, light_samples=1), "translate"),
+    ("interior-random", dict(width=48, height=48, spp=8, sppe=0, sppse=0), "path", dict(max_depth=3), "random"),
+    ("primary-edges", dict(width=48, height=48, spp=0, sppe=8, sppse=0), "direct", dict(bsdf_samples=1, light_samples=1), "translate"),
+    ("secondary-edges", dict(width=48, height=48, spp=0, sppe=0, sppse=32), "direct", dict(bsdf_samples=1, light_samples=1), "translate"),
+    ("all-terms", dict(width=48, height=48, spp=8, sppe=8, sppse=8), "path", dict(max_depth=2), "translate"),
+])
+def test_forward_mode_derivative_images(label, opts, kind, kw, what):
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    rng = np.random.default_rng(99)
+    pdesc = scene_io.load_scene_description(scene_path("cbox_bunny"))
+    odesc = orc.load_scene_description(scene_path("cbox_bunny"))
+    ctx = capi.Context(0)
+    ctx.load_description(pdesc, opts)
+    if what == "albedo":
+        ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "reflectance")
+    else:
+        ctx.grad_require(capi.PARAM_MESH_VERTICES, 1)
+    ctx.configure()
+    integ = capi.make_integrator(kind, **kw)
+    oi = orc.DirectIntegrator(kw.get("bsdf_samples", 1), kw.get("light_samples", 1)) if kind == "direct" else orc.PathIntegrator(kw["max_depth"])
+    nv = len(odesc["meshes"][1]["verts"])
+    if what == "albedo":
+        u = np.array([1.0, 0.5, 0.25], np.float32)
+    elif what == "translate":
+        u = np.tile(np.array([[1.0, 0.5, -0.3]], np.float32), (nv, 1))
+    else:
+        u = rng.normal(size=(nv, 3)).astype(np.float32)
+    ctx.render_d(integ)
+    dimg = ctx.render_d_jvp(integ, torch.from_numpy(u.reshape(-1)).cuda()).cpu().numpy()
+    osc = orc.Scene(odesc, opts)
+    if what == "albedo":
+        osc.set_bsdf_tangent(0, "reflectance", u.reshape(1, 1, 3))
+    else:
+        osc.set_mesh_vertex_tangent(1, u)
+    osc.configure()
+    _, ref = oi.renderD(osc)
+    assert np.linalg.norm(dimg - ref) <= 1e-3 * np.linalg.norm(ref), label
+    # forward / reverse consistency: <v, J u> == <J^T v, u> (1e-4 relative)
+    v = rng.uniform(-1, 1, size=dimg.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(v).cuda()).cpu().numpy()
+    a, b = float((v.astype(np.float64) * dimg).sum()), float((g.astype(np.float64) * u.reshape(-1)).sum())
+    assert abs(a - b) <= 2e-4 * max(abs(a), abs(b)), (label, a, b)
+    ctx.close()

@@ -129,6 +129,11 @@ def test_psdr_cuda_module_renders_and_differentiates(psdr_cuda):
     assert torch.equal(img_c, ref_c) and torch.equal(img.detach(), ref_d)
     assert torch.allclose(albedo.grad.reshape(-1), g[:3], rtol=1e-4, atol=1e-5)
     assert (verts.grad.reshape(-1) - g[3:]).norm() <= 1e-4 * g[3:].norm()
+    # forward mode through the module: directional derivative of the image along d(albedo) = (1, 1, 1)
+    img_f, dimg = integ.forward(sc, {albedo: torch.ones_like(albedo)})
+    ctx.render_d(ci)
+    flat = torch.zeros(ctx.grad_size(), device="cuda"); flat[:3] = 1
+    assert torch.allclose(dimg, ctx.render_d_jvp(ci, flat), rtol=1e-5, atol=1e-6)
     # an optimisation step moves the parameter and the next configure() picks it up (examples/utils/adam.py flow)
     with torch.no_grad():
         albedo -= 0.1 * albedo.grad / albedo.grad.abs().max()
