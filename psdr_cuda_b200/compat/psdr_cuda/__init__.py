@@ -40,6 +40,59 @@ def _read_exr(path, channels):
     return np.ascontiguousarray(img[:, :, :channels])
 
 
+def _enoki():
+    """the Enoki stand-in (psdr_cuda_b200/compat/enoki) if the caller imported it — examples/ do — else None"""
+    import sys
+    m = sys.modules.get("enoki")
+    return m if m is not None and getattr(m, "__psdr_b200_shim__", False) else None
+
+
+class _Proxy:
+    """param_map entry: forwards to the C++ object and accepts the Enoki stand-in's arrays (value + tangent) where the
+    reference accepts Enoki autodiff arrays (src/psdr.cpp:242-265)"""
+
+    def __init__(self, scene, key, obj):
+        object.__setattr__(self, "_scene", scene)
+        object.__setattr__(self, "_key", key)
+        object.__setattr__(self, "_obj", obj)
+
+    def __getattr__(self, name):
+        obj = object.__getattribute__(self, "_obj")
+        if name == "vertex_positions" and _enoki() is not None:
+            return _enoki().Vector3f(obj.vertex_positions)
+        return getattr(obj, name)
+
+    def __setattr__(self, name, value):
+        obj, scene = self._obj, self._scene
+        if name == "vertex_positions" and hasattr(value, "tangent_numpy"):
+            obj.vertex_positions = value.numpy()
+            scene._fwd_vertex[obj_index(obj)] = value.tangent_numpy() if value.has_tangent() else None
+            if value.has_tangent():
+                obj.requires_grad = True
+            return
+        setattr(obj, name, value)
+
+    def set_transform(self, mat, set_left=True):
+        obj, scene = self._obj, self._scene
+        if hasattr(mat, "v") and hasattr(mat, "d"):          # Matrix4f of the Enoki stand-in
+            obj.set_transform(mat.v, set_left)
+            if obj.type_name() == "Mesh":
+                scene._fwd_transform[(obj_index(obj), bool(set_left))] = mat.d
+                if mat.d is not None:
+                    obj.requires_grad = True
+            elif mat.d is not None:
+                raise RuntimeError("derivatives w.r.t. this object's transform are not implemented yet")
+        else:
+            obj.set_transform(np.asarray(mat, dtype=np.float32), set_left) if obj.type_name() == "Mesh" else obj.set_transform(np.asarray(mat, dtype=np.float32))
+
+    def __repr__(self):
+        return repr(self._obj)
+
+
+def obj_index(obj):
+    return obj.index
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():
@@ -54,12 +107,47 @@ class Scene(_h.Scene):
         super().__init__(device)
         self._device = device
         self._params = {}   # (key, field) -> torch leaf
+        self._fwd_vertex = {}      # mesh index -> (nv, 3) object-space vertex tangent (Enoki stand-in, forward mode)
+        self._fwd_transform = {}   # (mesh index, left?) -> 4x4 tangent of the transform
+
+    @property
+    def param_map(self):
+        raw = _h.Scene.param_map.fget(self)
+        return {k: _Proxy(self, k, v) for k, v in raw.items()}
+
+    def _raw_param_map(self):
+        return _h.Scene.param_map.fget(self)
+
+    def _forward_tangent(self):
+        """flat tangent vector (layout of the gradient vector) from what the Enoki stand-in stored on the scene: explicit vertex
+        tangents plus mesh-transform tangents mapped to object-space vertex tangents: u = M^-1 (dL raw R + L raw dR) (x, 1)"""
+        torch = _torch()
+        flat = np.zeros(max(1, self.grad_size()), np.float32)
+        raw = self._raw_param_map()
+        for key, field, off, cnt in self.grad_layout():
+            if field != "vertex_positions":
+                continue
+            m = raw[key]
+            i = m.index
+            u = np.zeros((m.num_vertices, 3), np.float64)
+            if self._fwd_vertex.get(i) is not None:
+                u += self._fwd_vertex[i]
+            dL, dR = self._fwd_transform.get((i, True)), self._fwd_transform.get((i, False))
+            if dL is not None or dR is not None:
+                L, R, W = m.to_world_left.astype(np.float64), m.to_world_right.astype(np.float64), m.to_world_raw.astype(np.float64)
+                M = L @ W @ R
+                dM = (0 if dL is None else dL.astype(np.float64) @ W @ R) + (0 if dR is None else L @ W @ dR.astype(np.float64))
+                x = np.concatenate([m.vertex_positions.astype(np.float64), np.ones((m.num_vertices, 1))], axis=1)
+                dworld = (x @ dM.T)[:, :3]
+                u += np.linalg.solve(M[:3, :3], dworld.T).T
+            flat[off:off + cnt] = u.reshape(-1).astype(np.float32)
+        return torch.from_numpy(flat).to("cuda:%d" % self._device)
 
     def parameter(self, key, field, requires_grad=True):
         """torch leaf mirroring `param_map[key].<field>` (e.g. ("BSDF[id=white]", "reflectance"), ("Mesh[1]", "vertex_positions")).
         Edit it in place / through an optimiser; `configure()` pushes the current value into the scene."""
         torch = _torch()
-        obj = self.param_map[key]
+        obj = self._raw_param_map()[key]
         value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
         t = torch.tensor(np.asarray(value), dtype=torch.float32, device="cuda:%d" % self._device, requires_grad=requires_grad)
         self._params[(key, field)] = t
@@ -67,7 +155,7 @@ class Scene(_h.Scene):
 
     def configure(self):
         for (key, field), t in self._params.items():
-            obj = self.param_map[key]
+            obj = self._raw_param_map()[key]
             val = t.detach().cpu().numpy()
             if field == "vertex_positions":
                 obj.vertex_positions = val
@@ -88,7 +176,7 @@ class Scene(_h.Scene):
     def _leaves_in_layout_order(self):
         """registered leaves matched to the segments of the flat gradient vector"""
         canon = {}
-        pm = self.param_map
+        pm = self._raw_param_map()
         for (key, field), t in self._params.items():
             obj = pm[key]
             for k2, o2 in pm.items():
@@ -111,12 +199,28 @@ class _IntegratorMixin:
         """Integrator.renderC (src/integrator/integrator.cpp:13-29) -> (H*W, 3) CUDA tensor, pixel = y*W + x"""
         img = _image_tensor(scene)
         self._render_c(scene, sensor_id, img.data_ptr())
-        return img
+        ek = _enoki()
+        return ek.Vector3f(img.cpu().numpy()) if ek is not None else img
 
     def renderD(self, scene, sensor_id=0):
         """Integrator.renderD (src/integrator/integrator.cpp:32-60) -> image attached to torch.autograd; backward() runs the
         reverse-mode kernels (interior + boundary terms) and fills .grad of the registered parameters"""
         torch = _torch()
+        ek = _enoki()
+        if ek is not None:   # examples/run_test.py flow: the derivative image is produced when ek.forward(P) runs
+            img = _image_tensor(scene)
+            self._render_d(scene, sensor_id, img.data_ptr())
+            out = ek.Vector3f(img.cpu().numpy())
+            integ = self
+
+            def run_forward():
+                dimg = torch.empty_like(img)
+                integ._render_d_jvp(scene, sensor_id, scene._forward_tangent().data_ptr(), dimg.data_ptr())
+                d = dimg.cpu().numpy()
+                out.x.d, out.y.d, out.z.d = d[:, 0].copy(), d[:, 1].copy(), d[:, 2].copy()
+            out._run_forward = run_forward
+            ek._pending.append(out)
+            return out
         segs = scene._leaves_in_layout_order()
         leaves = [t for t, _, _ in segs if t is not None and t.requires_grad]
         integ = self

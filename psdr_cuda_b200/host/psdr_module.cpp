@@ -601,7 +601,7 @@ PYBIND11_MODULE(_psdr_host, m) {
     };
     bitmap("BitmapD");
 
-    py::class_<BSDF, Object, std::shared_ptr<BSDF>>(m, "BSDF");
+    py::class_<BSDF, Object, std::shared_ptr<BSDF>>(m, "BSDF").def_readonly("index", &BSDF::index);
     py::class_<Diffuse, BSDF, std::shared_ptr<Diffuse>>(m, "DiffuseBSDF")
         .def_property_readonly("reflectance", [](Diffuse &d) -> Bitmap & { return d.reflectance; }, py::return_value_policy::reference_internal);
     py::class_<RoughConductor, BSDF, std::shared_ptr<RoughConductor>>(m, "RoughConductorBSDF")
@@ -630,6 +630,9 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_property("vertex_positions", &Mesh::get_vertices, &Mesh::set_vertices)
         .def_property_readonly("face_indices", &Mesh::get_faces)
         .def_property_readonly("to_world_raw", [](const Mesh &x) { return mat_to_numpy(x.to_world_raw); })
+        .def_property_readonly("to_world_left", [](const Mesh &x) { return mat_to_numpy(x.to_world_left); })
+        .def_property_readonly("to_world_right", [](const Mesh &x) { return mat_to_numpy(x.to_world_right); })
+        .def_readonly("index", &Mesh::index)
         .def_readonly("bsdf_index", &Mesh::bsdf)
         .def_readonly("emitter_index", &Mesh::emitter)
         .def_property_readonly("has_uv", [](const Mesh &x) { return !x.uvs.empty(); })
