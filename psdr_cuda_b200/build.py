@@ -50,7 +50,7 @@ def build_core(force=False, verbose=False):
         fh.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["--cudart", "static"])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["--cudart", "static"])
     return out
 
 

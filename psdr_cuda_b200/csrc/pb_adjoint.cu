@@ -7,6 +7,7 @@
 // Per lane the forward radiance is  L = Le(x0) + sum_k T_k * L_k,  T_{k+1} = T_k * w_k  (L_k: the event's MIS-weighted
 // connections, w_k: its continuation weight). With the suffix  S_k = L_k + w_k * S_{k+1}  the sensitivity of L to the
 // parameters touched by event k is  T_k * (dL_k + dw_k * S_{k+1}); the adjoint kernels run k = D-1 .. 0 carrying S.
+#include "pb_rc.cuh"
 #include "pb_trace.cuh"
 #include "pb_wavefront.cuh"
 
@@ -87,13 +88,18 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, floa
 
 // adjoint of one scattering event (texture parameters). E.thr_in: T_k; suffix: S_{k+1} in, S_k out; E.rad: the lane's
 // final forward radiance (decides which channels integrator.cpp:87 zeroed).
-__global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
+// RC: some rough-conductor texture requires a gradient (separate instantiation so that the diffuse-only kernel keeps its registers)
+template <int MINB, bool PREFETCH, bool RC>
+__global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
     const HitRec *__restrict__ hits = E.hits;
     __shared__ float s_acc[kMaxConstBsdf * 3];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float3 acc = f3(0.f);
     int bsdf_id = -1;
+    rc::TexGrad rc_acc;
+    bool rc_tex = false;
     if (i < P.n) {
+        if (PREFETCH) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
         int pix;
         const long long lane = global_lane(P, i, pix);
         const Vertex v = load_vertex(P, B, i, E);
@@ -116,6 +122,8 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
+        rc::Tex rtex;
+        if (RC) { rc_tex = v.active && rc::wants_tex_grad(v.bsdf); if (rc_tex) rtex = rc::load_tex(v.bsdf, its.uv); }
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
             const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
@@ -143,6 +151,13 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 }
                 if (cont) { w_cont = f * scale; gval += gw * scale; }
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gval, acc);
+                if (RC && rc_tex) {
+                    const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf(P.S, its.p, its1, true) : 0.f;
+                    rc::TexGrad tg;
+                    rc::bsdf_branch_tex_grad(rtex, its.wi, wo_l, s3, G, p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le(P.S, its1, true) : f3(0.f),
+                                             cont ? gw : f3(0.f), tg);
+                    rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                }
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     // value = K * (cos_o G J) with K = rho/pi * (Le weight gL + gw) / pdf0   (diffuse: pdf0 and the MIS weight are detached)
                     const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
@@ -184,6 +199,11 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gL * Le * scale, acc);
+                if (RC && rc_tex) {
+                    rc::TexGrad tg;
+                    rc::light_branch_tex_grad(rtex, its.wi, wo_l, G, ps.pdf, B.nb > 0, inv_nl, gL * Le, tg);
+                    rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                }
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
                     const float gc = pdot(gL * Le, rho) * kInvPi * weight / ps.pdf;
@@ -231,12 +251,20 @@ __global__ void __launch_bounds__(256) k_adjoint(RenderParams P, BounceParams B,
         return;
     }
     flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
+    if (RC) rc::flush_const_tex_grad(P.S, rc_tex ? bsdf_id : -1, rc_acc);
 }
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI) {
-    if (P.n > 0) k_adjoint<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E, suffix, dLdI);
+    if (P.n <= 0) return;
+    const unsigned g = nblk(P.n, 256);
+    if (B.rc_grad) { k_adjoint<1, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
+    switch (g_shade_tune) {
+        case 1: k_adjoint<2, true, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 2: case 3: k_adjoint<3, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        default: k_adjoint<2, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+    }
 }
 
 }  // namespace pb

@@ -629,7 +629,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                     for (int k = 0; k < plan.nbounce; ++k) {
                         BounceParams Bp;
                         Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
-                        Bp.hide_emitters = I.hide_emitters; Bp.ad = 0;
+                        Bp.hide_emitters = I.hide_emitters; Bp.ad = 0; Bp.rc_grad = 0;
                         Bp.jump = make_jump(base + 1 + (uint64_t)side * per_li + (uint64_t)k * per_event);
                         EventBuffers E;
                         E.hit_cur = (k == 0) ? hit0 : S.hits[(k - 1) & 1].as<HitRec>();
@@ -828,6 +828,10 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         BounceParams &Bp = bps[k];
         Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
         Bp.hide_emitters = I.hide_emitters; Bp.ad = (mode == MODE_C) ? 0 : 1;
+        Bp.rc_grad = 0;
+        if (mode == MODE_VJP)
+            for (const GradSegment &g : c->grad_segments)
+                if (g.kind == PB_PARAM_BSDF_TEXTURE && c->bsdfs[g.id].type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
         Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
     }
     size_t nev = 0, nev_edge = 0;
@@ -1196,6 +1200,9 @@ int pb_grad_segment(pb_ctx *c, int index, int *kind, int *id, int *slot, int64_t
         *kind = g.kind; *id = g.id; *slot = g.slot; *offset = g.offset; *count = g.count;
     });
 }
+static bool bsdf_slot_is_differentiable(int type, int slot) {
+    return type == PB_BSDF_DIFFUSE ? slot == PB_TEX_REFLECTANCE : (slot >= PB_TEX_ALPHA_U && slot <= PB_TEX_SPECULAR_REFLECTANCE);
+}
 int64_t pb_grad_size(pb_ctx *c) { return c->grad_segments.empty() ? 0 : c->grad_segments.back().offset + c->grad_segments.back().count; }
 int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *d_dLdI, float *d_grad) {
     return guard(c, [&] {
@@ -1204,8 +1211,8 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
         PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD || I->field == PB_FIELD_SILHOUETTE,
                       "FieldExtractionIntegrator: only the silhouette field (zero interior derivative) has gradients so far");
         for (const GradSegment &g : c->grad_segments)
-            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || (c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE),
-                          "pb_render_d_vjp: texture gradients are implemented for diffuse reflectance only so far");
+            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || bsdf_slot_is_differentiable(c->bsdfs[g.id].type, g.slot),
+                          "pb_render_d_vjp: this texture is not a parameter of its BSDF type (diffuse: reflectance; roughconductor: alpha_u, alpha_v, eta, k, specular_reflectance)");
         render_interior(c, *I, sensor, nullptr, MODE_VJP, d_dLdI, d_grad);
     });
 }
@@ -1216,6 +1223,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "trace_blocks_per_sm") == 0) pb::g_trace_blocks_per_sm = (int)value;
         else if (std::strcmp(key, "trace_smem") == 0) pb::g_trace_smem = (int)value;
         else if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
+        else if (std::strcmp(key, "shade_tune") == 0) pb::g_shade_tune = (int)value;
         else if (std::strcmp(key, "trace_smem_nodes") == 0) pb::g_trace_smem_nodes = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);
     });
@@ -1243,8 +1251,8 @@ int pb_render_d_jvp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
         PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD || I->field == PB_FIELD_SILHOUETTE,
                       "FieldExtractionIntegrator: only the silhouette field (zero interior derivative) has derivatives so far");
         for (const GradSegment &g : c->grad_segments)
-            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || (c->bsdfs[g.id].type == PB_BSDF_DIFFUSE && g.slot == PB_TEX_REFLECTANCE),
-                          "pb_render_d_jvp: texture derivatives are implemented for diffuse reflectance only so far");
+            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || bsdf_slot_is_differentiable(c->bsdfs[g.id].type, g.slot),
+                          "pb_render_d_jvp: this texture is not a parameter of its BSDF type (diffuse: reflectance; roughconductor: alpha_u, alpha_v, eta, k, specular_reflectance)");
         render_interior(c, *I, sensor, d_dimage, MODE_JVP, nullptr, const_cast<float *>(d_tangent));
     });
 }

@@ -16,6 +16,7 @@ struct BounceParams {
     int carry;              // 1: path mode, keep throughput/radiance state between events
     int hide_emitters;      // direct.h m_hide_emitters
     int ad;                 // 1: the reference's AD formulation of the primal (direct.cpp:83-95), 0: renderC's
+    int rc_grad;            // adjoint only: some rough-conductor texture requires a gradient
     RngJump jump;           // stream position of this event's first draw
 };
 
@@ -55,6 +56,7 @@ void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriR
 
 extern int g_trace_blocks_per_sm;
 extern int g_sort_mode;
+extern int g_shade_tune;   // debug: k_resolve / k_adjoint variant (0 default)
 extern int g_trace_smem;
 extern int g_trace_smem_nodes;
 extern int g_trace_variant;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while

@@ -1,0 +1,236 @@
+// psdr-b200: derivative of the rough-conductor scattering event (RoughConductor / GGXDistribution / fresnel in their
+// ad = true flavour: src/bsdf/roughconductor.cpp:40-93, src/bsdf/ggx.cpp:9-105, include/psdr/utils.h:149-164) as it appears in
+// DirectIntegrator::__Li<true> (src/integrator/direct.cpp:67-159).
+//
+// What is attached there (and therefore differentiated here): the BSDF value f(wi, wo; alpha, eta, k, spec), the pdf of the
+// BSDF-sampled direction *including the dependence of the sampled direction on alpha and wi* (bs.pdf = pdf(its, bs.wo), with
+// bs.wo = sample(its, u)), pdf1 of the emitter-sampled direction, and through them both MIS weights; the geometric term inside
+// pdf0 / pdf1 is detached (direct.cpp:93,147). The functions are templates over the scalar T = Dual<N> (pb_dual.cuh).
+#pragma once
+#include "pb_dual.cuh"
+#include "pb_shade.cuh"
+
+namespace pb {
+namespace rc {
+
+template <class T> PB_D T ggx_eval(const T &au, const T &av, const V3<T> &m) {   // ggx.cpp:15-34
+    const T result = 1.f / ((au * av) * dsqr(dsqr(m.x / au) + dsqr(m.y / av) + dsqr(m.z)) * kPi);
+    return val(result) * val(m.z) > 1e-5f ? result : T(0.f);
+}
+template <class T> PB_D T smith_g1(const T &au, const T &av, const V3<T> &v, const V3<T> &m) {   // ggx.cpp:79-93
+    const T xy_alpha_2 = dsqr(au * v.x) + dsqr(av * v.y);
+    T result = 2.f / (1.f + dsqrt(1.f + xy_alpha_2 / dsqr(v.z)));
+    if (val(xy_alpha_2) == 0.f) result = T(1.f);
+    if (val(vdot(v, m)) * val(v.z) <= 0.f) result = T(0.f);
+    return result;
+}
+// ggx.cpp:96-105; `p` is the concentric-disk image of the (constant) random numbers
+template <class T> PB_D void sample_visible_11(const T &cos_theta_i, float2 p, T &slope_x, T &slope_y) {
+    const T s = (1.f + cos_theta_i) * .5f;
+    const float a = safe_sqrt(1.f - sqr(p.x));
+    const T py = a + s * (p.y - a);   // lerp(a, p.y, s)
+    const T z = dsafe_sqrt(1.f - (dsqr(py) + sqr(p.x)));
+    const T sin_theta_i = dsafe_sqrt(1.f - dsqr(cos_theta_i));
+    const T nrm = 1.f / (sin_theta_i * py + cos_theta_i * z);
+    slope_x = (cos_theta_i * py - sin_theta_i * z) * nrm;
+    slope_y = nrm * p.x;
+}
+template <class T> PB_D V3<T> ggx_sample(const T &au, const T &av, const V3<T> &wi, float2 disk) {   // ggx.cpp:37-76
+    const V3<T> wi_p = vnormalize(V3<T>(au * wi.x, av * wi.y, wi.z));
+    const T sin_theta_2 = dsqr(wi_p.x) + dsqr(wi_p.y);
+    const bool degenerate = fabsf(val(sin_theta_2)) <= 4.f * kEpsilon;   // frame.h:103-117
+    T sin_phi(0.f), cos_phi(1.f);
+    if (!degenerate) {
+        const T inv_sin_theta = 1.f / dsqrt(sin_theta_2);
+        sin_phi = dclamp(wi_p.y * inv_sin_theta, -1.f, 1.f);
+        cos_phi = dclamp(wi_p.x * inv_sin_theta, -1.f, 1.f);
+    }
+    T sx, sy;
+    sample_visible_11<T>(wi_p.z, disk, sx, sy);
+    const T slx = (cos_phi * sx - sin_phi * sy) * au, sly = (sin_phi * sx + cos_phi * sy) * av;
+    return vnormalize(V3<T>(-slx, -sly, T(1.f)));
+}
+template <class T> PB_D T fresnel1(const T &eta_r, const T &eta_i, const T &cos_theta_i) {   // utils.h:149-164, one channel
+    const T c2 = dsqr(cos_theta_i), s2 = 1.f - c2, s4 = dsqr(s2);
+    const T temp_1 = dsqr(eta_r) - dsqr(eta_i) - s2;
+    const T a_2_pb_2 = dsafe_sqrt(dsqr(temp_1) + dsqr(eta_i * eta_r) * 4.f);
+    const T a = dsafe_sqrt((a_2_pb_2 + temp_1) * .5f);
+    const T term_1 = a_2_pb_2 + c2, term_2 = cos_theta_i * a * 2.f;
+    const T r_s = (term_1 - term_2) / (term_1 + term_2);
+    const T term_3 = a_2_pb_2 * c2 + s4, term_4 = term_2 * s2;
+    const T r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return (r_s + r_p) * .5f;
+}
+// D * G / (4 cos_i): the scalar part of RoughConductor::__eval (roughconductor.cpp:40-56), 0 outside its masks
+template <class T> PB_D T eval_scalar(const T &au, const T &av, const V3<T> &wi, const V3<T> &wo, const V3<T> &H) {
+    if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return T(0.f);
+    const T D = ggx_eval<T>(au, av, H);
+    if (val(D) == 0.f) return T(0.f);
+    return D * smith_g1<T>(au, av, wi, H) * smith_g1<T>(au, av, wo, H) / (wi.z * 4.f);
+}
+template <class T> PB_D T pdf(const T &au, const T &av, const V3<T> &wi, const V3<T> &wo) {   // roughconductor.cpp:60-75 (mask unused)
+    const V3<T> m = vnormalize(wo + wi);
+    return ggx_eval<T>(au, av, m) * smith_g1<T>(au, av, wi, m) / (wi.z * 4.f);
+}
+// pdf of the BSDF-sampled direction as a function of (alpha, wi): roughconductor.cpp:79-93
+template <class T> PB_D T sampled_pdf(const T &au, const T &av, const V3<T> &wi, float2 disk) {
+    const V3<T> m = ggx_sample<T>(au, av, wi, disk);
+    const T two_dot = vdot(wi, m) * 2.f;
+    const V3<T> wo(m.x * two_dot - wi.x, m.y * two_dot - wi.y, m.z * two_dot - wi.z);
+    return pdf<T>(au, av, wi, wo);
+}
+
+struct Tex { float au, av; float3 eta, k, spec; };
+PB_D Tex load_tex(const BsdfRec *b, float2 uv) {
+    Tex t;
+    t.au = tex_eval1(b->tex[TEX_ALPHA_U], uv); t.av = tex_eval1(b->tex[TEX_ALPHA_V], uv);
+    t.eta = tex_eval3(b->tex[TEX_ETA], uv); t.k = tex_eval3(b->tex[TEX_K], uv); t.spec = tex_eval3(b->tex[TEX_SPECULAR], uv);
+    return t;
+}
+PB_D bool wants_tex_grad(const BsdfRec *b) {
+    return b && b->type == BSDF_ROUGHCONDUCTOR &&
+           (b->tex[TEX_ALPHA_U].grad || b->tex[TEX_ALPHA_V].grad || b->tex[TEX_ETA].grad || b->tex[TEX_K].grad || b->tex[TEX_SPECULAR].grad);
+}
+
+// local gradient of one event's loss-weighted value w.r.t. the 11 texture-evaluated BSDF parameters
+struct TexGrad {
+    float au, av;
+    float3 eta, k, spec;
+    PB_D TexGrad() : au(0.f), av(0.f), eta(f3(0.f)), k(f3(0.f)), spec(f3(0.f)) {}
+    PB_D bool finite() const { return isfinite(au) && isfinite(av) && finite3(eta) && finite3(k) && finite3(spec); }
+    PB_D void add(const TexGrad &o) { au += o.au; av += o.av; eta += o.eta; k += o.k; spec += o.spec; }
+};
+
+// Shared tail of both branches: value = sum_ch coef_ch(alpha) * spec_ch * F_ch(eta_ch, k_ch) with
+// coef_ch = base(alpha) * (wA(alpha) * gA_ch + gB_ch); base and wA are Dual<2> in (alpha_u, alpha_v).
+PB_D void finish_tex_grad(const Tex &t, float cos_h, const Dual<2> &base, const Dual<2> &wA, float3 gA, float3 gB, TexGrad &g) {
+    typedef Dual<2> D2;
+    float F[3], dF_eta[3], dF_k[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const D2 f = fresnel1<D2>(D2::seed(getc(t.eta, c), 0), D2::seed(getc(t.k, c), 1), D2(cos_h));
+        F[c] = f.v; dF_eta[c] = f.d[0]; dF_k[c] = f.d[1];
+    }
+    const float ga[3] = {gA.x, gA.y, gA.z}, gb[3] = {gB.x, gB.y, gB.z}, sp[3] = {t.spec.x, t.spec.y, t.spec.z};
+    D2 total(0.f);
+    float g_spec[3], g_eta[3], g_k[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const D2 coef = base * (wA * ga[c] + gb[c]);
+        total += coef * (sp[c] * F[c]);
+        g_spec[c] = coef.v * F[c];
+        g_eta[c] = coef.v * sp[c] * dF_eta[c];
+        g_k[c] = coef.v * sp[c] * dF_k[c];
+    }
+    TexGrad r;
+    r.au = total.d[0]; r.av = total.d[1];
+    r.spec = f3(g_spec[0], g_spec[1], g_spec[2]); r.eta = f3(g_eta[0], g_eta[1], g_eta[2]); r.k = f3(g_k[0], g_k[1], g_k[2]);
+    if (r.finite()) g.add(r);   // degenerate sample (zero pdf, grazing direction): no contribution rather than a poisoned gradient
+}
+
+// BSDF-sampled connection (direct.cpp:67-113 with ad = true): value = f * G J / pdf0 * (Le weight [emitter hit] + S_next [continuation]),
+// pdf0 = bs.pdf * detach(G), weight = mis(pdf0, p_em) / nb. gA = dL/d(radiance) * T_k * Le (zero if the hit is no emitter),
+// gB = dL/d(radiance) * T_k * S_{k+1} (zero without continuation).
+PB_D void bsdf_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float3 s3, float G_geo, float p_em, bool use_mis, float inv_nb,
+                               float3 gA, float3 gB, TexGrad &g) {
+    typedef Dual<2> D2;
+    const D2 au = D2::seed(t.au, 0), av = D2::seed(t.av, 1);
+    const V3<D2> wi_d(wi), wo_d(wo_l);
+    const float3 Hf = normalize(wo_l + wi);
+    const D2 R = eval_scalar<D2>(au, av, wi_d, wo_d, V3<D2>(Hf));
+    if (R.v == 0.f) return;
+    const float2 disk = square_to_uniform_disk_concentric(s3.x, s3.y);   // roughconductor.cpp:87 uses head<2>(sample)
+    const D2 pdf0 = sampled_pdf<D2>(au, av, wi_d, disk) * G_geo;
+    D2 wA(inv_nb);
+    if (use_mis) { const D2 w1 = dsqr(pdf0); wA = w1 / (w1 + sqr(p_em)) * inv_nb; }
+    finish_tex_grad(t, dot(wi, Hf), R * G_geo / pdf0, wA, gA, gB, g);
+}
+// emitter-sampled connection (direct.cpp:119-159): value = f * G J / ps.pdf * Le * mis(ps.pdf, pdf1 * detach(G)) / nl
+PB_D void light_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float G_geo, float ps_pdf, bool use_mis, float inv_nl, float3 gA, TexGrad &g) {
+    typedef Dual<2> D2;
+    const D2 au = D2::seed(t.au, 0), av = D2::seed(t.av, 1);
+    const V3<D2> wi_d(wi), wo_d(wo_l);
+    const float3 Hf = normalize(wo_l + wi);
+    const D2 R = eval_scalar<D2>(au, av, wi_d, wo_d, V3<D2>(Hf));
+    if (R.v == 0.f) return;
+    D2 wA(inv_nl);
+    if (use_mis) { const D2 pdf1 = pdf<D2>(au, av, wi_d, wo_d) * G_geo; const float w1 = sqr(ps_pdf); wA = w1 / (w1 + dsqr(pdf1)) * inv_nl; }
+    finish_tex_grad(t, dot(wi, Hf), R * (G_geo / ps_pdf), wA, gA, f3(0.f), g);
+}
+
+// ---- scatter of the local gradient into the textures (Bitmap::eval's backward, bitmap.cpp:43-89) -------------------------------
+// reverse mode: atomics into the gradient segment; forward mode (S.tri_tangent set): dot with the texture's tangent.
+template <int C> PB_D void tex_scatter(const SceneView &S, const TexRef &t, float2 uv, const float *gv) {
+    if (!t.grad) return;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) any = any || gv[c] != 0.f;
+    if (!any) return;
+    const TexTap tap = tex_tap(t, uv);
+    const int n = tap.constant ? 1 : 4;
+    const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
+    const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
+    if (S.tri_tangent) {
+        float s = 0.f;
+        for (int k = 0; k < n; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) s = fmaf(w[k] * gv[c], __ldg(t.grad + idx[k] * C + c), s);
+        if (isfinite(s)) S.jvp_acc[blockIdx.x * blockDim.x + threadIdx.x] += s;
+        return;
+    }
+    for (int k = 0; k < n; ++k)
+#pragma unroll
+        for (int c = 0; c < C; ++c) if (gv[c] != 0.f) atomicAdd(t.grad + idx[k] * C + c, gv[c] * w[k]);
+}
+
+// Per-thread accumulator for 1x1 textures (the common case: one atomic per warp and parameter instead of one per lane);
+// bitmap textures scatter immediately.
+PB_D void emit_tex_grad(const SceneView &S, const BsdfRec *b, float2 uv, const TexGrad &g, TexGrad &acc_const) {
+    const bool all_const = b->tex[TEX_ALPHA_U].w * b->tex[TEX_ALPHA_U].h == 1 && b->tex[TEX_ALPHA_V].w * b->tex[TEX_ALPHA_V].h == 1 &&
+                           b->tex[TEX_ETA].w * b->tex[TEX_ETA].h == 1 && b->tex[TEX_K].w * b->tex[TEX_K].h == 1 &&
+                           b->tex[TEX_SPECULAR].w * b->tex[TEX_SPECULAR].h == 1;
+    if (all_const && !S.tri_tangent) { acc_const.add(g); return; }
+    const float e[3] = {g.eta.x, g.eta.y, g.eta.z}, k[3] = {g.k.x, g.k.y, g.k.z}, s[3] = {g.spec.x, g.spec.y, g.spec.z};
+    tex_scatter<1>(S, b->tex[TEX_ALPHA_U], uv, &g.au);
+    tex_scatter<1>(S, b->tex[TEX_ALPHA_V], uv, &g.av);
+    tex_scatter<3>(S, b->tex[TEX_ETA], uv, e);
+    tex_scatter<3>(S, b->tex[TEX_K], uv, k);
+    tex_scatter<3>(S, b->tex[TEX_SPECULAR], uv, s);
+}
+// warp-level flush of the 1x1-texture accumulators, grouped by BSDF id
+PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, const TexGrad &acc) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool has = bsdf_id >= 0 && (acc.au != 0.f || acc.av != 0.f || acc.eta.x != 0.f || acc.eta.y != 0.f || acc.eta.z != 0.f || acc.k.x != 0.f ||
+                                      acc.k.y != 0.f || acc.k.z != 0.f || acc.spec.x != 0.f || acc.spec.y != 0.f || acc.spec.z != 0.f);
+    unsigned remaining = __ballot_sync(full, has);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int key = __shfl_sync(full, bsdf_id, leader);
+        const bool mine = has && bsdf_id == key;
+        const unsigned grp = __ballot_sync(full, mine);
+        float v[11] = {acc.au, acc.av, acc.eta.x, acc.eta.y, acc.eta.z, acc.k.x, acc.k.y, acc.k.z, acc.spec.x, acc.spec.y, acc.spec.z};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            float x = mine ? v[k] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
+            v[k] = x;
+        }
+        if (lane == leader) {
+            const BsdfRec &b = S.bsdfs[key];
+            if (b.tex[TEX_ALPHA_U].grad && v[0] != 0.f) atomicAdd(b.tex[TEX_ALPHA_U].grad, v[0]);
+            if (b.tex[TEX_ALPHA_V].grad && v[1] != 0.f) atomicAdd(b.tex[TEX_ALPHA_V].grad, v[1]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (b.tex[TEX_ETA].grad && v[2 + c] != 0.f) atomicAdd(b.tex[TEX_ETA].grad + c, v[2 + c]);
+                if (b.tex[TEX_K].grad && v[5 + c] != 0.f) atomicAdd(b.tex[TEX_K].grad + c, v[5 + c]);
+                if (b.tex[TEX_SPECULAR].grad && v[8 + c] != 0.f) atomicAdd(b.tex[TEX_SPECULAR].grad + c, v[8 + c]);
+            }
+        }
+        remaining &= ~grp;
+    }
+}
+
+}  // namespace rc
+}  // namespace pb

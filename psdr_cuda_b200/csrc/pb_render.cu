@@ -239,13 +239,15 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
 }
 
 // direct.cpp:77-113 (BSDF-sampled connections) and 130-158 (emitter-sampled connections) for one scattering event
-__global__ void __launch_bounds__(256) k_resolve(RenderParams P, BounceParams B, EventBuffers E, float *__restrict__ film) {
+template <int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BounceParams B, EventBuffers E, float *__restrict__ film) {
     const HitRec *__restrict__ hits = E.hits;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i < P.n;
     int pix = -1;
     float3 out = f3(0.f);
     if (in_range) {
+        if (PREFETCH) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
         const long long lane = global_lane(P, i, pix);
         const Vertex v = load_vertex(P, B, i, E);
         const Its &its = v.its;
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 int g_trace_blocks_per_sm = 8;
+int g_shade_tune = 0;
 int g_trace_variant = 7;   // 7: counting-sorted + compacted wavefront (pb_sort.cu) for render calls; pb_trace uses the speculative kernel   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out) {
     if (n <= 0) return;
@@ -387,7 +390,14 @@ void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B,
     if (P.n > 0) k_shade<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
 }
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film) {
-    if (P.n > 0) k_resolve<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E, film);
+    if (P.n <= 0) return;
+    const unsigned g = nblk(P.n, 256);
+    switch (g_shade_tune) {   // debug: resident blocks per SM forced through the register cap / early prefetch of the connection hits
+        case 1: k_resolve<2, true><<<g, 256, 0, st>>>(P, B, E, film); break;
+        case 2: k_resolve<3, false><<<g, 256, 0, st>>>(P, B, E, film); break;
+        case 3: k_resolve<4, false><<<g, 256, 0, st>>>(P, B, E, film); break;
+        default: k_resolve<2, false><<<g, 256, 0, st>>>(P, B, E, film); break;
+    }
 }
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film, float4 *rad_out) {
     if (P.n > 0) k_field<<<nblk(P.n, 256), 256, 0, st>>>(P, field, hit0, film, rad_out);

@@ -35,6 +35,20 @@ PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax, float t_occ = 0.f
     q[1] = make_float4(d.x, d.y, d.z, t_occ);   // t_occ > 0: occlusion query, any hit closer than t_occ ends the traversal
 }
 
+// Start the dependent gathers of an event's connection rays early: read each ray's hit (so that the 16-byte record is in
+// L1 when load_hit asks for it) and prefetch the 128-byte triangle row it points at while the lane works on its own vertex.
+// Costs no registers; the kernels that reconstruct its1 are bound by this chain of L2 round trips (profiles/r01b_*).
+PB_D void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PB_D void prefetch_event_hits(const SceneView &S, const HitRec *__restrict__ hits, int rays, int n, int i) {
+    for (int j = 0; j < rays; ++j) {
+        const int tri = __ldg(reinterpret_cast<const int *>(hits + (size_t)j * n + i));
+        if (tri >= 0) {
+            const char *row = reinterpret_cast<const char *>(S.tri + tri);
+            prefetch_line(row); prefetch_line(row + 32); prefetch_line(row + 64); prefetch_line(row + 96);
+        }
+    }
+}
+
 PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const EventBuffers &E) {
     const HitRec *hit_cur = E.hit_cur;
     Vertex v;

@@ -459,3 +459,104 @@ def test_forward_mode_derivative_images(label, opts, kind, kw, what):
     a, b = float((v.astype(np.float64) * dimg).sum()), float((g.astype(np.float64) * u.reshape(-1)).sum())
     assert abs(a - b) <= 2e-4 * max(abs(a), abs(b)), (label, a, b)
     ctx.close()
+
+
+# ---- rough-conductor parameter gradients (a10 in its ad = true flavour) -------------------------------------------------------
+RC_SLOTS = [("alpha_u", 1), ("alpha_v", 1), ("eta", 3), ("k", 3), ("specular_reflectance", 3)]
+
+
+def _rc_reference_gradient(odesc, opts, integ, dLdI, bsdf):
+    """one oracle JVP per scalar parameter of the (1x1-textured) rough conductor"""
+    from oracle import orc
+    ref = []
+    for name, nch in RC_SLOTS:
+        for ch in range(nch):
+            osc = orc.Scene(odesc, opts)
+            t = np.zeros((1, 1, nch), np.float32); t[0, 0, ch] = 1
+            osc.set_bsdf_tangent(bsdf, name, t)
+            osc.configure()
+            ref.append(float((dLdI.astype(np.float64) * integ.renderD(osc)[1]).sum()))
+    return np.array(ref)
+
+
+@pytest.mark.parametrize("scene,kind,kw", [("bunny_env", "direct", dict(bsdf_samples=1, light_samples=1)), ("bunny_env", "path", dict(max_depth=3)),
+                                           ("bunny_env", "direct", dict(bsdf_samples=2, light_samples=0)), ("bunny_env", "direct", dict(bsdf_samples=0, light_samples=2))])
+def test_roughconductor_parameter_gradients_vs_oracle(scene, kind, kw):
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    opts = dict(width=32, height=32, spp=4, sppe=0, sppse=0)
+    desc = scene_io.load_scene_description(scene_path(scene))
+    rc = [i for i, b in enumerate(desc["bsdfs"]) if b["type"] == 1]
+    assert rc, "fixture has no rough conductor"
+    b = rc[0]
+    ctx = capi.Context(0)
+    ctx.load_description(desc, opts)
+    for name, _ in RC_SLOTS:
+        ctx.grad_require(capi.PARAM_BSDF_TEXTURE, b, name)
+    ctx.configure()
+    integ = capi.make_integrator(kind, **kw)
+    img = ctx.render_d(integ).cpu().numpy()
+    rng = np.random.default_rng(7)
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64)
+    assert g.shape == (11,)
+    oi = orc.DirectIntegrator(kw["bsdf_samples"], kw["light_samples"]) if kind == "direct" else orc.PathIntegrator(kw["max_depth"])
+    ref = _rc_reference_gradient(orc.load_scene_description(scene_path(scene)), opts, oi, dLdI, b)
+    assert np.all(np.isfinite(g)) and np.abs(ref).max() > 0
+    # per parameter group (their magnitudes differ by orders of magnitude): rtol 1e-3 of the group's largest entry
+    o = 0
+    for name, nch in RC_SLOTS:
+        gg, rr = g[o:o + nch], ref[o:o + nch]
+        assert np.all(np.abs(gg - rr) <= 1e-3 * max(np.abs(rr).max(), 1e-6)), (name, gg, rr)
+        o += nch
+    # forward mode through the same kernels: <dLdI, J t> == <g, t>
+    t = rng.normal(size=11).astype(np.float32)
+    dimg = ctx.render_d_jvp(integ, torch.from_numpy(t).cuda()).cpu().numpy().astype(np.float64)
+    lhs, rhs = float((dimg * dLdI).sum()), float((g * t).sum())
+    assert abs(lhs - rhs) <= 1e-3 * max(abs(rhs), 1e-6), (lhs, rhs)
+
+
+def test_roughconductor_bitmap_roughness_gradient_matches_oracle():
+    # a uv-mapped rough-conductor quad with roughness / eta maps under an area light: bilinear taps of 1- and 3-channel bitmaps
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    rng = np.random.default_rng(11)
+    au = rng.uniform(0.15, 0.5, size=(6, 5, 1)).astype(np.float32)
+    av = rng.uniform(0.15, 0.5, size=(4, 4, 1)).astype(np.float32)
+    eta = rng.uniform(0.1, 1.5, size=(3, 5, 3)).astype(np.float32)
+    quad = dict(verts=np.array([[-1, 0, -1], [-1, 0, 1], [1, 0, 1], [1, 0, -1]], np.float32) * 2, faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                uvs=np.array([[0.05, 0.1], [0.1, 0.9], [0.95, 0.85], [0.9, 0.05]], np.float32), uv_faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                bsdf=0, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    light = dict(verts=np.array([[-1.5, 3, -1.5], [1.5, 3, -1.5], [1.5, 3, 1.5], [-1.5, 3, 1.5]], np.float32), faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                 bsdf=1, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    cam = orc.m_look_at(np.array([0, 4, 6], np.float32), np.array([0, 0, 0], np.float32), np.array([0, 1, 0], np.float32))
+    one3 = np.ones((1, 1, 3), np.float32)
+    d = dict(opts=dict(width=24, height=24, spp=4, sppe=0, sppse=0), sensors=[dict(fov=40.0, near=0.1, far=1e4, to_world=cam)],
+             bsdfs=[dict(type=1, id="m", alpha_u=au, alpha_v=av, eta=eta, k=one3 * np.array([3.9, 2.4, 2.1], np.float32), specular_reflectance=one3 * 0.9,
+                         reflectance=one3 * 0.5),
+                    dict(type=0, id="k", reflectance=np.zeros((1, 1, 3), np.float32))],
+             meshes=[quad, light], emitters=[dict(mesh=1, radiance=np.array([30, 25, 20], np.float32))], envmap=None)
+    ctx = capi.Context(0)
+    ctx.load_description(d)
+    for name in ("alpha_u", "alpha_v", "eta", "k"):
+        ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, name)
+    ctx.configure()
+    integ = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+    osc = orc.Scene(d); osc.configure()
+    img = ctx.render_d(integ).cpu().numpy()
+    ref_img, _ = orc.DirectIntegrator(1, 1).renderD(osc)
+    assert_image_parity(img, ref_img)
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64)
+    layout = {capi_slot["slot"]: capi_slot for capi_slot in ctx.grad_layout()}
+    assert g.size == au.size + av.size + eta.size + 3
+    for name, arr in (("alpha_u", au), ("alpha_v", av), ("eta", eta)):
+        seg = layout[capi.TEX[name]]
+        gs = g[seg["offset"]:seg["offset"] + seg["count"]].reshape(arr.shape)
+        for k in range(2):
+            tdir = rng.normal(size=arr.shape).astype(np.float32)
+            o2 = orc.Scene(d); o2.set_bsdf_tangent(0, name, tdir); o2.configure()
+            _, dimg = orc.DirectIntegrator(1, 1).renderD(o2)
+            want = float((dLdI.astype(np.float64) * dimg).sum())
+            got = float((gs * tdir).sum())
+            assert abs(got - want) <= 1e-3 * max(abs(want), 1e-3), (name, got, want)
