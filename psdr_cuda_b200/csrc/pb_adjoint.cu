@@ -123,7 +123,13 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
         rc::Tex rtex;
-        if (RC) { rc_tex = v.active && rc::wants_tex_grad(v.bsdf); if (rc_tex) rtex = rc::load_tex(v.bsdf, its.uv); }
+        bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
+        float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
+        if (RC) {
+            rc_tex = v.active && rc::wants_tex_grad(v.bsdf);
+            geom_rc = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_ROUGHCONDUCTOR;
+            if (rc_tex || geom_rc) rtex = rc::load_tex(v.bsdf, its.uv);
+        }
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
             const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
@@ -157,6 +163,15 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                     rc::bsdf_branch_tex_grad(rtex, its.wi, wo_l, s3, G, p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le(P.S, its1, true) : f3(0.f),
                                              cont ? gw : f3(0.f), tg);
                     rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                }
+                if (RC && geom_rc) {
+                    const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf(P.S, its.p, its1, true) : 0.f;
+                    rc::GeomGrad gg;
+                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, its1.p, its1.n, B.depth == 0, v.rd, false, square_to_uniform_disk_concentric(s3.x, s3.y),
+                                             p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le(P.S, its1, true) : f3(0.f), cont ? gw : f3(0.f), gg)) {
+                        g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
+                        point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, gg.q, gg.nq, gg.c0);
+                    }
                 }
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     // value = K * (cos_o G J) with K = rho/pi * (Le weight gL + gw) / pdf0   (diffuse: pdf0 and the MIS weight are detached)
@@ -204,6 +219,15 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                     rc::light_branch_tex_grad(rtex, its.wi, wo_l, G, ps.pdf, B.nb > 0, inv_nl, gL * Le, tg);
                     rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
                 }
+                if (RC && geom_rc) {
+                    rc::GeomGrad gg;
+                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, ps.p, its1.n, B.depth == 0, v.rd, true, make_float2(0.f, 0.f), ps.pdf, B.nb > 0, inv_nl,
+                                             gL * Le, f3(0.f), gg)) {
+                        g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
+                        if (ps.tri >= 0) point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, gg.q, f3(0.f), gg.c0);   // area-light sample + its Jacobian; envmap samples are detached
+                        point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, f3(0.f), gg.nq, 0.f);
+                    }
+                }
                 if (geom && wo_l.z > 0.f && its.wi.z > 0.f) {
                     const float3 rho = tex_eval3(v.bsdf->tex[TEX_REFLECTANCE], its.uv);
                     const float gc = pdot(gL * Le, rho) * kInvPi * weight / ps.pdf;
@@ -220,7 +244,31 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
             const float3 Sk = L + w_cont * S_next;
             suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
         }
-        if (geom) {   // chain the vertex adjoints into its triangle (scene.cpp:326-376)
+        if (RC && geom_rc && B.depth > 0 && E.hit_prev && (g_a.x != 0.f || g_a.y != 0.f || g_a.z != 0.f) && finite3(g_a)) {
+            // the previous vertex moves wi: chain into its triangle (path-space point, or the camera hit in solid-angle form)
+            const HitRec hp = load_hit(E.hit_prev + i);
+            if (hp.tri >= 0) {
+                if (B.depth == 1) {
+                    const TriFull t = load_tri_full(P.S, hp.tri);
+                    if (t.flags & 8) {
+                        int pix0;
+                        Rng rng0((uint64_t)global_lane(P, i, pix0), P.jump0);
+                        const float2 jit = rng0.next_2d();
+                        float sx, sy;
+                        lane_pixel_sample(P, pix0, jit, sx, sy);
+                        float3 o, d;
+                        sample_primary_ray(P.cam, sx, sy, o, d);
+                        const RayTriGrad r = ray_intersect_triangle_vjp(t.p0, t.e1, t.e2, o, d, 0.f, 0.f, pdot(g_a, d));
+                        TriGrad tg;
+                        tg.p0 = r.p0; tg.e1 = r.e1; tg.e2 = r.e2;
+                        tri_grad_scatter(P.S, hp.tri, tg);
+                    }
+                } else {
+                    point_on_triangle_scatter(P.S, hp.tri, hp.u, hp.v, g_a, f3(0.f), 0.f);
+                }
+            }
+        }
+        if (geom || (RC && geom_rc)) {   // chain the vertex adjoints into its triangle (scene.cpp:326-376)
             const TriFull t = load_tri_full(P.S, its.tri);
             if (t.flags & 8) {
                 TriGrad tg;
@@ -262,8 +310,9 @@ void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &
     if (B.rc_grad) { k_adjoint<1, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
     switch (g_shade_tune) {
         case 1: k_adjoint<2, true, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        case 2: case 3: k_adjoint<3, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        default: k_adjoint<2, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 4: k_adjoint<2, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 5: k_adjoint<4, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        default: k_adjoint<3, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
     }
 }
 

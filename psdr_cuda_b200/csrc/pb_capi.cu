@@ -633,6 +633,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         Bp.jump = make_jump(base + 1 + (uint64_t)side * per_li + (uint64_t)k * per_event);
                         EventBuffers E;
                         E.hit_cur = (k == 0) ? hit0 : S.hits[(k - 1) & 1].as<HitRec>();
+                        E.hit_prev = nullptr;
                         E.prev_pos = (k == 0) ? nullptr : S.pos[(k - 1) & 1].as<float4>();
                         E.pos = S.pos[k & 1].as<float4>();
                         E.rays = S.rays.as<RayRec>();
@@ -832,6 +833,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         if (mode == MODE_VJP)
             for (const GradSegment &g : c->grad_segments)
                 if (g.kind == PB_PARAM_BSDF_TEXTURE && c->bsdfs[g.id].type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
+        if (mode == MODE_VJP && any_geom_jvp(c))   // geometry adjoints flow through every rough-conductor vertex on a path
+            for (const HostBsdf &hb : c->bsdfs) if (hb.type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
         Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
     }
     size_t nev = 0, nev_edge = 0;
@@ -843,6 +846,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             const int sl = keep ? k : (k & 1), sp = keep ? k - 1 : ((k - 1) & 1);
             EventBuffers E;
             E.hit_cur = (k == 0) ? hit0 : S.hits[sp].as<HitRec>() + off * R;
+            E.hit_prev = (k == 0 || !keep) ? nullptr : (k == 1 ? hit0 : S.hits[k - 2].as<HitRec>() + off * R);
             E.prev_pos = (k == 0) ? nullptr : S.pos[sp].as<float4>() + off;
             E.pos = S.pos[sl].as<float4>() + off;
             E.rays = S.rays.as<RayRec>();

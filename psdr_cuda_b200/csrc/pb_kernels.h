@@ -34,6 +34,7 @@ struct RenderParams {
 // device buffers of one scattering event for one batch of n lanes (R = nb + nl rays per lane)
 struct EventBuffers {
     const HitRec *hit_cur;   // [n]   hit that created this event's vertex
+    const HitRec *hit_prev;  // [n]   adjoint only: hit that created the previous vertex (null at depth 0)
     const float4 *prev_pos;  // [n]   position of the previous vertex (origin of the ray that found hit_cur); unused at depth 0
     float4 *pos;             // [n]   this vertex' position, written by k_shade
     RayRec *rays;            // [R*n] rays of this event (scratch, ray j of lane i at j*n + i)

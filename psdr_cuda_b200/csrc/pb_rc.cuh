@@ -158,6 +158,87 @@ PB_D void light_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float G_ge
     finish_tex_grad(t, dot(wi, Hf), R * (G_geo / ps_pdf), wA, gA, f3(0.f), g);
 }
 
+// ---- geometry: local gradient of one connection w.r.t. the points and normals it is built from ----------------------------------
+// inputs x[15] = (p, sh_n, a, q, n_q): the shaded point and its shading normal, the origin `a` of the ray that found it
+// (scene.cpp:343-349: wi = to_local(-(p - a)/|p - a|); at the camera vertex wi = to_local(-ray.d), scene.cpp:368), the far end
+// q of the connection and the geometric normal there. value = f(wi, wo) * G / pdf * (Le weight + S_next) as in direct.cpp:83-113 /
+// 133-158; the Jacobian J = A/detach(A) of q multiplies it (value 1), so its adjoint is the value itself.
+template <class T> struct FrameT {   // frame.h:9-52
+    V3<T> s, t, n;
+    PB_D explicit FrameT(const V3<T> &v) : n(v) {
+        const float sg = copysignf(1.f, val(v.z));
+        const bool neg = signbit(val(v.z));
+        const T a = -1.f / (sg + v.z);
+        const T b = v.x * v.y * a;
+        const T sx = dsqr(v.x) * a;
+        s = V3<T>((neg ? -sx : sx) + 1.f, neg ? -b : b, neg ? v.x : -v.x);
+        t = V3<T>(b, sg + dsqr(v.y) * a, -v.y);
+    }
+    PB_D V3<T> to_local(const V3<T> &v) const { return V3<T>(vdot(v, s), vdot(v, t), vdot(v, n)); }
+};
+
+template <int N>
+PB_D Dual<N> branch_value(const Tex &t, const float *x, int seed0, bool primary, float3 rd, bool light, float2 disk, float p_other, bool use_mis,
+                          float inv_cnt, float3 gA, float3 gB) {
+    typedef Dual<N> D;
+    D in[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        in[k] = D(x[k]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) if (k == seed0 + j) in[k].d[j] = 1.f;
+    }
+    const V3<D> p(in[0], in[1], in[2]), shn(in[3], in[4], in[5]), a(in[6], in[7], in[8]), q(in[9], in[10], in[11]), nq(in[12], in[13], in[14]);
+    const FrameT<D> fr(shn);
+    const V3<D> wi = primary ? fr.to_local(V3<D>(-rd)) : fr.to_local(-vnormalize(p - a));
+    const V3<D> dv = q - p;
+    const D r2 = vdot(dv, dv);
+    const V3<D> wo = dv / dsqrt(r2);
+    const V3<D> wo_l = fr.to_local(wo);
+    const V3<D> H = vnormalize(wo_l + wi);
+    const D au(t.au), av(t.av);
+    const D R = eval_scalar<D>(au, av, wi, wo_l, H);
+    if (R.v == 0.f) return D(0.f);
+    const D G = dabs(vdot(nq, wo)) / r2;
+    D wA(inv_cnt), base;
+    if (!light) {   // pdf0 = bs.pdf * detach(G)
+        const D pdf0 = sampled_pdf<D>(au, av, wi, disk) * G.v;
+        if (use_mis) { const D w1 = dsqr(pdf0); wA = w1 / (w1 + sqr(p_other)) * inv_cnt; }
+        base = R * G / pdf0;
+    } else {        // pdf1 = bsdf.pdf * detach(G); p_other = ps.pdf
+        if (use_mis) { const D pdf1 = pdf<D>(au, av, wi, wo_l) * G.v; const float w1 = sqr(p_other); wA = w1 / (w1 + dsqr(pdf1)) * inv_cnt; }
+        base = R * G / p_other;
+    }
+    const D cos_h = vdot(wi, H);
+    const float ga[3] = {gA.x, gA.y, gA.z}, gb[3] = {gB.x, gB.y, gB.z}, sp[3] = {t.spec.x, t.spec.y, t.spec.z};
+    D sum(0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sum += (wA * ga[c] + gb[c]) * fresnel1<D>(D(getc(t.eta, c)), D(getc(t.k, c)), cos_h) * sp[c];
+    return sum * base;
+}
+
+struct GeomGrad { float3 p, shn, a, q, nq; float c0; };
+// false: degenerate sample (non-finite derivative), nothing to add
+PB_D bool branch_geom_grad(const Tex &t, float3 p, float3 shn, float3 a, float3 q, float3 nq, bool primary, float3 rd, bool light, float2 disk,
+                           float p_other, bool use_mis, float inv_cnt, float3 gA, float3 gB, GeomGrad &g) {
+    const float x[15] = {p.x, p.y, p.z, shn.x, shn.y, shn.z, a.x, a.y, a.z, q.x, q.y, q.z, nq.x, nq.y, nq.z};
+    float d[15];
+    bool ok = true;
+    float c0 = 0.f;
+#pragma unroll 1
+    for (int chunk = 0; chunk < 3; ++chunk) {
+        const Dual<5> c = branch_value<5>(t, x, 5 * chunk, primary, rd, light, disk, p_other, use_mis, inv_cnt, gA, gB);
+        ok = ok && dfinite(c);
+        c0 = c.v;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) d[5 * chunk + j] = c.d[j];
+    }
+    if (!ok) return false;
+    g.p = f3(d[0], d[1], d[2]); g.shn = f3(d[3], d[4], d[5]); g.a = primary ? f3(0.f) : f3(d[6], d[7], d[8]);
+    g.q = f3(d[9], d[10], d[11]); g.nq = f3(d[12], d[13], d[14]); g.c0 = c0;
+    return true;
+}
+
 // ---- scatter of the local gradient into the textures (Bitmap::eval's backward, bitmap.cpp:43-89) -------------------------------
 // reverse mode: atomics into the gradient segment; forward mode (S.tri_tangent set): dot with the texture's tangent.
 template <int C> PB_D void tex_scatter(const SceneView &S, const TexRef &t, float2 uv, const float *gv) {

@@ -560,3 +560,50 @@ def test_roughconductor_bitmap_roughness_gradient_matches_oracle():
             want = float((dLdI.astype(np.float64) * dimg).sum())
             got = float((gs * tdir).sum())
             assert abs(got - want) <= 1e-3 * max(abs(want), 1e-3), (name, got, want)
+
+
+def test_roughconductor_vertex_gradients_interior():
+    """geometry adjoints through rough-conductor vertices (wi, wo, attached sampling pdf, MIS): configs[4] family"""
+    o = dict(width=48, height=48, spp=8, sppe=0, sppse=0)
+    # cbox with a smooth-normal rough-conductor bunny and floor under an area light (fixture of this repo)
+    _vertex_grad_case("cbox_bunny_rc", o, "direct", dict(bsdf_samples=1, light_samples=1), 1)
+    _vertex_grad_case("cbox_bunny_rc", o, "path", dict(max_depth=3), 1)       # bunny: shaded vertex, previous vertex and far end of connections
+    _vertex_grad_case("cbox_bunny_rc", o, "path", dict(max_depth=3), 2)       # the face-normal rough-conductor floor
+    _vertex_grad_case("cbox_bunny_rc", o, "path", dict(max_depth=2), 0)       # the emitter quad (sampled points + their Jacobian)
+    # reference fixture: face-normal rough-conductor bunny (alpha 0.05) under the environment map
+    oe = dict(width=40, height=40, spp=8, sppe=0, sppse=0)
+    _vertex_grad_case("bunny_env", oe, "direct", dict(bsdf_samples=1, light_samples=1), 0)
+    _vertex_grad_case("bunny_env", oe, "path", dict(max_depth=2), 0)
+
+
+def test_roughconductor_texture_and_vertex_gradients_cfg5_small():
+    """BASELINE.json configs[4] at test size: rough conductor + envmap, texture and vertex gradients in one VJP, all terms"""
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    opts = dict(width=32, height=32, spp=4, sppe=4, sppse=4)
+    rng = np.random.default_rng(5)
+    pdesc = scene_io.load_scene_description(scene_path("bunny_env"))
+    odesc = orc.load_scene_description(scene_path("bunny_env"))
+    ctx = capi.Context(0)
+    ctx.load_description(pdesc, opts)
+    ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "alpha_u")
+    ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "eta")
+    ctx.grad_require(capi.PARAM_MESH_VERTICES, 0)
+    ctx.configure()
+    integ = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+    img = ctx.render_d(integ).cpu().numpy()
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64)
+    nv = len(odesc["meshes"][0]["verts"])
+    assert g.size == 1 + 3 + 3 * nv and np.isfinite(g).all()
+    u = rng.normal(size=(nv, 3)).astype(np.float32)
+    ta, te = np.float32(0.7), rng.normal(size=3).astype(np.float32)
+    osc = orc.Scene(odesc, opts)
+    osc.set_bsdf_tangent(0, "alpha_u", np.full((1, 1, 1), ta, np.float32))
+    osc.set_bsdf_tangent(0, "eta", te.reshape(1, 1, 3))
+    osc.set_mesh_vertex_tangent(0, u)
+    osc.configure()
+    _, dimg = orc.DirectIntegrator(1, 1).renderD(osc)
+    want = float((dLdI.astype(np.float64) * dimg).sum())
+    got = float(g[0] * ta + (g[1:4] * te).sum() + (g[4:].reshape(nv, 3) * u).sum())
+    assert abs(got - want) <= 3e-3 * abs(want), (got, want)
