@@ -349,6 +349,11 @@ class Scene:
     def set_bsdf_tangent(self, bsdf, name, tang):
         _chk(lib().orc_set_bsdf_tangent(self.h, bsdf, TEX[name], _p(_f(tang)) if tang is not None else None))
 
+    def set_envmap_tangent(self, radiance_t=None, scale_t=0.0):
+        L = lib()
+        L.orc_set_envmap_tangent.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        _chk(L.orc_set_envmap_tangent(self.h, _p(_f(radiance_t)) if radiance_t is not None else None, float(scale_t)))
+
     def set_mesh_vertices(self, mesh, verts):
         _chk(lib().orc_set_mesh_vertices(self.h, mesh, _p(_f(verts))))
 

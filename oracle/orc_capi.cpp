@@ -135,6 +135,15 @@ int orc_add_envmap(void *h, int w, int hh, const float *rgb, float scale, const 
     s.emitter_env = (int)s.emitters.size() - 1;
     return s.emitter_env;
 }
+/* forward-mode tangents of the environment map's radiance texels (w*h*3, may be null) and of its scale */
+int orc_set_envmap_tangent(void *h, const float *radiance_t, float scale_t) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        Emitter &e = s.emitters.at(s.emitter_env);
+        if (radiance_t) e.env_radiance.tang.assign(radiance_t, radiance_t + e.env_radiance.data.size()); else e.env_radiance.tang.clear();
+        e.env_scale_t = scale_t;
+    });
+}
 int orc_set_envmap_transform(void *h, const float *left) {
     return guard([&] { Scene &s = ((Handle *)h)->scene; s.emitters.at(s.emitter_env).env_left = mat16(left); });
 }

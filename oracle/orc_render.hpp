@@ -64,8 +64,8 @@ struct Emitter {
     int mesh = -1;          // area.h:27
     float sampling_weight = 0.f;
     // envmap (envmap.h)
-    Bitmap env_radiance;
-    float env_scale = 1.f;
+    Bitmap env_radiance;    // .tang: forward-mode tangent of the radiance texels (EnvironmentMap.radiance.data is an AD leaf, psdr.cpp:236)
+    float env_scale = 1.f, env_scale_t = 0.f;   // scale and its tangent (psdr.cpp:237)
     M4f env_to_world_raw, env_left;
     M4f env_to_world, env_from_world;
     V3f lower, upper;
@@ -401,6 +401,15 @@ inline V3f env_eval_direction(const Emitter &e, const V3f &wi_world) {   // envm
     V3f r = e.env_radiance.eval3<float>(uv, false);
     return r * e.env_scale;
 }
+// envmap.cpp:42-58 in its ad = true flavour: attached to the direction (through atan2 / acos and the bilinear weights), to the
+// radiance texels and to the scale. m_from_world is a constant here (the oracle does not parameterise the envmap transform).
+inline V3<Dual> env_eval_direction_d(const Emitter &e, const V3<Dual> &wi_world) {
+    V3<Dual> wi = transform_dir(M4<Dual>(e.env_from_world), wi_world);
+    V2<Dual> uv(atan2_(wi.x, -wi.z) * kInvTwoPi, safe_acos(wi.y) * kInvPi);
+    uv.x = uv.x - floor_(uv.x); uv.y = uv.y - floor_(uv.y);
+    V3<Dual> r = e.env_radiance.eval3<Dual>(uv, false);
+    return r * Dual(e.env_scale, e.env_scale_t);
+}
 inline void configure_envmap(Emitter &e) {   // envmap.cpp:10-26
     int w = e.env_radiance.w, h = e.env_radiance.h;
     if (!(w > 1 && h > 1)) throw std::runtime_error("envmap resolution");
@@ -543,8 +552,12 @@ template <class R> inline V3<R> Scene::Le(const Intersection<R> &its, bool activ
     const Emitter &em = emitters[e];
     if (em.type == EMITTER_AREA) return val(its.wi.z) > 0.f ? lift<R>(em.radiance) : V3<R>();   // area.cpp:20-29
     // envmap.cpp:29-39: radiance along -wi (world)
-    V3f wi_world = detach(its.sh.to_world(its.wi));
-    return lift<R>(env_eval_direction(em, -wi_world));
+    if constexpr (std::is_same_v<R, Dual>) {
+        return env_eval_direction_d(em, -its.sh.to_world(its.wi));   // envmap.cpp:35-38: attached to the direction, the texels and the scale
+    } else {
+        V3f wi_world = its.sh.to_world(its.wi);
+        return env_eval_direction(em, -wi_world);
+    }
 }
 // mesh.cpp:306-330
 template <class R> inline PositionSample<R> Scene::mesh_sample_position(const Mesh &m, V2<R> sample2) const {

@@ -148,7 +148,10 @@ class Scene(_h.Scene):
         Edit it in place / through an optimiser; `configure()` pushes the current value into the scene."""
         torch = _torch()
         obj = self._raw_param_map()[key]
-        value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
+        if field in ("to_world_left", "to_world_right"):   # Mesh.set_transform / append_transform leaves (src/psdr.cpp:246-247)
+            value = getattr(obj, field)
+        else:
+            value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
         t = torch.tensor(np.asarray(value), dtype=torch.float32, device="cuda:%d" % self._device, requires_grad=requires_grad)
         self._params[(key, field)] = t
         return t
@@ -159,7 +162,10 @@ class Scene(_h.Scene):
             val = t.detach().cpu().numpy()
             if field == "vertex_positions":
                 obj.vertex_positions = val
-                obj.requires_grad = bool(t.requires_grad)
+                obj.requires_grad = bool(t.requires_grad) or obj.requires_grad
+            elif field in ("to_world_left", "to_world_right"):
+                obj.set_transform(val.astype(np.float32), field == "to_world_left")
+                obj.requires_grad = bool(t.requires_grad) or obj.requires_grad   # the transform gradient is a contraction of the vertex gradient
             else:
                 bm = getattr(obj, field)
                 bm.data = val
@@ -187,6 +193,36 @@ class Scene(_h.Scene):
         for key, field, off, cnt in self.grad_layout():
             out.append((canon.get((key, field)), off, cnt))
         return out
+
+    def _transform_leaves(self):
+        """registered mesh-transform leaves -> (tensor, mesh object, left?, offset, count of the mesh's vertex segment)"""
+        pm = self._raw_param_map()
+        seg = {}
+        for key, field, off, cnt in self.grad_layout():
+            if field == "vertex_positions":
+                seg[pm[key].index] = (off, cnt)
+        out = []
+        for (key, field), t in self._params.items():
+            if field in ("to_world_left", "to_world_right") and t.requires_grad and pm[key].index in seg:
+                out.append((t, pm[key], field == "to_world_left") + seg[pm[key].index])
+        return out
+
+    @staticmethod
+    def _transform_gradient(torch, mesh, left, g_obj):
+        """dL/d(to_world_left|right) from the object-space vertex gradient g_obj (nv, 3): world = M x with M = L W R (mesh.cpp:223),
+        g_obj = M3^T g_world, so g_M[:3, :] = sum_v g_world_v (x_v, 1)^T, then g_L = g_M (W R)^T, g_R = (L W)^T g_M. Affine
+        transforms only (the projective row gets no gradient), which is what examples/utils/differential.py builds."""
+        dev, f64 = g_obj.device, torch.float64
+        L = torch.tensor(mesh.to_world_left, dtype=f64, device=dev); W = torch.tensor(mesh.to_world_raw, dtype=f64, device=dev)
+        R = torch.tensor(mesh.to_world_right, dtype=f64, device=dev)
+        M = L @ W @ R
+        x = torch.tensor(mesh.vertex_positions, dtype=f64, device=dev)
+        x1 = torch.cat([x, torch.ones((x.shape[0], 1), dtype=f64, device=dev)], dim=1)
+        g_world = g_obj.to(f64) @ torch.linalg.inv(M[:3, :3])
+        g_M = torch.zeros((4, 4), dtype=f64, device=dev)
+        g_M[:3, :] = g_world.T @ x1
+        g = g_M @ (W @ R).T if left else (L @ W).T @ g_M
+        return g.to(torch.float32)
 
 
 def _image_tensor(scene):
@@ -222,7 +258,8 @@ class _IntegratorMixin:
             ek._pending.append(out)
             return out
         segs = scene._leaves_in_layout_order()
-        leaves = [t for t, _, _ in segs if t is not None and t.requires_grad]
+        xforms = scene._transform_leaves()
+        leaves = [t for t, _, _ in segs if t is not None and t.requires_grad] + [x[0] for x in xforms]
         integ = self
 
         class _RenderD(torch.autograd.Function):
@@ -246,6 +283,8 @@ class _IntegratorMixin:
                 for t, off, cnt in segs:
                     if t is not None and t.requires_grad:
                         outs.append(grad[off:off + cnt].view_as(t))
+                for t, mesh, left, off, cnt in xforms:
+                    outs.append(Scene._transform_gradient(torch, mesh, left, grad[off:off + cnt].view(-1, 3)))
                 return tuple(outs)
 
         return _RenderD.apply(*leaves) if leaves else _RenderD.apply()

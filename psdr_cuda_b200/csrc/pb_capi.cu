@@ -167,8 +167,10 @@ static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hi
     if (g_trace_variant == 7) {
         c->d_sort_hist.reserve(40000 * sizeof(unsigned));
         c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
+        c->d_sort_keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
         launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
-                            f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>());
+                            f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
+                            c->d_sort_keys.as<unsigned short>());
         c->launches += 3;
     } else {
         launch_trace(c->stream, c->view, n, rays, hits, nullptr);

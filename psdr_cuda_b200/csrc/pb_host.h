@@ -136,7 +136,7 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms

@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
         // The connection is valid iff the closest hit lies beyond dist - ShadowEpsilon and is an emitter (direct.cpp:130-131):
         // nothing past the sampled point can change that, and any closer hit decides it, so the ray is bounded and
         // flagged as an occlusion query.
-        store_ray(rays_out + (size_t)(B.nb + j) * P.n + i, v.its.p, wo, a1 ? fmaf(dist, 1e-5f, dist) + 2e-3f : -1.f, dist - kShadowEpsilon);
+        // Every BSDF here is zero unless both cosines are positive (diffuse.cpp:28, roughconductor.cpp:43), so the connection
+        // contributes exactly 0 (value and derivative) whatever the ray hits: such lanes are not traced.
+        const bool lit = v.its.wi.z > 0.f && dot(wo, v.its.sh.n) > 0.f;
+        store_ray(rays_out + (size_t)(B.nb + j) * P.n + i, v.its.p, wo, (a1 && lit) ? fmaf(dist, 1e-5f, dist) + 2e-3f : -1.f, dist - kShadowEpsilon);
     }
 }
 

@@ -51,14 +51,19 @@ PB_D int sort_key(float4 a, float4 b, float3 lo, float3 inv_ext) {
     return min(kSortBins - 1, (direction_bin_n(f3(b), 22) << 3) | cell);
 }
 
-__global__ void __launch_bounds__(1024) k_sort_hist(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ hist) {
+// The histogram pass is the only one that reads the rays: it leaves each ray's 13-bit key in `keys` (2 B instead of 32 B for
+// the scatter pass to read back).
+__global__ void __launch_bounds__(1024) k_sort_hist(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ hist,
+                                                    unsigned short *__restrict__ keys) {
     extern __shared__ unsigned s_hist[];
     for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-        atomicAdd(&s_hist[sort_key(ldg4(rp), ldg4(rp + 1), lo, inv_ext)], 1u);
+        const int key = sort_key(ldg4(rp), ldg4(rp + 1), lo, inv_ext);
+        keys[i] = (unsigned short)key;
+        atomicAdd(&s_hist[key], 1u);
     }
     __syncthreads();
     for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) if (s_hist[t]) atomicAdd(hist + t, s_hist[t]);
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist)
 // Scatter with block-level aggregation: lanes rank themselves inside the block with shared-memory atomics, then one
 // global atomic per (block, non-empty bin) reserves the block's range. Rays arrive in pixel order, so the lanes in flight
 // at any moment share an origin cell and hammer ~64 counters; per-lane global atomics serialised on them.
-__global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ cursor,
+__global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const unsigned short *__restrict__ keys, unsigned *__restrict__ cursor,
                                                        unsigned *__restrict__ perm, HitRec *__restrict__ hits) {
     extern __shared__ unsigned s_cnt[];
     for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) s_cnt[t] = 0;
@@ -99,8 +104,7 @@ __global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const RayRec
     int key = kSortBins;
     unsigned rank = 0;
     if (i < n) {
-        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-        key = sort_key(ldg4(rp), ldg4(rp + 1), lo, inv_ext);
+        key = __ldcs(keys + i);
         if (key == kSortBins) reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);   // inactive lane: a miss
         else rank = atomicAdd(&s_cnt[key], 1u);
     }
@@ -145,8 +149,9 @@ __global__ void __launch_bounds__(1024, 1) k_trace_perm_smem(const BvhNode *__re
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
-// hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned
-void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm) {
+// hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned; keys: n unsigned short
+void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
+                         unsigned short *keys) {
     if (n <= 0) return;
     static int mode_set = -1;
     if (mode_set != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); mode_set = g_sort_mode; }
@@ -159,9 +164,9 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
         cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, cnt_bytes);
         sort_attr = true;
     }
-    k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist);
+    k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist, keys);
     k_sort_scan<<<1, 1024, 0, st>>>(hist);
-    k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist, perm, hits);
+    k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
     if (g_trace_smem) {
         static bool attr_set = false;

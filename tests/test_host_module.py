@@ -139,3 +139,36 @@ def test_psdr_cuda_module_renders_and_differentiates(psdr_cuda):
         albedo -= 0.1 * albedo.grad / albedo.grad.abs().max()
     sc.configure()
     assert not torch.equal(integ.renderC(sc, 0), img_c)
+
+
+@pytest.mark.gpu
+def test_mesh_transform_leaf_gradient_matches_oracle(psdr_cuda):
+    """Mesh.set_transform as a differentiable leaf (src/psdr.cpp:246-247, examples/utils/differential.py:7-11): reverse mode
+    through the module against the oracle's forward mode for a translation and a rotation-like tangent of to_world_left."""
+    torch = pytest.importorskip("torch")
+    from oracle import orc
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path("cbox_bunny"), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse = 40, 40, 4, 4, 4
+    T = sc.parameter("Mesh[1]", "to_world_left")
+    sc.configure()
+    integ = psdr_cuda.DirectIntegrator(1, 1)
+    img = integ.renderD(sc, 0)
+    rng = np.random.default_rng(9)
+    w = torch.from_numpy(rng.uniform(-1, 1, size=(40 * 40, 3)).astype(np.float32)).to(img.device)
+    (img * w).sum().backward()
+    assert T.grad is not None and T.grad.shape == (4, 4)
+    g = T.grad.double().cpu().numpy()
+    odesc = orc.load_scene_description(scene_path("cbox_bunny"))
+    opts = dict(width=40, height=40, spp=4, sppe=4, sppse=4)
+    tangents = [np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)]
+    tangents[0][0, 3] = 1.0                                            # d/dP translate(P, 0, 0)
+    tangents[1][0, 1], tangents[1][1, 0], tangents[1][2, 3] = -1.0, 1.0, 0.5   # d/dP rotate(z, P) at P = 0, plus a z shift
+    for dM in tangents:
+        osc = orc.Scene(odesc, opts)
+        osc.set_mesh_transform_tangent(1, dM, True)
+        osc.configure()
+        _, dimg = orc.DirectIntegrator(1, 1).renderD(osc)
+        want = float((w.double().cpu().numpy() * dimg).sum())
+        got = float((g * dM).sum())
+        assert abs(got - want) <= 3e-3 * abs(want), (got, want)

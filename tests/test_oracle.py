@@ -151,3 +151,17 @@ def test_unconfigured_scene_raises(cbox_desc):
     sc = orc.Scene(cbox_desc, dict(width=8, height=8, spp=1, sppe=0, sppse=0))
     with pytest.raises(RuntimeError, match="must be configured"):
         orc.DirectIntegrator(1, 1).renderC(sc)
+
+
+def test_envmap_scale_tangent_is_the_exact_derivative():
+    """The environment map's sampling distribution is normalised, so the image is linear in EnvironmentMap.scale:
+    the forward-mode tangent must equal (I(1.1 s) - I(s)) / (0.1 s) at the same seeds."""
+    opts = dict(width=24, height=24, spp=4, sppe=0, sppse=0)
+    desc = orc.load_scene_description(scene_path("bunny_env"))
+    s0 = orc.Scene(desc, opts)
+    s0.set_envmap_tangent(None, 1.0)
+    s0.configure()
+    img, dimg = orc.DirectIntegrator(1, 1).renderD(s0)
+    assert np.abs(dimg).max() > 0
+    scale = desc["envmap"]["scale"]
+    assert np.allclose(dimg * scale, img, rtol=2e-4, atol=1e-6)
