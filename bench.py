@@ -166,7 +166,7 @@ def run_ours(args):
     h_dLdI = torch.ones((npix, 3), dtype=torch.float32).pin_memory()
     h_grad = torch.empty(ctx.grad_size(), dtype=torch.float32).pin_memory()
 
-    stats = {"trace_ms": 0.0, "rays": 0, "trace_launches": 0, "primary_ms": 0.0, "tc": 0.0, "td": 0.0}
+    stats = {"trace_ms": 0.0, "rays": 0, "active_rays": 0, "trace_launches": 0, "primary_ms": 0.0, "tc": 0.0, "td": 0.0}
 
     def step(e2e, collect=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -178,7 +178,7 @@ def run_ours(args):
             h_img_c.copy_(img_c, non_blocking=True)
         if collect:
             s = ctx.stats()
-            for k in ("trace_ms", "rays", "trace_launches", "primary_ms"):
+            for k in ("trace_ms", "rays", "active_rays", "trace_launches", "primary_ms"):
                 stats[k] += s[k]
         ev[1].record()
         ctx.render_d(integ, out=img_d)
@@ -233,7 +233,8 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     # roofline of the dominant kernel (k_trace) from the live CUDA-event durations of the renderC calls of the timed region
     avg_launch_s = stats["trace_ms"] * 1e-3 / max(1, stats["trace_launches"])
-    rays_per_launch = stats["rays"] / max(1, stats["trace_launches"])
+    rays_per_launch = stats["active_rays"] / max(1, stats["trace_launches"])   # rays actually traced (unlit / dead lanes are compacted away)
+    lanes_per_launch = stats["rays"] / max(1, stats["trace_launches"])
     achieved = BYTES_PER_RAY * rays_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k_trace_traffic.json")
@@ -256,9 +257,9 @@ def run_ours(args):
                            "ms_renderC": tc / args.steps, "ms_renderD_vjp": td / args.steps,
                            "Mpath_samples_per_s_renderC": W * H * SPP * args.steps / (tc * 1e-3) / 1e6,
                            "Mpath_samples_per_s_renderD_vjp": W * H * SPP * args.steps / (td * 1e-3) / 1e6},
-                "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "roofline": {"bound": "hbm", "kernel": "k_trace_perm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
-                             "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                             "rays_per_launch": rays_per_launch, "ray_slots_per_launch": lanes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                              "Grays_per_s": rays_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0,
                              "note": "traversal is L2-latency/divergence bound (no RT cores on B200); scene tables are L2 resident"},
                 "cpu_baseline": cpu,

@@ -33,7 +33,7 @@ enum { PB_FIELD_SILHOUETTE = 0, PB_FIELD_POSITION, PB_FIELD_DEPTH, PB_FIELD_GEON
 /* mesh flags: Mesh::m_use_face_normals / m_enable_edges (include/psdr/shape/mesh.h) */
 enum { PB_MESH_FACE_NORMALS = 1, PB_MESH_ENABLE_EDGES = 2 };
 /* differentiable leaves: what a gradient segment refers to */
-enum { PB_PARAM_BSDF_TEXTURE = 0, PB_PARAM_MESH_VERTICES = 1 };
+enum { PB_PARAM_BSDF_TEXTURE = 0, PB_PARAM_MESH_VERTICES = 1, PB_PARAM_ENVMAP_RADIANCE = 2, PB_PARAM_ENVMAP_SCALE = 3 };   /* EnvironmentMap.radiance.data / .scale, src/psdr.cpp:236-237 (id, slot ignored) */
 
 typedef struct pb_integrator {
     int kind;           /* PB_INTEG_* */
@@ -140,6 +140,7 @@ int pb_render_d_jvp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const f
 int64_t pb_stats_launches(pb_ctx *ctx);
 float pb_stats_last_trace_ms(pb_ctx *ctx);
 int64_t pb_stats_last_rays(pb_ctx *ctx);
+int64_t pb_stats_last_active_rays(pb_ctx *ctx);                                         /* rays the traversal kernels traced (inactive lanes are compacted away) */
 int pb_stats_last_trace_launches(pb_ctx *ctx);
 float pb_stats_last_primary_ms(pb_ctx *ctx);
 

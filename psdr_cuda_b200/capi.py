@@ -17,7 +17,7 @@ TEX = {"reflectance": 0, "alpha_u": 1, "alpha_v": 2, "eta": 3, "k": 4, "specular
 INTEG_DIRECT, INTEG_FIELD, INTEG_PATH = 0, 1, 2
 FIELDS = {"silhouette": 0, "position": 1, "depth": 2, "geoNormal": 3, "shNormal": 4, "uv": 5}
 MESH_FACE_NORMALS, MESH_ENABLE_EDGES = 1, 2
-PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES = 0, 1
+PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES, PARAM_ENVMAP_RADIANCE, PARAM_ENVMAP_SCALE = 0, 1, 2, 3
 
 SYMBOLS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream", "pb_ctx_set_retain_limit",
@@ -25,7 +25,7 @@ SYMBOLS = [
     "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_add_envmap", "pb_scene_set_envmap_transform", "pb_scene_num_meshes", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
-    "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
+    "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
     "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad",
 ]
 
@@ -47,6 +47,7 @@ def lib():
         L.pb_grad_size.restype = C.c_int64
         L.pb_stats_launches.restype = C.c_int64
         L.pb_stats_last_rays.restype = C.c_int64
+        L.pb_stats_last_active_rays.restype = C.c_int64
         L.pb_stats_last_trace_ms.restype = C.c_float
         L.pb_stats_last_primary_ms.restype = C.c_float
         _lib = L
@@ -276,5 +277,5 @@ class Context:
     # --- stats -------------------------------------------------------------------------------------------------
     def stats(self):
         L = lib()
-        return dict(launches=int(L.pb_stats_launches(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)),
+        return dict(launches=int(L.pb_stats_launches(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)), active_rays=int(L.pb_stats_last_active_rays(self.h)),
                     trace_launches=int(L.pb_stats_last_trace_launches(self.h)), primary_ms=float(L.pb_stats_last_primary_ms(self.h)))

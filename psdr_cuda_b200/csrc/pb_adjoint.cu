@@ -7,6 +7,7 @@
 // Per lane the forward radiance is  L = Le(x0) + sum_k T_k * L_k,  T_{k+1} = T_k * w_k  (L_k: the event's MIS-weighted
 // connections, w_k: its continuation weight). With the suffix  S_k = L_k + w_k * S_{k+1}  the sensitivity of L to the
 // parameters touched by event k is  T_k * (dL_k + dw_k * S_{k+1}); the adjoint kernels run k = D-1 .. 0 carrying S.
+#include "pb_env_adjoint.cuh"
 #include "pb_rc.cuh"
 #include "pb_trace.cuh"
 #include "pb_wavefront.cuh"
@@ -88,7 +89,8 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, floa
 
 // adjoint of one scattering event (texture parameters). E.thr_in: T_k; suffix: S_{k+1} in, S_k out; E.rad: the lane's
 // final forward radiance (decides which channels integrator.cpp:87 zeroed).
-// RC: some rough-conductor texture requires a gradient (separate instantiation so that the diffuse-only kernel keeps its registers)
+// RC ("extended" events): rough-conductor texture / geometry adjoints and the environment map's radiance / scale / direction
+// adjoints (separate instantiation so that the diffuse + area-light kernel keeps its registers)
 template <int MINB, bool PREFETCH, bool RC>
 __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
     const HitRec *__restrict__ hits = E.hits;
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
+        const bool env_on = RC && P.S.emitter_env >= 0 && (env_wants_grad(P.S) || geom_mode(P.S));
+        if (RC && B.depth == 0 && !B.hide_emitters && env_on) env_le_vjp(P.S, its, v.ro, g, false);   // Le(x0), direct.cpp:51: the camera ray is a constant
         rc::Tex rtex;
         bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
         float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
@@ -157,6 +161,11 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 }
                 if (cont) { w_cont = f * scale; gval += gw * scale; }
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gval, acc);
+                if (RC && a1 && env_on) {   // dLoss/dLe of this connection
+                    float weight = inv_nb;
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
+                    g_p += env_le_vjp(P.S, its1, its.p, gL * f * (scale * weight), geom_mode(P.S));
+                }
                 if (RC && rc_tex) {
                     const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf(P.S, its.p, its1, true) : 0.f;
                     rc::TexGrad tg;
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gL * Le * scale, acc);
+                if (RC && env_on) g_p += env_le_vjp(P.S, its1, its.p, gL * f * scale, geom_mode(P.S));
                 if (RC && rc_tex) {
                     rc::TexGrad tg;
                     rc::light_branch_tex_grad(rtex, its.wi, wo_l, G, ps.pdf, B.nb > 0, inv_nl, gL * Le, tg);

@@ -163,17 +163,20 @@ static void configure_sensor(HostSensor &s, int W, int H) {
 }
 
 // all wavefront ray launches go through here: sorted (variant 7) or in lane order (debug variants)
-static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits) {
+static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
     if (g_trace_variant == 7) {
+        if (!c->d_active_total.p) { c->d_active_total.reserve(sizeof(unsigned long long)); cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream); }
         c->d_sort_hist.reserve(40000 * sizeof(unsigned));
         c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
         c->d_sort_keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
         launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
                             f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
-                            c->d_sort_keys.as<unsigned short>());
+                            c->d_sort_keys.as<unsigned short>(), c->d_active_total.as<unsigned long long>(), ev0, ev1);
         c->launches += 3;
     } else {
+        if (ev0) cudaEventRecord(ev0, c->stream);
         launch_trace(c->stream, c->view, n, rays, hits, nullptr);
+        if (ev1) cudaEventRecord(ev1, c->stream);
     }
 }
 
@@ -504,6 +507,15 @@ static void configure(pb_ctx *c) {
             c->grad_segments.push_back({PB_PARAM_MESH_VERTICES, (int)i, 0, off, n});
             off += n;
         }
+    if (c->emitter_env >= 0) {
+        const HostEmitter &e = c->emitters[c->emitter_env];
+        if (e.env_radiance.requires_grad) {
+            const int64_t n = (int64_t)e.env_radiance.data.size();
+            c->grad_segments.push_back({PB_PARAM_ENVMAP_RADIANCE, c->emitter_env, 0, off, n});
+            off += n;
+        }
+        if (e.env_scale_requires_grad) { c->grad_segments.push_back({PB_PARAM_ENVMAP_SCALE, c->emitter_env, 0, off, 1}); off += 1; }
+    }
     c->ready = true;
     c->have_last_d = false;
     c->retained_valid = false;
@@ -741,7 +753,9 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     const int64_t npix = (int64_t)c->width * c->height;
     if (d_image) PB_CUDA(cudaMemsetAsync(d_image, 0, (size_t)npix * 3 * sizeof(float), st));
     if (jvp) d_image = nullptr;
-    c->last_trace_ms = 0.f; c->last_rays = 0; c->last_primary_ms = 0.f; c->last_trace_launches = 0;
+    c->last_trace_ms = 0.f; c->last_rays = 0; c->last_primary_ms = 0.f; c->last_trace_launches = 0; c->last_active_rays = 0;
+    if (!c->d_active_total.p) c->d_active_total.reserve(sizeof(unsigned long long));
+    PB_CUDA(cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream));
     const int s0 = (int)((int64_t)c->spp * c->rank / c->world), s1 = (int)((int64_t)c->spp * (c->rank + 1) / c->world);
     const int spp_local = s1 - s0;
     const Plan plan = make_plan(I);
@@ -791,6 +805,19 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;   // forward mode: the tangent, read only
         c->d_bsdfs_grad.upload(br, st);
         P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
+        bool env_grad = false;
+        for (const GradSegment &g : c->grad_segments) env_grad = env_grad || g.kind == PB_PARAM_ENVMAP_RADIANCE || g.kind == PB_PARAM_ENVMAP_SCALE;
+        if (env_grad) {   // emitter table whose environment map points at its gradient segments
+            std::vector<EmitterRec> er(c->emitters.size());
+            PB_CUDA(cudaMemcpyAsync(er.data(), c->d_emitters.p, er.size() * sizeof(EmitterRec), cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+            for (const GradSegment &g : c->grad_segments) {
+                if (g.kind == PB_PARAM_ENVMAP_RADIANCE) er[g.id].env_radiance.grad = d_grad + g.offset;
+                if (g.kind == PB_PARAM_ENVMAP_SCALE) er[g.id].env_scale_grad = d_grad + g.offset;
+            }
+            c->d_emitters_grad.upload(er, st);
+            P.S.emitters = c->d_emitters_grad.as<EmitterRec>();
+        }
         bool any_geom = false;
         for (const GradSegment &g : c->grad_segments) any_geom = any_geom || g.kind == PB_PARAM_MESH_VERTICES;
         if (any_geom) {
@@ -837,6 +864,10 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 if (g.kind == PB_PARAM_BSDF_TEXTURE && c->bsdfs[g.id].type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
         if (mode == MODE_VJP && any_geom_jvp(c))   // geometry adjoints flow through every rough-conductor vertex on a path
             for (const HostBsdf &hb : c->bsdfs) if (hb.type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
+        if (mode == MODE_VJP && c->emitter_env >= 0) {   // environment map: radiance / scale gradients, and its direction term in the geometry adjoints
+            const HostEmitter &he = c->emitters[c->emitter_env];
+            if (he.env_radiance.requires_grad || he.env_scale_requires_grad || any_geom_jvp(c)) Bp.rc_grad = 1;
+        }
         Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
     }
     size_t nev = 0, nev_edge = 0;
@@ -872,9 +903,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 const EventBuffers E = event(k);
                 launch_shade(st, P, bps[k], E);
                 cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
-                PB_CUDA(cudaEventRecord(t0, st));
-                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits);
-                PB_CUDA(cudaEventRecord(t1, st));
+                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, t0, t1);
                 launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
                 c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
             }
@@ -904,7 +933,14 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     }
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaStreamSynchronize(st));
-    // event pairs: per batch one for the primary kernel, then one per k_trace launch
+    if (g_trace_variant == 7) {   // rays the traversal kernels actually traced (inactive lanes are compacted away by the sort)
+        unsigned long long act = 0;
+        PB_CUDA(cudaMemcpy(&act, c->d_active_total.p, sizeof(act), cudaMemcpyDeviceToHost));
+        c->last_active_rays = (int64_t)act;
+    } else {
+        c->last_active_rays = c->last_rays;
+    }
+    // event pairs: per batch one for the primary kernel, then one per k_trace launch (the traversal kernel alone, without the sort)
     {
         const size_t per_batch = 2 + 2 * (size_t)(field ? 0 : plan.nbounce);
         for (size_t i = 0; i + 1 < nev; i += 2) {
@@ -1194,6 +1230,10 @@ int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
         } else if (kind == PB_PARAM_MESH_VERTICES) {
             PB_ASSERT_MSG(id >= 0 && id < (int)c->meshes.size(), "Invalid mesh id");
             c->meshes[id].requires_grad = enable != 0;
+        } else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE) {
+            PB_ASSERT_MSG(c->emitter_env >= 0, "The scene has no environment map");
+            if (kind == PB_PARAM_ENVMAP_RADIANCE) c->emitters[c->emitter_env].env_radiance.requires_grad = enable != 0;
+            else c->emitters[c->emitter_env].env_scale_requires_grad = enable != 0;
         } else throw Error("Unknown parameter kind");
         c->ready = false;
     });
@@ -1217,7 +1257,7 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
         PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD || I->field == PB_FIELD_SILHOUETTE,
                       "FieldExtractionIntegrator: only the silhouette field (zero interior derivative) has gradients so far");
         for (const GradSegment &g : c->grad_segments)
-            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || bsdf_slot_is_differentiable(c->bsdfs[g.id].type, g.slot),
+            PB_ASSERT_MSG(g.kind != PB_PARAM_BSDF_TEXTURE || bsdf_slot_is_differentiable(c->bsdfs[g.id].type, g.slot),
                           "pb_render_d_vjp: this texture is not a parameter of its BSDF type (diffuse: reflectance; roughconductor: alpha_u, alpha_v, eta, k, specular_reflectance)");
         render_interior(c, *I, sensor, nullptr, MODE_VJP, d_dLdI, d_grad);
     });
@@ -1257,7 +1297,7 @@ int pb_render_d_jvp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
         PB_ASSERT_MSG(I->kind != PB_INTEG_FIELD || I->field == PB_FIELD_SILHOUETTE,
                       "FieldExtractionIntegrator: only the silhouette field (zero interior derivative) has derivatives so far");
         for (const GradSegment &g : c->grad_segments)
-            PB_ASSERT_MSG(g.kind == PB_PARAM_MESH_VERTICES || bsdf_slot_is_differentiable(c->bsdfs[g.id].type, g.slot),
+            PB_ASSERT_MSG(g.kind != PB_PARAM_BSDF_TEXTURE || bsdf_slot_is_differentiable(c->bsdfs[g.id].type, g.slot),
                           "pb_render_d_jvp: this texture is not a parameter of its BSDF type (diffuse: reflectance; roughconductor: alpha_u, alpha_v, eta, k, specular_reflectance)");
         render_interior(c, *I, sensor, d_dimage, MODE_JVP, nullptr, const_cast<float *>(d_tangent));
     });
@@ -1265,6 +1305,7 @@ int pb_render_d_jvp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
 int64_t pb_stats_launches(pb_ctx *c) { return c->launches; }
 float pb_stats_last_trace_ms(pb_ctx *c) { return c->last_trace_ms; }
 int64_t pb_stats_last_rays(pb_ctx *c) { return c->last_rays; }
+int64_t pb_stats_last_active_rays(pb_ctx *c) { return c->last_active_rays; }
 float pb_stats_last_primary_ms(pb_ctx *c) { return c->last_primary_ms; }
 int pb_stats_last_trace_launches(pb_ctx *c) { return c->last_trace_launches; }
 int pb_ctx_set_stream(pb_ctx *c, void *stream) {

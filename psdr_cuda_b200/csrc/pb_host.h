@@ -79,6 +79,7 @@ struct HostEmitter {
     // environment map (envmap.h)
     HostTexture env_radiance;
     float env_scale = 1.f;
+    bool env_scale_requires_grad = false;   // env_radiance.requires_grad covers the texels
     Mat4h env_raw = Mat4h::identity(), env_left = Mat4h::identity();
     bool env_dirty = true;
     int env_res[2] = {0, 0};
@@ -136,7 +137,7 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms
@@ -154,7 +155,7 @@ struct pb_ctx {
     bool have_last_d = false;
     std::vector<pb::GradSegment> grad_segments;
     // stats
-    int64_t launches = 0, last_rays = 0;
+    int64_t launches = 0, last_rays = 0, last_active_rays = 0;
     float last_trace_ms = 0.f, last_primary_ms = 0.f;
     int last_trace_launches = 0;
     bool own_stream = true;

@@ -63,7 +63,7 @@ extern int g_trace_smem_nodes;
 extern int g_trace_variant;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys);
+                         unsigned short *keys, unsigned long long *active_total = nullptr, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);

@@ -72,6 +72,7 @@ struct EmitterRec {
     float3 env_lower; float pad4;
     float3 env_upper; float env_sum;
     const float *env_cmf, *env_pmf;
+    float *env_scale_grad;   // VJP: gradient of the scale (forward mode: its tangent), or nullptr
 };
 struct SensorRec {
     Mat4 sample_to_camera, to_world, world_to_sample;

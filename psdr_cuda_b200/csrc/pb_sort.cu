@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(1024) k_sort_hist(long long n, const RayRec *_
 }
 
 // exclusive scan of the kSortBins + 1 counters in place; hist[kSortBins + 1] receives the number of active rays
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist) {
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist, unsigned long long *__restrict__ active_total) {
     __shared__ unsigned s_part[1024];
     const int t = threadIdx.x;
     constexpr int per = (kSortBins + 1 + 1023) / 1024;
@@ -87,7 +87,10 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist)
     unsigned base = s_part[t] - sum;
     for (int k = 0; k < per; ++k) {
         const int idx = t * per + k;
-        if (idx <= kSortBins) { hist[idx] = base; if (idx == kSortBins) hist[kSortBins + 1] = base; }
+        if (idx <= kSortBins) {
+            hist[idx] = base;
+            if (idx == kSortBins) { hist[kSortBins + 1] = base; if (active_total) atomicAdd(active_total, (unsigned long long)base); }   // rays actually traced
+        }
         base += v[k];
     }
 }
@@ -151,7 +154,7 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 
 // hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned; keys: n unsigned short
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys) {
+                         unsigned short *keys, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (n <= 0) return;
     static int mode_set = -1;
     if (mode_set != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); mode_set = g_sort_mode; }
@@ -165,9 +168,10 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
         sort_attr = true;
     }
     k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist, keys);
-    k_sort_scan<<<1, 1024, 0, st>>>(hist);
+    k_sort_scan<<<1, 1024, 0, st>>>(hist, active_total);
     k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
+    if (ev0) cudaEventRecord(ev0, st);   // the pair brackets the traversal kernel alone (roofline: 48 B per traced ray / this duration)
     if (g_trace_smem) {
         static bool attr_set = false;
         const int cap = std::min(kTopNodes, std::max(32, g_trace_smem_nodes));
@@ -182,6 +186,7 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
             default: k_trace_perm<true, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
         }
     }
+    if (ev1) cudaEventRecord(ev1, st);
 }
 
 }  // namespace pb

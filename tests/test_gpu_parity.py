@@ -607,3 +607,52 @@ def test_roughconductor_texture_and_vertex_gradients_cfg5_small():
     want = float((dLdI.astype(np.float64) * dimg).sum())
     got = float(g[0] * ta + (g[1:4] * te).sum() + (g[4:].reshape(nv, 3) * u).sum())
     assert abs(got - want) <= 3e-3 * abs(want), (got, want)
+
+
+# ---- environment map in its ad = true flavour (a13): radiance texels, scale, and the direction term of the geometry adjoints ----
+@pytest.mark.parametrize("scene,kind,kw", [("bunny_env", "direct", dict(bsdf_samples=1, light_samples=1)), ("bunny_env_2", "path", dict(max_depth=2))])
+def test_envmap_radiance_and_scale_gradients_vs_oracle(scene, kind, kw):
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    opts = dict(width=32, height=32, spp=4, sppe=0, sppse=0)
+    pdesc = scene_io.load_scene_description(scene_path(scene))
+    odesc = orc.load_scene_description(scene_path(scene))
+    ctx = capi.Context(0)
+    ctx.load_description(pdesc, opts)
+    ctx.grad_require(capi.PARAM_ENVMAP_RADIANCE, 0)
+    ctx.grad_require(capi.PARAM_ENVMAP_SCALE, 0)
+    ctx.configure()
+    integ = capi.make_integrator(kind, **kw)
+    oi = orc.DirectIntegrator(kw["bsdf_samples"], kw["light_samples"]) if kind == "direct" else orc.PathIntegrator(kw["max_depth"])
+    img = ctx.render_d(integ).cpu().numpy()
+    rng = np.random.default_rng(21)
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64)
+    layout = ctx.grad_layout()
+    assert [s["kind"] for s in layout] == [capi.PARAM_ENVMAP_RADIANCE, capi.PARAM_ENVMAP_SCALE]
+    h, w = odesc["envmap"]["radiance"].shape[:2]
+    assert layout[0]["count"] == h * w * 3 and layout[1]["count"] == 1 and np.isfinite(g).all()
+    g_rad, g_scale = g[:h * w * 3].reshape(h, w, 3), g[-1]
+    assert np.abs(g_rad).max() > 0
+    for trial in range(3):
+        t_rad = rng.normal(size=(h, w, 3)).astype(np.float32) if trial < 2 else None
+        t_scale = float(rng.normal()) if trial != 0 else 0.0
+        osc = orc.Scene(odesc, opts)
+        osc.set_envmap_tangent(t_rad, t_scale)
+        osc.configure()
+        _, dimg = oi.renderD(osc)
+        want = float((dLdI.astype(np.float64) * dimg).sum())
+        got = (float((g_rad * t_rad).sum()) if t_rad is not None else 0.0) + g_scale * t_scale
+        assert abs(got - want) <= 1e-3 * max(abs(want), 1e-6), (trial, got, want)
+    # forward mode through the same kernels
+    t = np.zeros(g.size, np.float32); t[-1] = 0.5; t[:h * w * 3] = rng.normal(size=h * w * 3).astype(np.float32)
+    dimg = ctx.render_d_jvp(integ, torch.from_numpy(t).cuda()).cpu().numpy().astype(np.float64)
+    lhs, rhs = float((dimg * dLdI).sum()), float((g * t).sum())
+    assert abs(lhs - rhs) <= 1e-3 * max(abs(rhs), 1e-6), (lhs, rhs)
+
+
+def test_envmap_direction_term_in_vertex_gradients():
+    """diffuse meshes under the environment map: moving a vertex moves the direction in which the map is looked up (envmap.cpp:35-58)"""
+    o = dict(width=40, height=40, spp=8, sppe=0, sppse=0)
+    _vertex_grad_case("bunny_env_2", o, "direct", dict(bsdf_samples=1, light_samples=1), 1)
+    _vertex_grad_case("bunny_env_2", o, "path", dict(max_depth=2), 0)
