@@ -85,6 +85,7 @@ int pb_scene_add_area_emitter(pb_ctx *ctx, int mesh, const float h_radiance[3]);
  * radiance, interleaved. Must be added before the area emitters to keep the reference's emitter order. At configure the
  * context appends the 12-triangle bounding mesh the envmap radiates from (src/scene/scene.cpp:135-180). Returns id >= 0. */
 int pb_scene_add_envmap(pb_ctx *ctx, int w, int h, const float *h_rgb, float scale, const float h_to_world[16]);
+int pb_scene_set_envmap_radiance(pb_ctx *ctx, const float *h_rgb /* w*h*3 of the creation size, or NULL to keep */, float scale);   /* EnvironmentMap.radiance.data / .scale edits, src/psdr.cpp:236-237 */
 int pb_scene_set_envmap_transform(pb_ctx *ctx, const float h_left[16]);   /* EnvironmentMap::set_transform, envmap.h:18-21 */
 int pb_scene_num_meshes(pb_ctx *ctx);                                      /* Scene.num_meshes (includes the bounding mesh) */
 /* Scene::configure: src/scene/scene.cpp:56-278 (sampler seeding rule, mesh preprocessing, emitter pmf, triangle table, BVH) */

@@ -150,6 +150,8 @@ class Scene(_h.Scene):
         obj = self._raw_param_map()[key]
         if field in ("to_world_left", "to_world_right"):   # Mesh.set_transform / append_transform leaves (src/psdr.cpp:246-247)
             value = getattr(obj, field)
+        elif field == "scale":                              # EnvironmentMap.scale (src/psdr.cpp:237)
+            value = np.float32(obj.scale)
         else:
             value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
         t = torch.tensor(np.asarray(value), dtype=torch.float32, device="cuda:%d" % self._device, requires_grad=requires_grad)
@@ -163,6 +165,9 @@ class Scene(_h.Scene):
             if field == "vertex_positions":
                 obj.vertex_positions = val
                 obj.requires_grad = bool(t.requires_grad) or obj.requires_grad
+            elif field == "scale":
+                obj.scale = float(val)
+                obj.scale_requires_grad = bool(t.requires_grad)
             elif field in ("to_world_left", "to_world_right"):
                 obj.set_transform(val.astype(np.float32), field == "to_world_left")
                 obj.requires_grad = bool(t.requires_grad) or obj.requires_grad   # the transform gradient is a contraction of the vertex gradient

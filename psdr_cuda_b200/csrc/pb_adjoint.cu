@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
     int bsdf_id = -1;
     rc::TexGrad rc_acc;
     bool rc_tex = false;
+    float env_scale_acc = 0.f;
+    __shared__ float s_rc[RC ? rc::kFlushFloats : 1];
     if (i < P.n) {
         if (PREFETCH) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
         int pix;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
         const bool env_on = RC && P.S.emitter_env >= 0 && (env_wants_grad(P.S) || geom_mode(P.S));
-        if (RC && B.depth == 0 && !B.hide_emitters && env_on) env_le_vjp(P.S, its, v.ro, g, false);   // Le(x0), direct.cpp:51: the camera ray is a constant
+        if (RC && B.depth == 0 && !B.hide_emitters && env_on) env_le_vjp(P.S, its, v.ro, g, false, env_scale_acc);   // Le(x0), direct.cpp:51: the camera ray is a constant
         rc::Tex rtex;
         bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
         float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 if (RC && a1 && env_on) {   // dLoss/dLe of this connection
                     float weight = inv_nb;
                     if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
-                    g_p += env_le_vjp(P.S, its1, its.p, gL * f * (scale * weight), geom_mode(P.S));
+                    g_p += env_le_vjp(P.S, its1, its.p, gL * f * (scale * weight), geom_mode(P.S), env_scale_acc);
                 }
                 if (RC && rc_tex) {
                     const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf(P.S, its.p, its1, true) : 0.f;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gL * Le * scale, acc);
-                if (RC && env_on) g_p += env_le_vjp(P.S, its1, its.p, gL * f * scale, geom_mode(P.S));
+                if (RC && env_on) g_p += env_le_vjp(P.S, its1, its.p, gL * f * scale, geom_mode(P.S), env_scale_acc);
                 if (RC && rc_tex) {
                     rc::TexGrad tg;
                     rc::light_branch_tex_grad(rtex, its.wi, wo_l, G, ps.pdf, B.nb > 0, inv_nl, gL * Le, tg);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         return;
     }
     flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
-    if (RC) rc::flush_const_tex_grad(P.S, rc_tex ? bsdf_id : -1, rc_acc);
+    if (RC) rc::flush_const_tex_grad(P.S, rc_tex ? bsdf_id : -1, rc_acc, env_scale_acc, s_rc);
 }
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }

@@ -1141,6 +1141,15 @@ int pb_scene_add_envmap(pb_ctx *c, int w, int h, const float *rgb, float scale, 
         return c->emitter_env;
     });
 }
+int pb_scene_set_envmap_radiance(pb_ctx *c, const float *rgb, float scale) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->emitter_env >= 0, "No environment map");
+        HostEmitter &e = c->emitters[c->emitter_env];
+        if (rgb) { e.env_radiance.data.assign(rgb, rgb + e.env_radiance.data.size()); e.env_dirty = true; }   // resolution is fixed at creation
+        e.env_scale = scale;
+        c->ready = false;
+    });
+}
 int pb_scene_set_envmap_transform(pb_ctx *c, const float *left) {
     return guard(c, [&] {
         PB_ASSERT_MSG(c->emitter_env >= 0, "No environment map");

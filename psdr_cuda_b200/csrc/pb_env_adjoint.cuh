@@ -16,8 +16,9 @@ PB_D bool env_wants_grad(const SceneView &S) {
 }
 
 // gLe: dLoss/dLe (per channel). its1: the hit on the bounding mesh, seen from `origin`. Returns the adjoint of `origin`
-// (zero unless `want_dir`).
-PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float3 gLe, bool want_dir) {
+// (zero unless `want_dir`). The scale's gradient goes to the thread-private `scale_acc` (one address for every lane: the
+// kernel reduces it per block before touching global memory).
+PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float3 gLe, bool want_dir, float &scale_acc) {
     float3 g_origin = f3(0.f);
     if (!its1.valid || !finite3(gLe) || (gLe.x == 0.f && gLe.y == 0.f && gLe.z == 0.f)) return g_origin;
     const int e = S.meshes[its1.shape].emitter;
@@ -57,7 +58,7 @@ PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float
 #pragma unroll
         for (int c = 0; c < 3; ++c) s += g[c] * (w[0] * tex[0][c] + w[1] * tex[1][c] + w[2] * tex[2][c] + w[3] * tex[3][c]);
         if (fwd) jv = fmaf(s, __ldg(em.env_scale_grad), jv);
-        else if (s != 0.f && isfinite(s)) atomicAdd(em.env_scale_grad, s);
+        else if (isfinite(s)) scale_acc += s;
     }
     if (fwd && jv != 0.f && isfinite(jv)) S.jvp_acc[blockIdx.x * blockDim.x + threadIdx.x] += jv;
     // direction -> the looking vertex

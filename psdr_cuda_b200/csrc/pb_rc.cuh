@@ -278,10 +278,15 @@ PB_D void emit_tex_grad(const SceneView &S, const BsdfRec *b, float2 uv, const T
     tex_scatter<3>(S, b->tex[TEX_K], uv, k);
     tex_scatter<3>(S, b->tex[TEX_SPECULAR], uv, s);
 }
-// warp-level flush of the 1x1-texture accumulators, grouped by BSDF id
-PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, const TexGrad &acc) {
+// Block-level flush of the 1x1-texture accumulators (grouped by BSDF id) and of the environment map's scale accumulator:
+// warp shuffles, then shared-memory slots, then one global atomic per block and parameter. Every thread of the block calls it.
+constexpr int kConstSlots = 8;                        // BSDF ids below this reduce through shared memory, others per warp
+constexpr int kFlushFloats = kConstSlots * 11 + 1;    // + the environment map's scale
+PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, const TexGrad &acc, float env_scale_acc, float *s_buf) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < kFlushFloats; t += blockDim.x) s_buf[t] = 0.f;
+    __syncthreads();
     const bool has = bsdf_id >= 0 && (acc.au != 0.f || acc.av != 0.f || acc.eta.x != 0.f || acc.eta.y != 0.f || acc.eta.z != 0.f || acc.k.x != 0.f ||
                                       acc.k.y != 0.f || acc.k.z != 0.f || acc.spec.x != 0.f || acc.spec.y != 0.f || acc.spec.z != 0.f);
     unsigned remaining = __ballot_sync(full, has);
@@ -299,17 +304,41 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, const TexGrad &a
             v[k] = x;
         }
         if (lane == leader) {
-            const BsdfRec &b = S.bsdfs[key];
-            if (b.tex[TEX_ALPHA_U].grad && v[0] != 0.f) atomicAdd(b.tex[TEX_ALPHA_U].grad, v[0]);
-            if (b.tex[TEX_ALPHA_V].grad && v[1] != 0.f) atomicAdd(b.tex[TEX_ALPHA_V].grad, v[1]);
+            if (key < kConstSlots) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (b.tex[TEX_ETA].grad && v[2 + c] != 0.f) atomicAdd(b.tex[TEX_ETA].grad + c, v[2 + c]);
-                if (b.tex[TEX_K].grad && v[5 + c] != 0.f) atomicAdd(b.tex[TEX_K].grad + c, v[5 + c]);
-                if (b.tex[TEX_SPECULAR].grad && v[8 + c] != 0.f) atomicAdd(b.tex[TEX_SPECULAR].grad + c, v[8 + c]);
+                for (int k = 0; k < 11; ++k) if (v[k] != 0.f) atomicAdd(s_buf + key * 11 + k, v[k]);
+            } else {
+                const BsdfRec &b = S.bsdfs[key];
+                if (b.tex[TEX_ALPHA_U].grad && v[0] != 0.f) atomicAdd(b.tex[TEX_ALPHA_U].grad, v[0]);
+                if (b.tex[TEX_ALPHA_V].grad && v[1] != 0.f) atomicAdd(b.tex[TEX_ALPHA_V].grad, v[1]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (b.tex[TEX_ETA].grad && v[2 + c] != 0.f) atomicAdd(b.tex[TEX_ETA].grad + c, v[2 + c]);
+                    if (b.tex[TEX_K].grad && v[5 + c] != 0.f) atomicAdd(b.tex[TEX_K].grad + c, v[5 + c]);
+                    if (b.tex[TEX_SPECULAR].grad && v[8 + c] != 0.f) atomicAdd(b.tex[TEX_SPECULAR].grad + c, v[8 + c]);
+                }
             }
         }
         remaining &= ~grp;
+    }
+    float es = env_scale_acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(full, es, o);
+    if (lane == 0 && es != 0.f) atomicAdd(s_buf + kConstSlots * 11, es);
+    __syncthreads();
+    for (int t = threadIdx.x; t < kFlushFloats; t += blockDim.x) {
+        const float v = s_buf[t];
+        if (v == 0.f) continue;
+        if (t == kConstSlots * 11) {
+            if (S.emitter_env >= 0 && S.emitters[S.emitter_env].env_scale_grad) atomicAdd(S.emitters[S.emitter_env].env_scale_grad, v);
+            continue;
+        }
+        const int b = t / 11, k = t - 11 * b;
+        if (b >= S.num_bsdfs) continue;
+        const BsdfRec &br = S.bsdfs[b];
+        float *gp = k == 0 ? br.tex[TEX_ALPHA_U].grad : k == 1 ? br.tex[TEX_ALPHA_V].grad : k < 5 ? br.tex[TEX_ETA].grad : k < 8 ? br.tex[TEX_K].grad : br.tex[TEX_SPECULAR].grad;
+        const int off = k < 2 ? 0 : (k - 2) % 3;
+        if (gp) atomicAdd(gp + off, v);
     }
 }
 

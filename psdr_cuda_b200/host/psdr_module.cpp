@@ -254,6 +254,7 @@ struct AreaLight : Emitter {
 struct EnvironmentMap : Emitter {
     Bitmap radiance{3, 0.f};
     float scale = 1.f;
+    bool scale_dirty = false, scale_requires_grad = false;
     Mat4 to_world_raw, to_world_left;
     bool transform_dirty = false;
     std::string type_name() const override { return "AreaLight"; }   // sic: envmap.h:58
@@ -466,6 +467,7 @@ public:
             for (auto &s : sensors) check_id(pb_scene_add_sensor(ctx, s->fov_x, s->near_clip, s->far_clip, s->to_world.m));
             for (auto &b : bsdfs) check_id(pb_scene_add_bsdf(ctx, dynamic_cast<Diffuse *>(b.get()) ? PB_BSDF_DIFFUSE : PB_BSDF_ROUGHCONDUCTOR));
             if (envmap) check_id(pb_scene_add_envmap(ctx, envmap->radiance.width, envmap->radiance.height, envmap->radiance.data.data(), envmap->scale, envmap->to_world_raw.m));
+            if (envmap) { envmap->radiance.dirty = false; envmap->scale_dirty = false; }
             for (auto &m : meshes) {
                 const int flags = (m->use_face_normals ? PB_MESH_FACE_NORMALS : 0) | (m->enable_edges ? PB_MESH_ENABLE_EDGES : 0);
                 check_id(pb_scene_add_mesh(ctx, m->nv(), m->nf(), m->verts.data(), m->faces.data(), (int)m->uvs.size() / 2, m->uvs.empty() ? nullptr : m->uvs.data(),
@@ -494,6 +496,14 @@ public:
             check(pb_grad_require(ctx, PB_PARAM_MESH_VERTICES, m->index, 0, m->requires_grad ? 1 : 0));
         }
         if (envmap && envmap->transform_dirty) { check(pb_scene_set_envmap_transform(ctx, envmap->to_world_left.m)); envmap->transform_dirty = false; }
+        if (envmap) {
+            if (envmap->radiance.dirty || envmap->scale_dirty) {
+                check(pb_scene_set_envmap_radiance(ctx, envmap->radiance.dirty ? envmap->radiance.data.data() : nullptr, envmap->scale));
+                envmap->radiance.dirty = false; envmap->scale_dirty = false;
+            }
+            check(pb_grad_require(ctx, PB_PARAM_ENVMAP_RADIANCE, 0, 0, envmap->radiance.requires_grad ? 1 : 0));
+            check(pb_grad_require(ctx, PB_PARAM_ENVMAP_SCALE, 0, 0, envmap->scale_requires_grad ? 1 : 0));
+        }
         check(pb_scene_configure(ctx));
         configured = true;
     }
@@ -507,6 +517,8 @@ public:
             int kind, id, slot; int64_t off, cnt;
             check(pb_grad_segment(ctx, i, &kind, &id, &slot, &off, &cnt));
             if (kind == PB_PARAM_BSDF_TEXTURE) out.append(py::make_tuple("BSDF[" + std::to_string(id) + "]", std::string(slots[slot]), off, cnt));
+            else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE)
+                out.append(py::make_tuple("Emitter[" + std::to_string(id) + "]", std::string(kind == PB_PARAM_ENVMAP_RADIANCE ? "radiance" : "scale"), off, cnt));
             else out.append(py::make_tuple("Mesh[" + std::to_string(id) + "]", std::string("vertex_positions"), off, cnt));
         }
         return out;
@@ -620,7 +632,8 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_property_readonly("radiance", [](const AreaLight &a) { return py::make_tuple(a.radiance[0], a.radiance[1], a.radiance[2]); });
     py::class_<EnvironmentMap, Emitter, std::shared_ptr<EnvironmentMap>>(m, "EnvironmentMap")
         .def_property_readonly("radiance", [](EnvironmentMap &e) -> Bitmap & { return e.radiance; }, py::return_value_policy::reference_internal)
-        .def_readonly("scale", &EnvironmentMap::scale)
+        .def_property("scale", [](const EnvironmentMap &e) { return e.scale; }, [](EnvironmentMap &e, float v) { e.scale = v; e.scale_dirty = true; })
+        .def_readwrite("scale_requires_grad", &EnvironmentMap::scale_requires_grad)
         .def_property_readonly("to_world", [](const EnvironmentMap &e) { return mat_to_numpy(e.to_world_left * e.to_world_raw); })
         .def("set_transform", [](EnvironmentMap &e, const farray &a) { e.to_world_left = mat_from_numpy(a); e.transform_dirty = true; });
 

@@ -172,3 +172,55 @@ def test_mesh_transform_leaf_gradient_matches_oracle(psdr_cuda):
         want = float((w.double().cpu().numpy() * dimg).sum())
         got = float((g * dM).sum())
         assert abs(got - want) <= 3e-3 * abs(want), (got, want)
+
+
+@pytest.mark.gpu
+def test_roughconductor_and_envmap_leaves_through_the_module(psdr_cuda):
+    """RoughConductorBSDF.{alpha_u,eta}.data, EnvironmentMap.{radiance.data,scale} and Mesh.vertex_positions as torch leaves
+    (src/psdr.cpp:211-215,236-238): one backward through the module equals the VJP of the ctypes binding."""
+    torch = pytest.importorskip("torch")
+    from psdr_cuda_b200 import capi, scene_io
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path("bunny_env"), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse = 32, 32, 4, 0, 0
+    alpha = sc.parameter("BSDF[0]", "alpha_u")
+    eta = sc.parameter("BSDF[id=mat1]", "eta")
+    rad = sc.parameter("Emitter[0]", "radiance")
+    scale = sc.parameter("Emitter[0]", "scale")
+    verts = sc.parameter("Mesh[0]", "vertex_positions")
+    sc.configure()
+    integ = psdr_cuda.DirectIntegrator(1, 1)
+    img = integ.renderD(sc, 0)
+    w = torch.linspace(-1.0, 1.0, img.numel(), device=img.device).view_as(img)
+    (img * w).sum().backward()
+    for t in (alpha, eta, rad, scale, verts):
+        assert t.grad is not None and torch.isfinite(t.grad).all()
+    ctx = capi.Context(0)
+    ctx.load_description(scene_io.load_scene_description(scene_path("bunny_env")), dict(width=32, height=32, spp=4, sppe=0, sppse=0))
+    ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "alpha_u")
+    ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "eta")
+    ctx.grad_require(capi.PARAM_MESH_VERTICES, 0)
+    ctx.grad_require(capi.PARAM_ENVMAP_RADIANCE, 0)
+    ctx.grad_require(capi.PARAM_ENVMAP_SCALE, 0)
+    ctx.configure()
+    ci = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+    ref = ctx.render_d(ci)
+    assert torch.equal(img.detach(), ref)
+    g = ctx.render_d_vjp(ci, w.contiguous())
+    seg = {(s["kind"], s["slot"]): s for s in ctx.grad_layout()}
+    def part(kind, slot=0):
+        s = seg[(kind, slot)]
+        return g[s["offset"]:s["offset"] + s["count"]]
+    def close(a, b):
+        return (a.reshape(-1) - b).norm() <= 1e-4 * b.norm() + 1e-7
+    assert close(alpha.grad, part(capi.PARAM_BSDF_TEXTURE, capi.TEX["alpha_u"]))
+    assert close(eta.grad, part(capi.PARAM_BSDF_TEXTURE, capi.TEX["eta"]))
+    assert close(verts.grad, part(capi.PARAM_MESH_VERTICES))
+    assert close(rad.grad, part(capi.PARAM_ENVMAP_RADIANCE))
+    assert close(scale.grad, part(capi.PARAM_ENVMAP_SCALE))
+    # editing the leaves reaches the renderer at the next configure()
+    with torch.no_grad():
+        scale *= 0.5
+    sc.configure()
+    img2 = integ.renderC(sc, 0)
+    assert abs(float(img2.mean()) / float(integ.renderC(sc, 0).mean()) - 1.0) < 0.2 and float(img2.mean()) < 0.75 * float(img.detach().mean())
