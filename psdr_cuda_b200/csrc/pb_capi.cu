@@ -1279,6 +1279,8 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "trace_smem") == 0) pb::g_trace_smem = (int)value;
         else if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
         else if (std::strcmp(key, "shade_tune") == 0) pb::g_shade_tune = (int)value;
+        else if (std::strcmp(key, "trace_ld256") == 0) pb::g_trace_ld256 = (int)value;
+        else if (std::strcmp(key, "trace_sstack") == 0) pb::g_trace_sstack = (int)value;
         else if (std::strcmp(key, "trace_smem_nodes") == 0) pb::g_trace_smem_nodes = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);
     });

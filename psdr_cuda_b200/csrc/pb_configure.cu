@@ -85,6 +85,7 @@ __global__ void k_build_leaf_tris(int n, const int *__restrict__ order, const Tr
     l.a = make_float4(q0.x, q0.y, q0.z, __int_as_float(t));
     l.b = make_float4(q1.x, q1.y, q1.z, q1.w);   // w = mesh id
     l.c = make_float4(q2.x, q2.y, q2.z, 0.f);
+    l.pad = make_float4(0.f, 0.f, 0.f, 0.f);
     leaf[i] = l;
 }
 

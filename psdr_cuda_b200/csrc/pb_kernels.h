@@ -57,6 +57,8 @@ void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriR
 
 extern int g_trace_blocks_per_sm;
 extern int g_sort_mode;
+extern int g_trace_ld256;
+extern int g_trace_sstack;
 extern int g_shade_tune;   // debug: k_resolve / k_adjoint variant (0 default)
 extern int g_trace_smem;
 extern int g_trace_smem_nodes;

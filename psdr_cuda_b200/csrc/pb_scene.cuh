@@ -24,13 +24,14 @@ struct __align__(16) HitRec {      // 16 B: what cuda/psdr_cuda.cu:36-45 writes 
 // q[6] = face_normal.xyz, uv1.y                                    q[7] = uv2.x, uv2.y, -, -
 struct __align__(16) TriRec { float4 q[8]; };
 
-// triangles in BVH leaf order for the traversal kernel (48 B): p0.xyz,tri id | e1.xyz,- | e2.xyz,-
-struct __align__(16) LeafTri { float4 a, b, c; };
+// triangles in BVH leaf order for the traversal kernel: p0.xyz,tri id | e1.xyz,mesh id | e2.xyz,- | padding. 64 B so that a
+// record is two 256-bit loads (LDG.E.256 on sm_100a) instead of three 128-bit ones.
+struct __align__(32) LeafTri { float4 a, b, c, pad; };
 
 // BVH2 node, 64 B: both children's boxes + child links.
 // a = (l.lo.x, l.lo.y, l.lo.z, l.hi.x)  b = (l.hi.y, l.hi.z, r.lo.x, r.lo.y)  c = (r.lo.z, r.hi.x, r.hi.y, r.hi.z)
 // d = (left, right, -, -) as int bits; child >= 0: inner node index; child < 0: leaf, v = ~child, first = v >> 3, count = (v & 7) + 1
-struct __align__(16) BvhNode { float4 a, b, c, d; };
+struct __align__(64) BvhNode { float4 a, b, c, d; };
 
 // BVH4 node, 128 B = one line: the four children's boxes in SoA form (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4]),
 // child links (int bits; 0x80000000 = absent), padding. Built by collapsing the binary tree (pb_bvh.cpp).

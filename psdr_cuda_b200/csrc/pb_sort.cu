@@ -14,6 +14,8 @@
 namespace pb {
 
 int g_sort_mode = 0;
+int g_trace_sstack = 0;   // > 0: that many stack levels in shared memory
+int g_trace_ld256 = 1;   // 256-bit node / leaf loads in the sorted-wavefront traversal kernel
 int g_trace_smem_nodes = 512;
 int g_trace_smem = 0;   // stage the top of the BVH in shared memory (persistent blocks) for the sorted wavefront trace
 
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const unsign
     if (key != kSortBins) perm[s_cnt[key] + rank] = (unsigned)i;
 }
 
-template <bool FMA_SLAB, int MINB>
+template <bool FMA_SLAB, int MINB, bool LD256 = false>
 __global__ void __launch_bounds__(128, MINB) k_trace_perm(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
                                                     const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,7 +131,20 @@ __global__ void __launch_bounds__(128, MINB) k_trace_perm(const BvhNode *__restr
     // rays and hits stream through once: evict-first hints keep the BVH and the triangle tables resident in L2
     const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
     const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
-    const Hit h = trace_closest_spec<FMA_SLAB>(nodes, leaf, f3(a), f3(b), a.w, b.w);
+    const Hit h = trace_closest_spec<FMA_SLAB, 64, LD256>(nodes, leaf, f3(a), f3(b), a.w, b.w);
+    __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
+}
+
+template <int MINB, int SK>
+__global__ void __launch_bounds__(128, MINB) k_trace_perm_sstack(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
+                                                                 const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
+    __shared__ int s_stack[SK * 128];
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= __ldg(n_active)) return;
+    const unsigned i = __ldcs(perm + j);
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
+    const Hit h = trace_closest_spec_sstack<true, SK, true>(s_stack, nodes, leaf, f3(a), f3(b), a.w, b.w);
     __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
 }
 
@@ -179,7 +194,16 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
         if (!attr_set) { cudaFuncSetAttribute(k_trace_perm_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopNodes * 64); attr_set = true; }
         k_trace_perm_smem<true><<<148, 1024, smem, st>>>(S.nodes, S.num_nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits, cap);
     } else {
-        switch (g_trace_blocks_per_sm) {
+        if (g_trace_sstack == 16) {
+            k_trace_perm_sstack<8, 16><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+        } else if (g_trace_sstack == 24) {
+            k_trace_perm_sstack<8, 24><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+        } else if (g_trace_sstack == 12) {
+            k_trace_perm_sstack<10, 12><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+        } else if (g_trace_ld256) {
+            if (g_trace_blocks_per_sm == 10) k_trace_perm<true, 10, true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+            else k_trace_perm<true, 8, true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+        } else switch (g_trace_blocks_per_sm) {
             case 10: k_trace_perm<true, 10><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
             case 12: k_trace_perm<true, 12><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
             case 16: k_trace_perm<true, 16><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;

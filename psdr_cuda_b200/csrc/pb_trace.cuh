@@ -149,7 +149,17 @@ PB_D Hit trace_closest_ww(const BvhNode *__restrict__ nodes, const LeafTri *__re
 //             the emitter sample is blocked; direct.cpp:130-131).
 // The triangle test rejects on the sign of the unnormalised barycentrics before paying for the division; survivors run
 // the exact utils.h:67-77 arithmetic, so accepted hits are bit-identical to the oracle's.
-template <bool FMA_SLAB, int STACK = 64>
+// 256-bit read-only global load (sm_100a: LDG.E.256): a 64-byte BVH node or leaf triangle is two instructions instead of four / three
+struct F8 { float4 lo, hi; };
+PB_D F8 ldg256(const void *p) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+
+template <bool FMA_SLAB, int STACK = 64, bool LD256 = false>
 PB_D Hit trace_closest_spec(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, float3 o, float3 d, float tmax, float t_occ) {
     Hit best;
     best.tri = -1; best.shape = -1; best.u = -1.f; best.v = -1.f; best.t = tmax;
@@ -167,7 +177,9 @@ PB_D Hit trace_closest_spec(const BvhNode *__restrict__ nodes, const LeafTri *__
         bool searching = true;
         while (node >= 0) {
             const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-            const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2), l = ldg4(np + 3);
+            float4 a, b, c, l;
+            if (LD256) { const F8 n0 = ldg256(np), n1 = ldg256(np + 2); a = n0.lo; b = n0.hi; c = n1.lo; l = n1.hi; }
+            else { a = ldg4(np); b = ldg4(np + 1); c = ldg4(np + 2); l = ldg4(np + 3); }
             float t0, t1;
 #define PB_SLAB(lo, hi, oc, ic) if (FMA_SLAB) { t0 = fmaf(lo, ic, -oc); t1 = fmaf(hi, ic, -oc); } else { t0 = (lo - oc) * ic; t1 = (hi - oc) * ic; }
             PB_SLAB(a.x, a.w, ox, ix)
@@ -204,7 +216,9 @@ PB_D Hit trace_closest_spec(const BvhNode *__restrict__ nodes, const LeafTri *__
             const int first = v >> 3, cnt = (v & 7) + 1;
             for (int i = 0; i < cnt; ++i) {
                 const float4 *tp = reinterpret_cast<const float4 *>(leaf + first + i);
-                const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                float4 ta, tb, tc;
+                if (LD256) { const F8 t01 = ldg256(tp); ta = t01.lo; tb = t01.hi; tc = ldg4(tp + 2); }
+                else { ta = ldg4(tp); tb = ldg4(tp + 1); tc = ldg4(tp + 2); }
                 const float3 p0 = f3(ta), e1 = f3(tb), e2 = f3(tc);
                 // unnormalised barycentrics with the oracle's op order; sign-only early outs (guarded against underflow of u, v)
                 const float3 h = cross(d, e2);
@@ -232,6 +246,103 @@ PB_D Hit trace_closest_spec(const BvhNode *__restrict__ nodes, const LeafTri *__
     if (best.tri < 0) best.t = INFINITY;
     return best;
 }
+
+// Same traversal with the first SK stack levels in shared memory (column tid of an SK x blockDim array: conflict-free whatever
+// the lanes' stack depths are, where the local-memory stack costs one L1 wavefront per distinct depth in the warp); deeper
+// entries spill to a small local array.
+template <bool FMA_SLAB, int SK, bool LD256>
+PB_D Hit trace_closest_spec_sstack(int *__restrict__ s_stack, const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, float3 o, float3 d, float tmax, float t_occ) {
+    constexpr int STACK = 64 - SK;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+#define PB_PUSH(x) do { if (sp < SK) s_stack[sp * nthr + tid] = (x); else stack[sp - SK] = (x); ++sp; } while (0)
+#define PB_POP() (--sp, sp < SK ? s_stack[sp * nthr + tid] : stack[sp - SK])
+    Hit best;
+    best.tri = -1; best.shape = -1; best.u = -1.f; best.v = -1.f; best.t = tmax;
+    if (!(tmax > 0.f)) { best.t = INFINITY; return best; }
+    float ix = clamp_idir(d.x), iy = clamp_idir(d.y), iz = clamp_idir(d.z);
+    float ox = o.x, oy = o.y, oz = o.z;
+    if (FMA_SLAB) {
+        ix = fminf(fmaxf(ix, -1e30f), 1e30f); iy = fminf(fmaxf(iy, -1e30f), 1e30f); iz = fminf(fmaxf(iz, -1e30f), 1e30f);
+        ox = o.x * ix; oy = o.y * iy; oz = o.z * iz;
+    }
+    int stack[STACK];
+    int sp = 0;
+    int node = 0, parked = 0;   // parked: a leaf code (< 0) waiting to be intersected, 0 = none
+    while (node != kTraverseDone) {
+        bool searching = true;
+        while (node >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+            float4 a, b, c, l;
+            if (LD256) { const F8 n0 = ldg256(np), n1 = ldg256(np + 2); a = n0.lo; b = n0.hi; c = n1.lo; l = n1.hi; }
+            else { a = ldg4(np); b = ldg4(np + 1); c = ldg4(np + 2); l = ldg4(np + 3); }
+            float t0, t1;
+#define PB_SLAB(lo, hi, oc, ic) if (FMA_SLAB) { t0 = fmaf(lo, ic, -oc); t1 = fmaf(hi, ic, -oc); } else { t0 = (lo - oc) * ic; t1 = (hi - oc) * ic; }
+            PB_SLAB(a.x, a.w, ox, ix)
+            float ln = fminf(t0, t1), lf = fmaxf(t0, t1);
+            PB_SLAB(a.y, b.x, oy, iy)
+            ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+            PB_SLAB(a.z, b.y, oz, iz)
+            ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
+            PB_SLAB(b.z, c.y, ox, ix)
+            float rn = fminf(t0, t1), rf = fmaxf(t0, t1);
+            PB_SLAB(b.w, c.z, oy, iy)
+            rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+            PB_SLAB(c.x, c.w, oz, iz)
+            rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
+#undef PB_SLAB
+            const bool hl = fmaxf(ln, 0.f) <= fminf(lf, best.t), hr = fmaxf(rn, 0.f) <= fminf(rf, best.t);
+            int cl = __float_as_int(l.x), cr = __float_as_int(l.y);
+            if (hl && hr) {
+                if (rn < ln) { int t = cl; cl = cr; cr = t; }
+                PB_PUSH(cr);
+                node = cl;
+            } else if (hl) node = cl;
+            else if (hr) node = cr;
+            else node = sp ? PB_POP() : kTraverseDone;
+            if (node < 0 && node != kTraverseDone && parked == 0) {   // first leaf: park it, keep descending
+                searching = false;
+                parked = node;
+                node = sp ? PB_POP() : kTraverseDone;
+            }
+            if (__ballot_sync(__activemask(), searching) == 0) break;
+        }
+        while (parked < 0) {
+            const int v = ~parked;
+            const int first = v >> 3, cnt = (v & 7) + 1;
+            for (int i = 0; i < cnt; ++i) {
+                const float4 *tp = reinterpret_cast<const float4 *>(leaf + first + i);
+                float4 ta, tb, tc;
+                if (LD256) { const F8 t01 = ldg256(tp); ta = t01.lo; tb = t01.hi; tc = ldg4(tp + 2); }
+                else { ta = ldg4(tp); tb = ldg4(tp + 1); tc = ldg4(tp + 2); }
+                const float3 p0 = f3(ta), e1 = f3(tb), e2 = f3(tc);
+                // unnormalised barycentrics with the oracle's op order; sign-only early outs (guarded against underflow of u, v)
+                const float3 h = cross(d, e2);
+                const float a = dot(e1, h);
+                const float3 sv = sub3_rn(o, p0);
+                const float U = dot(sv, h);
+                const bool guard = fabsf(a) <= 1e18f;
+                if (guard && U * a < 0.f && fabsf(U) >= 1e-20f) continue;
+                const float3 q = cross(sv, e1);
+                const float V = dot(d, q);
+                if (guard && V * a < 0.f && fabsf(V) >= 1e-20f) continue;
+                const float f = div_rn(1.f, a);
+                const float u = mul_rn(f, U), w = mul_rn(f, V), t = mul_rn(f, dot(e2, q));
+                const int id = __float_as_int(ta.w);
+                if (u >= 0.f && w >= 0.f && add_rn(u, w) <= 1.f && t > kRayEpsilon && t < tmax &&
+                    (t < best.t || (t == best.t && (best.tri < 0 || id < best.tri)))) {
+                    best.t = t; best.u = u; best.v = w; best.tri = id; best.shape = __float_as_int(tb.w);
+                }
+            }
+            if (best.t <= t_occ) { node = kTraverseDone; break; }   // occluded: nothing else matters
+            parked = 0;
+            if (node < 0 && node != kTraverseDone) { parked = node; node = sp ? PB_POP() : kTraverseDone; }
+        }
+    }
+    if (best.tri < 0) best.t = INFINITY;
+    return best;
+}
+#undef PB_PUSH
+#undef PB_POP
 
 // ---- shared-memory staged traversal ------------------------------------------------------------------------------------
 // ncu shows the per-thread kernels bound by L1 wavefronts: every lane fetches its own 64-byte node with four 16-byte loads,
