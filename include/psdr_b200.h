@@ -140,6 +140,11 @@ int pb_render_d_jvp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const f
  * fused raygen + primary-trace kernel — bench.py's gpu_launches and roofline inputs */
 int64_t pb_stats_launches(pb_ctx *ctx);
 float pb_stats_last_trace_ms(pb_ctx *ctx);
+/* Scene::configure after a vertex-only edit keeps the BVH topology and recomputes its boxes on the device (replaces the per-configure
+ * optixAccelBuild of include/psdr/scene/optix.h:277-340); after `max_consecutive_refits` refits (default 16; 0 = always rebuild) the
+ * binned-SAH build runs again. Results do not depend on it: the traversal returns the exact closest hit for any valid tree. */
+int pb_ctx_set_bvh_refit(pb_ctx *ctx, int max_consecutive_refits);
+int pb_stats_bvh(pb_ctx *ctx, int *full_builds, int *refits);
 int64_t pb_stats_last_rays(pb_ctx *ctx);
 int64_t pb_stats_last_active_rays(pb_ctx *ctx);                                         /* rays the traversal kernels traced (inactive lanes are compacted away) */
 int pb_stats_last_trace_launches(pb_ctx *ctx);

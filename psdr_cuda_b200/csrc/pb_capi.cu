@@ -317,9 +317,11 @@ static void configure(pb_ctx *c) {
     for (auto &m : c->meshes) { m.face_offset = total; total += m.nf; }
     c->num_tri = total;
     c->d_tri.reserve(std::max<size_t>(1, total) * sizeof(TriRec));
+    bool any_topo = false;
     auto preprocess = [&](size_t i) {
         HostMesh &m = c->meshes[i];
         if (m.topo_dirty) {
+            if (!(c->has_bound_mesh && i + 1 == c->meshes.size())) any_topo = true;   // the envmap's box is re-created every time with the same faces
             m.d_faces.upload(m.faces, st);
             m.d_csr_off.upload(m.csr_off, st);
             m.d_csr_face.upload(m.csr_face, st);
@@ -390,12 +392,40 @@ static void configure(pb_ctx *c) {
             }
         }
         if (total == 0) for (int k = 0; k < 3; ++k) { c->scene_lo[k] = 0.f; c->scene_hi[k] = 1.f; }
+        std::vector<int> sig;
+        for (const HostMesh &m : c->meshes) sig.push_back(m.nf);
+        const bool bvh4_wanted = (g_trace_variant == 8 || g_trace_variant == 9);
+        const bool can_refit = c->bvh_valid && !any_topo && sig == c->bvh_sig && c->bvh_refits < c->bvh_max_refits && !bvh4_wanted && total > 0;
+        if (can_refit) {
+            float extent = 0.f;
+            for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(c->scene_lo[k]), std::fabs(c->scene_hi[k])));
+            launch_build_leaf_tris(st, total, c->d_order.as<int>(), c->d_tri.as<TriRec>(), c->d_leaf.as<LeafTri>());
+            c->d_node_boxes.reserve((size_t)c->view.num_nodes * 12 * sizeof(float));
+            launch_bvh_refit(st, c->d_nodes.as<BvhNode>(), c->d_node_boxes.as<float>(), c->d_leaf.as<LeafTri>(), c->bvh_level_off.data(),
+                             (int)c->bvh_level_off.size() - 1, extent);
+            c->launches += 1 + (int64_t)c->bvh_level_off.size() - 1;
+            c->bvh_refits++; c->bvh_refit_count++;
+        } else {
         std::vector<float> geo(9 * (size_t)total);
         for (int t = 0; t < total; ++t)
             for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) geo[9 * (size_t)t + 3 * k + a] = c->h_tri[(size_t)t * 32 + 4 * k + a];
         std::vector<HostNode> nodes;
         std::vector<int> order;
         build_bvh(geo.data(), total, nodes, order);
+        {   // level ranges of the breadth-first numbering (for the refit); a numbering that is not level-contiguous disables it
+            std::vector<int> level(nodes.size(), 0);
+            bool ok = true;
+            for (size_t i = 0; i < nodes.size(); ++i)
+                for (int ch : {nodes[i].left, nodes[i].right})
+                    if (ch >= 0) { if (ch <= (int)i) ok = false; else level[ch] = level[i] + 1; }
+            for (size_t i = 1; i < nodes.size(); ++i) if (level[i] < level[i - 1]) ok = false;
+            c->bvh_level_off.clear();
+            if (ok) {
+                for (size_t i = 0; i < nodes.size(); ++i) if (i == 0 || level[i] != level[i - 1]) c->bvh_level_off.push_back((int)i);
+                c->bvh_level_off.push_back((int)nodes.size());
+            }
+            c->bvh_valid = ok; c->bvh_sig = sig; c->bvh_refits = 0; c->bvh_builds++;
+        }
         std::vector<BvhNode> dn(nodes.size());
         for (size_t i = 0; i < nodes.size(); ++i) {
             const HostNode &n = nodes[i];
@@ -407,7 +437,7 @@ static void configure(pb_ctx *c) {
             dn[i].d = make_float4(l, r, 0.f, 0.f);
         }
         c->d_nodes.upload(dn, st);
-        {
+        if (bvh4_wanted) {   // only the measured-not-faster BVH4 debug variants read it
             std::vector<HostNode4> n4;
             collapse_bvh4(nodes, n4);
             static_assert(sizeof(HostNode4) == sizeof(BvhNode4), "BVH4 node layout");
@@ -419,6 +449,7 @@ static void configure(pb_ctx *c) {
         else launch_build_leaf_tris(st, total, c->d_order.as<int>(), c->d_tri.as<TriRec>(), c->d_leaf.as<LeafTri>());
         c->launches += 1;
         c->view.num_nodes = (int)dn.size();
+        }
     }
     // emitters (scene.cpp:183-196, area.cpp:10-17; the envmap keeps its default weight 1, emitter.h:27)
     std::vector<EmitterRec> er(c->emitters.size());
@@ -1300,6 +1331,8 @@ int pb_debug_retained_rad(pb_ctx *c, void **d_rad, int64_t *bytes) {
         *d_rad = c->retained.rad.p; *bytes = (int64_t)c->retained.rad.bytes;
     });
 }
+int pb_ctx_set_bvh_refit(pb_ctx *c, int max_consecutive_refits) { c->bvh_max_refits = max_consecutive_refits; return 0; }
+int pb_stats_bvh(pb_ctx *c, int *builds, int *refits) { if (builds) *builds = c->bvh_builds; if (refits) *refits = c->bvh_refit_count; return 0; }
 int pb_ctx_set_retain_limit(pb_ctx *c, int64_t bytes) { c->retain_limit = bytes; c->retained_valid = false; return 0; }
 int pb_render_d_jvp(pb_ctx *c, const pb_integrator *I, int sensor, const float *d_tangent, float *d_dimage) {
     return guard(c, [&] {

@@ -89,6 +89,67 @@ __global__ void k_build_leaf_tris(int n, const int *__restrict__ order, const Tr
     leaf[i] = l;
 }
 
+// ---- BVH refit: same tree, new boxes ---------------------------------------------------------------------------------------
+// An optimisation loop moves vertices a little every iteration and calls Scene::configure() each time (examples/run_test.py:117),
+// where the reference rebuilds its OptiX GAS (optix.h:277-340). Here the binned-SAH build runs on the host (~50-90 ms for 70 k
+// triangles); when only vertex positions changed the tree topology is kept and the child boxes are recomputed on the device,
+// one launch per tree level from the deepest up (nodes are numbered breadth-first, so a level is a contiguous index range).
+// Boxes only have to be conservative: the traversal returns the exact closest hit whatever the tree looks like.
+// `boxes`: 12 floats per node, the unpadded child boxes (scratch, rewritten every refit); nodes get the padded ones
+// (same padding rule as pb_bvh.cpp pad_box).
+__global__ void k_bvh_refit_level(BvhNode *__restrict__ nodes, float *__restrict__ boxes, const LeafTri *__restrict__ leaf, int start, int end, float extent) {
+    const int i = start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    float4 *np = reinterpret_cast<float4 *>(nodes + i);
+    const float4 a = np[0], b = np[1], c = np[2], d = np[3];
+    const int link[2] = {__float_as_int(d.x), __float_as_int(d.y)};
+    float old_lo[2][3] = {{a.x, a.y, a.z}, {b.z, b.w, c.x}}, old_hi[2][3] = {{a.w, b.x, b.y}, {c.y, c.z, c.w}};
+    float lo[2][3], hi[2][3], plo[2][3], phi[2][3];
+    const float kFar = 3.402823466e+38f;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (old_lo[s][0] >= kFar) {   // unreachable child (pb_bvh.cpp): keep it
+            for (int k = 0; k < 3; ++k) { lo[s][k] = plo[s][k] = old_lo[s][k]; hi[s][k] = phi[s][k] = old_hi[s][k]; }
+            continue;
+        }
+        for (int k = 0; k < 3; ++k) { lo[s][k] = INFINITY; hi[s][k] = -INFINITY; }
+        if (link[s] < 0) {
+            const int v = ~link[s], first = v >> 3, cnt = (v & 7) + 1;
+            for (int t = 0; t < cnt; ++t) {
+                const LeafTri lt = leaf[first + t];
+                const float p0[3] = {lt.a.x, lt.a.y, lt.a.z}, e1[3] = {lt.b.x, lt.b.y, lt.b.z}, e2[3] = {lt.c.x, lt.c.y, lt.c.z};
+                for (int k = 0; k < 3; ++k) {
+                    const float v1 = __fadd_rn(p0[k], e1[k]), v2 = __fadd_rn(p0[k], e2[k]);
+                    lo[s][k] = fminf(lo[s][k], fminf(p0[k], fminf(v1, v2)));
+                    hi[s][k] = fmaxf(hi[s][k], fmaxf(p0[k], fmaxf(v1, v2)));
+                }
+            }
+        } else {
+            const float *cb = boxes + 12 * (size_t)link[s];   // the child's own two (unpadded) child boxes, written by the previous launch
+            for (int k = 0; k < 3; ++k) {
+                lo[s][k] = fminf(cb[k] >= kFar ? INFINITY : cb[k], cb[6 + k] >= kFar ? INFINITY : cb[6 + k]);
+                hi[s][k] = fmaxf(cb[k] >= kFar ? -INFINITY : cb[3 + k], cb[6 + k] >= kFar ? -INFINITY : cb[9 + k]);
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            const float pad = __fadd_rn(__fmul_rn(1e-4f, fmaxf(1.f, fmaxf(fabsf(lo[s][k]), fabsf(hi[s][k])))), __fmul_rn(2.5e-7f, extent));
+            plo[s][k] = lo[s][k] - pad; phi[s][k] = hi[s][k] + pad;
+        }
+    }
+    float *ob = boxes + 12 * (size_t)i;
+    for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) { ob[6 * s + k] = lo[s][k]; ob[6 * s + 3 + k] = hi[s][k]; }
+    np[0] = make_float4(plo[0][0], plo[0][1], plo[0][2], phi[0][0]);
+    np[1] = make_float4(phi[0][1], phi[0][2], plo[1][0], plo[1][1]);
+    np[2] = make_float4(plo[1][2], phi[1][0], phi[1][1], phi[1][2]);
+}
+
+void launch_bvh_refit(cudaStream_t st, BvhNode *nodes, float *boxes, const LeafTri *leaf, const int *level_off, int num_levels, float extent) {
+    for (int l = num_levels - 1; l >= 0; --l) {
+        const int start = level_off[l], end = level_off[l + 1];
+        if (end > start) k_bvh_refit_level<<<(end - start + 127) / 128, 128, 0, st>>>(nodes, boxes, leaf, start, end, extent);
+    }
+}
+
 // ---- backward of the mesh preprocessing (mesh.cpp:19-51, 215-231): triangle-table adjoint -> vertex adjoints -------------
 // csr_slot[k] = 3*face + corner for the k-th (vertex, incident face) pair, same order as the forward gather.
 

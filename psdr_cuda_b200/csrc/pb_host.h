@@ -156,6 +156,11 @@ struct pb_ctx {
     std::vector<pb::GradSegment> grad_segments;
     // stats
     int64_t launches = 0, last_rays = 0, last_active_rays = 0;
+    // BVH refit (vertex-only updates keep the tree and recompute its boxes on the device)
+    bool bvh_valid = false;
+    int bvh_max_refits = 16, bvh_refits = 0, bvh_builds = 0, bvh_refit_count = 0;
+    std::vector<int> bvh_sig, bvh_level_off;
+    pb::DevBuf d_node_boxes;
     float last_trace_ms = 0.f, last_primary_ms = 0.f;
     int last_trace_launches = 0;
     bool own_stream = true;

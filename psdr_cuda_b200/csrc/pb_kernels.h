@@ -53,6 +53,7 @@ void launch_mesh_backward(cudaStream_t st, int nv, int nf, int face_offset, cons
 void launch_mesh_tangent(cudaStream_t st, int nv, int nf, int face_offset, const float *vraw, const float *vraw_t, const Mat4 &to_world, const float *vworld,
                          const int *faces, const int *csr_off, const int *csr_face, const float4 *fcross, float *vworld_t, float4 *fcross_t, float *vnormal_t,
                          float *tri_tangent);
+void launch_bvh_refit(cudaStream_t st, BvhNode *nodes, float *boxes, const LeafTri *leaf, const int *level_off, int num_levels, float extent);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_trace_blocks_per_sm;
