@@ -224,3 +224,58 @@ def test_roughconductor_and_envmap_leaves_through_the_module(psdr_cuda):
     sc.configure()
     img2 = integ.renderC(sc, 0)
     assert abs(float(img2.mean()) / float(integ.renderC(sc, 0).mean()) - 1.0) < 0.2 and float(img2.mean()) < 0.75 * float(img.detach().mean())
+
+
+@pytest.mark.gpu
+def test_inverse_rendering_loop_recovers_albedo_and_translation(psdr_cuda):
+    """The use the module exists for (docs/inverse_diff_render.rst:48-79, examples/utils/adam.py): gradient descent through
+    renderD on a material parameter and on a mesh transform (boundary terms on, BVH refit between iterations)."""
+    torch = pytest.importorskip("torch")
+
+    def scene(spp, sppe, sppse):
+        sc = psdr_cuda.Scene()
+        sc.load_file(scene_path("cbox_bunny"), False)
+        sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse = 64, 64, spp, sppe, sppse
+        return sc
+
+    integ = psdr_cuda.DirectIntegrator(1, 1)
+    # target: the fixture as it is
+    ref = scene(32, 0, 0); ref.configure()
+    target = integ.renderC(ref, 0).clone()
+
+    # (1) red wall albedo from a wrong start
+    sc = scene(16, 0, 0)
+    albedo = sc.parameter("BSDF[id=red]", "reflectance")
+    truth = albedo.detach().clone()
+    with torch.no_grad():
+        albedo.copy_(torch.tensor([0.3, 0.6, 0.6], device=albedo.device).view_as(albedo))
+    opt = torch.optim.Adam([albedo], lr=0.05)
+    err0 = float((albedo.detach() - truth).abs().max())
+    for it in range(40):
+        sc.configure()
+        opt.zero_grad()
+        loss = (integ.renderD(sc, 0) - target).square().mean()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            albedo.clamp_(0.0, 1.0)
+    assert float((albedo.detach() - truth).abs().max()) < 0.25 * err0
+
+    # (2) bunny translated along x: recover the offset through the primary / secondary boundary terms
+    sc = scene(8, 8, 8)
+    T = sc.parameter("Mesh[1]", "to_world_left")
+    with torch.no_grad():
+        T[0, 3] = 12.0
+    opt = torch.optim.Adam([T], lr=1.0)
+    losses = []
+    for it in range(30):
+        sc.configure()
+        opt.zero_grad()
+        loss = (integ.renderD(sc, 0) - target).square().mean()
+        loss.backward()
+        with torch.no_grad():   # a translation along x is the only degree of freedom of this test
+            g = T.grad[0, 3].clone(); T.grad.zero_(); T.grad[0, 3] = g
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert abs(float(T[0, 3])) < 4.0, (float(T[0, 3]), losses[0], losses[-1])
+    assert losses[-1] < 0.85 * losses[0]   # the rest is Monte-Carlo noise of 8 spp against the 32 spp target
