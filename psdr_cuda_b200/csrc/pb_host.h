@@ -132,7 +132,15 @@ struct pb_ctx {
     // configured device tables
     bool ready = false;
     int num_tri = 0;
-    pb::DevBuf d_tri, d_leaf, d_nodes, d_nodes4, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
+    // triangle table | BVH nodes | leaf triangles live in ONE allocation so that a single L2 access-policy window can keep the
+    // randomly gathered scene data resident while the wavefront streams through (pb_capi.cu: set_l2_window)
+    pb::DevBuf d_scene_arena;
+    size_t arena_tri_bytes = 0, arena_node_bytes = 0, arena_used = 0;
+    pb::TriRec *arena_tri() const { return d_scene_arena.as<pb::TriRec>(); }
+    pb::BvhNode *arena_nodes() const { return reinterpret_cast<pb::BvhNode *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes); }
+    pb::LeafTri *arena_leaf() const { return reinterpret_cast<pb::LeafTri *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes + arena_node_bytes); }
+    int l2_persist = 1;
+    pb::DevBuf d_nodes4, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
     std::vector<float> h_tri;   // host copy of the triangle table (BVH build, inspection)
     float emitter_sum = 0.f;
     pb::SceneView view;
