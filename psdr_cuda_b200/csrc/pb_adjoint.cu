@@ -91,7 +91,7 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, floa
 // final forward radiance (decides which channels integrator.cpp:87 zeroed).
 // RC ("extended" events): rough-conductor texture / geometry adjoints and the environment map's radiance / scale / direction
 // adjoints (separate instantiation so that the diffuse + area-light kernel keeps its registers)
-template <int MINB, bool PREFETCH, bool RC>
+template <int MINB, bool PREFETCH, bool RC, bool SIMPLE>
 __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
     const HitRec *__restrict__ hits = E.hits;
     __shared__ float s_acc[kMaxConstBsdf * 3];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         }
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
-            const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
+            const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, its, s3, v.active);
             bool a1 = v.active && bs.valid;
             const HitRec h1 = load_hit(hits + (size_t)j * P.n + i);
             const Its its1 = reconstruct_its(P.S, h1, its.p);
@@ -149,15 +149,15 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 float3 wo = its1.p - its.p;
                 wo = wo / its1.t;
                 const float3 wo_l = its.sh.to_local(wo);
-                const float3 f = bsdf_eval(v.bsdf, its, wo_l, true);
+                const float3 f = bsdf_eval<SIMPLE>(v.bsdf, its, wo_l, true);
                 const float G = fabsf(dot(its1.n, -wo)) / sqr(its1.t);
                 const float pdf0 = bs.pdf * G;
                 const float scale = G / pdf0;
                 float3 gval = f3(0.f);
                 if (a1) {
                     float weight = inv_nb;
-                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
-                    const float3 Le = emitter_Le(P.S, its1, true);
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true));
+                    const float3 Le = emitter_Le<SIMPLE>(P.S, its1, true);
                     L += Le * f * (scale * weight);
                     gval += gL * Le * (scale * weight);
                 }
@@ -165,21 +165,21 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gval, acc);
                 if (RC && a1 && env_on) {   // dLoss/dLe of this connection
                     float weight = inv_nb;
-                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true));
                     g_p += env_le_vjp(P.S, its1, its.p, gL * f * (scale * weight), geom_mode(P.S), env_scale_acc);
                 }
                 if (RC && rc_tex) {
-                    const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf(P.S, its.p, its1, true) : 0.f;
+                    const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true) : 0.f;
                     rc::TexGrad tg;
-                    rc::bsdf_branch_tex_grad(rtex, its.wi, wo_l, s3, G, p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le(P.S, its1, true) : f3(0.f),
+                    rc::bsdf_branch_tex_grad(rtex, its.wi, wo_l, s3, G, p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le<SIMPLE>(P.S, its1, true) : f3(0.f),
                                              cont ? gw : f3(0.f), tg);
                     rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
                 }
                 if (RC && geom_rc) {
-                    const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf(P.S, its.p, its1, true) : 0.f;
+                    const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true) : 0.f;
                     rc::GeomGrad gg;
                     if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, its1.p, its1.n, B.depth == 0, v.rd, false, square_to_uniform_disk_concentric(s3.x, s3.y),
-                                             p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le(P.S, its1, true) : f3(0.f), cont ? gw : f3(0.f), gg)) {
+                                             p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le<SIMPLE>(P.S, its1, true) : f3(0.f), cont ? gw : f3(0.f), gg)) {
                         g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
                         point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, gg.q, gg.nq, gg.c0);
                     }
@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                     float3 kk = f3(0.f);
                     if (a1) {
                         float weight = inv_nb;
-                        if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
-                        kk += gL * emitter_Le(P.S, its1, true) * weight;
+                        if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true));
+                        kk += gL * emitter_Le<SIMPLE>(P.S, its1, true) * weight;
                     }
                     if (cont) kk += gw;
                     const float gc = pdot(kk, rho) * kInvPi / pdf0;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         }
         for (int j = 0; j < B.nl; ++j) {
             const float2 s2 = rng.next_2d();
-            const PositionSample ps = sample_emitter_position(P.S, v.its.p, s2, v.active);
+            const PositionSample ps = sample_emitter_position<SIMPLE>(P.S, v.its.p, s2, v.active);
             bool a1 = v.active && ps.valid;
             float3 wo = ps.p - its.p;
             const float dist_sqr = squared_norm(wo);
@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
             if (a1) {
                 const float G = fabsf(dot(its1.n, -wo)) / dist_sqr;
                 const float3 wo_l = its.sh.to_local(wo);
-                const float3 f = bsdf_eval(v.bsdf, its, wo_l, true);
-                const float pdf1 = bsdf_pdf(v.bsdf, its, wo_l, true) * G;
+                const float3 f = bsdf_eval<SIMPLE>(v.bsdf, its, wo_l, true);
+                const float pdf1 = bsdf_pdf<SIMPLE>(v.bsdf, its, wo_l, true) * G;
                 float weight = inv_nl;
                 if (B.nb > 0) weight *= mis_weight(ps.pdf, pdf1);
-                const float3 Le = emitter_Le(P.S, its1, true);
+                const float3 Le = emitter_Le<SIMPLE>(P.S, its1, true);
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gL * Le * scale, acc);
@@ -319,12 +319,20 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI) {
     if (P.n <= 0) return;
     const unsigned g = nblk(P.n, 256);
-    if (B.rc_grad) { k_adjoint<1, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
+    if (B.rc_grad) { k_adjoint<1, false, true, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
+    if (P.S.simple && g_shade_simple) {
+        switch (g_shade_tune) {
+            case 4: k_adjoint<2, false, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+            case 5: k_adjoint<4, false, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+            default: k_adjoint<3, false, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        }
+        return;
+    }
     switch (g_shade_tune) {
-        case 1: k_adjoint<2, true, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        case 4: k_adjoint<2, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        case 5: k_adjoint<4, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        default: k_adjoint<3, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 1: k_adjoint<2, true, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 4: k_adjoint<2, false, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 5: k_adjoint<4, false, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        default: k_adjoint<3, false, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
     }
 }
 

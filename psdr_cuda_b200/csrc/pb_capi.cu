@@ -551,6 +551,8 @@ static void configure(pb_ctx *c) {
     V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
     V.emitter_env = c->emitter_env;
+    V.simple = (c->emitter_env < 0) ? 1 : 0;
+    for (const HostBsdf &hb : c->bsdfs) if (hb.type != PB_BSDF_DIFFUSE) V.simple = 0;
     V.tri_grad = nullptr;
     V.tri_tangent = nullptr; V.jvp_acc = nullptr; V.jvp_image = nullptr; V.jvp_channel = 0;
     configure_edges(c);
@@ -1344,6 +1346,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "trace_smem") == 0) pb::g_trace_smem = (int)value;
         else if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
         else if (std::strcmp(key, "shade_tune") == 0) pb::g_shade_tune = (int)value;
+        else if (std::strcmp(key, "shade_simple") == 0) pb::g_shade_simple = (int)value;
         else if (std::strcmp(key, "trace_ld256") == 0) pb::g_trace_ld256 = (int)value;
         else if (std::strcmp(key, "l2_persist") == 0) { c->l2_persist = (int)value; set_l2_window(c); }
         else if (std::strcmp(key, "trace_sstack") == 0) pb::g_trace_sstack = (int)value;

@@ -60,6 +60,7 @@ extern int g_trace_blocks_per_sm;
 extern int g_sort_mode;
 extern int g_trace_ld256;
 extern int g_trace_sstack;
+extern int g_shade_simple;   // debug: 0 = never use the diffuse + area-light instantiations
 extern int g_shade_tune;   // debug: k_resolve / k_adjoint variant (0 default)
 extern int g_trace_smem;
 extern int g_trace_smem_nodes;

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restr
 }
 
 // sample the connections of one scattering event and emit their rays (direct.cpp:69-76, 120-129)
+template <bool SIMPLE>
 __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, EventBuffers E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
@@ -220,13 +221,13 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
     Rng rng((uint64_t)global_lane(P, i, pix_unused), B.jump);
     for (int j = 0; j < B.nb; ++j) {
         const float3 s3 = rng.next_3d();
-        const BsdfSample bs = bsdf_sample(v.bsdf, v.its, s3, v.active);
+        const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, v.its, s3, v.active);
         const bool a1 = v.active && bs.valid;
         store_ray(rays_out + (size_t)j * P.n + i, v.its.p, v.its.sh.to_world(bs.wo), a1 ? INFINITY : -1.f);
     }
     for (int j = 0; j < B.nl; ++j) {
         const float2 s2 = rng.next_2d();
-        const PositionSample ps = sample_emitter_position(P.S, v.its.p, s2, v.active);
+        const PositionSample ps = sample_emitter_position<SIMPLE>(P.S, v.its.p, s2, v.active);
         const bool a1 = v.active && ps.valid;
         float3 wo = ps.p - v.its.p;
         const float dist = safe_sqrt(squared_norm(wo));
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
 }
 
 // direct.cpp:77-113 (BSDF-sampled connections) and 130-158 (emitter-sampled connections) for one scattering event
-template <int MINB, bool PREFETCH>
+template <int MINB, bool PREFETCH, bool SIMPLE>
 __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BounceParams B, EventBuffers E, float *__restrict__ film) {
     const HitRec *__restrict__ hits = E.hits;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
-            const BsdfSample bs = bsdf_sample(v.bsdf, its, s3, v.active);
+            const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, its, s3, v.active);
             bool a1 = v.active && bs.valid;
             const HitRec h1 = load_hit(hits + (size_t)j * P.n + i);
             const Its its1 = reconstruct_its(P.S, h1, its.p);
@@ -273,28 +274,28 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
                 if (B.ad) {   // direct.cpp:83-95
                     float3 wo = its1.p - its.p;
                     wo = wo / its1.t;
-                    bsdf_val = bsdf_eval(v.bsdf, its, its.sh.to_local(wo), true);
+                    bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, its.sh.to_local(wo), true);
                     const float G = fabsf(dot(its1.n, -wo)) / sqr(its1.t);
                     pdf0 = bs.pdf * G;
                     bsdf_val = bsdf_val * (G / pdf0);
                 } else {      // direct.cpp:96-106
                     const float3 d1 = its.sh.to_world(bs.wo);
-                    bsdf_val = bsdf_eval(v.bsdf, its, bs.wo, true);
+                    bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, bs.wo, true);
                     const float G = fabsf(dot(its1.n, -d1)) / sqr(its1.t);
                     pdf0 = bs.pdf * G;
                     bsdf_val = bsdf_val / bs.pdf;
                 }
                 if (a1) {
                     float weight = inv_nb;
-                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf(P.S, its.p, its1, true));
-                    L += emitter_Le(P.S, its1, true) * bsdf_val * weight;
+                    if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true));
+                    L += emitter_Le<SIMPLE>(P.S, its1, true) * bsdf_val * weight;
                 }
                 if (B.carry && j == 0 && cont) { w_cont = bsdf_val; has_cont = true; }
             }
         }
         for (int j = 0; j < B.nl; ++j) {
             const float2 s2 = rng.next_2d();
-            const PositionSample ps = sample_emitter_position(P.S, v.its.p, s2, v.active);
+            const PositionSample ps = sample_emitter_position<SIMPLE>(P.S, v.its.p, s2, v.active);
             bool a1 = v.active && ps.valid;
             float3 wo = ps.p - its.p;
             const float dist_sqr = squared_norm(wo);
@@ -306,17 +307,17 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             if (a1) {
                 const float G = fabsf(dot(its1.n, -wo)) / dist_sqr;
                 const float3 wo_local = its.sh.to_local(wo);
-                float3 bsdf_val = bsdf_eval(v.bsdf, its, wo_local, true);
-                const float pdf1 = bsdf_pdf(v.bsdf, its, wo_local, true) * G;
+                float3 bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, wo_local, true);
+                const float pdf1 = bsdf_pdf<SIMPLE>(v.bsdf, its, wo_local, true) * G;
                 bsdf_val = bsdf_val * (G / ps.pdf);
                 float weight = inv_nl;
                 if (B.nb > 0) weight *= mis_weight(ps.pdf, pdf1);
-                L += emitter_Le(P.S, its1, true) * bsdf_val * weight;
+                L += emitter_Le<SIMPLE>(P.S, its1, true) * bsdf_val * weight;
             }
         }
         float3 thr = f3(1.f), rad;
         if (B.depth == 0) {
-            rad = B.hide_emitters ? f3(0.f) : emitter_Le(P.S, its, its.valid);   // direct.cpp:51
+            rad = B.hide_emitters ? f3(0.f) : emitter_Le<SIMPLE>(P.S, its, its.valid);   // direct.cpp:51
         } else {
             thr = f3(ldg4(E.thr_in + i)); rad = f3(E.rad[i]);
         }
@@ -363,6 +364,7 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 
 int g_trace_blocks_per_sm = 8;
 int g_shade_tune = 0;
+int g_shade_simple = 1;
 int g_trace_variant = 7;   // 7: counting-sorted + compacted wavefront (pb_sort.cu) for render calls; pb_trace uses the speculative kernel   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out) {
     if (n <= 0) return;
@@ -390,16 +392,26 @@ void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0) {
     if (P.n > 0) k_primary<<<nblk(P.n, 128), 128, 0, st>>>(P, hit0);
 }
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E) {
-    if (P.n > 0) k_shade<<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
+    if (P.n <= 0) return;
+    if (P.S.simple && g_shade_simple) k_shade<true><<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
+    else k_shade<false><<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
 }
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film) {
     if (P.n <= 0) return;
     const unsigned g = nblk(P.n, 256);
+    if (P.S.simple && g_shade_simple) {   // diffuse BSDFs + area emitters only: the instantiation without rough-conductor / envmap code
+        switch (g_shade_tune) {
+            case 2: k_resolve<3, false, true><<<g, 256, 0, st>>>(P, B, E, film); break;
+            case 4: k_resolve<2, false, true><<<g, 256, 0, st>>>(P, B, E, film); break;
+            default: k_resolve<4, false, true><<<g, 256, 0, st>>>(P, B, E, film); break;
+        }
+        return;
+    }
     switch (g_shade_tune) {   // debug: resident blocks per SM forced through the register cap / early prefetch of the connection hits
-        case 1: k_resolve<2, true><<<g, 256, 0, st>>>(P, B, E, film); break;    // + L1 prefetch of the connection hits: 27 % slower (L1 thrash)
-        case 2: k_resolve<3, false><<<g, 256, 0, st>>>(P, B, E, film); break;
-        case 4: k_resolve<2, false><<<g, 256, 0, st>>>(P, B, E, film); break;   // 127 registers, no spills, 25 % occupancy
-        default: k_resolve<4, false><<<g, 256, 0, st>>>(P, B, E, film); break;  // 64 registers + 360 B spills, 50 % occupancy: 5 % faster step
+        case 1: k_resolve<2, true, false><<<g, 256, 0, st>>>(P, B, E, film); break;    // + L1 prefetch of the connection hits: 27 % slower (L1 thrash)
+        case 2: k_resolve<3, false, false><<<g, 256, 0, st>>>(P, B, E, film); break;
+        case 4: k_resolve<2, false, false><<<g, 256, 0, st>>>(P, B, E, film); break;   // 127 registers, no spills, 25 % occupancy
+        default: k_resolve<4, false, false><<<g, 256, 0, st>>>(P, B, E, film); break;  // 64 registers + 360 B spills, 50 % occupancy: 5 % faster step
     }
 }
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film, float4 *rad_out) {

@@ -106,6 +106,7 @@ struct SceneView {
     float emitter_sum;
     int num_tri, num_nodes, num_meshes, num_bsdfs, num_emitters;
     int emitter_env;
+    int simple;             // 1: only diffuse BSDFs and area emitters (kernels use their instantiation without rough-conductor / envmap code)
     float *tri_grad;        // VJP only: kTriGradStride floats per triangle (adjoint of the triangle table), or nullptr
     // forward mode (JVP): the same adjoint kernels run once per colour channel with a unit seed; instead of scattering a
     // local gradient they dot it with the tangent of what it refers to and add the result to the lane's accumulator

@@ -220,11 +220,15 @@ PB_D const BsdfRec *its_bsdf(const SceneView &S, const Its &its) {
     return b >= 0 ? S.bsdfs + b : nullptr;
 }
 
+// SIMPLE (template flag of the shading functions and of the kernels that call them): the scene has only diffuse BSDFs and area
+// emitters — the host knows at configure — so the rough-conductor / environment-map code is compiled out of that instantiation
+// (it costs registers even when it never runs).
+template <bool SIMPLE = false>
 PB_D float3 bsdf_eval(const BsdfRec *b, const Its &its, float3 wo, bool active) {
     if (!active || !b) return f3(0.f);
     const float cos_i = its.wi.z, cos_o = wo.z;
     if (!(cos_i > 0.f && cos_o > 0.f)) return f3(0.f);
-    if (b->type == BSDF_DIFFUSE)   // diffuse.cpp:25-33
+    if (SIMPLE || b->type == BSDF_DIFFUSE)   // diffuse.cpp:25-33
         return tex_eval3(b->tex[TEX_REFLECTANCE], its.uv) * kInvPi * cos_o;
     // roughconductor.cpp:40-56
     const float au = tex_eval1(b->tex[TEX_ALPHA_U], its.uv), av = tex_eval1(b->tex[TEX_ALPHA_V], its.uv);
@@ -236,9 +240,10 @@ PB_D float3 bsdf_eval(const BsdfRec *b, const Its &its, float3 wo, bool active) 
     const float3 F = fresnel_conductor(tex_eval3(b->tex[TEX_ETA], its.uv), tex_eval3(b->tex[TEX_K], its.uv), dot(its.wi, H));
     return F * result * tex_eval3(b->tex[TEX_SPECULAR], its.uv);
 }
+template <bool SIMPLE = false>
 PB_D float bsdf_pdf(const BsdfRec *b, const Its &its, float3 wo, bool active) {
     if (!b) return 0.f;
-    if (b->type == BSDF_DIFFUSE) {   // diffuse.cpp:69-82
+    if (SIMPLE || b->type == BSDF_DIFFUSE) {   // diffuse.cpp:69-82
         if (!active || !(its.wi.z > 0.f && wo.z > 0.f)) return 0.f;
         return kInvPi * wo.z;
     }
@@ -248,11 +253,12 @@ PB_D float bsdf_pdf(const BsdfRec *b, const Its &its, float3 wo, bool active) {
     return ggx::eval(au, av, m) * ggx::smith_g1(au, av, its.wi, m) / (4.f * its.wi.z);
 }
 struct BsdfSample { float3 wo; float pdf; bool valid; };
+template <bool SIMPLE = false>
 PB_D BsdfSample bsdf_sample(const BsdfRec *b, const Its &its, float3 smp, bool active) {
     BsdfSample bs;
     bs.wo = f3(0.f); bs.pdf = 0.f; bs.valid = false;
     if (!b) return bs;
-    if (b->type == BSDF_DIFFUSE) {   // diffuse.cpp:47-55 — consumes tail<2>(sample)
+    if (SIMPLE || b->type == BSDF_DIFFUSE) {   // diffuse.cpp:47-55 — consumes tail<2>(sample)
         bs.wo = square_to_cosine_hemisphere(smp.y, smp.z);
         bs.pdf = kInvPi * bs.wo.z;
         bs.valid = active && its.wi.z > 0.f;
@@ -263,7 +269,7 @@ PB_D BsdfSample bsdf_sample(const BsdfRec *b, const Its &its, float3 smp, bool a
     const float3 m = ggx::sample(au, av, its.wi, smp.x, smp.y);
     const float two_dot = 2.f * dot(its.wi, m);
     bs.wo = f3(fmaf(m.x, two_dot, -its.wi.x), fmaf(m.y, two_dot, -its.wi.y), fmaf(m.z, two_dot, -its.wi.z));
-    bs.pdf = bsdf_pdf(b, its, bs.wo, active);
+    bs.pdf = bsdf_pdf<false>(b, its, bs.wo, active);
     bs.valid = active && its.wi.z > 0.f && bs.pdf != 0.f && bs.wo.z > 0.f;
     return bs;
 }
@@ -281,12 +287,13 @@ PB_D float3 env_eval_direction(const EmitterRec &em, float3 wi_world) {
     return tex_eval3(em.env_radiance, uv, false) * em.env_scale;
 }
 
+template <bool SIMPLE = false>
 PB_D float3 emitter_Le(const SceneView &S, const Its &its, bool active) {   // intersection.h:36-38
     if (!active || !its.valid) return f3(0.f);
     const int e = S.meshes[its.shape].emitter;
     if (e < 0) return f3(0.f);
     const EmitterRec &em = S.emitters[e];
-    if (em.type == EMITTER_AREA) return its.wi.z > 0.f ? em.radiance : f3(0.f);   // area.cpp:20-29
+    if (SIMPLE || em.type == EMITTER_AREA) return its.wi.z > 0.f ? em.radiance : f3(0.f);   // area.cpp:20-29
     return env_eval_direction(em, -its.sh.to_world(its.wi));                      // envmap.cpp:29-39
 }
 
@@ -305,13 +312,14 @@ PB_D void ray_intersect_scene_aabb(float3 o, float3 d, float3 lo, float3 hi, flo
 }
 
 struct PositionSample { float3 p, n; float pdf; int tri; float s, t; bool valid; };
+template <bool SIMPLE = false>
 PB_D PositionSample sample_emitter_position(const SceneView &S, float3 ref_p, float2 smp, bool active) {   // scene.cpp:427-447
     PositionSample r;
     int ei = 0;
     float emitter_pdf = 1.f;
     if (S.num_emitters > 1) ei = sample_reuse(S.emitter_cmf, S.emitter_pmf, S.num_emitters, S.emitter_sum, smp.y, emitter_pdf);
     const EmitterRec &em = S.emitters[ei];
-    if (em.type == EMITTER_AREA) {   // mesh.cpp:306-330
+    if (SIMPLE || em.type == EMITTER_AREA) {   // mesh.cpp:306-330
         float face_pdf;
         const int f = sample_reuse(em.face_cmf, em.face_pmf, em.num_faces, em.face_sum, smp.x, face_pdf);
         const float2 st = square_to_uniform_triangle(smp.x, smp.y);
@@ -343,12 +351,13 @@ PB_D PositionSample sample_emitter_position(const SceneView &S, float3 ref_p, fl
     r.valid = active;
     return r;
 }
+template <bool SIMPLE = false>
 PB_D float emitter_position_pdf(const SceneView &S, float3 ref_p, const Its &its, bool active) {   // scene.cpp:451-453
     if (!active || !its.valid) return 0.f;
     const MeshRec &m = S.meshes[its.shape];
     if (m.emitter < 0) return 0.f;
     const EmitterRec &em = S.emitters[m.emitter];
-    if (em.type == EMITTER_AREA) return em.sampling_weight * m.inv_total_area;   // area.cpp:58-62
+    if (SIMPLE || em.type == EMITTER_AREA) return em.sampling_weight * m.inv_total_area;   // area.cpp:58-62
     // envmap.cpp:125-143 (no sampling_weight factor)
     float3 d = its.p - ref_p;
     const float dist2 = squared_norm(d);
