@@ -91,7 +91,7 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, floa
 // final forward radiance (decides which channels integrator.cpp:87 zeroed).
 // RC ("extended" events): rough-conductor texture / geometry adjoints and the environment map's radiance / scale / direction
 // adjoints (separate instantiation so that the diffuse + area-light kernel keeps its registers)
-template <int MINB, bool PREFETCH, bool RC, bool SIMPLE>
+template <int MINB, bool PREFETCH, bool RC, bool SIMPLE, int EV>
 __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
     const HitRec *__restrict__ hits = E.hits;
     __shared__ float s_acc[kMaxConstBsdf * 3];
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         if (PREFETCH) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
         int pix;
         const long long lane = global_lane(P, i, pix);
-        const Vertex v = load_vertex(P, B, i, E);
+        const Vertex v = load_vertex<EV>(P, B, i, E);
         const Its &its = v.its;
         bsdf_id = v.bsdf ? (int)(v.bsdf - P.S.bsdfs) : -1;
         // loss adjoint of this lane's radiance
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         if (!isfinite(rad_final.y)) g.y = 0.f;
         if (!isfinite(rad_final.z)) g.z = 0.f;
         float3 T = f3(1.f);
-        if (B.depth > 0) T = f3(ldg4(E.thr_in + i));
+        if (!ev_depth0<EV>(B)) T = f3(ldg4(E.thr_in + i));
         const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
         const float3 gL = g * T, gw = gL * S_next;
         Rng rng((uint64_t)lane, B.jump);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
         const bool env_on = RC && P.S.emitter_env >= 0 && (env_wants_grad(P.S) || geom_mode(P.S));
-        if (RC && B.depth == 0 && !B.hide_emitters && env_on) env_le_vjp(P.S, its, v.ro, g, false, env_scale_acc);   // Le(x0), direct.cpp:51: the camera ray is a constant
+        if (RC && ev_depth0<EV>(B) && !B.hide_emitters && env_on) env_le_vjp(P.S, its, v.ro, g, false, env_scale_acc);   // Le(x0), direct.cpp:51: the camera ray is a constant
         rc::Tex rtex;
         bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
         float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 if (RC && geom_rc) {
                     const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true) : 0.f;
                     rc::GeomGrad gg;
-                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, its1.p, its1.n, B.depth == 0, v.rd, false, square_to_uniform_disk_concentric(s3.x, s3.y),
+                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, its1.p, its1.n, ev_depth0<EV>(B), v.rd, false, square_to_uniform_disk_concentric(s3.x, s3.y),
                                              p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le<SIMPLE>(P.S, its1, true) : f3(0.f), cont ? gw : f3(0.f), gg)) {
                         g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
                         point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, gg.q, gg.nq, gg.c0);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 }
                 if (RC && geom_rc) {
                     rc::GeomGrad gg;
-                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, ps.p, its1.n, B.depth == 0, v.rd, true, make_float2(0.f, 0.f), ps.pdf, B.nb > 0, inv_nl,
+                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, ps.p, its1.n, ev_depth0<EV>(B), v.rd, true, make_float2(0.f, 0.f), ps.pdf, B.nb > 0, inv_nl,
                                              gL * Le, f3(0.f), gg)) {
                         g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
                         if (ps.tri >= 0) point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, gg.q, f3(0.f), gg.c0);   // area-light sample + its Jacobian; envmap samples are detached
@@ -252,11 +252,11 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 }
             }
         }
-        if (B.depth > 0) {
+        if (!ev_depth0<EV>(B)) {
             const float3 Sk = L + w_cont * S_next;
             suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
         }
-        if (RC && geom_rc && B.depth > 0 && E.hit_prev && (g_a.x != 0.f || g_a.y != 0.f || g_a.z != 0.f) && finite3(g_a)) {
+        if (RC && geom_rc && !ev_depth0<EV>(B) && E.hit_prev && (g_a.x != 0.f || g_a.y != 0.f || g_a.z != 0.f) && finite3(g_a)) {
             // the previous vertex moves wi: chain into its triangle (path-space point, or the camera hit in solid-angle form)
             const HitRec hp = load_hit(E.hit_prev + i);
             if (hp.tri >= 0) {
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 float gu = 0.f, gv = 0.f;
                 if (t.flags & 1) tg.fn += g_shn;
                 else shading_normal_vjp(t.n0, t.n1, t.n2, v.h.u, v.h.v, g_shn, tg, gu, gv);
-                if (B.depth == 0) {   // solid-angle form: (u, v, t) come from the differentiable ray/triangle test, p = o + t d
+                if (ev_depth0<EV>(B)) {   // solid-angle form: (u, v, t) come from the differentiable ray/triangle test, p = o + t d
                     const RayTriGrad r = ray_intersect_triangle_vjp(t.p0, t.e1, t.e2, v.ro, v.rd, gu, gv, pdot(g_p, v.rd));
                     tg.p0 += r.p0; tg.e1 += r.e1; tg.e2 += r.e2;
                 } else {              // path-space form: barycentrics are frozen, the point rides the triangle
@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 const TexRef &t = P.S.bsdfs[bsdf_id].tex[TEX_REFLECTANCE];
                 if (t.grad && t.w == 1 && t.h == 1) jvp_add(P.S, acc.x * __ldg(t.grad) + acc.y * __ldg(t.grad + 1) + acc.z * __ldg(t.grad + 2));
             }
-            if (B.depth == 0) { global_lane(P, i, pix); total = P.S.jvp_acc[i]; }
+            if (ev_depth0<EV>(B)) { global_lane(P, i, pix); total = P.S.jvp_acc[i]; }
         }
-        if (B.depth == 0) film_accumulate1(P.S.jvp_image, pix, P.S.jvp_channel, total);
+        if (ev_depth0<EV>(B)) film_accumulate1(P.S.jvp_image, pix, P.S.jvp_channel, total);
         return;
     }
     flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
@@ -319,20 +319,18 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI) {
     if (P.n <= 0) return;
     const unsigned g = nblk(P.n, 256);
-    if (B.rc_grad) { k_adjoint<1, false, true, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
+    if (B.rc_grad) { k_adjoint<1, false, true, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
     if (P.S.simple && g_shade_simple) {
-        switch (g_shade_tune) {
-            case 4: k_adjoint<2, false, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-            case 5: k_adjoint<4, false, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-            default: k_adjoint<3, false, false, true><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        }
+        if (g_shade_tune == 6) k_adjoint<3, false, false, true, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
+        else if (B.depth == 0) k_adjoint<3, false, false, true, 3><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
+        else k_adjoint<3, false, false, true, 2><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
         return;
     }
     switch (g_shade_tune) {
-        case 1: k_adjoint<2, true, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        case 4: k_adjoint<2, false, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        case 5: k_adjoint<4, false, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
-        default: k_adjoint<3, false, false, false><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 1: k_adjoint<2, true, false, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 4: k_adjoint<2, false, false, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        case 5: k_adjoint<4, false, false, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
+        default: k_adjoint<3, false, false, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); break;
     }
 }
 

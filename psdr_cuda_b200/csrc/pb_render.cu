@@ -210,12 +210,12 @@ __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restr
 }
 
 // sample the connections of one scattering event and emit their rays (direct.cpp:69-76, 120-129)
-template <bool SIMPLE>
+template <bool SIMPLE, int EV>
 __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, EventBuffers E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     RayRec *__restrict__ rays_out = E.rays;
-    const Vertex v = load_vertex(P, B, i, E);
+    const Vertex v = load_vertex<EV>(P, B, i, E);
     E.pos[i] = make_float4(v.its.p.x, v.its.p.y, v.its.p.z, 0.f);
     int pix_unused;
     Rng rng((uint64_t)global_lane(P, i, pix_unused), B.jump);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
 }
 
 // direct.cpp:77-113 (BSDF-sampled connections) and 130-158 (emitter-sampled connections) for one scattering event
-template <int MINB, bool PREFETCH, bool SIMPLE>
+template <int MINB, bool PREFETCH, bool SIMPLE, int EV>
 __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BounceParams B, EventBuffers E, float *__restrict__ film) {
     const HitRec *__restrict__ hits = E.hits;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
     if (in_range) {
         if (PREFETCH) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
         const long long lane = global_lane(P, i, pix);
-        const Vertex v = load_vertex(P, B, i, E);
+        const Vertex v = load_vertex<EV>(P, B, i, E);
         const Its &its = v.its;
         Rng rng((uint64_t)lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             if (a1 || (B.carry && j == 0 && cont)) {
                 float3 bsdf_val;
                 float pdf0;
-                if (B.ad) {   // direct.cpp:83-95
+                if (ev_ad<EV>(B)) {   // direct.cpp:83-95
                     float3 wo = its1.p - its.p;
                     wo = wo / its1.t;
                     bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, its.sh.to_local(wo), true);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             }
         }
         float3 thr = f3(1.f), rad;
-        if (B.depth == 0) {
+        if (ev_depth0<EV>(B)) {
             rad = B.hide_emitters ? f3(0.f) : emitter_Le<SIMPLE>(P.S, its, its.valid);   // direct.cpp:51
         } else {
             thr = f3(ldg4(E.thr_in + i)); rad = f3(E.rad[i]);
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             // A path without a continuation is dead. A zero-throughput path contributes nothing either, but its deeper
             // events still enter the derivative w.r.t. whatever made the throughput zero (d(rho X)/d rho = X at rho = 0),
             // so it is only dropped by renderC.
-            const bool dead = !has_cont || (!B.ad && !(t2.x != 0.f || t2.y != 0.f || t2.z != 0.f));
+            const bool dead = !has_cont || (!ev_ad<EV>(B) && !(t2.x != 0.f || t2.y != 0.f || t2.z != 0.f));
             E.thr_out[i] = make_float4(t2.x, t2.y, t2.z, dead ? 1.f : 0.f);
         }
         if (E.rad) E.rad[i] = make_float4(rad.x, rad.y, rad.z, 0.f);
@@ -393,25 +393,45 @@ void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0) {
 }
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E) {
     if (P.n <= 0) return;
-    if (P.S.simple && g_shade_simple) k_shade<true><<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
-    else k_shade<false><<<nblk(P.n, 256), 256, 0, st>>>(P, B, E);
+    const unsigned g = nblk(P.n, 256);
+    if (P.S.simple && g_shade_simple) {
+        switch ((B.depth == 0 ? 1 : 0) | (B.ad ? 2 : 0)) {
+            case 0: k_shade<true, 0><<<g, 256, 0, st>>>(P, B, E); break;
+            case 1: k_shade<true, 1><<<g, 256, 0, st>>>(P, B, E); break;
+            case 2: k_shade<true, 2><<<g, 256, 0, st>>>(P, B, E); break;
+            default: k_shade<true, 3><<<g, 256, 0, st>>>(P, B, E); break;
+        }
+    } else k_shade<false, -1><<<g, 256, 0, st>>>(P, B, E);
 }
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film) {
     if (P.n <= 0) return;
     const unsigned g = nblk(P.n, 256);
     if (P.S.simple && g_shade_simple) {   // diffuse BSDFs + area emitters only: the instantiation without rough-conductor / envmap code
-        switch (g_shade_tune) {
-            case 2: k_resolve<3, false, true><<<g, 256, 0, st>>>(P, B, E, film); break;
-            case 4: k_resolve<2, false, true><<<g, 256, 0, st>>>(P, B, E, film); break;
-            default: k_resolve<4, false, true><<<g, 256, 0, st>>>(P, B, E, film); break;
+        const int ev = (B.depth == 0 ? 1 : 0) | (B.ad ? 2 : 0);
+        if (g_shade_tune == 6) {   // run-time event class (what the specialised instantiations are measured against)
+            k_resolve<4, false, true, -1><<<g, 256, 0, st>>>(P, B, E, film);
+        } else if (g_shade_tune == 2) {
+            switch (ev) {
+                case 0: k_resolve<3, false, true, 0><<<g, 256, 0, st>>>(P, B, E, film); break;
+                case 1: k_resolve<3, false, true, 1><<<g, 256, 0, st>>>(P, B, E, film); break;
+                case 2: k_resolve<3, false, true, 2><<<g, 256, 0, st>>>(P, B, E, film); break;
+                default: k_resolve<3, false, true, 3><<<g, 256, 0, st>>>(P, B, E, film); break;
+            }
+        } else {
+            switch (ev) {
+                case 0: k_resolve<4, false, true, 0><<<g, 256, 0, st>>>(P, B, E, film); break;
+                case 1: k_resolve<4, false, true, 1><<<g, 256, 0, st>>>(P, B, E, film); break;
+                case 2: k_resolve<4, false, true, 2><<<g, 256, 0, st>>>(P, B, E, film); break;
+                default: k_resolve<4, false, true, 3><<<g, 256, 0, st>>>(P, B, E, film); break;
+            }
         }
         return;
     }
     switch (g_shade_tune) {   // debug: resident blocks per SM forced through the register cap / early prefetch of the connection hits
-        case 1: k_resolve<2, true, false><<<g, 256, 0, st>>>(P, B, E, film); break;    // + L1 prefetch of the connection hits: 27 % slower (L1 thrash)
-        case 2: k_resolve<3, false, false><<<g, 256, 0, st>>>(P, B, E, film); break;
-        case 4: k_resolve<2, false, false><<<g, 256, 0, st>>>(P, B, E, film); break;   // 127 registers, no spills, 25 % occupancy
-        default: k_resolve<4, false, false><<<g, 256, 0, st>>>(P, B, E, film); break;  // 64 registers + 360 B spills, 50 % occupancy: 5 % faster step
+        case 1: k_resolve<2, true, false, -1><<<g, 256, 0, st>>>(P, B, E, film); break;    // + L1 prefetch of the connection hits: 27 % slower (L1 thrash)
+        case 2: k_resolve<3, false, false, -1><<<g, 256, 0, st>>>(P, B, E, film); break;
+        case 4: k_resolve<2, false, false, -1><<<g, 256, 0, st>>>(P, B, E, film); break;   // 127 registers, no spills, 25 % occupancy
+        default: k_resolve<4, false, false, -1><<<g, 256, 0, st>>>(P, B, E, film); break;  // 64 registers + 360 B spills, 50 % occupancy: 5 % faster step
     }
 }
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film, float4 *rad_out) {

@@ -49,11 +49,18 @@ PB_D void prefetch_event_hits(const SceneView &S, const HitRec *__restrict__ hit
     }
 }
 
+// EV (template int of the event kernels): -1 = read the event class from BounceParams at run time; otherwise bit 0 = first event
+// (camera vertex), bit 1 = the AD formulation — known at launch, so the instantiation drops the other class' code and registers
+// (the camera-ray regeneration of renderD's first event is the largest piece).
+template <int EV> PB_D bool ev_depth0(const BounceParams &B) { return EV < 0 ? B.depth == 0 : (EV & 1) != 0; }
+template <int EV> PB_D bool ev_ad(const BounceParams &B) { return EV < 0 ? B.ad != 0 : (EV & 2) != 0; }
+
+template <int EV = -1>
 PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, const EventBuffers &E) {
     const HitRec *hit_cur = E.hit_cur;
     Vertex v;
-    if (B.depth == 0) {
-        if (B.ad) {   // renderD: the camera hit is differentiated in solid-angle form (scene.cpp:355-376)
+    if (ev_depth0<EV>(B)) {
+        if (ev_ad<EV>(B)) {   // renderD: the camera hit is differentiated in solid-angle form (scene.cpp:355-376)
             int pix;
             const long long lane = global_lane(P, i, pix);
             Rng rng((uint64_t)lane, P.jump0);
