@@ -271,7 +271,7 @@ def run_ours(args):
 
 
 def ctx_batch_mb(args):
-    lanes = args.batch if args.batch else (1 << 24)
+    lanes = args.batch if args.batch else (1 << 25)
     return lanes * (16 + 2 * 2 * (32 + 16) + 2 * 32) / 1e6
 
 

@@ -50,7 +50,7 @@ int pb_ctx_create(int device, pb_ctx **out);
 int pb_ctx_destroy(pb_ctx *ctx);
 const char *pb_last_error(pb_ctx *ctx);            /* ctx may be NULL: message of the last failed pb_ctx_create */
 int pb_version(void);
-/* lanes per wavefront batch (multiple of 1024); 0 restores the default (2^24). Tiling replaces the reference's
+/* lanes per wavefront batch (multiple of 1024); 0 restores the default (2^25). Tiling replaces the reference's
  * "all W*H*spp lanes at once" (src/integrator/integrator.cpp:69-76). */
 int pb_ctx_set_batch(pb_ctx *ctx, int64_t lanes);
 /* multi-GPU: this context renders shard `rank` of `world`: samples [spp*rank/world, spp*(rank+1)/world) of every pixel

@@ -1074,7 +1074,7 @@ int pb_ctx_destroy(pb_ctx *c) {
 const char *pb_last_error(pb_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
 int pb_ctx_set_batch(pb_ctx *c, int64_t lanes) {
     return guard(c, [&] {
-        if (lanes <= 0) lanes = 1 << 24;
+        if (lanes <= 0) lanes = 1 << 25;
         PB_ASSERT_MSG(lanes % 1024 == 0, "batch must be a multiple of 1024 lanes");
         c->batch = lanes;
     });

@@ -125,7 +125,7 @@ struct pb_ctx {
     bool has_bound_mesh = false;   // the last mesh is the envmap's bounding box (scene.cpp:135-180)
     // sharding / tiling
     int rank = 0, world = 1;
-    int64_t batch = 1 << 24;   // 16 Mi lanes: large wavefronts sort into more coherent bins
+    int64_t batch = 1 << 25;   // 32 Mi lanes: large wavefronts sort into more coherent bins
     // samplers (scene.cpp:65-79): lane count the streams were seeded for and draws consumed so far
     int64_t sampler_count[3] = {0, 0, 0};
     uint64_t sampler_offset[3] = {0, 0, 0};
