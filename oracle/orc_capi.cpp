@@ -147,6 +147,14 @@ int orc_set_envmap_tangent(void *h, const float *radiance_t, float scale_t) {
 int orc_set_envmap_transform(void *h, const float *left) {
     return guard([&] { Scene &s = ((Handle *)h)->scene; s.emitters.at(s.emitter_env).env_left = mat16(left); });
 }
+/* forward-mode tangent of a sensor's to_world (Sensor.to_world is an AD leaf, src/psdr.cpp:220-224); null clears it */
+int orc_set_sensor_transform_tangent(void *h, int sensor, const float *tang) {
+    return guard([&] {
+        Sensor &c = ((Handle *)h)->scene.sensors.at(sensor);
+        c.has_t = tang != nullptr;
+        if (tang) c.to_world_t = mat16(tang);
+    });
+}
 int orc_add_sensor(void *h, float fov_x, float near_clip, float far_clip, const float *to_world) {
     Scene &s = ((Handle *)h)->scene;
     Sensor c;

@@ -152,6 +152,8 @@ class Scene(_h.Scene):
             value = getattr(obj, field)
         elif field == "scale":                              # EnvironmentMap.scale (src/psdr.cpp:237)
             value = np.float32(obj.scale)
+        elif field == "to_world":                           # Sensor.to_world (src/psdr.cpp:220-224)
+            value = obj.to_world
         else:
             value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
         t = torch.tensor(np.asarray(value), dtype=torch.float32, device="cuda:%d" % self._device, requires_grad=requires_grad)
@@ -168,6 +170,9 @@ class Scene(_h.Scene):
             elif field == "scale":
                 obj.scale = float(val)
                 obj.scale_requires_grad = bool(t.requires_grad)
+            elif field == "to_world":
+                obj.to_world = val.astype(np.float32)
+                obj.requires_grad = bool(t.requires_grad)
             elif field in ("to_world_left", "to_world_right"):
                 obj.set_transform(val.astype(np.float32), field == "to_world_left")
                 obj.requires_grad = bool(t.requires_grad) or obj.requires_grad   # the transform gradient is a contraction of the vertex gradient

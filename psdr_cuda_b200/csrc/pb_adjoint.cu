@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
         float3 g_p = f3(0.f), g_shn = f3(0.f);   // adjoints of this vertex' position and shading normal
         const bool env_on = RC && P.S.emitter_env >= 0 && (env_wants_grad(P.S) || geom_mode(P.S));
-        if (RC && ev_depth0<EV>(B) && !B.hide_emitters && env_on) env_le_vjp(P.S, its, v.ro, g, false, env_scale_acc);   // Le(x0), direct.cpp:51: the camera ray is a constant
+        float3 g_rd_env = f3(0.f);   // Le(x0), direct.cpp:51: its direction is the camera ray's, which only the sensor pose moves
+        if (RC && ev_depth0<EV>(B) && !B.hide_emitters && env_on)
+            env_le_vjp(P.S, its, v.ro, g, P.S.sensor_grad != nullptr, env_scale_acc, &g_rd_env);
         rc::Tex rtex;
         bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
         float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 if (RC && geom_rc) {
                     const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true) : 0.f;
                     rc::GeomGrad gg;
-                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, its1.p, its1.n, ev_depth0<EV>(B), v.rd, false, square_to_uniform_disk_concentric(s3.x, s3.y),
+                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, ev_depth0<EV>(B) ? v.rd : v.ro, its1.p, its1.n, ev_depth0<EV>(B), v.rd, false, square_to_uniform_disk_concentric(s3.x, s3.y),
                                              p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le<SIMPLE>(P.S, its1, true) : f3(0.f), cont ? gw : f3(0.f), gg)) {
                         g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
                         point_on_triangle_scatter(P.S, its1.tri, h1.u, h1.v, gg.q, gg.nq, gg.c0);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 }
                 if (RC && geom_rc) {
                     rc::GeomGrad gg;
-                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, v.ro, ps.p, its1.n, ev_depth0<EV>(B), v.rd, true, make_float2(0.f, 0.f), ps.pdf, B.nb > 0, inv_nl,
+                    if (rc::branch_geom_grad(rtex, its.p, its.sh.n, ev_depth0<EV>(B) ? v.rd : v.ro, ps.p, its1.n, ev_depth0<EV>(B), v.rd, true, make_float2(0.f, 0.f), ps.pdf, B.nb > 0, inv_nl,
                                              gL * Le, f3(0.f), gg)) {
                         g_p += gg.p; g_shn += gg.shn; g_a += gg.a;
                         if (ps.tri >= 0) point_on_triangle_scatter(P.S, ps.tri, ps.s, ps.t, gg.q, f3(0.f), gg.c0);   // area-light sample + its Jacobian; envmap samples are detached
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
             if (hp.tri >= 0) {
                 if (B.depth == 1) {
                     const TriFull t = load_tri_full(P.S, hp.tri);
-                    if (t.flags & 8) {
+                    if ((t.flags & 8) || P.S.sensor_grad) {
                         int pix0;
                         Rng rng0((uint64_t)global_lane(P, i, pix0), P.jump0);
                         const float2 jit = rng0.next_2d();
@@ -271,18 +273,26 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                         float3 o, d;
                         sample_primary_ray(P.cam, sx, sy, o, d);
                         const RayTriGrad r = ray_intersect_triangle_vjp(t.p0, t.e1, t.e2, o, d, 0.f, 0.f, pdot(g_a, d));
-                        TriGrad tg;
-                        tg.p0 = r.p0; tg.e1 = r.e1; tg.e2 = r.e2;
-                        tri_grad_scatter(P.S, hp.tri, tg);
+                        if (t.flags & 8) {
+                            TriGrad tg;
+                            tg.p0 = r.p0; tg.e1 = r.e1; tg.e2 = r.e2;
+                            tri_grad_scatter(P.S, hp.tri, tg);
+                        }
+                        if (P.S.sensor_grad) {   // the camera hit is o + t d
+                            const float jv = sensor_ray_adjoint(P.S, P.cam, sx, sy, r.o + g_a, r.d + g_a * norm(v.ro - o));
+                            if (P.S.tri_tangent) jvp_add(P.S, jv);
+                        }
                     }
                 } else {
                     point_on_triangle_scatter(P.S, hp.tri, hp.u, hp.v, g_a, f3(0.f), 0.f);
                 }
             }
         }
-        if (geom || (RC && geom_rc)) {   // chain the vertex adjoints into its triangle (scene.cpp:326-376)
+        const bool want_cam = RC && ev_depth0<EV>(B) && P.S.sensor_grad != nullptr && its.valid;
+        if (geom || (RC && geom_rc) || want_cam) {   // chain the vertex adjoints into its triangle (scene.cpp:326-376) and, at the camera vertex, into the sensor pose
             const TriFull t = load_tri_full(P.S, its.tri);
-            if (t.flags & 8) {
+            const bool want_tri = (t.flags & 8) != 0;
+            if (want_tri || want_cam) {
                 TriGrad tg;
                 float gu = 0.f, gv = 0.f;
                 if (t.flags & 1) tg.fn += g_shn;
@@ -290,10 +300,14 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 if (ev_depth0<EV>(B)) {   // solid-angle form: (u, v, t) come from the differentiable ray/triangle test, p = o + t d
                     const RayTriGrad r = ray_intersect_triangle_vjp(t.p0, t.e1, t.e2, v.ro, v.rd, gu, gv, pdot(g_p, v.rd));
                     tg.p0 += r.p0; tg.e1 += r.e1; tg.e2 += r.e2;
+                    if (want_cam) {
+                        const float jv = sensor_ray_adjoint(P.S, P.cam, v.film.x, v.film.y, r.o + g_p, r.d + g_p * its.t + g_a + g_rd_env);
+                        if (P.S.tri_tangent) jvp_add(P.S, jv);
+                    }
                 } else {              // path-space form: barycentrics are frozen, the point rides the triangle
                     tg.p0 += g_p; tg.e1 += g_p * v.h.u; tg.e2 += g_p * v.h.v;
                 }
-                tri_grad_scatter(P.S, its.tri, tg);
+                if (want_tri) tri_grad_scatter(P.S, its.tri, tg);
             }
         }
     }

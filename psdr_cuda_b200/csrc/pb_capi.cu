@@ -150,6 +150,7 @@ static void configure_sensor(HostSensor &s, int W, int H) {
     const Mat4h c2s = matmul(matmul(sc, tr), pe);
     const Mat4h s2c = inverse(c2s);
     const Mat4h w2s = matmul(c2s, inverse(s.to_world));
+    s.c2s = c2s;
     SensorRec &r = s.rec;
     r.sample_to_camera = to_dev(s2c);
     r.to_world = to_dev(s.to_world);
@@ -554,7 +555,7 @@ static void configure(pb_ctx *c) {
     V.simple = (c->emitter_env < 0) ? 1 : 0;
     for (const HostBsdf &hb : c->bsdfs) if (hb.type != PB_BSDF_DIFFUSE) V.simple = 0;
     V.tri_grad = nullptr;
-    V.tri_tangent = nullptr; V.jvp_acc = nullptr; V.jvp_image = nullptr; V.jvp_channel = 0;
+    V.tri_tangent = nullptr; V.jvp_acc = nullptr; V.jvp_image = nullptr; V.jvp_channel = 0; V.sensor_grad = nullptr;
     configure_edges(c);
     // gradient layout
     c->grad_segments.clear();
@@ -572,6 +573,8 @@ static void configure(pb_ctx *c) {
             c->grad_segments.push_back({PB_PARAM_MESH_VERTICES, (int)i, 0, off, n});
             off += n;
         }
+    for (size_t i = 0; i < c->sensors.size(); ++i)
+        if (c->sensors[i].requires_grad) { c->grad_segments.push_back({PB_PARAM_SENSOR_TRANSFORM, (int)i, 0, off, 16}); off += 16; }
     if (c->emitter_env >= 0) {
         const HostEmitter &e = c->emitters[c->emitter_env];
         if (e.env_radiance.requires_grad) {
@@ -636,9 +639,25 @@ static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t 
     for (int k = 0; k < nslots + 1; ++k) S.thr[k].reserve((size_t)lanes * sizeof(float4));
 }
 
-static bool any_geom_jvp(const pb_ctx *c) {
-    for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_MESH_VERTICES) return true;
+static bool any_geom_jvp(const pb_ctx *c) {   // anything that differentiates geometry (vertices or the sensor pose)
+    for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_MESH_VERTICES || g.kind == PB_PARAM_SENSOR_TRANSFORM) return true;
     return false;
+}
+// adjoint of to_world from the adjoint of world_to_sample = camera_to_sample * inverse(to_world):  g_M = -Minv^T (C^T g_W) Minv^T
+static void fold_w2s_adjoint(const HostSensor &s, const float *g_w2s, float *g_m_accum) {
+    const Mat4h Minv = inverse(s.to_world);
+    double CtG[16], tmp[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += (double)s.c2s.m[4 * k + i] * g_w2s[4 * k + j]; CtG[4 * i + j] = a; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += (double)Minv.m[4 * k + i] * CtG[4 * k + j]; tmp[4 * i + j] = a; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += tmp[4 * i + k] * (double)Minv.m[4 * j + k]; g_m_accum[4 * i + j] -= (float)a; }
+}
+// tangent of world_to_sample from the tangent of to_world:  W_t = -C Minv M_t Minv
+static void w2s_tangent(const HostSensor &s, const float *m_t, float *w_t) {
+    const Mat4h Minv = inverse(s.to_world);
+    double a1[16], a2[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += (double)Minv.m[4 * i + k] * m_t[4 * k + j]; a1[4 * i + j] = a; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += a1[4 * i + k] * (double)Minv.m[4 * k + j]; a2[4 * i + j] = a; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += (double)s.c2s.m[4 * i + k] * a2[4 * k + j]; w_t[4 * i + j] = -(float)a; }
 }
 
 // the three ray launches + evaluation of the secondary-edge estimator for one batch (direct.cpp:225-316)
@@ -885,7 +904,22 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             P.S.emitters = c->d_emitters_grad.as<EmitterRec>();
         }
         bool any_geom = false;
-        for (const GradSegment &g : c->grad_segments) any_geom = any_geom || g.kind == PB_PARAM_MESH_VERTICES;
+        for (const GradSegment &g : c->grad_segments) any_geom = any_geom || g.kind == PB_PARAM_MESH_VERTICES || g.kind == PB_PARAM_SENSOR_TRANSFORM;
+        for (const GradSegment &g : c->grad_segments)
+            if (g.kind == PB_PARAM_SENSOR_TRANSFORM && g.id == sensor) {   // pose of the sensor being rendered (other sensors get a zero gradient)
+                c->d_sensor_acc.reserve(32 * sizeof(float));
+                if (jvp) {   // tangents of to_world and of world_to_sample
+                    float h[32];
+                    PB_CUDA(cudaMemcpyAsync(h, d_grad + g.offset, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+                    PB_CUDA(cudaStreamSynchronize(st));
+                    w2s_tangent(c->sensors[sensor], h, h + 16);
+                    PB_CUDA(cudaMemcpyAsync(c->d_sensor_acc.p, h, sizeof(h), cudaMemcpyHostToDevice, st));
+                    PB_CUDA(cudaStreamSynchronize(st));
+                } else {
+                    PB_CUDA(cudaMemsetAsync(c->d_sensor_acc.p, 0, 32 * sizeof(float), st));
+                }
+                P.S.sensor_grad = c->d_sensor_acc.as<float>();
+            }
         if (any_geom) {
             c->d_tri_grad.reserve((size_t)std::max(1, c->num_tri) * kTriGradStride * sizeof(float));
             PB_CUDA(cudaMemsetAsync(c->d_tri_grad.p, 0, (size_t)std::max(1, c->num_tri) * kTriGradStride * sizeof(float), st));
@@ -930,6 +964,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 if (g.kind == PB_PARAM_BSDF_TEXTURE && c->bsdfs[g.id].type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
         if (mode == MODE_VJP && any_geom_jvp(c))   // geometry adjoints flow through every rough-conductor vertex on a path
             for (const HostBsdf &hb : c->bsdfs) if (hb.type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
+        if (mode == MODE_VJP)
+            for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_SENSOR_TRANSFORM) Bp.rc_grad = 1;   // the pose adjoint lives in the extended kernel
         if (mode == MODE_VJP && c->emitter_env >= 0) {   // environment map: radiance / scale gradients, and its direction term in the geometry adjoints
             const HostEmitter &he = c->emitters[c->emitter_env];
             if (he.env_radiance.requires_grad || he.env_scale_requires_grad || any_geom_jvp(c)) Bp.rc_grad = 1;
@@ -985,6 +1021,19 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         }
     }
     if (mode == MODE_VJP && (P.S.tri_grad || (jvp && any_geom_jvp(c)))) run_edge_terms(c, I, sensor, plan, P, d_dLdI, &nev_edge);
+    if (mode == MODE_VJP && !jvp && P.S.sensor_grad) {   // fold the world_to_sample adjoint into the to_world adjoint and add it to the gradient vector
+        float h[32], cur[16];
+        PB_CUDA(cudaMemcpyAsync(h, c->d_sensor_acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        for (const GradSegment &g : c->grad_segments)
+            if (g.kind == PB_PARAM_SENSOR_TRANSFORM && g.id == sensor) {
+                PB_CUDA(cudaMemcpyAsync(cur, d_grad + g.offset, sizeof(cur), cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+                fold_w2s_adjoint(c->sensors[sensor], h + 16, h);
+                for (int k = 0; k < 16; ++k) cur[k] += h[k];
+                PB_CUDA(cudaMemcpyAsync(d_grad + g.offset, cur, sizeof(cur), cudaMemcpyHostToDevice, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+            }
+    }
     if (mode == MODE_VJP && P.S.tri_grad) {   // triangle-table adjoint -> object-space vertex gradients (mesh.cpp:19-51,215-231 backward)
         for (const GradSegment &g : c->grad_segments)
             if (g.kind == PB_PARAM_MESH_VERTICES) {
@@ -1306,6 +1355,9 @@ int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
         } else if (kind == PB_PARAM_MESH_VERTICES) {
             PB_ASSERT_MSG(id >= 0 && id < (int)c->meshes.size(), "Invalid mesh id");
             c->meshes[id].requires_grad = enable != 0;
+        } else if (kind == PB_PARAM_SENSOR_TRANSFORM) {
+            PB_ASSERT_MSG(id >= 0 && id < (int)c->sensors.size(), "Invalid sensor id");
+            c->sensors[id].requires_grad = enable != 0;
         } else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE) {
             PB_ASSERT_MSG(c->emitter_env >= 0, "The scene has no environment map");
             if (kind == PB_PARAM_ENVMAP_RADIANCE) c->emitters[c->emitter_env].env_radiance.requires_grad = enable != 0;

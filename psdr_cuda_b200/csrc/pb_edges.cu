@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k_edge_primary_grad(RenderParams P, EdgeP
     const PrimEdgeSample es = sample_primary_edge(Q, P.cam, rng.next_1d());
     if (es.idx < 0) return;
     float *gworld = Q.mesh_gworld[es.rec.mesh];
-    if (!gworld) return;
+    if (!gworld && !P.S.sensor_grad) return;
     const float3 delta = f3(rad_n[i]) - f3(rad_p[i]);
     const bool jvp = P.S.tri_tangent != nullptr;
     float w = 0.f;
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(256) k_edge_primary_grad(RenderParams P, EdgeP
         const float tw = M[12] * x.x + M[13] * x.y + M[14] * x.z + M[15];
         const float gt0 = gq[e][0] / tw, gt1 = gq[e][1] / tw, gt3 = -(gq[e][0] * qv[e][0] + gq[e][1] * qv[e][1]) / tw;
         const float3 gx = f3(M[0] * gt0 + M[4] * gt1 + M[12] * gt3, M[1] * gt0 + M[5] * gt1 + M[13] * gt3, M[2] * gt0 + M[6] * gt1 + M[14] * gt3);
-        jsum += vertex_adjoint(P.S, gworld, vid[e], gx);
+        if (gworld) jsum += vertex_adjoint(P.S, gworld, vid[e], gx);
+        jsum += sensor_projection_adjoint(P.S, x, gt0, gt1, gt3);
     }
     if (jvp && jsum != 0.f && isfinite(jsum)) atomicAdd(P.S.jvp_image + 3 * (size_t)es.idx + P.S.jvp_channel, jsum);
 }
@@ -317,11 +318,16 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
     {
         const float4 *q = reinterpret_cast<const float4 *>(P.S.tri + hc.tri);
         const float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2);
-        if (__float_as_int(q2.w) & 8) {
+        float jcam = 0.f;
+        if ((__float_as_int(q2.w) & 8) || P.S.sensor_grad) {
             const RayTriGrad rc = ray_intersect_triangle_vjp(f3(q0), f3(q1), f3(q2), cam_o, cam_d, 0.f, 0.f, pdot(g_x1, cam_d));
-            TriGrad g; g.p0 = rc.p0; g.e1 = rc.e1; g.e2 = rc.e2;
-            tri_grad_scatter(P.S, hc.tri, g);
+            if (__float_as_int(q2.w) & 8) {
+                TriGrad g; g.p0 = rc.p0; g.e1 = rc.e1; g.e2 = rc.e2;
+                tri_grad_scatter(P.S, hc.tri, g);
+            }
+            jcam = sensor_ray_adjoint(P.S, P.cam, sds.qx, sds.qy, rc.o + g_x1, rc.d + g_x1 * itc.t);   // the camera ray moves with the sensor pose
         }
+        if (jvp && jcam != 0.f) P.S.jvp_acc[i] += jcam;
     }
     // edge point p0 = (1-s) v0 + s v1
     float *gworld = Q.mesh_gworld[bss.info.mesh];

@@ -18,7 +18,9 @@ PB_D bool env_wants_grad(const SceneView &S) {
 // gLe: dLoss/dLe (per channel). its1: the hit on the bounding mesh, seen from `origin`. Returns the adjoint of `origin`
 // (zero unless `want_dir`). The scale's gradient goes to the thread-private `scale_acc` (one address for every lane: the
 // kernel reduces it per block before touching global memory).
-PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float3 gLe, bool want_dir, float &scale_acc) {
+// `g_dir_out` (optional) receives the adjoint of the looked-up direction itself: the camera ray's direction d = M3 d_cam is not
+// re-normalised (perspective.cpp:120-127), so the sensor pose sees the unprojected adjoint.
+PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float3 gLe, bool want_dir, float &scale_acc, float3 *g_dir_out = nullptr) {
     float3 g_origin = f3(0.f);
     if (!its1.valid || !finite3(gLe) || (gLe.x == 0.f && gLe.y == 0.f && gLe.z == 0.f)) return g_origin;
     const int e = S.meshes[its1.shape].emitter;
@@ -79,6 +81,7 @@ PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float
         const Mat4 &M = em.env_from_world;
         const float3 g_dw = f3(M.m[0] * gvec.x + M.m[4] * gvec.y + M.m[8] * gvec.z, M.m[1] * gvec.x + M.m[5] * gvec.y + M.m[9] * gvec.z,
                                M.m[2] * gvec.x + M.m[6] * gvec.y + M.m[10] * gvec.z);
+        if (g_dir_out && finite3(g_dw)) *g_dir_out = g_dw;
         const float3 g_dv = normalize_vjp(its1.p - origin, g_dw);   // dw = (q - p)/|q - p|
         if (finite3(g_dv)) g_origin = -g_dv;
     }

@@ -89,6 +89,8 @@ struct HostEmitter {
 struct HostSensor {
     float fov_x = 45.f, near_clip = 0.1f, far_clip = 1e4f;
     Mat4h to_world = Mat4h::identity();
+    bool requires_grad = false;   // Sensor.to_world is a differentiable leaf
+    Mat4h c2s = Mat4h::identity();   // camera_to_sample (perspective.cpp:14-17), kept for the pose adjoint
     SensorRec rec;
     // primary-edge list (perspective.cpp:39-111)
     int num_prim = 0;
@@ -145,7 +147,7 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad, d_sensor_acc;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms

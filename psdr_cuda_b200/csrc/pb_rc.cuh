@@ -160,7 +160,8 @@ PB_D void light_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float G_ge
 
 // ---- geometry: local gradient of one connection w.r.t. the points and normals it is built from ----------------------------------
 // inputs x[15] = (p, sh_n, a, q, n_q): the shaded point and its shading normal, the origin `a` of the ray that found it
-// (scene.cpp:343-349: wi = to_local(-(p - a)/|p - a|); at the camera vertex wi = to_local(-ray.d), scene.cpp:368), the far end
+// (scene.cpp:343-349: wi = to_local(-(p - a)/|p - a|); at the camera vertex `a` is the ray direction, wi = to_local(-ray.d),
+// scene.cpp:368, whose adjoint only matters for the sensor pose), the far end
 // q of the connection and the geometric normal there. value = f(wi, wo) * G / pdf * (Le weight + S_next) as in direct.cpp:83-113 /
 // 133-158; the Jacobian J = A/detach(A) of q multiplies it (value 1), so its adjoint is the value itself.
 template <class T> struct FrameT {   // frame.h:9-52
@@ -190,7 +191,7 @@ PB_D Dual<N> branch_value(const Tex &t, const float *x, int seed0, bool primary,
     }
     const V3<D> p(in[0], in[1], in[2]), shn(in[3], in[4], in[5]), a(in[6], in[7], in[8]), q(in[9], in[10], in[11]), nq(in[12], in[13], in[14]);
     const FrameT<D> fr(shn);
-    const V3<D> wi = primary ? fr.to_local(V3<D>(-rd)) : fr.to_local(-vnormalize(p - a));
+    const V3<D> wi = primary ? fr.to_local(-a) : fr.to_local(-vnormalize(p - a));   // camera vertex: `a` is the ray direction
     const V3<D> dv = q - p;
     const D r2 = vdot(dv, dv);
     const V3<D> wo = dv / dsqrt(r2);
@@ -234,7 +235,7 @@ PB_D bool branch_geom_grad(const Tex &t, float3 p, float3 shn, float3 a, float3 
         for (int j = 0; j < 5; ++j) d[5 * chunk + j] = c.d[j];
     }
     if (!ok) return false;
-    g.p = f3(d[0], d[1], d[2]); g.shn = f3(d[3], d[4], d[5]); g.a = primary ? f3(0.f) : f3(d[6], d[7], d[8]);
+    g.p = f3(d[0], d[1], d[2]); g.shn = f3(d[3], d[4], d[5]); g.a = f3(d[6], d[7], d[8]);
     g.q = f3(d[9], d[10], d[11]); g.nq = f3(d[12], d[13], d[14]); g.c0 = c0;
     return true;
 }

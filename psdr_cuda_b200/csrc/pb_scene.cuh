@@ -114,6 +114,11 @@ struct SceneView {
     float *jvp_acc;             // one float per lane of the batch
     int jvp_channel;            // colour channel of this pass
     float *jvp_image;           // W*H*3 derivative image
+    // Sensor.to_world as a differentiable leaf (src/psdr.cpp:220-224): 32 floats or nullptr. Reverse mode: [0,16) accumulates the
+    // adjoint of to_world through the camera rays (o = M (0,0,0,1), d = M3 d_cam; perspective.cpp:120-136), [16,32) the adjoint of
+    // world_to_sample through the projected primary-edge end points (perspective.cpp:85-96); the host folds the second into the first.
+    // Forward mode: the tangents of the two matrices (read only).
+    float *sensor_grad;
 };
 
 enum { INTEG_DIRECT = 0, INTEG_FIELD = 1, INTEG_PATH = 2 };

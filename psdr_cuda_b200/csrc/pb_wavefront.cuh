@@ -5,6 +5,9 @@
 #include "pb_kernels.h"
 #include "pb_shade.cuh"
 
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
 namespace pb {
 
 // shard-local lane index -> (pixel, global lane id). A shard owns samples [s0, s0 + spp_local) of every pixel, so the
@@ -21,7 +24,7 @@ PB_D void lane_pixel_sample(const RenderParams &P, int pix, float2 jitter, float
     sy = div_rn(add_rn((float)y, jitter.y), (float)P.height);
 }
 
-struct Vertex { Its its; const BsdfRec *bsdf; bool active; HitRec h; float3 ro, rd; };
+struct Vertex { Its its; const BsdfRec *bsdf; bool active; HitRec h; float3 ro, rd; float2 film; };   // film: the camera ray's film sample (first event of renderD)
 
 PB_D HitRec load_hit(const HitRec *p) {
     const float4 h = ldg4(reinterpret_cast<const float4 *>(p));
@@ -70,7 +73,7 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
             float3 o, d;
             sample_primary_ray(P.cam, sx, sy, o, d);
             v.h = load_hit(hit_cur + i);
-            v.ro = o; v.rd = d;
+            v.ro = o; v.rd = d; v.film = make_float2(sx, sy);
             v.its = reconstruct_its_primary(P.S, v.h, o, d);
         } else {
             v.h = load_hit(hit_cur + i);
@@ -145,6 +148,49 @@ PB_D void film_accumulate1(float *img, int pix, int channel, float val) {
     }
     const int prev = __shfl_up_sync(full, pix, 1);
     if (pix >= 0 && (lane == 0 || prev != pix) && val != 0.f) atomicAdd(img + 3 * (size_t)pix + channel, val);
+}
+
+// ---- sensor pose adjoint ----------------------------------------------------------------------------------------------
+// Add `g[k]` to 16 consecutive floats at `dst` from whatever lanes of the warp are here together: coalesced-group reduction,
+// then one atomic per entry and group (every lane targets the same 16 addresses, per-lane atomics would serialise).
+PB_D void sensor_atomic_add16(float *dst, const float *g) {
+    namespace cg = cooperative_groups;
+    const cg::coalesced_group grp = cg::coalesced_threads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (!grp.any(g[k] != 0.f)) continue;
+        const float v = cg::reduce(grp, isfinite(g[k]) ? g[k] : 0.f, cg::plus<float>());
+        if (grp.thread_rank() == 0 && v != 0.f) atomicAdd(dst + k, v);
+    }
+}
+// adjoint (g_o, g_d) of a camera ray through film sample (sx, sy): o = M (0,0,0,1), d = M3 d_cam (perspective.cpp:120-136).
+// Reverse mode accumulates dL/dM, forward mode returns <dL/dM, tangent of M>.
+PB_D float sensor_ray_adjoint(const SceneView &S, const SensorRec &cam, float sx, float sy, float3 g_o, float3 g_d) {
+    if (!S.sensor_grad || !finite3(g_o) || !finite3(g_d)) return 0.f;
+    const float3 dc = normalize(transform_pos(cam.sample_to_camera, f3(sx, sy, 0.f)));
+    const float g[16] = {g_d.x * dc.x, g_d.x * dc.y, g_d.x * dc.z, g_o.x, g_d.y * dc.x, g_d.y * dc.y, g_d.y * dc.z, g_o.y,
+                         g_d.z * dc.x, g_d.z * dc.y, g_d.z * dc.z, g_o.z, 0.f, 0.f, 0.f, 0.f};
+    if (S.tri_tangent) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s = fmaf(g[k], __ldg(S.sensor_grad + k), s);
+        return s;
+    }
+    sensor_atomic_add16(S.sensor_grad, g);
+    return 0.f;
+}
+// adjoint of the homogeneous coordinates (g0, g1, g3 for rows 0, 1, 3) of world_to_sample (x, 1) (perspective.cpp:85-96)
+PB_D float sensor_projection_adjoint(const SceneView &S, float3 x, float g0, float g1, float g3) {
+    if (!S.sensor_grad || !isfinite(g0) || !isfinite(g1) || !isfinite(g3)) return 0.f;
+    const float g[16] = {g0 * x.x, g0 * x.y, g0 * x.z, g0, g1 * x.x, g1 * x.y, g1 * x.z, g1, 0.f, 0.f, 0.f, 0.f, g3 * x.x, g3 * x.y, g3 * x.z, g3};
+    if (S.tri_tangent) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s = fmaf(g[k], __ldg(S.sensor_grad + 16 + k), s);
+        return s;
+    }
+    sensor_atomic_add16(S.sensor_grad + 16, g);
+    return 0.f;
 }
 
 struct TriFull { float3 p0, e1, e2, n0, n1, n2, fn; float area; int flags; };

@@ -242,7 +242,7 @@ struct Mesh : Object {
 struct Sensor : Object {
     float fov_x = 45.f, near_clip = 0.1f, far_clip = 1e4f;
     Mat4 to_world;
-    bool dirty = false;
+    bool dirty = false, requires_grad = false;
     std::string type_name() const override { return "PerspectiveCamera"; }
 };
 struct Emitter : Object {};
@@ -478,6 +478,7 @@ public:
             uploaded = true;
         }
         for (auto &s : sensors) if (s->dirty) { check(pb_scene_set_sensor_transform(ctx, (int)(&s - &sensors[0]), s->to_world.m)); s->dirty = false; }
+        for (auto &s : sensors) check(pb_grad_require(ctx, PB_PARAM_SENSOR_TRANSFORM, (int)(&s - &sensors[0]), 0, s->requires_grad ? 1 : 0));
         for (auto &b : bsdfs) {
             if (auto *d = dynamic_cast<Diffuse *>(b.get())) push_bitmap(b->index, PB_TEX_REFLECTANCE, d->reflectance);
             else if (auto *r = dynamic_cast<RoughConductor *>(b.get())) {
@@ -517,6 +518,7 @@ public:
             int kind, id, slot; int64_t off, cnt;
             check(pb_grad_segment(ctx, i, &kind, &id, &slot, &off, &cnt));
             if (kind == PB_PARAM_BSDF_TEXTURE) out.append(py::make_tuple("BSDF[" + std::to_string(id) + "]", std::string(slots[slot]), off, cnt));
+            else if (kind == PB_PARAM_SENSOR_TRANSFORM) out.append(py::make_tuple("Sensor[" + std::to_string(id) + "]", std::string("to_world"), off, cnt));
             else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE)
                 out.append(py::make_tuple("Emitter[" + std::to_string(id) + "]", std::string(kind == PB_PARAM_ENVMAP_RADIANCE ? "radiance" : "scale"), off, cnt));
             else out.append(py::make_tuple("Mesh[" + std::to_string(id) + "]", std::string("vertex_positions"), off, cnt));
@@ -625,6 +627,7 @@ PYBIND11_MODULE(_psdr_host, m) {
 
     py::class_<Sensor, Object, std::shared_ptr<Sensor>>(m, "PerspectiveCamera")
         .def_property("to_world", [](const Sensor &s) { return mat_to_numpy(s.to_world); }, [](Sensor &s, const farray &a) { s.to_world = mat_from_numpy(a); s.dirty = true; })
+        .def_readwrite("requires_grad", &Sensor::requires_grad)
         .def_readonly("fov_x", &Sensor::fov_x).def_readonly("near_clip", &Sensor::near_clip).def_readonly("far_clip", &Sensor::far_clip);
 
     py::class_<Emitter, Object, std::shared_ptr<Emitter>>(m, "Emitter");

@@ -699,3 +699,64 @@ def test_bvh_refit_after_vertex_edits_gives_the_same_hits_and_images(desc):
     ctx.set_mesh_vertices(1, verts)
     ctx.configure()
     assert ctx.bvh_stats()["builds"] == 2
+
+
+# ---- Sensor.to_world as a differentiable leaf (a4 in its ad flavour: camera rays, projected primary edges, secondary-edge camera ray) ----
+def _sensor_grad_case(scene, opts, kind, kw, rtol=3e-3, smooth_weights=False):
+    from oracle import orc
+    from psdr_cuda_b200 import capi, scene_io
+    rng = np.random.default_rng(31)
+    pdesc = scene_io.load_scene_description(scene_path(scene))
+    odesc = orc.load_scene_description(scene_path(scene))
+    W, H = opts["width"], opts["height"]
+    dLdI = rng.uniform(-1, 1, size=(W * H, 3)).astype(np.float32)
+    if smooth_weights:
+        # The directly visible environment map dominates this derivative: every background lane carries a large term (HDR texel
+        # slopes x 1023 texels per turn) whose fp32 evaluation differs between CUDA's and libm's atan2 / acos at the 1e-4 level.
+        # Random-sign weights would compare the small net of those terms; smooth positive weights compare their sum.
+        yy, xx = np.mgrid[0:H, 0:W]
+        dLdI = (1.0 + 0.5 * np.sin(xx / W * 3.0 + 0.3)[..., None] * np.cos(yy / H * 2.0)[..., None] * np.array([1.0, 0.8, 0.6])).reshape(-1, 3).astype(np.float32)
+    ctx = capi.Context(0)
+    ctx.load_description(pdesc, opts)
+    ctx.grad_require(capi.PARAM_SENSOR_TRANSFORM, 0)
+    ctx.configure()
+    integ = capi.make_integrator(kind, **kw)
+    oi = orc.DirectIntegrator(kw.get("bsdf_samples", 1), kw.get("light_samples", 1)) if kind == "direct" else (
+        orc.PathIntegrator(kw["max_depth"]) if kind == "path" else orc.FieldExtractionIntegrator(kw["field"]))
+    ctx.render_d(integ)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64).reshape(4, 4)
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    # every affine entry of to_world against an oracle JVP with a unit tangent; the rotation block (through the ray direction) and
+    # the translation column (through the ray origin) differ by the scene scale, so each is compared to its own largest entry
+    ref = np.zeros((4, 4))
+    for i in range(3):
+        for j in range(4):
+            T = np.zeros((4, 4), np.float32); T[i, j] = 1
+            osc = orc.Scene(odesc, opts)
+            osc.set_sensor_transform_tangent(0, T)
+            osc.configure()
+            _, dimg = oi.renderD(osc)
+            ref[i, j] = float((dLdI.astype(np.float64) * dimg).sum())
+    assert np.all(np.abs(g[:3, :3] - ref[:3, :3]) <= rtol * np.abs(ref[:3, :3]).max()), (g, ref)
+    assert np.all(np.abs(g[:3, 3] - ref[:3, 3]) <= rtol * np.abs(ref[:3, 3]).max()), (g, ref)
+    # forward mode: <dLdI, J T> == <g, T>
+    T = rng.normal(size=(4, 4)).astype(np.float32); T[3, :] = 0
+    dimg = ctx.render_d_jvp(integ, torch.from_numpy(T.reshape(-1)).cuda()).cpu().numpy().astype(np.float64)
+    lhs, rhs = float((dimg * dLdI).sum()), float((g * T).sum())
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(rhs), 1e-6), (lhs, rhs)
+    ctx.close()
+
+
+def test_sensor_pose_gradient_interior():
+    o = dict(width=48, height=48, spp=8, sppe=0, sppse=0)
+    _sensor_grad_case("cbox_bunny", o, "direct", dict(bsdf_samples=1, light_samples=1))
+    _sensor_grad_case("cbox_bunny", o, "path", dict(max_depth=3))
+    _sensor_grad_case("cbox_bunny_rc", o, "path", dict(max_depth=3))            # wi of rough-conductor vertices moves with the camera ray
+    _sensor_grad_case("bunny_env", dict(width=40, height=40, spp=8, sppe=0, sppse=0), "direct", dict(bsdf_samples=1, light_samples=1), smooth_weights=True)   # + Le(x0) of the envmap
+
+
+def test_sensor_pose_gradient_boundary_terms():
+    _sensor_grad_case("bunny", dict(width=64, height=64, spp=0, sppe=16, sppse=0), "field", dict(field="silhouette"))
+    _sensor_grad_case("cbox_bunny", dict(width=48, height=48, spp=0, sppe=8, sppse=0), "direct", dict(bsdf_samples=1, light_samples=1))
+    _sensor_grad_case("cbox_bunny", dict(width=48, height=48, spp=0, sppe=0, sppse=32), "direct", dict(bsdf_samples=1, light_samples=1))
+    _sensor_grad_case("cbox_bunny", dict(width=48, height=48, spp=8, sppe=8, sppse=8), "path", dict(max_depth=2))

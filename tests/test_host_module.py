@@ -279,3 +279,29 @@ def test_inverse_rendering_loop_recovers_albedo_and_translation(psdr_cuda):
         losses.append(float(loss.detach()))
     assert abs(float(T[0, 3])) < 4.0, (float(T[0, 3]), losses[0], losses[-1])
     assert losses[-1] < 0.85 * losses[0]   # the rest is Monte-Carlo noise of 8 spp against the 32 spp target
+
+
+@pytest.mark.gpu
+def test_sensor_pose_leaf_through_the_module(psdr_cuda):
+    """Sensor.to_world as a torch leaf (src/psdr.cpp:220-224): backward through the module equals the ctypes VJP; a pose
+    optimisation step moves the image towards the target."""
+    torch = pytest.importorskip("torch")
+    from psdr_cuda_b200 import capi, scene_io
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path("cbox_bunny"), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse = 40, 40, 4, 4, 4
+    pose = sc.parameter("Sensor[0]", "to_world")
+    sc.configure()
+    integ = psdr_cuda.DirectIntegrator(1, 1)
+    img = integ.renderD(sc, 0)
+    w = torch.linspace(-1.0, 1.0, img.numel(), device=img.device).view_as(img)
+    (img * w).sum().backward()
+    assert pose.grad is not None and pose.grad.shape == (4, 4) and torch.isfinite(pose.grad).all() and pose.grad.abs().max() > 0
+    ctx = capi.Context(0)
+    ctx.load_description(scene_io.load_scene_description(scene_path("cbox_bunny")), dict(width=40, height=40, spp=4, sppe=4, sppse=4))
+    ctx.grad_require(capi.PARAM_SENSOR_TRANSFORM, 0)
+    ctx.configure()
+    ci = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+    assert torch.equal(img.detach(), ctx.render_d(ci))
+    g = ctx.render_d_vjp(ci, w.contiguous()).view(4, 4)
+    assert (pose.grad - g).norm() <= 1e-4 * g.norm()
