@@ -13,11 +13,11 @@
 namespace pb {
 namespace rc {
 
-template <class T> PB_D T ggx_eval(const T &au, const T &av, const V3<T> &m) {   // ggx.cpp:15-34
+template <class T> PB_HD T ggx_eval(const T &au, const T &av, const V3<T> &m) {   // ggx.cpp:15-34
     const T result = 1.f / ((au * av) * dsqr(dsqr(m.x / au) + dsqr(m.y / av) + dsqr(m.z)) * kPi);
     return val(result) * val(m.z) > 1e-5f ? result : T(0.f);
 }
-template <class T> PB_D T smith_g1(const T &au, const T &av, const V3<T> &v, const V3<T> &m) {   // ggx.cpp:79-93
+template <class T> PB_HD T smith_g1(const T &au, const T &av, const V3<T> &v, const V3<T> &m) {   // ggx.cpp:79-93
     const T xy_alpha_2 = dsqr(au * v.x) + dsqr(av * v.y);
     T result = 2.f / (1.f + dsqrt(1.f + xy_alpha_2 / dsqr(v.z)));
     if (val(xy_alpha_2) == 0.f) result = T(1.f);
@@ -25,7 +25,7 @@ template <class T> PB_D T smith_g1(const T &au, const T &av, const V3<T> &v, con
     return result;
 }
 // ggx.cpp:96-105; `p` is the concentric-disk image of the (constant) random numbers
-template <class T> PB_D void sample_visible_11(const T &cos_theta_i, float2 p, T &slope_x, T &slope_y) {
+template <class T> PB_HD void sample_visible_11(const T &cos_theta_i, float2 p, T &slope_x, T &slope_y) {
     const T s = (1.f + cos_theta_i) * .5f;
     const float a = safe_sqrt(1.f - sqr(p.x));
     const T py = a + s * (p.y - a);   // lerp(a, p.y, s)
@@ -35,7 +35,7 @@ template <class T> PB_D void sample_visible_11(const T &cos_theta_i, float2 p, T
     slope_x = (cos_theta_i * py - sin_theta_i * z) * nrm;
     slope_y = nrm * p.x;
 }
-template <class T> PB_D V3<T> ggx_sample(const T &au, const T &av, const V3<T> &wi, float2 disk) {   // ggx.cpp:37-76
+template <class T> PB_HD V3<T> ggx_sample(const T &au, const T &av, const V3<T> &wi, float2 disk) {   // ggx.cpp:37-76
     const V3<T> wi_p = vnormalize(V3<T>(au * wi.x, av * wi.y, wi.z));
     const T sin_theta_2 = dsqr(wi_p.x) + dsqr(wi_p.y);
     const bool degenerate = fabsf(val(sin_theta_2)) <= 4.f * kEpsilon;   // frame.h:103-117
@@ -50,7 +50,7 @@ template <class T> PB_D V3<T> ggx_sample(const T &au, const T &av, const V3<T> &
     const T slx = (cos_phi * sx - sin_phi * sy) * au, sly = (sin_phi * sx + cos_phi * sy) * av;
     return vnormalize(V3<T>(-slx, -sly, T(1.f)));
 }
-template <class T> PB_D T fresnel1(const T &eta_r, const T &eta_i, const T &cos_theta_i) {   // utils.h:149-164, one channel
+template <class T> PB_HD T fresnel1(const T &eta_r, const T &eta_i, const T &cos_theta_i) {   // utils.h:149-164, one channel
     const T c2 = dsqr(cos_theta_i), s2 = 1.f - c2, s4 = dsqr(s2);
     const T temp_1 = dsqr(eta_r) - dsqr(eta_i) - s2;
     const T a_2_pb_2 = dsafe_sqrt(dsqr(temp_1) + dsqr(eta_i * eta_r) * 4.f);
@@ -62,18 +62,18 @@ template <class T> PB_D T fresnel1(const T &eta_r, const T &eta_i, const T &cos_
     return (r_s + r_p) * .5f;
 }
 // D * G / (4 cos_i): the scalar part of RoughConductor::__eval (roughconductor.cpp:40-56), 0 outside its masks
-template <class T> PB_D T eval_scalar(const T &au, const T &av, const V3<T> &wi, const V3<T> &wo, const V3<T> &H) {
+template <class T> PB_HD T eval_scalar(const T &au, const T &av, const V3<T> &wi, const V3<T> &wo, const V3<T> &H) {
     if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return T(0.f);
     const T D = ggx_eval<T>(au, av, H);
     if (val(D) == 0.f) return T(0.f);
     return D * smith_g1<T>(au, av, wi, H) * smith_g1<T>(au, av, wo, H) / (wi.z * 4.f);
 }
-template <class T> PB_D T pdf(const T &au, const T &av, const V3<T> &wi, const V3<T> &wo) {   // roughconductor.cpp:60-75 (mask unused)
+template <class T> PB_HD T pdf(const T &au, const T &av, const V3<T> &wi, const V3<T> &wo) {   // roughconductor.cpp:60-75 (mask unused)
     const V3<T> m = vnormalize(wo + wi);
     return ggx_eval<T>(au, av, m) * smith_g1<T>(au, av, wi, m) / (wi.z * 4.f);
 }
 // pdf of the BSDF-sampled direction as a function of (alpha, wi): roughconductor.cpp:79-93
-template <class T> PB_D T sampled_pdf(const T &au, const T &av, const V3<T> &wi, float2 disk) {
+template <class T> PB_HD T sampled_pdf(const T &au, const T &av, const V3<T> &wi, float2 disk) {
     const V3<T> m = ggx_sample<T>(au, av, wi, disk);
     const T two_dot = vdot(wi, m) * 2.f;
     const V3<T> wo(m.x * two_dot - wi.x, m.y * two_dot - wi.y, m.z * two_dot - wi.z);
@@ -96,14 +96,14 @@ PB_D bool wants_tex_grad(const BsdfRec *b) {
 struct TexGrad {
     float au, av;
     float3 eta, k, spec;
-    PB_D TexGrad() : au(0.f), av(0.f), eta(f3(0.f)), k(f3(0.f)), spec(f3(0.f)) {}
-    PB_D bool finite() const { return isfinite(au) && isfinite(av) && finite3(eta) && finite3(k) && finite3(spec); }
-    PB_D void add(const TexGrad &o) { au += o.au; av += o.av; eta += o.eta; k += o.k; spec += o.spec; }
+    PB_HD TexGrad() : au(0.f), av(0.f), eta(f3(0.f)), k(f3(0.f)), spec(f3(0.f)) {}
+    PB_HD bool finite() const { return isfinite(au) && isfinite(av) && finite3(eta) && finite3(k) && finite3(spec); }
+    PB_HD void add(const TexGrad &o) { au += o.au; av += o.av; eta += o.eta; k += o.k; spec += o.spec; }
 };
 
 // Shared tail of both branches: value = sum_ch coef_ch(alpha) * spec_ch * F_ch(eta_ch, k_ch) with
 // coef_ch = base(alpha) * (wA(alpha) * gA_ch + gB_ch); base and wA are Dual<2> in (alpha_u, alpha_v).
-PB_D void finish_tex_grad(const Tex &t, float cos_h, const Dual<2> &base, const Dual<2> &wA, float3 gA, float3 gB, TexGrad &g) {
+PB_HD void finish_tex_grad(const Tex &t, float cos_h, const Dual<2> &base, const Dual<2> &wA, float3 gA, float3 gB, TexGrad &g) {
     typedef Dual<2> D2;
     float F[3], dF_eta[3], dF_k[3];
 #pragma unroll
@@ -131,7 +131,7 @@ PB_D void finish_tex_grad(const Tex &t, float cos_h, const Dual<2> &base, const 
 // BSDF-sampled connection (direct.cpp:67-113 with ad = true): value = f * G J / pdf0 * (Le weight [emitter hit] + S_next [continuation]),
 // pdf0 = bs.pdf * detach(G), weight = mis(pdf0, p_em) / nb. gA = dL/d(radiance) * T_k * Le (zero if the hit is no emitter),
 // gB = dL/d(radiance) * T_k * S_{k+1} (zero without continuation).
-PB_D void bsdf_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float3 s3, float G_geo, float p_em, bool use_mis, float inv_nb,
+PB_HD void bsdf_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float3 s3, float G_geo, float p_em, bool use_mis, float inv_nb,
                                float3 gA, float3 gB, TexGrad &g) {
     typedef Dual<2> D2;
     const D2 au = D2::seed(t.au, 0), av = D2::seed(t.av, 1);
@@ -146,7 +146,7 @@ PB_D void bsdf_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float3 s3, 
     finish_tex_grad(t, dot(wi, Hf), R * G_geo / pdf0, wA, gA, gB, g);
 }
 // emitter-sampled connection (direct.cpp:119-159): value = f * G J / ps.pdf * Le * mis(ps.pdf, pdf1 * detach(G)) / nl
-PB_D void light_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float G_geo, float ps_pdf, bool use_mis, float inv_nl, float3 gA, TexGrad &g) {
+PB_HD void light_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float G_geo, float ps_pdf, bool use_mis, float inv_nl, float3 gA, TexGrad &g) {
     typedef Dual<2> D2;
     const D2 au = D2::seed(t.au, 0), av = D2::seed(t.av, 1);
     const V3<D2> wi_d(wi), wo_d(wo_l);
@@ -166,7 +166,7 @@ PB_D void light_branch_tex_grad(const Tex &t, float3 wi, float3 wo_l, float G_ge
 // 133-158; the Jacobian J = A/detach(A) of q multiplies it (value 1), so its adjoint is the value itself.
 template <class T> struct FrameT {   // frame.h:9-52
     V3<T> s, t, n;
-    PB_D explicit FrameT(const V3<T> &v) : n(v) {
+    PB_HD explicit FrameT(const V3<T> &v) : n(v) {
         const float sg = copysignf(1.f, val(v.z));
         const bool neg = signbit(val(v.z));
         const T a = -1.f / (sg + v.z);
@@ -175,12 +175,12 @@ template <class T> struct FrameT {   // frame.h:9-52
         s = V3<T>((neg ? -sx : sx) + 1.f, neg ? -b : b, neg ? v.x : -v.x);
         t = V3<T>(b, sg + dsqr(v.y) * a, -v.y);
     }
-    PB_D V3<T> to_local(const V3<T> &v) const { return V3<T>(vdot(v, s), vdot(v, t), vdot(v, n)); }
+    PB_HD V3<T> to_local(const V3<T> &v) const { return V3<T>(vdot(v, s), vdot(v, t), vdot(v, n)); }
 };
 
 template <int N>
-PB_D Dual<N> branch_value(const Tex &t, const float *x, int seed0, bool primary, float3 rd, bool light, float2 disk, float p_other, bool use_mis,
-                          float inv_cnt, float3 gA, float3 gB) {
+PB_HD Dual<N> branch_value(const Tex &t, const float *x, int seed0, bool primary, float3 rd, bool light, float2 disk, float p_other, bool use_mis,
+                          float inv_cnt, float3 gA, float3 gB, float g_frozen = -1.f) {   // g_frozen: tests only — the detached G of pdf0 / pdf1 held at this value
     typedef Dual<N> D;
     D in[15];
 #pragma unroll
@@ -201,13 +201,14 @@ PB_D Dual<N> branch_value(const Tex &t, const float *x, int seed0, bool primary,
     const D R = eval_scalar<D>(au, av, wi, wo_l, H);
     if (R.v == 0.f) return D(0.f);
     const D G = dabs(vdot(nq, wo)) / r2;
+    const float G_det = g_frozen > 0.f ? g_frozen : G.v;   // detach(G_val), direct.cpp:93,147
     D wA(inv_cnt), base;
     if (!light) {   // pdf0 = bs.pdf * detach(G)
-        const D pdf0 = sampled_pdf<D>(au, av, wi, disk) * G.v;
+        const D pdf0 = sampled_pdf<D>(au, av, wi, disk) * G_det;
         if (use_mis) { const D w1 = dsqr(pdf0); wA = w1 / (w1 + sqr(p_other)) * inv_cnt; }
         base = R * G / pdf0;
     } else {        // pdf1 = bsdf.pdf * detach(G); p_other = ps.pdf
-        if (use_mis) { const D pdf1 = pdf<D>(au, av, wi, wo_l) * G.v; const float w1 = sqr(p_other); wA = w1 / (w1 + dsqr(pdf1)) * inv_cnt; }
+        if (use_mis) { const D pdf1 = pdf<D>(au, av, wi, wo_l) * G_det; const float w1 = sqr(p_other); wA = w1 / (w1 + dsqr(pdf1)) * inv_cnt; }
         base = R * G / p_other;
     }
     const D cos_h = vdot(wi, H);
@@ -220,7 +221,7 @@ PB_D Dual<N> branch_value(const Tex &t, const float *x, int seed0, bool primary,
 
 struct GeomGrad { float3 p, shn, a, q, nq; float c0; };
 // false: degenerate sample (non-finite derivative), nothing to add
-PB_D bool branch_geom_grad(const Tex &t, float3 p, float3 shn, float3 a, float3 q, float3 nq, bool primary, float3 rd, bool light, float2 disk,
+PB_HD bool branch_geom_grad(const Tex &t, float3 p, float3 shn, float3 a, float3 q, float3 nq, bool primary, float3 rd, bool light, float2 disk,
                            float p_other, bool use_mis, float inv_cnt, float3 gA, float3 gB, GeomGrad &g) {
     const float x[15] = {p.x, p.y, p.z, shn.x, shn.y, shn.z, a.x, a.y, a.z, q.x, q.y, q.z, nq.x, nq.y, nq.z};
     float d[15];

@@ -18,3 +18,16 @@ def test_adjoint_helpers_match_finite_differences(tmp_path):
                            os.path.join(ROOT, "tests", "native", "adjoint_check.cu")], stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "adjoint_check: ok" in out.stdout, out.stdout[-2000:]
+
+
+def test_roughconductor_dual_derivatives_match_finite_differences(tmp_path):
+    """csrc/pb_rc.cuh: the local forward-mode duals of a rough-conductor event (geometry inputs and BSDF parameters, BSDF- and
+    emitter-sampled connections, camera / path-space vertices, with and without MIS) against central differences."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "rc_dual_check")
+    subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "rc_dual_check.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "rc_dual_check: ok" in out.stdout, out.stdout[-2000:]

@@ -305,3 +305,38 @@ def test_sensor_pose_leaf_through_the_module(psdr_cuda):
     assert torch.equal(img.detach(), ctx.render_d(ci))
     g = ctx.render_d_vjp(ci, w.contiguous()).view(4, 4)
     assert (pose.grad - g).norm() <= 1e-4 * g.norm()
+
+
+def test_transform_gradient_contraction_matches_finite_differences(psdr_cuda):
+    """psdr_cuda.Scene._transform_gradient (CPU, torch): dL/d(to_world_left|right) from an object-space vertex gradient must be
+    the derivative of <g_world, world vertices> for world = L W R (x, 1) (mesh.cpp:223)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(0)
+
+    class FakeMesh:
+        to_world_left = (np.eye(4) + 0.1 * rng.normal(size=(4, 4))).astype(np.float32)
+        to_world_raw = (np.eye(4) + 0.1 * rng.normal(size=(4, 4))).astype(np.float32)
+        to_world_right = (np.eye(4) + 0.1 * rng.normal(size=(4, 4))).astype(np.float32)
+        vertex_positions = rng.normal(size=(7, 3)).astype(np.float32)
+    for m in (FakeMesh.to_world_left, FakeMesh.to_world_raw, FakeMesh.to_world_right):
+        m[3] = [0, 0, 0, 1]
+    g_world = rng.normal(size=(7, 3))
+
+    def world(L, R):
+        M = L.astype(np.float64) @ FakeMesh.to_world_raw.astype(np.float64) @ R.astype(np.float64)
+        x1 = np.concatenate([FakeMesh.vertex_positions.astype(np.float64), np.ones((7, 1))], axis=1)
+        return (x1 @ M.T)[:, :3]
+
+    M3 = (FakeMesh.to_world_left.astype(np.float64) @ FakeMesh.to_world_raw.astype(np.float64) @ FakeMesh.to_world_right.astype(np.float64))[:3, :3]
+    g_obj = torch.tensor(g_world @ M3)                      # what the renderer returns: g_obj = M3^T g_world per vertex
+    for left in (True, False):
+        g = psdr_cuda.Scene._transform_gradient(torch, FakeMesh, left, g_obj).double().numpy()
+        for (i, j) in ((0, 3), (1, 1), (2, 0), (0, 2)):
+            h = 1e-4
+            A = FakeMesh.to_world_left if left else FakeMesh.to_world_right
+            Ap, Am = A.astype(np.float64).copy(), A.astype(np.float64).copy()
+            Ap[i, j] += h; Am[i, j] -= h
+            wp = world(Ap, FakeMesh.to_world_right) if left else world(FakeMesh.to_world_left, Ap)
+            wm = world(Am, FakeMesh.to_world_right) if left else world(FakeMesh.to_world_left, Am)
+            fd = float((g_world * (wp - wm)).sum() / (2 * h))
+            assert abs(fd - g[i, j]) <= 1e-3 * max(1.0, abs(fd)), (left, i, j, fd, g[i, j])
