@@ -85,7 +85,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_sample(steps, warmup, w=96, h=96, spp=8):
+def oracle_sample(steps, warmup, w=256, h=256, spp=16):
     """Time the CPU oracle (port of the reference algorithm) on a bounded sample of the same workload."""
     from oracle import orc
     desc = orc.load_scene_description(SCENE)
