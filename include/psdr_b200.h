@@ -33,7 +33,8 @@ enum { PB_FIELD_SILHOUETTE = 0, PB_FIELD_POSITION, PB_FIELD_DEPTH, PB_FIELD_GEON
 /* mesh flags: Mesh::m_use_face_normals / m_enable_edges (include/psdr/shape/mesh.h) */
 enum { PB_MESH_FACE_NORMALS = 1, PB_MESH_ENABLE_EDGES = 2 };
 /* differentiable leaves: what a gradient segment refers to */
-enum { PB_PARAM_BSDF_TEXTURE = 0, PB_PARAM_MESH_VERTICES = 1, PB_PARAM_ENVMAP_RADIANCE = 2, PB_PARAM_ENVMAP_SCALE = 3, PB_PARAM_SENSOR_TRANSFORM = 4 /* Sensor.to_world, 16 floats row-major, id = sensor; src/psdr.cpp:220-224 */ };   /* EnvironmentMap.radiance.data / .scale, src/psdr.cpp:236-237 (id, slot ignored) */
+enum { PB_PARAM_BSDF_TEXTURE = 0, PB_PARAM_MESH_VERTICES = 1, PB_PARAM_ENVMAP_RADIANCE = 2, PB_PARAM_ENVMAP_SCALE = 3, PB_PARAM_SENSOR_TRANSFORM = 4 /* Sensor.to_world, 16 floats row-major, id = sensor; src/psdr.cpp:220-224 */,
+       PB_PARAM_ENVMAP_TRANSFORM = 5 /* the matrix EnvironmentMap.set_transform sets (to_world = left * raw), 16 floats; src/psdr.cpp:238 */ };   /* EnvironmentMap.radiance.data / .scale, src/psdr.cpp:236-237 (id, slot ignored) */
 
 typedef struct pb_integrator {
     int kind;           /* PB_INTEG_* */

@@ -354,6 +354,11 @@ class Scene:
         L.orc_set_sensor_transform_tangent.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _chk(L.orc_set_sensor_transform_tangent(self.h, sensor, _p(_f(tang)) if tang is not None else None))
 
+    def set_envmap_transform_tangent(self, tang):
+        L = lib()
+        L.orc_set_envmap_transform_tangent.argtypes = [C.c_void_p, C.c_void_p]
+        _chk(L.orc_set_envmap_transform_tangent(self.h, _p(_f(tang)) if tang is not None else None))
+
     def set_envmap_tangent(self, radiance_t=None, scale_t=0.0):
         L = lib()
         L.orc_set_envmap_tangent.argtypes = [C.c_void_p, C.c_void_p, C.c_float]

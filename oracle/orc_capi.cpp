@@ -144,6 +144,15 @@ int orc_set_envmap_tangent(void *h, const float *radiance_t, float scale_t) {
         e.env_scale_t = scale_t;
     });
 }
+/* forward-mode tangent of the matrix EnvironmentMap.set_transform sets (to_world = left * raw, envmap.cpp:23); null clears it */
+int orc_set_envmap_transform_tangent(void *h, const float *tang) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        Emitter &e = s.emitters.at(s.emitter_env);
+        e.env_has_t = tang != nullptr;
+        if (tang) e.env_left_t = mat16(tang);
+    });
+}
 int orc_set_envmap_transform(void *h, const float *left) {
     return guard([&] { Scene &s = ((Handle *)h)->scene; s.emitters.at(s.emitter_env).env_left = mat16(left); });
 }

@@ -66,8 +66,10 @@ struct Emitter {
     // envmap (envmap.h)
     Bitmap env_radiance;    // .tang: forward-mode tangent of the radiance texels (EnvironmentMap.radiance.data is an AD leaf, psdr.cpp:236)
     float env_scale = 1.f, env_scale_t = 0.f;   // scale and its tangent (psdr.cpp:237)
-    M4f env_to_world_raw, env_left;
+    M4f env_to_world_raw, env_left, env_left_t;   // env_left_t: forward-mode tangent of the matrix set by EnvironmentMap.set_transform (psdr.cpp:238)
+    bool env_has_t = false;
     M4f env_to_world, env_from_world;
+    M4<Dual> env_from_world_d;
     V3f lower, upper;
     HyperCube<2> env_distrb;
     std::vector<float> env_cell_lum;
@@ -404,7 +406,7 @@ inline V3f env_eval_direction(const Emitter &e, const V3f &wi_world) {   // envm
 // envmap.cpp:42-58 in its ad = true flavour: attached to the direction (through atan2 / acos and the bilinear weights), to the
 // radiance texels and to the scale. m_from_world is a constant here (the oracle does not parameterise the envmap transform).
 inline V3<Dual> env_eval_direction_d(const Emitter &e, const V3<Dual> &wi_world) {
-    V3<Dual> wi = transform_dir(M4<Dual>(e.env_from_world), wi_world);
+    V3<Dual> wi = transform_dir(e.env_from_world_d, wi_world);   // m_from_world is attached (envmap.cpp:46)
     V2<Dual> uv(atan2_(wi.x, -wi.z) * kInvTwoPi, safe_acos(wi.y) * kInvPi);
     uv.x = uv.x - floor_(uv.x); uv.y = uv.y - floor_(uv.y);
     V3<Dual> r = e.env_radiance.eval3<Dual>(uv, false);
@@ -426,6 +428,11 @@ inline void configure_envmap(Emitter &e) {   // envmap.cpp:10-26
     e.env_distrb.set_mass(mass);
     e.env_to_world = e.env_left * e.env_to_world_raw;
     e.env_from_world = inverse(e.env_to_world);
+    {
+        M4<Dual> left_d(e.env_left);
+        if (e.env_has_t) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) left_d.m[i][j].d = e.env_left_t.m[i][j];
+        e.env_from_world_d = inverse(left_d * M4<Dual>(e.env_to_world_raw));
+    }
     // m_sampling_weight keeps its default 1.f (emitter.h:27) until Scene::configure normalises it
 }
 

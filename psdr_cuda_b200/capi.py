@@ -17,7 +17,7 @@ TEX = {"reflectance": 0, "alpha_u": 1, "alpha_v": 2, "eta": 3, "k": 4, "specular
 INTEG_DIRECT, INTEG_FIELD, INTEG_PATH = 0, 1, 2
 FIELDS = {"silhouette": 0, "position": 1, "depth": 2, "geoNormal": 3, "shNormal": 4, "uv": 5}
 MESH_FACE_NORMALS, MESH_ENABLE_EDGES = 1, 2
-PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES, PARAM_ENVMAP_RADIANCE, PARAM_ENVMAP_SCALE, PARAM_SENSOR_TRANSFORM = 0, 1, 2, 3, 4
+PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES, PARAM_ENVMAP_RADIANCE, PARAM_ENVMAP_SCALE, PARAM_SENSOR_TRANSFORM, PARAM_ENVMAP_TRANSFORM = 0, 1, 2, 3, 4, 5
 
 SYMBOLS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream", "pb_ctx_set_retain_limit",

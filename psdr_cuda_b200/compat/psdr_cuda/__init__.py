@@ -173,6 +173,9 @@ class Scene(_h.Scene):
             elif field == "to_world":
                 obj.to_world = val.astype(np.float32)
                 obj.requires_grad = bool(t.requires_grad)
+            elif field == "to_world_left" and isinstance(obj, EnvironmentMap):   # EnvironmentMap.set_transform (src/psdr.cpp:238)
+                obj.set_transform(val.astype(np.float32))
+                obj.transform_requires_grad = bool(t.requires_grad)
             elif field in ("to_world_left", "to_world_right"):
                 obj.set_transform(val.astype(np.float32), field == "to_world_left")
                 obj.requires_grad = bool(t.requires_grad) or obj.requires_grad   # the transform gradient is a contraction of the vertex gradient
@@ -213,7 +216,7 @@ class Scene(_h.Scene):
                 seg[pm[key].index] = (off, cnt)
         out = []
         for (key, field), t in self._params.items():
-            if field in ("to_world_left", "to_world_right") and t.requires_grad and pm[key].index in seg:
+            if field in ("to_world_left", "to_world_right") and t.requires_grad and not isinstance(pm[key], EnvironmentMap) and pm[key].index in seg:
                 out.append((t, pm[key], field == "to_world_left") + seg[pm[key].index])
         return out
 

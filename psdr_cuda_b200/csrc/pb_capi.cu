@@ -583,6 +583,7 @@ static void configure(pb_ctx *c) {
             off += n;
         }
         if (e.env_scale_requires_grad) { c->grad_segments.push_back({PB_PARAM_ENVMAP_SCALE, c->emitter_env, 0, off, 1}); off += 1; }
+        if (e.env_xf_requires_grad) { c->grad_segments.push_back({PB_PARAM_ENVMAP_TRANSFORM, c->emitter_env, 0, off, 16}); off += 16; }
     }
     set_l2_window(c);
     c->ready = true;
@@ -891,7 +892,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         c->d_bsdfs_grad.upload(br, st);
         P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
         bool env_grad = false;
-        for (const GradSegment &g : c->grad_segments) env_grad = env_grad || g.kind == PB_PARAM_ENVMAP_RADIANCE || g.kind == PB_PARAM_ENVMAP_SCALE;
+        for (const GradSegment &g : c->grad_segments)
+            env_grad = env_grad || g.kind == PB_PARAM_ENVMAP_RADIANCE || g.kind == PB_PARAM_ENVMAP_SCALE || g.kind == PB_PARAM_ENVMAP_TRANSFORM;
         if (env_grad) {   // emitter table whose environment map points at its gradient segments
             std::vector<EmitterRec> er(c->emitters.size());
             PB_CUDA(cudaMemcpyAsync(er.data(), c->d_emitters.p, er.size() * sizeof(EmitterRec), cudaMemcpyDeviceToHost, st));
@@ -899,6 +901,24 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             for (const GradSegment &g : c->grad_segments) {
                 if (g.kind == PB_PARAM_ENVMAP_RADIANCE) er[g.id].env_radiance.grad = d_grad + g.offset;
                 if (g.kind == PB_PARAM_ENVMAP_SCALE) er[g.id].env_scale_grad = d_grad + g.offset;
+                if (g.kind == PB_PARAM_ENVMAP_TRANSFORM) {   // the kernels see from_world = inverse(left * raw): its adjoint (or tangent) lives in a scratch buffer
+                    const HostEmitter &he = c->emitters[g.id];
+                    c->d_env_xf_acc.reserve(16 * sizeof(float));
+                    if (jvp) {   // F_t = -F (L_t R) F
+                        float lt[16], ft[16];
+                        PB_CUDA(cudaMemcpyAsync(lt, d_grad + g.offset, sizeof(lt), cudaMemcpyDeviceToHost, st));
+                        PB_CUDA(cudaStreamSynchronize(st));
+                        Mat4h Lt; std::memcpy(Lt.m, lt, sizeof(lt));
+                        const Mat4h F = inverse(matmul(he.env_left, he.env_raw));
+                        const Mat4h T = matmul(matmul(F, matmul(Lt, he.env_raw)), F);
+                        for (int k = 0; k < 16; ++k) ft[k] = -T.m[k];
+                        PB_CUDA(cudaMemcpyAsync(c->d_env_xf_acc.p, ft, sizeof(ft), cudaMemcpyHostToDevice, st));
+                        PB_CUDA(cudaStreamSynchronize(st));
+                    } else {
+                        PB_CUDA(cudaMemsetAsync(c->d_env_xf_acc.p, 0, 16 * sizeof(float), st));
+                    }
+                    er[g.id].env_xf_grad = c->d_env_xf_acc.as<float>();
+                }
             }
             c->d_emitters_grad.upload(er, st);
             P.S.emitters = c->d_emitters_grad.as<EmitterRec>();
@@ -968,7 +988,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_SENSOR_TRANSFORM) Bp.rc_grad = 1;   // the pose adjoint lives in the extended kernel
         if (mode == MODE_VJP && c->emitter_env >= 0) {   // environment map: radiance / scale gradients, and its direction term in the geometry adjoints
             const HostEmitter &he = c->emitters[c->emitter_env];
-            if (he.env_radiance.requires_grad || he.env_scale_requires_grad || any_geom_jvp(c)) Bp.rc_grad = 1;
+            if (he.env_radiance.requires_grad || he.env_scale_requires_grad || he.env_xf_requires_grad || any_geom_jvp(c)) Bp.rc_grad = 1;
         }
         Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
     }
@@ -1021,6 +1041,22 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         }
     }
     if (mode == MODE_VJP && (P.S.tri_grad || (jvp && any_geom_jvp(c)))) run_edge_terms(c, I, sensor, plan, P, d_dLdI, &nev_edge);
+    if (mode == MODE_VJP && !jvp)   // adjoint of the envmap's from_world = inverse(left * raw) -> adjoint of `left`: g_L = -(F^T g_F F^T) R^T
+        for (const GradSegment &g : c->grad_segments)
+            if (g.kind == PB_PARAM_ENVMAP_TRANSFORM) {
+                const HostEmitter &he = c->emitters[g.id];
+                float gf[16], cur[16];
+                PB_CUDA(cudaMemcpyAsync(gf, c->d_env_xf_acc.p, sizeof(gf), cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaMemcpyAsync(cur, d_grad + g.offset, sizeof(cur), cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+                const Mat4h F = inverse(matmul(he.env_left, he.env_raw));
+                double a1[16], a2[16];
+                for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += (double)F.m[4 * k + i] * gf[4 * k + j]; a1[4 * i + j] = a; }          // F^T g_F
+                for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += a1[4 * i + k] * (double)F.m[4 * j + k]; a2[4 * i + j] = -a; }        // -(..) F^T
+                for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double a = 0; for (int k = 0; k < 4; ++k) a += a2[4 * i + k] * (double)he.env_raw.m[4 * j + k]; cur[4 * i + j] += (float)a; }   // (..) R^T
+                PB_CUDA(cudaMemcpyAsync(d_grad + g.offset, cur, sizeof(cur), cudaMemcpyHostToDevice, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+            }
     if (mode == MODE_VJP && !jvp && P.S.sensor_grad) {   // fold the world_to_sample adjoint into the to_world adjoint and add it to the gradient vector
         float h[32], cur[16];
         PB_CUDA(cudaMemcpyAsync(h, c->d_sensor_acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1358,10 +1394,11 @@ int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
         } else if (kind == PB_PARAM_SENSOR_TRANSFORM) {
             PB_ASSERT_MSG(id >= 0 && id < (int)c->sensors.size(), "Invalid sensor id");
             c->sensors[id].requires_grad = enable != 0;
-        } else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE) {
+        } else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE || kind == PB_PARAM_ENVMAP_TRANSFORM) {
             PB_ASSERT_MSG(c->emitter_env >= 0, "The scene has no environment map");
             if (kind == PB_PARAM_ENVMAP_RADIANCE) c->emitters[c->emitter_env].env_radiance.requires_grad = enable != 0;
-            else c->emitters[c->emitter_env].env_scale_requires_grad = enable != 0;
+            else if (kind == PB_PARAM_ENVMAP_SCALE) c->emitters[c->emitter_env].env_scale_requires_grad = enable != 0;
+            else c->emitters[c->emitter_env].env_xf_requires_grad = enable != 0;
         } else throw Error("Unknown parameter kind");
         c->ready = false;
     });

@@ -4,15 +4,14 @@
 // which the emitter is seen, i.e. to the position p of the vertex that looks at it (the bounding mesh point q carries no
 // gradient). Sampling and pdfs of the environment map are detached in the reference (envmap.cpp:72-95, 125-143).
 #pragma once
-#include "pb_adjoint_math.cuh"
-#include "pb_shade.cuh"
+#include "pb_wavefront.cuh"
 
 namespace pb {
 
 PB_D bool env_wants_grad(const SceneView &S) {
     if (S.emitter_env < 0) return false;
     const EmitterRec &em = S.emitters[S.emitter_env];
-    return em.env_radiance.grad != nullptr || em.env_scale_grad != nullptr;
+    return em.env_radiance.grad != nullptr || em.env_scale_grad != nullptr || em.env_xf_grad != nullptr;
 }
 
 // gLe: dLoss/dLe (per channel). its1: the hit on the bounding mesh, seen from `origin`. Returns the adjoint of `origin`
@@ -62,9 +61,8 @@ PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float
         if (fwd) jv = fmaf(s, __ldg(em.env_scale_grad), jv);
         else if (isfinite(s)) scale_acc += s;
     }
-    if (fwd && jv != 0.f && isfinite(jv)) S.jvp_acc[blockIdx.x * blockDim.x + threadIdx.x] += jv;
-    // direction -> the looking vertex
-    if (want_dir) {
+    // direction -> the looking vertex; from_world -> the environment map's transform (v = F dw)
+    if (want_dir || em.env_xf_grad) {
         float gu = 0.f, gv = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -77,14 +75,27 @@ PB_D float3 env_le_vjp(const SceneView &S, const Its &its1, float3 origin, float
         float3 gvec = f3(0.f);
         if (r2 > 0.f) { gvec.x = gu * kInvTwoPi * (-v.z) / r2; gvec.z = gu * kInvTwoPi * v.x / r2; }
         if (fabsf(v.y) < 1.f) gvec.y = -gv * kInvPi / sqrtf(1.f - v.y * v.y);
+        if (em.env_xf_grad && finite3(gvec)) {   // g_F[i][j] = g_v[i] dw[j]
+            const float gF[16] = {gvec.x * dw.x, gvec.x * dw.y, gvec.x * dw.z, 0.f, gvec.y * dw.x, gvec.y * dw.y, gvec.y * dw.z, 0.f,
+                                  gvec.z * dw.x, gvec.z * dw.y, gvec.z * dw.z, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (fwd) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) jv = fmaf(gF[k], __ldg(em.env_xf_grad + k), jv);
+            } else {
+                sensor_atomic_add16(em.env_xf_grad, gF);
+            }
+        }
         // dw = from_world^T-applied adjoint: v = M dw  =>  g_dw = M^T g_v
         const Mat4 &M = em.env_from_world;
+        if (fwd && jv != 0.f && isfinite(jv)) { S.jvp_acc[blockIdx.x * blockDim.x + threadIdx.x] += jv; jv = 0.f; }
+        if (!want_dir) return g_origin;
         const float3 g_dw = f3(M.m[0] * gvec.x + M.m[4] * gvec.y + M.m[8] * gvec.z, M.m[1] * gvec.x + M.m[5] * gvec.y + M.m[9] * gvec.z,
                                M.m[2] * gvec.x + M.m[6] * gvec.y + M.m[10] * gvec.z);
         if (g_dir_out && finite3(g_dw)) *g_dir_out = g_dw;
         const float3 g_dv = normalize_vjp(its1.p - origin, g_dw);   // dw = (q - p)/|q - p|
         if (finite3(g_dv)) g_origin = -g_dv;
     }
+    if (fwd && jv != 0.f && isfinite(jv)) S.jvp_acc[blockIdx.x * blockDim.x + threadIdx.x] += jv;
     return g_origin;
 }
 

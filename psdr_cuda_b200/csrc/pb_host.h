@@ -80,6 +80,7 @@ struct HostEmitter {
     HostTexture env_radiance;
     float env_scale = 1.f;
     bool env_scale_requires_grad = false;   // env_radiance.requires_grad covers the texels
+    bool env_xf_requires_grad = false;      // the matrix EnvironmentMap.set_transform sets
     Mat4h env_raw = Mat4h::identity(), env_left = Mat4h::identity();
     bool env_dirty = true;
     int env_res[2] = {0, 0};
@@ -147,7 +148,7 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad, d_sensor_acc;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad, d_sensor_acc, d_env_xf_acc;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms

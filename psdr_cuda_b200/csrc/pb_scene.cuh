@@ -74,6 +74,7 @@ struct EmitterRec {
     float3 env_upper; float env_sum;
     const float *env_cmf, *env_pmf;
     float *env_scale_grad;   // VJP: gradient of the scale (forward mode: its tangent), or nullptr
+    float *env_xf_grad;      // VJP: 16 floats accumulating the adjoint of env_from_world (forward mode: its tangent), or nullptr
 };
 struct SensorRec {
     Mat4 sample_to_camera, to_world, world_to_sample;

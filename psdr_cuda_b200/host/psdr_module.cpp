@@ -254,7 +254,7 @@ struct AreaLight : Emitter {
 struct EnvironmentMap : Emitter {
     Bitmap radiance{3, 0.f};
     float scale = 1.f;
-    bool scale_dirty = false, scale_requires_grad = false;
+    bool scale_dirty = false, scale_requires_grad = false, transform_requires_grad = false;
     Mat4 to_world_raw, to_world_left;
     bool transform_dirty = false;
     std::string type_name() const override { return "AreaLight"; }   // sic: envmap.h:58
@@ -504,6 +504,7 @@ public:
             }
             check(pb_grad_require(ctx, PB_PARAM_ENVMAP_RADIANCE, 0, 0, envmap->radiance.requires_grad ? 1 : 0));
             check(pb_grad_require(ctx, PB_PARAM_ENVMAP_SCALE, 0, 0, envmap->scale_requires_grad ? 1 : 0));
+            check(pb_grad_require(ctx, PB_PARAM_ENVMAP_TRANSFORM, 0, 0, envmap->transform_requires_grad ? 1 : 0));
         }
         check(pb_scene_configure(ctx));
         configured = true;
@@ -519,6 +520,7 @@ public:
             check(pb_grad_segment(ctx, i, &kind, &id, &slot, &off, &cnt));
             if (kind == PB_PARAM_BSDF_TEXTURE) out.append(py::make_tuple("BSDF[" + std::to_string(id) + "]", std::string(slots[slot]), off, cnt));
             else if (kind == PB_PARAM_SENSOR_TRANSFORM) out.append(py::make_tuple("Sensor[" + std::to_string(id) + "]", std::string("to_world"), off, cnt));
+            else if (kind == PB_PARAM_ENVMAP_TRANSFORM) out.append(py::make_tuple("Emitter[" + std::to_string(id) + "]", std::string("to_world_left"), off, cnt));
             else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE)
                 out.append(py::make_tuple("Emitter[" + std::to_string(id) + "]", std::string(kind == PB_PARAM_ENVMAP_RADIANCE ? "radiance" : "scale"), off, cnt));
             else out.append(py::make_tuple("Mesh[" + std::to_string(id) + "]", std::string("vertex_positions"), off, cnt));
@@ -637,6 +639,8 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_property_readonly("radiance", [](EnvironmentMap &e) -> Bitmap & { return e.radiance; }, py::return_value_policy::reference_internal)
         .def_property("scale", [](const EnvironmentMap &e) { return e.scale; }, [](EnvironmentMap &e, float v) { e.scale = v; e.scale_dirty = true; })
         .def_readwrite("scale_requires_grad", &EnvironmentMap::scale_requires_grad)
+        .def_readwrite("transform_requires_grad", &EnvironmentMap::transform_requires_grad)
+        .def_property_readonly("to_world_left", [](const EnvironmentMap &e) { return mat_to_numpy(e.to_world_left); })
         .def_property_readonly("to_world", [](const EnvironmentMap &e) { return mat_to_numpy(e.to_world_left * e.to_world_raw); })
         .def("set_transform", [](EnvironmentMap &e, const farray &a) { e.to_world_left = mat_from_numpy(a); e.transform_dirty = true; });
 
