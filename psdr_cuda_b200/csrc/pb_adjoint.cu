@@ -50,6 +50,39 @@ PB_D void bsdf_eval_grad_tex(const SceneView &S, const BsdfRec *b, const Its &it
     // TODO(roughconductor): alpha_u/alpha_v/eta/k/specular_reflectance adjoints
 }
 
+// adjoint of the texture coordinate through one bitmap lookup (Bitmap::eval<ad> is attached to uv, bitmap.cpp:43-89): gv[c] is
+// dLoss/d(value_c). At the camera vertex the barycentrics — hence uv — move with the geometry (scene.cpp:355-376).
+template <int C> PB_D float2 tex_uv_adjoint(const TexRef &t, float2 uv, const float *gv, bool flip_v = true) {
+    if (t.w == 1 && t.h == 1) return make_float2(0.f, 0.f);
+    const TexTap tap = tex_tap(t, uv, flip_v);
+    const float *d = t.data;
+    const int i = tap.idx;
+    float gx = 0.f, gy = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (gv[c] == 0.f) continue;
+        const float v00 = __ldg(d + i * C + c), v10 = __ldg(d + (i + 1) * C + c), v01 = __ldg(d + (i + t.w) * C + c), v11 = __ldg(d + (i + t.w + 1) * C + c);
+        gx += gv[c] * (tap.w0y * (v10 - v00) + tap.w1y * (v11 - v01));
+        gy += gv[c] * (tap.w0x * (v01 - v00) + tap.w1x * (v11 - v10));
+    }
+    return make_float2(gx * (float)(t.w - 1), gy * (float)(t.h - 1) * (flip_v ? -1.f : 1.f));
+}
+PB_D bool bsdf_has_bitmap(const BsdfRec *b) {
+    if (!b) return false;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < TEX_COUNT; ++k) any = any || (b->tex[k].data != nullptr && b->tex[k].w * b->tex[k].h > 1);
+    return any;
+}
+
+PB_D float2 rc_uv_adjoint(const BsdfRec *b, float2 uv, const rc::TexGrad &tg) {
+    if (!tg.finite()) return make_float2(0.f, 0.f);
+    const float e[3] = {tg.eta.x, tg.eta.y, tg.eta.z}, k[3] = {tg.k.x, tg.k.y, tg.k.z}, sp[3] = {tg.spec.x, tg.spec.y, tg.spec.z};
+    const float2 a = tex_uv_adjoint<1>(b->tex[TEX_ALPHA_U], uv, &tg.au), c = tex_uv_adjoint<1>(b->tex[TEX_ALPHA_V], uv, &tg.av),
+                 d = tex_uv_adjoint<3>(b->tex[TEX_ETA], uv, e), f = tex_uv_adjoint<3>(b->tex[TEX_K], uv, k), g = tex_uv_adjoint<3>(b->tex[TEX_SPECULAR], uv, sp);
+    return make_float2(a.x + c.x + d.x + f.x + g.x, a.y + c.y + d.y + f.y + g.y);
+}
+
 // block-level reduction of the per-thread constant-texture accumulators, keyed by BSDF id
 PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, float *s_acc) {
     const unsigned full = 0xffffffffu;
@@ -130,13 +163,15 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         float3 g_rd_env = f3(0.f);   // Le(x0), direct.cpp:51: its direction is the camera ray's, which only the sensor pose moves
         if (RC && ev_depth0<EV>(B) && !B.hide_emitters && env_on)
             env_le_vjp(P.S, its, v.ro, g, P.S.sensor_grad != nullptr, env_scale_acc, &g_rd_env);
+        float2 g_uv = make_float2(0.f, 0.f);   // adjoint of the camera vertex' texture coordinate (bitmap textures only)
+        const bool uv_geom = RC && ev_depth0<EV>(B) && geom_mode(P.S) && v.active && bsdf_has_bitmap(v.bsdf);
         rc::Tex rtex;
         bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
         float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
         if (RC) {
             rc_tex = v.active && rc::wants_tex_grad(v.bsdf);
             geom_rc = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_ROUGHCONDUCTOR;
-            if (rc_tex || geom_rc) rtex = rc::load_tex(v.bsdf, its.uv);
+            if (rc_tex || geom_rc || (uv_geom && v.bsdf->type == BSDF_ROUGHCONDUCTOR)) rtex = rc::load_tex(v.bsdf, its.uv);
         }
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
@@ -165,17 +200,22 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 }
                 if (cont) { w_cont = f * scale; gval += gw * scale; }
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gval, acc);
+                if (RC && uv_geom && v.bsdf->type == BSDF_DIFFUSE && wo_l.z > 0.f && its.wi.z > 0.f) {
+                    const float3 gr = gval * (kInvPi * wo_l.z);
+                    if (finite3(gr)) { const float gv3[3] = {gr.x, gr.y, gr.z}; const float2 a = tex_uv_adjoint<3>(v.bsdf->tex[TEX_REFLECTANCE], its.uv, gv3); g_uv.x += a.x; g_uv.y += a.y; }
+                }
                 if (RC && a1 && env_on) {   // dLoss/dLe of this connection
                     float weight = inv_nb;
                     if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true));
                     g_p += env_le_vjp(P.S, its1, its.p, gL * f * (scale * weight), geom_mode(P.S), env_scale_acc);
                 }
-                if (RC && rc_tex) {
+                if (RC && (rc_tex || (uv_geom && v.bsdf->type == BSDF_ROUGHCONDUCTOR))) {
                     const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true) : 0.f;
                     rc::TexGrad tg;
                     rc::bsdf_branch_tex_grad(rtex, its.wi, wo_l, s3, G, p_em, a1 && B.nl > 0, inv_nb, a1 ? gL * emitter_Le<SIMPLE>(P.S, its1, true) : f3(0.f),
                                              cont ? gw : f3(0.f), tg);
-                    rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                    if (rc_tex) rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                    if (uv_geom) { const float2 a = rc_uv_adjoint(v.bsdf, its.uv, tg); g_uv.x += a.x; g_uv.y += a.y; }
                 }
                 if (RC && geom_rc) {
                     const float p_em = (a1 && B.nl > 0) ? emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true) : 0.f;
@@ -227,11 +267,16 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 const float scale = G / ps.pdf * weight;
                 L += Le * f * scale;
                 bsdf_eval_grad_tex(P.S, v.bsdf, its, wo_l, gL * Le * scale, acc);
+                if (RC && uv_geom && v.bsdf->type == BSDF_DIFFUSE && wo_l.z > 0.f && its.wi.z > 0.f) {
+                    const float3 gr = gL * Le * (scale * kInvPi * wo_l.z);
+                    if (finite3(gr)) { const float gv3[3] = {gr.x, gr.y, gr.z}; const float2 a = tex_uv_adjoint<3>(v.bsdf->tex[TEX_REFLECTANCE], its.uv, gv3); g_uv.x += a.x; g_uv.y += a.y; }
+                }
                 if (RC && env_on) g_p += env_le_vjp(P.S, its1, its.p, gL * f * scale, geom_mode(P.S), env_scale_acc);
-                if (RC && rc_tex) {
+                if (RC && (rc_tex || (uv_geom && v.bsdf->type == BSDF_ROUGHCONDUCTOR))) {
                     rc::TexGrad tg;
                     rc::light_branch_tex_grad(rtex, its.wi, wo_l, G, ps.pdf, B.nb > 0, inv_nl, gL * Le, tg);
-                    rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                    if (rc_tex) rc::emit_tex_grad(P.S, v.bsdf, its.uv, tg, rc_acc);
+                    if (uv_geom) { const float2 a = rc_uv_adjoint(v.bsdf, its.uv, tg); g_uv.x += a.x; g_uv.y += a.y; }
                 }
                 if (RC && geom_rc) {
                     rc::GeomGrad gg;
@@ -298,6 +343,13 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                 if (t.flags & 1) tg.fn += g_shn;
                 else shading_normal_vjp(t.n0, t.n1, t.n2, v.h.u, v.h.v, g_shn, tg, gu, gv);
                 if (ev_depth0<EV>(B)) {   // solid-angle form: (u, v, t) come from the differentiable ray/triangle test, p = o + t d
+                    if (RC && uv_geom && (t.flags & 2) && isfinite(g_uv.x) && isfinite(g_uv.y)) {   // uv = uv0 + u (uv1 - uv0) + v (uv2 - uv0)
+                        const float4 *tq = reinterpret_cast<const float4 *>(P.S.tri + its.tri);
+                        const float u0x = ldg4(tq + 3).w, u0y = ldg4(tq + 4).w, u1x = ldg4(tq + 5).w, u1y = ldg4(tq + 6).w;
+                        const float4 q7 = ldg4(tq + 7);
+                        gu += g_uv.x * (u1x - u0x) + g_uv.y * (u1y - u0y);
+                        gv += g_uv.x * (q7.x - u0x) + g_uv.y * (q7.y - u0y);
+                    }
                     const RayTriGrad r = ray_intersect_triangle_vjp(t.p0, t.e1, t.e2, v.ro, v.rd, gu, gv, pdot(g_p, v.rd));
                     tg.p0 += r.p0; tg.e1 += r.e1; tg.e2 += r.e2;
                     if (want_cam) {

@@ -986,6 +986,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             for (const HostBsdf &hb : c->bsdfs) if (hb.type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
         if (mode == MODE_VJP)
             for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_SENSOR_TRANSFORM) Bp.rc_grad = 1;   // the pose adjoint lives in the extended kernel
+        if (mode == MODE_VJP && any_geom_jvp(c))   // bitmap textures: the camera vertex' uv moves with the geometry
+            for (const HostBsdf &hb : c->bsdfs) for (int k = 0; k < TEX_COUNT; ++k) if (hb.tex[k].w * hb.tex[k].h > 1) Bp.rc_grad = 1;
         if (mode == MODE_VJP && c->emitter_env >= 0) {   // environment map: radiance / scale gradients, and its direction term in the geometry adjoints
             const HostEmitter &he = c->emitters[c->emitter_env];
             if (he.env_radiance.requires_grad || he.env_scale_requires_grad || he.env_xf_requires_grad || any_geom_jvp(c)) Bp.rc_grad = 1;

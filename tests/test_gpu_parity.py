@@ -799,3 +799,45 @@ def test_envmap_transform_gradient_vs_oracle():
     dimg = ctx.render_d_jvp(integ, torch.from_numpy(T.reshape(-1)).cuda()).cpu().numpy().astype(np.float64)
     lhs, rhs = float((dimg * dLdI).sum()), float((g * T).sum())
     assert abs(lhs - rhs) <= 2e-3 * max(abs(rhs), 1e-6), (lhs, rhs)
+
+
+@pytest.mark.parametrize("kind", ["diffuse", "roughconductor"])
+def test_vertex_gradients_through_bitmap_texture_coordinates(kind):
+    """The camera vertex' barycentrics — hence its texture coordinate — move with the geometry (scene.cpp:355-376) and Bitmap::eval is
+    attached to uv (bitmap.cpp:43-89): vertex gradients of a uv-mapped quad with bitmap textures against oracle JVPs."""
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    rng = np.random.default_rng(17)
+    one3 = np.ones((1, 1, 3), np.float32)
+    if kind == "diffuse":
+        bsdf = dict(type=0, id="t", reflectance=rng.uniform(0.2, 0.9, size=(5, 7, 3)).astype(np.float32))
+    else:
+        bsdf = dict(type=1, id="m", alpha_u=rng.uniform(0.2, 0.5, size=(6, 5, 1)).astype(np.float32), alpha_v=rng.uniform(0.2, 0.5, size=(4, 4, 1)).astype(np.float32),
+                    eta=rng.uniform(0.2, 1.5, size=(3, 5, 3)).astype(np.float32), k=one3 * np.array([3.9, 2.4, 2.1], np.float32),
+                    specular_reflectance=rng.uniform(0.6, 1.0, size=(4, 3, 3)).astype(np.float32), reflectance=one3 * 0.5)
+    quad = dict(verts=np.array([[-1, 0, -1], [-1, 0, 1], [1, 0, 1], [1, 0, -1]], np.float32) * 2, faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                uvs=np.array([[0.05, 0.1], [0.1, 0.9], [0.95, 0.85], [0.9, 0.05]], np.float32), uv_faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                bsdf=0, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    light = dict(verts=np.array([[-1.5, 3, -1.5], [1.5, 3, -1.5], [1.5, 3, 1.5], [-1.5, 3, 1.5]], np.float32), faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                 bsdf=1, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    cam = orc.m_look_at(np.array([0, 4, 6], np.float32), np.array([0, 0, 0], np.float32), np.array([0, 1, 0], np.float32))
+    d = dict(opts=dict(width=32, height=32, spp=8, sppe=0, sppse=0), sensors=[dict(fov=40.0, near=0.1, far=1e4, to_world=cam)],
+             bsdfs=[bsdf, dict(type=0, id="k", reflectance=np.zeros((1, 1, 3), np.float32))],
+             meshes=[quad, light], emitters=[dict(mesh=1, radiance=np.array([30, 25, 20], np.float32))], envmap=None)
+    ctx = capi.Context(0)
+    ctx.load_description(d)
+    ctx.grad_require(capi.PARAM_MESH_VERTICES, 0)
+    ctx.configure()
+    integ = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+    img = ctx.render_d(integ).cpu().numpy()
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64).reshape(4, 3)
+    wants = []
+    for trial in range(4):
+        u = rng.normal(size=(4, 3)).astype(np.float32) if trial else np.tile(np.array([[0.7, 0.0, -0.4]], np.float32), (4, 1))   # trial 0 slides the quad in its plane: only uv moves
+        osc = orc.Scene(d); osc.set_mesh_vertex_tangent(0, u); osc.configure()
+        _, dimg = orc.DirectIntegrator(1, 1).renderD(osc)
+        want = float((dLdI.astype(np.float64) * dimg).sum()); got = float((g * u).sum())
+        wants.append(abs(want))
+        assert abs(got - want) <= 3e-3 * max(abs(want), 0.05 * max(wants)), (kind, trial, got, want)
+    assert wants[0] > 1e-3 * max(wants)      # the in-plane slide is seen through the texture only
