@@ -34,6 +34,7 @@ enum { PB_FIELD_SILHOUETTE = 0, PB_FIELD_POSITION, PB_FIELD_DEPTH, PB_FIELD_GEON
 enum { PB_MESH_FACE_NORMALS = 1, PB_MESH_ENABLE_EDGES = 2 };
 /* differentiable leaves: what a gradient segment refers to */
 enum { PB_PARAM_BSDF_TEXTURE = 0, PB_PARAM_MESH_VERTICES = 1, PB_PARAM_ENVMAP_RADIANCE = 2, PB_PARAM_ENVMAP_SCALE = 3, PB_PARAM_SENSOR_TRANSFORM = 4 /* Sensor.to_world, 16 floats row-major, id = sensor; src/psdr.cpp:220-224 */,
+       PB_PARAM_MESH_UV = 6 /* Mesh.vertex_uv, 2 floats per uv vertex in the order given to pb_scene_add_mesh; src/psdr.cpp:254 */,
        PB_PARAM_ENVMAP_TRANSFORM = 5 /* the matrix EnvironmentMap.set_transform sets (to_world = left * raw), 16 floats; src/psdr.cpp:238 */ };   /* EnvironmentMap.radiance.data / .scale, src/psdr.cpp:236-237 (id, slot ignored) */
 
 typedef struct pb_integrator {
@@ -79,6 +80,7 @@ int pb_scene_set_bsdf_texture(pb_ctx *ctx, int bsdf, int slot, const float *h_da
 int pb_scene_add_mesh(pb_ctx *ctx, int num_vertices, int num_faces, const float *h_vertices, const int *h_faces, int num_uvs,
                       const float *h_uvs, const int *h_uv_faces, int flags, int bsdf, const float h_to_world[16]);
 int pb_scene_set_mesh_vertices(pb_ctx *ctx, int mesh, const float *h_vertices);              /* Mesh.vertex_positions setter */
+int pb_scene_set_mesh_uvs(pb_ctx *ctx, int mesh, const float *h_uvs);                        /* Mesh.vertex_uv setter (same count as at pb_scene_add_mesh), src/psdr.cpp:254 */
 int pb_scene_set_mesh_transform(pb_ctx *ctx, int mesh, const float h_mat[16], int left);     /* Mesh::set_transform, mesh.h:19-26 */
 /* AreaLight(radiance, mesh): src/emitter/area.cpp, src/psdr.cpp:230-231. Returns id >= 0. */
 int pb_scene_add_area_emitter(pb_ctx *ctx, int mesh, const float h_radiance[3]);

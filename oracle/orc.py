@@ -349,6 +349,11 @@ class Scene:
     def set_bsdf_tangent(self, bsdf, name, tang):
         _chk(lib().orc_set_bsdf_tangent(self.h, bsdf, TEX[name], _p(_f(tang)) if tang is not None else None))
 
+    def set_mesh_uv_tangent(self, mesh, tang):
+        L = lib()
+        L.orc_set_mesh_uv_tangent.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _chk(L.orc_set_mesh_uv_tangent(self.h, mesh, _p(_f(tang)) if tang is not None else None))
+
     def set_sensor_transform_tangent(self, sensor, tang):
         L = lib()
         L.orc_set_sensor_transform_tangent.argtypes = [C.c_void_p, C.c_int, C.c_void_p]

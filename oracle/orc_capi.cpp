@@ -156,6 +156,13 @@ int orc_set_envmap_transform_tangent(void *h, const float *tang) {
 int orc_set_envmap_transform(void *h, const float *left) {
     return guard([&] { Scene &s = ((Handle *)h)->scene; s.emitters.at(s.emitter_env).env_left = mat16(left); });
 }
+/* forward-mode tangent of a mesh's texture coordinates (same layout as the uv array given to orc_add_mesh); null clears it */
+int orc_set_mesh_uv_tangent(void *h, int mesh, const float *tang) {
+    return guard([&] {
+        Mesh &m = ((Handle *)h)->scene.meshes.at(mesh);
+        if (tang) m.uvs_t.assign(tang, tang + m.uvs.size()); else m.uvs_t.clear();
+    });
+}
 /* forward-mode tangent of a sensor's to_world (Sensor.to_world is an AD leaf, src/psdr.cpp:220-224); null clears it */
 int orc_set_sensor_transform_tangent(void *h, int sensor, const float *tang) {
     return guard([&] {

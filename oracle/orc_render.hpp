@@ -183,7 +183,7 @@ struct Scene {
     std::vector<SamplerLane> samplers[3];
     // configured global tables (scene.cpp:205-244)
     std::vector<TriangleInfo<Dual>> tri;
-    std::vector<std::array<V2f, 3>> tri_uv;
+    std::vector<std::array<V2f, 3>> tri_uv, tri_uv_t;   // per-triangle texture coordinates and their tangents
     std::vector<int> tri_mesh;          // shape id per global triangle
     std::vector<SecEdge<Dual>> sec_edges;
     DiscreteDistribution sec_edge_distrb, emitters_distrb;
@@ -307,7 +307,7 @@ inline void Scene::configure() {   // scene.cpp:56-278
         float inv = 1.f / emitters_distrb.sum;
         for (Emitter &e : emitters) e.sampling_weight *= inv;
     }
-    tri.clear(); tri_uv.clear(); tri_mesh.clear(); sec_edges.clear();
+    tri.clear(); tri_uv.clear(); tri_uv_t.clear(); tri_mesh.clear(); sec_edges.clear();
     for (size_t i = 0; i < meshes.size(); ++i) {
         Mesh &m = meshes[i];
         m.face_offset = (int)tri.size();
@@ -316,6 +316,9 @@ inline void Scene::configure() {   // scene.cpp:56-278
             std::array<V2f, 3> uv;
             if (m.has_uv) for (int k = 0; k < 3; ++k) { int j = m.uv_faces[3 * f + k]; uv[k] = V2f(m.uvs[2 * j], m.uvs[2 * j + 1]); }
             tri_uv.push_back(uv);
+            std::array<V2f, 3> uvt;
+            if (m.has_uv && !m.uvs_t.empty()) for (int k = 0; k < 3; ++k) { int j = m.uv_faces[3 * f + k]; uvt[k] = V2f(m.uvs_t[2 * j], m.uvs_t[2 * j + 1]); }
+            tri_uv_t.push_back(uvt);
             tri_mesh.push_back((int)i);
         }
         if (opts.sppse > 0 && m.enable_edges) for (auto &s : m.sec_edges) sec_edges.push_back(s);
@@ -355,6 +358,12 @@ inline Intersection<R> Scene::ray_intersect(const Ray<R> &ray, bool active, Tria
     if constexpr (ad && PS) its.J = ti.face_area / detach(ti.face_area); else its.J = R(1.f);
     its.n = ti.face_normal;
     V2<R> tuv0(R(tuv[0].x), R(tuv[0].y)), tuve1(R(tuv[1].x - tuv[0].x), R(tuv[1].y - tuv[0].y)), tuve2(R(tuv[2].x - tuv[0].x), R(tuv[2].y - tuv[0].y));
+    if constexpr (ad) {   // Mesh.vertex_uv tangents (m_triangle_uv is gathered from the AD vertex uvs, mesh.cpp:232-236)
+        const auto &tt = tri_uv_t[hit.tri];
+        tuv0.x.d = tt[0].x; tuv0.y.d = tt[0].y;
+        tuve1.x.d = tt[1].x - tt[0].x; tuve1.y.d = tt[1].y - tt[0].y;
+        tuve2.x.d = tt[2].x - tt[0].x; tuve2.y.d = tt[2].y - tt[0].y;
+    }
     if constexpr (!ad || PS) {
         V2<R> uv(R(hit.u), R(hit.v));
         V3<R> sh_n = normalize(bilinear(ti.n0, ti.n1 - ti.n0, ti.n2 - ti.n0, uv));

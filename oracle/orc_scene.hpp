@@ -240,6 +240,7 @@ struct Mesh {
     std::vector<int> faces;               // nf*3
     bool has_uv = false;
     std::vector<float> uvs;               // n*2
+    std::vector<float> uvs_t;             // forward-mode tangent of the texture coordinates (Mesh.vertex_uv is an AD leaf, psdr.cpp:254), or empty
     std::vector<int> uv_faces;            // nf*3
     bool face_normals = false, enable_edges = true;
     int bsdf = -1, emitter = -1;

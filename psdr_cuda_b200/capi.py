@@ -17,12 +17,12 @@ TEX = {"reflectance": 0, "alpha_u": 1, "alpha_v": 2, "eta": 3, "k": 4, "specular
 INTEG_DIRECT, INTEG_FIELD, INTEG_PATH = 0, 1, 2
 FIELDS = {"silhouette": 0, "position": 1, "depth": 2, "geoNormal": 3, "shNormal": 4, "uv": 5}
 MESH_FACE_NORMALS, MESH_ENABLE_EDGES = 1, 2
-PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES, PARAM_ENVMAP_RADIANCE, PARAM_ENVMAP_SCALE, PARAM_SENSOR_TRANSFORM, PARAM_ENVMAP_TRANSFORM = 0, 1, 2, 3, 4, 5
+PARAM_BSDF_TEXTURE, PARAM_MESH_VERTICES, PARAM_ENVMAP_RADIANCE, PARAM_ENVMAP_SCALE, PARAM_SENSOR_TRANSFORM, PARAM_ENVMAP_TRANSFORM, PARAM_MESH_UV = 0, 1, 2, 3, 4, 5, 6
 
 SYMBOLS = [
     "pb_ctx_create", "pb_ctx_destroy", "pb_last_error", "pb_version", "pb_ctx_set_batch", "pb_ctx_set_shard", "pb_ctx_set_stream", "pb_ctx_set_retain_limit",
     "pb_scene_set_options", "pb_scene_add_sensor", "pb_scene_set_sensor_transform", "pb_scene_add_bsdf", "pb_scene_set_bsdf_texture",
-    "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_add_envmap", "pb_scene_set_envmap_radiance", "pb_scene_set_envmap_transform", "pb_scene_num_meshes", "pb_scene_configure",
+    "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_uvs", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_add_envmap", "pb_scene_set_envmap_radiance", "pb_scene_set_envmap_transform", "pb_scene_num_meshes", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
@@ -146,6 +146,9 @@ class Context:
 
     def set_mesh_vertices(self, mesh, verts):
         self._chk(lib().pb_scene_set_mesh_vertices(self.h, mesh, _p(_f(verts))))
+
+    def set_mesh_uvs(self, mesh, uvs):
+        self._chk(lib().pb_scene_set_mesh_uvs(self.h, mesh, _p(_f(uvs))))
 
     def set_mesh_transform(self, mesh, mat, left=True):
         self._chk(lib().pb_scene_set_mesh_transform(self.h, mesh, _p(_f(mat)), int(left)))

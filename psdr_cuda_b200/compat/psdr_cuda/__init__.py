@@ -154,6 +154,8 @@ class Scene(_h.Scene):
             value = np.float32(obj.scale)
         elif field == "to_world":                           # Sensor.to_world (src/psdr.cpp:220-224)
             value = obj.to_world
+        elif field == "vertex_uv":                          # Mesh.vertex_uv (src/psdr.cpp:254)
+            value = obj.vertex_uv
         else:
             value = obj.vertex_positions if field == "vertex_positions" else getattr(obj, field).data
         t = torch.tensor(np.asarray(value), dtype=torch.float32, device="cuda:%d" % self._device, requires_grad=requires_grad)
@@ -173,6 +175,9 @@ class Scene(_h.Scene):
             elif field == "to_world":
                 obj.to_world = val.astype(np.float32)
                 obj.requires_grad = bool(t.requires_grad)
+            elif field == "vertex_uv":
+                obj.vertex_uv = val.astype(np.float32)
+                obj.uv_requires_grad = bool(t.requires_grad)
             elif field == "to_world_left" and isinstance(obj, EnvironmentMap):   # EnvironmentMap.set_transform (src/psdr.cpp:238)
                 obj.set_transform(val.astype(np.float32))
                 obj.transform_requires_grad = bool(t.requires_grad)

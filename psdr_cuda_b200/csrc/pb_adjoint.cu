@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         if (RC && ev_depth0<EV>(B) && !B.hide_emitters && env_on)
             env_le_vjp(P.S, its, v.ro, g, P.S.sensor_grad != nullptr, env_scale_acc, &g_rd_env);
         float2 g_uv = make_float2(0.f, 0.f);   // adjoint of the camera vertex' texture coordinate (bitmap textures only)
-        const bool uv_geom = RC && ev_depth0<EV>(B) && geom_mode(P.S) && v.active && bsdf_has_bitmap(v.bsdf);
+        float *uv_leaf = (RC && v.active) ? P.S.meshes[its.shape].uv_grad : nullptr;   // Mesh.vertex_uv of this vertex' mesh is a leaf
+        const bool uv_geom = RC && v.active && bsdf_has_bitmap(v.bsdf) && ((ev_depth0<EV>(B) && geom_mode(P.S)) || uv_leaf != nullptr);
         rc::Tex rtex;
         bool geom_rc = false;       // geometry adjoints of a rough-conductor vertex (local duals, pb_rc.cuh)
         float3 g_a = f3(0.f);       // adjoint of the previous vertex' position (enters through wi)
@@ -332,6 +333,22 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                     point_on_triangle_scatter(P.S, hp.tri, hp.u, hp.v, g_a, f3(0.f), 0.f);
                 }
             }
+        }
+        if (RC && uv_leaf && (g_uv.x != 0.f || g_uv.y != 0.f) && isfinite(g_uv.x) && isfinite(g_uv.y)) {
+            // uv = (1 - u - v) uv0 + u uv1 + v uv2 with the triangle's three uv vertices (mesh.cpp:232-236)
+            const MeshRec &mr = P.S.meshes[its.shape];
+            const int f = its.tri - mr.face_offset;
+            float bu = v.h.u, bv = v.h.v;
+            if (ev_depth0<EV>(B)) { float tt; ray_intersect_triangle(load_tri_geom(P.S, its.tri).p0, load_tri_geom(P.S, its.tri).e1, load_tri_geom(P.S, its.tri).e2, v.ro, v.rd, bu, bv, tt); }
+            const float wgt[3] = {1.f - bu - bv, bu, bv};
+            float jv = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int j = __ldg(mr.uv_faces + 3 * f + k);
+                if (P.S.tri_tangent) jv += wgt[k] * (g_uv.x * __ldg(uv_leaf + 2 * j) + g_uv.y * __ldg(uv_leaf + 2 * j + 1));
+                else { atomicAdd(uv_leaf + 2 * j, wgt[k] * g_uv.x); atomicAdd(uv_leaf + 2 * j + 1, wgt[k] * g_uv.y); }
+            }
+            if (P.S.tri_tangent) jvp_add(P.S, jv);
         }
         const bool want_cam = RC && ev_depth0<EV>(B) && P.S.sensor_grad != nullptr && its.valid;
         if (geom || (RC && geom_rc) || want_cam) {   // chain the vertex adjoints into its triangle (scene.cpp:326-376) and, at the camera vertex, into the sensor pose

@@ -362,6 +362,7 @@ static void configure(pb_ctx *c) {
             m.topo_dirty = false;
         }
         if (m.verts_dirty) { m.d_vraw.upload(m.verts, st); m.verts_dirty = false; }
+        if (m.uv_dirty && (m.flags & 2)) { m.d_uvs.upload(m.uvs, st); m.uv_dirty = false; }   // texture coordinates only: the BVH is untouched
         m.d_vworld.reserve(3 * (size_t)m.nv * sizeof(float));
         m.d_vnormal.reserve(3 * (size_t)m.nv * sizeof(float));
         m.d_fcross.reserve((size_t)m.nf * sizeof(float4));
@@ -530,6 +531,7 @@ static void configure(pb_ctx *c) {
         std::memset(&mr[i], 0, sizeof(MeshRec));
         mr[i].bsdf = m.bsdf; mr[i].emitter = m.emitter; mr[i].inv_total_area = m.inv_total_area;
         mr[i].face_offset = m.face_offset; mr[i].num_faces = m.nf; mr[i].flags = m.flags & 3;
+        mr[i].uv_faces = (m.flags & 2) ? m.d_uv_faces.as<int>() : nullptr; mr[i].uv_grad = nullptr;
     }
     c->d_meshes.upload(mr, st);
     std::vector<BsdfRec> br(c->bsdfs.size());
@@ -571,6 +573,12 @@ static void configure(pb_ctx *c) {
         if (c->meshes[i].requires_grad) {
             const int64_t n = 3 * (int64_t)c->meshes[i].nv;
             c->grad_segments.push_back({PB_PARAM_MESH_VERTICES, (int)i, 0, off, n});
+            off += n;
+        }
+    for (size_t i = 0; i < c->meshes.size(); ++i)
+        if (c->meshes[i].uv_requires_grad && (c->meshes[i].flags & 2)) {
+            const int64_t n = (int64_t)c->meshes[i].uvs.size();
+            c->grad_segments.push_back({PB_PARAM_MESH_UV, (int)i, 0, off, n});
             off += n;
         }
     for (size_t i = 0; i < c->sensors.size(); ++i)
@@ -891,6 +899,18 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;   // forward mode: the tangent, read only
         c->d_bsdfs_grad.upload(br, st);
         P.S.bsdfs = c->d_bsdfs_grad.as<BsdfRec>();
+        {   // mesh table whose uv-gradient pointers point at their segments (Mesh.vertex_uv leaves)
+            bool any_uv = false;
+            for (const GradSegment &g : c->grad_segments) any_uv = any_uv || g.kind == PB_PARAM_MESH_UV;
+            if (any_uv) {
+                std::vector<MeshRec> mr(c->meshes.size());
+                PB_CUDA(cudaMemcpyAsync(mr.data(), c->d_meshes.p, mr.size() * sizeof(MeshRec), cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+                for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_MESH_UV) mr[g.id].uv_grad = d_grad + g.offset;
+                c->d_meshes_grad.upload(mr, st);
+                P.S.meshes = c->d_meshes_grad.as<MeshRec>();
+            }
+        }
         bool env_grad = false;
         for (const GradSegment &g : c->grad_segments)
             env_grad = env_grad || g.kind == PB_PARAM_ENVMAP_RADIANCE || g.kind == PB_PARAM_ENVMAP_SCALE || g.kind == PB_PARAM_ENVMAP_TRANSFORM;
@@ -986,6 +1006,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             for (const HostBsdf &hb : c->bsdfs) if (hb.type == PB_BSDF_ROUGHCONDUCTOR) Bp.rc_grad = 1;
         if (mode == MODE_VJP)
             for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_SENSOR_TRANSFORM) Bp.rc_grad = 1;   // the pose adjoint lives in the extended kernel
+        if (mode == MODE_VJP)
+            for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_MESH_UV) Bp.rc_grad = 1;
         if (mode == MODE_VJP && any_geom_jvp(c))   // bitmap textures: the camera vertex' uv moves with the geometry
             for (const HostBsdf &hb : c->bsdfs) for (int k = 0; k < TEX_COUNT; ++k) if (hb.tex[k].w * hb.tex[k].h > 1) Bp.rc_grad = 1;
         if (mode == MODE_VJP && c->emitter_env >= 0) {   // environment map: radiance / scale gradients, and its direction term in the geometry adjoints
@@ -1259,6 +1281,15 @@ int pb_scene_set_mesh_vertices(pb_ctx *c, int mesh, const float *verts) {
         c->ready = false;
     });
 }
+int pb_scene_set_mesh_uvs(pb_ctx *c, int mesh, const float *uvs) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size() && uvs && (c->meshes[mesh].flags & 2), "Invalid mesh id, or the mesh has no texture coordinates");
+        HostMesh &m = c->meshes[mesh];
+        m.uvs.assign(uvs, uvs + m.uvs.size());   // count and indices stay those of pb_scene_add_mesh
+        m.uv_dirty = true;
+        c->ready = false;
+    });
+}
 int pb_scene_set_mesh_transform(pb_ctx *c, int mesh, const float *mat, int left) {
     return guard(c, [&] {
         PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size(), "Invalid mesh id");
@@ -1393,6 +1424,9 @@ int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
         } else if (kind == PB_PARAM_MESH_VERTICES) {
             PB_ASSERT_MSG(id >= 0 && id < (int)c->meshes.size(), "Invalid mesh id");
             c->meshes[id].requires_grad = enable != 0;
+        } else if (kind == PB_PARAM_MESH_UV) {
+            PB_ASSERT_MSG(id >= 0 && id < (int)c->meshes.size() && (c->meshes[id].flags & 2), "Invalid mesh id, or the mesh has no texture coordinates");
+            c->meshes[id].uv_requires_grad = enable != 0;
         } else if (kind == PB_PARAM_SENSOR_TRANSFORM) {
             PB_ASSERT_MSG(id >= 0 && id < (int)c->sensors.size(), "Invalid sensor id");
             c->sensors[id].requires_grad = enable != 0;

@@ -65,7 +65,7 @@ struct HostMesh {
     std::vector<float> verts, uvs;
     std::vector<int> faces, uv_faces, edges, csr_off, csr_face, csr_slot;
     Mat4h raw = Mat4h::identity(), left = Mat4h::identity(), right = Mat4h::identity();
-    bool verts_dirty = true, topo_dirty = true, requires_grad = false;
+    bool verts_dirty = true, topo_dirty = true, requires_grad = false, uv_requires_grad = false, uv_dirty = false;
     DevBuf d_vraw, d_faces, d_uvs, d_uv_faces, d_csr_off, d_csr_face, d_csr_slot, d_vworld, d_fcross, d_vnormal, d_face_area, d_face_cmf;
     DevBuf d_gworld, d_gnsum, d_gcorner, d_fcross_t, d_vnormal_t;   // VJP scratch: direct world-space vertex adjoint, normal-sum adjoint, per-corner adjoint
     int face_offset = 0;
@@ -148,7 +148,7 @@ struct pb_ctx {
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad, d_sensor_acc, d_env_xf_acc;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad, d_sensor_acc, d_env_xf_acc, d_meshes_grad;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms

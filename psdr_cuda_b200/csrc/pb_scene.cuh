@@ -37,12 +37,14 @@ struct __align__(64) BvhNode { float4 a, b, c, d; };
 // child links (int bits; 0x80000000 = absent), padding. Built by collapsing the binary tree (pb_bvh.cpp).
 struct __align__(16) BvhNode4 { float4 lox, loy, loz, hix, hiy, hiz, child, pad; };
 
-struct MeshRec {           // 32 B, per mesh
+struct MeshRec {           // 48 B, per mesh
     int bsdf, emitter;     // -1 = none
     float inv_total_area;
     int face_offset, num_faces;
     int flags;             // bit0 face normals, bit1 has uv
     int pad0, pad1;
+    const int *uv_faces;   // 3 uv indices per face, or nullptr
+    float *uv_grad;        // VJP: gradient of Mesh.vertex_uv (2 floats per uv vertex; forward mode: its tangent), or nullptr
 };
 enum { BSDF_DIFFUSE = 0, BSDF_ROUGHCONDUCTOR = 1 };
 enum { TEX_REFLECTANCE = 0, TEX_ALPHA_U, TEX_ALPHA_V, TEX_ETA, TEX_K, TEX_SPECULAR, TEX_COUNT };

@@ -162,8 +162,8 @@ struct Mesh : Object {
     int index = -1, bsdf = -1, emitter = -1;
     std::vector<float> verts, uvs;
     std::vector<int> faces, uv_faces;
-    bool use_face_normals = false, enable_edges = true, requires_grad = false;
-    bool verts_dirty = false, transform_dirty = false;
+    bool use_face_normals = false, enable_edges = true, requires_grad = false, uv_requires_grad = false;
+    bool verts_dirty = false, transform_dirty = false, uvs_dirty = false;
     Mat4 to_world_raw, to_world_left, to_world_right;
     int nv() const { return (int)verts.size() / 3; }
     int nf() const { return (int)faces.size() / 3; }
@@ -217,6 +217,16 @@ struct Mesh : Object {
         if ((size_t)a.size() != verts.size()) throw std::runtime_error("vertex_positions: wrong size");
         verts.assign(a.data(), a.data() + a.size());
         verts_dirty = true;
+    }
+    farray get_uvs() const {
+        farray a(std::vector<py::ssize_t>{(py::ssize_t)(uvs.size() / 2), 2});
+        std::memcpy(a.mutable_data(), uvs.data(), uvs.size() * sizeof(float));
+        return a;
+    }
+    void set_uvs(const farray &a) {
+        if ((size_t)a.size() != uvs.size()) throw std::runtime_error("vertex_uv: wrong size");
+        uvs.assign(a.data(), a.data() + a.size());
+        uvs_dirty = true;
     }
     iarray get_faces() const {
         iarray a(std::vector<py::ssize_t>{(py::ssize_t)nf(), 3});
@@ -495,6 +505,8 @@ public:
                 m->transform_dirty = false;
             }
             check(pb_grad_require(ctx, PB_PARAM_MESH_VERTICES, m->index, 0, m->requires_grad ? 1 : 0));
+            if (m->uvs_dirty && !m->uvs.empty()) { check(pb_scene_set_mesh_uvs(ctx, m->index, m->uvs.data())); m->uvs_dirty = false; }
+            if (!m->uvs.empty()) check(pb_grad_require(ctx, PB_PARAM_MESH_UV, m->index, 0, m->uv_requires_grad ? 1 : 0));
         }
         if (envmap && envmap->transform_dirty) { check(pb_scene_set_envmap_transform(ctx, envmap->to_world_left.m)); envmap->transform_dirty = false; }
         if (envmap) {
@@ -519,6 +531,7 @@ public:
             int kind, id, slot; int64_t off, cnt;
             check(pb_grad_segment(ctx, i, &kind, &id, &slot, &off, &cnt));
             if (kind == PB_PARAM_BSDF_TEXTURE) out.append(py::make_tuple("BSDF[" + std::to_string(id) + "]", std::string(slots[slot]), off, cnt));
+            else if (kind == PB_PARAM_MESH_UV) out.append(py::make_tuple("Mesh[" + std::to_string(id) + "]", std::string("vertex_uv"), off, cnt));
             else if (kind == PB_PARAM_SENSOR_TRANSFORM) out.append(py::make_tuple("Sensor[" + std::to_string(id) + "]", std::string("to_world"), off, cnt));
             else if (kind == PB_PARAM_ENVMAP_TRANSFORM) out.append(py::make_tuple("Emitter[" + std::to_string(id) + "]", std::string("to_world_left"), off, cnt));
             else if (kind == PB_PARAM_ENVMAP_RADIANCE || kind == PB_PARAM_ENVMAP_SCALE)
@@ -648,6 +661,7 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_property_readonly("num_vertices", &Mesh::nv)
         .def_property_readonly("num_faces", &Mesh::nf)
         .def_property("vertex_positions", &Mesh::get_vertices, &Mesh::set_vertices)
+        .def_property("vertex_uv", &Mesh::get_uvs, &Mesh::set_uvs)
         .def_property_readonly("face_indices", &Mesh::get_faces)
         .def_property_readonly("to_world_raw", [](const Mesh &x) { return mat_to_numpy(x.to_world_raw); })
         .def_property_readonly("to_world_left", [](const Mesh &x) { return mat_to_numpy(x.to_world_left); })
@@ -659,6 +673,7 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_readwrite("enable_edges", &Mesh::enable_edges)
         .def_readwrite("use_face_normals", &Mesh::use_face_normals)
         .def_readwrite("requires_grad", &Mesh::requires_grad)
+        .def_readwrite("uv_requires_grad", &Mesh::uv_requires_grad)
         .def_property_readonly("to_world", [](const Mesh &x) { return mat_to_numpy(x.to_world_left * x.to_world_raw * x.to_world_right); })
         .def("set_transform", [](Mesh &x, const farray &a, bool set_left) { (set_left ? x.to_world_left : x.to_world_right) = mat_from_numpy(a); x.transform_dirty = true; },
              py::arg("mat"), py::arg("set_left") = true)   // mesh.h:19-26

@@ -841,3 +841,63 @@ def test_vertex_gradients_through_bitmap_texture_coordinates(kind):
         wants.append(abs(want))
         assert abs(got - want) <= 3e-3 * max(abs(want), 0.05 * max(wants)), (kind, trial, got, want)
     assert wants[0] > 1e-3 * max(wants)      # the in-plane slide is seen through the texture only
+
+
+def test_vertex_uv_gradient_vs_oracle():
+    """Mesh.vertex_uv as a differentiable leaf (src/psdr.cpp:254): two uv-mapped bitmap-textured quads that see each other, Path(2), so
+    that texture lookups at the camera vertex (attached barycentrics) and at path-space vertices (frozen barycentrics) both count."""
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    rng = np.random.default_rng(23)
+    one3 = np.ones((1, 1, 3), np.float32)
+    floor = dict(verts=np.array([[-2, 0, -2], [-2, 0, 2], [2, 0, 2], [2, 0, -2]], np.float32), faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                 uvs=np.array([[0.05, 0.1], [0.1, 0.9], [0.95, 0.85], [0.9, 0.05]], np.float32), uv_faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                 bsdf=0, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    wall = dict(verts=np.array([[-2, 0, -2], [2, 0, -2], [2, 3, -2], [-2, 3, -2]], np.float32), faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                uvs=np.array([[0.2, 0.2], [0.8, 0.25], [0.75, 0.8], [0.15, 0.7], [0.5, 0.5]], np.float32), uv_faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                bsdf=2, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    light = dict(verts=np.array([[-1.5, 4, -1.5], [1.5, 4, -1.5], [1.5, 4, 1.5], [-1.5, 4, 1.5]], np.float32), faces=np.array([[0, 1, 2], [0, 2, 3]], np.int32),
+                 bsdf=1, face_normals=True, enable_edges=True, id="", to_world=np.eye(4, dtype=np.float32))
+    cam = orc.m_look_at(np.array([0, 4, 7], np.float32), np.array([0, 0.8, 0], np.float32), np.array([0, 1, 0], np.float32))
+    d = dict(opts=dict(width=32, height=32, spp=8, sppe=0, sppse=0), sensors=[dict(fov=40.0, near=0.1, far=1e4, to_world=cam)],
+             bsdfs=[dict(type=0, id="t", reflectance=rng.uniform(0.2, 0.9, size=(5, 7, 3)).astype(np.float32)),
+                    dict(type=0, id="k", reflectance=np.zeros((1, 1, 3), np.float32)),
+                    dict(type=1, id="m", alpha_u=rng.uniform(0.3, 0.6, size=(6, 5, 1)).astype(np.float32), alpha_v=one3[:, :, :1] * 0.4,
+                         eta=rng.uniform(0.2, 1.5, size=(3, 5, 3)).astype(np.float32), k=one3 * np.array([3.9, 2.4, 2.1], np.float32),
+                         specular_reflectance=one3 * 0.9, reflectance=one3 * 0.5)],
+             meshes=[floor, light, wall], emitters=[dict(mesh=1, radiance=np.array([30, 25, 20], np.float32))], envmap=None)
+    ctx = capi.Context(0)
+    ctx.load_description(d)
+    ctx.grad_require(capi.PARAM_MESH_UV, 0)
+    ctx.grad_require(capi.PARAM_MESH_UV, 2)
+    ctx.configure()
+    integ = capi.make_integrator("path", max_depth=2)
+    img = ctx.render_d(integ).cpu().numpy()
+    ref_img, _ = orc.PathIntegrator(2).renderD((lambda s: (s.configure(), s)[1])(orc.Scene(d)))
+    assert_image_parity(img, ref_img)
+    dLdI = rng.uniform(-1, 1, size=img.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64)
+    layout = ctx.grad_layout()
+    assert [(s["kind"], s["id"], s["count"]) for s in layout] == [(capi.PARAM_MESH_UV, 0, 8), (capi.PARAM_MESH_UV, 2, 10)]
+    g0, g2 = g[:8].reshape(4, 2), g[8:].reshape(5, 2)
+    assert np.abs(g0).max() > 0 and np.abs(g2[:4]).max() > 0 and np.all(g2[4] == 0)     # the fifth uv vertex of the wall is unreferenced
+    wants = []
+    for trial in range(3):
+        t0, t2 = rng.normal(size=(4, 2)).astype(np.float32) * 0.05, rng.normal(size=(5, 2)).astype(np.float32) * 0.05
+        osc = orc.Scene(d); osc.set_mesh_uv_tangent(0, t0); osc.set_mesh_uv_tangent(2, t2); osc.configure()
+        _, dimg = orc.PathIntegrator(2).renderD(osc)
+        want = float((dLdI.astype(np.float64) * dimg).sum()); got = float((g0 * t0).sum() + (g2 * t2).sum())
+        wants.append(abs(want))
+        assert abs(got - want) <= 3e-3 * max(abs(want), 0.05 * max(wants)), (trial, got, want)
+    t = rng.normal(size=18).astype(np.float32)
+    dimg = ctx.render_d_jvp(integ, torch.from_numpy(t).cuda()).cpu().numpy().astype(np.float64)
+    lhs, rhs = float((dimg * dLdI).sum()), float((g * t).sum())
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(rhs), 1e-6), (lhs, rhs)
+    # the setter: new texture coordinates reach the renderer without touching the BVH
+    new_uv = floor["uvs"] + 0.05
+    ctx.set_mesh_uvs(0, new_uv)
+    ctx.configure(reseed=True)       # same sampler position as a fresh context
+    d2 = dict(d); d2["meshes"] = [dict(m) for m in d["meshes"]]; d2["meshes"][0]["uvs"] = new_uv
+    fresh = capi.Context(0); fresh.load_description(d2); fresh.configure()
+    assert ctx.bvh_stats()["builds"] == 1
+    assert torch.allclose(ctx.render_c(integ), fresh.render_c(integ), rtol=1e-5, atol=1e-6)
