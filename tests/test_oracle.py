@@ -165,3 +165,20 @@ def test_envmap_scale_tangent_is_the_exact_derivative():
     assert np.abs(dimg).max() > 0
     scale = desc["envmap"]["scale"]
     assert np.allclose(dimg * scale, img, rtol=2e-4, atol=1e-6)
+
+
+def test_derivative_goldens():
+    """forward-mode derivative images of every leaf kind (rough conductor, environment map, sensor pose, vertices) against the
+    committed projections (tests/golden/derivative_golden.npz, generator make_golden_derivatives.py)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_derivatives", os.path.join(GOLDEN, "make_golden_derivatives.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(GOLDEN, "derivative_golden.npz"))
+    got = mod.compute()
+    assert set(got) == set(gold.files)
+    for k, v in got.items():
+        g = gold[k]
+        assert np.all(np.isfinite(v)) and g[1] > 0, k
+        # projected derivative (relative to the derivative image's L1 mass: OpenMP changes fp32 summation order), L1 mass, image sum
+        assert abs(v[0] - g[0]) <= 1e-4 * g[1] and abs(v[1] - g[1]) <= 1e-4 * g[1] and abs(v[2] - g[2]) <= 1e-5 * abs(g[2]), (k, v, g)
