@@ -901,3 +901,52 @@ def test_vertex_uv_gradient_vs_oracle():
     fresh = capi.Context(0); fresh.load_description(d2); fresh.configure()
     assert ctx.bvh_stats()["builds"] == 1
     assert torch.allclose(ctx.render_c(integ), fresh.render_c(integ), rtol=1e-5, atol=1e-6)
+
+
+def test_reverse_mode_against_committed_derivative_goldens():
+    """<J^T w, t> from the CUDA reverse mode == <w, J t> stored in tests/golden/derivative_golden.npz (oracle forward mode, generator
+    make_golden_derivatives.py) for every kind of leaf: rough-conductor parameters, environment map, sensor pose, vertices."""
+    import importlib.util
+    from psdr_cuda_b200 import capi, scene_io
+    spec = importlib.util.spec_from_file_location("make_golden_derivatives", os.path.join(GOLDEN, "make_golden_derivatives.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(GOLDEN, "derivative_golden.npz"))
+    rng = np.random.default_rng(5)
+    env_t = rng.normal(size=(512, 1024, 3)).astype(np.float32)      # the generator's radiance tangent (same seed, first draw)
+    T = capi.TEX
+    # label -> (scene, opts, integrator, [(kind, id, slot, tangent)])
+    o = dict(width=24, height=24, spp=4, sppe=0, sppse=0)
+    oe = dict(width=24, height=24, spp=4, sppe=4, sppse=4)
+    d11, p2 = ("direct", dict(bsdf_samples=1, light_samples=1)), ("path", dict(max_depth=2))
+    table = {
+        "rc_alpha_u": ("bunny_env", o, d11, [(capi.PARAM_BSDF_TEXTURE, 0, T["alpha_u"], np.ones(1))]),
+        "rc_eta_path2": ("bunny_env", o, p2, [(capi.PARAM_BSDF_TEXTURE, 0, T["eta"], np.array([1.0, -0.5, 0.25]))]),
+        "rc_k": ("cbox_bunny_rc", o, p2, [(capi.PARAM_BSDF_TEXTURE, 3, T["k"], np.array([0.3, 1.0, -0.7]))]),
+        "env_scale": ("bunny_env_2", o, d11, [(capi.PARAM_ENVMAP_SCALE, 0, 0, np.ones(1))]),
+        "env_radiance": ("bunny_env_2", o, p2, [(capi.PARAM_ENVMAP_RADIANCE, 0, 0, env_t.reshape(-1))]),
+        "env_transform": ("bunny_env_2", o, d11, [(capi.PARAM_ENVMAP_TRANSFORM, 0, 0, np.array([[0, -1, 0, 0], [1, 0, 0.5, 0], [0, -0.5, 0, 0], [0, 0, 0, 0]], np.float64).reshape(-1))]),
+        "sensor_translate_all_terms": ("cbox_bunny", oe, d11, [(capi.PARAM_SENSOR_TRANSFORM, 0, 0, np.array([[0, 0, 0, 1], [0, 0, 0, 0.5], [0, 0, 0, 0], [0, 0, 0, 0]], np.float64).reshape(-1))]),
+        "sensor_rotate_rc": ("cbox_bunny_rc", o, p2, [(capi.PARAM_SENSOR_TRANSFORM, 0, 0, np.array([[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]], np.float64).reshape(-1))]),
+        "vertices_rc_bunny": ("cbox_bunny_rc", o, p2, [(capi.PARAM_MESH_VERTICES, 1, 0, np.tile(np.array([1.0, 0.5, -0.3]), 34817))]),
+        "vertices_env_floor": ("bunny_env_2", o, d11, [(capi.PARAM_MESH_VERTICES, 1, 0, np.tile(np.array([0.2, -0.4, 1.0]), 4))]),
+    }
+    assert set(table) == set(gold.files)
+    for label, (scene, opts, (kind, kw), leaves) in table.items():
+        ctx = capi.Context(0)
+        ctx.load_description(scene_io.load_scene_description(scene_path(scene)), opts)
+        for pk, pid, slot, _ in leaves:
+            ctx.grad_require(pk, pid, slot)
+        ctx.configure()
+        integ = capi.make_integrator(kind, **kw)
+        img = ctx.render_d(integ)
+        w = mod.weights(img.shape[0])
+        g = ctx.render_d_vjp(integ, torch.from_numpy(w).cuda()).cpu().numpy().astype(np.float64)
+        got = 0.0
+        for seg, (pk, pid, slot, tang) in zip(ctx.grad_layout(), leaves):
+            assert (seg["kind"], seg["id"]) == (pk, pid) and seg["count"] == tang.size, (label, seg)
+            got += float((g[seg["offset"]:seg["offset"] + seg["count"]] * tang).sum())
+        want, mass, img_sum = gold[label]
+        assert abs(float(img.double().sum()) - img_sum) <= 2e-3 * abs(img_sum), (label, "primal")
+        assert abs(got - want) <= 5e-3 * max(abs(want), 0.05 * mass), (label, got, want, mass)
+        ctx.close()
