@@ -1,0 +1,11 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE: compiles the reference's own vendored ingest code (tinyobj, tinyexr + miniz) from /root/reference, in place,
+# into oracle/_ref/libref_ingest.so (git-ignored; travels to the GPU box with the snapshot). No reference source is copied.
+# The renderer itself (Enoki + OptiX) cannot be built here; see DESIGN.md §2.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${PSDR_REFERENCE:-/root/reference}"
+[ -d "$REF/include/tiny_obj_loader" ] || { echo "reference not present at $REF: keeping any prebuilt oracle/_ref"; exit 0; }
+mkdir -p "$HERE/_ref"
+g++ -O2 -std=c++17 -shared -fPIC -w -I"$REF/include" "$HERE/ref_ingest_shim.cpp" "$REF/src/core/miniz.cpp" -o "$HERE/_ref/libref_ingest.so"
+echo "built $HERE/_ref/libref_ingest.so"

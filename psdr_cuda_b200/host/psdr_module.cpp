@@ -658,6 +658,12 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def("set_transform", [](EnvironmentMap &e, const farray &a) { e.to_world_left = mat_from_numpy(a); e.transform_dirty = true; });
 
     py::class_<Mesh, Object, std::shared_ptr<Mesh>>(m, "Mesh")
+        .def(py::init<>())                                                      // src/psdr.cpp:242-243
+        .def("load", [](Mesh &x, const std::string &path, bool) { x.load(path); }, py::arg("fname"), py::arg("verbose") = false)
+        .def_property_readonly("face_uv_indices", [](const Mesh &x) {
+            iarray a(std::vector<py::ssize_t>{(py::ssize_t)(x.uv_faces.size() / 3), 3});
+            if (!x.uv_faces.empty()) std::memcpy(a.mutable_data(), x.uv_faces.data(), x.uv_faces.size() * sizeof(int));
+            return a; })
         .def_property_readonly("num_vertices", &Mesh::nv)
         .def_property_readonly("num_faces", &Mesh::nf)
         .def_property("vertex_positions", &Mesh::get_vertices, &Mesh::set_vertices)
