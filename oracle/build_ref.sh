@@ -1,6 +1,7 @@
 #!/bin/bash
-# TEST INFRASTRUCTURE: compiles the reference's own vendored ingest code (tinyobj, tinyexr + miniz) from /root/reference, in place,
-# into oracle/_ref/libref_ingest.so (git-ignored; travels to the GPU box with the snapshot). No reference source is copied.
+# TEST INFRASTRUCTURE: compiles, from /root/reference and in place, (1) the reference's own vendored ingest code (tinyobj, tinyexr +
+# miniz) into oracle/_ref/libref_ingest.so and (2) its header-only math + src/bsdf/ggx.cpp against a scalar Enoki stand-in into
+# oracle/_ref/libref_math.so (git-ignored; travels to the GPU box with the snapshot). No reference source is copied.
 # The renderer itself (Enoki + OptiX) cannot be built here; see DESIGN.md §2.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -9,3 +10,6 @@ REF="${PSDR_REFERENCE:-/root/reference}"
 mkdir -p "$HERE/_ref"
 g++ -O2 -std=c++17 -shared -fPIC -w -I"$REF/include" "$HERE/ref_ingest_shim.cpp" "$REF/src/core/miniz.cpp" -o "$HERE/_ref/libref_ingest.so"
 echo "built $HERE/_ref/libref_ingest.so"
+# the reference's own header-only math + src/bsdf/ggx.cpp, compiled unmodified against the scalar Enoki stand-in (oracle/ref_stub)
+g++ -O1 -std=c++17 -ffp-contract=off -shared -fPIC -w -I"$HERE/ref_stub" -I"$REF/include" -I"$REF" "$HERE/ref_math_shim.cpp" "$REF/src/core/miniz.cpp" -o "$HERE/_ref/libref_math.so"
+echo "built $HERE/_ref/libref_math.so"

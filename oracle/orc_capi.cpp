@@ -306,6 +306,59 @@ int orc_debug_lane(void *h, void *Iv, int sensor, int64_t lane, int ad, float *o
 int orc_preprocess_secondary_edges(void *h, void *I, int sensor, const int *reso4, int nrounds) {
     return guard([&] { preprocess_secondary_edges(*(Integrator *)I, ((Handle *)h)->scene, sensor, reso4, nrounds); });
 }
+// ---- the oracle's math, one call per reference function, for tests/test_ref_math.py (pinned against oracle/_ref/libref_math.so) ----
+static V3f mv3(const float *p) { return V3f(p[0], p[1], p[2]); }
+static void mput(float *o, const V3f &v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+void orc_math_square_to_uniform_disk_concentric(const float *s, float *out) { V2f r = square_to_uniform_disk_concentric(V2f(s[0], s[1])); out[0] = r.x; out[1] = r.y; }
+void orc_math_square_to_cosine_hemisphere(const float *s, float *out) { mput(out, square_to_cosine_hemisphere(V2f(s[0], s[1]))); }
+void orc_math_square_to_uniform_triangle(const float *s, float *out) { V2f r = square_to_uniform_triangle(V2f(s[0], s[1])); out[0] = r.x; out[1] = r.y; }
+void orc_math_frame(const float *n, float *s_out, float *t_out) { Frame<float> f(mv3(n)); mput(s_out, f.s); mput(t_out, f.t); }
+void orc_math_frame_to_local(const float *n, const float *v, float *out) { Frame<float> f(mv3(n)); mput(out, f.to_local(mv3(v))); }
+void orc_math_frame_to_world(const float *n, const float *v, float *out) { Frame<float> f(mv3(n)); mput(out, f.to_world(mv3(v))); }
+void orc_math_ray_intersect_triangle(const float *p0, const float *e1, const float *e2, const float *o, const float *d, float *uvt) {
+    ray_intersect_triangle<float>(mv3(p0), mv3(e1), mv3(e2), Ray<float>(mv3(o), mv3(d)), uvt[0], uvt[1], uvt[2]);
+}
+void orc_math_bilinear(const float *p0, const float *e1, const float *e2, const float *st, float *out) { mput(out, bilinear<float>(mv3(p0), mv3(e1), mv3(e2), V2f(st[0], st[1]))); }
+float orc_math_rgb2luminance(const float *rgb) { return rgb2luminance(mv3(rgb)); }
+int orc_math_sign_eps(float x, float eps) { return sign_eps(x, eps); }
+void orc_math_fresnel(const float *eta, const float *k, float cos_theta_i, float *out) { mput(out, fresnel<float>(mv3(eta), mv3(k), cos_theta_i)); }
+void orc_math_ray_intersect_scene_aabb(const float *o, const float *d, const float *lo, const float *hi, float *t_n_G) {
+    V3f n; ray_intersect_scene_aabb(mv3(o), mv3(d), mv3(lo), mv3(hi), t_n_G[0], n, t_n_G[4]); mput(t_n_G + 1, n);
+}
+float orc_math_ggx_eval(float au, float av, const float *m) { return ggx::eval<float>(au, av, mv3(m)); }
+float orc_math_ggx_smith_g1(float au, float av, const float *v, const float *m) { return ggx::smith_g1<float>(au, av, mv3(v), mv3(m)); }
+void orc_math_ggx_sample(float au, float av, const float *wi, const float *s3, float *out) { mput(out, ggx::sample<float>(au, av, mv3(wi), mv3(s3))); }
+void orc_math_ggx_sample_visible_11(float cos_theta_i, const float *s2, float *out) { V2f r = ggx::sample_visible_11<float>(cos_theta_i, V2f(s2[0], s2[1])); out[0] = r.x; out[1] = r.y; }
+
+void orc_math_sampler_lane(uint64_t lane, int n, float *out_1d, float *out_2d, float *out_3d) {
+    SamplerLane s = SamplerLane::make(lane);
+    for (int i = 0; i < n; ++i) out_1d[i] = s.next_1d();
+    V2f a = s.next_2d(); out_2d[0] = a.x; out_2d[1] = a.y;
+    mput(out_3d, s.next_3d());
+}
+// BSDFs with constant textures through the oracle's Scene::bsdf_* (one mesh, one BSDF)
+static Scene &bsdf_scene(int type, const float *prm) {
+    static thread_local Scene s;
+    if (s.meshes.empty()) { s.meshes.emplace_back(); s.meshes[0].bsdf = 0; s.bsdfs.emplace_back(); }
+    Bsdf &b = s.bsdfs[0];
+    b.type = type;
+    if (type == BSDF_DIFFUSE) b.reflectance = Bitmap::constant3(prm[0], prm[1], prm[2]);
+    else {
+        b.alpha_u = Bitmap::constant1(prm[0]); b.alpha_v = Bitmap::constant1(prm[1]);
+        b.eta = Bitmap::constant3(prm[2], prm[3], prm[4]); b.k = Bitmap::constant3(prm[5], prm[6], prm[7]);
+        b.specular_reflectance = Bitmap::constant3(prm[8], prm[9], prm[10]);
+    }
+    return s;
+}
+static Intersection<float> its_wi(const float *wi) { Intersection<float> its; its.shape = 0; its.tri = 0; its.wi = mv3(wi); its.uv = V2f(0.f, 0.f); return its; }
+void orc_math_bsdf_eval(int type, const float *prm, const float *wi, const float *wo, float *out) { mput(out, bsdf_scene(type, prm).bsdf_eval<float>(its_wi(wi), mv3(wo), true)); }
+float orc_math_bsdf_pdf(int type, const float *prm, const float *wi, const float *wo) { return bsdf_scene(type, prm).bsdf_pdf<float>(its_wi(wi), mv3(wo), true); }
+int orc_math_bsdf_sample(int type, const float *prm, const float *wi, const float *s3, float *wo_pdf) {
+    BSDFSample<float> bs = bsdf_scene(type, prm).bsdf_sample<float>(its_wi(wi), mv3(s3), true);
+    mput(wo_pdf, bs.wo); wo_pdf[3] = bs.pdf;
+    return bs.valid ? 1 : 0;
+}
+
 int orc_reseed(void *h) {   // drop sampler state so that the next configure() starts the streams afresh
     Scene &s = ((Handle *)h)->scene;
     for (auto &v : s.samplers) v.clear();

@@ -1,0 +1,2 @@
+#pragma once
+#include "../enoki_scalar_stub.h"
