@@ -897,7 +897,13 @@ inline int eval_secondary_edge(const Scene &scene, const Sensor &sensor, const V
     valid = valid && (sinphi > kEpsilon) && (sinphi2 > kEpsilon);
     V3f d0 = -cam_d;
     V3f d0_local = _its1.sh.to_local(d0);
-    V3f bsdf_val = scene.bsdf_eval<float>(_its1, d0_local, valid);
+    // direct.cpp:278-284: with one BSDF (or one mesh) in the scene the reference evaluates meshes[0]'s BSDF WITHOUT looking at the mesh that
+    // was hit — so a boundary segment whose camera-side end point lies on the environment map's bounding mesh (no BSDF of its own, and, unlike
+    // in Li (direct.cpp:58-61), not masked out here) is shaded with that BSDF. Seen by running the reference's own source
+    // (tests/test_ref_render.py); reproduced here and in the CUDA kernel (pb_edges.cu) for parity.
+    Intersection<float> _its1_b = _its1;
+    if (_its1.valid() && (scene.bsdfs.size() == 1 || scene.meshes.size() == 1)) _its1_b.shape = 0;
+    V3f bsdf_val = scene.bsdf_eval<float>(_its1_b, d0_local, valid);
     float correction = std::fabs((_its1.wi.z * dot(d0, _its1.n)) / (d0_local.z * dot(_dir, _its1.n)));
     if (valid) bsdf_val = bsdf_val * correction;
     V3f value0;

@@ -1,0 +1,376 @@
+// TEST INFRASTRUCTURE (oracle/): C entry points around psdr-cuda's OWN renderer, compiled unmodified from where it lies under
+// /root/reference (every src/**/*.cpp except the pybind module, the OptiX glue and the embedded PTX) against the CPU stand-in for
+// Enoki in oracle/ref_dyn/. Built by oracle/build_ref.sh into oracle/_ref/libref_render.so; tests/test_ref_render.py runs the
+// reference's Scene::load_file / configure / Integrator::renderC / renderD through it and pins the oracle to the result.
+//
+// Two things are NOT the reference's here, because they are external to it:
+//  * Enoki  -> oracle/ref_dyn/enoki_dyn.h (host arrays; forward-mode tangents instead of the reverse-mode tape),
+//  * OptiX  -> Scene_OptiX below (scene_optix.cpp replaced): the closest hit over all triangles with t in (RayEpsilon, tmax),
+//              computed with the arithmetic of the reference's ray_intersect_triangle (utils.h:67-77), ties to the lowest triangle id;
+//              it fills the same outputs as cuda/psdr_cuda.cu:27-45 (global triangle id, shape id, barycentrics; -1 on a miss).
+#include <unistd.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#define protected public   // the entry points below read Scene's tables (m_triangle_info, m_sec_edge_info) for the table parity tests
+#include <misc/Exception.h>
+#include <psdr/psdr.h>
+#include <psdr/core/ray.h>
+#include <psdr/core/intersection.h>
+#include <psdr/core/sampler.h>
+#include <psdr/core/bitmap.h>
+#include <psdr/core/transform.h>
+#include <psdr/bsdf/diffuse.h>
+#include <psdr/bsdf/roughconductor.h>
+#include <psdr/emitter/area.h>
+#include <psdr/emitter/envmap.h>
+#include <psdr/sensor/perspective.h>
+#include <psdr/shape/mesh.h>
+#include <psdr/scene/scene_optix.h>
+#include <psdr/scene/scene.h>
+#include <psdr/integrator/direct.h>
+#include <psdr/integrator/field.h>
+#undef protected
+
+// ---- stand-in for the OptiX acceleration structure -----------------------------------------------------------------------------------------
+struct PathTracerState {
+    struct Tri { float p0[3], e1[3], e2[3]; int shape, id; };
+    std::vector<Tri> tris;
+    struct Box { float lo[3], hi[3]; int first, count; };
+    std::vector<Box> boxes;   // one per mesh: a conservative early-out only
+};
+
+namespace psdr {
+
+void Intersection_OptiX::reserve(int64_t size) {
+    PSDR_ASSERT(size > 0);
+    if (size != m_size) {
+        m_size = size;
+        triangle_id = empty<IntC>(size);
+        shape_id = empty<IntC>(size);
+        uv = empty<Vector2fC>(size);
+    }
+}
+
+Scene_OptiX::Scene_OptiX() { m_accel = nullptr; }
+Scene_OptiX::~Scene_OptiX() { delete m_accel; }
+
+void Scene_OptiX::configure(const std::vector<Mesh *> &meshes) {
+    PSDR_ASSERT(!meshes.empty());
+    if (m_accel == nullptr) m_accel = new PathTracerState();
+    m_accel->tris.clear();
+    m_accel->boxes.clear();
+    int offset = 0;
+    for (size_t s = 0; s < meshes.size(); ++s) {
+        const Mesh *mesh = meshes[s];
+        PSDR_ASSERT(static_cast<int>(slices(mesh->m_vertex_buffer)) == mesh->m_num_vertices * 3);
+        PSDR_ASSERT(static_cast<int>(slices(mesh->m_face_buffer)) == mesh->m_num_faces * 3);
+        const float *vb = mesh->m_vertex_buffer.data();   // what scene_optix.cpp:48-63 hands to OptiX
+        const int *fb = mesh->m_face_buffer.data();
+        PathTracerState::Box box;
+        box.first = offset; box.count = mesh->m_num_faces;
+        for (int c = 0; c < 3; ++c) { box.lo[c] = std::numeric_limits<float>::max(); box.hi[c] = -std::numeric_limits<float>::max(); }
+        for (int f = 0; f < mesh->m_num_faces; ++f) {
+            PathTracerState::Tri t;
+            const float *a = vb + 3 * fb[3 * f], *b = vb + 3 * fb[3 * f + 1], *c = vb + 3 * fb[3 * f + 2];
+            for (int k = 0; k < 3; ++k) {
+                t.p0[k] = a[k]; t.e1[k] = b[k] - a[k]; t.e2[k] = c[k] - a[k];
+                box.lo[k] = std::min(box.lo[k], std::min(a[k], std::min(b[k], c[k])));
+                box.hi[k] = std::max(box.hi[k], std::max(a[k], std::max(b[k], c[k])));
+            }
+            t.shape = (int)s; t.id = offset + f;
+            m_accel->tris.push_back(t);
+        }
+        for (int k = 0; k < 3; ++k) { const float pad = 1e-3f * (1.f + std::abs(box.lo[k]) + std::abs(box.hi[k])); box.lo[k] -= pad; box.hi[k] += pad; }
+        m_accel->boxes.push_back(box);
+        offset += mesh->m_num_faces;
+    }
+}
+
+bool Scene_OptiX::is_ready() const { return m_accel != nullptr; }
+
+static inline float dot3(const float *a, const float *b) { return std::fma(a[0], b[0], std::fma(a[1], b[1], a[2] * b[2])); }
+static inline void cross3(const float *a, const float *b, float *r) {
+    r[0] = std::fma(a[1], b[2], -(a[2] * b[1])); r[1] = std::fma(a[2], b[0], -(a[0] * b[2])); r[2] = std::fma(a[0], b[1], -(a[1] * b[0]));
+}
+static bool hits_box(const PathTracerState::Box &b, const float *o, const float *d, float tmax) {
+    float t0 = 0.f, t1 = tmax;
+    for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.f) { if (o[k] < b.lo[k] || o[k] > b.hi[k]) return false; continue; }
+        float a = (b.lo[k] - o[k]) / d[k], c = (b.hi[k] - o[k]) / d[k];
+        if (a > c) std::swap(a, c);
+        t0 = std::max(t0, a * 0.999f - 1e-3f); t1 = std::min(t1, c * 1.001f + 1e-3f);
+        if (!(t0 <= t1)) return false;
+    }
+    return true;
+}
+
+template <bool ad>
+Vector2i<ad> Scene_OptiX::ray_intersect(const Ray<ad> &ray, Mask<ad> &active) const {
+    const int m = static_cast<int>(slices(ray.o));
+    m_its.reserve(m);
+    const RayC r = [&] { if constexpr (ad) return detach(ray); else return ray; }();
+    int *tri_out = m_its.triangle_id.data(), *shape_out = m_its.shape_id.data();
+    float *u_out = m_its.uv.x().data(), *v_out = m_its.uv.y().data();
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < m; ++i) {
+        tri_out[i] = shape_out[i] = -1; u_out[i] = v_out[i] = -1.f;   // __miss__psdr_ms
+        if (!bool(lval(active, i))) continue;                       // the caller masks these lanes out anyway (active &= hit)
+        const float o[3] = {lval(r.o.x(), i), lval(r.o.y(), i), lval(r.o.z(), i)}, d[3] = {lval(r.d.x(), i), lval(r.d.y(), i), lval(r.d.z(), i)};
+        float best = lval(r.tmax, i);
+        for (const auto &box : m_accel->boxes) {
+            if (!hits_box(box, o, d, best)) continue;
+            for (int k = box.first; k < box.first + box.count; ++k) {
+                const auto &t = m_accel->tris[k];
+                float h[3], s[3], q[3];
+                cross3(d, t.e2, h);                                  // utils.h:68-76
+                const float a = dot3(t.e1, h), f = 1.f / a;
+                for (int c = 0; c < 3; ++c) s[c] = o[c] - t.p0[c];
+                const float u = f * dot3(s, h);
+                cross3(s, t.e1, q);
+                const float v = f * dot3(d, q), tt = f * dot3(t.e2, q);
+                if (u >= 0.f && v >= 0.f && u + v <= 1.f && tt > RayEpsilon && tt < best) { best = tt; tri_out[i] = t.id; shape_out[i] = t.shape; u_out[i] = u; v_out[i] = v; }
+            }
+        }
+    }
+    active &= (m_its.shape_id >= 0) && (m_its.triangle_id >= 0);
+    return Vector2i<ad>(m_its.shape_id, m_its.triangle_id);
+}
+template Vector2iC Scene_OptiX::ray_intersect(const RayC &ray, MaskC &active) const;
+template Vector2iD Scene_OptiX::ray_intersect(const RayD &ray, MaskD &active) const;
+
+}  // namespace psdr
+
+// ---- C entry points -------------------------------------------------------------------------------------------------------------------------
+using namespace psdr;
+static thread_local std::string g_err;
+template <class F> static int guard(F &&f) {
+    try { f(); return 0; } catch (const std::exception &e) { g_err = e.what(); return 1; }
+}
+static void set_tangent(FloatD &x, const float *t, size_t n, size_t stride, size_t off) {
+    if (!t) { x.g = FloatC(); return; }
+    if (x.size() != n) throw Exception("tangent size mismatch: array has " + std::to_string(x.size()) + " lanes, tangent " + std::to_string(n));
+    x.g.d.resize(n);
+    for (size_t i = 0; i < n; ++i) x.g.d[i] = t[i * stride + off];
+}
+template <size_t k> static void set_tangent(Array<FloatD, k> &x, const float *t, size_t n) { for (size_t c = 0; c < k; ++c) set_tangent(x[c], t, n, k, c); }
+static void set_tangent(Matrix4fD &m, const float *t) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) set_tangent(m(i, j), t ? t + 4 * i + j : nullptr, 1, 1, 0); }
+
+extern "C" {
+
+const char *ref_last_error() { return g_err.c_str(); }
+void ref_set_matvec_plain(int on) { enoki::matvec_plain() = on != 0; }   // see oracle/ref_dyn/enoki_dyn.h
+
+// Scene::load_file(xml, false) with the working directory the scene's relative paths expect, RenderOption overrides, then configure()
+void *ref_scene_load(const char *xml_path, const char *cwd, int width, int height, int spp, int sppe, int sppse) {
+    Scene *scene = nullptr;
+    if (guard([&] {
+            char old[4096];
+            if (!getcwd(old, sizeof old)) throw Exception("getcwd failed");
+            if (cwd && chdir(cwd) != 0) throw Exception(std::string("cannot chdir to ") + cwd);
+            try {
+                scene = new Scene();
+                scene->load_file(xml_path, false);
+            } catch (...) { (void)!chdir(old); delete scene; scene = nullptr; throw; }
+            (void)!chdir(old);
+            if (width > 0) { scene->m_opts.width = width; scene->m_opts.height = height; }
+            if (spp >= 0) { scene->m_opts.spp = spp; scene->m_opts.sppe = sppe; scene->m_opts.sppse = sppse; }
+            scene->m_opts.log_level = 0;
+        })) return nullptr;
+    return scene;
+}
+void ref_scene_free(void *s) { delete (Scene *)s; }
+int ref_scene_configure(void *s) { return guard([&] { ((Scene *)s)->configure(); }); }
+void ref_scene_options(void *s, int *out5) { const RenderOption &o = ((Scene *)s)->m_opts; out5[0] = o.width; out5[1] = o.height; out5[2] = o.spp; out5[3] = o.sppe; out5[4] = o.sppse; }
+int ref_scene_num_meshes(void *s) { return ((Scene *)s)->m_num_meshes; }
+
+// kind 0: DirectIntegrator(bsdf_samples, light_samples) with m_hide_emitters; kind 1: FieldExtractionIntegrator(field)
+void *ref_integrator_new(int kind, int bsdf_samples, int light_samples, int hide_emitters, const char *field) {
+    Integrator *I = nullptr;
+    if (guard([&] {
+            if (kind == 0) { auto *d = new DirectIntegrator(bsdf_samples, light_samples); d->m_hide_emitters = hide_emitters != 0; I = d; }
+            else I = new FieldExtractionIntegrator(field);
+        })) return nullptr;
+    return I;
+}
+void ref_integrator_free(void *I) { delete (Integrator *)I; }
+
+static void put_image(const float *src, size_t n_src, float *out, int npix, int c) { for (int i = 0; i < npix; ++i) out[3 * i + c] = n_src == 0 ? 0.f : src[n_src == 1 ? 0 : i]; }
+// Integrator::renderC -> out[npix][3]
+int ref_render_c(void *s, void *I, int sensor, float *out) {
+    return guard([&] {
+        Scene &scene = *(Scene *)s;
+        SpectrumC img = ((Integrator *)I)->renderC(scene, sensor);
+        for (int c = 0; c < 3; ++c) put_image(img[c].data(), img[c].size(), out, scene.m_opts.width * scene.m_opts.height, c);
+    });
+}
+// Integrator::renderD -> out[npix][3] and the forward-mode tangent image out_t[npix][3] for the tangents currently set on the scene
+int ref_render_d(void *s, void *I, int sensor, float *out, float *out_t) {
+    return guard([&] {
+        Scene &scene = *(Scene *)s;
+        SpectrumD img = ((Integrator *)I)->renderD(scene, sensor);
+        const int npix = scene.m_opts.width * scene.m_opts.height;
+        for (int c = 0; c < 3; ++c) { put_image(img[c].v.data(), img[c].v.size(), out, npix, c); put_image(img[c].g.data(), img[c].g.size(), out_t, npix, c); }
+    });
+}
+// debugging aid: the per-lane radiance Integrator::__render scatters (integrator.cpp:72-87 up to, not including, the scatter_add), for lanes
+// of a freshly configured scene; consumes sampler 0 exactly like one render
+int ref_debug_li(void *s, void *Iv, int sensor, int ad, int skip_dims, float *out) {   // skip_dims: sampler dimensions dropped between the pixel jitter and Li
+    return guard([&] {
+        Scene &scene = *(Scene *)s;
+        const RenderOption &opts = scene.m_opts;
+        const Integrator &I = *(Integrator *)Iv;
+        const int64_t n = (int64_t)opts.width * opts.height * opts.spp;
+        auto run = [&](auto tag) {
+            constexpr bool AD = decltype(tag)::value;
+            Int<AD> idx = arange<Int<AD>>(n);
+            if (opts.spp > 1) idx /= opts.spp;
+            Vector2f<AD> base = gather<Vector2f<AD>>(meshgrid(arange<Float<AD>>(opts.width), arange<Float<AD>>(opts.height)), idx);
+            Vector2f<AD> samples = (base + scene.m_samplers[0].next_2d<AD>()) / ScalarVector2f(opts.width, opts.height);
+            Ray<AD> ray = scene.m_sensors[sensor]->sample_primary_ray(samples);
+            for (int k = 0; k < skip_dims; ++k) scene.m_samplers[0].next_1d<false>();
+            Spectrum<AD> value = I.Li(scene, scene.m_samplers[0], ray);
+            for (int c = 0; c < 3; ++c) for (int64_t i = 0; i < n; ++i) out[3 * i + c] = lval(detach(value[c]), i);
+        };
+        if (ad) run(std::true_type()); else run(std::false_type());
+    });
+}
+int ref_preprocess_secondary_edges(void *s, void *I, int sensor, const int *reso4, int nrounds) {
+    return guard([&] { ((Integrator *)I)->preprocess_secondary_edges(*(Scene *)s, sensor, ScalarVector4i(reso4[0], reso4[1], reso4[2], reso4[3]), nrounds); });
+}
+
+// ---- parameters: tangents (what ek.set_requires_gradient + ek.forward seed in the reference's Python flow) and values --------------------------
+// which: 0 reflectance | 1 alpha_u | 2 alpha_v | 3 eta | 4 k | 5 specular_reflectance; t has one entry (x3) per texel, or null to clear
+int ref_set_bsdf_tangent(void *s, int bsdf, int which, const float *t) {
+    return guard([&] {
+        BSDF *b = ((Scene *)s)->m_bsdfs.at(bsdf);
+        if (auto *d = dynamic_cast<Diffuse *>(b)) { PSDR_ASSERT(which == 0); set_tangent(d->m_reflectance.m_data, t, slices(d->m_reflectance.m_data)); return; }
+        auto *r = dynamic_cast<RoughConductor *>(b);
+        PSDR_ASSERT(r != nullptr);
+        switch (which) {
+            case 1: set_tangent(r->m_alpha_u.m_data, t, slices(r->m_alpha_u.m_data), 1, 0); break;
+            case 2: set_tangent(r->m_alpha_v.m_data, t, slices(r->m_alpha_v.m_data), 1, 0); break;
+            case 3: set_tangent(r->m_eta.m_data, t, slices(r->m_eta.m_data)); break;
+            case 4: set_tangent(r->m_k.m_data, t, slices(r->m_k.m_data)); break;
+            case 5: set_tangent(r->m_specular_reflectance.m_data, t, slices(r->m_specular_reflectance.m_data)); break;
+            default: PSDR_ASSERT(false);
+        }
+    });
+}
+int ref_set_bsdf_texture(void *s, int bsdf, int which, const float *data, int width, int height) {
+    return guard([&] {
+        BSDF *b = ((Scene *)s)->m_bsdfs.at(bsdf);
+        const size_t n = (size_t)width * height;
+        auto fill3 = [&](Bitmap3fD &bm) { std::vector<float> ch(n); Vector3fD v; for (int c = 0; c < 3; ++c) { for (size_t i = 0; i < n; ++i) ch[i] = data[3 * i + c]; v[c] = FloatD::copy(ch.data(), n); } bm.m_data = v; bm.m_resolution = ScalarVector2i(width, height); };
+        auto fill1 = [&](Bitmap1fD &bm) { bm.m_data = FloatD::copy(data, n); bm.m_resolution = ScalarVector2i(width, height); };
+        if (auto *d = dynamic_cast<Diffuse *>(b)) { PSDR_ASSERT(which == 0); fill3(d->m_reflectance); return; }
+        auto *r = dynamic_cast<RoughConductor *>(b);
+        PSDR_ASSERT(r != nullptr);
+        switch (which) {
+            case 1: fill1(r->m_alpha_u); break;
+            case 2: fill1(r->m_alpha_v); break;
+            case 3: fill3(r->m_eta); break;
+            case 4: fill3(r->m_k); break;
+            case 5: fill3(r->m_specular_reflectance); break;
+            default: PSDR_ASSERT(false);
+        }
+    });
+}
+int ref_mesh_num_vertices(void *s, int mesh) { return ((Scene *)s)->m_meshes.at(mesh)->m_num_vertices; }
+int ref_set_mesh_vertex_tangent(void *s, int mesh, const float *t) {   // d(m_vertex_positions_raw)[nv][3]; needs configure() afterwards
+    return guard([&] { Mesh *m = ((Scene *)s)->m_meshes.at(mesh); set_tangent(m->m_vertex_positions_raw, t, m->m_num_vertices); m->m_ready = false; });
+}
+int ref_set_mesh_uv_tangent(void *s, int mesh, const float *t) {
+    return guard([&] { Mesh *m = ((Scene *)s)->m_meshes.at(mesh); set_tangent(m->m_vertex_uv, t, slices(m->m_vertex_uv)); m->m_ready = false; });
+}
+int ref_set_mesh_transform(void *s, int mesh, const float *mat16, int left) {   // Mesh::set_transform
+    return guard([&] { Matrix4fD M; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) M(i, j) = FloatD(mat16[4 * i + j]); ((Scene *)s)->m_meshes.at(mesh)->set_transform(M, left != 0); });
+}
+int ref_set_mesh_transform_tangent(void *s, int mesh, const float *t16, int left) {
+    return guard([&] { Mesh *m = ((Scene *)s)->m_meshes.at(mesh); set_tangent(left ? m->m_to_world_left : m->m_to_world_right, t16); m->m_ready = false; });
+}
+int ref_set_sensor_transform_tangent(void *s, int sensor, const float *t16) {
+    return guard([&] { set_tangent(((Scene *)s)->m_sensors.at(sensor)->m_to_world, t16); });
+}
+int ref_set_envmap_tangent(void *s, const float *radiance_t, float scale_t) {
+    return guard([&] {
+        EnvironmentMap *e = ((Scene *)s)->m_emitter_env;
+        PSDR_ASSERT(e != nullptr);
+        set_tangent(e->m_radiance.m_data, radiance_t, slices(e->m_radiance.m_data));
+        if (scale_t != 0.f) set_tangent(e->m_scale, &scale_t, 1, 1, 0); else set_tangent(e->m_scale, nullptr, 1, 1, 0);
+    });
+}
+int ref_set_envmap_transform_tangent(void *s, const float *t16) {   // d(m_to_world_left), EnvironmentMap::set_transform's argument
+    return guard([&] { EnvironmentMap *e = ((Scene *)s)->m_emitter_env; PSDR_ASSERT(e != nullptr); set_tangent(e->m_to_world_left, t16); e->m_ready = false; });
+}
+
+// ---- tables, in the oracle's introspection layouts (oracle/orc_capi.cpp) ----------------------------------------------------------------------
+int ref_num_triangles(void *s) { return (int)slices(((Scene *)s)->m_triangle_info); }
+int ref_get_triangle_info(void *s, float *out) {   // [n][22]: p0 e1 e2 n0 n1 n2 face_normal face_area
+    const TriangleInfoD &t = ((Scene *)s)->m_triangle_info;
+    const Vector3fD *v[7] = {&t.p0, &t.e1, &t.e2, &t.n0, &t.n1, &t.n2, &t.face_normal};
+    const size_t n = slices(t);
+    for (size_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 7; ++k) for (int c = 0; c < 3; ++c) out[22 * i + 3 * k + c] = (*v[k])[c][i];
+        out[22 * i + 21] = t.face_area[i];
+    }
+    return 0;
+}
+int ref_num_sec_edges(void *s) { return ((Scene *)s)->m_opts.sppse > 0 ? (int)slices(((Scene *)s)->m_sec_edge_info) : 0; }
+int ref_get_sec_edges(void *s, float *out) {   // [n][16]: p0 e1 n0 n1 p2 is_boundary
+    const SecondaryEdgeInfo &e = ((Scene *)s)->m_sec_edge_info;
+    const Vector3fD *v[5] = {&e.p0, &e.e1, &e.n0, &e.n1, &e.p2};
+    const size_t n = slices(e);
+    for (size_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 5; ++k) for (int c = 0; c < 3; ++c) out[16 * i + 3 * k + c] = (*v[k])[c][i];
+        out[16 * i + 15] = e.is_boundary[i] ? 1.f : 0.f;
+    }
+    return 0;
+}
+int ref_num_primary_edges(void *s, int sensor) { const Sensor *c = ((Scene *)s)->m_sensors.at(sensor); return c->m_enable_edges ? (int)slices(c->m_edge_info) : 0; }
+int ref_get_primary_edges(void *s, int sensor, float *out) {   // [n][7]: p0.xy p1.xy edge_normal.xy edge_length
+    const PrimaryEdgeInfo &e = ((Scene *)s)->m_sensors.at(sensor)->m_edge_info;
+    const size_t n = slices(e);
+    for (size_t i = 0; i < n; ++i) {
+        out[7 * i + 0] = e.p0.x()[i]; out[7 * i + 1] = e.p0.y()[i]; out[7 * i + 2] = e.p1.x()[i]; out[7 * i + 3] = e.p1.y()[i];
+        out[7 * i + 4] = e.edge_normal.x()[i]; out[7 * i + 5] = e.edge_normal.y()[i]; out[7 * i + 6] = e.edge_length[i];
+    }
+    return 0;
+}
+int ref_get_sensor(void *s, int sensor, float *out) {   // sample_to_camera(16) world_to_sample(16) to_world(16) camera_pos(3) camera_dir(3) inv_area(1)
+    return guard([&] {
+        auto *c = dynamic_cast<PerspectiveCamera *>(((Scene *)s)->m_sensors.at(sensor));
+        PSDR_ASSERT(c != nullptr);
+        const Matrix4fD *m[3] = {&c->m_sample_to_camera, &c->m_world_to_sample, &c->m_to_world};
+        for (int k = 0; k < 3; ++k) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[16 * k + 4 * i + j] = (*m[k])(i, j)[0];
+        for (int k = 0; k < 3; ++k) { out[48 + k] = c->m_camera_pos[k][0]; out[51 + k] = c->m_camera_dir[k][0]; }
+        out[54] = c->m_inv_area[0];
+    });
+}
+int ref_mesh_num_edges(void *s, int mesh) { return (int)slices(((Scene *)s)->m_meshes.at(mesh)->m_edge_indices); }
+int ref_mesh_get_edges(void *s, int mesh, int *out) {   // [n][5]: Mesh::m_edge_indices (mesh.cpp:143-203)
+    const auto &e = ((Scene *)s)->m_meshes.at(mesh)->m_edge_indices;
+    const size_t n = slices(e);
+    for (size_t i = 0; i < n; ++i) for (int k = 0; k < 5; ++k) out[5 * i + k] = e[k][i];
+    return 0;
+}
+// Scene::ray_intersect<false> on n rays -> global triangle id, shape index into m_meshes, OptiX-style barycentrics and its.t
+int ref_trace(void *s, int64_t n, const float *o, const float *d, int *tri, int *shape, float *u, float *v, float *t) {
+    return guard([&] {
+        Scene &scene = *(Scene *)s;
+        std::vector<float> buf(n);
+        Vector3fC O, D;
+        for (int c = 0; c < 3; ++c) { for (int64_t i = 0; i < n; ++i) buf[i] = o[3 * i + c]; O[c] = FloatC::copy(buf.data(), n); for (int64_t i = 0; i < n; ++i) buf[i] = d[3 * i + c]; D[c] = FloatC::copy(buf.data(), n); }
+        IntersectionC its = scene.ray_intersect<false>(RayC(O, D), MaskC(true));
+        const Intersection_OptiX &h = scene.m_optix->m_its;
+        for (int64_t i = 0; i < n; ++i) {
+            tri[i] = h.triangle_id[i]; u[i] = h.uv.x()[i]; v[i] = h.uv.y()[i]; t[i] = its.t[i];
+            shape[i] = -1;
+            for (int k = 0; k < scene.m_num_meshes; ++k) if (its.shape[i] == scene.m_meshes[k]) shape[i] = k;
+        }
+    });
+}
+
+}  // extern "C"

@@ -270,7 +270,12 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
     if (!(sinphi > kEpsilon && sinphi2 > kEpsilon)) return;
     const float base_v = (its1.t / dist) * (sinphi / sinphi2) * cos2;
     const float3 d0 = -cam_d, d0_local = its1.sh.to_local(d0);
-    float3 bsdf_val = bsdf_eval(its_bsdf(P.S, its1), its1, d0_local, true);
+    // direct.cpp:278-284: with one BSDF (or one mesh) in the scene the reference evaluates meshes[0]'s BSDF without looking at the mesh
+    // that was hit, so an end point on the environment map's bounding mesh (no BSDF of its own; not masked out here as it is in Li,
+    // direct.cpp:58-61) is shaded with it. Reproduced for parity (seen by running the reference's source: tests/test_ref_render.py).
+    const BsdfRec *b1 = its_bsdf(P.S, its1);
+    if (its1.valid && (P.S.num_bsdfs == 1 || P.S.num_meshes == 1)) b1 = P.S.meshes[0].bsdf >= 0 ? P.S.bsdfs + P.S.meshes[0].bsdf : nullptr;
+    float3 bsdf_val = bsdf_eval(b1, its1, d0_local, true);
     const float correction = fabsf((its1.wi.z * dot(d0, its1.n)) / (d0_local.z * dot(dir, its1.n)));
     bsdf_val = bsdf_val * correction;
     float3 value0 = bsdf_val * emitter_Le(P.S, its2, true) * (base_v * sds.sensor_val / bss.pdf);
