@@ -1,4 +1,4 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned: the reference ships no golden vectors).
+"""ORACLE — TEST INFRASTRUCTURE ONLY (parity pinned against the reference's own source run on the CPU, oracle/_ref/libref_render.so: DESIGN.md §2).
 
 ctypes driver + an independent Mitsuba-XML / OBJ loader for the CPU restatement in oracle/*.hpp.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may import this.

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned; see orc_math.hpp header and DESIGN.md).
+// ORACLE — TEST INFRASTRUCTURE ONLY (parity pinned against the reference's own source run on the CPU; see orc_math.hpp header and DESIGN.md §2).
 //
 // C entry points over the CPU restatement so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // `--impl reference` leg can drive it through ctypes. The product never links or loads this library.

@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned: the reference ships no golden vectors).
+// ORACLE — TEST INFRASTRUCTURE ONLY. Parity pinned against the reference's own source: psdr-cuda's renderer compiled unmodified from
+// /root/reference against CPU stand-ins for its external dependencies Enoki and OptiX (oracle/_ref/libref_render.so, tests/test_ref_render.py,
+// tests/test_ref_math.py, tests/test_ref_ingest.py); what stays assumed is Enoki's / OptiX's own rounding and tie-breaking.
 //
 // Scalar fp32 / forward-mode-dual math used by the CPU restatement of psdr-cuda's hot path.
 // Nothing under oracle/ may be imported, linked or executed by the product (psdr_cuda_b200/);

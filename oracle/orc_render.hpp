@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned; see orc_math.hpp header and DESIGN.md).
+// ORACLE — TEST INFRASTRUCTURE ONLY (parity pinned against the reference's own source run on the CPU; see orc_math.hpp header and DESIGN.md §2).
 //
 // CPU restatement of psdr-cuda's sensor, scene, BSDF, emitter and integrator layers. R = float is the
 // reference's "C" flavour, R = Dual (one forward-mode tangent) its "D" flavour; detach() drops the tangent.

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned; see orc_math.hpp header and DESIGN.md).
+// ORACLE — TEST INFRASTRUCTURE ONLY (parity pinned against the reference's own source run on the CPU; see orc_math.hpp header and DESIGN.md §2).
 //
 // CPU restatement of psdr-cuda's scene layer: RNG, discrete / hyper-cube distributions, bitmap lookup,
 // mesh preprocessing + edge lists, perspective sensor, exact closest-hit ray casting, Scene::configure.

@@ -2,7 +2,7 @@
 tinyexr (+ miniz), compiled in place from /root/reference by oracle/build_ref.sh and called the way Mesh::load (mesh.cpp:62-141) and
 BitmapLoader::load_openexr_rgba (bitmap_loader.cpp:13-53) call them. Every fixture OBJ and the environment map must come out of the
 oracle's loader, the product's Python loader and the product's C++ loader exactly as out of the reference's parsers.
-(The renderer itself needs Enoki + OptiX and cannot be built here: parity of the rendering path stays unpinned)"""
+(The renderer itself is pinned separately, against its own source compiled with stand-ins for Enoki + OptiX: tests/test_ref_render.py.)"""
 import ctypes as C
 import glob
 import os
