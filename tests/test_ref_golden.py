@@ -1,0 +1,107 @@
+"""tests/golden/ref_source_golden.npz holds outputs of psdr-cuda's OWN renderer source run on the CPU (oracle/_ref/libref_render.so, see
+tests/golden/make_ref_golden.py and DESIGN.md §2). It travels in git, so here the oracle (CPU test) and the CUDA product through the C ABI
+(GPU test, on the box where /root/reference does not exist) are each compared DIRECTLY with what the reference's code computes, case by
+case: renderC images, field images, and renderD forward-mode derivative images for albedo, rough-conductor roughness, envmap scale and
+vertex translation through the interior, primary-edge and secondary-edge terms.
+
+Tolerance: per pixel 2e-4 (images) / 1e-3 (derivative images) of the image maximum, for all but a bounded share of the non-zero pixels:
+the knife-edge lanes of tests/test_ref_render.py (last-bit differences in the camera ray flip a grazing shadow ray or a primary-edge ray
+pair 1e-5 off a silhouette). The projections (image sums) must agree to what those pixels can carry."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, scene_path
+
+_spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(GOLDEN, "make_ref_golden.py"))
+gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gen)
+CASES = gen.cases()
+# allowed share of non-zero pixels over tolerance (image, derivative image)
+OUTLIERS = {"d_cbox_primary": 0.25, "d_cbox_secondary": 0.08, "d_env_secondary": 0.08}
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLDEN, "ref_source_golden.npz"))
+
+
+def close(a, b, rel, outliers, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape and np.isfinite(a).all(), what
+    scale = max(np.abs(b).max(), 1e-12)
+    d = np.abs(a - b).max(axis=1)
+    bad = int((d > rel * scale).sum())
+    nz = int(((np.abs(a).max(axis=1) > 0) | (np.abs(b).max(axis=1) > 0)).sum())
+    allowed = max(1, int(np.ceil(outliers * nz)))
+    assert bad <= allowed, "%s: %d of %d non-zero pixels over %g of the maximum (allowed %d), worst %g" % (what, bad, nz, rel, allowed, d.max() / scale)
+    assert abs(a.sum() - b.sum()) <= 2e-3 * np.abs(b).sum() + (bad + 1) * scale, what
+
+
+@pytest.mark.parametrize("label", sorted(CASES))
+def test_oracle_matches_reference_source_goldens(label, golden):
+    from oracle import orc
+    name, (w, h, spp, sppe, sppse), integ, leaf = CASES[label]
+    desc = orc.load_scene_description(scene_path(name))
+    sc = orc.Scene(desc, dict(width=w, height=h, spp=spp, sppe=sppe, sppse=sppse))
+    gen.seed(sc, leaf, len(desc["meshes"][leaf[1]]["verts"]) if leaf and leaf[0] == "translate" else 0)
+    sc.configure()
+    I = orc.DirectIntegrator(integ[1], integ[2]) if integ[0] == "direct" else orc.FieldExtractionIntegrator(integ[1])
+    if leaf is None:
+        close(I.renderC(sc), golden[label], 2e-4 if integ[0] == "direct" else 2e-5, 0.01, label)
+    else:
+        img, dimg = I.renderD(sc)
+        if np.abs(golden[label]).max() > 0:
+            close(img, golden[label], 2e-4, 0.01, label)
+        else:
+            assert np.abs(img).max() == 0
+        close(dimg, golden[label + "_t"], 1e-3, OUTLIERS.get(label, 0.02), label + " derivative")
+
+
+def test_oracle_tables_match_reference_source_goldens(golden):
+    from oracle import orc
+    sc = orc.Scene(orc.load_scene_description(scene_path("cbox_bunny")), dict(width=16, height=16, spp=1, sppe=1, sppse=1))
+    sc.configure()
+    tri, sec, prim = sc.triangle_info(), sc.sec_edges(), sc.primary_edges()
+    assert [len(tri), len(sec), len(prim)] == list(golden["t_counts"])
+    assert np.abs(tri[::97] - golden["t_tri_rows"]).max() <= 4e-7 * np.abs(tri).max()
+    assert np.abs(sec[::97] - golden["t_sec_rows"]).max() <= 4e-7 * np.abs(sec).max()
+    assert np.abs(prim[::97][:, :4] - golden["t_prim_rows"][:, :4]).max() <= 2e-6
+    assert np.allclose(tri.astype(np.float64).sum(0), golden["t_tri_sum"], rtol=1e-6, atol=1e-3)
+    assert np.allclose(sec.astype(np.float64).sum(0), golden["t_sec_sum"], rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("label", sorted(CASES))
+def test_cuda_matches_reference_source_goldens(label, golden):
+    """the sm_100a path through the C ABI against the reference-source vectors (no oracle in between)"""
+    torch = pytest.importorskip("torch")
+    from psdr_cuda_b200 import capi, scene_io
+    name, (w, h, spp, sppe, sppse), integ, leaf = CASES[label]
+    desc = scene_io.load_scene_description(scene_path(name))
+    ctx = capi.Context(0)
+    ctx.load_description(desc, dict(width=w, height=h, spp=spp, sppe=sppe, sppse=sppse))
+    u = None
+    if leaf is not None:
+        if leaf[0] == "bsdf":
+            ctx.grad_require(capi.PARAM_BSDF_TEXTURE, leaf[1], leaf[2])
+            u = np.asarray(leaf[3], np.float32)
+        elif leaf[0] == "translate":
+            ctx.grad_require(capi.PARAM_MESH_VERTICES, leaf[1])
+            u = np.tile(np.asarray([gen.TRANSLATE], np.float32), (len(desc["meshes"][leaf[1]]["verts"]), 1))
+        elif leaf[0] == "env_scale":
+            ctx.grad_require(capi.PARAM_ENVMAP_SCALE, 0)
+            u = np.ones(1, np.float32)
+    ctx.configure()
+    I = capi.make_integrator("direct", bsdf_samples=integ[1], light_samples=integ[2]) if integ[0] == "direct" else capi.make_integrator("field", field=integ[1])
+    if leaf is None:
+        close(ctx.render_c(I).cpu().numpy(), golden[label], 2e-4 if integ[0] == "direct" else 2e-5, 0.01, label)
+    else:
+        img = ctx.render_d(I).cpu().numpy()
+        dimg = ctx.render_d_jvp(I, torch.from_numpy(u.reshape(-1)).cuda()).cpu().numpy()
+        if np.abs(golden[label]).max() > 0:
+            close(img, golden[label], 2e-4, 0.01, label)
+        close(dimg, golden[label + "_t"], 1e-3, 1.5 * OUTLIERS.get(label, 0.02), label + " derivative")
+    ctx.close()
