@@ -801,10 +801,17 @@ inline V3<R> Li(const Integrator &I, const Scene &scene, SamplerLane &smp, const
 }
 
 // integrator.cpp:64-95. out/out_t: W*H*3 interleaved image and (R = Dual) its tangent.
+// scene.cpp:404: emitter sampling on a scene without emitters is an error. Raised here, before the OpenMP loops (an exception must not leave
+// a parallel region): Li samples emitters when the integrator has light samples (every Path event does), the secondary-edge sampler always.
+inline void require_emitters(const Integrator &I, const Scene &scene, bool edge_sampler = false) {
+    const bool needs = edge_sampler || (I.kind == INTEG_DIRECT && I.light_samples > 0) || I.kind == INTEG_PATH;
+    if (needs && scene.emitters.empty()) throw std::runtime_error("No Emitter!");
+}
 template <class R>
 inline void render_interior(const Integrator &I, Scene &scene, int sensor_id, float *out, float *out_t) {
     if (!scene.ready) throw std::runtime_error("Input scene must be configured!");
     if (sensor_id < 0 || sensor_id >= (int)scene.sensors.size()) throw std::runtime_error("Invalid sensor id!");
+    require_emitters(I, scene);
     const RenderOption &o = scene.opts;
     const int npix = o.width * o.height;
     if (o.spp <= 0) return;
@@ -837,6 +844,7 @@ inline void render_primary_edges(const Integrator &I, Scene &scene, int sensor_i
     const RenderOption &o = scene.opts;
     const Sensor &sensor = scene.sensors[sensor_id];
     if (!sensor.enable_edges) return;
+    require_emitters(I, scene);
     const int64_t n = (int64_t)o.width * o.height * o.sppe;
     auto &lanes = scene.samplers[1];
     std::vector<float> contrib((size_t)n * 3, 0.f);
@@ -931,6 +939,7 @@ inline int eval_secondary_edge(const Scene &scene, const Sensor &sensor, const V
 inline void preprocess_secondary_edges(Integrator &I, Scene &scene, int sensor_id, const int reso[4], int nrounds) {
     if (nrounds <= 0) throw std::runtime_error("nrounds > 0");
     if (!scene.ready) throw std::runtime_error("Scene needs to be configured!");
+    require_emitters(I, scene, true);
     if (I.warpper.size() != scene.sensors.size()) I.warpper.resize(scene.sensors.size());
     if (!I.warpper[sensor_id]) I.warpper[sensor_id] = std::make_unique<HyperCube<3>>();
     HyperCube<3> &w = *I.warpper[sensor_id];
@@ -968,6 +977,7 @@ inline void render_secondary_edges(const Integrator &I, Scene &scene, int sensor
     const RenderOption &o = scene.opts;
     const Sensor &sensor = scene.sensors[sensor_id];
     const int64_t n = (int64_t)o.width * o.height * o.sppse;
+    require_emitters(I, scene, true);
     auto &lanes = scene.samplers[2];
     const HyperCube<3> *w = (I.warpper.empty() || !I.warpper[sensor_id]) ? nullptr : I.warpper[sensor_id].get();
     std::vector<float> contrib((size_t)n * 3, 0.f);

@@ -151,6 +151,8 @@ def test_missing_emitter_raises_like_the_reference():
     r, o = pair("bunny", 12, 12, 1)
     with pytest.raises(RuntimeError, match="No Emitter"):
         refrun.DirectIntegrator(1, 1).renderC(r)
+    with pytest.raises(RuntimeError, match="No Emitter"):
+        orc.DirectIntegrator(1, 1).renderC(o)
     a, b = refrun.DirectIntegrator(1, 0).renderC(r), orc.DirectIntegrator(1, 0).renderC(o)
     assert np.abs(a).max() == 0 and np.abs(b).max() == 0
 
