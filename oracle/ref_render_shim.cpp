@@ -373,4 +373,83 @@ int ref_trace(void *s, int64_t n, const float *o, const float *d, int *tri, int 
     });
 }
 
+// ---- the reference's utility classes that its Python module exposes (src/psdr.cpp:140-164, 100-118, 242-265), for pinning the host-side
+//      mirrors in psdr_cuda_b200/compat/psdr_cuda/_surface.py ---------------------------------------------------------------------------------
+// DiscreteDistribution::init + sample (pmf.cpp:7-27) and sample_reuse (pmf.cpp:30-50)
+int ref_discrete_sample(const float *pmf, int n, const float *u, int m, int reuse, int *idx, float *pdf, float *u_out) {
+    return guard([&] {
+        DiscreteDistribution d;
+        d.init(FloatC::copy(pmf, n));
+        FloatC samples = FloatC::copy(u, m);
+        auto r = reuse ? d.sample_reuse<false>(samples) : d.sample(samples);
+        for (int i = 0; i < m; ++i) { idx[i] = lval(r.first, i); pdf[i] = lval(r.second, i); u_out[i] = lval(samples, i); }
+    });
+}
+// HyperCubeDistribution<ndim>: set_resolution + set_mass + sample_reuse + pdf (cube_distrb.cpp:8-62); samples[m][ndim] in, warped samples out
+int ref_hypercube(int ndim, const int *reso, const float *mass, const float *samples, int m, float *warped, float *pdf_sample, float *pdf_eval, int *cells) {
+    return guard([&] {
+        auto run = [&](auto &hc, auto reso_v, auto smp) {
+            hc.set_resolution(reso_v);
+            hc.set_mass(FloatC::copy(mass, hc.m_num_cells));
+            std::vector<float> buf(m);
+            for (int c = 0; c < ndim; ++c) { for (int i = 0; i < m; ++i) buf[i] = samples[i * ndim + c]; smp[c] = FloatC::copy(buf.data(), m); }
+            FloatC pe = hc.pdf(smp);
+            FloatC ps = hc.sample_reuse(smp);
+            for (int i = 0; i < m; ++i) { pdf_sample[i] = lval(ps, i); pdf_eval[i] = lval(pe, i); for (int c = 0; c < ndim; ++c) warped[i * ndim + c] = lval(smp[c], i); }
+            for (int k = 0; k < hc.m_num_cells; ++k) for (int c = 0; c < ndim; ++c) cells[k * ndim + c] = lval(hc.m_cells[c], k);
+        };
+        if (ndim == 2) { HyperCubeDistribution2f hc; run(hc, ScalarVector2i(reso[0], reso[1]), Vector2fC()); }
+        else { HyperCubeDistribution3f hc; run(hc, ScalarVector3i(reso[0], reso[1], reso[2]), Vector3fC()); }
+    });
+}
+// Bitmap<channels>::eval<false>(uv, flip_v) (bitmap.cpp:56-96) on a width x height texture given as [h][w][channels]
+int ref_bitmap_eval(int channels, int width, int height, const float *data, const float *uv, int m, int flip_v, float *out) {
+    return guard([&] {
+        const size_t n = (size_t)width * height;
+        std::vector<float> buf(std::max<size_t>(n, m));
+        Vector2fC q;
+        for (int c = 0; c < 2; ++c) { for (int i = 0; i < m; ++i) buf[i] = uv[2 * i + c]; q[c] = FloatC::copy(buf.data(), m); }
+        if (channels == 1) {
+            Bitmap1fD bm(width, height, FloatD::copy(data, n));
+            FloatC r = bm.eval<false>(q, flip_v != 0);
+            for (int i = 0; i < m; ++i) out[i] = lval(r, i);
+        } else {
+            Vector3fD v;
+            for (int c = 0; c < 3; ++c) { for (size_t i = 0; i < n; ++i) buf[i] = data[3 * i + c]; v[c] = FloatD::copy(buf.data(), n); }
+            Bitmap3fD bm(width, height, v);
+            Vector3fC r = bm.eval<false>(q, flip_v != 0);
+            for (int i = 0; i < m; ++i) for (int c = 0; c < 3; ++c) out[3 * i + c] = lval(r[c], i);
+        }
+    });
+}
+// Mesh::sample_position(sample2) of a configured scene's mesh (mesh.cpp:277-303; needs an emitter mesh: the others drop their triangle
+// table after Scene::configure, scene.cpp:245-262) -> p[m][3], n[m][3], pdf[m]
+int ref_mesh_sample_position(void *s, int mesh, const float *sample2, int m, float *p, float *n, float *pdf) {
+    return guard([&] {
+        const Mesh *M = ((Scene *)s)->m_meshes.at(mesh);
+        std::vector<float> buf(m);
+        Vector2fC q;
+        for (int c = 0; c < 2; ++c) { for (int i = 0; i < m; ++i) buf[i] = sample2[2 * i + c]; q[c] = FloatC::copy(buf.data(), m); }
+        PositionSampleC ps = M->sample_position(q, MaskC(true));
+        for (int i = 0; i < m; ++i) { for (int c = 0; c < 3; ++c) { p[3 * i + c] = lval(ps.p[c], i); n[3 * i + c] = lval(ps.n[c], i); } pdf[i] = lval(ps.pdf, i); }
+    });
+}
+// Mesh::m_vertex_normals_raw after configure (mesh.cpp:19-51 on the object-space positions)
+int ref_mesh_vertex_normals(void *s, int mesh, float *out) {
+    return guard([&] {
+        const Mesh *M = ((Scene *)s)->m_meshes.at(mesh);
+        for (int i = 0; i < M->m_num_vertices; ++i) for (int c = 0; c < 3; ++c) out[3 * i + c] = M->m_vertex_normals_raw[c][i];
+    });
+}
+// keys of Scene::m_param_map (scene_loader.cpp:184-240, 343-352), '\n'-separated
+const char *ref_param_map_keys(void *s) {
+    static thread_local std::string keys;
+    keys.clear();
+    std::vector<std::string> v;
+    for (const auto &kv : ((Scene *)s)->m_param_map) v.push_back(kv.first + "=" + kv.second.type_name());
+    std::sort(v.begin(), v.end());
+    for (const auto &k : v) keys += k + "\n";
+    return keys.c_str();
+}
+
 }  // extern "C"

@@ -19,10 +19,14 @@ import os
 import numpy as np
 
 from . import _psdr_host as _h
-from ._psdr_host import (AreaLight, BitmapD, DiffuseBSDF, EnvironmentMap, Mesh, Object, PerspectiveCamera, RenderOption,  # noqa: F401
+from . import _surface
+from ._psdr_host import (BSDF, AreaLight, BitmapD, DiffuseBSDF, Emitter, EnvironmentMap, Mesh, Object, PerspectiveCamera, RenderOption,  # noqa: F401
                          RoughConductorBSDF)
+from ._surface import (DiscreteDistribution, FrameC, FrameD, HyperCubeDistribution2f, HyperCubeDistribution3f, PositionSampleC,  # noqa: F401
+                       PositionSampleD, RayC, RayD, SampleRecordC, SampleRecordD)
 
 Bitmap1fD = Bitmap3fD = BitmapD
+Sensor = PerspectiveCamera   # src/psdr.cpp:216-222: the reference's only Sensor is the PerspectiveCamera; one class serves both names
 
 
 def _read_exr(path, channels):
@@ -38,6 +42,31 @@ def _read_exr(path, channels):
     else:
         img = img[:, :, [2, 1, 0] + list(range(3, img.shape[2]))]
     return np.ascontiguousarray(img[:, :, :channels])
+
+
+def _bitmap_load_openexr(self, file_name):
+    """Bitmap::load_openexr (bitmap.cpp:34-43): channel 0 for Bitmap1fD, RGB for Bitmap3fD"""
+    img = _read_exr(file_name, self.channels)
+    self.resolution = (img.shape[1], img.shape[0])
+    self.data = img.reshape(-1, self.channels) if self.channels == 3 else img.reshape(-1)
+
+
+BitmapD.load_openexr = _bitmap_load_openexr
+BitmapD.eval = _surface.bitmap_eval                                               # src/psdr.cpp:107,117
+Mesh.vertex_normals = property(_surface.mesh_vertex_normals)                      # src/psdr.cpp:253
+Mesh.edge_indices = _surface.mesh_edge_indices                                    # src/psdr.cpp:263
+Mesh.sample_position = _surface.mesh_sample_position                              # src/psdr.cpp:248-249
+Mesh.bsdf = property(lambda self: None)                                           # src/psdr.cpp:251; param_map entries resolve it (see _Proxy)
+
+
+def _mesh_configure(self):
+    """Mesh::configure (mesh.cpp:215-274) for a stand-alone mesh: validates it; the tables are built on the device by Scene.configure"""
+    if self.num_vertices == 0 or self.num_faces == 0:
+        raise RuntimeError("Mesh::configure: empty mesh")
+    _surface.mesh_vertex_normals(self)
+
+
+Mesh.configure = _mesh_configure                                                  # src/psdr.cpp:245
 
 
 def _enoki():
@@ -60,6 +89,9 @@ class _Proxy:
         obj = object.__getattribute__(self, "_obj")
         if name == "vertex_positions" and _enoki() is not None:
             return _enoki().Vector3f(obj.vertex_positions)
+        if name == "bsdf" and obj.type_name() == "Mesh":      # Mesh::m_bsdf (src/psdr.cpp:251)
+            scene = object.__getattribute__(self, "_scene")
+            return scene._raw_param_map().get("BSDF[%d]" % obj.bsdf_index) if obj.bsdf_index >= 0 else None
         return getattr(obj, name)
 
     def __setattr__(self, name, value):
@@ -340,3 +372,5 @@ class FieldExtractionIntegrator(_IntegratorMixin, _h.FieldExtractionIntegrator):
 
 
 Integrator = _h.Integrator
+# src/psdr.cpp:283-286: renderC / renderD live on the Integrator base, so every integrator object answers them
+Integrator.renderC, Integrator.renderD, Integrator.forward = _IntegratorMixin.renderC, _IntegratorMixin.renderD, _IntegratorMixin.forward

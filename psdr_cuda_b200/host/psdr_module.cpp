@@ -151,11 +151,11 @@ struct Bitmap {   // Bitmap1fD / Bitmap3fD (src/core/bitmap.cpp, src/psdr.cpp:10
 struct BSDF : Object { int index = -1; };
 struct Diffuse : BSDF {
     Bitmap reflectance{3, .5f};
-    std::string type_name() const override { return "DiffuseBSDF"; }
+    std::string type_name() const override { return "Diffuse"; }                // the C++ class name, as PSDR_CLASS_DECL_END yields (diffuse.h:41)
 };
 struct RoughConductor : BSDF {
     Bitmap alpha_u{1, .1f}, alpha_v{1, .1f}, eta{3, 0.f}, k{3, 1.f}, specular_reflectance{3, 1.f};
-    std::string type_name() const override { return "RoughConductorBSDF"; }
+    std::string type_name() const override { return "RoughConductor"; }         // roughconductor.h:54
 };
 
 struct Mesh : Object {
@@ -630,7 +630,8 @@ PYBIND11_MODULE(_psdr_host, m) {
     };
     bitmap("BitmapD");
 
-    py::class_<BSDF, Object, std::shared_ptr<BSDF>>(m, "BSDF").def_readonly("index", &BSDF::index);
+    py::class_<BSDF, Object, std::shared_ptr<BSDF>>(m, "BSDF").def_readonly("index", &BSDF::index)
+        .def("anisotropic", [](const BSDF &) { return false; });   // bsdf.h:33; every BSDF the loader / Python can create is isotropic (roughconductor.h:11-18)
     py::class_<Diffuse, BSDF, std::shared_ptr<Diffuse>>(m, "DiffuseBSDF")
         .def_property_readonly("reflectance", [](Diffuse &d) -> Bitmap & { return d.reflectance; }, py::return_value_policy::reference_internal);
     py::class_<RoughConductor, BSDF, std::shared_ptr<RoughConductor>>(m, "RoughConductorBSDF")
