@@ -335,3 +335,31 @@ def test_bitmap_textures():
     (a, at), (b, bt) = refrun.DirectIntegrator(1, 1).renderD(r), orc.DirectIntegrator(1, 1).renderD(o)
     assert_images_close(a, b, rel=2e-4, outliers=0.01, what="primal")
     assert_images_close(at, bt, rel=5e-4, outliers=0.02, what="tangent")
+
+
+def test_stand_in_tangents_are_derivatives_of_the_reference_run():
+    """independent of the oracle: the forward-mode tangent the Enoki stand-in carries through the reference's renderD equals the central
+    finite difference of the reference's own renderD image, for parameters that do not steer the sampling (conductor eta / k enter only
+    the Fresnel term, roughconductor.cpp:52-54; the envmap scale only the emitted radiance, envmap.cpp:53-57), with the sampler streams
+    held fixed (a fresh scene per evaluation)"""
+    def render(eta=None, k=None, tangent=None):
+        refrun.set_matvec_plain(True)
+        sc = refrun.Scene(scene_path("bunny_env"), TESTS, 16, 16, 2, 0, 0)
+        if eta is not None:
+            sc.set_bsdf_texture(0, "eta", np.asarray(eta, np.float32).reshape(1, 1, 3))
+        if k is not None:
+            sc.set_bsdf_texture(0, "k", np.asarray(k, np.float32).reshape(1, 1, 3))
+        if tangent is not None:
+            sc.set_bsdf_tangent(0, tangent[0], np.asarray(tangent[1], np.float32).reshape(1, 3))
+        sc.configure()
+        return refrun.DirectIntegrator(1, 1).renderD(sc)
+    b = desc("bunny_env")["bsdfs"][0]
+    eta0, k0 = b["eta"].reshape(3).astype(np.float64), b["k"].reshape(3).astype(np.float64)
+    for name, base, direction in (("eta", eta0, np.array([1.0, 0.5, 0.25])), ("k", k0, np.array([0.3, 1.0, 0.6]))):
+        _, dimg = render(tangent=(name, direction))
+        h = 2e-2
+        plus = render(**{name: base + h * direction})[0].astype(np.float64)
+        minus = render(**{name: base - h * direction})[0].astype(np.float64)
+        fd = (plus - minus) / (2 * h)
+        assert np.abs(dimg).max() > 0
+        assert np.abs(fd - dimg).max() <= 2e-3 * np.abs(dimg).max(), (name, np.abs(fd - dimg).max(), np.abs(dimg).max())
