@@ -342,6 +342,28 @@ def test_transform_gradient_contraction_matches_finite_differences(psdr_cuda):
             assert abs(fd - g[i, j]) <= 1e-3 * max(1.0, abs(fd)), (left, i, j, fd, g[i, j])
 
 
+def test_cpp_loader_on_a_uv_mapped_two_sensor_scene(psdr_cuda, textured_scene):
+    """texture coordinates, uv face indices, a rotated mesh transform and a second sensor through the C++ ingest vs the oracle's loader
+    (itself compared with the reference's loader + configure on this scene in tests/test_ref_render.py)"""
+    from oracle import orc
+    ref = orc.load_scene_description(textured_scene)
+    sc = psdr_cuda.Scene(-1)
+    sc.load_file(textured_scene, False)
+    assert sc.num_sensors == 2 and sc.num_meshes == 3 and (sc.opts.width, sc.opts.height, sc.opts.spp) == (24, 16, 2)
+    pm = sc.param_map
+    for i, m in enumerate(ref["meshes"]):
+        o = pm["Mesh[%d]" % i]
+        assert np.array_equal(o.vertex_positions, m["verts"]) and np.array_equal(o.face_indices, m["faces"])
+        assert np.allclose(o.to_world_raw, m["to_world"], atol=1e-7)
+        if "uvs" in m:
+            assert o.has_uv and np.array_equal(o.vertex_uv, m["uvs"]) and np.array_equal(o.face_uv_indices, m["uv_faces"])
+        else:
+            assert not o.has_uv
+    for i, s in enumerate(ref["sensors"]):
+        assert np.allclose(pm["Sensor[%d]" % i].to_world, s["to_world"], atol=1e-7) and pm["Sensor[%d]" % i].fov_x == np.float32(s["fov"])
+    assert pm["Mesh[id=wall]"].bsdf.type_name() == "RoughConductor" and pm["BSDF[id=metal]"].alpha_u.data.reshape(-1)[0] == np.float32(0.3)
+
+
 # ---- the module surface against the reference's own pybind11 module (src/psdr.cpp), and its utilities against the reference's own code ----
 def test_python_surface_covers_the_reference_module(psdr_cuda):
     """tests/golden/ref_python_surface.json = every class / method / property psdr.cpp binds (tests/golden/make_ref_surface.py); each must

@@ -363,3 +363,51 @@ def test_stand_in_tangents_are_derivatives_of_the_reference_run():
         fd = (plus - minus) / (2 * h)
         assert np.abs(dimg).max() > 0
         assert np.abs(fd - dimg).max() <= 2e-3 * np.abs(dimg).max(), (name, np.abs(fd - dimg).max(), np.abs(dimg).max())
+
+
+@pytest.mark.parametrize("sensor,leaf", [(0, "texels"), (1, "texels"), (0, "rc_texels"), (0, "vertices"), (1, "uv"), (0, "boundary")])
+def test_textured_uv_mapped_scene_matches_reference_source(textured_scene, sensor, leaf):
+    """bitmap.cpp:56-96 inside a render (bilinear texels at interpolated, wrapped uvs), their derivative w.r.t. texels, w.r.t. the vertices
+    through the barycentrics (scene.cpp:338-341,361-364) and w.r.t. Mesh.vertex_uv, for a diffuse and a rough-conductor texture, from either
+    of two sensors (scene_loader.cpp:246-292: film and sampler come from the first)"""
+    rng = np.random.default_rng(21)
+    refrun.set_matvec_plain(True)
+    sppe = sppse = 8 if leaf == "boundary" else 0
+    spp = 0 if leaf == "boundary" else 4
+    r = refrun.Scene(textured_scene, TESTS, 0, 0, spp, sppe, sppse)
+    d = orc.load_scene_description(textured_scene)
+    assert (r.opts["width"], r.opts["height"]) == (24, 16) == (d["opts"]["width"], d["opts"]["height"])
+    o = orc.Scene(d, dict(spp=spp, sppe=sppe, sppse=sppse))
+    tex3 = rng.uniform(0.05, 0.95, (6, 9, 3)).astype(np.float32)
+    tex1 = rng.uniform(0.1, 0.6, (5, 4, 1)).astype(np.float32)
+    for s in (r, o):
+        s.set_bsdf_texture(0, "reflectance", tex3)
+        s.set_bsdf_texture(1, "alpha_u", tex1)
+        s.set_bsdf_texture(1, "alpha_v", tex1)
+    if leaf == "texels":
+        t = rng.uniform(0, 1, tex3.shape).astype(np.float32)
+        r.set_bsdf_tangent(0, "reflectance", t.reshape(-1, 3))
+        o.set_bsdf_tangent(0, "reflectance", t)
+    elif leaf == "rc_texels":
+        t = rng.uniform(0, 1, tex1.shape).astype(np.float32)
+        r.set_bsdf_tangent(1, "alpha_u", t.reshape(-1))
+        o.set_bsdf_tangent(1, "alpha_u", t)
+    elif leaf in ("vertices", "boundary"):
+        for m in (0, 1):
+            t = rng.normal(size=(4, 3)).astype(np.float32)
+            r.set_mesh_vertex_tangent(m, t)
+            o.set_mesh_vertex_tangent(m, t)
+    elif leaf == "uv":
+        t = rng.normal(size=(4, 2)).astype(np.float32)
+        r.set_mesh_uv_tangent(0, t)
+        o.set_mesh_uv_tangent(0, t)
+    r.configure()
+    o.configure()
+    (a, at), (b, bt) = refrun.DirectIntegrator(1, 1).renderD(r, sensor), orc.DirectIntegrator(1, 1).renderD(o, sensor)
+    assert np.abs(bt).max() > 0
+    if leaf != "boundary":
+        assert_images_close(a, b, rel=2e-4, outliers=0.01, what="primal")
+        a2, b2 = refrun.DirectIntegrator(1, 1).renderC(r, sensor), orc.DirectIntegrator(1, 1).renderC(o, sensor)
+        assert np.abs(b2).max() > 0
+        assert_images_close(a2, b2, rel=2e-4, outliers=0.01, what="renderC")
+    assert_images_close(at, bt, rel=1e-3, outliers=0.05 if leaf == "boundary" else 0.02, what="tangent")
