@@ -60,6 +60,11 @@ def set_matvec_plain(on):
     lib().ref_set_matvec_plain(int(on))
 
 
+def set_inverse_rounded(on):
+    """4x4 inverses computed in double precision and rounded (the oracle's / the product host's form) instead of an fp32 cofactor expansion"""
+    lib().ref_set_inverse_rounded(int(on))
+
+
 class Scene:
     """psdr::Scene: load_file(xml, auto_configure=False) + RenderOption overrides; configure() is explicit, as in the reference"""
 
