@@ -127,7 +127,7 @@ def _load_transform(node):
         if ch.tag == "translate":
             t = m_translate([g("x", 0), g("y", 0), g("z", 0)])
         elif ch.tag == "rotate":
-            t = m_rotate([g("x", 0), g("y", 0), g("z", 0)], float(np.float32(g("angle", 0)) * np.float32(math.pi) / np.float32(180)))
+            t = m_rotate([g("x", 0), g("y", 0), g("z", 0)], float(np.float32(g("angle", 0)) * (np.float32(math.pi) / np.float32(180))))
         elif ch.tag == "scale":
             t = m_scale([g("x", 1), g("y", 1), g("z", 1)])
         elif ch.tag in ("look_at", "lookAt", "lookat"):

@@ -42,7 +42,7 @@ inline M4f m_rotate(V3f a, float angle_rad) {   // right-handed rotation about a
 }
 inline M4f m_perspective(float fov_deg, float near_, float far_) {   // transform.h:45-59
     float recip = 1.f / (far_ - near_);
-    float t = std::tan(fov_deg * .5f * kPi / 180.f), cot = 1.f / t;
+    float t = std::tan((fov_deg * .5f) * (kPi / 180.f)), cot = 1.f / t;   // enoki::tan(deg_to_rad(fov * .5f)), deg_to_rad(a) = a * (Pi / 180)
     M4f m;
     m.m[0][0] = cot; m.m[1][1] = cot; m.m[2][2] = far_ * recip; m.m[3][3] = 0.f;
     m.m[2][3] = -near_ * far_ * recip; m.m[3][2] = 1.f;

@@ -144,7 +144,7 @@ static void configure_sensor(HostSensor &s, int W, int H) {
     sc.m[0] = -0.5f; sc.m[5] = -0.5f * aspect;
     tr.m[3] = -1.f; tr.m[7] = -1.f / aspect;
     const float recip = 1.f / (s.far_clip - s.near_clip);
-    const float tn = std::tan(s.fov_x * .5f * kPi / 180.f), cot = 1.f / tn;
+    const float tn = std::tan((s.fov_x * .5f) * (kPi / 180.f)), cot = 1.f / tn;   // transform.h:50: tan(deg_to_rad(fov * .5f)), deg_to_rad(a) = a * (Pi / 180)
     pe.m[0] = cot; pe.m[5] = cot; pe.m[10] = s.far_clip * recip; pe.m[15] = 0.f;
     pe.m[11] = -s.near_clip * s.far_clip * recip; pe.m[14] = 1.f;
     const Mat4h c2s = matmul(matmul(sc, tr), pe);

@@ -60,7 +60,7 @@ Mat4 mat_from_numpy(const farray &a) {
 Mat4 m_translate(float x, float y, float z) { Mat4 m; m.m[3] = x; m.m[7] = y; m.m[11] = z; return m; }
 Mat4 m_scale(float x, float y, float z) { Mat4 m; m.m[0] = x; m.m[5] = y; m.m[10] = z; return m; }
 Mat4 m_rotate(float x, float y, float z, float angle_deg) {
-    const float ang = angle_deg * 3.14159265358979323846f / 180.f;
+    const float ang = angle_deg * (3.14159265358979323846f / 180.f);   // transform.h:27: deg_to_rad(a) = a * (Pi / 180)
     const float s = (float)std::sin((double)ang), c = (float)std::cos((double)ang), k = 1.f - c;
     Mat4 m;
     m.m[0] = x * x * k + c;     m.m[1] = x * y * k - z * s; m.m[2] = x * z * k + y * s;

@@ -63,7 +63,7 @@ class Transform:
 
     @staticmethod
     def rotate(axis, angle_deg):
-        ang = float(F32(angle_deg) * F32(math.pi) / F32(180))
+        ang = float(F32(angle_deg) * (F32(math.pi) / F32(180)))   # transform.h:27: deg_to_rad(a) = a * (Pi / 180)
         s, c = F32(math.sin(ang)), F32(math.cos(ang))
         x, y, z = (F32(v) for v in axis)
         k = F32(1) - c

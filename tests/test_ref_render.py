@@ -8,8 +8,9 @@ reference's own ray/triangle arithmetic). Every test runs the same steps through
 What agrees and how closely: integer tables exactly; fp32 tables to the last bit or two; images and forward-mode derivative images to
 ~1e-5 of the image maximum per pixel, EXCEPT a small fraction of pixels (bounded below) in which one lane took the other side of a
 knife-edge decision — a shadow ray leaving a surface at grazing incidence, a primary-edge ray 1e-5 (sample space) off a silhouette — because
-the two differ in the last bit of the camera ray (the 4x4 inverse is computed differently). Those lanes are all-or-nothing in both
-directions (seen lane by lane in test_lane_radiance); they are fp32 conditioning of the reference's algorithm, not a difference in it.
+the two differ in last bits (the path-space hit point of the D flavour, the 4x4 inverse behind world_to_sample). Those lanes are
+all-or-nothing in both directions (seen lane by lane in test_lane_radiance); they are fp32 conditioning of the reference's algorithm, not
+a difference in it.
 
 What stays assumed: Enoki's and OptiX's own semantics — the stand-ins implement the same assumptions the oracle makes
 (exact rcp / rsqrt, sequential sums, closest hit with ties to the lowest id), so this file pins the oracle's reading of psdr-cuda's code,
@@ -76,17 +77,10 @@ def test_tables_match_reference_source(name):
         assert np.allclose(sr[k], so[k], rtol=2e-6, atol=1e-6 * np.abs(so[k]).max()), (k, sr[k], so[k])
     er, eo = r.sec_edges(), o.sec_edges()
     pr, po = r.primary_edges(), o.primary_edges()
-    if name == "tree":
-        # rotated meshes: sin / cos enter the vertex transform, positions differ in the last bit, and a handful of edges sit on the
-        # dot(n0, n1) < 1 - EdgeEpsilon / front-back facing thresholds; the lists agree as sets up to those
-        assert abs(len(er) - len(eo)) <= 4 and abs(len(pr) - len(po)) <= 4
-        key = lambda e: set(map(tuple, np.round(e[:, :6].astype(np.float64), 3)))
-        assert len(key(er) ^ key(eo)) <= 8
-        return
     assert er.shape == eo.shape and np.abs(er - eo).max() <= 4e-7 * max(1.0, np.abs(eo).max())
     assert pr.shape == po.shape
     # end points in sample space; the unit normal of an edge of length L carries the end points' rounding amplified by 1 / L
-    assert np.abs(pr[:, :4] - po[:, :4]).max() <= 2e-6
+    assert (np.abs(pr[:, :4] - po[:, :4]) <= 2e-6 * np.maximum(1.0, np.abs(po[:, :4]))).all()
     assert (np.abs(pr[:, 4:6] - po[:, 4:6]).max(axis=1) <= 1e-5 + 4e-7 / np.maximum(po[:, 6], 1e-12)).all()
     assert np.allclose(pr[:, 6], po[:, 6], rtol=1e-3, atol=1e-6)
 
@@ -176,7 +170,7 @@ def test_lane_radiance():
         d = np.abs(a - b).max(axis=1)
         scale = np.maximum(np.abs(b).max(axis=1), 1e-2)
         bad = np.nonzero(d > 1e-3 * scale)[0]
-        assert len(bad) <= 6, (ad, len(bad))
+        assert len(bad) <= 4, (ad, len(bad))
         for lane in bad:
             assert np.abs(a[lane]).max() == 0 or np.abs(b[lane]).max() == 0, (lane, a[lane], b[lane])
 
