@@ -44,14 +44,13 @@ struct PathTracerState {
 
 namespace psdr {
 
+// the per-launch output buffers of scene_optix.h:10-17, (re)allocated when the wavefront size changes
 void Intersection_OptiX::reserve(int64_t size) {
     PSDR_ASSERT(size > 0);
-    if (size != m_size) {
-        m_size = size;
-        triangle_id = empty<IntC>(size);
-        shape_id = empty<IntC>(size);
-        uv = empty<Vector2fC>(size);
-    }
+    if (m_size == size) return;
+    triangle_id = shape_id = zero<IntC>(size);
+    uv = zero<Vector2fC>(size);
+    m_size = size;
 }
 
 Scene_OptiX::Scene_OptiX() { m_accel = nullptr; }
