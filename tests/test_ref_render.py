@@ -406,3 +406,23 @@ def test_textured_uv_mapped_scene_matches_reference_source(textured_scene, senso
         assert np.abs(b2).max() > 0
         assert_images_close(a2, b2, rel=2e-4, outliers=0.01, what="renderC")
     assert_images_close(at, bt, rel=1e-3, outliers=0.05 if leaf == "boundary" else 0.02, what="tangent")
+
+
+@pytest.mark.parametrize("name,w,h,spp,sppe,sppse,bs,ls,hide,mesh", [
+    ("cbox_bunny_mutiemitter", 30, 20, 1, 0, 0, 2, 3, False, 1),      # spp = 1 (no division of the lane index), several samples of each kind
+    ("cbox_bunny_mutiemitter", 30, 20, 3, 2, 8, 3, 2, True, 0),       # hidden emitters, emitter-vertex tangent, all three terms
+    ("tree", 24, 24, 2, 4, 16, 1, 1, False, 2),                        # rotated / scaled meshes, all three terms
+    ("bunny_env_2", 32, 18, 2, 4, 16, 1, 1, False, 1),                 # two BSDFs + envmap: bounding-mesh end points get no BSDF
+    ("cbox_bunny_rc", 20, 20, 2, 2, 8, 2, 2, False, 2),
+])
+def test_mixed_configurations_match_reference_source(name, w, h, spp, sppe, sppse, bs, ls, hide, mesh):
+    """non-square films, spp = 1, several BSDF / emitter samples, hidden emitters, all three terms in one renderD"""
+    rng = np.random.default_rng(5)
+    r, o = pair(name, w, h, spp, sppe, sppse, configure=False)
+    _seed(r, o, ("vertices", mesh), rng, name)
+    r.configure()
+    o.configure()
+    (a, at), (b, bt) = refrun.DirectIntegrator(bs, ls, hide).renderD(r), orc.DirectIntegrator(bs, ls, hide).renderD(o)
+    assert np.abs(b).max() > 0 and np.abs(bt).max() > 0
+    assert_images_close(a, b, rel=1e-3, outliers=0.01, what="primal")
+    assert_images_close(at, bt, rel=1e-3, outliers=0.03, what="tangent")
