@@ -108,6 +108,30 @@ def oracle_sample(steps, warmup, w=256, h=256, spp=16):
                 sample="cbox_bunny %dx%d/%dspp PathIntegrator(max_depth=%d): renderC + renderD with one forward-mode tangent, OpenMP over pixels, mean of %d" % (w, h, spp, DEPTH, len(times)))
 
 
+def reference_source_sample(w=48, h=48, spp=4):
+    """psdr-cuda's OWN code (oracle/_ref/libref_render.so: its src/**/*.cpp compiled for the CPU against stand-ins for Enoki and OptiX,
+    DESIGN.md §2) on the nearest workload it has — the snapshot has no PathIntegrator: DirectIntegrator(1,1) renderC + renderD
+    with one forward-mode albedo tangent. Informational: the stand-in is a plain host-array implementation, not a tuned CPU renderer."""
+    try:
+        from oracle import refrun
+        import numpy as np
+        if not os.path.exists(refrun.LIB_PATH):
+            return None
+        refrun.set_matvec_plain(True)
+        sc = refrun.Scene(SCENE, os.path.join(ROOT, "tests"), w, h, spp, 0, 0)
+        sc.set_bsdf_tangent(0, "reflectance", np.ones((1, 3), np.float32))
+        sc.configure()
+        integ = refrun.DirectIntegrator(1, 1)
+        t0 = time.perf_counter()
+        integ.renderC(sc)
+        integ.renderD(sc)
+        t = time.perf_counter() - t0
+        return {"value": 2.0 * w * h * spp / t / 1e6, "unit": UNIT, "kind": "reference", "seconds": t,
+                "sample": "cbox_bunny %dx%d/%dspp DirectIntegrator(1,1): renderC + renderD with one forward-mode tangent, the reference's own source on a CPU stand-in for Enoki/OptiX (single thread + OpenMP ray cast)" % (w, h, spp)}
+    except Exception as e:   # the checker library is optional for the bench
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -118,7 +142,10 @@ def run_reference(args):
             "config": {"workload": "cbox_bunny.xml 512x512/256spp PathIntegrator(max_depth=5) renderC+renderD, diffuse-albedo gradients (timed on a bounded sample, normalised per path-sample)"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "psdr-cuda has no CPU path and its OptiX/Enoki build is unavailable offline (SURVEY F4): this arm is the CPU oracle port"}
+            "note": "psdr-cuda has no CPU path and its OptiX/Enoki build is unavailable offline (SURVEY F4): this arm is the CPU oracle port (the only one with a PathIntegrator); reference_source times the reference's own code on its DirectIntegrator"}
+    rs = reference_source_sample()
+    if rs is not None:
+        line["reference_source"] = rs
     print(json.dumps(line), flush=True)
 
 
