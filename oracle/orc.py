@@ -227,11 +227,20 @@ def load_scene_description(xml_path=None, xml_string=None):
     desc = {"sensors": [], "bsdfs": [], "meshes": [], "emitters": [], "envmap": None, "opts": None}
     for node in root.findall("sensor"):
         film, sampler = node.find("film"), node.find("sampler")
-        if not desc["sensors"]:
+        if not desc["sensors"]:            # scene_loader.cpp:251-262: film and sampler belong to the first sensor, and only to it
+            if film is None:
+                raise RuntimeError("Missing film node")
+            if sampler is None:
+                raise RuntimeError("Missing sampler node")
             w = int(_find_named(film, ("width",)).get("value"))
             h = int(_find_named(film, ("height",)).get("value"))
             spp = int(sampler.find("integer").get("value"))
             desc["opts"] = dict(width=w, height=h, spp=spp, sppe=spp, sppse=spp)
+        else:
+            if film is not None:
+                raise RuntimeError("Duplicate film node")
+            if sampler is not None:
+                raise RuntimeError("Duplicate sampler node")
         if node.get("type") != "perspective":
             raise RuntimeError("Unsupported sensor: %s" % node.get("type"))
         fa = _find_named(node, ("fov_axis", "fovAxis"))

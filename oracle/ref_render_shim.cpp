@@ -157,6 +157,14 @@ static void set_tangent(FloatD &x, const float *t, size_t n, size_t stride, size
 template <size_t k> static void set_tangent(Array<FloatD, k> &x, const float *t, size_t n) { for (size_t c = 0; c < k; ++c) set_tangent(x[c], t, n, k, c); }
 static void set_tangent(Matrix4fD &m, const float *t) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) set_tangent(m(i, j), t ? t + 4 * i + j : nullptr, 1, 1, 0); }
 
+// what SceneLoader made of an XML file (before configure): one line per object, numbers printed with %.9g, for comparing loaders
+static void put_mat(std::ostringstream &os, const Matrix4fD &m) { char b[32]; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { snprintf(b, sizeof b, " %.9g", (double)m(i, j)[0]); os << b; } }
+template <class V> static void put_tex(std::ostringstream &os, const char *name, const V &data, const ScalarVector2i &reso, int ch) {
+    char b[32];
+    os << " " << name << "[" << reso.x() << "x" << reso.y() << "]";
+    if (reso.x() == 1 && reso.y() == 1) for (int c = 0; c < ch; ++c) { float v; if constexpr (is_arr_v<V>) v = data[c][0]; else v = data[0]; snprintf(b, sizeof b, " %.9g", (double)v); os << b; }
+}
+
 extern "C" {
 
 const char *ref_last_error() { return g_err.c_str(); }
@@ -450,6 +458,53 @@ const char *ref_param_map_keys(void *s) {
     std::sort(v.begin(), v.end());
     for (const auto &k : v) keys += k + "\n";
     return keys.c_str();
+}
+
+const char *ref_scene_describe(void *sp) {
+    static thread_local std::string out;
+    const Scene &s = *(Scene *)sp;
+    std::ostringstream os;
+    char b[64];
+    os << "opts " << s.m_opts.width << " " << s.m_opts.height << " " << s.m_opts.spp << " " << s.m_opts.sppe << " " << s.m_opts.sppse << "\n";
+    for (const Sensor *c : s.m_sensors) {
+        auto *p = dynamic_cast<const PerspectiveCamera *>(c);
+        snprintf(b, sizeof b, "sensor %.9g %.9g %.9g", (double)p->m_fov_x, (double)p->m_near_clip, (double)p->m_far_clip); os << b; put_mat(os, c->m_to_world); os << "\n";
+    }
+    for (const BSDF *bs : s.m_bsdfs) {
+        os << "bsdf " << bs->type_name() << " id=" << bs->m_id;
+        if (auto *d = dynamic_cast<const Diffuse *>(bs)) put_tex(os, "reflectance", d->m_reflectance.m_data, d->m_reflectance.m_resolution, 3);
+        if (auto *r = dynamic_cast<const RoughConductor *>(bs)) {
+            put_tex(os, "alpha_u", r->m_alpha_u.m_data, r->m_alpha_u.m_resolution, 1); put_tex(os, "alpha_v", r->m_alpha_v.m_data, r->m_alpha_v.m_resolution, 1);
+            put_tex(os, "eta", r->m_eta.m_data, r->m_eta.m_resolution, 3); put_tex(os, "k", r->m_k.m_data, r->m_k.m_resolution, 3);
+            put_tex(os, "specular_reflectance", r->m_specular_reflectance.m_data, r->m_specular_reflectance.m_resolution, 3);
+        }
+        os << "\n";
+    }
+    if (s.m_emitter_env) {
+        snprintf(b, sizeof b, "envmap %.9g %dx%d", (double)s.m_emitter_env->m_scale[0], s.m_emitter_env->m_radiance.m_resolution.x(), s.m_emitter_env->m_radiance.m_resolution.y());
+        os << b; put_mat(os, s.m_emitter_env->m_to_world_raw); os << "\n";
+    }
+    for (const Mesh *m : s.m_meshes) {
+        os << "mesh id=" << m->m_id << " nv=" << m->m_num_vertices << " nf=" << m->m_num_faces << " uv=" << (m->m_has_uv ? (int)slices(m->m_vertex_uv) : 0)
+           << " face_normals=" << m->m_use_face_normals << " edges=" << m->m_enable_edges << " bsdf=" << (m->m_bsdf ? m->m_bsdf->m_id : std::string("-"));
+        if (auto *a = dynamic_cast<const AreaLight *>(m->m_emitter)) { snprintf(b, sizeof b, " radiance %.9g %.9g %.9g", (double)a->m_radiance[0][0], (double)a->m_radiance[1][0], (double)a->m_radiance[2][0]); os << b; }
+        os << " to_world"; put_mat(os, m->m_to_world_raw); os << "\n";
+    }
+    out = os.str();
+    return out.c_str();
+}
+// SceneLoader::load_from_string on an XML text (relative file names resolve against cwd)
+void *ref_scene_load_string(const char *xml, const char *cwd) {
+    Scene *scene = nullptr;
+    if (guard([&] {
+            char old[4096];
+            if (!getcwd(old, sizeof old)) throw Exception("getcwd failed");
+            if (cwd && chdir(cwd) != 0) throw Exception(std::string("cannot chdir to ") + cwd);
+            try { scene = new Scene(); scene->load_string(xml, false); } catch (...) { (void)!chdir(old); delete scene; scene = nullptr; throw; }
+            (void)!chdir(old);
+            scene->m_opts.log_level = 0;
+        })) return nullptr;
+    return scene;
 }
 
 }  // extern "C"

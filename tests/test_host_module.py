@@ -523,3 +523,165 @@ def test_mesh_helpers_match_reference_code(psdr_cuda, refrun):
     assert np.allclose(f.to_local(f.to_world(p)), p, atol=1e-3)
     ray = psdr_cuda.RayC(p, n)
     assert np.array_equal(ray.reversed().d, -n)
+
+
+# ---- loader semantics on awkward XML, against the reference's own SceneLoader -----------------------------------------------------------------
+def _describe_product(psdr_cuda, sc):
+    """the same text oracle/ref_render_shim.cpp:ref_scene_describe prints for the reference's Scene, from this module's objects"""
+    pm = sc._raw_param_map()
+    fmt = lambda v: " %.9g" % float(v)
+    mat = lambda m: "".join(fmt(x) for x in np.asarray(m, np.float32).reshape(-1))
+
+    def tex(name, bm, ch):
+        w, h = bm.resolution
+        s = " %s[%dx%d]" % (name, w, h)
+        if (w, h) == (1, 1):
+            s += "".join(fmt(x) for x in np.asarray(bm.data, np.float32).reshape(-1)[:ch])
+        return s
+    out = ["opts %d %d %d %d %d" % (sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse)]
+    for i in range(sc.num_sensors):
+        s = pm["Sensor[%d]" % i]
+        out.append("sensor" + fmt(s.fov_x) + fmt(s.near_clip) + fmt(s.far_clip) + mat(s.to_world))
+    i = 0
+    while "BSDF[%d]" % i in pm:
+        b = pm["BSDF[%d]" % i]
+        line = "bsdf %s id=%s" % (b.type_name(), b.id)
+        if b.type_name() == "Diffuse":
+            line += tex("reflectance", b.reflectance, 3)
+        else:
+            line += tex("alpha_u", b.alpha_u, 1) + tex("alpha_v", b.alpha_v, 1) + tex("eta", b.eta, 3) + tex("k", b.k, 3) + tex("specular_reflectance", b.specular_reflectance, 3)
+        out.append(line)
+        i += 1
+    emitters = []
+    i = 0
+    while "Emitter[%d]" % i in pm:
+        emitters.append(pm["Emitter[%d]" % i])
+        i += 1
+    for e in emitters:
+        if isinstance(e, psdr_cuda.EnvironmentMap):
+            w, h = e.radiance.resolution
+            out.append("envmap" + fmt(e.scale) + " %dx%d" % (w, h) + mat(e.to_world))
+    i = 0
+    while "Mesh[%d]" % i in pm:
+        m = pm["Mesh[%d]" % i]
+        line = "mesh id=%s nv=%d nf=%d uv=%d face_normals=%d edges=%d bsdf=%s" % (m.id, m.num_vertices, m.num_faces, len(m.vertex_uv) if m.has_uv else 0, int(m.use_face_normals),
+                                                                                  int(m.enable_edges), pm["BSDF[%d]" % m.bsdf_index].id if m.bsdf_index >= 0 else "-")
+        if m.emitter_index >= 0:
+            line += " radiance" + "".join(fmt(x) for x in emitters[m.emitter_index].radiance)
+        out.append(line + " to_world" + mat(m.to_world_raw))
+        i += 1
+    return "\n".join(out) + "\n"
+
+
+_SENSOR = """<sensor type="perspective"><float name="fov" value="%s"/>%s
+  <transform name="%s">%s</transform>
+  <sampler type="independent"><integer name="sampleCount" value="3"/></sampler>
+  <film type="hdrfilm"><integer name="width" value="20"/><integer name="height" value="10"/></film></sensor>"""
+_SHAPE = """<shape type="obj" id="%s"><string name="filename" value="./data/objects/cbox/%s.obj"/>%s<ref id="%s"/>%s</shape>"""
+LOADER_CASES = {
+    # aliases (toWorld / lookAt / fovAxis / nearClip / farClip / faceNormals), attribute defaults of translate / scale, float and short rgb values
+    "aliases": "<scene>" + _SENSOR % ("35.5", '<string name="fovAxis" value="x"/><float name="nearClip" value="0.5"/><float name="farClip" value="250"/>', "toWorld",
+                                      '<lookAt origin="1, 2, 3" target="0, 0.5, 0" up="0, 1, 0"/>')
+    + '<bsdf type="diffuse" id="a"><float name="reflectance" value="0.3"/></bsdf><bsdf type="diffuse" id="b"><rgb name="reflectance" value="0.7"/></bsdf>'
+    + '<bsdf type="diffuse" id="c"><rgb name="reflectance" value="0.1, 0.6"/></bsdf>'
+    + _SHAPE % ("f", "floor", '<transform name="toWorld"><scale x="2"/><translate y="-1.5"/><rotate x="0" y="0" z="1" angle="33"/></transform>', "a", "")
+    + _SHAPE % ("l", "emitter", '<boolean name="faceNormals" value="true"/>', "c", '<emitter type="area"><rgb name="radiance" value="5"/></emitter>') + "</scene>",
+    # matrix transforms, a transform sequence applied left to right, lookat spelled lowercase, a second sensor without film / sampler
+    "matrix": "<scene>" + _SENSOR % ("60", "", "to_world", '<matrix value="1 0 0 0.5  0 1 0 -2  0 0 1 7  0 0 0 1"/><translate x="1" z="-1"/>')
+    + '<sensor type="perspective"><float name="fov" value="20"/><transform name="to_world"><lookat origin="0, 1, 9" target="0, 1, 0" up="0, 1, 0"/></transform></sensor>'
+    + '<bsdf type="roughconductor" id="m"><float name="alpha" value="0.25"/><rgb name="eta" value="0.2, 0.9, 1.1"/><rgb name="k" value="3.9"/></bsdf>'
+    + _SHAPE % ("w", "wall_back", '<transform name="to_world"><rotate x="1" y="0" z="0" angle="-90"/><scale x="0.5" y="2" z="3"/><matrix value="0 1 0 0  1 0 0 0  0 0 1 0  0 0 0 1"/></transform>', "m", "")
+    + _SHAPE % ("l", "emitter", "", "m", '<emitter type="area"><rgb name="radiance" value="1, 2, 3"/></emitter>') + "</scene>",
+}
+LOADER_ERRORS = {
+    "unknown bsdf ref": "<scene>" + _SENSOR % ("30", "", "to_world", "") + '<bsdf type="diffuse" id="a"><float name="reflectance" value="0.3"/></bsdf>' + _SHAPE % ("f", "floor", "", "zzz", "") + "</scene>",
+    "duplicate bsdf id": "<scene>" + _SENSOR % ("30", "", "to_world", "") + '<bsdf type="diffuse" id="a"><float name="reflectance" value="0.3"/></bsdf><bsdf type="diffuse" id="a"><float name="reflectance" value="0.4"/></bsdf>' + "</scene>",
+    "fov axis y": "<scene>" + _SENSOR % ("30", '<string name="fov_axis" value="y"/>', "to_world", "") + "</scene>",
+    "unsupported bsdf": "<scene>" + _SENSOR % ("30", "", "to_world", "") + '<bsdf type="plastic" id="a"/>' + "</scene>",
+    "unsupported transform": "<scene>" + _SENSOR % ("30", "", "to_world", '<shear x="1"/>') + "</scene>",
+    "bad transform name": "<scene>" + _SENSOR % ("30", "", "world", "") + "</scene>",
+    "second film": "<scene>" + _SENSOR % ("30", "", "to_world", "") + _SENSOR % ("30", "", "to_world", "") + "</scene>",
+    "missing reflectance": "<scene>" + _SENSOR % ("30", "", "to_world", "") + '<bsdf type="diffuse" id="a"/>' + "</scene>",
+    "short vector": "<scene>" + _SENSOR % ("30", "", "to_world", '<lookat origin="1, 2" target="0, 0, 0" up="0, 1, 0"/>') + "</scene>",
+}
+
+
+@pytest.mark.parametrize("case", sorted(LOADER_CASES))
+def test_loader_semantics_match_reference_loader(psdr_cuda, refrun, monkeypatch, case):
+    """scene_loader.cpp:24-419 on XML the fixtures do not contain: what the reference's own SceneLoader::load_from_string makes of it vs
+    this module's C++ ingest, object by object and number by number"""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    L = refrun.lib()
+    L.ref_scene_describe.restype = C.c_char_p
+    L.ref_scene_load_string.restype = C.c_void_p
+    L.ref_scene_load_string.argtypes = [C.c_char_p, C.c_char_p]
+    tests_dir = os.path.join(ROOT, "tests")
+    h = L.ref_scene_load_string(LOADER_CASES[case].encode(), tests_dir.encode())
+    assert h, L.ref_last_error()
+    ref = L.ref_scene_describe(C.c_void_p(h)).decode()
+    L.ref_scene_free(C.c_void_p(h))
+    monkeypatch.chdir(tests_dir)
+    sc = psdr_cuda.Scene(-1)
+    sc.load_string(LOADER_CASES[case], False)
+    mine = _describe_product(psdr_cuda, sc)
+    rl, ml = ref.strip().split("\n"), mine.strip().split("\n")
+    assert len(rl) == len(ml), (ref, mine)
+    for a, b in zip(rl, ml):
+        ta, tb = a.split(), b.split()
+        assert len(ta) == len(tb), (a, b)
+        for x, y in zip(ta, tb):
+            try:
+                fx, fy = float(x), float(y)
+            except ValueError:
+                assert x == y, (a, b)
+                continue
+            assert abs(fx - fy) <= 2e-6 * max(1.0, abs(fx)), (a, b)
+
+
+@pytest.mark.parametrize("case", sorted(LOADER_ERRORS))
+def test_loader_errors_match_reference_loader(psdr_cuda, refrun, monkeypatch, case):
+    """malformed scenes the reference's loader rejects (PSDR_ASSERT_MSG in scene_loader.cpp) are rejected here too"""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    L = refrun.lib()
+    L.ref_scene_load_string.restype = C.c_void_p
+    L.ref_scene_load_string.argtypes = [C.c_char_p, C.c_char_p]
+    tests_dir = os.path.join(ROOT, "tests")
+    h = L.ref_scene_load_string(LOADER_ERRORS[case].encode(), tests_dir.encode())
+    assert not h, "the reference accepted: " + case
+    monkeypatch.chdir(tests_dir)
+    with pytest.raises(RuntimeError):
+        psdr_cuda.Scene(-1).load_string(LOADER_ERRORS[case], False)
+
+
+@pytest.mark.parametrize("case", sorted(LOADER_CASES))
+def test_python_loaders_agree_on_the_awkward_xml(monkeypatch, case):
+    """the ctypes path's loader (scene_io.py) and the checker's (orc.py) read the same XML to the same description"""
+    import os
+    from conftest import ROOT
+    from oracle import orc
+    from psdr_cuda_b200 import scene_io
+    monkeypatch.chdir(os.path.join(ROOT, "tests"))
+    a, b = scene_io.load_scene_description(xml_string=LOADER_CASES[case]), orc.load_scene_description(xml_string=LOADER_CASES[case])
+    assert a["opts"] == b["opts"] and len(a["meshes"]) == len(b["meshes"]) and len(a["sensors"]) == len(b["sensors"])
+    for x, y in zip(a["sensors"], b["sensors"]):
+        assert np.array_equal(x["to_world"], y["to_world"]) and (x["fov"], x["near"], x["far"]) == (y["fov"], y["near"], y["far"])
+    for x, y in zip(a["meshes"], b["meshes"]):
+        assert np.array_equal(x["to_world"], y["to_world"]) and np.array_equal(x["verts"], y["verts"]) and x["bsdf"] == y["bsdf"] and x["face_normals"] == y["face_normals"]
+    for x, y in zip(a["bsdfs"], b["bsdfs"]):
+        assert x["type"] == y["type"] and all(np.array_equal(x[k], y[k]) for k in x if isinstance(x[k], np.ndarray))
+
+
+@pytest.mark.parametrize("case", sorted(LOADER_ERRORS))
+def test_python_loaders_reject_what_the_reference_rejects(monkeypatch, case):
+    import os
+    from conftest import ROOT
+    from oracle import orc
+    from psdr_cuda_b200 import scene_io
+    monkeypatch.chdir(os.path.join(ROOT, "tests"))
+    for load in (scene_io.load_scene_description, orc.load_scene_description):
+        with pytest.raises(Exception):
+            load(xml_string=LOADER_ERRORS[case])
