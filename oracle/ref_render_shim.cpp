@@ -507,4 +507,7 @@ void *ref_scene_load_string(const char *xml, const char *cwd) {
     return scene;
 }
 
+// Mesh::dump (mesh.cpp:318-392) of a loaded scene's mesh
+int ref_mesh_dump(void *s, int mesh, const char *path) { return guard([&] { ((Scene *)s)->m_meshes.at(mesh)->dump(path); }); }
+
 }  // extern "C"

@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -233,19 +234,50 @@ struct Mesh : Object {
         std::memcpy(a.mutable_data(), faces.data(), faces.size() * sizeof(int));
         return a;
     }
-    void dump(const std::string &fname) const {   // Mesh::dump (mesh.cpp:354-418): object-space OBJ
-        std::ofstream out(fname);
-        if (!out) throw std::runtime_error("Failed to open: " + fname);
-        for (int v = 0; v < nv(); ++v) out << "v " << verts[3 * v] << " " << verts[3 * v + 1] << " " << verts[3 * v + 2] << "\n";
-        for (size_t t = 0; t + 1 < uvs.size(); t += 2) out << "vt " << uvs[t] << " " << uvs[t + 1] << "\n";
+    // object-space, area-weighted vertex normals (mesh.cpp:19-51 on the raw positions, mesh.cpp:219)
+    std::vector<float> vertex_normals() const {
+        std::vector<float> n(verts.size(), 0.f), w(nv(), 0.f);
         for (int f = 0; f < nf(); ++f) {
-            out << "f";
+            const float *a = &verts[3 * faces[3 * f]], *b = &verts[3 * faces[3 * f + 1]], *c = &verts[3 * faces[3 * f + 2]];
+            const float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+            const float fn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            const float area = std::sqrt(fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2]);
             for (int k = 0; k < 3; ++k) {
-                out << " " << faces[3 * f + k] + 1;
-                if (!uv_faces.empty()) out << "/" << uv_faces[3 * f + k] + 1;
+                const int v = faces[3 * f + k];
+                for (int d = 0; d < 3; ++d) n[3 * v + d] += fn[d];
+                w[v] += area;
             }
-            out << "\n";
         }
+        for (int v = 0; v < nv(); ++v) {
+            float x[3] = {n[3 * v] / w[v], n[3 * v + 1] / w[v], n[3 * v + 2] / w[v]};
+            const float inv = 1.f / std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+            for (int d = 0; d < 3; ++d) n[3 * v + d] = x[d] * inv;
+        }
+        return n;
+    }
+    // Mesh::dump (mesh.cpp:318-392): object-space OBJ in the reference's layout — "v" (+ "vn" per vertex unless face normals are used)
+    // in %.6e, then "vt", then faces as v, v/vt, v//vn or v/vt/vn
+    void dump(const std::string &fname) const {
+        FILE *out = std::fopen(fname.c_str(), "wt");
+        if (!out) throw std::runtime_error("Failed to open: " + fname);
+        std::vector<float> vn;
+        if (!use_face_normals) vn = vertex_normals();
+        for (int v = 0; v < nv(); ++v) {
+            std::fprintf(out, "v %.6e %.6e %.6e\n", verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]);
+            if (!use_face_normals) std::fprintf(out, "vn %.6e %.6e %.6e\n", vn[3 * v], vn[3 * v + 1], vn[3 * v + 2]);
+        }
+        const bool has_uv = !uvs.empty();
+        for (size_t t = 0; t + 1 < uvs.size(); t += 2) std::fprintf(out, "vt %.6e %.6e\n", (double)uvs[t], (double)uvs[t + 1]);
+        for (int f = 0; f < nf(); ++f) {
+            const int v0 = faces[3 * f] + 1, v1 = faces[3 * f + 1] + 1, v2 = faces[3 * f + 2] + 1;
+            if (has_uv) {
+                const int t0 = uv_faces[3 * f] + 1, t1 = uv_faces[3 * f + 1] + 1, t2 = uv_faces[3 * f + 2] + 1;
+                if (use_face_normals) std::fprintf(out, "f %d/%d %d/%d %d/%d\n", v0, t0, v1, t1, v2, t2);
+                else std::fprintf(out, "f %d/%d/%d %d/%d/%d %d/%d/%d\n", v0, t0, v0, v1, t1, v1, v2, t2, v2);
+            } else if (use_face_normals) std::fprintf(out, "f %d %d %d\n", v0, v1, v2);
+            else std::fprintf(out, "f %d//%d %d//%d %d//%d\n", v0, v0, v1, v1, v2, v2);
+        }
+        std::fclose(out);
     }
 };
 

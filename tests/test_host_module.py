@@ -685,3 +685,26 @@ def test_python_loaders_reject_what_the_reference_rejects(monkeypatch, case):
     for load in (scene_io.load_scene_description, orc.load_scene_description):
         with pytest.raises(Exception):
             load(xml_string=LOADER_ERRORS[case])
+
+
+def test_mesh_dump_writes_the_reference_file(psdr_cuda, refrun, textured_scene, tmp_path):
+    """Mesh::dump (mesh.cpp:318-392): smooth-normal, face-normal and uv-mapped meshes come out as the files the reference writes (numbers
+    in %.6e; a vertex normal may differ in its last printed digit)"""
+    import os
+    from conftest import ROOT
+    L = refrun.lib()
+    for xml, meshes in ((scene_path("cbox_bunny"), (0, 1)), (textured_scene, (0, 2))):
+        r = refrun.Scene(xml, os.path.join(ROOT, "tests"), 8, 8, 1, 0, 0)
+        r.configure()
+        sc = psdr_cuda.Scene(-1)
+        sc.load_file(xml, False)
+        for i in meshes:
+            a, b = str(tmp_path / "ref.obj"), str(tmp_path / "mine.obj")
+            assert L.ref_mesh_dump(r.h, i, a.encode()) == 0, L.ref_last_error()
+            sc.param_map["Mesh[%d]" % i].dump(b)
+            la, lb = open(a).read().split("\n"), open(b).read().split("\n")
+            assert len(la) == len(lb)
+            for x, y in zip(la, lb):
+                if x != y:
+                    tx, ty = x.split(), y.split()
+                    assert tx[0] == ty[0] == "vn" and np.allclose([float(v) for v in tx[1:]], [float(v) for v in ty[1:]], atol=2e-6), (x, y)
