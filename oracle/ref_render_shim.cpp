@@ -454,7 +454,7 @@ const char *ref_param_map_keys(void *s) {
     static thread_local std::string keys;
     keys.clear();
     std::vector<std::string> v;
-    for (const auto &kv : ((Scene *)s)->m_param_map) v.push_back(kv.first + "=" + kv.second.type_name());
+    for (const auto &kv : ((Scene *)s)->m_param_map) v.push_back(kv.first + "=" + kv.second.type_name() + "\t" + kv.second.to_string());
     std::sort(v.begin(), v.end());
     for (const auto &k : v) keys += k + "\n";
     return keys.c_str();

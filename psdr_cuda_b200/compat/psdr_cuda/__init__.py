@@ -118,7 +118,11 @@ class _Proxy:
             obj.set_transform(np.asarray(mat, dtype=np.float32), set_left) if obj.type_name() == "Mesh" else obj.set_transform(np.asarray(mat, dtype=np.float32))
 
     def __repr__(self):
-        return repr(self._obj)
+        obj = self._obj
+        if obj.type_name() == "Mesh":   # Mesh::to_string (mesh.cpp:421-427)
+            b = self.bsdf
+            return "Mesh[nv=%d, nf=%d%s, bsdf=%s]" % (obj.num_vertices, obj.num_faces, ", id=" + obj.id if obj.id else "", repr(b) if b is not None else "None")
+        return repr(obj)
 
 
 def obj_index(obj):

@@ -300,6 +300,7 @@ struct EnvironmentMap : Emitter {
     Mat4 to_world_raw, to_world_left;
     bool transform_dirty = false;
     std::string type_name() const override { return "AreaLight"; }   // sic: envmap.h:58
+    std::string to_string() const override { return "EnvironmentMap[sampling_weight = 1]"; }   // envmap.cpp:146-150 (weight of a lone emitter)
 };
 
 struct RenderOption {   // types.h:171-182, psdr.cpp:53-72
@@ -646,9 +647,9 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def(py::init<>()).def(py::init<int, int, int>()).def(py::init<int, int, int, int>()).def(py::init<int, int, int, int, int>())
         .def_readwrite("width", &RenderOption::width).def_readwrite("height", &RenderOption::height).def_readwrite("spp", &RenderOption::spp)
         .def_readwrite("sppe", &RenderOption::sppe).def_readwrite("sppse", &RenderOption::sppse).def_readwrite("log_level", &RenderOption::log_level)
-        .def("__repr__", [](const RenderOption &o) {
+        .def("__repr__", [](const RenderOption &o) {   // src/psdr.cpp:63-71
             std::ostringstream s;
-            s << "RenderOption[width = " << o.width << ", height = " << o.height << ", spp = " << o.spp << ", sppe = " << o.sppe << ", sppse = " << o.sppse << "]";
+            s << "[width: " << o.width << ", height: " << o.height << ", spp: " << o.spp << ", sppe: " << o.sppe << ", sppse: " << o.sppse << ", log_level: " << o.log_level << "]";
             return s.str();
         });
 

@@ -422,7 +422,7 @@ def test_param_map_keys_and_type_names_match_reference_loader(psdr_cuda, refrun,
     L = refrun.lib()
     L.ref_param_map_keys.restype = C.c_char_p
     r = refrun.Scene(scene_path(name), os.path.join(ROOT, "tests"))
-    ref = dict(l.rsplit("=", 1) for l in L.ref_param_map_keys(r.h).decode().strip().split("\n"))
+    ref = dict(l.split("\t", 1)[0].rsplit("=", 1) for l in L.ref_param_map_keys(r.h).decode().strip().split("\n"))   # key=type_name<TAB>to_string
     sc = psdr_cuda.Scene(-1)
     sc.load_file(scene_path(name), False)
     mine = {k: v.type_name() for k, v in sc._raw_param_map().items()}
@@ -708,3 +708,28 @@ def test_mesh_dump_writes_the_reference_file(psdr_cuda, refrun, textured_scene, 
                 if x != y:
                     tx, ty = x.split(), y.split()
                     assert tx[0] == ty[0] == "vn" and np.allclose([float(v) for v in tx[1:]], [float(v) for v in ty[1:]], atol=2e-6), (x, y)
+
+
+def test_reprs_match_reference_to_string(psdr_cuda, refrun):
+    """Object::to_string of the reference's scene objects (what repr() shows in its Python module) for BSDFs, meshes, sensors and the
+    environment map; AreaLight prints an Enoki array and is left out"""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    L = refrun.lib()
+    L.ref_param_map_keys.restype = C.c_char_p
+    for name in ("cbox_bunny_rc", "bunny_env", "tree"):
+        r = refrun.Scene(scene_path(name), os.path.join(ROOT, "tests"))
+        sc = psdr_cuda.Scene(-1)
+        sc.load_file(scene_path(name), False)
+        pm = sc.param_map
+        n = 0
+        for line in L.ref_param_map_keys(r.h).decode().strip().split("\n"):
+            head, rep = line.split("\t", 1)
+            key = head[:head.index("]=") + 1]
+            if rep.startswith("AreaLight["):
+                continue
+            assert repr(pm[key]) == rep, (key, rep, repr(pm[key]))
+            n += 1
+        assert n >= 4
+    assert repr(psdr_cuda.RenderOption(3, 4, 5)) == "[width: 3, height: 4, spp: 5, sppe: 5, sppse: 5, log_level: 1]"
