@@ -6,7 +6,8 @@
 // Two things are NOT the reference's here, because they are external to it:
 //  * Enoki  -> oracle/ref_dyn/enoki_dyn.h (host arrays; forward-mode tangents instead of the reverse-mode tape),
 //  * OptiX  -> Scene_OptiX below (scene_optix.cpp replaced): the closest hit over all triangles with t in (RayEpsilon, tmax),
-//              computed with the arithmetic of the reference's ray_intersect_triangle (utils.h:67-77), ties to the lowest triangle id;
+//              computed with the arithmetic of the reference's ray_intersect_triangle (utils.h:67-77), ties to the lowest triangle id
+//              (a small BVH only prunes; it returns what testing every triangle returns);
 //              it fills the same outputs as cuda/psdr_cuda.cu:27-45 (global triangle id, shape id, barycentrics; -1 on a miss).
 #include <unistd.h>
 
@@ -37,9 +38,34 @@
 // ---- stand-in for the OptiX acceleration structure -----------------------------------------------------------------------------------------
 struct PathTracerState {
     struct Tri { float p0[3], e1[3], e2[3]; int shape, id; };
-    std::vector<Tri> tris;
-    struct Box { float lo[3], hi[3]; int first, count; };
-    std::vector<Box> boxes;   // one per mesh: a conservative early-out only
+    std::vector<Tri> tris;                 // in BVH leaf order; `id` is the global triangle id
+    struct Node { float lo[3], hi[3]; int left, right, first, count; };   // leaf: count > 0
+    std::vector<Node> nodes;               // a median-split BVH: an accelerator only, boxes padded so that no hit is lost
+    int build(int first, int count) {
+        Node n;
+        for (int c = 0; c < 3; ++c) { n.lo[c] = std::numeric_limits<float>::max(); n.hi[c] = -std::numeric_limits<float>::max(); }
+        float clo[3] = {n.lo[0], n.lo[1], n.lo[2]}, chi[3] = {n.hi[0], n.hi[1], n.hi[2]};
+        for (int i = first; i < first + count; ++i) for (int c = 0; c < 3; ++c) {
+            const Tri &t = tris[i];
+            const float a = t.p0[c], b = t.p0[c] + t.e1[c], d = t.p0[c] + t.e2[c], ce = (a + b + d) / 3.f;
+            n.lo[c] = std::min(n.lo[c], std::min(a, std::min(b, d))); n.hi[c] = std::max(n.hi[c], std::max(a, std::max(b, d)));
+            clo[c] = std::min(clo[c], ce); chi[c] = std::max(chi[c], ce);
+        }
+        for (int c = 0; c < 3; ++c) { const float pad = 1e-4f * (1.f + std::abs(n.lo[c]) + std::abs(n.hi[c])); n.lo[c] -= pad; n.hi[c] += pad; }
+        n.left = n.right = -1; n.first = first; n.count = count;
+        const int me = (int)nodes.size();
+        nodes.push_back(n);
+        if (count > 4) {
+            int axis = 0;
+            for (int c = 1; c < 3; ++c) if (chi[c] - clo[c] > chi[axis] - clo[axis]) axis = c;
+            const int mid = first + count / 2;
+            std::nth_element(tris.begin() + first, tris.begin() + mid, tris.begin() + first + count, [axis](const Tri &x, const Tri &y) {
+                return x.p0[axis] * 3.f + x.e1[axis] + x.e2[axis] < y.p0[axis] * 3.f + y.e1[axis] + y.e2[axis]; });
+            const int l = build(first, mid - first), r = build(mid, first + count - mid);
+            nodes[me].left = l; nodes[me].right = r; nodes[me].count = 0;
+        }
+        return me;
+    }
 };
 
 namespace psdr {
@@ -60,7 +86,7 @@ void Scene_OptiX::configure(const std::vector<Mesh *> &meshes) {
     PSDR_ASSERT(!meshes.empty());
     if (m_accel == nullptr) m_accel = new PathTracerState();
     m_accel->tris.clear();
-    m_accel->boxes.clear();
+    m_accel->nodes.clear();
     int offset = 0;
     for (size_t s = 0; s < meshes.size(); ++s) {
         const Mesh *mesh = meshes[s];
@@ -68,24 +94,16 @@ void Scene_OptiX::configure(const std::vector<Mesh *> &meshes) {
         PSDR_ASSERT(static_cast<int>(slices(mesh->m_face_buffer)) == mesh->m_num_faces * 3);
         const float *vb = mesh->m_vertex_buffer.data();   // what scene_optix.cpp:48-63 hands to OptiX
         const int *fb = mesh->m_face_buffer.data();
-        PathTracerState::Box box;
-        box.first = offset; box.count = mesh->m_num_faces;
-        for (int c = 0; c < 3; ++c) { box.lo[c] = std::numeric_limits<float>::max(); box.hi[c] = -std::numeric_limits<float>::max(); }
         for (int f = 0; f < mesh->m_num_faces; ++f) {
             PathTracerState::Tri t;
             const float *a = vb + 3 * fb[3 * f], *b = vb + 3 * fb[3 * f + 1], *c = vb + 3 * fb[3 * f + 2];
-            for (int k = 0; k < 3; ++k) {
-                t.p0[k] = a[k]; t.e1[k] = b[k] - a[k]; t.e2[k] = c[k] - a[k];
-                box.lo[k] = std::min(box.lo[k], std::min(a[k], std::min(b[k], c[k])));
-                box.hi[k] = std::max(box.hi[k], std::max(a[k], std::max(b[k], c[k])));
-            }
+            for (int k = 0; k < 3; ++k) { t.p0[k] = a[k]; t.e1[k] = b[k] - a[k]; t.e2[k] = c[k] - a[k]; }
             t.shape = (int)s; t.id = offset + f;
             m_accel->tris.push_back(t);
         }
-        for (int k = 0; k < 3; ++k) { const float pad = 1e-3f * (1.f + std::abs(box.lo[k]) + std::abs(box.hi[k])); box.lo[k] -= pad; box.hi[k] += pad; }
-        m_accel->boxes.push_back(box);
         offset += mesh->m_num_faces;
     }
+    m_accel->build(0, (int)m_accel->tris.size());
 }
 
 bool Scene_OptiX::is_ready() const { return m_accel != nullptr; }
@@ -94,7 +112,7 @@ static inline float dot3(const float *a, const float *b) { return std::fma(a[0],
 static inline void cross3(const float *a, const float *b, float *r) {
     r[0] = std::fma(a[1], b[2], -(a[2] * b[1])); r[1] = std::fma(a[2], b[0], -(a[0] * b[2])); r[2] = std::fma(a[0], b[1], -(a[1] * b[0]));
 }
-static bool hits_box(const PathTracerState::Box &b, const float *o, const float *d, float tmax) {
+static bool hits_box(const PathTracerState::Node &b, const float *o, const float *d, float tmax) {
     float t0 = 0.f, t1 = tmax;
     for (int k = 0; k < 3; ++k) {
         if (d[k] == 0.f) { if (o[k] < b.lo[k] || o[k] > b.hi[k]) return false; continue; }
@@ -119,9 +137,13 @@ Vector2i<ad> Scene_OptiX::ray_intersect(const Ray<ad> &ray, Mask<ad> &active) co
         if (!bool(lval(active, i))) continue;                       // the caller masks these lanes out anyway (active &= hit)
         const float o[3] = {lval(r.o.x(), i), lval(r.o.y(), i), lval(r.o.z(), i)}, d[3] = {lval(r.d.x(), i), lval(r.d.y(), i), lval(r.d.z(), i)};
         float best = lval(r.tmax, i);
-        for (const auto &box : m_accel->boxes) {
-            if (!hits_box(box, o, d, best)) continue;
-            for (int k = box.first; k < box.first + box.count; ++k) {
+        int stack[64], sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const auto &node = m_accel->nodes[stack[--sp]];
+            if (!hits_box(node, o, d, best)) continue;
+            if (node.count == 0) { stack[sp++] = node.left; stack[sp++] = node.right; continue; }
+            for (int k = node.first; k < node.first + node.count; ++k) {
                 const auto &t = m_accel->tris[k];
                 float h[3], s[3], q[3];
                 cross3(d, t.e2, h);                                  // utils.h:68-76
@@ -130,7 +152,10 @@ Vector2i<ad> Scene_OptiX::ray_intersect(const Ray<ad> &ray, Mask<ad> &active) co
                 const float u = f * dot3(s, h);
                 cross3(s, t.e1, q);
                 const float v = f * dot3(d, q), tt = f * dot3(t.e2, q);
-                if (u >= 0.f && v >= 0.f && u + v <= 1.f && tt > RayEpsilon && tt < best) { best = tt; tri_out[i] = t.id; shape_out[i] = t.shape; u_out[i] = u; v_out[i] = v; }
+                // the closest hit; equal distances go to the lowest triangle id, whatever order the leaves are visited in
+                if (u >= 0.f && v >= 0.f && u + v <= 1.f && tt > RayEpsilon && (tt < best || (tt == best && tri_out[i] >= 0 && t.id < tri_out[i]))) {
+                    best = tt; tri_out[i] = t.id; shape_out[i] = t.shape; u_out[i] = u; v_out[i] = v;
+                }
             }
         }
     }
