@@ -27,6 +27,8 @@ def scene(name):
 def cases():
     """label -> (scene, (w, h, spp, sppe, sppse), integrator spec, leaf spec or None). Shared with the tests that replay them."""
     return {
+        # BASELINE.json configs[0] at full size: DirectIntegrator renderC on cbox_bunny, 128x128, 16 spp
+        "c_cfg1_full": ("cbox_bunny", (128, 128, 16, 0, 0), ("direct", 1, 1), None),
         "c_cbox_d11": ("cbox_bunny", (48, 48, 4, 0, 0), ("direct", 1, 1), None),
         "c_cbox_d21": ("cbox_bunny", (48, 48, 4, 0, 0), ("direct", 2, 1), None),
         "c_multi_d11": ("cbox_bunny_mutiemitter", (40, 40, 4, 0, 0), ("direct", 1, 1), None),
