@@ -303,6 +303,22 @@ int orc_debug_lane(void *h, void *Iv, int sensor, int64_t lane, int ad, float *o
         }
     });
 }
+// same lane in the D formulation, value and forward-mode tangent (for the tangents set on the scene)
+int orc_debug_lane_d(void *h, void *Iv, int sensor, int64_t lane, float *out3, float *out3_t) {
+    return guard([&] {
+        Scene &s = ((Handle *)h)->scene;
+        const Integrator &I = *(Integrator *)Iv;
+        const RenderOption &o = s.opts;
+        SamplerLane smp = SamplerLane::make((uint64_t)lane);
+        int pix = (int)(lane / o.spp);
+        V2f j = smp.next_2d();
+        float bx = (float)(pix % o.width), by = (float)(pix / o.width);
+        V2<Dual> smpl(Dual((bx + j.x) / (float)o.width), Dual((by + j.y) / (float)o.height));
+        Ray<Dual> ray = s.sensors[sensor].sample_primary_ray<Dual>(smpl);
+        V3<Dual> v = Li<Dual>(I, s, smp, ray);
+        for (int k = 0; k < 3; ++k) { out3[k] = v[k].v; out3_t[k] = v[k].d; }
+    });
+}
 int orc_preprocess_secondary_edges(void *h, void *I, int sensor, const int *reso4, int nrounds) {
     return guard([&] { preprocess_secondary_edges(*(Integrator *)I, ((Handle *)h)->scene, sensor, reso4, nrounds); });
 }

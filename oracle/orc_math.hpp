@@ -62,7 +62,9 @@ inline Dual fma_(float a, Dual b, Dual c) { return fma_(Dual(a), b, c); }
 inline Dual fma_(Dual a, Dual b, float c) { return fma_(a, b, Dual(c)); }
 
 inline float sqrt_(float x) { return std::sqrt(x); }
-inline Dual sqrt_(Dual x) { float s = std::sqrt(x.v); return {s, x.d / (2.f * s)}; }
+// A zero tangent stays zero through an infinite local derivative (sqrt at 0, acos at +-1): Enoki's autodiff multiplies edge weights with a
+// "safe" product in which 0 * inf = 0, and the stand-in the reference's own code is run under (oracle/ref_dyn) does the same.
+inline Dual sqrt_(Dual x) { float s = std::sqrt(x.v); return {s, x.d == 0.f ? 0.f : x.d / (2.f * s)}; }
 inline float abs_(float x) { return std::fabs(x); }
 inline Dual abs_(Dual x) { return x.v < 0.f ? Dual(-x.v, -x.d) : x; }
 inline float sin_(float x) { return std::sin(x); }
@@ -70,7 +72,7 @@ inline Dual sin_(Dual x) { return {std::sin(x.v), std::cos(x.v) * x.d}; }
 inline float cos_(float x) { return std::cos(x); }
 inline Dual cos_(Dual x) { return {std::cos(x.v), -std::sin(x.v) * x.d}; }
 inline float acos_(float x) { return std::acos(x); }
-inline Dual acos_(Dual x) { return {std::acos(x.v), -x.d / std::sqrt(1.f - x.v * x.v)}; }
+inline Dual acos_(Dual x) { return {std::acos(x.v), x.d == 0.f ? 0.f : -x.d / std::sqrt(1.f - x.v * x.v)}; }
 inline float atan2_(float y, float x) { return std::atan2(y, x); }
 inline Dual atan2_(Dual y, Dual x) {
     float r2 = x.v * x.v + y.v * y.v;

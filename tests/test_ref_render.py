@@ -426,3 +426,21 @@ def test_mixed_configurations_match_reference_source(name, w, h, spp, sppe, spps
     assert np.abs(b).max() > 0 and np.abs(bt).max() > 0
     assert_images_close(a, b, rel=1e-3, outliers=0.01, what="primal")
     assert_images_close(at, bt, rel=1e-3, outliers=0.03, what="tangent")
+
+
+def test_zero_tangent_through_an_infinite_local_derivative_stays_zero():
+    """camera rays that leave through a pole of the environment map clamp the latitude cosine to +-1, where acos has an infinite derivative;
+    with a zero direction tangent the derivative image must stay finite (Enoki's autodiff multiplies with 0 * inf = 0; found with the oracle
+    returning NaN in 2 pixels of this image)"""
+    r, o = pair("bunny_env", 128, 128, 8, configure=False)
+    t = np.array([[0.3, -0.2, 0.5]], np.float32)
+    r.set_bsdf_tangent(0, "eta", t)
+    o.set_bsdf_tangent(0, "eta", t.reshape(1, 1, 3))
+    r.configure()
+    o.configure()
+    (a, at), (b, bt) = refrun.DirectIntegrator(1, 1).renderD(r), orc.DirectIntegrator(1, 1).renderD(o)
+    assert np.isfinite(at).all() and np.isfinite(bt).all()
+    for px in (9786, 10295):   # the two pole pixels
+        assert np.abs(at[px] - bt[px]).max() <= 1e-3 * np.abs(bt).max()
+    assert_images_close(a, b, rel=2e-4, outliers=0.01, what="primal")
+    assert_images_close(at, bt, rel=1e-3, outliers=0.02, what="tangent")
