@@ -61,9 +61,30 @@ def run(label, name, opts, leaves, guiding=None, bs=1, ls=1):
     sys.stdout.flush()
 
 
+def conditioning():
+    """the reference's own code against itself with matrix * vector rounded differently in the last bit (fmadd chain vs plain sums): how much
+    of the primary-edge term's difference to the oracle is fp32 conditioning of the estimator (ray pairs 1e-5 off a silhouette seen from
+    1000 units away), not a difference in the algorithm"""
+    xml = os.path.join(T, "data", "scenes", "cbox_bunny.xml")
+    out = []
+    for plain in (True, False):
+        refrun.set_matvec_plain(plain)
+        r = refrun.Scene(xml, T, 64, 64, 0, 16, 0)
+        r.set_mesh_vertex_tangent(1, np.random.default_rng(17).normal(size=(r.num_vertices(1), 3)).astype(np.float32))
+        r.configure()
+        out.append(refrun.DirectIntegrator(1, 1).renderD(r)[1])
+    refrun.set_matvec_plain(True)
+    print("== conditioning: reference source vs reference source, primary edges only, cbox_bunny 64x64 sppe 16, plain vs fmadd matrix product")
+    print("   d image : " + stats(out[0], out[1], 1e-3))
+
+
 if __name__ == "__main__":
+    if "--conditioning" in sys.argv:
+        conditioning()
+        sys.exit(0)
     run("cfg1 (full size)", "cbox_bunny", (128, 128, 16, 0, 0), [("albedo", 0)])
     run("cfg2 (reduced)", "cbox_bunny", (256, 256, 16, 0, 0), [("albedo", 0)])
     run("cfg3 (reduced)", "cbox_bunny", (128, 128, 8, 8, 8), [("vertices", 1)])
     run("cfg3 guided (reduced)", "cbox_bunny", (128, 128, 8, 8, 8), [("vertices", 1)], guiding=([40, 5, 5, 2], 4))
     run("cfg5 (reduced)", "bunny_env", (128, 128, 8, 8, 8), [("rc", 0), ("vertices", 0)])
+    conditioning()
