@@ -164,7 +164,7 @@ struct Mesh : Object {
     std::vector<float> verts, uvs;
     std::vector<int> faces, uv_faces;
     bool use_face_normals = false, enable_edges = true, requires_grad = false, uv_requires_grad = false;
-    bool verts_dirty = false, transform_dirty = false, uvs_dirty = false;
+    bool verts_dirty = false, transform_dirty = false, uvs_dirty = false, uploaded = false;
     Mat4 to_world_raw, to_world_left, to_world_right;
     int nv() const { return (int)verts.size() / 3; }
     int nf() const { return (int)faces.size() / 3; }
@@ -233,6 +233,19 @@ struct Mesh : Object {
         iarray a(std::vector<py::ssize_t>{(py::ssize_t)nf(), 3});
         std::memcpy(a.mutable_data(), faces.data(), faces.size() * sizeof(int));
         return a;
+    }
+    // face_indices / face_uv_indices are read-write in the reference (src/psdr.cpp:255-256). The topology goes to the device with the first
+    // Scene.configure (BVH, edge lists), so it can be edited until then.
+    void set_index_array(std::vector<int> &dst, const iarray &a, int limit, const char *what) {
+        if (uploaded) throw std::runtime_error(std::string(what) + ": the topology of a mesh that is already on the device cannot be edited");
+        if (a.ndim() != 2 || a.shape(1) != 3) throw std::runtime_error(std::string(what) + ": expected an (n, 3) integer array");
+        for (py::ssize_t i = 0; i < a.size(); ++i) if (a.data()[i] < 0 || a.data()[i] >= limit) throw std::runtime_error(std::string(what) + ": index out of range");
+        dst.assign(a.data(), a.data() + a.size());
+    }
+    void set_faces(const iarray &a) { set_index_array(faces, a, nv(), "face_indices"); }
+    void set_uv_faces(const iarray &a) {
+        if ((size_t)a.size() != faces.size()) throw std::runtime_error("face_uv_indices: one uv triple per face");
+        set_index_array(uv_faces, a, (int)uvs.size() / 2, "face_uv_indices");
     }
     // object-space, area-weighted vertex normals (mesh.cpp:19-51 on the raw positions, mesh.cpp:219)
     std::vector<float> vertex_normals() const {
@@ -517,6 +530,7 @@ public:
                                            m->uv_faces.empty() ? nullptr : m->uv_faces.data(), flags, m->bsdf, m->to_world_raw.m));
                 if (m->emitter >= 0) check_id(pb_scene_add_area_emitter(ctx, m->index, std::static_pointer_cast<AreaLight>(emitters[m->emitter])->radiance));
                 m->verts_dirty = false;
+                m->uploaded = true;
             }
             uploaded = true;
         }
@@ -694,15 +708,15 @@ PYBIND11_MODULE(_psdr_host, m) {
     py::class_<Mesh, Object, std::shared_ptr<Mesh>>(m, "Mesh")
         .def(py::init<>())                                                      // src/psdr.cpp:242-243
         .def("load", [](Mesh &x, const std::string &path, bool) { x.load(path); }, py::arg("fname"), py::arg("verbose") = false)
-        .def_property_readonly("face_uv_indices", [](const Mesh &x) {
+        .def_property("face_uv_indices", [](const Mesh &x) {
             iarray a(std::vector<py::ssize_t>{(py::ssize_t)(x.uv_faces.size() / 3), 3});
             if (!x.uv_faces.empty()) std::memcpy(a.mutable_data(), x.uv_faces.data(), x.uv_faces.size() * sizeof(int));
-            return a; })
+            return a; }, &Mesh::set_uv_faces)
         .def_property_readonly("num_vertices", &Mesh::nv)
         .def_property_readonly("num_faces", &Mesh::nf)
         .def_property("vertex_positions", &Mesh::get_vertices, &Mesh::set_vertices)
         .def_property("vertex_uv", &Mesh::get_uvs, &Mesh::set_uvs)
-        .def_property_readonly("face_indices", &Mesh::get_faces)
+        .def_property("face_indices", &Mesh::get_faces, &Mesh::set_faces)
         .def_property_readonly("to_world_raw", [](const Mesh &x) { return mat_to_numpy(x.to_world_raw); })
         .def_property_readonly("to_world_left", [](const Mesh &x) { return mat_to_numpy(x.to_world_left); })
         .def_property_readonly("to_world_right", [](const Mesh &x) { return mat_to_numpy(x.to_world_right); })

@@ -733,3 +733,18 @@ def test_reprs_match_reference_to_string(psdr_cuda, refrun):
             n += 1
         assert n >= 4
     assert repr(psdr_cuda.RenderOption(3, 4, 5)) == "[width: 3, height: 4, spp: 5, sppe: 5, sppse: 5, log_level: 1]"
+
+
+def test_face_indices_are_writable_before_the_first_configure(psdr_cuda):
+    """src/psdr.cpp:255-256: face_indices / face_uv_indices are read-write; here until the mesh has gone to the device"""
+    sc = psdr_cuda.Scene(-1)
+    sc.load_file(scene_path("cbox_bunny"), False)
+    m = sc.param_map["Mesh[2]"]
+    f = m.face_indices.copy()
+    m.face_indices = f[:, [1, 2, 0]]
+    assert np.array_equal(m.face_indices, f[:, [1, 2, 0]])
+    assert np.abs(m.vertex_normals - sc.param_map["Mesh[2]"].vertex_normals).max() == 0
+    with pytest.raises(RuntimeError, match="out of range"):
+        m.face_indices = f + 100
+    with pytest.raises(RuntimeError):
+        m.face_indices = f.reshape(-1)
