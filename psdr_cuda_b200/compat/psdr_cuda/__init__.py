@@ -25,7 +25,33 @@ from ._psdr_host import (BSDF, AreaLight, BitmapD, DiffuseBSDF, Emitter, Environ
 from ._surface import (DiscreteDistribution, FrameC, FrameD, HyperCubeDistribution2f, HyperCubeDistribution3f, PositionSampleC,  # noqa: F401
                        PositionSampleD, RayC, RayD, SampleRecordC, SampleRecordD)
 
-Bitmap1fD = Bitmap3fD = BitmapD
+
+
+class _BitmapCtor:
+    """constructors of src/psdr.cpp:102-106,112-116: (), (value), (width, height, data), (file name)"""
+    _channels = 0
+
+    def __init__(self, *args):
+        BitmapD.__init__(self, self._channels)
+        if len(args) == 1 and isinstance(args[0], str):
+            self.load_openexr(args[0])
+        elif len(args) == 1:
+            self.data = np.broadcast_to(np.asarray(args[0], np.float32).reshape(-1), (self._channels,)).copy()
+        elif len(args) == 3:
+            self.resolution = (int(args[0]), int(args[1]))
+            self.data = np.asarray(args[2], np.float32).reshape(int(args[0]) * int(args[1]), self._channels)
+        elif args:
+            raise TypeError("Bitmap%dfD(): expected (), (value), (width, height, data) or (file name)" % self._channels)
+
+
+class Bitmap1fD(_BitmapCtor, BitmapD):
+    _channels = 1
+
+
+class Bitmap3fD(_BitmapCtor, BitmapD):
+    _channels = 3
+
+
 Sensor = PerspectiveCamera   # src/psdr.cpp:216-222: the reference's only Sensor is the PerspectiveCamera; one class serves both names
 
 

@@ -147,6 +147,12 @@ struct Bitmap {   // Bitmap1fD / Bitmap3fD (src/core/bitmap.cpp, src/psdr.cpp:10
         data.assign(a.data(), a.data() + a.size());
         dirty = true;
     }
+    // `bsdf.reflectance = Bitmap3fD(...)`: the reference's members are read-write (src/psdr.cpp:208-215,236); the value is copied into the
+    // scene's own bitmap, which keeps its place in the gradient vector
+    void assign(const Bitmap &o) {
+        if (o.channels != channels) throw std::runtime_error("Bitmap: expected " + std::to_string(channels) + " channel(s), got " + std::to_string(o.channels));
+        width = o.width; height = o.height; data = o.data; dirty = true;
+    }
 };
 
 struct BSDF : Object { int index = -1; };
@@ -669,6 +675,7 @@ PYBIND11_MODULE(_psdr_host, m) {
 
     auto bitmap = [&](const char *name) {
         return py::class_<Bitmap>(m, name)
+            .def(py::init([](int channels) { if (channels != 1 && channels != 3) throw std::runtime_error("Bitmap: 1 or 3 channels"); return Bitmap(channels, 0.f); }), py::arg("channels"))
             .def_property("data", &Bitmap::get_data, &Bitmap::set_data)
             .def_property("resolution", [](const Bitmap &b) { return py::make_tuple(b.width, b.height); },
                           [](Bitmap &b, std::pair<int, int> r) { b.width = r.first; b.height = r.second; b.data.assign((size_t)b.width * b.height * b.channels, 0.f); b.dirty = true; })
@@ -680,13 +687,13 @@ PYBIND11_MODULE(_psdr_host, m) {
     py::class_<BSDF, Object, std::shared_ptr<BSDF>>(m, "BSDF").def_readonly("index", &BSDF::index)
         .def("anisotropic", [](const BSDF &) { return false; });   // bsdf.h:33; every BSDF the loader / Python can create is isotropic (roughconductor.h:11-18)
     py::class_<Diffuse, BSDF, std::shared_ptr<Diffuse>>(m, "DiffuseBSDF")
-        .def_property_readonly("reflectance", [](Diffuse &d) -> Bitmap & { return d.reflectance; }, py::return_value_policy::reference_internal);
+        .def_property("reflectance", py::cpp_function([](Diffuse &d) -> Bitmap & { return d.reflectance; }, py::return_value_policy::reference_internal), [](Diffuse &d, const Bitmap &b) { d.reflectance.assign(b); });
     py::class_<RoughConductor, BSDF, std::shared_ptr<RoughConductor>>(m, "RoughConductorBSDF")
-        .def_property_readonly("alpha_u", [](RoughConductor &d) -> Bitmap & { return d.alpha_u; }, py::return_value_policy::reference_internal)
-        .def_property_readonly("alpha_v", [](RoughConductor &d) -> Bitmap & { return d.alpha_v; }, py::return_value_policy::reference_internal)
-        .def_property_readonly("eta", [](RoughConductor &d) -> Bitmap & { return d.eta; }, py::return_value_policy::reference_internal)
-        .def_property_readonly("k", [](RoughConductor &d) -> Bitmap & { return d.k; }, py::return_value_policy::reference_internal)
-        .def_property_readonly("specular_reflectance", [](RoughConductor &d) -> Bitmap & { return d.specular_reflectance; }, py::return_value_policy::reference_internal);
+        .def_property("alpha_u", py::cpp_function([](RoughConductor &d) -> Bitmap & { return d.alpha_u; }, py::return_value_policy::reference_internal), [](RoughConductor &d, const Bitmap &b) { d.alpha_u.assign(b); })
+        .def_property("alpha_v", py::cpp_function([](RoughConductor &d) -> Bitmap & { return d.alpha_v; }, py::return_value_policy::reference_internal), [](RoughConductor &d, const Bitmap &b) { d.alpha_v.assign(b); })
+        .def_property("eta", py::cpp_function([](RoughConductor &d) -> Bitmap & { return d.eta; }, py::return_value_policy::reference_internal), [](RoughConductor &d, const Bitmap &b) { d.eta.assign(b); })
+        .def_property("k", py::cpp_function([](RoughConductor &d) -> Bitmap & { return d.k; }, py::return_value_policy::reference_internal), [](RoughConductor &d, const Bitmap &b) { d.k.assign(b); })
+        .def_property("specular_reflectance", py::cpp_function([](RoughConductor &d) -> Bitmap & { return d.specular_reflectance; }, py::return_value_policy::reference_internal), [](RoughConductor &d, const Bitmap &b) { d.specular_reflectance.assign(b); });
 
     py::class_<Sensor, Object, std::shared_ptr<Sensor>>(m, "PerspectiveCamera")
         .def_property("to_world", [](const Sensor &s) { return mat_to_numpy(s.to_world); }, [](Sensor &s, const farray &a) { s.to_world = mat_from_numpy(a); s.dirty = true; })
@@ -697,7 +704,7 @@ PYBIND11_MODULE(_psdr_host, m) {
     py::class_<AreaLight, Emitter, std::shared_ptr<AreaLight>>(m, "AreaLight")
         .def_property_readonly("radiance", [](const AreaLight &a) { return py::make_tuple(a.radiance[0], a.radiance[1], a.radiance[2]); });
     py::class_<EnvironmentMap, Emitter, std::shared_ptr<EnvironmentMap>>(m, "EnvironmentMap")
-        .def_property_readonly("radiance", [](EnvironmentMap &e) -> Bitmap & { return e.radiance; }, py::return_value_policy::reference_internal)
+        .def_property("radiance", py::cpp_function([](EnvironmentMap &e) -> Bitmap & { return e.radiance; }, py::return_value_policy::reference_internal), [](EnvironmentMap &e, const Bitmap &b) { e.radiance.assign(b); })
         .def_property("scale", [](const EnvironmentMap &e) { return e.scale; }, [](EnvironmentMap &e, float v) { e.scale = v; e.scale_dirty = true; })
         .def_readwrite("scale_requires_grad", &EnvironmentMap::scale_requires_grad)
         .def_readwrite("transform_requires_grad", &EnvironmentMap::transform_requires_grad)

@@ -748,3 +748,28 @@ def test_face_indices_are_writable_before_the_first_configure(psdr_cuda):
         m.face_indices = f + 100
     with pytest.raises(RuntimeError):
         m.face_indices = f.reshape(-1)
+
+
+def test_bitmap_constructors_and_writable_members(psdr_cuda):
+    """Bitmap1fD / Bitmap3fD (), (value), (width, height, data), (file name) (src/psdr.cpp:102-106,112-116) and the read-write bitmap members
+    of the BSDFs and the environment map (src/psdr.cpp:208-215,236)"""
+    import os
+    from conftest import DATA
+    assert psdr_cuda.Bitmap3fD().resolution == (1, 1) and psdr_cuda.Bitmap1fD().channels == 1
+    assert np.allclose(psdr_cuda.Bitmap3fD([0.1, 0.2, 0.3]).data, [[0.1, 0.2, 0.3]]) and np.allclose(psdr_cuda.Bitmap1fD(0.25).data, [[0.25]])
+    t = psdr_cuda.Bitmap3fD(2, 3, np.arange(18, dtype=np.float32).reshape(6, 3))
+    assert t.resolution == (2, 3) and np.allclose(t.eval(np.array([[0.5, 0.5]], np.float32)), [[7.5, 8.5, 9.5]])
+    assert psdr_cuda.Bitmap3fD(os.path.join(DATA, "envmaps", "ballroom_1k.exr")).resolution == (1024, 512)
+    sc = psdr_cuda.Scene(-1)
+    sc.load_file(scene_path("cbox_bunny_rc"), False)
+    pm = sc.param_map
+    pm["BSDF[0]"].reflectance = t
+    assert pm["BSDF[0]"].reflectance.resolution == (2, 3) and np.array_equal(pm["BSDF[0]"].reflectance.data, t.data)
+    pm["BSDF[3]"].alpha_u = psdr_cuda.Bitmap1fD(0.4)
+    assert np.allclose(pm["BSDF[3]"].alpha_u.data, 0.4)
+    with pytest.raises(RuntimeError, match="channel"):
+        pm["BSDF[3]"].alpha_u = t
+    sc2 = psdr_cuda.Scene(-1)
+    sc2.load_file(scene_path("bunny_env"), False)
+    sc2.param_map["Emitter[0]"].radiance = psdr_cuda.Bitmap3fD(4, 2, np.ones((8, 3), np.float32))
+    assert sc2.param_map["Emitter[0]"].radiance.resolution == (4, 2)
