@@ -52,6 +52,18 @@ class Bitmap3fD(_BitmapCtor, BitmapD):
     _channels = 3
 
 
+_envmap_init = EnvironmentMap.__init__
+
+
+def _envmap_from_file(self, file_name):
+    """EnvironmentMap(file name) (envmap.h:14-16): a latitude-longitude OpenEXR radiance map"""
+    _envmap_init(self)
+    img = _read_exr(file_name, 3)
+    self.radiance.resolution = (img.shape[1], img.shape[0])
+    self.radiance.data = img.reshape(-1, 3)
+
+
+EnvironmentMap.__init__ = _envmap_from_file
 Sensor = PerspectiveCamera   # src/psdr.cpp:216-222: the reference's only Sensor is the PerspectiveCamera; one class serves both names
 
 

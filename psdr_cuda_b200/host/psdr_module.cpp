@@ -13,6 +13,7 @@
 
 #include <unistd.h>
 
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <cstdio>
@@ -696,14 +697,20 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_property("specular_reflectance", py::cpp_function([](RoughConductor &d) -> Bitmap & { return d.specular_reflectance; }, py::return_value_policy::reference_internal), [](RoughConductor &d, const Bitmap &b) { d.specular_reflectance.assign(b); });
 
     py::class_<Sensor, Object, std::shared_ptr<Sensor>>(m, "PerspectiveCamera")
+        .def(py::init([](float fov_x, float near_clip, float far_clip) { auto s = std::make_shared<Sensor>(); s->fov_x = fov_x; s->near_clip = near_clip; s->far_clip = far_clip; return s; }),
+             py::arg("fov_x"), py::arg("near"), py::arg("far"))   // src/psdr.cpp:223
         .def_property("to_world", [](const Sensor &s) { return mat_to_numpy(s.to_world); }, [](Sensor &s, const farray &a) { s.to_world = mat_from_numpy(a); s.dirty = true; })
         .def_readwrite("requires_grad", &Sensor::requires_grad)
         .def_readonly("fov_x", &Sensor::fov_x).def_readonly("near_clip", &Sensor::near_clip).def_readonly("far_clip", &Sensor::far_clip);
 
     py::class_<Emitter, Object, std::shared_ptr<Emitter>>(m, "Emitter");
     py::class_<AreaLight, Emitter, std::shared_ptr<AreaLight>>(m, "AreaLight")
+        .def(py::init([](const std::array<float, 3> &radiance, const Mesh *mesh) {   // src/psdr.cpp:231
+                 auto a = std::make_shared<AreaLight>(); for (int k = 0; k < 3; ++k) a->radiance[k] = radiance[k]; a->mesh = mesh ? mesh->index : -1; return a; }),
+             py::arg("radiance"), py::arg("mesh"))
         .def_property_readonly("radiance", [](const AreaLight &a) { return py::make_tuple(a.radiance[0], a.radiance[1], a.radiance[2]); });
     py::class_<EnvironmentMap, Emitter, std::shared_ptr<EnvironmentMap>>(m, "EnvironmentMap")
+        .def(py::init([]() { return std::make_shared<EnvironmentMap>(); }))   // the Python layer adds the (file name) form of src/psdr.cpp:234
         .def_property("radiance", py::cpp_function([](EnvironmentMap &e) -> Bitmap & { return e.radiance; }, py::return_value_policy::reference_internal), [](EnvironmentMap &e, const Bitmap &b) { e.radiance.assign(b); })
         .def_property("scale", [](const EnvironmentMap &e) { return e.scale; }, [](EnvironmentMap &e, float v) { e.scale = v; e.scale_dirty = true; })
         .def_readwrite("scale_requires_grad", &EnvironmentMap::scale_requires_grad)

@@ -773,3 +773,26 @@ def test_bitmap_constructors_and_writable_members(psdr_cuda):
     sc2.load_file(scene_path("bunny_env"), False)
     sc2.param_map["Emitter[0]"].radiance = psdr_cuda.Bitmap3fD(4, 2, np.ones((8, 3), np.float32))
     assert sc2.param_map["Emitter[0]"].radiance.resolution == (4, 2)
+
+
+def test_every_class_the_reference_can_construct_from_python_can_be_constructed(psdr_cuda):
+    """py::init<> overloads of src/psdr.cpp (the fixture counts them per class): each such class has a working constructor here"""
+    import json
+    import os
+    from conftest import DATA, GOLDEN
+    with open(os.path.join(GOLDEN, "ref_python_surface.json")) as fh:
+        surface = json.load(fh)
+    mesh = psdr_cuda.Mesh()
+    mesh.load(os.path.join(DATA, "objects", "cbox", "emitter.obj"))
+    exr = os.path.join(DATA, "envmaps", "ballroom_1k.exr")
+    args = {"RenderOption": (32, 16, 4), "RayC": (), "RayD": (), "FrameC": (np.array([[0, 0, 1.0]], np.float32),), "FrameD": (), "Bitmap1fD": (0.5,), "Bitmap3fD": ([0.1, 0.2, 0.3],),
+            "DiscreteDistribution": (), "HyperCubeDistribution2f": (), "HyperCubeDistribution3f": (), "PerspectiveCamera": (40.0, 0.1, 1e3), "AreaLight": ([1.0, 2.0, 3.0], mesh),
+            "EnvironmentMap": (exr,), "Mesh": (), "Scene": (-1,), "FieldExtractionIntegrator": ("depth",), "DirectIntegrator": (2, 1)}
+    constructible = sorted(c for c, info in surface.items() if info["constructors"] > 0)
+    assert constructible == sorted(args)
+    for cls in constructible:
+        obj = getattr(psdr_cuda, cls)(*args[cls])
+        assert obj is not None
+    cam = psdr_cuda.PerspectiveCamera(40.0, 0.1, 1e3)
+    assert cam.fov_x == 40.0 and np.array_equal(cam.to_world, np.eye(4, dtype=np.float32))
+    assert psdr_cuda.EnvironmentMap(exr).radiance.resolution == (1024, 512) and psdr_cuda.AreaLight([1.0, 2.0, 3.0], mesh).radiance == (1.0, 2.0, 3.0)
