@@ -444,3 +444,18 @@ def test_zero_tangent_through_an_infinite_local_derivative_stays_zero():
         assert np.abs(at[px] - bt[px]).max() <= 1e-3 * np.abs(bt).max()
     assert_images_close(a, b, rel=2e-4, outliers=0.01, what="primal")
     assert_images_close(at, bt, rel=1e-3, outliers=0.02, what="tangent")
+
+
+@pytest.mark.parametrize("field", ["silhouette", "position", "depth", "geoNormal", "shNormal"])
+def test_field_integrator_derivatives_match_reference_source(field):
+    """FieldExtractionIntegrator in its D flavour (field.cpp:34-54 on the solid-angle intersection, scene.cpp:345-372) plus its primary-edge
+    term (integrator.cpp:98-119) — the reference's examples/config.py `bunny_silhouette` setup: vertex tangent of the bunny"""
+    rng = np.random.default_rng(3)
+    r, o = pair("bunny", 32, 32, 2, 8, 0, configure=False)
+    _seed(r, o, ("vertices", 0), rng, "bunny")
+    r.configure()
+    o.configure()
+    (a, at), (b, bt) = refrun.FieldExtractionIntegrator(field).renderD(r), orc.FieldExtractionIntegrator(field).renderD(o)
+    assert np.abs(bt).max() > 0
+    assert_images_close(a, b, rel=2e-5, what="primal")
+    assert_images_close(at, bt, rel=1e-3, outliers=0.02, what="tangent")
