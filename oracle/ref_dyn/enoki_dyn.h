@@ -386,7 +386,13 @@ template <class X, class T, size_t n, std::enable_if_t<std::is_same_v<X, Array<T
 ENOKI_DYN_AASSIGN(+) ENOKI_DYN_AASSIGN(-) ENOKI_DYN_AASSIGN(*) ENOKI_DYN_AASSIGN(/) ENOKI_DYN_AASSIGN(&)
 #undef ENOKI_DYN_AASSIGN
 template <class I, class A, std::enable_if_t<is_arr_v<A>, int> = 0> I floor2int(const A &a) { I r; for (size_t i = 0; i < arr_size<A>::value; ++i) r.d[i] = floor2int<typename I::Value>(a.d[i]); return r; }
-template <class T, class U, size_t n> auto dot(const Array<T, n> &a, const Array<U, n> &b) { auto r = a.d[n - 1] * b.d[n - 1]; for (size_t i = n - 1; i-- > 0;) r = fmadd(a.d[i], b.d[i], r); return r; }
+// dot as an fmadd chain: from the last component down (the oracle's and the CUDA product's form; default) or, with dot_from_first(), from the
+// first component up (what Enoki's generic dot over nested arrays is believed to do): a last-bit difference, measured like matvec_plain()
+inline bool &dot_from_first() { static bool on = false; return on; }
+template <class T, class U, size_t n> auto dot(const Array<T, n> &a, const Array<U, n> &b) {
+    if (dot_from_first()) { auto r = a.d[0] * b.d[0]; for (size_t i = 1; i < n; ++i) r = fmadd(a.d[i], b.d[i], r); return r; }
+    auto r = a.d[n - 1] * b.d[n - 1]; for (size_t i = n - 1; i-- > 0;) r = fmadd(a.d[i], b.d[i], r); return r;
+}
 template <class T, size_t n> T squared_norm(const Array<T, n> &a) { return dot(a, a); }
 template <class T, size_t n> T norm(const Array<T, n> &a) { return sqrt(squared_norm(a)); }
 template <class T, size_t n> Array<T, n> normalize(const Array<T, n> &a) { return a * rsqrt(squared_norm(a)); }

@@ -195,6 +195,7 @@ extern "C" {
 const char *ref_last_error() { return g_err.c_str(); }
 void ref_set_matvec_plain(int on) { enoki::matvec_plain() = on != 0; }   // see oracle/ref_dyn/enoki_dyn.h
 void ref_set_inverse_rounded(int on) { enoki::inverse_rounded() = on != 0; }
+void ref_set_dot_from_first(int on) { enoki::dot_from_first() = on != 0; }
 
 // Scene::load_file(xml, false) with the working directory the scene's relative paths expect, RenderOption overrides, then configure()
 void *ref_scene_load(const char *xml_path, const char *cwd, int width, int height, int spp, int sppe, int sppse) {

@@ -65,6 +65,11 @@ def set_inverse_rounded(on):
     lib().ref_set_inverse_rounded(int(on))
 
 
+def set_dot_from_first(on):
+    """dot products accumulated from the first component up instead of from the last down (see oracle/ref_dyn/enoki_dyn.h)"""
+    lib().ref_set_dot_from_first(int(on))
+
+
 class Scene:
     """psdr::Scene: load_file(xml, auto_configure=False) + RenderOption overrides; configure() is explicit, as in the reference"""
 

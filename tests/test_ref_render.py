@@ -86,14 +86,22 @@ def test_tables_match_reference_source(name):
     assert np.allclose(pr[:, 6], po[:, 6], rtol=1e-3, atol=2e-6)
 
 
-def test_tables_with_the_assumed_enoki_matrix_product():
-    """same with matrix * vector as the fmadd chain assumed for Enoki (the oracle and the CUDA product use plain sums): the last bit of a
-    transformed vertex, nothing else; a few coplanar edges then fall on the other side of the 1 - EdgeEpsilon test (mesh.cpp:262)"""
-    r, o = pair("cbox_bunny", 16, 16, 1, 1, 1, plain=False)
-    tr, to = r.triangle_info(), o.triangle_info()
-    assert np.abs(tr - to).max() <= 3e-7 * np.abs(to).max()
-    assert abs(len(r.sec_edges()) - len(o.sec_edges())) <= 8
-    refrun.set_matvec_plain(True)
+def test_with_the_forms_assumed_for_enoki():
+    """the stand-in's two arithmetic switches set to what Enoki itself is believed to do — matrix * vector as an fmadd chain over columns, dot
+    accumulated from the first component up — where the oracle and the CUDA product use plain sums and accumulate from the last component
+    down: last bits of the tables (a few coplanar edges then fall on the other side of the 1 - EdgeEpsilon test, mesh.cpp:262), and an image
+    within the usual tolerance"""
+    refrun.set_dot_from_first(True)
+    try:
+        r, o = pair("cbox_bunny", 24, 24, 2, 1, 1, plain=False)
+        tr, to = r.triangle_info(), o.triangle_info()
+        assert np.abs(tr - to).max() <= 1e-6 * np.abs(to).max()
+        assert abs(len(r.sec_edges()) - len(o.sec_edges())) <= 8
+        a, b = refrun.DirectIntegrator(1, 1).renderC(r), orc.DirectIntegrator(1, 1).renderC(o)
+        assert_images_close(a, b, rel=2e-4, outliers=0.01, what="renderC")
+    finally:
+        refrun.set_dot_from_first(False)
+        refrun.set_matvec_plain(True)
 
 
 def test_closest_hits_match():
