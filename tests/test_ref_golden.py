@@ -118,3 +118,22 @@ def test_cuda_matches_reference_source_goldens(label, golden):
             close(img, golden[label], 2e-4, 0.01, label)
         close(dimg, golden[label + "_t"], 1e-3, 1.5 * OUTLIERS.get(label, 0.02), label + " derivative")
     ctx.close()
+
+
+@pytest.mark.parametrize("label", ["c_cbox_d11", "d_cbox_translate", "d_env_secondary"])
+def test_committed_goldens_are_what_the_reference_run_produces(label, golden):
+    """where /root/reference is present (this container): the committed vectors are bit for bit what oracle/_ref/libref_render.so produces today"""
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip("oracle/_ref/libref_render.so not built and /root/reference absent")
+    refrun.set_matvec_plain(True)
+    name, (w, h, spp, sppe, sppse), integ, leaf = CASES[label]
+    sc = refrun.Scene(scene_path(name), os.path.join(ROOT, "tests"), w, h, spp, sppe, sppse)
+    gen.seed(sc, leaf, sc.num_vertices(leaf[1]) if leaf and leaf[0] == "translate" else 0)
+    sc.configure()
+    I = refrun.DirectIntegrator(integ[1], integ[2])
+    if leaf is None:
+        assert np.array_equal(I.renderC(sc), golden[label])
+    else:
+        img, dimg = I.renderD(sc)
+        assert np.array_equal(img, golden[label]) and np.array_equal(dimg, golden[label + "_t"])
