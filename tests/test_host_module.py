@@ -593,6 +593,15 @@ LOADER_CASES = {
     + _SHAPE % ("w", "wall_back", '<transform name="to_world"><rotate x="1" y="0" z="0" angle="-90"/><scale x="0.5" y="2" z="3"/><matrix value="0 1 0 0  1 0 0 0  0 0 1 0  0 0 0 1"/></transform>', "m", "")
     + _SHAPE % ("l", "emitter", "", "m", '<emitter type="area"><rgb name="radiance" value="1, 2, 3"/></emitter>') + "</scene>",
 }
+# bitmap textures (texture type="bitmap" + filename) on a diffuse reflectance and a rough-conductor roughness, and an environment map with a
+# scale and a transform
+LOADER_CASES["textures"] = ("<scene>" + _SENSOR % ("45", "", "to_world", '<translate z="5"/>')
+    + '<bsdf type="diffuse" id="t"><texture name="reflectance" type="bitmap"><string name="filename" value="./data/envmaps/ballroom_1k.exr"/></texture></bsdf>'
+    + '<bsdf type="roughconductor" id="r"><texture name="alpha" type="bitmap"><string name="filename" value="./data/envmaps/ballroom_1k.exr"/></texture>'
+    + '<rgb name="eta" value="0.2, 0.9, 1.1"/><rgb name="k" value="3.9, 2.4, 2.2"/></bsdf>'
+    + '<emitter type="envmap"><string name="filename" value="./data/envmaps/ballroom_1k.exr"/><float name="scale" value="2.5"/>'
+    + '<transform name="to_world"><rotate x="0" y="1" z="0" angle="90"/></transform></emitter>'
+    + _SHAPE % ("f", "floor", "", "t", "") + _SHAPE % ("w", "wall_back", "", "r", "") + "</scene>")
 LOADER_ERRORS = {
     "unknown bsdf ref": "<scene>" + _SENSOR % ("30", "", "to_world", "") + '<bsdf type="diffuse" id="a"><float name="reflectance" value="0.3"/></bsdf>' + _SHAPE % ("f", "floor", "", "zzz", "") + "</scene>",
     "duplicate bsdf id": "<scene>" + _SENSOR % ("30", "", "to_world", "") + '<bsdf type="diffuse" id="a"><float name="reflectance" value="0.3"/></bsdf><bsdf type="diffuse" id="a"><float name="reflectance" value="0.4"/></bsdf>' + "</scene>",
