@@ -467,3 +467,25 @@ def test_field_integrator_derivatives_match_reference_source(field):
     assert np.abs(bt).max() > 0
     assert_images_close(a, b, rel=2e-5, what="primal")
     assert_images_close(at, bt, rel=1e-3, outliers=0.02, what="tangent")
+
+
+def test_xml_bitmap_textures_and_transformed_envmap_render(tmp_path, monkeypatch):
+    """a scene whose XML loads OpenEXR bitmaps (a diffuse reflectance and a rough-conductor roughness texture; the meshes carry no uvs, so
+    the lookups run at uv = 0) under an environment map with a scale and a rotated to_world: loader -> configure -> renderC / renderD"""
+    from test_host_module import LOADER_CASES
+    xml = tmp_path / "textures.xml"
+    xml.write_text(LOADER_CASES["textures"])
+    monkeypatch.chdir(TESTS)
+    refrun.set_matvec_plain(True)
+    r = refrun.Scene(str(xml), TESTS, 24, 16, 4, 0, 0)
+    d = orc.load_scene_description(str(xml))
+    o = orc.Scene(d, dict(width=24, height=16, spp=4, sppe=0, sppse=0))
+    for s in (r, o):
+        s.set_envmap_tangent(None, 1.0)
+    r.configure()
+    o.configure()
+    assert_images_close(refrun.DirectIntegrator(1, 1).renderC(r), orc.DirectIntegrator(1, 1).renderC(o), rel=2e-4, outliers=0.01, what="renderC")
+    (a, at), (b, bt) = refrun.DirectIntegrator(1, 1).renderD(r), orc.DirectIntegrator(1, 1).renderD(o)
+    assert np.abs(b).max() > 0 and np.abs(bt).max() > 0
+    assert_images_close(a, b, rel=2e-4, outliers=0.01, what="renderD")
+    assert_images_close(at, bt, rel=1e-3, outliers=0.02, what="tangent")
