@@ -489,3 +489,35 @@ def test_xml_bitmap_textures_and_transformed_envmap_render(tmp_path, monkeypatch
     assert np.abs(b).max() > 0 and np.abs(bt).max() > 0
     assert_images_close(a, b, rel=2e-4, outliers=0.01, what="renderD")
     assert_images_close(at, bt, rel=1e-3, outliers=0.02, what="tangent")
+
+
+def test_reference_run_derivative_image_agrees_with_finite_differences_of_the_geometry():
+    """the physical check of examples/run_test.py:150-231 on the reference run itself, independent of the oracle: translating the bunny of
+    cbox_bunny along x, the forward-mode derivative image (interior + primary-edge + secondary-edge terms, carried by the stand-in's tangents
+    through the reference's own statements) matches the central finite difference of the reference's renderC images; without the boundary
+    terms it does not — what path-space differentiable rendering is about"""
+    W, spp, eps = 32, 128, 1.0
+    xml = scene_path("cbox_bunny")
+    refrun.set_matvec_plain(True)
+
+    def render(dx, terms):
+        r = refrun.Scene(xml, TESTS, W, W, spp, spp if terms == "all" else 0, spp if terms == "all" else 0)
+        M = np.eye(4, dtype=np.float32)
+        M[0, 3] = dx
+        r.set_mesh_transform(1, M, True)
+        if terms:
+            t = np.zeros((4, 4), np.float32)
+            t[0, 3] = 1.0
+            r.set_mesh_transform_tangent(1, t, True)
+        r.configure()
+        I = refrun.DirectIntegrator(1, 1)
+        return I.renderD(r)[1] if terms else I.renderC(r)
+
+    def blur(x):   # 4x4 box filter on the luminance-like channel mean: the estimators are noisy per pixel
+        return x.reshape(W, W, 3).mean(2).reshape(W // 4, 4, W // 4, 4).mean((1, 3)).ravel()
+    fd = blur((render(eps, None) - render(-eps, None)) / (2 * eps))
+    full, interior = blur(render(0.0, "all")), blur(render(0.0, "interior"))
+    corr = lambda a, b: float(np.corrcoef(a, b)[0, 1])
+    assert corr(full, fd) > 0.85, corr(full, fd)
+    assert corr(interior, fd) < 0.6, corr(interior, fd)
+    assert 0.8 < np.linalg.norm(full) / np.linalg.norm(fd) < 1.25
