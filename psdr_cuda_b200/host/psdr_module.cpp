@@ -665,7 +665,10 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def("__repr__", &Object::to_string);
 
     py::class_<RenderOption>(m, "RenderOption")
-        .def(py::init<>()).def(py::init<int, int, int>()).def(py::init<int, int, int, int>()).def(py::init<int, int, int, int, int>())
+        .def(py::init<>())   // keyword names as in src/psdr.cpp:55-57
+        .def(py::init<int, int, int>(), py::arg("width"), py::arg("height"), py::arg("spp/sppe"))
+        .def(py::init<int, int, int, int>(), py::arg("width"), py::arg("height"), py::arg("spp"), py::arg("sppe"))
+        .def(py::init<int, int, int, int, int>(), py::arg("width"), py::arg("height"), py::arg("spp"), py::arg("sppe"), py::arg("sppse"))
         .def_readwrite("width", &RenderOption::width).def_readwrite("height", &RenderOption::height).def_readwrite("spp", &RenderOption::spp)
         .def_readwrite("sppe", &RenderOption::sppe).def_readwrite("sppse", &RenderOption::sppse).def_readwrite("log_level", &RenderOption::log_level)
         .def("__repr__", [](const RenderOption &o) {   // src/psdr.cpp:63-71
@@ -721,7 +724,7 @@ PYBIND11_MODULE(_psdr_host, m) {
 
     py::class_<Mesh, Object, std::shared_ptr<Mesh>>(m, "Mesh")
         .def(py::init<>())                                                      // src/psdr.cpp:242-243
-        .def("load", [](Mesh &x, const std::string &path, bool) { x.load(path); }, py::arg("fname"), py::arg("verbose") = false)
+        .def("load", [](Mesh &x, const std::string &path, bool) { x.load(path); }, py::arg("filename"), py::arg("verbose") = false)
         .def_property("face_uv_indices", [](const Mesh &x) {
             iarray a(std::vector<py::ssize_t>{(py::ssize_t)(x.uv_faces.size() / 3), 3});
             if (!x.uv_faces.empty()) std::memcpy(a.mutable_data(), x.uv_faces.data(), x.uv_faces.size() * sizeof(int));

@@ -805,3 +805,31 @@ def test_every_class_the_reference_can_construct_from_python_can_be_constructed(
     cam = psdr_cuda.PerspectiveCamera(40.0, 0.1, 1e3)
     assert cam.fov_x == 40.0 and np.array_equal(cam.to_world, np.eye(4, dtype=np.float32))
     assert psdr_cuda.EnvironmentMap(exr).radiance.resolution == (1024, 512) and psdr_cuda.AreaLight([1.0, 2.0, 3.0], mesh).radiance == (1.0, 2.0, 3.0)
+
+
+def test_keyword_arguments_of_the_reference_bindings(psdr_cuda, monkeypatch):
+    """the "name"_a keywords of src/psdr.cpp (RenderOption, Mesh.load / set_transform / append_transform / sample_position, Scene.load_file /
+    load_string, Bitmap.eval, DirectIntegrator) are accepted under the same names and defaults"""
+    import os
+    from conftest import DATA, ROOT
+    o = psdr_cuda.RenderOption(width=8, height=4, spp=2, sppe=1, sppse=3)
+    assert (o.width, o.height, o.spp, o.sppe, o.sppse) == (8, 4, 2, 1, 3)
+    assert psdr_cuda.RenderOption(width=8, height=4, spp=2, sppe=5).sppse == 5
+    m = psdr_cuda.Mesh()
+    m.load(filename=os.path.join(DATA, "objects", "cbox", "emitter.obj"), verbose=False)
+    m.set_transform(mat=np.eye(4, dtype=np.float32), set_left=False)
+    m.append_transform(mat=np.eye(4, dtype=np.float32), append_left=True)
+    assert m.sample_position(sample2=np.array([[0.3, 0.6]], np.float32), active=True).p.shape == (1, 3)
+    sc = psdr_cuda.Scene(-1)
+    sc.load_file(file_name=scene_path("cbox_bunny"), auto_configure=False)
+    monkeypatch.chdir(os.path.join(ROOT, "tests"))
+    sc2 = psdr_cuda.Scene(-1)
+    sc2.load_string(scene_xml=LOADER_CASES["aliases"], auto_configure=False)
+    assert sc2.num_meshes == 2
+    assert psdr_cuda.Bitmap3fD([0.5, 0.5, 0.5]).eval(uv=np.zeros((2, 2), np.float32), flip_v=False).shape == (2, 3)
+    d = psdr_cuda.DirectIntegrator(bsdf_samples=2, light_samples=3)
+    assert not d.hide_emitters
+    import inspect
+    assert list(inspect.signature(psdr_cuda.Integrator.renderC).parameters)[1:] == ["scene", "sensor_id"]
+    assert list(inspect.signature(psdr_cuda.Integrator.renderD).parameters)[1:] == ["scene", "sensor_id"]
+    assert "nrounds" in psdr_cuda.Integrator.preprocess_secondary_edges.__doc__ and "resolution" in psdr_cuda.Integrator.preprocess_secondary_edges.__doc__
