@@ -182,3 +182,22 @@ def test_sampler_streams_match_reference_source(libs):
     a, b, c = np.zeros(3, np.float32), np.zeros(2, np.float32), np.zeros(3, np.float32)
     ref.ref_sampler_lane(C.c_uint64(0), 3, p(a), p(b), p(c))
     assert np.allclose(a, [0.79081202, 0.05460072, 0.82107019], atol=1e-7)
+
+
+def test_product_device_math_matches_reference_source(tmp_path):
+    """tests/native/ref_math_check.cu: the per-lane math the sm_100a kernels inline (csrc/pb_math.cuh: warps, frame, ray / triangle, bilinear,
+    luminance, sampler streams incl. the jump-ahead; csrc/pb_rc.cuh: GGX, Smith G1, visible-normal sampling, conductor Fresnel, rough-conductor
+    eval / pdf / sample), host-compiled, against the reference's own source in oracle/_ref/libref_math.so — function by function, no oracle
+    in between"""
+    import shutil
+    import subprocess
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/libref_math.so not built (needs /root/reference: bash oracle/build_ref.sh)")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "ref_math_check")
+    subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "ref_math_check.cu"), "-ldl"], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe, REF], capture_output=True, text=True)
+    assert out.returncode == 0 and "ref_math_check: ok" in out.stdout, out.stdout[-3000:]
