@@ -10,7 +10,9 @@
 #include <math.h>
 
 #define PB_HD __host__ __device__ __forceinline__
+#ifndef PB_D   // tests/native/ref_shade_check.cu compiles the per-lane shading functions for the host and predefines this
 #define PB_D __device__ __forceinline__
+#endif
 
 namespace pb {
 

@@ -201,3 +201,23 @@ def test_product_device_math_matches_reference_source(tmp_path):
                            os.path.join(ROOT, "tests", "native", "ref_math_check.cu"), "-ldl"], stderr=subprocess.DEVNULL)
     out = subprocess.run([exe, REF], capture_output=True, text=True)
     assert out.returncode == 0 and "ref_math_check: ok" in out.stdout, out.stdout[-3000:]
+
+
+def test_product_shading_primitives_match_reference_source(tmp_path):
+    """tests/native/ref_shade_check.cu: csrc/pb_shade.cuh as the primal kernels inline it — bitmap lookups, discrete sampling with sample reuse,
+    the float GGX / Fresnel path, BSDF eval / pdf / sample for diffuse and rough-conductor records (both kernel instantiations), the scene-box
+    exit of environment-map samples — host-compiled, against the reference's own ggx.cpp / diffuse.cpp / roughconductor.cpp / utils.h
+    (libref_math.so) and bitmap.cpp / pmf.cpp (libref_render.so)"""
+    import shutil
+    import subprocess
+    render = os.path.join(ROOT, "oracle", "_ref", "libref_render.so")
+    if not (os.path.exists(REF) and os.path.exists(render)):
+        pytest.skip("oracle/_ref libraries not built (needs /root/reference: bash oracle/build_ref.sh)")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "ref_shade_check")
+    subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "ref_shade_check.cu"), "-ldl"], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe, REF, render], capture_output=True, text=True)
+    assert out.returncode == 0 and "ref_shade_check: ok" in out.stdout, out.stdout[-3000:]
