@@ -536,4 +536,37 @@ void *ref_scene_load_string(const char *xml, const char *cwd) {
 // Mesh::dump (mesh.cpp:318-392) of a loaded scene's mesh
 int ref_mesh_dump(void *s, int mesh, const char *path) { return guard([&] { ((Scene *)s)->m_meshes.at(mesh)->dump(path); }); }
 
+// PerspectiveCamera::sample_primary_ray(samples) (perspective.cpp:120-136, the C flavour) -> o[n][3], d[n][3]
+int ref_sample_primary_ray(void *s, int sensor, const float *samples2, int n, float *o, float *d) {
+    return guard([&] {
+        std::vector<float> buf(n);
+        Vector2fC q;
+        for (int c = 0; c < 2; ++c) { for (int i = 0; i < n; ++i) buf[i] = samples2[2 * i + c]; q[c] = FloatC::copy(buf.data(), n); }
+        RayC r = ((Scene *)s)->m_sensors.at(sensor)->sample_primary_ray(q);
+        for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) { o[3 * i + c] = lval(r.o[c], i); d[3 * i + c] = lval(r.d[c], i); }
+    });
+}
+// the configured environment map: scale, resolution, m_from_world, and its radiance texels [h][w][3]
+int ref_get_envmap(void *s, float *scale_w_h_from_world19, float *radiance) {
+    return guard([&] {
+        const EnvironmentMap *e = ((Scene *)s)->m_emitter_env;
+        PSDR_ASSERT(e != nullptr && e->m_ready);
+        scale_w_h_from_world19[0] = e->m_scale[0]; scale_w_h_from_world19[1] = (float)e->m_radiance.m_resolution.x(); scale_w_h_from_world19[2] = (float)e->m_radiance.m_resolution.y();
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) scale_w_h_from_world19[3 + 4 * i + j] = e->m_from_world(i, j)[0];
+        if (radiance) { const size_t n = slices(e->m_radiance.m_data); for (size_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) radiance[3 * i + c] = e->m_radiance.m_data[c][i]; }
+    });
+}
+// EnvironmentMap::eval_direction<false>(wi) (envmap.cpp:42-58)
+int ref_env_eval_direction(void *s, const float *dirs, int n, float *out) {
+    return guard([&] {
+        const EnvironmentMap *e = ((Scene *)s)->m_emitter_env;
+        PSDR_ASSERT(e != nullptr);
+        std::vector<float> buf(n);
+        Vector3fC w;
+        for (int c = 0; c < 3; ++c) { for (int i = 0; i < n; ++i) buf[i] = dirs[3 * i + c]; w[c] = FloatC::copy(buf.data(), n); }
+        SpectrumC v = e->eval_direction<false>(w, MaskC(true));
+        for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) out[3 * i + c] = lval(v[c], i);
+    });
+}
+
 }  // extern "C"

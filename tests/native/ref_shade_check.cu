@@ -2,7 +2,8 @@
 // discrete-distribution sampling with sample reuse, the float GGX / Fresnel path of the primal kernels, BSDF eval / pdf / sample for diffuse
 // and rough-conductor records, the scene-box exit of environment-map samples — against the REFERENCE'S OWN SOURCE compiled for the CPU:
 // argv[1] = oracle/_ref/libref_math.so (ggx.cpp, diffuse.cpp, roughconductor.cpp, utils.h), argv[2] = oracle/_ref/libref_render.so
-// (bitmap.cpp, pmf.cpp). pb_shade.cuh is device code; for this check its functions are compiled __host__ __device__ (PB_D predefined) and
+// (bitmap.cpp, pmf.cpp; and, when argv[3] = the tests/ directory is given, perspective.cpp's camera rays and envmap.cpp's direction lookup on
+// the fixture scenes loaded and configured by the reference's own Scene). pb_shade.cuh is device code; for this check its functions are compiled __host__ __device__ (PB_D predefined) and
 // its three device intrinsics (__ldg, __float_as_int) read memory / bits directly.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -12,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <random>
+#include <string>
 #include <vector>
 
 #define PB_D __host__ __device__ __forceinline__
@@ -32,7 +34,7 @@ static void expect(bool ok, const char *what, float a, float b) { ++checked; if 
 static TexRef tex(const float *d, int w, int h, int c) { TexRef t; t.data = d; t.grad = nullptr; t.w = w; t.h = h; t.c = c; t.pad = 0; return t; }
 
 int main(int argc, char **argv) {
-    if (argc < 3) { std::printf("usage: ref_shade_check <libref_math.so> <libref_render.so>\n"); return 2; }
+    if (argc < 3) { std::printf("usage: ref_shade_check <libref_math.so> <libref_render.so> [tests dir]\n"); return 2; }
     void *hm = dlopen(argv[1], RTLD_NOW), *hr = dlopen(argv[2], RTLD_NOW);
     if (!hm || !hr) { std::printf("cannot load the reference libraries: %s\n", dlerror()); return 2; }
 #define SYM(lib, name, type) auto name = (type)dlsym(lib, #name); if (!name) { std::printf("missing %s\n", #name); return 2; }
@@ -155,6 +157,58 @@ int main(int argc, char **argv) {
             float x = u[i], p;
             const int k = sample_reuse(cmf.data(), pmf.data(), n, acc, x, p);
             expect(k == idx[i] && close(pdf[i], p, 2) && close(uo[i], x, 4, 2e-6f), "sample_reuse", (float)idx[i], (float)k);
+        }
+    }
+    if (argc > 3) {
+        SYM(hr, ref_scene_load, void *(*)(const char *, const char *, int, int, int, int, int))
+        SYM(hr, ref_scene_configure, int (*)(void *))
+        SYM(hr, ref_scene_free, void (*)(void *))
+        SYM(hr, ref_get_sensor, int (*)(void *, int, float *))
+        SYM(hr, ref_sample_primary_ray, int (*)(void *, int, const float *, int, float *, float *))
+        SYM(hr, ref_get_envmap, int (*)(void *, float *, float *))
+        SYM(hr, ref_env_eval_direction, int (*)(void *, const float *, int, float *))
+        const std::string dir = argv[3];
+        for (const char *name : {"cbox_bunny", "tree", "bunny_env", "bunny_env_2"}) {
+            void *sc = ref_scene_load((dir + "/data/scenes/" + name + ".xml").c_str(), dir.c_str(), 40, 24, 1, 0, 0);
+            if (!sc || ref_scene_configure(sc) != 0) { std::printf("cannot load %s through the reference\n", name); return 2; }
+            // camera rays (perspective.cpp:120-136) from the reference's own matrices
+            float cam[55];
+            ref_get_sensor(sc, 0, cam);
+            SensorRec C;
+            std::memset(&C, 0, sizeof C);
+            for (int i = 0; i < 16; ++i) { C.sample_to_camera.m[i] = cam[i]; C.world_to_sample.m[i] = cam[16 + i]; C.to_world.m[i] = cam[32 + i]; }
+            const int n = 2000;
+            std::vector<float> smp(2 * n), ro(3 * n), rd(3 * n);
+            for (auto &x : smp) x = U(0, 1);
+            ref_sample_primary_ray(sc, 0, smp.data(), n, ro.data(), rd.data());
+            for (int i = 0; i < n; ++i) {
+                float3 o, d;
+                sample_primary_ray(C, smp[2 * i], smp[2 * i + 1], o, d);
+                expect(ro[3 * i] == o.x && ro[3 * i + 1] == o.y && ro[3 * i + 2] == o.z, "camera ray origin", ro[3 * i], o.x);
+                expect(close(rd[3 * i], d.x, 4, 2e-7f) && close(rd[3 * i + 1], d.y, 4, 2e-7f) && close(rd[3 * i + 2], d.z, 4, 2e-7f), "camera ray direction", rd[3 * i + 2], d.z);
+            }
+            // environment map lookup by direction (envmap.cpp:42-58; bitmap.cpp:56-96 without the v flip)
+            float env[19];
+            if (std::strncmp(name, "bunny_env", 9) == 0 && ref_get_envmap(sc, env, nullptr) == 0) {
+                const int w = (int)env[1], h = (int)env[2];
+                std::vector<float> texels((size_t)w * h * 3);
+                ref_get_envmap(sc, env, texels.data());
+                EmitterRec em;
+                std::memset(&em, 0, sizeof em);
+                em.type = EMITTER_ENVMAP; em.env_radiance = tex(texels.data(), w, h, 3); em.env_scale = env[0];
+                for (int i = 0; i < 16; ++i) em.env_from_world.m[i] = env[3 + i];
+                std::vector<float> dirs(3 * n), out(3 * n);
+                for (int i = 0; i < n; ++i) { const float3 d = unit3(); dirs[3 * i] = d.x; dirs[3 * i + 1] = d.y; dirs[3 * i + 2] = d.z; }
+                dirs[0] = 0.f; dirs[1] = 1.f; dirs[2] = 0.f; dirs[3] = 0.f; dirs[4] = -1.f; dirs[5] = 0.f;   // the poles
+                ref_env_eval_direction(sc, dirs.data(), n, out.data());
+                for (int i = 0; i < n; ++i) {
+                    const float3 e = env_eval_direction(em, f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+                    // a last-bit difference in atan2 / acos moves the lookup by 1e-7 of the map; neighbouring texels of an HDR map differ
+                    const float tol = 2e-4f * std::fmax(1.f, std::fmax(out[3 * i], std::fmax(out[3 * i + 1], out[3 * i + 2])));
+                    expect(close(out[3 * i], e.x, 64, tol) && close(out[3 * i + 1], e.y, 64, tol) && close(out[3 * i + 2], e.z, 64, tol), "env_eval_direction", out[3 * i], e.x);
+                }
+            }
+            ref_scene_free(sc);
         }
     }
     std::printf("ref_shade_check: %s (%d comparisons, %d mismatches)\n", bad ? "FAILED" : "ok", checked, bad);

@@ -219,5 +219,5 @@ def test_product_shading_primitives_match_reference_source(tmp_path):
     exe = str(tmp_path / "ref_shade_check")
     subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
                            os.path.join(ROOT, "tests", "native", "ref_shade_check.cu"), "-ldl"], stderr=subprocess.DEVNULL)
-    out = subprocess.run([exe, REF, render], capture_output=True, text=True)
+    out = subprocess.run([exe, REF, render, os.path.join(ROOT, "tests")], capture_output=True, text=True)   # + camera rays and envmap lookups on the fixtures
     assert out.returncode == 0 and "ref_shade_check: ok" in out.stdout, out.stdout[-3000:]
