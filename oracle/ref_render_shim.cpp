@@ -569,4 +569,23 @@ int ref_env_eval_direction(void *s, const float *dirs, int n, float *out) {
     });
 }
 
+// RoughConductor eval / pdf / sample in the D flavour with a forward-mode tangent on its eleven (constant-texture) parameters
+// [alpha_u, alpha_v, eta(3), k(3), specular_reflectance(3)] (roughconductor.cpp:40-93): values and tangents. what: 0 eval (3 + 3 floats),
+// 1 pdf (1 + 1), 2 the pdf of sample(wi, sample3) (1 + 1; 0 when the sample is invalid)
+int ref_rc_d(int what, const float *prm, const float *prm_t, const float *wi, const float *wo_or_sample, float *out, float *out_t) {
+    return guard([&] {
+        auto f1 = [&](int k) { FloatD x(prm[k]); x.g = FloatC(prm_t[k]); return Bitmap1fD(1, 1, x); };
+        auto f3 = [&](int k) { Vector3fD x; for (int c = 0; c < 3; ++c) { x[c] = FloatD(prm[k + c]); x[c].g = FloatC(prm_t[k + c]); } return Bitmap3fD(1, 1, x); };
+        RoughConductor rc(f1(0), f1(1), f3(2), f3(5), f3(8));
+        IntersectionD its;
+        its.wi = Vector3fD(wi[0], wi[1], wi[2]);
+        its.uv = Vector2fD(0.f, 0.f);
+        const Vector3fD w(wo_or_sample[0], wo_or_sample[1], wo_or_sample[2]);
+        auto put = [&](const FloatD &x, int k) { out[k] = lval(x, 0); out_t[k] = ltan(x, 0); };
+        if (what == 0) { SpectrumD v = rc.eval(its, w, MaskD(true)); for (int c = 0; c < 3; ++c) put(v[c], c); }
+        else if (what == 1) put(rc.pdf(its, w, MaskD(true)), 0);
+        else { BSDFSampleD bs = rc.sample(its, w, MaskD(true)); put(bs.pdf & bs.is_valid, 0); }
+    });
+}
+
 }  // extern "C"

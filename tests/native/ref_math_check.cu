@@ -1,7 +1,10 @@
 // CPU check (host-compiled with nvcc, no GPU): the PRODUCT's per-lane math — csrc/pb_math.cuh (warps, shading frame, ray / triangle, bilinear,
 // luminance, the psdr sampler streams) and csrc/pb_rc.cuh (GGX distribution, visible-normal sampling, Smith G1, conductor Fresnel, the
 // rough-conductor eval / pdf / sample) — against the REFERENCE'S OWN SOURCE: oracle/_ref/libref_math.so is psdr-cuda's warp.h, frame.h,
-// utils.h, ggx.cpp, roughconductor.cpp, sampler.cpp compiled unmodified (oracle/build_ref.sh). argv[1] = path of that library.
+// utils.h, ggx.cpp, roughconductor.cpp, sampler.cpp compiled unmodified (oracle/build_ref.sh). argv[1] = path of that library; with
+// argv[2] = oracle/_ref/libref_render.so also the DERIVATIVES: pb_rc.cuh's local forward-mode duals of the rough-conductor eval / pdf /
+// sampled pdf with respect to (alpha_u, alpha_v, eta, k, specular reflectance) against the tangents the reference's own roughconductor.cpp
+// produces in its D flavour (its detach() placement included) under the forward-mode stand-in for Enoki's autodiff.
 // The same functions are what the sm_100a kernels inline (the host path of pb_math.cuh uses fmaf / sqrtf where the device uses
 // __fmaf_rn / __fsqrt_rn: IEEE-identical), so this pins the kernels' arithmetic to the reference function by function, not image by image.
 #include <dlfcn.h>
@@ -145,6 +148,47 @@ int main(int argc, char **argv) {
         // and jumped ahead: the stream position a second render starts from
         Rng j(lane, make_jump(5));
         expect(j.next_1d() == r1[5] && j.next_1d() == r1[6], "sampler stream after a jump of 5", r1[5], 0.f);
+    }
+    if (argc > 2) {
+        void *hr = dlopen(argv[2], RTLD_NOW);
+        if (!hr) { std::printf("cannot load %s: %s\n", argv[2], dlerror()); return 2; }
+        auto ref_rc_d = (int (*)(int, const float *, const float *, const float *, const float *, float *, float *))dlsym(hr, "ref_rc_d");
+        if (!ref_rc_d) { std::printf("missing ref_rc_d\n"); return 2; }
+        using D1 = Dual<1>;
+        auto dual = [](float v, float t) { D1 x(v); x.d[0] = t; return x; };
+        auto dclose = [](float a, float b, float scale) { return std::fabs((double)a - b) <= 2e-3 * std::fmax(std::fabs(a), std::fabs(b)) + 1e-4 * scale; };
+        for (int it = 0; it < 2000; ++it) {
+            float prm[11] = {U(0.1f, 0.7f), U(0.1f, 0.7f), U(0.2f, 1.5f), U(0.2f, 1.5f), U(0.2f, 1.5f), U(1.5f, 4.f), U(1.5f, 4.f), U(1.5f, 4.f), U(0.3f, 1.f), U(0.3f, 1.f), U(0.3f, 1.f)};
+            float tn[11];
+            for (auto &x : tn) x = U(-1.f, 1.f);
+            float3 wi = unit3(), wo = unit3();
+            wi.z = std::fabs(wi.z) + 0.05f; wo.z = std::fabs(wo.z) + 0.05f;
+            { const float q = std::sqrt(wi.x * wi.x + wi.y * wi.y + wi.z * wi.z); wi = f3(wi.x / q, wi.y / q, wi.z / q); }
+            { const float q = std::sqrt(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z); wo = f3(wo.x / q, wo.y / q, wo.z / q); }
+            const float awi[3] = {wi.x, wi.y, wi.z}, awo[3] = {wo.x, wo.y, wo.z}, s3[3] = {U(0.05f, 0.95f), U(0.05f, 0.95f), U(0.05f, 0.95f)};
+            const D1 au = dual(prm[0], tn[0]), av = dual(prm[1], tn[1]);
+            const V3<D1> WI(D1(wi.x), D1(wi.y), D1(wi.z)), WO(D1(wo.x), D1(wo.y), D1(wo.z));
+            float rv[3], rt[3];
+            // eval = Fresnel * D G / (4 cos_i) * specular reflectance, attached to all eleven parameters
+            if (ref_rc_d(0, prm, tn, awi, awo, rv, rt) != 0) { std::printf("ref_rc_d failed\n"); return 2; }
+            const V3<D1> H = vnormalize(WO + WI);
+            const D1 sc = rc::eval_scalar<D1>(au, av, WI, WO, H);
+            for (int ch = 0; ch < 3; ++ch) {
+                const D1 mine = rc::fresnel1<D1>(dual(prm[2 + ch], tn[2 + ch]), dual(prm[5 + ch], tn[5 + ch]), vdot(WI, H)) * sc * dual(prm[8 + ch], tn[8 + ch]);
+                const float scale = std::fabs(rv[ch]) * 10.f + 1e-3f;
+                expect(close(rv[ch], mine.v, 64, 1e-9f), "D eval value", rv[ch], mine.v);
+                expect(sc.v == 0.f || dclose(rt[ch], mine.d[0], scale), "D eval tangent", rt[ch], mine.d[0]);
+            }
+            // pdf(wi, wo) and the pdf of the sampled direction, attached to the roughness
+            ref_rc_d(1, prm, tn, awi, awo, rv, rt);
+            D1 p = rc::pdf<D1>(au, av, WI, WO);
+            expect(close(rv[0], p.v, 64, 1e-9f) && dclose(rt[0], p.d[0], std::fabs(rv[0]) * 10.f + 1e-3f), "D pdf", rt[0], p.d[0]);
+            ref_rc_d(2, prm, tn, awi, s3, rv, rt);
+            const float2 disk = square_to_uniform_disk_concentric(s3[0], s3[1]);
+            p = rc::sampled_pdf<D1>(au, av, WI, disk);
+            if (rv[0] > 1e-3f && p.v > 1e-3f)
+                expect(std::fabs(rv[0] - p.v) <= 2e-3f * rv[0] && dclose(rt[0], p.d[0], std::fabs(rv[0]) * 20.f + 1e-2f), "D sampled pdf", rt[0], p.d[0]);
+        }
     }
     std::printf("ref_math_check: %s (%d comparisons, %d mismatches)\n", bad ? "FAILED" : "ok", checked, bad);
     return bad ? 1 : 0;

@@ -199,7 +199,9 @@ def test_product_device_math_matches_reference_source(tmp_path):
     exe = str(tmp_path / "ref_math_check")
     subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
                            os.path.join(ROOT, "tests", "native", "ref_math_check.cu"), "-ldl"], stderr=subprocess.DEVNULL)
-    out = subprocess.run([exe, REF], capture_output=True, text=True)
+    render = os.path.join(ROOT, "oracle", "_ref", "libref_render.so")   # adds the derivatives: the kernels' forward-mode duals of the rough conductor
+    args = [exe, REF] + ([render] if os.path.exists(render) else [])    # vs the tangents of the reference's D flavour (roughconductor.cpp with its detach() calls)
+    out = subprocess.run(args, capture_output=True, text=True)
     assert out.returncode == 0 and "ref_math_check: ok" in out.stdout, out.stdout[-3000:]
 
 
