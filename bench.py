@@ -108,7 +108,7 @@ def oracle_sample(steps, warmup, w=256, h=256, spp=16):
                 sample="cbox_bunny %dx%d/%dspp PathIntegrator(max_depth=%d): renderC + renderD with one forward-mode tangent, OpenMP over pixels, mean of %d" % (w, h, spp, DEPTH, len(times)))
 
 
-def reference_source_sample(w=48, h=48, spp=4):
+def reference_source_sample(w=128, h=128, spp=16):
     """psdr-cuda's OWN code (oracle/_ref/libref_render.so: its src/**/*.cpp compiled for the CPU against stand-ins for Enoki and OptiX,
     DESIGN.md §2) on the nearest workload it has — the snapshot has no PathIntegrator: DirectIntegrator(1,1) renderC + renderD
     with one forward-mode albedo tangent. Informational: the stand-in is a plain host-array implementation, not a tuned CPU renderer."""
