@@ -104,7 +104,9 @@ int pb_scene_mesh_get_edges(pb_ctx *ctx, int mesh, int *h_out);
 
 /* ---- hot path ------------------------------------------------------------------------------------------------- */
 /* Scene_OptiX::ray_intersect (src/scene/scene_optix.cpp:80-126, cuda/psdr_cuda.cu:9-45): n rays as 8 floats each
- * (o.xyz, tmax, d.xyz, t_occ; t_occ = 0 for a closest-hit query, > 0 to stop at any hit closer than t_occ), hits as 4 x 32 bit each (tri id, shape id, u, v); d_t (optional) receives the distance. */
+ * (o.xyz, tmax, d.xyz, t_occ; t_occ = 0 for a closest-hit query, > 0 to stop at any hit closer than t_occ), hits as 4 x 32 bit each (tri id, shape id, u, v).
+ * d_t != NULL: rays in lane order through the general kernel (any origin), d_t receives the distance. d_t == NULL: the launch the render
+ * calls use (counting sort by direction / origin cell, compaction of inactive rays, persistent streaming kernel); origins inside the scene box. */
 int pb_trace(pb_ctx *ctx, int64_t n, const float *d_rays, void *d_hits, float *d_t);
 /* Integrator::renderC (src/integrator/integrator.cpp:13-29): d_image receives W*H*3 floats, pixel = y*W + x */
 int pb_render_c(pb_ctx *ctx, const pb_integrator *integ, int sensor, float *d_image);

@@ -215,6 +215,15 @@ class Context:
         self._chk(lib().pb_trace(self.h, C.c_int64(n), _dp(rays), _dp(hits), _dp(t)))
         return hits, t
 
+    def trace_wavefront(self, rays):
+        """The render calls' own ray launch (sort by direction / origin cell, compaction, streaming traversal kernel): rays (n, 8) float32
+        CUDA tensor (o.xyz, tmax, d.xyz, t_occ) with origins inside the scene box -> hits int32 (n, 4)"""
+        import torch
+        n = rays.shape[0]
+        hits = torch.empty((n, 4), dtype=torch.int32, device=rays.device)
+        self._chk(lib().pb_trace(self.h, C.c_int64(n), _dp(rays), _dp(hits), None))
+        return hits
+
     def _image(self):
         import torch
         return torch.empty((self.height * self.width, 3), dtype=torch.float32, device="cuda:%d" % self.device)

@@ -170,9 +170,10 @@ static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hi
         c->d_sort_hist.reserve(40000 * sizeof(unsigned));
         c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
         c->d_sort_keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
+        c->d_stream_counter.reserve(sizeof(unsigned));
         launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
                             f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
-                            c->d_sort_keys.as<unsigned short>(), c->d_active_total.as<unsigned long long>(), ev0, ev1);
+                            c->d_sort_keys.as<unsigned short>(), c->d_stream_counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1);
         c->launches += 3;
     } else {
         if (ev0) cudaEventRecord(ev0, c->stream);
@@ -342,11 +343,11 @@ static void configure(pb_ctx *c) {
     c->num_tri = total;
     {
         const size_t nt = std::max<size_t>(1, total);
-        const size_t tri_b = nt * sizeof(TriRec), node_b = (2 * nt + 1) * sizeof(BvhNode), leaf_b = nt * sizeof(LeafTri);
+        const size_t tri_b = nt * sizeof(TriRec), node_b = (2 * nt + 1) * sizeof(BvhNode), leaf_b = nt * sizeof(LeafTri), nodec_b = (2 * nt + 1) * sizeof(BvhNodeC);
         if (tri_b != c->arena_tri_bytes || node_b != c->arena_node_bytes || !c->d_scene_arena.p) {   // layout changes: the old tree is gone
             c->bvh_valid = false;
-            c->d_scene_arena.reserve(tri_b + node_b + leaf_b);
-            c->arena_tri_bytes = tri_b; c->arena_node_bytes = node_b; c->arena_used = tri_b + node_b + leaf_b;
+            c->d_scene_arena.reserve(tri_b + node_b + leaf_b + nodec_b);
+            c->arena_tri_bytes = tri_b; c->arena_node_bytes = node_b; c->arena_leaf_bytes = leaf_b; c->arena_used = tri_b + node_b + leaf_b + nodec_b;
         }
     }
     bool any_topo = false;
@@ -485,6 +486,12 @@ static void configure(pb_ctx *c) {
         c->view.num_nodes = (int)dn.size();
         }
     }
+    {   // the compact copy of the tree the wavefront traversal reads (pb_trace2.cuh)
+        float extent = 0.f;
+        for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(c->scene_lo[k]), std::fabs(c->scene_hi[k])));
+        launch_nodes_to_compact(st, c->view.num_nodes, c->arena_nodes(), c->arena_nodes_c(), extent);
+        c->launches++;
+    }
     // emitters (scene.cpp:183-196, area.cpp:10-17; the envmap keeps its default weight 1, emitter.h:27)
     std::vector<EmitterRec> er(c->emitters.size());
     if (!c->emitters.empty()) {
@@ -549,7 +556,7 @@ static void configure(pb_ctx *c) {
     c->d_bsdfs.upload(br, st);
     PB_CUDA(cudaStreamSynchronize(st));
     SceneView &V = c->view;
-    V.tri = c->arena_tri(); V.leaf = c->arena_leaf(); V.nodes = c->arena_nodes(); V.nodes4 = c->d_nodes4.as<BvhNode4>();
+    V.tri = c->arena_tri(); V.leaf = c->arena_leaf(); V.nodes = c->arena_nodes(); V.nodes4 = c->d_nodes4.as<BvhNode4>(); V.nodes_c = c->arena_nodes_c();
     V.meshes = c->d_meshes.as<MeshRec>(); V.bsdfs = c->d_bsdfs.as<BsdfRec>(); V.emitters = c->d_emitters.as<EmitterRec>();
     V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
@@ -1382,7 +1389,8 @@ int pb_trace(pb_ctx *c, int64_t n, const float *d_rays, void *d_hits, float *d_t
         PB_CUDA(cudaSetDevice(c->device));
         cudaEvent_t e0 = get_event(c, 0), e1 = get_event(c, 1);
         PB_CUDA(cudaEventRecord(e0, c->stream));
-        launch_trace(c->stream, c->view, n, reinterpret_cast<const RayRec *>(d_rays), reinterpret_cast<HitRec *>(d_hits), d_t);
+        if (d_t) launch_trace(c->stream, c->view, n, reinterpret_cast<const RayRec *>(d_rays), reinterpret_cast<HitRec *>(d_hits), d_t);
+        else trace_wavefront(c, n, reinterpret_cast<const RayRec *>(d_rays), reinterpret_cast<HitRec *>(d_hits));   // what the render calls use
         PB_CUDA(cudaEventRecord(e1, c->stream));
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1476,6 +1484,8 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "l2_persist") == 0) { c->l2_persist = (int)value; set_l2_window(c); }
         else if (std::strcmp(key, "trace_sstack") == 0) pb::g_trace_sstack = (int)value;
         else if (std::strcmp(key, "trace_smem_nodes") == 0) pb::g_trace_smem_nodes = (int)value;
+        else if (std::strcmp(key, "trace_kernel") == 0) pb::g_trace_kernel = (int)value;
+        else if (std::strcmp(key, "trace_node_min") == 0) pb::g_trace_node_min = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);
     });
 }

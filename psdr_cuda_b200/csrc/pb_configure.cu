@@ -307,6 +307,40 @@ void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, in
     if (nf > 0) k_assemble_triangles<<<nblk(nf, 256), 256, 0, st>>>(nf, face_offset, mesh_id, flags, vworld, faces, fcross, vnormal, uvs, uv_faces, tri, face_area);
 }
 
+// BvhNode (padded lo / hi boxes) -> BvhNodeC (centre + half extent). Conservative: c = rn((lo + hi) / 2), h = ru(max(hi - c, c - lo))
+// + the rounding slack of the three-FFMA slab test (2^-24 (3 |o| + 2 |c|) in world units <= 4e-7 extent), then rounded up to bf16.
+__device__ __forceinline__ unsigned bf16_up(float h) {
+    const unsigned u = __float_as_uint(h);
+    return (u + 0xffffu) >> 16;   // h >= 0 and finite: next bf16 at or above
+}
+__global__ void k_nodes_to_compact(int n, const BvhNode *__restrict__ nodes, BvhNodeC *__restrict__ out, float extent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *np = reinterpret_cast<const float4 *>(nodes + i);
+    const float4 a = np[0], b = np[1], c = np[2], d = np[3];
+    const float lo[2][3] = {{a.x, a.y, a.z}, {b.z, b.w, c.x}}, hi[2][3] = {{a.w, b.x, b.y}, {c.y, c.z, c.w}};
+    float cen[2][3];
+    unsigned hb[2][3];
+    const float slack = __fmul_ru(4e-7f, extent);
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (lo[s][k] >= 3.402823466e+38f) { cen[s][k] = lo[s][k]; hb[s][k] = 0u; continue; }   // unreachable child (pb_bvh.cpp)
+            const float m = __fadd_rn(__fmul_rn(0.5f, lo[s][k]), __fmul_rn(0.5f, hi[s][k]));
+            const float h = __fadd_ru(fmaxf(__fsub_ru(hi[s][k], m), __fsub_ru(m, lo[s][k])), slack);
+            cen[s][k] = m; hb[s][k] = bf16_up(fmaxf(h, 0.f));
+        }
+    BvhNodeC o;
+    o.a = make_float4(cen[0][0], cen[0][1], cen[0][2], cen[1][0]);
+    o.b = make_float4(cen[1][1], cen[1][2], d.x, d.y);
+    o.c = make_float4(__uint_as_float((hb[0][0] << 16) | hb[1][0]), __uint_as_float((hb[0][1] << 16) | hb[1][1]), __uint_as_float((hb[0][2] << 16) | hb[1][2]), 0.f);
+    out[i] = o;
+}
+void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent) {
+    if (num_nodes > 0) k_nodes_to_compact<<<nblk(num_nodes, 256), 256, 0, st>>>(num_nodes, nodes, out, extent);
+}
+
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf) {
     if (n > 0) k_build_leaf_tris<<<nblk(n, 256), 256, 0, st>>>(n, order, tri, leaf);
 }

@@ -138,17 +138,18 @@ struct pb_ctx {
     // triangle table | BVH nodes | leaf triangles live in ONE allocation so that a single L2 access-policy window can keep the
     // randomly gathered scene data resident while the wavefront streams through (pb_capi.cu: set_l2_window)
     pb::DevBuf d_scene_arena;
-    size_t arena_tri_bytes = 0, arena_node_bytes = 0, arena_used = 0;
+    size_t arena_tri_bytes = 0, arena_node_bytes = 0, arena_leaf_bytes = 0, arena_used = 0;
     pb::TriRec *arena_tri() const { return d_scene_arena.as<pb::TriRec>(); }
     pb::BvhNode *arena_nodes() const { return reinterpret_cast<pb::BvhNode *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes); }
     pb::LeafTri *arena_leaf() const { return reinterpret_cast<pb::LeafTri *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes + arena_node_bytes); }
+    pb::BvhNodeC *arena_nodes_c() const { return reinterpret_cast<pb::BvhNodeC *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes + arena_node_bytes + arena_leaf_bytes); }
     int l2_persist = 1;
     pb::DevBuf d_nodes4, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
     std::vector<float> h_tri;   // host copy of the triangle table (BVH build, inspection)
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers
-    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_active_total, d_emitters_grad, d_sensor_acc, d_env_xf_acc, d_meshes_grad;
+    pb::DevBuf d_suffix, d_bsdfs_grad, d_tri_grad, d_tri_tangent, d_jvp_acc, d_sort_hist, d_sort_perm, d_sort_keys, d_stream_counter, d_active_total, d_emitters_grad, d_sensor_acc, d_env_xf_acc, d_meshes_grad;
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {1, 1, 1};
     float env_lower[3] = {0, 0, 0}, env_upper[3] = {1, 1, 1};
     // boundary terms

@@ -54,6 +54,7 @@ void launch_mesh_tangent(cudaStream_t st, int nv, int nf, int face_offset, const
                          const int *faces, const int *csr_off, const int *csr_face, const float4 *fcross, float *vworld_t, float4 *fcross_t, float *vnormal_t,
                          float *tri_tangent);
 void launch_bvh_refit(cudaStream_t st, BvhNode *nodes, float *boxes, const LeafTri *leaf, const int *level_off, int num_levels, float extent);
+void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_trace_blocks_per_sm;
@@ -64,10 +65,12 @@ extern int g_shade_simple;   // debug: 0 = never use the diffuse + area-light in
 extern int g_shade_tune;   // debug: k_resolve / k_adjoint variant (0 default)
 extern int g_trace_smem;
 extern int g_trace_smem_nodes;
+extern int g_trace_kernel;    // sorted-wavefront traversal kernel: 0 first generation (k_trace_perm), 1 compact nodes, 2 compact + postponed leaf, 3 persistent streaming
+extern int g_trace_node_min;  // streaming kernel: node steps continue while at least this many lanes descend
 extern int g_trace_variant;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys, unsigned long long *active_total = nullptr, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total = nullptr, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);

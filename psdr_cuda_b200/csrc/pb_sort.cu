@@ -10,10 +10,13 @@
 
 #include "pb_kernels.h"
 #include "pb_trace.cuh"
+#include "pb_trace2.cuh"
 
 namespace pb {
 
 int g_sort_mode = 0;
+int g_trace_kernel = 3;     // 0 first generation (k_trace_perm), 1 compact nodes, 2 compact nodes + postponed leaf, 3 persistent streaming kernel
+int g_trace_node_min = 16;  // streaming kernel: node steps continue while at least this many lanes descend
 int g_trace_sstack = 0;   // > 0: that many stack levels in shared memory
 int g_trace_ld256 = 1;   // 256-bit node / leaf loads in the sorted-wavefront traversal kernel
 int g_trace_smem_nodes = 512;
@@ -165,11 +168,24 @@ __global__ void __launch_bounds__(1024, 1) k_trace_perm_smem(const BvhNode *__re
     }
 }
 
+// one ray per thread over the compact nodes (pb_trace2.cuh)
+template <bool SPEC, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_trace_compact(const BvhNodeC *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
+                                                             const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= __ldg(n_active)) return;
+    const unsigned i = __ldcs(perm + j);
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
+    const Hit h = trace_closest_c<SPEC>(nodes, leaf, f3(a), f3(b), a.w, b.w);
+    __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
+}
+
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 // hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned; keys: n unsigned short
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1) {
+                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (n <= 0) return;
     static int mode_set = -1;
     if (mode_set != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); mode_set = g_sort_mode; }
@@ -186,8 +202,37 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
     k_sort_scan<<<1, 1024, 0, st>>>(hist, active_total);
     k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
+    if (g_trace_kernel == 3) cudaMemsetAsync(stream_counter, 0, sizeof(unsigned), st);
     if (ev0) cudaEventRecord(ev0, st);   // the pair brackets the traversal kernel alone (roofline: 48 B per traced ray / this duration)
-    if (g_trace_smem) {
+    if (g_trace_kernel == 3) {
+        StreamArgs A;
+        A.nodes = S.nodes_c; A.leaf = S.leaf; A.n_active = hist + kSortBins + 1; A.perm = perm; A.rays = rays; A.hits = hits; A.counter = stream_counter;
+        const unsigned grid = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 8);
+        const unsigned grid10 = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 10), grid12 = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 12);
+        switch (g_trace_node_min) {
+            case 201: k_trace_stream<16, 8, 8, 1><<<grid, 128, 0, st>>>(A); break;   // prefetch the postponed child
+            case 202: k_trace_stream<16, 8, 8, 2><<<grid, 128, 0, st>>>(A); break;   // prefetch the leaf triangle when a leaf is reached
+            case 203: k_trace_stream<16, 8, 8, 3><<<grid, 128, 0, st>>>(A); break;   // both
+            case 210: k_trace_stream<16, 8, 10><<<grid10, 128, 0, st>>>(A); break;   // 10 blocks / SM (51 registers)
+            case 212: k_trace_stream<16, 8, 12><<<grid12, 128, 0, st>>>(A); break;   // 12 blocks / SM (42 registers)
+            case 213: k_trace_stream<16, 8, 12, 3><<<grid12, 128, 0, st>>>(A); break;
+            case 304: k_trace_stream<16, 4, 8><<<grid, 128, 0, st>>>(A); break;
+            case 312: k_trace_stream<16, 12, 8><<<grid, 128, 0, st>>>(A); break;
+            case 14: k_trace_stream<14, 8, 8><<<grid, 128, 0, st>>>(A); break;
+            case 18: k_trace_stream<18, 8, 8><<<grid, 128, 0, st>>>(A); break;
+            case 8: k_trace_stream<8, 8, 8><<<grid, 128, 0, st>>>(A); break;
+            case 12: k_trace_stream<12, 8, 8><<<grid, 128, 0, st>>>(A); break;
+            case 16: k_trace_stream<16, 8, 8><<<grid, 128, 0, st>>>(A); break;
+            case 20: k_trace_stream<20, 8, 8><<<grid, 128, 0, st>>>(A); break;
+            case 101: k_trace_stream<1, 1, 8><<<grid, 128, 0, st>>>(A); break;     // refill as soon as one lane is idle
+            case 116: k_trace_stream<16, 16, 8><<<grid, 128, 0, st>>>(A); break;   // refill only when half the warp is idle
+            default: k_trace_stream<1, 8, 8><<<grid, 128, 0, st>>>(A); break;
+        }
+    } else if (g_trace_kernel == 1) {
+        k_trace_compact<false, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes_c, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+    } else if (g_trace_kernel == 2) {
+        k_trace_compact<true, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes_c, S.leaf, hist + kSortBins + 1, perm, rays, hits);
+    } else if (g_trace_smem) {
         static bool attr_set = false;
         const int cap = std::min(kTopNodes, std::max(32, g_trace_smem_nodes));
         const int smem = cap * 64;

@@ -108,6 +108,29 @@ def test_trace_bit_exact_vs_golden_and_oracle(desc, golden):
     hg = hg.cpu().numpy()
     assert np.array_equal(hg[:, 0], tri) and np.array_equal(hg[:, 1], shape)
     assert np.array_equal(hg[:, 2].view(np.uint32), u.view(np.uint32)) and np.array_equal(tg.cpu().numpy().view(np.uint32), t.view(np.uint32))
+    # the render calls' own launch (sorted + compacted wavefront, streaming kernel over the compact nodes), every traversal kernel variant
+    rw = r.copy(); rw[1::7, 3] = -1.0                   # some inactive lanes
+    occ = np.zeros(m, bool); occ[2::5] = True; occ[1::7] = False
+    t_occ = np.where(np.isfinite(t), t, 100.0) * rng.uniform(0.5, 1.5, m).astype(np.float32)
+    rw[occ, 3] = (t_occ[occ] * 1.25 + 1.0).astype(np.float32)       # bounded occlusion queries, as k_shade emits them
+    rw[occ, 7] = t_occ[occ]
+    active = rw[:, 3] > 0
+    for kern in (3, 2, 1, 0):
+        ctx.debug_set("trace_kernel", kern)
+        for node_min in ((1, 12, 101, 116) if kern == 3 else (1,)):
+            ctx.debug_set("trace_node_min", node_min)
+            hw = ctx.trace_wavefront(torch.from_numpy(rw).cuda()).cpu().numpy()
+            assert np.all(hw[~active, 0] == -1), (kern, node_min)
+            in_reach = np.isfinite(t) & (t < rw[:, 3])           # the closest hit lies inside (0, tmax)
+            decided = occ & in_reach & (t <= rw[:, 7])           # occluded: any hit closer than t_occ may be reported
+            exact = active & ~decided
+            want_tri = np.where(in_reach, tri, -1)
+            assert np.array_equal(hw[exact, 0], want_tri[exact]), (kern, node_min, int((hw[exact, 0] != want_tri[exact]).sum()))
+            hit = exact & in_reach
+            assert np.array_equal(hw[hit, 1], shape[hit])
+            assert np.array_equal(hw[hit, 2].view(np.uint32), u[hit].view(np.uint32)) and np.array_equal(hw[hit, 3].view(np.uint32), v[hit].view(np.uint32))
+            assert np.all(hw[decided, 0] >= 0), (kern, node_min)
+    ctx.debug_set("trace_kernel", 3); ctx.debug_set("trace_node_min", 1)
 
 
 @pytest.mark.parametrize("name,kind,kw", [("direct11", "direct", dict(bsdf_samples=1, light_samples=1)), ("direct21", "direct", dict(bsdf_samples=2, light_samples=1)),
@@ -179,6 +202,54 @@ def test_renderD_and_albedo_vjp_vs_oracle(desc, golden):
     # replaying the VJP gives the same gradient (up to fp32 atomics order); it accumulates into the buffer
     g2 = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda(), grad=torch.from_numpy(g.copy()).cuda()).cpu().numpy()
     assert np.allclose(g2, 2 * g, rtol=1e-4, atol=1e-5)
+
+
+def test_headline_config_path5_vs_oracle(desc):
+    # the benchmarked integrator (BASELINE.json configs[1]: PathIntegrator, max_depth 5, diffuse-albedo gradients) against the oracle:
+    # renderC, renderD and the full 12-entry albedo gradient, 96x96 / 8 spp
+    from oracle import orc
+    from psdr_cuda_b200 import capi
+    opts = dict(width=96, height=96, spp=8, sppe=0, sppse=0)
+    ctx = make_ctx(desc, opts, grads=True)
+    integ = capi.make_integrator("path", max_depth=5)
+    odesc = orc.load_scene_description(scene_path("cbox_bunny"))
+    osc = orc.Scene(odesc, opts); osc.configure()
+    oi = orc.PathIntegrator(5)
+    assert_image_parity(ctx.render_c(integ).cpu().numpy(), oi.renderC(osc))
+    img_d = ctx.render_d(integ).cpu().numpy()          # second render: the streams continue
+    rng = np.random.default_rng(77)
+    dLdI = rng.uniform(-1, 1, size=img_d.shape).astype(np.float32)
+    g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().astype(np.float64)
+    ref = np.zeros(12)
+    for b in range(4):
+        for ch in range(3):
+            o2 = orc.Scene(odesc, opts)
+            t = np.zeros((1, 1, 3), np.float32); t[0, 0, ch] = 1
+            o2.set_bsdf_tangent(b, "reflectance", t)
+            o2.configure()
+            oi.renderC(o2)                               # same stream position as the product's renderD
+            ref_d, dimg = oi.renderD(o2)
+            ref[3 * b + ch] = float((dLdI.astype(np.float64) * dimg).sum())
+    assert_image_parity(img_d, ref_d)
+    assert np.linalg.norm(g - ref) <= 1e-3 * np.linalg.norm(ref), (g, ref)
+    assert np.all(np.abs(g - ref) <= 1e-3 * np.abs(ref).max()), (g, ref)
+
+
+def test_path1_equals_direct11_on_the_cuda_path(desc):
+    # the only pin the reference gives the PathIntegrator: depth 1 reproduces DirectIntegrator(1, 1) (direct.cpp:47-163)
+    from psdr_cuda_b200 import capi
+    opts = dict(width=64, height=64, spp=4, sppe=0, sppse=0)
+    dLdI = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, size=(64 * 64, 3)).astype(np.float32)).cuda()
+    out = {}
+    for name, integ in (("path", capi.make_integrator("path", max_depth=1)), ("direct", capi.make_integrator("direct", bsdf_samples=1, light_samples=1))):
+        ctx = make_ctx(desc, opts, grads=True)
+        c = ctx.render_c(integ).cpu().numpy()
+        d = ctx.render_d(integ).cpu().numpy()
+        g = ctx.render_d_vjp(integ, dLdI).cpu().numpy()
+        out[name] = (c, d, g)
+    assert np.abs(out["path"][0] - out["direct"][0]).max() <= 1e-6
+    assert np.abs(out["path"][1] - out["direct"][1]).max() <= 1e-6
+    assert np.allclose(out["path"][2], out["direct"][2], rtol=1e-5, atol=1e-6)
 
 
 def test_bitmap_texture_gradient_matches_oracle():
