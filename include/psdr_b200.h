@@ -59,6 +59,12 @@ int pb_ctx_set_batch(pb_ctx *ctx, int64_t lanes);
  * (lane ranges for the edge terms). RNG streams stay indexed by the global lane id, so the sum of the shards' images
  * equals the single-GPU image up to fp32 summation order. Default (0, 1). */
 int pb_ctx_set_shard(pb_ctx *ctx, int rank, int world);
+/* How the interior term is split over ranks. PB_SHARD_SAMPLES (default): every rank renders spp / world samples of every pixel (perfect
+ * load balance; the films are partial sums). PB_SHARD_PIXELS: rank r renders every sample of the image-row tiles t * world + r of
+ * `tile_rows` rows (0 = height / world: one contiguous block per rank; 1 = interleaved rows); the films are disjoint and their union is
+ * bit-identical to the single-GPU image. The boundary terms are always split by lane range (integrator.cpp:98-119). */
+enum { PB_SHARD_SAMPLES = 0, PB_SHARD_PIXELS = 1 };
+int pb_ctx_set_shard_mode(pb_ctx *ctx, int mode, int tile_rows);
 /* pb_render_d keeps every event's hit records / vertex positions / throughputs of the whole shard (352 B per lane for a
  * depth-5 path) when they fit in `bytes` (default 64 GiB of the 180 GB HBM3e), so that pb_render_d_vjp runs only the
  * adjoint kernels; otherwise the VJP re-traces the forward pass batch by batch. 0 disables retention. */
@@ -115,6 +121,13 @@ int pb_render_c_host(pb_ctx *ctx, const pb_integrator *integ, int sensor, float 
 /* Integrator::renderD primal (src/integrator/integrator.cpp:32-60): the AD formulation's image; remembers the sampler
  * positions so that pb_render_d_vjp replays the same paths */
 int pb_render_d(pb_ctx *ctx, const pb_integrator *integ, int sensor, float *d_image);
+/* The reference's tape lets a loss depend on several renderD images (one per sensor, src/integrator/integrator.cpp:32-60 called in a
+ * loop) before one ek.backward. pb_render_d_vjp / _jvp replay "the last pb_render_d"; these two calls make any earlier one the last
+ * again: get_state after a pb_render_d returns {interior, primary-edge, secondary-edge sampler positions, serial number}; set_state
+ * before the VJP of that image restores them (records retained for a later render are dropped: that VJP re-traces its paths).
+ * A state is valid until the next pb_scene_configure. */
+int pb_render_d_get_state(pb_ctx *ctx, uint64_t state[4]);
+int pb_render_d_set_state(pb_ctx *ctx, const uint64_t state[4]);
 
 /* DirectIntegrator::preprocess_secondary_edges (src/integrator/direct.cpp:166-204, src/psdr.cpp:285): builds the guiding grid
  * resolution[0..2] cells x resolution[3] samples per cell x nrounds over the secondary-edge sample space of `sensor` */
@@ -132,6 +145,21 @@ int64_t pb_grad_size(pb_ctx *ctx);
  * both exist only in the derivative, so they are evaluated here and not in pb_render_d.
  * On several GPUs each rank holds a private d_grad and the caller all-reduces it once. */
 int pb_render_d_vjp(pb_ctx *ctx, const pb_integrator *integ, int sensor, const float *d_dLdI, float *d_grad);
+
+/* ---- several GPUs (BASELINE.json north_star; the reference is single-GPU): one process and one context per GPU, NCCL resolved at run time.
+ * pb_dist_unique_id on rank 0, the 128 bytes handed to every rank (any transport), pb_dist_init everywhere (also sets the shard);
+ * or pb_dist_adopt_comm with an existing ncclComm_t. pb_allreduce_grads enqueues ONE ncclAllReduce(sum) of the flat gradient vector on
+ * the context's stream, i.e. right behind the last adjoint kernel of pb_render_d_vjp — the single exchange step of renderD
+ * (replaces nothing in the reference). pb_allreduce_image completes a film after pb_render_c / pb_render_d: an in-place
+ * all-gather for equal contiguous pixel tiles, a sum otherwise. Both are no-ops on one GPU. */
+int pb_dist_available(void);
+int pb_dist_unique_id(pb_ctx *ctx, char id128[128]);
+int pb_dist_init(pb_ctx *ctx, const char id128[128], int rank, int world);
+int pb_dist_adopt_comm(pb_ctx *ctx, void *nccl_comm, int rank, int world);
+int pb_dist_finalize(pb_ctx *ctx);
+int pb_allreduce_grads(pb_ctx *ctx, float *d_grad, int64_t count);
+int pb_allreduce_image(pb_ctx *ctx, float *d_image);
+int64_t pb_stats_collectives(pb_ctx *ctx);
 
 /* forward mode (ek.forward + ek.gradient(image) in the reference, examples/run_test.py:126-129): d_tangent is a flat vector with the
  * layout of the gradient vector (the direction in parameter space), d_dimage receives the W*H*3 derivative image. Needs a

@@ -26,7 +26,8 @@ SYMBOLS = [
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
-    "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad",
+    "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad", "pb_render_d_get_state", "pb_render_d_set_state",
+    "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
 ]
 
 
@@ -46,6 +47,7 @@ def lib():
         L.pb_last_error.argtypes = [C.c_void_p]
         L.pb_grad_size.restype = C.c_int64
         L.pb_stats_launches.restype = C.c_int64
+        L.pb_stats_collectives.restype = C.c_int64
         L.pb_stats_last_rays.restype = C.c_int64
         L.pb_stats_last_active_rays.restype = C.c_int64
         L.pb_stats_last_trace_ms.restype = C.c_float
@@ -86,6 +88,8 @@ class Context:
         self.h = h
         self.device = int(device)
         self.width = self.height = 0
+        self._stream = None     # None: the context's own stream (never ordered against torch's: see _bind_stream)
+        self._stream_pinned = False
 
     def close(self):
         if self.h is not None:
@@ -119,11 +123,62 @@ class Context:
         self._chk(lib().pb_ctx_set_retain_limit(self.h, C.c_int64(nbytes)))
 
     def set_stream(self, cuda_stream):
-        """run on the caller's stream (int handle, e.g. torch.cuda.current_stream().cuda_stream; 0 = legacy default)"""
+        """run on the caller's stream (int handle, e.g. torch.cuda.current_stream().cuda_stream; 0 = legacy default) from now on"""
         self._chk(lib().pb_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+        self._stream, self._stream_pinned = int(cuda_stream), True
+
+    def _bind_stream(self):
+        """Every call that touches caller buffers (images, dL/dI, gradient vectors are torch tensors produced on torch's current
+        stream) runs on that stream, so the library's kernels are ordered against their producers and consumers. Without this the
+        context's private non-blocking stream would race with e.g. the zero-fill of a fresh gradient tensor."""
+        if self._stream_pinned:
+            return
+        import torch
+        cur = int(torch.cuda.current_stream(self.device).cuda_stream)
+        if cur != self._stream:
+            self._chk(lib().pb_ctx_set_stream(self.h, C.c_void_p(cur)))
+            self._stream = cur
 
     def set_shard(self, rank, world):
         self._chk(lib().pb_ctx_set_shard(self.h, rank, world))
+
+    def set_shard_mode(self, mode, tile_rows=0):
+        """"samples" (every rank renders spp / world samples of every pixel) or "pixels" (image-row tiles of tile_rows rows, 0 = one block per rank)"""
+        self._chk(lib().pb_ctx_set_shard_mode(self.h, {"samples": 0, "pixels": 1}.get(mode, mode), int(tile_rows)))
+
+    # --- several GPUs: NCCL communicator owned by the library, collectives enqueued on the context's stream ----------------
+    def dist_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._chk(lib().pb_dist_unique_id(self.h, buf))
+        return buf.raw
+
+    def dist_init(self, unique_id, rank, world):
+        self._chk(lib().pb_dist_init(self.h, C.c_char_p(bytes(unique_id)), int(rank), int(world)))
+
+    def dist_init_from_torch(self, group=None):
+        """create the library's communicator for the ranks of an initialised torch.distributed group (the id travels through the group)"""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = "cuda:%d" % self.device if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.dist_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.dist_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def dist_finalize(self):
+        self._chk(lib().pb_dist_finalize(self.h))
+
+    def allreduce_grads(self, grad):
+        self._bind_stream()
+        self._chk(lib().pb_allreduce_grads(self.h, _dp(grad), C.c_int64(grad.numel())))
+        return grad
+
+    def allreduce_image(self, img):
+        self._bind_stream()
+        self._chk(lib().pb_allreduce_image(self.h, _dp(img)))
+        return img
 
     def add_sensor(self, fov, near, far, to_world):
         return self._id(lib().pb_scene_add_sensor(self.h, C.c_float(fov), C.c_float(near), C.c_float(far), _p(_f(to_world))))
@@ -166,6 +221,7 @@ class Context:
         self._chk(lib().pb_scene_set_envmap_transform(self.h, _p(_f(left))))
 
     def configure(self, reseed=False):
+        self._bind_stream()
         if reseed:
             lib().pb_scene_reseed(self.h)
         self._chk(lib().pb_scene_configure(self.h))
@@ -208,6 +264,7 @@ class Context:
     # --- hot path ------------------------------------------------------------------------------------------------
     def trace(self, rays):
         """rays: (n, 8) float32 CUDA tensor (o.xyz, tmax, d.xyz, 0) -> (hits int32 (n,4) view pair, t)"""
+        self._bind_stream()
         import torch
         n = rays.shape[0]
         hits = torch.empty((n, 4), dtype=torch.int32, device=rays.device)
@@ -218,6 +275,7 @@ class Context:
     def trace_wavefront(self, rays):
         """The render calls' own ray launch (sort by direction / origin cell, compaction, streaming traversal kernel): rays (n, 8) float32
         CUDA tensor (o.xyz, tmax, d.xyz, t_occ) with origins inside the scene box -> hits int32 (n, 4)"""
+        self._bind_stream()
         import torch
         n = rays.shape[0]
         hits = torch.empty((n, 4), dtype=torch.int32, device=rays.device)
@@ -229,6 +287,7 @@ class Context:
         return torch.empty((self.height * self.width, 3), dtype=torch.float32, device="cuda:%d" % self.device)
 
     def render_c(self, integ, sensor=0, out=None):
+        self._bind_stream()
         img = out if out is not None else self._image()
         self._chk(lib().pb_render_c(self.h, C.byref(integ), sensor, _dp(img)))
         return img
@@ -239,11 +298,13 @@ class Context:
         return img
 
     def render_d(self, integ, sensor=0, out=None):
+        self._bind_stream()
         img = out if out is not None else self._image()
         self._chk(lib().pb_render_d(self.h, C.byref(integ), sensor, _dp(img)))
         return img
 
     def preprocess_secondary_edges(self, sensor, resolution, nrounds=1):
+        self._bind_stream()
         r = _i(resolution)
         assert r.shape == (4,)
         self._chk(lib().pb_preprocess_secondary_edges(self.h, sensor, _p(r), nrounds))
@@ -265,8 +326,22 @@ class Context:
     def grad_size(self):
         return int(lib().pb_grad_size(self.h))
 
-    def render_d_vjp(self, integ, dLdI, sensor=0, grad=None):
+    def render_d_state(self):
+        """replay state of the last render_d (sampler positions + serial number): pass it to render_d_vjp / render_d_jvp to
+        differentiate that image after later renders (several sensors before one backward)"""
+        st = (C.c_uint64 * 4)()
+        self._chk(lib().pb_render_d_get_state(self.h, st))
+        return tuple(int(x) for x in st)
+
+    def _restore_state(self, state):
+        if state is not None:
+            st = (C.c_uint64 * 4)(*state)
+            self._chk(lib().pb_render_d_set_state(self.h, st))
+
+    def render_d_vjp(self, integ, dLdI, sensor=0, grad=None, state=None):
         import torch
+        self._bind_stream()
+        self._restore_state(state)
         if grad is None:
             grad = torch.zeros(max(1, self.grad_size()), dtype=torch.float32, device=dLdI.device)
         self._chk(lib().pb_render_d_vjp(self.h, C.byref(integ), sensor, _dp(dLdI.contiguous()), _dp(grad)))
@@ -280,8 +355,10 @@ class Context:
         self._chk(lib().pb_debug_ray_buffer(self.h, event, C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
 
-    def render_d_jvp(self, integ, tangent, sensor=0, out=None):
+    def render_d_jvp(self, integ, tangent, sensor=0, out=None, state=None):
         """forward mode: tangent is a flat CUDA tensor laid out like the gradient vector -> derivative image (W*H, 3)"""
+        self._bind_stream()
+        self._restore_state(state)
         img = out if out is not None else self._image()
         self._chk(lib().pb_render_d_jvp(self.h, C.byref(integ), sensor, _dp(tangent.contiguous()), _dp(img)))
         return img
@@ -297,5 +374,5 @@ class Context:
     # --- stats -------------------------------------------------------------------------------------------------
     def stats(self):
         L = lib()
-        return dict(launches=int(L.pb_stats_launches(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)), active_rays=int(L.pb_stats_last_active_rays(self.h)),
+        return dict(launches=int(L.pb_stats_launches(self.h)), collectives=int(L.pb_stats_collectives(self.h)), trace_ms=float(L.pb_stats_last_trace_ms(self.h)), rays=int(L.pb_stats_last_rays(self.h)), active_rays=int(L.pb_stats_last_active_rays(self.h)),
                     trace_launches=int(L.pb_stats_last_trace_launches(self.h)), primary_ms=float(L.pb_stats_last_primary_ms(self.h)))

@@ -114,6 +114,59 @@ def _enoki():
     return m if m is not None and getattr(m, "__psdr_b200_shim__", False) else None
 
 
+_TEXTURE_FIELDS = ("reflectance", "alpha_u", "alpha_v", "eta", "k", "specular_reflectance")
+
+
+def _canonical_key(obj):
+    """the param_map key the gradient layout uses for this object ("BSDF[i]" / "Mesh[i]"); other objects keep their type name"""
+    t = obj.type_name()
+    if t == "Mesh":
+        return "Mesh[%d]" % obj.index
+    if t in ("Diffuse", "RoughConductor"):
+        return "BSDF[%d]" % obj.index
+    return t
+
+
+class _BitmapProxy:
+    """a texture of a param_map entry (src/psdr.cpp:100-118): `.data` reads / accepts arrays of the Enoki stand-in, so that
+    `ek.set_requires_gradient(bsdf.reflectance.data)` and `bsdf.reflectance.data = u` (examples/utils/adam.py:26-49) reach the scene"""
+
+    def __init__(self, scene, key, field, bitmap):
+        object.__setattr__(self, "_scene", scene)
+        object.__setattr__(self, "_key", key)
+        object.__setattr__(self, "_field", field)
+        object.__setattr__(self, "_bm", bitmap)
+
+    def __getattr__(self, name):
+        bm = object.__getattribute__(self, "_bm")
+        if name == "data" and _enoki() is not None:
+            return self._scene._ek_array(self._key, self._field, lambda: self._to_ek(np.asarray(bm.data)))
+        return getattr(bm, name)
+
+    def _to_ek(self, a):
+        ek = _enoki()
+        return ek.Vector3f(a.reshape(-1, 3)) if self._bm.channels == 3 else ek.Float32(a.reshape(-1))
+
+    def __setattr__(self, name, value):
+        bm, scene = self._bm, self._scene
+        if name == "data" and hasattr(value, "_tracked"):
+            a = value.numpy()
+            n = max(1, bm.resolution[0] * bm.resolution[1])
+            a = np.broadcast_to(a.reshape(-1, bm.channels) if bm.channels == 3 else a.reshape(-1, 1), (n, bm.channels))
+            bm.data = np.ascontiguousarray(a if bm.channels == 3 else a.reshape(-1), dtype=np.float32)
+            scene._ek_inputs[(self._key, self._field)] = value
+            t = value.tangent_numpy() if hasattr(value, "tangent_numpy") else (None if value.d is None else value.d)
+            has_t = value.has_tangent() if hasattr(value, "has_tangent") else value.d is not None
+            scene._fwd_texture[(self._key, self._field)] = np.broadcast_to(np.asarray(t, np.float32).reshape(-1, bm.channels), (n, bm.channels)).reshape(-1).copy() if has_t else None
+            if has_t or value._tracked():
+                bm.requires_grad = True
+            return
+        setattr(bm, name, value)
+
+    def __repr__(self):
+        return repr(self._bm)
+
+
 class _Proxy:
     """param_map entry: forwards to the C++ object and accepts the Enoki stand-in's arrays (value + tangent) where the
     reference accepts Enoki autodiff arrays (src/psdr.cpp:242-265)"""
@@ -125,8 +178,11 @@ class _Proxy:
 
     def __getattr__(self, name):
         obj = object.__getattribute__(self, "_obj")
-        if name == "vertex_positions" and _enoki() is not None:
-            return _enoki().Vector3f(obj.vertex_positions)
+        if name == "vertex_positions" and _enoki() is not None:   # one array object per mesh, so that set_requires_gradient on it sticks
+            scene = object.__getattribute__(self, "_scene")
+            return scene._ek_array(_canonical_key(obj), "vertex_positions", lambda: _enoki().Vector3f(obj.vertex_positions))
+        if name in _TEXTURE_FIELDS and obj.type_name() in ("Diffuse", "RoughConductor") and hasattr(obj, name):
+            return _BitmapProxy(object.__getattribute__(self, "_scene"), _canonical_key(obj), name, getattr(obj, name))
         if name == "bsdf" and obj.type_name() == "Mesh":      # Mesh::m_bsdf (src/psdr.cpp:251)
             scene = object.__getattribute__(self, "_scene")
             return scene._raw_param_map().get("BSDF[%d]" % obj.bsdf_index) if obj.bsdf_index >= 0 else None
@@ -137,7 +193,8 @@ class _Proxy:
         if name == "vertex_positions" and hasattr(value, "tangent_numpy"):
             obj.vertex_positions = value.numpy()
             scene._fwd_vertex[obj_index(obj)] = value.tangent_numpy() if value.has_tangent() else None
-            if value.has_tangent():
+            scene._ek_inputs[(_canonical_key(obj), "vertex_positions")] = value
+            if value.has_tangent() or value._tracked():
                 obj.requires_grad = True
             return
         setattr(obj, name, value)
@@ -145,11 +202,18 @@ class _Proxy:
     def set_transform(self, mat, set_left=True):
         obj, scene = self._obj, self._scene
         if hasattr(mat, "v") and hasattr(mat, "d"):          # Matrix4f of the Enoki stand-in
-            obj.set_transform(mat.v, set_left)
+            if obj.type_name() == "Mesh":
+                obj.set_transform(mat.v, set_left)
+            else:
+                obj.set_transform(mat.v)
             if obj.type_name() == "Mesh":
                 scene._fwd_transform[(obj_index(obj), bool(set_left))] = mat.d
                 if mat.d is not None:
                     obj.requires_grad = True
+            elif isinstance(obj, EnvironmentMap):        # examples/utils/differential.py envmap_rotate
+                scene._fwd_envmap = None if mat.d is None else np.asarray(mat.d, np.float32).reshape(16).copy()
+                if mat.d is not None:
+                    obj.transform_requires_grad = True
             elif mat.d is not None:
                 raise RuntimeError("derivatives w.r.t. this object's transform are not implemented yet")
         else:
@@ -183,6 +247,9 @@ class Scene(_h.Scene):
         self._params = {}   # (key, field) -> torch leaf
         self._fwd_vertex = {}      # mesh index -> (nv, 3) object-space vertex tangent (Enoki stand-in, forward mode)
         self._fwd_transform = {}   # (mesh index, left?) -> 4x4 tangent of the transform
+        self._fwd_texture = {}     # (BSDF key, field) -> flat texel tangent
+        self._fwd_envmap = None    # 16 floats: tangent of the matrix EnvironmentMap.set_transform sets
+        self._ek_inputs = {}       # (canonical key, field) -> array of the Enoki stand-in stored in / read from the scene
 
     @property
     def param_map(self):
@@ -191,6 +258,24 @@ class Scene(_h.Scene):
 
     def _raw_param_map(self):
         return _h.Scene.param_map.fget(self)
+
+    def _ek_array(self, key, field, make):
+        """the one array object of the Enoki stand-in that stands for `param_map[key].<field>`"""
+        arr = self._ek_inputs.get((key, field))
+        if arr is None:
+            arr = self._ek_inputs[(key, field)] = make()
+        return arr
+
+    def _push_ek_flags(self):
+        """arrays marked by ek.set_requires_gradient after they were read from the scene (docs/inverse_diff_render.rst:66) -> requires_grad"""
+        raw = self._raw_param_map()
+        for (key, field), arr in self._ek_inputs.items():
+            if not arr._tracked() or key not in raw:
+                continue
+            if field == "vertex_positions":
+                raw[key].requires_grad = True
+            else:
+                getattr(raw[key], field).requires_grad = True
 
     def _forward_tangent(self):
         """flat tangent vector (layout of the gradient vector) from what the Enoki stand-in stored on the scene: explicit vertex
@@ -215,6 +300,12 @@ class Scene(_h.Scene):
                 dworld = (x @ dM.T)[:, :3]
                 u += np.linalg.solve(M[:3, :3], dworld.T).T
             flat[off:off + cnt] = u.reshape(-1).astype(np.float32)
+        for key, field, off, cnt in self.grad_layout():      # texture tangents (examples/utils/differential.py material_roughness)
+            t = self._fwd_texture.get((key, field))
+            if t is not None and t.size == cnt:
+                flat[off:off + cnt] = t
+            if field == "to_world_left" and key.startswith("Emitter") and self._fwd_envmap is not None and cnt == 16:
+                flat[off:off + cnt] = self._fwd_envmap
         return torch.from_numpy(flat).to("cuda:%d" % self._device)
 
     def parameter(self, key, field, requires_grad=True):
@@ -262,14 +353,37 @@ class Scene(_h.Scene):
                 bm = getattr(obj, field)
                 bm.data = val
                 bm.requires_grad = bool(t.requires_grad)
-        if self._params or True:
-            try:
-                import torch
-                if torch.cuda.is_available():
-                    self.set_stream(torch.cuda.current_stream(self._device).cuda_stream)
-            except ImportError:
-                pass
+        if _enoki() is not None:
+            self._push_ek_flags()
+        self._bind_stream()
         super().configure()
+
+    def _bind_stream(self):
+        """run on torch's current stream: images, dL/dI and gradient vectors are torch tensors produced / consumed on it"""
+        try:
+            import torch
+            if torch.cuda.is_available() and self._device >= 0:
+                cur = int(torch.cuda.current_stream(self._device).cuda_stream)
+                if getattr(self, "_stream", None) != cur:
+                    self.set_stream(cur)
+                    self._stream = cur
+        except ImportError:
+            pass
+
+    def init_distributed(self, group=None, mode="pixels", tile_rows=0):
+        """one process per GPU under torch.distributed: create the library's NCCL communicator for the group's ranks (the unique id
+        travels through the group), shard the scene over them. From then on renderC / renderD return the complete film and
+        backward() returns the complete gradient: one collective each, enqueued by the library on the scene's stream."""
+        torch = _torch()
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = "cuda:%d" % self._device if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.dist_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.dist_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+        self.set_shard_mode(mode, tile_rows)
 
     def _leaves_in_layout_order(self):
         """registered leaves matched to the segments of the flat gradient vector"""
@@ -325,52 +439,82 @@ def _image_tensor(scene):
 class _IntegratorMixin:
     def renderC(self, scene, sensor_id=0):
         """Integrator.renderC (src/integrator/integrator.cpp:13-29) -> (H*W, 3) CUDA tensor, pixel = y*W + x"""
+        scene._bind_stream()
         img = _image_tensor(scene)
         self._render_c(scene, sensor_id, img.data_ptr())
+        if scene.shard_world > 1:
+            scene._allreduce_image(img.data_ptr())     # the film of a sharded scene is complete when the call returns
         ek = _enoki()
         return ek.Vector3f(img.cpu().numpy()) if ek is not None else img
 
     def renderD(self, scene, sensor_id=0):
         """Integrator.renderD (src/integrator/integrator.cpp:32-60) -> image attached to torch.autograd; backward() runs the
-        reverse-mode kernels (interior + boundary terms) and fills .grad of the registered parameters"""
+        reverse-mode kernels (interior + boundary terms) and fills .grad of the registered parameters. With the Enoki stand-in
+        imported the image is one of its arrays instead: ek.forward / ek.backward differentiate it (examples/run_test.py:126-129,
+        docs/inverse_diff_render.rst:63-79)."""
         torch = _torch()
         ek = _enoki()
-        if ek is not None:   # examples/run_test.py flow: the derivative image is produced when ek.forward(P) runs
+        scene._bind_stream()
+        integ = self
+        if ek is not None:
             img = _image_tensor(scene)
             self._render_d(scene, sensor_id, img.data_ptr())
+            if scene.shard_world > 1:
+                scene._allreduce_image(img.data_ptr())
+            state = scene._render_d_state()
             out = ek.Vector3f(img.cpu().numpy())
-            integ = self
 
-            def run_forward():
+            def run_forward():   # ek.forward(P): the derivative image is produced now
                 dimg = torch.empty_like(img)
+                scene._render_d_set_state(list(state))
                 integ._render_d_jvp(scene, sensor_id, scene._forward_tangent().data_ptr(), dimg.data_ptr())
+                if scene.shard_world > 1:
+                    scene._allreduce_image(dimg.data_ptr())
                 d = dimg.cpu().numpy()
                 out.x.d, out.y.d, out.z.d = d[:, 0].copy(), d[:, 1].copy(), d[:, 2].copy()
             out._run_forward = run_forward
             ek._pending.append(out)
+
+            inputs = [(key, field, arr) for (key, field), arr in scene._ek_inputs.items() if arr._tracked()]
+
+            def vjp(dLdI):       # ek.backward(loss) reached this image
+                g = torch.from_numpy(np.ascontiguousarray(dLdI, dtype=np.float32)).to(img.device)
+                grad = torch.zeros(max(1, scene.grad_size()), dtype=torch.float32, device=img.device)
+                scene._render_d_set_state(list(state))
+                integ._render_d_vjp(scene, sensor_id, g.data_ptr(), grad.data_ptr())
+                if scene.shard_world > 1:
+                    scene._allreduce_grads(grad.data_ptr(), grad.numel())
+                flat = grad.cpu().numpy()
+                seg = {(key, field): (off, cnt) for key, field, off, cnt in scene.grad_layout()}
+                return [(arr, flat[seg[(key, field)][0]:seg[(key, field)][0] + seg[(key, field)][1]]) for key, field, arr in inputs if (key, field) in seg]
+            if inputs:
+                ek._attach_render(out, [arr for _, _, arr in inputs], vjp)
             return out
         segs = scene._leaves_in_layout_order()
         xforms = scene._transform_leaves()
         leaves = [t for t, _, _ in segs if t is not None and t.requires_grad] + [x[0] for x in xforms]
-        integ = self
 
         class _RenderD(torch.autograd.Function):
             @staticmethod
             def forward(ctx, *inputs):
                 img = _image_tensor(scene)
                 integ._render_d(scene, sensor_id, img.data_ptr())
+                if scene.shard_world > 1:
+                    scene._allreduce_image(img.data_ptr())
+                # the reference's tape differentiates each renderD image with its own samples, however many renders precede backward()
+                # (one image per sensor in a multi-view loss): remember this render's sampler positions for the VJP
+                ctx.render_state = scene._render_d_state()
                 return img
 
             @staticmethod
             def backward(ctx, g):
+                scene._bind_stream()
                 grad = torch.zeros(max(1, scene.grad_size()), dtype=torch.float32, device=g.device)
                 g = g.contiguous().float()
+                scene._render_d_set_state(list(ctx.render_state))
                 integ._render_d_vjp(scene, sensor_id, g.data_ptr(), grad.data_ptr())
-                try:
-                    from psdr_cuda_b200 import dist as _dist
-                    _dist.all_reduce_sum_(grad)
-                except ImportError:
-                    pass
+                if scene.shard_world > 1:   # only a scene that was sharded explicitly exchanges anything: one sum of the gradient vector
+                    scene._allreduce_grads(grad.data_ptr(), grad.numel())
                 outs = []
                 for t, off, cnt in segs:
                     if t is not None and t.requires_grad:
@@ -387,8 +531,11 @@ class _IntegratorMixin:
         parameters (the tensors returned by scene.parameter) to tangent tensors of the same shape; returns (image, d image).
         Unlisted parameters get a zero tangent."""
         torch = _torch()
+        scene._bind_stream()
         img = _image_tensor(scene)
         self._render_d(scene, sensor_id, img.data_ptr())
+        if scene.shard_world > 1:
+            scene._allreduce_image(img.data_ptr())
         flat = torch.zeros(max(1, scene.grad_size()), dtype=torch.float32, device=img.device)
         for t, off, cnt in scene._leaves_in_layout_order():
             if t is None:
@@ -398,6 +545,8 @@ class _IntegratorMixin:
                     flat[off:off + cnt] = tan.to(flat.device, torch.float32).reshape(-1)
         dimg = torch.empty_like(img)
         self._render_d_jvp(scene, sensor_id, flat.data_ptr(), dimg.data_ptr())
+        if scene.shard_world > 1:
+            scene._allreduce_image(dimg.data_ptr())
         return img, dimg
 
 

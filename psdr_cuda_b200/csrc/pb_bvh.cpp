@@ -166,7 +166,7 @@ void build_bvh(const float *p0e1e2, int n, std::vector<HostNode> &nodes, std::ve
     float extent = 0.f;
     for (const Box &b : tb) for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
     for (auto &nd : B.nodes) { pad_box(nd.llo, nd.lhi, extent); pad_box(nd.rlo, nd.rhi, extent); }
-    {   // breadth-first renumbering: the top of the tree gets the smallest indices (it is staged in shared memory, pb_trace.cuh)
+    {   // breadth-first renumbering: a tree level is a contiguous index range (the device refit walks the levels bottom-up)
         std::vector<int> order_bfs, new_id(B.nodes.size(), -1);
         order_bfs.reserve(B.nodes.size());
         order_bfs.push_back(0);
@@ -186,63 +186,6 @@ void build_bvh(const float *p0e1e2, int n, std::vector<HostNode> &nodes, std::ve
     }
     nodes.swap(B.nodes);
     order.swap(B.order);
-}
-
-// Collapse the binary tree into 4-wide nodes: start from a node's two children and keep opening the inner child with the
-// largest surface area until there are four (or only leaves are left). Halves the number of dependent node fetches per
-// ray; boxes are the (already padded) child boxes of the binary nodes.
-namespace {
-struct Entry { int code; float lo[3], hi[3]; };
-float entry_area(const Entry &e) {
-    const float dx = e.hi[0] - e.lo[0], dy = e.hi[1] - e.lo[1], dz = e.hi[2] - e.lo[2];
-    return dx * dy + dy * dz + dz * dx;
-}
-void children_of(const HostNode &n, Entry &l, Entry &r) {
-    l.code = n.left; r.code = n.right;
-    for (int k = 0; k < 3; ++k) { l.lo[k] = n.llo[k]; l.hi[k] = n.lhi[k]; r.lo[k] = n.rlo[k]; r.hi[k] = n.rhi[k]; }
-}
-int collapse_rec(const std::vector<HostNode> &n2, int node, std::vector<HostNode4> &n4) {
-    const int id = (int)n4.size();
-    n4.emplace_back();
-    Entry e[4];
-    int cnt = 2;
-    children_of(n2[node], e[0], e[1]);
-    while (cnt < 4) {
-        int best = -1;
-        float best_area = -1.f;
-        for (int i = 0; i < cnt; ++i)
-            if (e[i].code >= 0 && e[i].hi[0] < std::numeric_limits<float>::max()) {
-                const float a = entry_area(e[i]);
-                if (a > best_area) { best_area = a; best = i; }
-            }
-        if (best < 0) break;
-        Entry l, r;
-        children_of(n2[e[best].code], l, r);
-        e[best] = l;
-        e[cnt++] = r;
-    }
-    int codes[4];
-    for (int i = 0; i < 4; ++i) {
-        if (i < cnt && e[i].hi[0] < std::numeric_limits<float>::max()) codes[i] = e[i].code >= 0 ? collapse_rec(n2, e[i].code, n4) : e[i].code;
-        else codes[i] = kBvh4Empty;
-    }
-    HostNode4 &o = n4[id];
-    for (int i = 0; i < 4; ++i) {
-        const bool present = codes[i] != kBvh4Empty;
-        const float far_away = std::numeric_limits<float>::max();
-        o.lox[i] = present ? e[i].lo[0] : far_away; o.loy[i] = present ? e[i].lo[1] : far_away; o.loz[i] = present ? e[i].lo[2] : far_away;
-        o.hix[i] = present ? e[i].hi[0] : far_away; o.hiy[i] = present ? e[i].hi[1] : far_away; o.hiz[i] = present ? e[i].hi[2] : far_away;
-        o.child[i] = codes[i];
-        o.pad[i] = 0;
-    }
-    return id;
-}
-}  // namespace
-
-void collapse_bvh4(const std::vector<HostNode> &n2, std::vector<HostNode4> &n4) {
-    n4.clear();
-    n4.reserve(n2.size());
-    collapse_rec(n2, 0, n4);
 }
 
 }  // namespace pb

@@ -163,23 +163,18 @@ static void configure_sensor(HostSensor &s, int W, int H) {
     r.width = W; r.height = H;
 }
 
-// all wavefront ray launches go through here: sorted (variant 7) or in lane order (debug variants)
+// all wavefront ray launches go through here: counting sort by (origin cell, direction octant) with compaction of inactive lanes,
+// then the streaming traversal kernel over the sorted stream (pb_sort.cu, pb_trace2.cuh)
 static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
-    if (g_trace_variant == 7) {
-        if (!c->d_active_total.p) { c->d_active_total.reserve(sizeof(unsigned long long)); cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream); }
-        c->d_sort_hist.reserve(40000 * sizeof(unsigned));
-        c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
-        c->d_sort_keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
-        c->d_stream_counter.reserve(sizeof(unsigned));
-        launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
-                            f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
-                            c->d_sort_keys.as<unsigned short>(), c->d_stream_counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1);
-        c->launches += 3;
-    } else {
-        if (ev0) cudaEventRecord(ev0, c->stream);
-        launch_trace(c->stream, c->view, n, rays, hits, nullptr);
-        if (ev1) cudaEventRecord(ev1, c->stream);
-    }
+    if (!c->d_active_total.p) { c->d_active_total.reserve(sizeof(unsigned long long)); cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream); }
+    c->d_sort_hist.reserve(40000 * sizeof(unsigned));
+    c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
+    c->d_sort_keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
+    c->d_stream_counter.reserve(sizeof(unsigned));
+    launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
+                        f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
+                        c->d_sort_keys.as<unsigned short>(), c->d_stream_counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1);
+    c->launches += 3;
 }
 
 // Keep triangle table + BVH + leaf triangles (22 MB for 70 k triangles) resident in L2 while rays, hits and path state stream
@@ -428,8 +423,7 @@ static void configure(pb_ctx *c) {
         if (total == 0) for (int k = 0; k < 3; ++k) { c->scene_lo[k] = 0.f; c->scene_hi[k] = 1.f; }
         std::vector<int> sig;
         for (const HostMesh &m : c->meshes) sig.push_back(m.nf);
-        const bool bvh4_wanted = (g_trace_variant == 8 || g_trace_variant == 9);
-        const bool can_refit = c->bvh_valid && !any_topo && sig == c->bvh_sig && c->bvh_refits < c->bvh_max_refits && !bvh4_wanted && total > 0;
+        const bool can_refit = c->bvh_valid && !any_topo && sig == c->bvh_sig && c->bvh_refits < c->bvh_max_refits && total > 0;
         if (can_refit) {
             float extent = 0.f;
             for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(c->scene_lo[k]), std::fabs(c->scene_hi[k])));
@@ -473,12 +467,6 @@ static void configure(pb_ctx *c) {
         PB_ASSERT_MSG(dn.size() * sizeof(BvhNode) <= c->arena_node_bytes, "internal: BVH larger than its arena");
         PB_CUDA(cudaMemcpyAsync(c->arena_nodes(), dn.data(), dn.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
         PB_CUDA(cudaStreamSynchronize(st));   // dn is a local
-        if (bvh4_wanted) {   // only the measured-not-faster BVH4 debug variants read it
-            std::vector<HostNode4> n4;
-            collapse_bvh4(nodes, n4);
-            static_assert(sizeof(HostNode4) == sizeof(BvhNode4), "BVH4 node layout");
-            c->d_nodes4.upload(n4, st);
-        }
         c->d_order.upload(order, st);
         if (total == 0) PB_CUDA(cudaMemsetAsync(c->arena_leaf(), 0, sizeof(LeafTri), st));
         else launch_build_leaf_tris(st, total, c->d_order.as<int>(), c->arena_tri(), c->arena_leaf());
@@ -556,7 +544,7 @@ static void configure(pb_ctx *c) {
     c->d_bsdfs.upload(br, st);
     PB_CUDA(cudaStreamSynchronize(st));
     SceneView &V = c->view;
-    V.tri = c->arena_tri(); V.leaf = c->arena_leaf(); V.nodes = c->arena_nodes(); V.nodes4 = c->d_nodes4.as<BvhNode4>(); V.nodes_c = c->arena_nodes_c();
+    V.tri = c->arena_tri(); V.leaf = c->arena_leaf(); V.nodes = c->arena_nodes(); V.nodes_c = c->arena_nodes_c();
     V.meshes = c->d_meshes.as<MeshRec>(); V.bsdfs = c->d_bsdfs.as<BsdfRec>(); V.emitters = c->d_emitters.as<EmitterRec>();
     V.emitter_cmf = c->d_emitter_cmf.as<float>(); V.emitter_pmf = c->d_emitter_pmf.as<float>(); V.emitter_sum = c->emitter_sum;
     V.num_tri = total; V.num_meshes = (int)mr.size(); V.num_bsdfs = (int)br.size(); V.num_emitters = (int)er.size();
@@ -602,6 +590,7 @@ static void configure(pb_ctx *c) {
     }
     set_l2_window(c);
     c->ready = true;
+    c->d_generation_at_configure = c->d_generation;
     c->have_last_d = false;
     c->retained_valid = false;
 }
@@ -722,7 +711,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
     c->d_edge_rad.reserve((size_t)B * sizeof(float4));
     RenderParams P = Pbase;
     if (P.S.tri_tangent) { c->d_jvp_acc.reserve((size_t)B * sizeof(float)); P.S.jvp_acc = c->d_jvp_acc.as<float>(); }
-    P.spp = 1; P.spp_local = 1; P.s0 = 0; P.inv_spp = 1.f;
+    P.spp = 1; P.spp_local = 1; P.s0 = 0; P.inv_spp = 1.f; P.tile_rows = 0;   // edge lanes are sharded by index range
     EventStore &S = c->scratch;
     // ---- primary edges
     if (c->sppe > 0 && Q.num_prim > 0) {
@@ -857,8 +846,16 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     c->last_trace_ms = 0.f; c->last_rays = 0; c->last_primary_ms = 0.f; c->last_trace_launches = 0; c->last_active_rays = 0;
     if (!c->d_active_total.p) c->d_active_total.reserve(sizeof(unsigned long long));
     PB_CUDA(cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream));
-    const int s0 = (int)((int64_t)c->spp * c->rank / c->world), s1 = (int)((int64_t)c->spp * (c->rank + 1) / c->world);
+    const bool by_pixels = (c->shard_mode == 1 && c->world > 1);
+    const int s0 = by_pixels ? 0 : (int)((int64_t)c->spp * c->rank / c->world), s1 = by_pixels ? c->spp : (int)((int64_t)c->spp * (c->rank + 1) / c->world);
     const int spp_local = s1 - s0;
+    // pixel sharding: rows of the tiles t * world + rank
+    const int tile_rows = by_pixels ? std::max(1, c->tile_rows > 0 ? c->tile_rows : (c->height + c->world - 1) / c->world) : 0;
+    int64_t local_rows = c->height;
+    if (by_pixels) {
+        local_rows = 0;
+        for (int64_t r0 = (int64_t)c->rank * tile_rows; r0 < c->height; r0 += (int64_t)tile_rows * c->world) local_rows += std::min<int64_t>(tile_rows, c->height - r0);
+    }
     const Plan plan = make_plan(I);
     const uint64_t base = (mode == MODE_VJP) ? c->last_d_offset : c->sampler_offset[0];
     if (mode == MODE_D) c->retained_valid = false;
@@ -875,7 +872,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         return;
     }
     PB_ASSERT_MSG(field || !c->emitters.empty(), "No Emitter!");
-    const int64_t total = (c->spp > 0 && spp_local > 0) ? npix * spp_local : 0;
+    const int64_t total = (c->spp > 0 && spp_local > 0) ? local_rows * c->width * spp_local : 0;
     const int R = std::max(1, plan.nb + plan.nl);
     const int64_t B = std::max<int64_t>(1024, std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024));
     const int D = std::max(1, plan.nbounce);
@@ -897,6 +894,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     P.S = c->view; P.cam = c->sensors[sensor].rec;
     P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
     P.spp_local = spp_local; P.s0 = s0;
+    P.tile_rows = tile_rows; P.rank = c->rank; P.world = c->world;
     P.jump0 = make_jump(base);
     if (mode == MODE_VJP) {   // BSDF table whose textures point at their gradient segments
         std::vector<BsdfRec> br(c->bsdfs.size());
@@ -1115,12 +1113,10 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     }
     PB_CUDA(cudaGetLastError());
     PB_CUDA(cudaStreamSynchronize(st));
-    if (g_trace_variant == 7) {   // rays the traversal kernels actually traced (inactive lanes are compacted away by the sort)
+    {   // rays the traversal kernels actually traced (inactive lanes are compacted away by the sort)
         unsigned long long act = 0;
         PB_CUDA(cudaMemcpy(&act, c->d_active_total.p, sizeof(act), cudaMemcpyDeviceToHost));
         c->last_active_rays = (int64_t)act;
-    } else {
-        c->last_active_rays = c->last_rays;
     }
     // event pairs: per batch one for the primary kernel, then one per k_trace launch (the traversal kernel alone, without the sort)
     {
@@ -1181,6 +1177,7 @@ int pb_ctx_destroy(pb_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    pb_dist_finalize(c);
     if (!c->own_stream && c->l2_persist) { c->l2_persist = 0; set_l2_window(c); }   // leave the caller's stream as it was
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1196,7 +1193,13 @@ int pb_ctx_set_batch(pb_ctx *c, int64_t lanes) {
     });
 }
 int pb_ctx_set_shard(pb_ctx *c, int rank, int world) {
-    return guard(c, [&] { PB_ASSERT_MSG(world >= 1 && rank >= 0 && rank < world, "Invalid shard"); c->rank = rank; c->world = world; });
+    return guard(c, [&] { PB_ASSERT_MSG(world >= 1 && rank >= 0 && rank < world, "Invalid shard"); c->rank = rank; c->world = world; c->retained_valid = false; });
+}
+int pb_ctx_set_shard_mode(pb_ctx *c, int mode, int tile_rows) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG((mode == PB_SHARD_SAMPLES || mode == PB_SHARD_PIXELS) && tile_rows >= 0, "Invalid shard mode");
+        c->shard_mode = mode; c->tile_rows = tile_rows; c->retained_valid = false;
+    });
 }
 
 int pb_scene_set_options(pb_ctx *c, int w, int h, int spp, int sppe, int sppse) {
@@ -1417,6 +1420,24 @@ int pb_render_d(pb_ctx *c, const pb_integrator *I, int sensor, float *d_image) {
         const uint64_t off = c->sampler_offset[0];
         render_interior(c, *I, sensor, d_image, MODE_D);
         c->last_d_offset = off; c->have_last_d = true;
+        c->d_generation++;
+    });
+}
+int pb_render_d_get_state(pb_ctx *c, uint64_t *state) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(state, "Null argument");
+        PB_ASSERT_MSG(c->have_last_d, "pb_render_d_get_state needs a preceding pb_render_d on the configured scene");
+        state[0] = c->last_d_offset; state[1] = c->last_d_offset_e; state[2] = c->last_d_offset_s; state[3] = c->d_generation;
+    });
+}
+int pb_render_d_set_state(pb_ctx *c, const uint64_t *state) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(state, "Null argument");
+        PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+        PB_ASSERT_MSG(state[3] > c->d_generation_at_configure && state[3] <= c->d_generation, "pb_render_d_set_state: this state is not from a pb_render_d on the scene as configured now");
+        if (state[3] != c->d_generation) c->retained_valid = false;   // the retained records belong to a later render: the VJP re-traces
+        c->last_d_offset = state[0]; c->last_d_offset_e = state[1]; c->last_d_offset_s = state[2];
+        c->have_last_d = true;
     });
 }
 
@@ -1474,16 +1495,10 @@ int pb_render_d_vjp(pb_ctx *c, const pb_integrator *I, int sensor, const float *
 
 int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
     return guard(c, [&] {
-        if (std::strcmp(key, "trace_variant") == 0) pb::g_trace_variant = (int)value;
-        else if (std::strcmp(key, "trace_blocks_per_sm") == 0) pb::g_trace_blocks_per_sm = (int)value;
-        else if (std::strcmp(key, "trace_smem") == 0) pb::g_trace_smem = (int)value;
-        else if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
+        if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
         else if (std::strcmp(key, "shade_tune") == 0) pb::g_shade_tune = (int)value;
         else if (std::strcmp(key, "shade_simple") == 0) pb::g_shade_simple = (int)value;
-        else if (std::strcmp(key, "trace_ld256") == 0) pb::g_trace_ld256 = (int)value;
         else if (std::strcmp(key, "l2_persist") == 0) { c->l2_persist = (int)value; set_l2_window(c); }
-        else if (std::strcmp(key, "trace_sstack") == 0) pb::g_trace_sstack = (int)value;
-        else if (std::strcmp(key, "trace_smem_nodes") == 0) pb::g_trace_smem_nodes = (int)value;
         else if (std::strcmp(key, "trace_kernel") == 0) pb::g_trace_kernel = (int)value;
         else if (std::strcmp(key, "trace_node_min") == 0) pb::g_trace_node_min = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);

@@ -319,22 +319,21 @@ __global__ void k_nodes_to_compact(int n, const BvhNode *__restrict__ nodes, Bvh
     const float4 *np = reinterpret_cast<const float4 *>(nodes + i);
     const float4 a = np[0], b = np[1], c = np[2], d = np[3];
     const float lo[2][3] = {{a.x, a.y, a.z}, {b.z, b.w, c.x}}, hi[2][3] = {{a.w, b.x, b.y}, {c.y, c.z, c.w}};
-    float cen[2][3];
-    unsigned hb[2][3];
+    float cen[2][3], hf[2][3];
     const float slack = __fmul_ru(4e-7f, extent);
 #pragma unroll
     for (int s = 0; s < 2; ++s)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (lo[s][k] >= 3.402823466e+38f) { cen[s][k] = lo[s][k]; hb[s][k] = 0u; continue; }   // unreachable child (pb_bvh.cpp)
+            if (lo[s][k] >= 3.402823466e+38f) { cen[s][k] = lo[s][k]; hf[s][k] = 0.f; continue; }   // unreachable child (pb_bvh.cpp)
             const float m = __fadd_rn(__fmul_rn(0.5f, lo[s][k]), __fmul_rn(0.5f, hi[s][k]));
-            const float h = __fadd_ru(fmaxf(__fsub_ru(hi[s][k], m), __fsub_ru(m, lo[s][k])), slack);
-            cen[s][k] = m; hb[s][k] = bf16_up(fmaxf(h, 0.f));
+            cen[s][k] = m;
+            hf[s][k] = fmaxf(__fadd_ru(fmaxf(__fsub_ru(hi[s][k], m), __fsub_ru(m, lo[s][k])), slack), 0.f);
         }
     BvhNodeC o;
-    o.a = make_float4(cen[0][0], cen[0][1], cen[0][2], cen[1][0]);
-    o.b = make_float4(cen[1][1], cen[1][2], d.x, d.y);
-    o.c = make_float4(__uint_as_float((hb[0][0] << 16) | hb[1][0]), __uint_as_float((hb[0][1] << 16) | hb[1][1]), __uint_as_float((hb[0][2] << 16) | hb[1][2]), 0.f);
+    o.a = make_float4(cen[0][0], cen[0][1], cen[0][2], cen[1][2]);
+    o.b = make_float4(cen[1][0], cen[1][1], d.x, d.y);
+    o.c = make_float4(__uint_as_float((bf16_up(hf[0][0]) << 16) | bf16_up(hf[1][0])), __uint_as_float((bf16_up(hf[0][1]) << 16) | bf16_up(hf[1][1])), hf[0][2], hf[1][2]);
     out[i] = o;
 }
 void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent) {

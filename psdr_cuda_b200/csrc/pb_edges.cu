@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) k_edge_primary_rays(RenderParams P, EdgeP
     const float sg = side == 0 ? 1.f : -1.f;   // side 0: ray_p (+n), side 1: ray_n (-n)
     float3 o, d;
     sample_primary_ray(P.cam, es.px + sg * kEdgeEpsilon * es.rec.nx, es.py + sg * kEdgeEpsilon * es.rec.ny, o, d);
-    Hit h = trace_closest_ww(P.S.nodes, P.S.leaf, o, d, es.idx >= 0 ? INFINITY : -1.f);
+    Hit h = trace_closest(P.S.nodes, P.S.leaf, o, d, es.idx >= 0 ? INFINITY : -1.f);
     reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
 }
 

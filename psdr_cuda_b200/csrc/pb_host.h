@@ -128,6 +128,9 @@ struct pb_ctx {
     bool has_bound_mesh = false;   // the last mesh is the envmap's bounding box (scene.cpp:135-180)
     // sharding / tiling
     int rank = 0, world = 1;
+    int shard_mode = 0, tile_rows = 0;   // 0: every shard renders spp / world samples of every pixel; 1: image-row tiles of tile_rows rows, dealt round-robin
+    void *nccl_comm = nullptr;           // pb_dist.cpp: communicator of pb_dist_init / pb_dist_adopt_comm
+    bool nccl_owned = false;
     int64_t batch = 1 << 25;   // 32 Mi lanes: large wavefronts sort into more coherent bins
     // samplers (scene.cpp:65-79): lane count the streams were seeded for and draws consumed so far
     int64_t sampler_count[3] = {0, 0, 0};
@@ -144,7 +147,7 @@ struct pb_ctx {
     pb::LeafTri *arena_leaf() const { return reinterpret_cast<pb::LeafTri *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes + arena_node_bytes); }
     pb::BvhNodeC *arena_nodes_c() const { return reinterpret_cast<pb::BvhNodeC *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes + arena_node_bytes + arena_leaf_bytes); }
     int l2_persist = 1;
-    pb::DevBuf d_nodes4, d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
+    pb::DevBuf d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
     std::vector<float> h_tri;   // host copy of the triangle table (BVH build, inspection)
     float emitter_sum = 0.f;
     pb::SceneView view;
@@ -165,9 +168,10 @@ struct pb_ctx {
     // replay info of the last renderD
     uint64_t last_d_offset = 0;
     bool have_last_d = false;
+    uint64_t d_generation = 0, d_generation_at_configure = 0;   // pb_render_d calls so far / at the last configure (pb_render_d_{get,set}_state)
     std::vector<pb::GradSegment> grad_segments;
     // stats
-    int64_t launches = 0, last_rays = 0, last_active_rays = 0;
+    int64_t launches = 0, last_rays = 0, last_active_rays = 0, collectives = 0;
     // BVH refit (vertex-only updates keep the tree and recompute its boxes on the device)
     bool bvh_valid = false;
     int bvh_max_refits = 16, bvh_refits = 0, bvh_builds = 0, bvh_refit_count = 0;

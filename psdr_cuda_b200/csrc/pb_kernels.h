@@ -26,7 +26,8 @@ struct RenderParams {
     int width, height, spp;
     float inv_spp;
     long long local0;       // shard-local index of the first lane of this batch
-    int spp_local, s0;      // this shard owns samples [s0, s0 + spp_local) of every pixel
+    int spp_local, s0;      // this shard owns samples [s0, s0 + spp_local) of every pixel (sample sharding; all of them under pixel sharding)
+    int tile_rows, rank, world;   // pixel sharding: tile_rows > 0 and this shard owns the image-row tiles t * world + rank (tile_rows rows each); 0 = every pixel
     int n;                  // lanes in this batch
     RngJump jump0;          // stream position of the pixel jitter
 };
@@ -57,17 +58,11 @@ void launch_bvh_refit(cudaStream_t st, BvhNode *nodes, float *boxes, const LeafT
 void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
-extern int g_trace_blocks_per_sm;
-extern int g_sort_mode;
-extern int g_trace_ld256;
-extern int g_trace_sstack;
-extern int g_shade_simple;   // debug: 0 = never use the diffuse + area-light instantiations
-extern int g_shade_tune;   // debug: k_resolve / k_adjoint variant (0 default)
-extern int g_trace_smem;
-extern int g_trace_smem_nodes;
-extern int g_trace_kernel;    // sorted-wavefront traversal kernel: 0 first generation (k_trace_perm), 1 compact nodes, 2 compact + postponed leaf, 3 persistent streaming
+extern int g_sort_mode;       // debug: sort key (pb_sort.cu)
+extern int g_shade_simple;    // debug: 0 = never use the diffuse + area-light instantiations
+extern int g_shade_tune;      // debug: k_resolve / k_adjoint variant (0 default)
+extern int g_trace_kernel;    // sorted-wavefront traversal kernel: 3 persistent streaming kernel (default), 1 one ray per thread
 extern int g_trace_node_min;  // streaming kernel: node steps continue while at least this many lanes descend
-extern int g_trace_variant;   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
                          unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total = nullptr, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);

@@ -26,173 +26,6 @@ __global__ void __launch_bounds__(128) k_trace(const BvhNode *__restrict__ nodes
     if (t_out) t_out[i] = h.t;
 }
 
-__global__ void __launch_bounds__(128) k_trace_ww(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
-                                                  const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const float4 a = ldg4(rp), b = ldg4(rp + 1);
-    const Hit h = trace_closest_ww(nodes, leaf, f3(a), f3(b), a.w);
-    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
-    if (t_out) t_out[i] = h.t;
-}
-
-template <bool FMA_SLAB>
-__global__ void __launch_bounds__(128) k_trace_spec(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
-                                                    const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const float4 a = ldg4(rp), b = ldg4(rp + 1);
-    const Hit h = trace_closest_spec<FMA_SLAB>(nodes, leaf, f3(a), f3(b), a.w, b.w);
-    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
-    if (t_out) t_out[i] = h.t;
-}
-
-template <bool FMA_SLAB>
-__global__ void __launch_bounds__(128) k_trace_bvh4(const BvhNode4 *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
-                                                    const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const float4 a = ldg4(rp), b = ldg4(rp + 1);
-    const Hit h = trace_closest_bvh4<FMA_SLAB>(nodes, leaf, f3(a), f3(b), a.w, b.w);
-    reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
-    if (t_out) t_out[i] = h.t;
-}
-
-// Block-local regrouping: the 256 rays of a block are counting-sorted in shared memory by (active, direction bin) so
-// that each warp traverses rays that point the same way and inactive lanes collect in warps that exit at once.
-// Only the thread<->ray assignment changes; every ray's hit is written back to its own slot.
-template <bool WW>
-__global__ void __launch_bounds__(256) k_trace_sorted(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
-                                                      const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out) {
-    constexpr int NB = 65;   // 64 direction bins + inactive
-    __shared__ int s_count[NB + 1];
-    __shared__ float4 s_ray[2][256];
-    __shared__ unsigned short s_src[256];
-    const int tid = threadIdx.x;
-    const long long base = (long long)blockIdx.x * 256;
-    const long long i = base + tid;
-    if (tid < NB + 1) s_count[tid] = 0;
-    __syncthreads();
-    float4 a = make_float4(0.f, 0.f, 0.f, -1.f), b = make_float4(0.f, 0.f, 1.f, 0.f);
-    if (i < n) { const float4 *rp = reinterpret_cast<const float4 *>(rays + i); a = ldg4(rp); b = ldg4(rp + 1); }
-    const int key = (a.w > 0.f) ? direction_bin(f3(b)) : 64;
-    const int rank = atomicAdd(&s_count[key], 1);
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int k = 0; k < NB; ++k) { const int c = s_count[k]; s_count[k] = acc; acc += c; }
-    }
-    __syncthreads();
-    const int pos = s_count[key] + rank;
-    s_ray[0][pos] = a; s_ray[1][pos] = b; s_src[pos] = (unsigned short)tid;
-    __syncthreads();
-    const float4 ra = s_ray[0][tid], rb = s_ray[1][tid];
-    const long long dst = base + s_src[tid];
-    if (dst >= n) return;
-    const Hit h = WW ? trace_closest_ww(nodes, leaf, f3(ra), f3(rb), ra.w) : trace_closest(nodes, leaf, f3(ra), f3(rb), ra.w);
-    reinterpret_cast<float4 *>(hits)[dst] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
-    if (t_out) t_out[dst] = h.t;
-}
-
-// Persistent traversal with dynamic ray fetch (Aila & Laine 2009): a warp keeps its lanes busy by handing a new ray to
-// every lane whose ray has terminated, as soon as fewer than kFetchThreshold lanes are still traversing. Ray lengths in
-// this workload differ by an order of magnitude (12 wall triangles vs a 69k-triangle bunny), which is what starves the
-// one-ray-per-thread kernels of SIMD lanes.
-constexpr int kFetchThreshold = 20;
-
-__global__ void __launch_bounds__(128) k_trace_dynamic(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, long long n,
-                                                       const RayRec *__restrict__ rays, HitRec *__restrict__ hits, float *__restrict__ t_out,
-                                                       unsigned long long *__restrict__ counter) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    float3 o = f3(0.f), d = f3(0.f);
-    float ix = 0.f, iy = 0.f, iz = 0.f, tmax = 0.f;
-    Hit best;
-    best.tri = -1; best.shape = -1; best.u = best.v = -1.f; best.t = 0.f;
-    int stack[64];
-    int sp = 0;
-    int node = kTraverseDone;
-    long long ray_idx = -1;
-    while (true) {
-        // retire finished rays and fetch new ones
-        const bool idle = (node == kTraverseDone);
-        if (idle && ray_idx >= 0) {
-            if (best.tri < 0) best.t = INFINITY;
-            reinterpret_cast<float4 *>(hits)[ray_idx] = make_float4(__int_as_float(best.tri), __int_as_float(best.shape), best.u, best.v);
-            if (t_out) t_out[ray_idx] = best.t;
-            ray_idx = -1;
-        }
-        const unsigned m = __ballot_sync(full, idle);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-            base = __shfl_sync(full, base, leader);
-            if (idle) {
-                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < n) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(rays + idx);
-                    const float4 a = ldg4(rp), b = ldg4(rp + 1);
-                    o = f3(a); d = f3(b); tmax = a.w;
-                    ix = clamp_idir(d.x); iy = clamp_idir(d.y); iz = clamp_idir(d.z);
-                    best.tri = -1; best.shape = -1; best.u = best.v = -1.f; best.t = tmax;
-                    sp = 0;
-                    ray_idx = idx;
-                    node = (tmax > 0.f) ? 0 : kTraverseDone;   // inactive lanes are retired on the next round
-                }
-            }
-        }
-        if (__all_sync(full, ray_idx < 0)) break;
-        while (node != kTraverseDone) {
-            if (node >= 0) {
-                const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-                const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2), l = ldg4(np + 3);
-                float t0, t1;
-                t0 = (a.x - o.x) * ix; t1 = (a.w - o.x) * ix;
-                float ln = fminf(t0, t1), lf = fmaxf(t0, t1);
-                t0 = (a.y - o.y) * iy; t1 = (b.x - o.y) * iy;
-                ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
-                t0 = (a.z - o.z) * iz; t1 = (b.y - o.z) * iz;
-                ln = fmaxf(ln, fminf(t0, t1)); lf = fminf(lf, fmaxf(t0, t1));
-                t0 = (b.z - o.x) * ix; t1 = (c.y - o.x) * ix;
-                float rn = fminf(t0, t1), rf = fmaxf(t0, t1);
-                t0 = (b.w - o.y) * iy; t1 = (c.z - o.y) * iy;
-                rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
-                t0 = (c.x - o.z) * iz; t1 = (c.w - o.z) * iz;
-                rn = fmaxf(rn, fminf(t0, t1)); rf = fminf(rf, fmaxf(t0, t1));
-                const bool hl = fmaxf(ln, 0.f) <= fminf(lf, best.t), hr = fmaxf(rn, 0.f) <= fminf(rf, best.t);
-                int cl = __float_as_int(l.x), cr = __float_as_int(l.y);
-                if (hl && hr) {
-                    if (rn < ln) { int t = cl; cl = cr; cr = t; }
-                    stack[sp++] = cr;
-                    node = cl;
-                } else if (hl) node = cl;
-                else if (hr) node = cr;
-                else node = sp ? stack[--sp] : kTraverseDone;
-            } else {
-                const int v = ~node;
-                const int first = v >> 3, cnt = (v & 7) + 1;
-                for (int i = 0; i < cnt; ++i) {
-                    const float4 *tp = reinterpret_cast<const float4 *>(leaf + first + i);
-                    const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
-                    float u, w, t;
-                    ray_intersect_triangle(f3(ta), f3(tb), f3(tc), o, d, u, w, t);
-                    const int id = __float_as_int(ta.w);
-                    if (u >= 0.f && w >= 0.f && add_rn(u, w) <= 1.f && t > kRayEpsilon && t < tmax &&
-                        (t < best.t || (t == best.t && (best.tri < 0 || id < best.tri)))) {
-                        best.t = t; best.u = u; best.v = w; best.tri = id; best.shape = __float_as_int(tb.w);
-                    }
-                }
-                node = sp ? stack[--sp] : kTraverseDone;
-            }
-            if (__popc(__activemask()) < kFetchThreshold) break;
-        }
-    }
-}
-
 // integrator.cpp:76-85 + the first ray launch of direct.cpp:48
 __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restrict__ hit0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,31 +195,11 @@ __global__ void __launch_bounds__(256) k_field(RenderParams P, int field, const 
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
-int g_trace_blocks_per_sm = 8;
 int g_shade_tune = 0;
 int g_shade_simple = 1;
-int g_trace_variant = 7;   // 7: counting-sorted + compacted wavefront (pb_sort.cu) for render calls; pb_trace uses the speculative kernel   // 0 baseline, 1 while-while, 2 block-sorted, 3 block-sorted + while-while
+// rays in lane order through the general kernel (any origin; pb_trace with a distance output, debug)
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out) {
-    if (n <= 0) return;
-    switch (g_trace_variant) {
-        case 0: k_trace<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 1: k_trace_ww<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 2: k_trace_sorted<false><<<nblk(n, 256), 256, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 3: k_trace_sorted<true><<<nblk(n, 256), 256, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 5: k_trace_spec<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 6: k_trace_spec<true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 7: k_trace_spec<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out); break;
-        case 8: k_trace_bvh4<false><<<nblk(n, 128), 128, 0, st>>>(S.nodes4, S.leaf, n, rays, hits, t_out); break;
-        case 9: k_trace_bvh4<true><<<nblk(n, 128), 128, 0, st>>>(S.nodes4, S.leaf, n, rays, hits, t_out); break;
-        default: {
-            static unsigned long long *counter = nullptr;   // one per process; launches on a stream are ordered
-            if (!counter) cudaMalloc(&counter, sizeof(unsigned long long));
-            cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
-            const unsigned blocks = (unsigned)std::min<long long>((n + 127) / 128, 148LL * g_trace_blocks_per_sm);
-            k_trace_dynamic<<<blocks, 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out, counter);
-            break;
-        }
-    }
+    if (n > 0) k_trace<<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, n, rays, hits, t_out);
 }
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0) {
     if (P.n > 0) k_primary<<<nblk(P.n, 128), 128, 0, st>>>(P, hit0);

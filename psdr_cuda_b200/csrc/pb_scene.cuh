@@ -34,13 +34,10 @@ struct __align__(32) LeafTri { float4 a, b, c, pad; };
 struct __align__(64) BvhNode { float4 a, b, c, d; };
 
 // Compact BVH2 node for the wavefront traversal (pb_trace2.cuh), 48 B = three 128-bit loads: child boxes as centre + half extent,
-// centres in fp32, half extents as bf16 rounded up (left child's in the high halves, right child's in the low halves).
-// a = (cL.x, cL.y, cL.z, cR.x)   b = (cR.y, cR.z, left, right)   c = (hx, hy, hz, -); links as in BvhNode
+// centres in fp32, x / y half extents as bf16 rounded up (left child's in the high halves, right child's in the low halves).
+// a = (cL.x, cL.y, cL.z, cR.z)   b = (cR.x, cR.y, left, right)   c = (hx, hy, hL.z, hR.z) with hx / hy = bf16(hL) << 16 | bf16(hR) and the z half
+// extents in fp32: every operand pair of the traversal's packed FFMA2 is an aligned register pair of a 128-bit load. Links as in BvhNode.
 struct __align__(16) BvhNodeC { float4 a, b, c; };
-
-// BVH4 node, 128 B = one line: the four children's boxes in SoA form (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4]),
-// child links (int bits; 0x80000000 = absent), padding. Built by collapsing the binary tree (pb_bvh.cpp).
-struct __align__(16) BvhNode4 { float4 lox, loy, loz, hix, hiy, hiz, child, pad; };
 
 struct MeshRec {           // 48 B, per mesh
     int bsdf, emitter;     // -1 = none
@@ -106,7 +103,6 @@ struct SceneView {
     const TriRec *tri;
     const LeafTri *leaf;
     const BvhNode *nodes;
-    const BvhNode4 *nodes4;
     const BvhNodeC *nodes_c;   // the same tree as `nodes` in the compact layout
     const MeshRec *meshes;
     const BsdfRec *bsdfs;

@@ -14,32 +14,17 @@
 
 namespace pb {
 
-int g_sort_mode = 0;
+int g_sort_mode = 5;      // 5: origin cell (8x8x8, Morton) x direction octant; 0: 6-bit direction bin x 4x4x4 cells (the A/B is in profiles/r02e_*)
 int g_trace_kernel = 3;     // 0 first generation (k_trace_perm), 1 compact nodes, 2 compact nodes + postponed leaf, 3 persistent streaming kernel
-int g_trace_node_min = 16;  // streaming kernel: node steps continue while at least this many lanes descend
-int g_trace_sstack = 0;   // > 0: that many stack levels in shared memory
-int g_trace_ld256 = 1;   // 256-bit node / leaf loads in the sorted-wavefront traversal kernel
-int g_trace_smem_nodes = 512;
-int g_trace_smem = 0;   // stage the top of the BVH in shared memory (persistent blocks) for the sorted wavefront trace
+int g_trace_node_min = 312;  // streaming kernel: node steps continue while at least this many lanes descend
 
 constexpr int kSortBins = 4096;   // 6 bits direction (octahedral 8x8, Morton) x 6 bits origin cell (4x4x4, Morton); finer keys measured slower
 
-__constant__ int c_sort_mode = 0;   // 0: 6 bits direction + 6 bits origin cell; 1: 8 + 3 (+ray kind); 2: 9 bits direction + 3 bits cell
-
-PB_D int direction_bin_n(float3 d, int n) {   // octahedral n x n grid, row-major
-    const float inv = 1.f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
-    float px = d.x * inv, py = d.y * inv;
-    if (d.z < 0.f) {
-        const float qx = (1.f - fabsf(py)) * (px >= 0.f ? 1.f : -1.f), qy = (1.f - fabsf(px)) * (py >= 0.f ? 1.f : -1.f);
-        px = qx; py = qy;
-    }
-    const int ux = min(n - 1, max(0, (int)((px * .5f + .5f) * (float)n))), uy = min(n - 1, max(0, (int)((py * .5f + .5f) * (float)n)));
-    return ((uy & 1) ? (n - 1 - ux) : ux) + uy * n;   // boustrophedon rows keep neighbouring bins adjacent
-}
+__constant__ int c_sort_mode = 5;
 
 PB_D int sort_key(float4 a, float4 b, float3 lo, float3 inv_ext) {
     if (!(a.w > 0.f)) return kSortBins;
-    if (c_sort_mode == 0) {
+    if (c_sort_mode == 0) {   // 6 bits direction (octahedral 8x8, Morton) x 6 bits origin cell (4x4x4, Morton)
         const int db = direction_bin(f3(b));
         const int cx = min(3, max(0, (int)((a.x - lo.x) * inv_ext.x * 4.f)));
         const int cy = min(3, max(0, (int)((a.y - lo.y) * inv_ext.y * 4.f)));
@@ -49,11 +34,14 @@ PB_D int sort_key(float4 a, float4 b, float3 lo, float3 inv_ext) {
         for (int k = 0; k < 2; ++k) cell |= (((cx >> k) & 1) << (3 * k)) | (((cy >> k) & 1) << (3 * k + 1)) | (((cz >> k) & 1) << (3 * k + 2));
         return (db << 6) | cell;
     }
-    const int cx = min(1, max(0, (int)((a.x - lo.x) * inv_ext.x * 2.f))), cy = min(1, max(0, (int)((a.y - lo.y) * inv_ext.y * 2.f))),
-              cz = min(1, max(0, (int)((a.z - lo.z) * inv_ext.z * 2.f)));
-    const int cell = cx | (cy << 1) | (cz << 2);
-    if (c_sort_mode == 1) return (((b.w > 0.f) ? 1 : 0) << 11) | (direction_bin_n(f3(b), 16) << 3) | cell;
-    return min(kSortBins - 1, (direction_bin_n(f3(b), 22) << 3) | cell);
+    // 9 bits origin cell (8x8x8, Morton) x 3 bits direction octant, cell-major: a chunk of the stream starts in one small region
+    const int cx = min(7, max(0, (int)((a.x - lo.x) * inv_ext.x * 8.f)));
+    const int cy = min(7, max(0, (int)((a.y - lo.y) * inv_ext.y * 8.f)));
+    const int cz = min(7, max(0, (int)((a.z - lo.z) * inv_ext.z * 8.f)));
+    int cell = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cell |= (((cx >> k) & 1) << (3 * k)) | (((cy >> k) & 1) << (3 * k + 1)) | (((cz >> k) & 1) << (3 * k + 2));
+    return cell << 3 | (((b.x < 0.f) ? 4 : 0) | ((b.y < 0.f) ? 2 : 0) | ((b.z < 0.f) ? 1 : 0));
 }
 
 // The histogram pass is the only one that reads the rays: it leaves each ray's 13-bit key in `keys` (2 B instead of 32 B for
@@ -125,51 +113,8 @@ __global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const unsign
     if (key != kSortBins) perm[s_cnt[key] + rank] = (unsigned)i;
 }
 
-template <bool FMA_SLAB, int MINB, bool LD256 = false>
-__global__ void __launch_bounds__(128, MINB) k_trace_perm(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
-                                                    const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
-    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= __ldg(n_active)) return;
-    const unsigned i = __ldcs(perm + j);
-    // rays and hits stream through once: evict-first hints keep the BVH and the triangle tables resident in L2
-    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
-    const Hit h = trace_closest_spec<FMA_SLAB, 64, LD256>(nodes, leaf, f3(a), f3(b), a.w, b.w);
-    __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
-}
-
-template <int MINB, int SK>
-__global__ void __launch_bounds__(128, MINB) k_trace_perm_sstack(const BvhNode *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
-                                                                 const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
-    __shared__ int s_stack[SK * 128];
-    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= __ldg(n_active)) return;
-    const unsigned i = __ldcs(perm + j);
-    const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-    const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
-    const Hit h = trace_closest_spec_sstack<true, SK, true>(s_stack, nodes, leaf, f3(a), f3(b), a.w, b.w);
-    __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
-}
-
-// persistent blocks (one per SM, 1024 threads, 192 KiB of shared memory for the top of the tree) over the sorted rays
-template <bool FMA_SLAB>
-__global__ void __launch_bounds__(1024, 1) k_trace_perm_smem(const BvhNode *__restrict__ nodes, int num_nodes, const LeafTri *__restrict__ leaf,
-                                                             const unsigned *__restrict__ n_active, const unsigned *__restrict__ perm,
-                                                             const RayRec *__restrict__ rays, HitRec *__restrict__ hits, int cap) {
-    extern __shared__ float4 s_nodes[];
-    const int top = stage_top_nodes(s_nodes, nodes, num_nodes, cap);
-    const unsigned n = __ldg(n_active);
-    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const unsigned i = __ldg(perm + j);
-        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-        const float4 a = ldg4(rp), b = ldg4(rp + 1);
-        const Hit h = trace_closest_smem<FMA_SLAB>(s_nodes, top, cap, nodes, leaf, f3(a), f3(b), a.w, b.w);
-        reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
-    }
-}
-
 // one ray per thread over the compact nodes (pb_trace2.cuh)
-template <bool SPEC, int MINB>
+template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_trace_compact(const BvhNodeC *__restrict__ nodes, const LeafTri *__restrict__ leaf, const unsigned *__restrict__ n_active,
                                                              const unsigned *__restrict__ perm, const RayRec *__restrict__ rays, HitRec *__restrict__ hits) {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,7 +122,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_compact(const BvhNodeC *__r
     const unsigned i = __ldcs(perm + j);
     const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
     const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
-    const Hit h = trace_closest_c<SPEC>(nodes, leaf, f3(a), f3(b), a.w, b.w);
+    const Hit h = trace_closest_c(nodes, leaf, f3(a), f3(b), a.w, b.w);
     __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
 }
 
@@ -187,7 +132,7 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
                          unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (n <= 0) return;
-    static int mode_set = -1;
+    static int mode_set = 5;   // debug switch only (process-wide like the other pb_debug_set keys; the default needs no upload)
     if (mode_set != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); mode_set = g_sort_mode; }
     const float3 inv_ext = f3(1.f / fmaxf(hi.x - lo.x, 1e-20f), 1.f / fmaxf(hi.y - lo.y, 1e-20f), 1.f / fmaxf(hi.z - lo.z, 1e-20f));
     cudaMemsetAsync(hist, 0, (kSortBins + 2) * sizeof(unsigned), st);   // hist must hold kSortBins + 2 counters
@@ -207,53 +152,11 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
     if (g_trace_kernel == 3) {
         StreamArgs A;
         A.nodes = S.nodes_c; A.leaf = S.leaf; A.n_active = hist + kSortBins + 1; A.perm = perm; A.rays = rays; A.hits = hits; A.counter = stream_counter;
-        const unsigned grid = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 8);
-        const unsigned grid10 = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 10), grid12 = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 12);
-        switch (g_trace_node_min) {
-            case 201: k_trace_stream<16, 8, 8, 1><<<grid, 128, 0, st>>>(A); break;   // prefetch the postponed child
-            case 202: k_trace_stream<16, 8, 8, 2><<<grid, 128, 0, st>>>(A); break;   // prefetch the leaf triangle when a leaf is reached
-            case 203: k_trace_stream<16, 8, 8, 3><<<grid, 128, 0, st>>>(A); break;   // both
-            case 210: k_trace_stream<16, 8, 10><<<grid10, 128, 0, st>>>(A); break;   // 10 blocks / SM (51 registers)
-            case 212: k_trace_stream<16, 8, 12><<<grid12, 128, 0, st>>>(A); break;   // 12 blocks / SM (42 registers)
-            case 213: k_trace_stream<16, 8, 12, 3><<<grid12, 128, 0, st>>>(A); break;
-            case 304: k_trace_stream<16, 4, 8><<<grid, 128, 0, st>>>(A); break;
-            case 312: k_trace_stream<16, 12, 8><<<grid, 128, 0, st>>>(A); break;
-            case 14: k_trace_stream<14, 8, 8><<<grid, 128, 0, st>>>(A); break;
-            case 18: k_trace_stream<18, 8, 8><<<grid, 128, 0, st>>>(A); break;
-            case 8: k_trace_stream<8, 8, 8><<<grid, 128, 0, st>>>(A); break;
-            case 12: k_trace_stream<12, 8, 8><<<grid, 128, 0, st>>>(A); break;
-            case 16: k_trace_stream<16, 8, 8><<<grid, 128, 0, st>>>(A); break;
-            case 20: k_trace_stream<20, 8, 8><<<grid, 128, 0, st>>>(A); break;
-            case 101: k_trace_stream<1, 1, 8><<<grid, 128, 0, st>>>(A); break;     // refill as soon as one lane is idle
-            case 116: k_trace_stream<16, 16, 8><<<grid, 128, 0, st>>>(A); break;   // refill only when half the warp is idle
-            default: k_trace_stream<1, 8, 8><<<grid, 128, 0, st>>>(A); break;
-        }
-    } else if (g_trace_kernel == 1) {
-        k_trace_compact<false, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes_c, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-    } else if (g_trace_kernel == 2) {
-        k_trace_compact<true, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes_c, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-    } else if (g_trace_smem) {
-        static bool attr_set = false;
-        const int cap = std::min(kTopNodes, std::max(32, g_trace_smem_nodes));
-        const int smem = cap * 64;
-        if (!attr_set) { cudaFuncSetAttribute(k_trace_perm_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopNodes * 64); attr_set = true; }
-        k_trace_perm_smem<true><<<148, 1024, smem, st>>>(S.nodes, S.num_nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits, cap);
+        const unsigned grid = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 8);   // persistent: 8 blocks of 4 warps per SM
+        if (g_trace_node_min == 1) k_trace_stream<1, 12, 8, 2><<<grid, 128, 0, st>>>(A);    // node steps until no lane descends (plain while-while; 40 % slower)
+        else k_trace_stream<16, 12, 8, 2><<<grid, 128, 0, st>>>(A);
     } else {
-        if (g_trace_sstack == 16) {
-            k_trace_perm_sstack<8, 16><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-        } else if (g_trace_sstack == 24) {
-            k_trace_perm_sstack<8, 24><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-        } else if (g_trace_sstack == 12) {
-            k_trace_perm_sstack<10, 12><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-        } else if (g_trace_ld256) {
-            if (g_trace_blocks_per_sm == 10) k_trace_perm<true, 10, true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-            else k_trace_perm<true, 8, true><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits);
-        } else switch (g_trace_blocks_per_sm) {
-            case 10: k_trace_perm<true, 10><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
-            case 12: k_trace_perm<true, 12><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
-            case 16: k_trace_perm<true, 16><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
-            default: k_trace_perm<true, 8><<<nblk(n, 128), 128, 0, st>>>(S.nodes, S.leaf, hist + kSortBins + 1, perm, rays, hits); break;
-        }
+        k_trace_compact<8><<<nblk(n, 128), 128, 0, st>>>(S.nodes_c, S.leaf, hist + kSortBins + 1, perm, rays, hits);
     }
     if (ev1) cudaEventRecord(ev1, st);
 }

@@ -10,12 +10,20 @@
 
 namespace pb {
 
-// shard-local lane index -> (pixel, global lane id). A shard owns samples [s0, s0 + spp_local) of every pixel, so the
-// global lane id (= RNG stream id, integrator.cpp:76) is pix*spp + s and results do not depend on the GPU count.
+// shard-local lane index -> (pixel, global lane id). A shard owns samples [s0, s0 + spp_local) of every pixel (sample sharding) or
+// every sample of the pixels of its image-row tiles (pixel sharding, BASELINE.json configs[3]); either way the global lane id
+// (= RNG stream id, integrator.cpp:76) is pix*spp + s, so results do not depend on the GPU count or on the partition.
 PB_D long long global_lane(const RenderParams &P, int i, int &pix) {
     const long long li = P.local0 + i;
-    pix = (int)(li / P.spp_local);
-    return (long long)pix * P.spp + P.s0 + (int)(li - (long long)pix * P.spp_local);
+    int lp = (int)(li / P.spp_local);
+    const int s = (int)(li - (long long)lp * P.spp_local);
+    if (P.tile_rows > 0) {   // local row -> global row of this shard's tiles (only the last tile of the image can be partial)
+        const int lr = lp / P.width, x = lp - lr * P.width;
+        const int t = lr / P.tile_rows;
+        lp = ((t * P.world + P.rank) * P.tile_rows + (lr - t * P.tile_rows)) * P.width + x;
+    }
+    pix = lp;
+    return (long long)lp * P.spp + P.s0 + s;
 }
 
 PB_D void lane_pixel_sample(const RenderParams &P, int pix, float2 jitter, float &sx, float &sy) {

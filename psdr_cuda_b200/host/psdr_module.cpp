@@ -355,6 +355,7 @@ public:
     std::shared_ptr<EnvironmentMap> envmap;
     std::map<std::string, std::shared_ptr<Object>> param_map;
     bool loaded = false, uploaded = false, configured = false;
+    int shard_world = 1;   // > 1: the scene renders one shard of a multi-GPU job (set_shard / dist_init)
 
     // device < 0: description only (ingest and inspection work, configure / render need a context)
     explicit Scene(int device = 0) { if (device >= 0 && pb_ctx_create(device, &ctx)) throw std::runtime_error(pb_last_error(nullptr)); }
@@ -765,7 +766,28 @@ PYBIND11_MODULE(_psdr_host, m) {
         .def_property_readonly("param_map", [](Scene &s) { py::dict d; for (auto &kv : s.param_map) d[py::str(kv.first)] = py::cast(kv.second); return d; })
         .def("grad_layout", &Scene::grad_layout)
         .def("grad_size", [](const Scene &s) { return (int64_t)pb_grad_size(s.ctx); })
-        .def("set_shard", [](Scene &s, int rank, int world) { s.check(pb_ctx_set_shard(s.ctx, rank, world)); })
+        .def("set_shard", [](Scene &s, int rank, int world) { s.check(pb_ctx_set_shard(s.ctx, rank, world)); s.shard_world = world; })
+        .def("set_shard_mode", [](Scene &s, const std::string &mode, int tile_rows) {
+                 if (mode != "samples" && mode != "pixels") throw std::runtime_error("shard mode must be \"samples\" or \"pixels\"");
+                 s.check(pb_ctx_set_shard_mode(s.ctx, mode == "pixels" ? PB_SHARD_PIXELS : PB_SHARD_SAMPLES, tile_rows));
+             }, py::arg("mode"), py::arg("tile_rows") = 0)
+        // several GPUs: the library owns an NCCL communicator and enqueues the film / gradient collectives on the scene's stream
+        .def_static("dist_available", []() { return pb_dist_available() != 0; })
+        .def("dist_unique_id", [](Scene &s) { char id[128]; s.check(pb_dist_unique_id(s.ctx, id)); return py::bytes(id, 128); })
+        .def("dist_init", [](Scene &s, const std::string &id, int rank, int world) {
+                 if (id.size() != 128) throw std::runtime_error("the NCCL unique id has 128 bytes");
+                 s.check(pb_dist_init(s.ctx, id.data(), rank, world)); s.shard_world = world;
+             }, py::arg("unique_id"), py::arg("rank"), py::arg("world"))
+        .def("dist_finalize", [](Scene &s) { s.check(pb_dist_finalize(s.ctx)); })
+        .def_property_readonly("shard_world", [](const Scene &s) { return s.shard_world; })
+        .def("_allreduce_image", [](Scene &s, uintptr_t d_image) { s.check(pb_allreduce_image(s.ctx, reinterpret_cast<float *>(d_image))); })
+        .def("_allreduce_grads", [](Scene &s, uintptr_t d_grad, int64_t n) { s.check(pb_allreduce_grads(s.ctx, reinterpret_cast<float *>(d_grad), n)); })
+        .def("_render_d_state", [](Scene &s) { uint64_t st[4]; s.check(pb_render_d_get_state(s.ctx, st)); return py::make_tuple(st[0], st[1], st[2], st[3]); })
+        .def("_render_d_set_state", [](Scene &s, const std::vector<uint64_t> &st) {
+                 if (st.size() != 4) throw std::runtime_error("a renderD state has 4 entries");
+                 s.check(pb_render_d_set_state(s.ctx, st.data()));
+             })
+        .def("stats_collectives", [](const Scene &s) { return (int64_t)pb_stats_collectives(s.ctx); })
         .def("set_stream", [](Scene &s, uintptr_t stream) { s.check(pb_ctx_set_stream(s.ctx, reinterpret_cast<void *>(stream))); })
         .def("stats_launches", [](const Scene &s) { return (int64_t)pb_stats_launches(s.ctx); })
         .def("__repr__", &Scene::to_string);

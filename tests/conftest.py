@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
 
+collect_ignore_glob = ["data/*"]   # fixtures (tests/data/examples/ holds the reference's own scripts, run by test_examples_verbatim.py)
+
 DATA = os.path.join(ROOT, "tests", "data")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 

@@ -115,9 +115,9 @@ def test_trace_bit_exact_vs_golden_and_oracle(desc, golden):
     rw[occ, 3] = (t_occ[occ] * 1.25 + 1.0).astype(np.float32)       # bounded occlusion queries, as k_shade emits them
     rw[occ, 7] = t_occ[occ]
     active = rw[:, 3] > 0
-    for kern in (3, 2, 1, 0):
+    for kern in (3, 1):                                  # persistent streaming kernel (default) / one ray per thread
         ctx.debug_set("trace_kernel", kern)
-        for node_min in ((1, 12, 101, 116) if kern == 3 else (1,)):
+        for node_min in ((16, 1) if kern == 3 else (16,)):
             ctx.debug_set("trace_node_min", node_min)
             hw = ctx.trace_wavefront(torch.from_numpy(rw).cuda()).cpu().numpy()
             assert np.all(hw[~active, 0] == -1), (kern, node_min)
@@ -130,7 +130,7 @@ def test_trace_bit_exact_vs_golden_and_oracle(desc, golden):
             assert np.array_equal(hw[hit, 1], shape[hit])
             assert np.array_equal(hw[hit, 2].view(np.uint32), u[hit].view(np.uint32)) and np.array_equal(hw[hit, 3].view(np.uint32), v[hit].view(np.uint32))
             assert np.all(hw[decided, 0] >= 0), (kern, node_min)
-    ctx.debug_set("trace_kernel", 3); ctx.debug_set("trace_node_min", 1)
+    ctx.debug_set("trace_kernel", 3); ctx.debug_set("trace_node_min", 16)
 
 
 @pytest.mark.parametrize("name,kind,kw", [("direct11", "direct", dict(bsdf_samples=1, light_samples=1)), ("direct21", "direct", dict(bsdf_samples=2, light_samples=1)),

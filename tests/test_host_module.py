@@ -227,6 +227,51 @@ def test_roughconductor_and_envmap_leaves_through_the_module(psdr_cuda):
 
 
 @pytest.mark.gpu
+def test_two_renders_before_one_backward_use_their_own_samples(psdr_cuda):
+    """A multi-view loss renders several images before one backward (the reference's tape differentiates each with the samples
+    that produced it). Every renderD node remembers its sampler positions (pb_render_d_get_state) and restores them for its VJP:
+    the gradient of view A must not change because view B was rendered in between."""
+    torch = pytest.importorskip("torch")
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path("cbox_bunny"), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse, sc.opts.log_level = 48, 48, 4, 2, 2, 0
+    albedo = sc.parameter("BSDF[id=white]", "reflectance")
+    verts = sc.parameter("Mesh[1]", "vertex_positions")
+    sc.configure()
+    integ = psdr_cuda.PathIntegrator(2)
+    w = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, size=(48 * 48, 3)).astype(np.float32)).cuda()
+    # A alone
+    img_a = integ.renderD(sc, 0)
+    (img_a * w).sum().backward()
+    ga, gv = albedo.grad.clone(), verts.grad.clone()
+    albedo.grad = None; verts.grad = None
+    # the same A, then B, then one backward through A only / through both
+    sc2 = psdr_cuda.Scene()                             # a fresh scene starts the sampler streams again
+    sc2.load_file(scene_path("cbox_bunny"), False)
+    sc2.opts.width, sc2.opts.height, sc2.opts.spp, sc2.opts.sppe, sc2.opts.sppse, sc2.opts.log_level = 48, 48, 4, 2, 2, 0
+    albedo2 = sc2.parameter("BSDF[id=white]", "reflectance")
+    verts2 = sc2.parameter("Mesh[1]", "vertex_positions")
+    sc2.configure()
+    img_a2 = integ.renderD(sc2, 0)
+    img_b2 = integ.renderD(sc2, 0)                      # a second view (same sensor, next samples) before backward
+    assert torch.equal(img_a2.detach(), img_a.detach()) and not torch.equal(img_b2.detach(), img_a2.detach())
+    (img_a2 * w).sum().backward(retain_graph=True)
+    assert torch.allclose(albedo2.grad, ga, rtol=1e-4, atol=1e-6)
+    assert (verts2.grad - gv).norm() <= 1e-3 * gv.norm()
+    albedo2.grad = None; verts2.grad = None
+    ((img_a2 + img_b2) * w).sum().backward()            # both nodes' VJPs, each with its own samples
+    sc3 = psdr_cuda.Scene()
+    sc3.load_file(scene_path("cbox_bunny"), False)
+    sc3.opts.width, sc3.opts.height, sc3.opts.spp, sc3.opts.sppe, sc3.opts.sppse, sc3.opts.log_level = 48, 48, 4, 2, 2, 0
+    albedo3 = sc3.parameter("BSDF[id=white]", "reflectance")
+    sc3.configure()
+    integ.renderD(sc3, 0)
+    img_b3 = integ.renderD(sc3, 0)
+    (img_b3 * w).sum().backward()                       # B alone, rendered last: the plain path
+    assert torch.allclose(albedo2.grad, ga + albedo3.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_inverse_rendering_loop_recovers_albedo_and_translation(psdr_cuda):
     """The use the module exists for (docs/inverse_diff_render.rst:48-79, examples/utils/adam.py): gradient descent through
     renderD on a material parameter and on a mesh transform (boundary terms on, BVH refit between iterations)."""
