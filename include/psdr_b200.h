@@ -133,6 +133,11 @@ int pb_render_d_set_state(pb_ctx *ctx, const uint64_t state[4]);
  * resolution[0..2] cells x resolution[3] samples per cell x nrounds over the secondary-edge sample space of `sensor` */
 int pb_preprocess_secondary_edges(pb_ctx *ctx, int sensor, const int resolution[4], int nrounds);
 
+/* Scene::sample_boundary_segment_direct (src/scene/scene.cpp:456-492, bound at src/psdr.cpp:274): n samples of 3 floats -> 17 floats each:
+ * p0 (point on a face edge), edge (unit), edge2 (to the opposite vertex), p2 and n (point on an emitter), pdf, is_valid (1 / 0).
+ * Needs sppse > 0: like the reference, configure builds the secondary-edge table only then. */
+int pb_sample_boundary_segment_direct(pb_ctx *ctx, int64_t n, const float *d_sample3, float *d_out);
+
 /* ---- gradients (reverse mode: ek.backward + ek.gradient in the reference, docs/inverse_diff_render.rst:71-79) -- */
 /* mark a leaf as requiring a gradient (ek.set_requires_gradient); slot only for PB_PARAM_BSDF_TEXTURE */
 int pb_grad_require(pb_ctx *ctx, int param_kind, int id, int slot, int enable);

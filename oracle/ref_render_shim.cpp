@@ -390,6 +390,23 @@ int ref_mesh_get_edges(void *s, int mesh, int *out) {   // [n][5]: Mesh::m_edge_
     for (size_t i = 0; i < n; ++i) for (int k = 0; k < 5; ++k) out[5 * i + k] = e[k][i];
     return 0;
 }
+// Scene::sample_boundary_segment_direct (scene.cpp:456-492) on n samples -> [n][17]: p0 edge edge2 p2 n pdf is_valid
+int ref_sample_boundary_segment_direct(void *s, int64_t n, const float *sample3, float *out) {
+    return guard([&] {
+        Scene &scene = *(Scene *)s;
+        std::vector<float> buf(n);
+        Vector3fC S3;
+        for (int c = 0; c < 3; ++c) { for (int64_t i = 0; i < n; ++i) buf[i] = sample3[3 * i + c]; S3[c] = FloatC::copy(buf.data(), n); }
+        BoundarySegSampleDirect b = scene.sample_boundary_segment_direct(S3, MaskC(true));
+        const Vector3fC p0 = detach(b.p0);
+        const Vector3fC *v[5] = {&p0, &b.edge, &b.edge2, &b.p2, &b.n};
+        for (int64_t i = 0; i < n; ++i) {
+            for (int k = 0; k < 5; ++k) for (int c = 0; c < 3; ++c) { const FloatC &a = (*v[k])[c]; out[17 * i + 3 * k + c] = a[slices(a) == 1 ? 0 : i]; }
+            out[17 * i + 15] = b.pdf[slices(b.pdf) == 1 ? 0 : i];
+            out[17 * i + 16] = b.is_valid[slices(b.is_valid) == 1 ? 0 : i] ? 1.f : 0.f;
+        }
+    });
+}
 // Scene::ray_intersect<false> on n rays -> global triangle id, shape index into m_meshes, OptiX-style barycentrics and its.t
 int ref_trace(void *s, int64_t n, const float *o, const float *d, int *tri, int *shape, float *u, float *v, float *t) {
     return guard([&] {

@@ -157,6 +157,13 @@ class Scene:
         return dict(sample_to_camera=out[:16].reshape(4, 4), world_to_sample=out[16:32].reshape(4, 4), to_world=out[32:48].reshape(4, 4),
                     camera_pos=out[48:51], camera_dir=out[51:54], inv_area=out[54])
 
+    def sample_boundary_segment_direct(self, sample3):
+        """Scene::sample_boundary_segment_direct (scene.cpp:456-492) -> (n, 17): p0 edge edge2 p2 n pdf is_valid"""
+        s3 = _f(sample3)
+        out = np.zeros((len(s3), 17), np.float32)
+        _chk(lib().ref_sample_boundary_segment_direct(self.h, C.c_int64(len(s3)), _p(s3), _p(out)))
+        return out
+
     def trace(self, o, d):
         o, d = _f(o), _f(d)
         n = len(o)

@@ -27,7 +27,7 @@ SYMBOLS = [
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
     "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad", "pb_render_d_get_state", "pb_render_d_set_state",
-    "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
+    "pb_sample_boundary_segment_direct", "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
 ]
 
 
@@ -281,6 +281,15 @@ class Context:
         hits = torch.empty((n, 4), dtype=torch.int32, device=rays.device)
         self._chk(lib().pb_trace(self.h, C.c_int64(n), _dp(rays), _dp(hits), None))
         return hits
+
+    def sample_boundary_segment_direct(self, sample3):
+        """Scene::sample_boundary_segment_direct: (n, 3) CUDA tensor of samples -> (n, 17): p0 edge edge2 p2 n pdf is_valid"""
+        import torch
+        self._bind_stream()
+        s3 = sample3.contiguous().float()
+        out = torch.empty((s3.shape[0], 17), dtype=torch.float32, device=s3.device)
+        self._chk(lib().pb_sample_boundary_segment_direct(self.h, C.c_int64(s3.shape[0]), _dp(s3), _dp(out)))
+        return out
 
     def _image(self):
         import torch

@@ -22,7 +22,7 @@ from . import _psdr_host as _h
 from . import _surface
 from ._psdr_host import (BSDF, AreaLight, BitmapD, DiffuseBSDF, Emitter, EnvironmentMap, Mesh, Object, PerspectiveCamera, RenderOption,  # noqa: F401
                          RoughConductorBSDF)
-from ._surface import (DiscreteDistribution, FrameC, FrameD, HyperCubeDistribution2f, HyperCubeDistribution3f, PositionSampleC,  # noqa: F401
+from ._surface import (BoundarySegSampleDirect, DiscreteDistribution, FrameC, FrameD, HyperCubeDistribution2f, HyperCubeDistribution3f, PositionSampleC,  # noqa: F401
                        PositionSampleD, RayC, RayD, SampleRecordC, SampleRecordD)
 
 
@@ -384,6 +384,30 @@ class Scene(_h.Scene):
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self.dist_init(bytes(t.cpu().numpy().tobytes()), rank, world)
         self.set_shard_mode(mode, tile_rows)
+
+    def sample_boundary_segment_direct(self, sample3, active=True):
+        """Scene::sample_boundary_segment_direct (src/scene/scene.cpp:456-492, src/psdr.cpp:274): a point on a face edge and a point on
+        an emitter per 3-D sample. `sample3`: (n, 3) array (numpy / torch / Vector3f of the Enoki stand-in); fields come back in kind."""
+        torch = _torch()
+        ek = _enoki()
+        s3 = sample3.numpy() if hasattr(sample3, "tangent_numpy") else sample3
+        s3 = torch.as_tensor(np.asarray(s3.detach().cpu()) if hasattr(s3, "detach") else np.asarray(s3), dtype=torch.float32).reshape(-1, 3).to("cuda:%d" % self._device)
+        self._bind_stream()
+        out = torch.empty((s3.shape[0], 17), dtype=torch.float32, device=s3.device)
+        self._sample_boundary_segment_direct(int(s3.shape[0]), s3.data_ptr(), out.data_ptr())
+        valid = out[:, 16] > 0
+        if active is not True:
+            act = torch.as_tensor(np.asarray(active), dtype=torch.bool, device=out.device).reshape(-1).expand(out.shape[0])
+            valid = valid & act
+        pdf = torch.where(valid, out[:, 15], torch.zeros_like(out[:, 15]))
+        f = [out[:, 0:3], out[:, 3:6], out[:, 6:9], out[:, 9:12], out[:, 12:15]]
+        if ek is not None or isinstance(sample3, np.ndarray):
+            f = [x.cpu().numpy() for x in f]
+            pdf, valid = pdf.cpu().numpy(), valid.cpu().numpy()
+            if ek is not None:
+                f = [ek.Vector3f(x) for x in f]
+                pdf = ek.Float32(pdf)
+        return BoundarySegSampleDirect(*f, pdf=pdf, is_valid=valid)
 
     def _leaves_in_layout_order(self):
         """registered leaves matched to the segments of the flat gradient vector"""

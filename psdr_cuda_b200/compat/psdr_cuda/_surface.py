@@ -101,6 +101,14 @@ class PositionSampleD(_PositionSample, SampleRecordD):
     pass
 
 
+class BoundarySegSampleDirect(SampleRecordC):
+    """records.h:35-45: what Scene.sample_boundary_segment_direct returns"""
+
+    def __init__(self, p0=None, edge=None, edge2=None, p2=None, n=None, pdf=None, is_valid=None):
+        super().__init__(pdf, is_valid)
+        self.p0, self.edge, self.edge2, self.p2, self.n = p0, edge, edge2, p2, n
+
+
 class DiscreteDistribution:
     """src/core/pmf.cpp:7-50: inclusive fp32 prefix sums; sample = first index whose cmf is not below u * sum"""
 

@@ -1445,6 +1445,21 @@ int pb_preprocess_secondary_edges(pb_ctx *c, int sensor, const int *resolution, 
     return guard(c, [&] { PB_ASSERT_MSG(resolution, "Null argument"); preprocess_secondary_edges(c, sensor, resolution, nrounds); });
 }
 
+int pb_sample_boundary_segment_direct(pb_ctx *c, int64_t n, const float *d_sample3, float *d_out) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->ready, "Scene needs to be configured!");
+        PB_ASSERT_MSG(n >= 0 && n <= std::numeric_limits<int>::max() && (n == 0 || (d_sample3 && d_out)), "Invalid arguments");
+        PB_ASSERT_MSG(c->sppse > 0 && c->num_sec > 0, "sample_boundary_segment_direct needs sppse > 0 (the secondary-edge table is built by configure only then, scene.cpp:205) and at least one edge");
+        PB_ASSERT_MSG(!c->emitters.empty(), "No Emitter!");
+        PB_CUDA(cudaSetDevice(c->device));
+        const EdgeParams Q = make_edge_params(c, 0, nullptr);
+        launch_sample_boundary_segment(c->stream, (int)n, c->view, Q, d_sample3, d_out);
+        c->launches++;
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
 int pb_grad_require(pb_ctx *c, int kind, int id, int slot, int enable) {
     return guard(c, [&] {
         if (kind == PB_PARAM_BSDF_TEXTURE) {

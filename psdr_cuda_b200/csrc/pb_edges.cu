@@ -176,6 +176,22 @@ PB_D BoundarySample sample_boundary_segment_direct(const SceneView &S, const Edg
     return r;
 }
 
+// Scene::sample_boundary_segment_direct as a call of its own (src/psdr.cpp:274): n samples (3 floats each) -> 17 floats each
+// (p0, edge, edge2, p2, n, pdf, is_valid)
+__global__ void __launch_bounds__(256) k_sample_boundary_segment(int n, SceneView S, EdgeParams Q, const float *__restrict__ sample3, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BoundarySample b = sample_boundary_segment_direct(S, Q, f3(sample3[3 * i], sample3[3 * i + 1], sample3[3 * i + 2]));
+    float *o = out + 17 * (size_t)i;
+    const float3 v[5] = {b.p0, b.edge, b.edge2, b.p2, b.n};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { o[3 * k] = v[k].x; o[3 * k + 1] = v[k].y; o[3 * k + 2] = v[k].z; }
+    o[15] = b.pdf; o[16] = b.valid ? 1.f : 0.f;
+}
+void launch_sample_boundary_segment(cudaStream_t st, int n, const SceneView &S, const EdgeParams &Q, const float *sample3, float *out) {
+    if (n > 0) k_sample_boundary_segment<<<(n + 255) / 256, 256, 0, st>>>(n, S, Q, sample3, out);
+}
+
 // stage A: sample the boundary segment; emit ray 0 (edge point -> emitter point) and ray 1 (opposite direction)
 __global__ void __launch_bounds__(256) k_edge_secondary_rays(RenderParams P, EdgeParams Q, RayRec *__restrict__ rays, int guide_spc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -76,6 +76,7 @@ void launch_edge_secondary_rays(cudaStream_t st, const RenderParams &P, const Ed
 void launch_edge_secondary_camera(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const RayRec *rays, const HitRec *hits, RayRec *cam_rays, int guide_spc);
 void launch_edge_secondary_eval(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const RayRec *rays, const HitRec *hits, const RayRec *cam_rays,
                                 const HitRec *cam_hits, const float *dLdI, float inv_sppse, float *guide_out, int guide_spc);
+void launch_sample_boundary_segment(cudaStream_t st, int n, const SceneView &S, const EdgeParams &Q, const float *sample3, float *out);
 void launch_field(cudaStream_t st, const RenderParams &P, int field, const HitRec *hit0, float *film, float4 *rad_out);
 
 }  // namespace pb

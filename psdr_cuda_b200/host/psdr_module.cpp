@@ -787,6 +787,10 @@ PYBIND11_MODULE(_psdr_host, m) {
                  if (st.size() != 4) throw std::runtime_error("a renderD state has 4 entries");
                  s.check(pb_render_d_set_state(s.ctx, st.data()));
              })
+        .def("_sample_boundary_segment_direct", [](Scene &s, int64_t n, uintptr_t d_sample3, uintptr_t d_out) {
+                 if (!s.configured) throw std::runtime_error("Scene needs to be configured!");
+                 s.check(pb_sample_boundary_segment_direct(s.ctx, n, reinterpret_cast<const float *>(d_sample3), reinterpret_cast<float *>(d_out)));
+             })
         .def("stats_collectives", [](const Scene &s) { return (int64_t)pb_stats_collectives(s.ctx); })
         .def("set_stream", [](Scene &s, uintptr_t stream) { s.check(pb_ctx_set_stream(s.ctx, reinterpret_cast<void *>(stream))); })
         .def("stats_launches", [](const Scene &s) { return (int64_t)pb_stats_launches(s.ctx); })

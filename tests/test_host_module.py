@@ -426,7 +426,7 @@ def test_python_surface_covers_the_reference_module(psdr_cuda):
         spec.loader.exec_module(gen)
         with open(ref_src) as fh:
             assert gen.extract(fh.read()) == surface
-    absent = {("Scene", "sample_boundary_segment_direct")}   # the boundary-segment sampler runs inside the edge kernels (pb_edges.cu); no host-side copy
+    absent = set()                                       # every class, method and property src/psdr.cpp binds is present
     missing = []
     for cls, info in sorted(surface.items()):
         if not hasattr(psdr_cuda, cls):

@@ -137,3 +137,50 @@ def test_committed_goldens_are_what_the_reference_run_produces(label, golden):
     else:
         img, dimg = I.renderD(sc)
         assert np.array_equal(img, golden[label]) and np.array_equal(dimg, golden[label + "_t"])
+
+
+def _boundary_segment_close(got, ref, what):
+    """(n, 17): p0 edge edge2 p2 n pdf is_valid. The validity flag must agree except for knife-edge samples (|cos| or the edge-normal
+    signs within fp32 noise of their thresholds); geometry to 1e-5 of the scene size, pdf to 1e-4 relative on the valid samples."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape
+    scale = np.abs(ref[:, :15]).max()
+    assert np.abs(got[:, :15] - ref[:, :15]).max() <= 1e-5 * scale, what
+    flips = int((got[:, 16] != ref[:, 16]).sum())
+    assert flips <= max(1, len(ref) // 1000), (what, flips)
+    both = (got[:, 16] > 0) & (ref[:, 16] > 0)
+    assert both.sum() > 50
+    assert np.all(np.abs(got[both, 15] - ref[both, 15]) <= 1e-4 * np.abs(ref[both, 15])), what
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cbox_bunny", "bunny_env"])
+def test_cuda_sample_boundary_segment_direct_matches_reference_source(name):
+    # Scene::sample_boundary_segment_direct (scene.cpp:456-492, src/psdr.cpp:274) of the reference's own source vs the C ABI call, and
+    # through the module surface (`import psdr_cuda`: Scene.sample_boundary_segment_direct(sample3))
+    torch = pytest.importorskip("torch")
+    from psdr_cuda_b200 import capi, scene_io
+    G = np.load(os.path.join(GOLDEN, "boundary_segment_golden.npz"))
+    ctx = capi.Context(0)
+    ctx.load_description(scene_io.load_scene_description(scene_path(name)), dict(width=32, height=32, spp=1, sppe=1, sppse=1))
+    ctx.configure()
+    got = ctx.sample_boundary_segment_direct(torch.from_numpy(G["sample3"]).cuda()).cpu().numpy()
+    _boundary_segment_close(got, G[name], name)
+    ctx.close()
+    import psdr_cuda_b200.compat  # noqa: F401
+    import psdr_cuda
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path(name), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse, sc.opts.log_level = 32, 32, 1, 1, 1, 0
+    sc.configure()
+    b = sc.sample_boundary_segment_direct(G["sample3"])
+    assert type(b).__name__ == "BoundarySegSampleDirect"
+    m = np.concatenate([b.p0, b.edge, b.edge2, b.p2, b.n, np.asarray(b.pdf)[:, None], np.asarray(b.is_valid, np.float32)[:, None]], axis=1)
+    ref = G[name].copy(); ref[ref[:, 16] == 0, 15] = 0
+    _boundary_segment_close(m, ref, name + " (module)")
+    sc0 = psdr_cuda.Scene()
+    sc0.load_file(scene_path(name), False)
+    sc0.opts.sppse = 0
+    sc0.configure()
+    with pytest.raises(RuntimeError, match="sppse"):
+        sc0.sample_boundary_segment_direct(G["sample3"][:4])
