@@ -104,6 +104,14 @@ int pb_scene_reseed(pb_ctx *ctx);
 int pb_scene_num_triangles(pb_ctx *ctx);
 /* configured tables, for inspection: 22 floats per triangle (p0 e1 e2 n0 n1 n2 face_normal area; types.h:136-146) */
 int pb_scene_get_triangle_info(pb_ctx *ctx, float *h_out);
+/* the edge tables Scene::configure builds (on the device: csrc/pb_tables.cu), copied to the host for inspection: primary edges of a sensor
+ * (PrimaryEdgeInfo, src/sensor/perspective.cpp:39-111) as 7 floats each (p0.xy, p1.xy, edge_normal.xy, edge_length), secondary edges
+ * (SecondaryEdgeInfo, src/shape/mesh.cpp:251-264, src/scene/scene.cpp:219-235) as 16 floats each (p0, e1, n0, n1, p2, is_boundary);
+ * cmf (optional) receives the running sums of the edge lengths the samplers search. Built only when sppe > 0 / sppse > 0. */
+int pb_scene_num_primary_edges(pb_ctx *ctx, int sensor);
+int pb_scene_get_primary_edges(pb_ctx *ctx, int sensor, float *h_out, float *h_cmf);
+int pb_scene_num_secondary_edges(pb_ctx *ctx);
+int pb_scene_get_secondary_edges(pb_ctx *ctx, float *h_out, float *h_cmf);
 /* unique edges of a mesh, 5 ints each (v0 v1 f0 f1|-1 opposite vertex): src/shape/mesh.cpp:143-203, Mesh.edge_indices() */
 int pb_scene_mesh_num_edges(pb_ctx *ctx, int mesh);
 int pb_scene_mesh_get_edges(pb_ctx *ctx, int mesh, int *h_out);

@@ -27,7 +27,7 @@ SYMBOLS = [
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
     "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad", "pb_render_d_get_state", "pb_render_d_set_state",
-    "pb_sample_boundary_segment_direct", "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
+    "pb_sample_boundary_segment_direct", "pb_scene_num_primary_edges", "pb_scene_get_primary_edges", "pb_scene_num_secondary_edges", "pb_scene_get_secondary_edges", "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
 ]
 
 
@@ -217,6 +217,10 @@ class Context:
         tw = _f(to_world if to_world is not None else np.eye(4))
         return self._id(lib().pb_scene_add_envmap(self.h, r.shape[1], r.shape[0], _p(r), C.c_float(scale), _p(tw)))
 
+    def set_envmap_radiance(self, radiance, scale=1.0):
+        r = _f(radiance)
+        self._chk(lib().pb_scene_set_envmap_radiance(self.h, _p(r), C.c_float(scale)))
+
     def set_envmap_transform(self, left):
         self._chk(lib().pb_scene_set_envmap_transform(self.h, _p(_f(left))))
 
@@ -281,6 +285,20 @@ class Context:
         hits = torch.empty((n, 4), dtype=torch.int32, device=rays.device)
         self._chk(lib().pb_trace(self.h, C.c_int64(n), _dp(rays), _dp(hits), None))
         return hits
+
+    def primary_edges(self, sensor=0):
+        """(n, 7) primary-edge table of a sensor as configure built it (p0.xy p1.xy normal.xy length) and its cmf"""
+        n = self._id(lib().pb_scene_num_primary_edges(self.h, sensor))
+        out, cmf = np.zeros((n, 7), np.float32), np.zeros(n, np.float32)
+        self._chk(lib().pb_scene_get_primary_edges(self.h, sensor, _p(out), _p(cmf)))
+        return out, cmf
+
+    def secondary_edges(self):
+        """(n, 16) secondary-edge table (p0 e1 n0 n1 p2 is_boundary) and its cmf"""
+        n = self._id(lib().pb_scene_num_secondary_edges(self.h))
+        out, cmf = np.zeros((n, 16), np.float32), np.zeros(n, np.float32)
+        self._chk(lib().pb_scene_get_secondary_edges(self.h, _p(out), _p(cmf)))
+        return out, cmf
 
     def sample_boundary_segment_direct(self, sample3):
         """Scene::sample_boundary_segment_direct: (n, 3) CUDA tensor of samples -> (n, 17): p0 edge edge2 p2 n pdf is_valid"""

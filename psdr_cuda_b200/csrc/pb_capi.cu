@@ -91,46 +91,26 @@ static void build_csr(HostMesh &m) {
         }
 }
 
-// Bitmap<3>::eval on the host (bitmap.cpp:43-89), used for the envmap cell masses (envmap.cpp:17-21)
-static float3 host_tex_eval3(const HostTexture &t, float u, float v, bool flip_v) {
-    const float *d = t.data.data();
-    if (t.w == 1 && t.h == 1) return f3(d[0], d[1], d[2]);
-    if (flip_v) v = -v;
-    u -= std::floor(u); v -= std::floor(v);
-    u *= (float)(t.w - 1); v *= (float)(t.h - 1);
-    int px = (int)std::floor(u), py = (int)std::floor(v);
-    const float w1x = u - (float)px, w1y = v - (float)py, w0x = 1.f - w1x, w0y = 1.f - w1y;
-    px = std::min(px, t.w - 2); py = std::min(py, t.h - 2);
-    const int i = py * t.w + px;
-    float o[3];
-    for (int k = 0; k < 3; ++k) {
-        const float v00 = d[i * 3 + k], v10 = d[(i + 1) * 3 + k], v01 = d[(i + t.w) * 3 + k], v11 = d[(i + t.w + 1) * 3 + k];
-        const float a = fmaf(w0x, v00, w1x * v10), b = fmaf(w0x, v01, w1x * v11);
-        o[k] = fmaf(w0y, a, w1y * b);
-    }
-    return f3(o[0], o[1], o[2]);
-}
-
-// EnvironmentMap::configure (envmap.cpp:10-26): luminance * sin(theta) mass of every cell of the 2(w-1) x 2(h-1) grid
+// EnvironmentMap::configure (envmap.cpp:10-26): luminance * sin(theta) mass of every cell of the 2(w-1) x 2(h-1) grid, evaluated and
+// summed on the device (pb_tables.cu); the host contributes the ry values of sin(theta) (libm, as the reference evaluates them)
 static void configure_envmap_distribution(pb_ctx *c, HostEmitter &e) {
     if (!e.env_dirty) return;
     const int w = e.env_radiance.w, h = e.env_radiance.h;
     PB_ASSERT_MSG(w > 1 && h > 1, "Environment map must be larger than 1x1");
     const int rx = (w - 1) << 1, ry = (h - 1) << 1;
     e.env_res[0] = rx; e.env_res[1] = ry;
-    const float ux = 1.f / (float)rx, uy = 1.f / (float)ry;
-    std::vector<float> pmf((size_t)rx * ry), cmf((size_t)rx * ry);
-    for (int i = 0; i < rx; ++i)
-        for (int j = 0; j < ry; ++j) {
-            const float3 col = host_tex_eval3(e.env_radiance, ((float)i + .5f) * ux, ((float)j + .5f) * uy, false);
-            const float theta = ((float)j + .5f) * (kPi / (float)ry);
-            pmf[(size_t)i * ry + j] = (col.x * .2126f + col.y * .7152f + col.z * .0722f) * std::sin(theta);
-        }
-    float acc = 0.f;
-    for (size_t k = 0; k < pmf.size(); ++k) { acc += pmf[k]; cmf[k] = acc; }
-    e.env_sum = acc;
-    e.d_env_pmf.upload(pmf, c->stream); e.d_env_cmf.upload(cmf, c->stream);
+    std::vector<float> sin_theta(ry);
+    for (int j = 0; j < ry; ++j) sin_theta[j] = std::sin(((float)j + .5f) * (kPi / (float)ry));
+    const size_t cells = (size_t)rx * ry;
     e.env_radiance.d.upload(e.env_radiance.data, c->stream);
+    c->d_env_sin.upload(sin_theta, c->stream);
+    e.d_env_pmf.reserve(cells * sizeof(float)); e.d_env_cmf.reserve(cells * sizeof(float));
+    c->d_edge_out.reserve(16 * sizeof(int));
+    launch_envmap_pmf(c->stream, rx, ry, w, h, e.env_radiance.d.as<float>(), c->d_env_sin.as<float>(), e.d_env_pmf.as<float>());
+    launch_seq_cmf(c->stream, (long long)cells, e.d_env_pmf.as<float>(), e.d_env_cmf.as<float>(), c->d_edge_out.as<float>(), nullptr);
+    c->launches += 2;
+    PB_CUDA(cudaMemcpyAsync(&e.env_sum, c->d_edge_out.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(cudaStreamSynchronize(c->stream));   // also: sin_theta is a local
     e.env_dirty = false;
 }
 
@@ -210,9 +190,10 @@ static cudaEvent_t get_event(pb_ctx *c, size_t idx) {
 }
 
 // Primary-edge list of every sensor (perspective.cpp:39-111) and the global secondary-edge table (mesh.cpp:251-264,
-// scene.cpp:219-235). Host code over the downloaded world-space vertices and the triangle table; the cmfs are
-// sequential fp32 sums like the oracle's.
-static void configure_edges(pb_ctx *c) {
+// scene.cpp:219-235), built on the device from the resident triangle table and world-space vertices (pb_tables.cu): nothing but
+// the two counts, the two sums and the per-mesh kept counts (perspective.cpp:67's assertion) come back to the host.
+struct EdgeSrcHost { int v0, v1, f0, f1, v2, mesh; };
+static void configure_edges(pb_ctx *c, bool topo_changed) {
     cudaStream_t st = c->stream;
     const bool need_prim = c->sppe > 0, need_sec = c->sppse > 0;
     std::vector<const float *> vw_ptrs(c->meshes.size());
@@ -221,84 +202,65 @@ static void configure_edges(pb_ctx *c) {
     for (auto &s : c->sensors) { s.num_prim = 0; s.prim_sum = 0.f; }
     c->num_sec = 0; c->sec_sum = 0.f;
     if (!need_prim && !need_sec) return;
-    std::vector<std::vector<float>> vworld(c->meshes.size());
-    for (size_t i = 0; i < c->meshes.size(); ++i) {
-        HostMesh &m = c->meshes[i];
-        if (!(m.flags & 4)) continue;
-        vworld[i].resize(3 * (size_t)m.nv);
-        if (m.nv) PB_CUDA(cudaMemcpyAsync(vworld[i].data(), m.d_vworld.p, vworld[i].size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
-    PB_CUDA(cudaStreamSynchronize(st));
-    auto tri_p0 = [&](int t) { const float *q = &c->h_tri[(size_t)t * 32]; return f3(q[0], q[1], q[2]); };
-    auto tri_fn = [&](int t) { const float *q = &c->h_tri[(size_t)t * 32 + 24]; return f3(q[0], q[1], q[2]); };
-    auto vert = [&](size_t mi, int v) { const float *q = &vworld[mi][3 * (size_t)v]; return f3(q[0], q[1], q[2]); };
-    if (need_prim) {
-        for (auto &s : c->sensors) {
-            std::vector<PrimEdgeRec> recs;
-            const float3 cam = s.rec.camera_pos;
-            for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
-                const HostMesh &m = c->meshes[mi];
-                if (!(m.flags & 4)) continue;
-                size_t kept = 0;
-                for (size_t e = 0; e < m.edges.size(); e += 5) {
-                    const int *ed = &m.edges[e];
-                    const bool interior = ed[3] >= 0;
-                    const float3 e0 = normalize(cam - tri_p0(m.face_offset + ed[2])), n0 = tri_fn(m.face_offset + ed[2]);
-                    float3 e1 = f3(0.f), n1 = f3(0.f);
-                    if (interior) { e1 = normalize(cam - tri_p0(m.face_offset + ed[3])); n1 = tri_fn(m.face_offset + ed[3]); }
-                    bool keep;
-                    if (m.flags & 1) keep = !(interior && ((dot(e0, n0) < kEpsilon && dot(e1, n1) < kEpsilon) || dot(n0, n1) > 1.f - kEpsilon));
-                    else keep = !interior || ((dot(e0, n0) > kEpsilon) != (dot(e1, n1) > kEpsilon));
-                    if (!keep) continue;
-                    ++kept;
-                    const float3 q0 = transform_pos(s.rec.world_to_sample, vert(mi, ed[0])), q1 = transform_pos(s.rec.world_to_sample, vert(mi, ed[1]));
-                    PrimEdgeRec r;
-                    r.p0x = q0.x; r.p0y = q0.y; r.p1x = q1.x; r.p1y = q1.y;
-                    const float ex = q1.x - q0.x, ey = q1.y - q0.y;
-                    const float len = sqrt_rn(fma_rn(ex, ex, mul_rn(ey, ey)));
-                    r.nx = -(ey / len); r.ny = ex / len; r.len = len; r.pad = 0.f;
-                    r.mesh = (int)mi; r.v0 = ed[0]; r.v1 = ed[1]; r.pad2 = 0;
-                    recs.push_back(r);
-                }
-                PB_ASSERT_MSG(kept > 0, "A mesh with enabled edges contributes no primary edge (perspective.cpp:67)");
-            }
-            std::vector<float> pmf(recs.size()), cmf(recs.size());
-            float acc = 0.f;
-            for (size_t i = 0; i < recs.size(); ++i) { pmf[i] = recs[i].len; acc += pmf[i]; cmf[i] = acc; }
-            s.num_prim = (int)recs.size(); s.prim_sum = acc;
-            s.d_prim.upload(recs, st); s.d_prim_pmf.upload(pmf, st); s.d_prim_cmf.upload(cmf, st);
-        }
-    }
-    if (need_sec) {
-        std::vector<SecEdgeRec> recs;
-        std::vector<float> pmf, cmf;
-        float acc = 0.f;
+    // edge topology of every mesh with enabled edges, in mesh order (uploaded when the topology or the flags change)
+    std::vector<int> edge_sig;
+    for (const HostMesh &m : c->meshes) { edge_sig.push_back((m.flags & 4) ? (int)m.edges.size() : -1); edge_sig.push_back(m.nf); }
+    if (topo_changed || edge_sig != c->edge_sig || !c->d_edge_src.p) {
+        std::vector<EdgeSrcHost> src;
         for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
             const HostMesh &m = c->meshes[mi];
             if (!(m.flags & 4)) continue;
-            for (size_t e = 0; e < m.edges.size(); e += 5) {
-                const int *ed = &m.edges[e];
-                const bool boundary = ed[3] < 0;
-                const float3 p0 = vert(mi, ed[0]), e1 = vert(mi, ed[1]) - p0, n0 = tri_fn(m.face_offset + ed[2]);
-                const float3 n1 = boundary ? f3(0.f) : tri_fn(m.face_offset + ed[3]), p2 = vert(mi, ed[4]);
-                if (!(dot(n0, n1) < 1.f - kEdgeEpsilon)) continue;   // mesh.cpp:262-263
-                SecEdgeRec r;
-                float fm, f0, f1;
-                const int im = (int)mi;
-                std::memcpy(&fm, &im, 4); std::memcpy(&f0, &ed[0], 4); std::memcpy(&f1, &ed[1], 4);
-                r.a = make_float4(p0.x, p0.y, p0.z, boundary ? 1.f : 0.f);
-                r.b = make_float4(e1.x, e1.y, e1.z, fm);
-                r.c = make_float4(n0.x, n0.y, n0.z, f0);
-                r.d = make_float4(n1.x, n1.y, n1.z, f1);
-                r.e = make_float4(p2.x, p2.y, p2.z, 0.f);
-                recs.push_back(r);
-                const float len = norm(e1);
-                pmf.push_back(len); acc += len; cmf.push_back(acc);
-            }
+            for (size_t e = 0; e < m.edges.size(); e += 5) src.push_back({m.edges[e], m.edges[e + 1], m.edges[e + 2], m.edges[e + 3], m.edges[e + 4], (int)mi});
         }
-        c->num_sec = (int)recs.size(); c->sec_sum = acc;
-        c->d_sec.upload(recs, st); c->d_sec_pmf.upload(pmf, st); c->d_sec_cmf.upload(cmf, st);
+        c->num_edge_src = (int)src.size();
+        c->d_edge_src.upload(src, st);
+        PB_CUDA(cudaStreamSynchronize(st));   // src is a local
+        c->edge_sig = edge_sig;
     }
+    const int E = c->num_edge_src;
+    if (E == 0) return;
+    const int tiles = (E + 4095) / 4096, nm = (int)c->meshes.size();
+    c->d_edge_flags.reserve((size_t)E);
+    c->d_edge_local.reserve((size_t)E * sizeof(int));
+    c->d_edge_tiles.reserve((size_t)tiles * sizeof(int));
+    c->d_edge_out.reserve((size_t)(nm + 4) * sizeof(int));   // [0] count, [1] sum (float), [2..] kept edges per mesh
+    int *out = c->d_edge_out.as<int>();
+    std::vector<int> h_out(nm + 4);
+    const float *const *vw = c->d_mesh_vworld.as<const float *>();
+    if (need_prim) {
+        for (auto &s : c->sensors) {
+            s.d_prim.reserve((size_t)E * sizeof(PrimEdgeRec)); s.d_prim_pmf.reserve((size_t)E * sizeof(float)); s.d_prim_cmf.reserve((size_t)E * sizeof(float));
+            launch_primary_edge_table(st, E, c->d_edge_src.p, c->view, vw, s.rec.camera_pos, s.rec.world_to_sample, c->d_edge_flags.as<unsigned char>(),
+                                      c->d_edge_local.as<int>(), c->d_edge_tiles.as<int>(), out + 2, nm, s.d_prim.as<PrimEdgeRec>(), s.d_prim_pmf.as<float>(),
+                                      s.d_prim_cmf.as<float>(), out, reinterpret_cast<float *>(out + 1));
+            c->launches += 6;
+            PB_CUDA(cudaMemcpyAsync(h_out.data(), out, (size_t)(nm + 2) * sizeof(int), cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+            for (int mi = 0; mi < nm; ++mi)
+                PB_ASSERT_MSG(!(c->meshes[mi].flags & 4) || c->meshes[mi].edges.empty() || h_out[2 + mi] > 0, "A mesh with enabled edges contributes no primary edge (perspective.cpp:67)");
+            s.num_prim = h_out[0];
+            std::memcpy(&s.prim_sum, &h_out[1], 4);
+        }
+    }
+    if (need_sec) {
+        c->d_sec.reserve((size_t)E * sizeof(SecEdgeRec)); c->d_sec_pmf.reserve((size_t)E * sizeof(float)); c->d_sec_cmf.reserve((size_t)E * sizeof(float));
+        launch_secondary_edge_table(st, E, c->d_edge_src.p, c->view, vw, c->d_edge_flags.as<unsigned char>(), c->d_edge_local.as<int>(), c->d_edge_tiles.as<int>(),
+                                    c->d_sec.as<SecEdgeRec>(), c->d_sec_pmf.as<float>(), c->d_sec_cmf.as<float>(), out, reinterpret_cast<float *>(out + 1));
+        c->launches += 5;
+        PB_CUDA(cudaMemcpyAsync(h_out.data(), out, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        c->num_sec = h_out[0];
+        std::memcpy(&c->sec_sum, &h_out[1], 4);
+    }
+}
+
+// host copy of the triangle table, fetched when something on the host needs it (BVH build, pb_scene_get_triangle_info)
+static void download_triangle_table(pb_ctx *c) {
+    if (c->h_tri_valid) return;
+    c->h_tri.resize((size_t)c->num_tri * 32);
+    if (c->num_tri) PB_CUDA(cudaMemcpyAsync(c->h_tri.data(), c->arena_tri(), (size_t)c->num_tri * sizeof(TriRec), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(cudaStreamSynchronize(c->stream));
+    c->h_tri_valid = true;
 }
 
 static void configure(pb_ctx *c) {
@@ -371,20 +333,25 @@ static void configure(pb_ctx *c) {
     };
     const size_t num_regular = c->meshes.size() - (c->has_bound_mesh ? 1 : 0);
     for (size_t i = 0; i < num_regular; ++i) preprocess(i);
-    c->h_tri.resize((size_t)total * 32);
+    c->h_tri_valid = false;
     const int regular_tris = total - (c->has_bound_mesh ? 12 : 0);
-    if (regular_tris) PB_CUDA(cudaMemcpyAsync(c->h_tri.data(), c->arena_tri(), (size_t)regular_tris * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
+    // bounds of the regular geometry, reduced on the device (6 floats come back)
+    c->d_bounds.reserve(6 * sizeof(float));
+    auto device_bounds = [&](int ntri, float *lo, float *hi) {
+        float lohi[6];
+        launch_tri_bounds(st, ntri, c->arena_tri(), c->d_bounds.as<float>());
+        c->launches++;
+        PB_CUDA(cudaMemcpyAsync(lohi, c->d_bounds.p, sizeof(lohi), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 3; ++k) { lo[k] = lohi[k]; hi[k] = lohi[3 + k]; }
+    };
+    float reg_lo[3], reg_hi[3];
+    device_bounds(regular_tris, reg_lo, reg_hi);
     if (c->has_bound_mesh) {
         // scene box: all vertices + camera positions, upper initialised to the smallest positive float (scene.cpp:88-89 quirk),
         // grown by 5 % of its smallest extent (scene.cpp:136-137)
         float lo[3], hi[3];
-        for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<float>::max(); hi[k] = std::numeric_limits<float>::min(); }
-        for (int t = 0; t < regular_tris; ++t) {
-            const float *q = &c->h_tri[(size_t)t * 32];
-            for (int a = 0; a < 3; ++a)
-                for (float v : {q[a], q[a] + q[4 + a], q[a] + q[8 + a]}) { lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
-        }
+        for (int k = 0; k < 3; ++k) { lo[k] = std::min(reg_lo[k], std::numeric_limits<float>::max()); hi[k] = std::max(reg_hi[k], std::numeric_limits<float>::min()); }
         for (auto &s : c->sensors) {
             const float p[3] = {s.rec.camera_pos.x, s.rec.camera_pos.y, s.rec.camera_pos.z};
             for (int a = 0; a < 3; ++a) { lo[a] = p[a] < lo[a] ? p[a] : lo[a]; hi[a] = p[a] > hi[a] ? p[a] : hi[a]; }
@@ -396,30 +363,31 @@ static void configure(pb_ctx *c) {
         for (int i = 0; i < 8; ++i) for (int j = 0; j < 3; ++j) b.verts[3 * i + j] = (i & (1 << j)) ? hi[j] : lo[j];
         b.verts_dirty = true;
         preprocess(c->meshes.size() - 1);
-        PB_CUDA(cudaMemcpyAsync(c->h_tri.data() + (size_t)regular_tris * 32, c->arena_tri() + regular_tris, 12 * sizeof(TriRec), cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaStreamSynchronize(st));
     }
-    // face-area pmf / cmf per emitter mesh (mesh.cpp:238-249): sequential fp32 sums, as the oracle
-    for (auto &m : c->meshes) {
-        if (m.emitter < 0) continue;
-        std::vector<float> cmf(m.nf);
-        float acc = 0.f;
-        for (int f = 0; f < m.nf; ++f) { acc += c->h_tri[(size_t)(m.face_offset + f) * 32 + 3]; cmf[f] = acc; }
-        m.total_area = acc; m.face_sum = acc;
-        m.inv_total_area = 1.f / acc;
-        m.d_face_cmf.upload(cmf, st);
+    // face-area pmf / cmf per emitter mesh (mesh.cpp:238-249): sequential fp32 sums as the oracle's, on the device
+    {
+        int ne = 0;
+        for (auto &m : c->meshes) if (m.emitter >= 0) ++ne;
+        c->d_area_sums.reserve((size_t)std::max(1, ne) * sizeof(float));
+        int k = 0;
+        for (auto &m : c->meshes) {
+            if (m.emitter < 0) continue;
+            m.d_face_cmf.reserve((size_t)std::max(1, m.nf) * sizeof(float));
+            launch_seq_cmf(st, m.nf, m.d_face_area.as<float>(), m.d_face_cmf.as<float>(), c->d_area_sums.as<float>() + k++, nullptr);
+            c->launches++;
+        }
+        std::vector<float> sums(std::max(1, ne));
+        if (ne) { PB_CUDA(cudaMemcpyAsync(sums.data(), c->d_area_sums.p, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost, st)); PB_CUDA(cudaStreamSynchronize(st)); }
+        k = 0;
+        for (auto &m : c->meshes) {
+            if (m.emitter < 0) continue;
+            m.total_area = sums[k]; m.face_sum = sums[k]; m.inv_total_area = 1.f / sums[k]; ++k;
+        }
     }
     // BVH over all triangles (replaces optixAccelBuild, optix.h:277-340)
     {
-        for (int k = 0; k < 3; ++k) { c->scene_lo[k] = std::numeric_limits<float>::max(); c->scene_hi[k] = -std::numeric_limits<float>::max(); }
-        for (int t = 0; t < total; ++t) {
-            const float *q = &c->h_tri[(size_t)t * 32];
-            for (int a = 0; a < 3; ++a) {
-                const float v0 = q[a], v1 = q[a] + q[4 + a], v2 = q[a] + q[8 + a];
-                c->scene_lo[a] = std::min(c->scene_lo[a], std::min(v0, std::min(v1, v2)));
-                c->scene_hi[a] = std::max(c->scene_hi[a], std::max(v0, std::max(v1, v2)));
-            }
-        }
+        if (c->has_bound_mesh) device_bounds(total, c->scene_lo, c->scene_hi);
+        else for (int k = 0; k < 3; ++k) { c->scene_lo[k] = reg_lo[k]; c->scene_hi[k] = reg_hi[k]; }
         if (total == 0) for (int k = 0; k < 3; ++k) { c->scene_lo[k] = 0.f; c->scene_hi[k] = 1.f; }
         std::vector<int> sig;
         for (const HostMesh &m : c->meshes) sig.push_back(m.nf);
@@ -434,6 +402,7 @@ static void configure(pb_ctx *c) {
             c->launches += 1 + (int64_t)c->bvh_level_off.size() - 1;
             c->bvh_refits++; c->bvh_refit_count++;
         } else {
+        download_triangle_table(c);   // the binned-SAH build runs on the host (first build / topology change only)
         std::vector<float> geo(9 * (size_t)total);
         for (int t = 0; t < total; ++t)
             for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) geo[9 * (size_t)t + 3 * k + a] = c->h_tri[(size_t)t * 32 + 4 * k + a];
@@ -519,6 +488,7 @@ static void configure(pb_ctx *c) {
         }
     }
     c->d_emitters.upload(er, st);
+    c->h_emitters = er;
     // mesh + bsdf tables
     std::vector<MeshRec> mr(c->meshes.size());
     for (size_t i = 0; i < mr.size(); ++i) {
@@ -529,6 +499,7 @@ static void configure(pb_ctx *c) {
         mr[i].uv_faces = (m.flags & 2) ? m.d_uv_faces.as<int>() : nullptr; mr[i].uv_grad = nullptr;
     }
     c->d_meshes.upload(mr, st);
+    c->h_meshrecs = mr;
     std::vector<BsdfRec> br(c->bsdfs.size());
     for (size_t i = 0; i < br.size(); ++i) {
         HostBsdf &b = c->bsdfs[i];
@@ -542,6 +513,7 @@ static void configure(pb_ctx *c) {
         }
     }
     c->d_bsdfs.upload(br, st);
+    c->h_bsdfs = br;
     PB_CUDA(cudaStreamSynchronize(st));
     SceneView &V = c->view;
     V.tri = c->arena_tri(); V.leaf = c->arena_leaf(); V.nodes = c->arena_nodes(); V.nodes_c = c->arena_nodes_c();
@@ -553,7 +525,7 @@ static void configure(pb_ctx *c) {
     for (const HostBsdf &hb : c->bsdfs) if (hb.type != PB_BSDF_DIFFUSE) V.simple = 0;
     V.tri_grad = nullptr;
     V.tri_tangent = nullptr; V.jvp_acc = nullptr; V.jvp_image = nullptr; V.jvp_channel = 0; V.sensor_grad = nullptr;
-    configure_edges(c);
+    configure_edges(c, any_topo);
     // gradient layout
     c->grad_segments.clear();
     int64_t off = 0;
@@ -886,6 +858,10 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             use_retained = true; run_forward = false;
         }
     }
+    if (use_retained && run_forward) {   // the store may not fit next to what else lives on the device: fall back to re-tracing in the VJP
+        try { size_store(c->retained, total, D, R, B); }
+        catch (const Error &) { cudaGetLastError(); c->retained.release(); use_retained = false; }
+    }
     const bool keep = use_retained || mode == MODE_VJP;   // every event has its own slot
     EventStore &S = use_retained ? c->retained : c->scratch;
     size_store(S, use_retained ? total : B, keep ? D : 2, R, B);
@@ -897,9 +873,9 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     P.tile_rows = tile_rows; P.rank = c->rank; P.world = c->world;
     P.jump0 = make_jump(base);
     if (mode == MODE_VJP) {   // BSDF table whose textures point at their gradient segments
-        std::vector<BsdfRec> br(c->bsdfs.size());
-        PB_CUDA(cudaMemcpyAsync(br.data(), c->d_bsdfs.p, br.size() * sizeof(BsdfRec), cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaStreamSynchronize(st));
+        // the tables of configure with their gradient pointers filled in: patched on the host copies, uploaded asynchronously (no read-back)
+        std::vector<BsdfRec> &br = c->h_bsdfs_grad;
+        br = c->h_bsdfs;
         for (const GradSegment &g : c->grad_segments)
             if (g.kind == PB_PARAM_BSDF_TEXTURE) br[g.id].tex[g.slot].grad = d_grad + g.offset;   // forward mode: the tangent, read only
         c->d_bsdfs_grad.upload(br, st);
@@ -908,9 +884,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             bool any_uv = false;
             for (const GradSegment &g : c->grad_segments) any_uv = any_uv || g.kind == PB_PARAM_MESH_UV;
             if (any_uv) {
-                std::vector<MeshRec> mr(c->meshes.size());
-                PB_CUDA(cudaMemcpyAsync(mr.data(), c->d_meshes.p, mr.size() * sizeof(MeshRec), cudaMemcpyDeviceToHost, st));
-                PB_CUDA(cudaStreamSynchronize(st));
+                std::vector<MeshRec> &mr = c->h_meshrecs_grad;
+                mr = c->h_meshrecs;
                 for (const GradSegment &g : c->grad_segments) if (g.kind == PB_PARAM_MESH_UV) mr[g.id].uv_grad = d_grad + g.offset;
                 c->d_meshes_grad.upload(mr, st);
                 P.S.meshes = c->d_meshes_grad.as<MeshRec>();
@@ -920,9 +895,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         for (const GradSegment &g : c->grad_segments)
             env_grad = env_grad || g.kind == PB_PARAM_ENVMAP_RADIANCE || g.kind == PB_PARAM_ENVMAP_SCALE || g.kind == PB_PARAM_ENVMAP_TRANSFORM;
         if (env_grad) {   // emitter table whose environment map points at its gradient segments
-            std::vector<EmitterRec> er(c->emitters.size());
-            PB_CUDA(cudaMemcpyAsync(er.data(), c->d_emitters.p, er.size() * sizeof(EmitterRec), cudaMemcpyDeviceToHost, st));
-            PB_CUDA(cudaStreamSynchronize(st));
+            std::vector<EmitterRec> &er = c->h_emitters_grad;
+            er = c->h_emitters;
             for (const GradSegment &g : c->grad_segments) {
                 if (g.kind == PB_PARAM_ENVMAP_RADIANCE) er[g.id].env_radiance.grad = d_grad + g.offset;
                 if (g.kind == PB_PARAM_ENVMAP_SCALE) er[g.id].env_scale_grad = d_grad + g.offset;
@@ -1258,6 +1232,10 @@ int pb_scene_add_mesh(pb_ctx *c, int nv, int nf, const float *verts, const int *
     return guard_id(c, [&] {
         PB_ASSERT_MSG(nv >= 0 && nf >= 0 && (nv == 0 || verts) && (nf == 0 || faces), "Invalid mesh buffers");
         PB_ASSERT_MSG(bsdf >= -1 && bsdf < (int)c->bsdfs.size(), "Unknown BSDF id");
+        if (c->has_bound_mesh) {   // the environment map's bounding box is always the last mesh (scene.cpp:135-180): take it off, configure re-creates it
+            c->meshes.pop_back(); c->has_bound_mesh = false;
+            if (c->emitter_env >= 0) c->emitters[c->emitter_env].mesh = -1;
+        }
         c->meshes.emplace_back();
         HostMesh &m = c->meshes.back();
         try {
@@ -1363,6 +1341,8 @@ int pb_scene_num_triangles(pb_ctx *c) { return c->num_tri; }
 int pb_scene_get_triangle_info(pb_ctx *c, float *out) {
     return guard(c, [&] {
         PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+        PB_CUDA(cudaSetDevice(c->device));
+        download_triangle_table(c);
         for (int t = 0; t < c->num_tri; ++t) {
             const float *q = &c->h_tri[(size_t)t * 32];
             float *o = out + 22 * (size_t)t;
@@ -1372,6 +1352,44 @@ int pb_scene_get_triangle_info(pb_ctx *c, float *out) {
                 o[18 + a] = q[24 + a];                                              // face normal
             }
             o[21] = q[3];
+        }
+    });
+}
+/* edge tables as configure built them (device -> host copies for inspection / parity tests) */
+int pb_scene_num_primary_edges(pb_ctx *c, int sensor) {
+    if (!c || !c->ready || sensor < 0 || sensor >= (int)c->sensors.size()) return -1;
+    return c->sensors[sensor].num_prim;
+}
+int pb_scene_get_primary_edges(pb_ctx *c, int sensor, float *out, float *cmf_out) {   // [n][7]: p0.xy p1.xy edge_normal.xy edge_length; cmf [n]
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+        PB_ASSERT_MSG(sensor >= 0 && sensor < (int)c->sensors.size(), "Invalid sensor id!");
+        const HostSensor &s = c->sensors[sensor];
+        PB_CUDA(cudaSetDevice(c->device));
+        std::vector<PrimEdgeRec> recs(s.num_prim);
+        if (s.num_prim) PB_CUDA(cudaMemcpyAsync(recs.data(), s.d_prim.p, recs.size() * sizeof(PrimEdgeRec), cudaMemcpyDeviceToHost, c->stream));
+        if (s.num_prim && cmf_out) PB_CUDA(cudaMemcpyAsync(cmf_out, s.d_prim_cmf.p, recs.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const PrimEdgeRec &r = recs[i];
+            const float v[7] = {r.p0x, r.p0y, r.p1x, r.p1y, r.nx, r.ny, r.len};
+            std::copy(v, v + 7, out + 7 * i);
+        }
+    });
+}
+int pb_scene_num_secondary_edges(pb_ctx *c) { return (c && c->ready) ? c->num_sec : -1; }
+int pb_scene_get_secondary_edges(pb_ctx *c, float *out, float *cmf_out) {   // [n][16]: p0 e1 n0 n1 p2 is_boundary; cmf [n]
+    return guard(c, [&] {
+        PB_ASSERT_MSG(c->ready, "Input scene must be configured!");
+        PB_CUDA(cudaSetDevice(c->device));
+        std::vector<SecEdgeRec> recs(c->num_sec);
+        if (c->num_sec) PB_CUDA(cudaMemcpyAsync(recs.data(), c->d_sec.p, recs.size() * sizeof(SecEdgeRec), cudaMemcpyDeviceToHost, c->stream));
+        if (c->num_sec && cmf_out) PB_CUDA(cudaMemcpyAsync(cmf_out, c->d_sec_cmf.p, recs.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const SecEdgeRec &r = recs[i];
+            const float v[16] = {r.a.x, r.a.y, r.a.z, r.b.x, r.b.y, r.b.z, r.c.x, r.c.y, r.c.z, r.d.x, r.d.y, r.d.z, r.e.x, r.e.y, r.e.z, r.a.w};
+            std::copy(v, v + 16, out + 16 * i);
         }
     });
 }

@@ -28,6 +28,7 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
     ~DevBuf() { if (p) cudaFree(p); }
     void reserve(size_t n) {   // grow-only
         if (n <= bytes) return;
@@ -110,6 +111,7 @@ struct GradSegment { int kind, id, slot; int64_t offset, count; };
 struct EventStore {
     DevBuf hit0, rad, rays;
     std::vector<DevBuf> pos, hits, thr;
+    void release() { hit0.release(); rad.release(); rays.release(); pos.clear(); hits.clear(); thr.clear(); }
 };
 
 }  // namespace pb
@@ -148,7 +150,17 @@ struct pb_ctx {
     pb::BvhNodeC *arena_nodes_c() const { return reinterpret_cast<pb::BvhNodeC *>(static_cast<char *>(d_scene_arena.p) + arena_tri_bytes + arena_node_bytes + arena_leaf_bytes); }
     int l2_persist = 1;
     pb::DevBuf d_order, d_meshes, d_bsdfs, d_emitters, d_emitter_cmf, d_emitter_pmf;
-    std::vector<float> h_tri;   // host copy of the triangle table (BVH build, inspection)
+    // host copies of the small device tables (configure) and their gradient-pointer variants (VJP): persistent, so that the
+    // asynchronous uploads never read freed memory and the VJP never reads the tables back
+    std::vector<pb::BsdfRec> h_bsdfs, h_bsdfs_grad;
+    std::vector<pb::MeshRec> h_meshrecs, h_meshrecs_grad;
+    std::vector<pb::EmitterRec> h_emitters, h_emitters_grad;
+    std::vector<float> h_tri;   // host copy of the triangle table, fetched on demand (host BVH build, inspection)
+    bool h_tri_valid = false;
+    // device-side configure (pb_tables.cu): edge topology of all meshes with enabled edges + scratch
+    pb::DevBuf d_edge_src, d_edge_flags, d_edge_local, d_edge_tiles, d_edge_out, d_bounds, d_area_sums, d_env_sin;
+    int num_edge_src = 0;
+    std::vector<int> edge_sig;
     float emitter_sum = 0.f;
     pb::SceneView view;
     // wavefront buffers

@@ -55,6 +55,15 @@ void launch_mesh_tangent(cudaStream_t st, int nv, int nf, int face_offset, const
                          const int *faces, const int *csr_off, const int *csr_face, const float4 *fcross, float *vworld_t, float4 *fcross_t, float *vnormal_t,
                          float *tri_tangent);
 void launch_bvh_refit(cudaStream_t st, BvhNode *nodes, float *boxes, const LeafTri *leaf, const int *level_off, int num_levels, float extent);
+// device-side tables of Scene::configure (pb_tables.cu)
+void launch_seq_cmf(cudaStream_t st, long long n, const float *pmf, float *cmf, float *sum_out, const int *n_dev);
+void launch_primary_edge_table(cudaStream_t st, int n, const void *edge_src, const SceneView &S, const float *const *vworld, float3 cam, const Mat4 &w2s,
+                               unsigned char *flags, int *local, int *tile_sum, int *mesh_kept, int num_meshes, PrimEdgeRec *recs, float *pmf, float *cmf,
+                               int *count_out, float *sum_out);
+void launch_secondary_edge_table(cudaStream_t st, int n, const void *edge_src, const SceneView &S, const float *const *vworld, unsigned char *flags, int *local,
+                                 int *tile_sum, SecEdgeRec *recs, float *pmf, float *cmf, int *count_out, float *sum_out);
+void launch_envmap_pmf(cudaStream_t st, int rx, int ry, int w, int h, const float *texel, const float *sin_theta, float *pmf);
+void launch_tri_bounds(cudaStream_t st, int n, const TriRec *tri, float *lohi);
 void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 

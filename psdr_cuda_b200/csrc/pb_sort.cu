@@ -132,17 +132,18 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
                          unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (n <= 0) return;
-    static int mode_set = 5;   // debug switch only (process-wide like the other pb_debug_set keys; the default needs no upload)
-    if (mode_set != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); mode_set = g_sort_mode; }
+    {   // debug switch (process-wide like the other pb_debug_set keys); __constant__ memory is per device, so is the record of what it holds
+        static int mode_set[64];
+        static bool init = false;
+        if (!init) { for (int &m : mode_set) m = 5; init = true; }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int &cur = mode_set[dev & 63];
+        if (cur != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); cur = g_sort_mode; }
+    }
     const float3 inv_ext = f3(1.f / fmaxf(hi.x - lo.x, 1e-20f), 1.f / fmaxf(hi.y - lo.y, 1e-20f), 1.f / fmaxf(hi.z - lo.z, 1e-20f));
     cudaMemsetAsync(hist, 0, (kSortBins + 2) * sizeof(unsigned), st);   // hist must hold kSortBins + 2 counters
     const int cnt_bytes = (kSortBins + 1) * (int)sizeof(unsigned);
-    static bool sort_attr = false;
-    if (!sort_attr) {
-        cudaFuncSetAttribute(k_sort_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, cnt_bytes);
-        cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, cnt_bytes);
-        sort_attr = true;
-    }
     k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist, keys);
     k_sort_scan<<<1, 1024, 0, st>>>(hist, active_total);
     k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);

@@ -119,12 +119,12 @@ PB_D Hit trace_closest_c(const BvhNodeC *__restrict__ nodes, const LeafTri *__re
 // ---- persistent streaming traversal -------------------------------------------------------------------------------------
 // One-ray-per-thread kernels leave 13 of 32 lanes idle per instruction on this workload (ncu): a warp lasts as long as its longest
 // ray, and lanes that reached a leaf wait for lanes still descending. Here a warp is a persistent worker over the sorted ray
-// stream: it grabs chunks of kStreamChunk consecutive (hence similar) rays with one atomic, stages them 32 at a time in shared memory
+// stream: it grabs chunks of up to kStreamChunk consecutive (hence similar) rays with one atomic, stages them 32 at a time in shared memory
 // with cp.async (the gather through the sort permutation is off the critical path: no register scoreboard waits on it), and hands a
 // staged ray to every lane whose ray has terminated. Lanes are inner-node, triangle or idle lanes; the warp alternates between
 // node steps (while at least kNodeMin lanes descend) and single-triangle steps, so both instruction streams run nearly full.
 constexpr int kStreamRing = 64;      // staged rays per warp (two blocks of 32)
-constexpr unsigned kStreamChunk = 256;    // rays per atomic grab
+constexpr unsigned kStreamChunk = 256;    // most rays per atomic grab
 
 PB_D void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -164,11 +164,20 @@ __global__ void __launch_bounds__(128, MINB) k_trace_stream(StreamArgs A) {
         blk_cnt = 0;
         if (exhausted) return;
         if (chunk_next >= chunk_end) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(A.counter, kStreamChunk);
+            // guided self-scheduling: chunks shrink with the work that is left (kStreamChunk rays while there is plenty, 32 at the end),
+            // so the last warps finish together; with fixed 256-ray chunks the tail was 10 % of a 12 M-ray launch (one GPU's share of
+            // an 8-GPU job). The counter is read without ordering: a stale value only changes the size asked for.
+            unsigned base = 0, size = 0;
+            if (lane == 0) {
+                const unsigned cur = *reinterpret_cast<volatile unsigned *>(A.counter);
+                const unsigned rem = cur < n ? n - cur : 0u;
+                size = min(kStreamChunk, max(32u, (rem / (gridDim.x * 8u)) & ~31u));
+                base = atomicAdd(A.counter, size);
+            }
             base = __shfl_sync(full, base, 0);
+            size = __shfl_sync(full, size, 0);
             if (base >= n) { exhausted = true; return; }
-            chunk_next = base; chunk_end = min(base + kStreamChunk, n);
+            chunk_next = base; chunk_end = min(base + size, n);
         }
         blk_cnt = min(32u, chunk_end - chunk_next);
         if ((unsigned)lane < blk_cnt) p_src = __ldcs(A.perm + chunk_next + lane);

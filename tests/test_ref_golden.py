@@ -5,9 +5,11 @@ case: renderC images (among them BASELINE.json's configs[0] at full size, 128x12
 <= 1e-4), field images, and renderD forward-mode derivative images for albedo, rough-conductor roughness, envmap scale and
 vertex translation through the interior, primary-edge and secondary-edge terms.
 
-Tolerance: per pixel 2e-4 (images) / 1e-3 (derivative images) of the image maximum, for all but a bounded share of the non-zero pixels:
-the knife-edge lanes of tests/test_ref_render.py (last-bit differences in the camera ray flip a grazing shadow ray or a primary-edge ray
-pair 1e-5 off a silhouette). The projections (image sums) must agree to what those pixels can carry."""
+Tolerance: per pixel 2e-4 (images) / 1e-3 (derivative images) of the image maximum, for all but a bounded share of the non-zero pixels
+(2 %; 3-5 % for the boundary terms and the vertex translation): the knife-edge lanes of tests/test_ref_render.py (last-bit differences in
+the camera ray flip a grazing shadow ray or a primary-edge ray pair 1e-5 off a silhouette; such a lane is all-or-nothing). Measured shares
+through the oracle: primary edges 2 of 118 pixels, secondary 2 of 203, translation 3 of 122. The projections (image sums) must agree to what
+those pixels can carry."""
 import importlib.util
 import os
 
@@ -21,7 +23,7 @@ gen = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(gen)
 CASES = gen.cases()
 # allowed share of non-zero pixels over tolerance (image, derivative image)
-OUTLIERS = {"d_cbox_primary": 0.25, "d_cbox_secondary": 0.08, "d_env_secondary": 0.08}
+OUTLIERS = {"d_cbox_primary": 0.05, "d_cbox_secondary": 0.03, "d_cbox_translate": 0.04}
 
 
 @pytest.fixture(scope="module")
@@ -116,7 +118,7 @@ def test_cuda_matches_reference_source_goldens(label, golden):
         dimg = ctx.render_d_jvp(I, torch.from_numpy(u.reshape(-1)).cuda()).cpu().numpy()
         if np.abs(golden[label]).max() > 0:
             close(img, golden[label], 2e-4, 0.01, label)
-        close(dimg, golden[label + "_t"], 1e-3, 1.5 * OUTLIERS.get(label, 0.02), label + " derivative")
+        close(dimg, golden[label + "_t"], 1e-3, OUTLIERS.get(label, 0.02), label + " derivative")
     ctx.close()
 
 
