@@ -69,7 +69,11 @@ int pb_ctx_set_shard_mode(pb_ctx *ctx, int mode, int tile_rows);
  * depth-5 path) when they fit in `bytes` (default 64 GiB of the 180 GB HBM3e), so that pb_render_d_vjp runs only the
  * adjoint kernels; otherwise the VJP re-traces the forward pass batch by batch. 0 disables retention. */
 int pb_ctx_set_retain_limit(pb_ctx *ctx, int64_t bytes);
-/* run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream) instead of the context's own */
+/* Run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream) instead of the context's own.
+ * STREAM CONTRACT: every kernel and copy of a call is enqueued on the context's stream and the call returns after synchronising it. A fresh
+ * context owns a private cudaStreamNonBlocking stream, which is NOT ordered against work the caller has in flight elsewhere: buffers passed
+ * in (d_image, d_dLdI, d_grad, device-pointer setters) must be complete before the call, or — the normal case with torch / CuPy tensors —
+ * the caller passes the stream that produces and consumes them here, once or whenever it changes. */
 int pb_ctx_set_stream(pb_ctx *ctx, void *cuda_stream);
 
 /* ---- scene description: what SceneLoader::load_scene builds (src/scene/scene_loader.cpp:208-242) ------------- */
@@ -104,6 +108,15 @@ int pb_scene_reseed(pb_ctx *ctx);
 int pb_scene_num_triangles(pb_ctx *ctx);
 /* configured tables, for inspection: 22 floats per triangle (p0 e1 e2 n0 n1 n2 face_normal area; types.h:136-146) */
 int pb_scene_get_triangle_info(pb_ctx *ctx, float *h_out);
+/* the two setters above from DEVICE pointers: an optimiser that keeps its parameters on the GPU updates the scene without a host round trip
+ * (the reference's Enoki arrays live on the device too: `mesh.vertex_positions = u`, examples/utils/adam.py:63); the copies are enqueued on the
+ * context's stream. Texture resolution stays what it was. pb_scene_get_mesh_vertices reads the current positions back (host buffer, 3 nv floats). */
+int pb_scene_set_mesh_vertices_device(pb_ctx *ctx, int mesh, const float *d_verts);
+int pb_scene_set_bsdf_texture_device(pb_ctx *ctx, int bsdf, int slot, const float *d_data);
+int pb_scene_get_mesh_vertices(pb_ctx *ctx, int mesh, float *h_out);
+/* importance of a secondary edge in the edge distribution: 0 = its length (the reference, src/scene/scene.cpp:236), 1 = length x exterior
+ * dihedral angle, pi for boundary edges — the alternative the reference keeps under `#if 0` (scene.cpp:230-233). Unbiased either way. */
+int pb_scene_set_edge_importance(pb_ctx *ctx, int mode);
 /* the edge tables Scene::configure builds (on the device: csrc/pb_tables.cu), copied to the host for inspection: primary edges of a sensor
  * (PrimaryEdgeInfo, src/sensor/perspective.cpp:39-111) as 7 floats each (p0.xy, p1.xy, edge_normal.xy, edge_length), secondary edges
  * (SecondaryEdgeInfo, src/shape/mesh.cpp:251-264, src/scene/scene.cpp:219-235) as 16 floats each (p0, e1, n0, n1, p2, is_boundary);

@@ -27,6 +27,7 @@ SYMBOLS = [
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
     "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
     "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad", "pb_render_d_get_state", "pb_render_d_set_state",
+    "pb_scene_set_mesh_vertices_device", "pb_scene_set_bsdf_texture_device", "pb_scene_get_mesh_vertices", "pb_scene_set_edge_importance",
     "pb_sample_boundary_segment_direct", "pb_scene_num_primary_edges", "pb_scene_get_primary_edges", "pb_scene_num_secondary_edges", "pb_scene_get_secondary_edges", "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
 ]
 
@@ -201,6 +202,24 @@ class Context:
 
     def set_mesh_vertices(self, mesh, verts):
         self._chk(lib().pb_scene_set_mesh_vertices(self.h, mesh, _p(_f(verts))))
+
+    def set_mesh_vertices_device(self, mesh, verts):
+        """vertices from a CUDA tensor (nv, 3): no host round trip (an optimiser with its parameters on the GPU)"""
+        self._bind_stream()
+        self._chk(lib().pb_scene_set_mesh_vertices_device(self.h, mesh, _dp(verts.contiguous().float())))
+
+    def set_bsdf_texture_device(self, bsdf, slot, data):
+        self._bind_stream()
+        self._chk(lib().pb_scene_set_bsdf_texture_device(self.h, bsdf, TEX[slot] if isinstance(slot, str) else slot, _dp(data.contiguous().float())))
+
+    def get_mesh_vertices(self, mesh, nv):
+        out = np.zeros((nv, 3), np.float32)
+        self._chk(lib().pb_scene_get_mesh_vertices(self.h, mesh, _p(out)))
+        return out
+
+    def set_edge_importance(self, mode):
+        """"length" (the reference) or "dihedral" (length x exterior dihedral angle: scene.cpp:230-233, disabled there)"""
+        self._chk(lib().pb_scene_set_edge_importance(self.h, {"length": 0, "dihedral": 1}.get(mode, mode)))
 
     def set_mesh_uvs(self, mesh, uvs):
         self._chk(lib().pb_scene_set_mesh_uvs(self.h, mesh, _p(_f(uvs))))

@@ -178,6 +178,11 @@ class _Proxy:
 
     def __getattr__(self, name):
         obj = object.__getattribute__(self, "_obj")
+        if name == "vertex_positions" and obj.type_name() == "Mesh":
+            scene = object.__getattribute__(self, "_scene")
+            if obj.index in scene._device_newer:               # last set from a CUDA leaf: bring the host mirror up to date
+                scene._get_vertices_device(obj.index)
+                scene._device_newer.discard(obj.index)
         if name == "vertex_positions" and _enoki() is not None:   # one array object per mesh, so that set_requires_gradient on it sticks
             scene = object.__getattribute__(self, "_scene")
             return scene._ek_array(_canonical_key(obj), "vertex_positions", lambda: _enoki().Vector3f(obj.vertex_positions))
@@ -250,6 +255,7 @@ class Scene(_h.Scene):
         self._fwd_texture = {}     # (BSDF key, field) -> flat texel tangent
         self._fwd_envmap = None    # 16 floats: tangent of the matrix EnvironmentMap.set_transform sets
         self._ek_inputs = {}       # (canonical key, field) -> array of the Enoki stand-in stored in / read from the scene
+        self._device_newer = set() # meshes whose vertices were last set from a CUDA leaf (the host mirror is refreshed when it is read)
 
     @property
     def param_map(self):
@@ -327,9 +333,24 @@ class Scene(_h.Scene):
         self._params[(key, field)] = t
         return t
 
+    _TEX_SLOT = {"reflectance": 0, "alpha_u": 1, "alpha_v": 2, "eta": 3, "k": 4, "specular_reflectance": 5}
+
     def configure(self):
-        for (key, field), t in self._params.items():
+        self._bind_stream()
+        on_device = self.uploaded      # after the first configure the leaves update the scene device-to-device: an optimisation loop
+        for (key, field), t in self._params.items():   # (torch.optim on CUDA leaves -> configure -> renderD -> backward) never touches the host
             obj = self._raw_param_map()[key]
+            if on_device and field == "vertex_positions":
+                self._set_vertices_device(obj.index, t.detach().contiguous().data_ptr())
+                self._device_newer.add(obj.index)
+                obj.requires_grad = bool(t.requires_grad) or obj.requires_grad
+                continue
+            if on_device and field in self._TEX_SLOT and obj.type_name() in ("Diffuse", "RoughConductor"):
+                bm = getattr(obj, field)
+                if t.numel() == max(1, bm.resolution[0] * bm.resolution[1]) * bm.channels:
+                    self._set_texture_device(obj.index, self._TEX_SLOT[field], t.detach().contiguous().data_ptr())
+                    bm.requires_grad = bool(t.requires_grad)
+                    continue
             val = t.detach().cpu().numpy()
             if field == "vertex_positions":
                 obj.vertex_positions = val

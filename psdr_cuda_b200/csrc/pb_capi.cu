@@ -245,7 +245,7 @@ static void configure_edges(pb_ctx *c, bool topo_changed) {
     if (need_sec) {
         c->d_sec.reserve((size_t)E * sizeof(SecEdgeRec)); c->d_sec_pmf.reserve((size_t)E * sizeof(float)); c->d_sec_cmf.reserve((size_t)E * sizeof(float));
         launch_secondary_edge_table(st, E, c->d_edge_src.p, c->view, vw, c->d_edge_flags.as<unsigned char>(), c->d_edge_local.as<int>(), c->d_edge_tiles.as<int>(),
-                                    c->d_sec.as<SecEdgeRec>(), c->d_sec_pmf.as<float>(), c->d_sec_cmf.as<float>(), out, reinterpret_cast<float *>(out + 1));
+                                    c->d_sec.as<SecEdgeRec>(), c->d_sec_pmf.as<float>(), c->d_sec_cmf.as<float>(), out, reinterpret_cast<float *>(out + 1), c->edge_importance);
         c->launches += 5;
         PB_CUDA(cudaMemcpyAsync(h_out.data(), out, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
@@ -1266,8 +1266,54 @@ int pb_scene_set_mesh_vertices(pb_ctx *c, int mesh, const float *verts) {
         HostMesh &m = c->meshes[mesh];
         m.verts.assign(verts, verts + 3 * (size_t)m.nv);
         m.verts_dirty = true;
+        m.verts_host_stale = false;
         c->ready = false;
     });
+}
+/* the same two setters from DEVICE memory: an optimiser that keeps its parameters on the GPU (torch.optim on CUDA leaves) updates the scene
+ * without a host round trip; the copies are enqueued on the context's stream, configure() then refits / rebuilds on the device */
+int pb_scene_set_mesh_vertices_device(pb_ctx *c, int mesh, const float *d_verts) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size() && d_verts, "Invalid mesh id");
+        HostMesh &m = c->meshes[mesh];
+        PB_CUDA(cudaSetDevice(c->device));
+        m.d_vraw.reserve(3 * (size_t)std::max(1, m.nv) * sizeof(float));
+        PB_CUDA(cudaMemcpyAsync(m.d_vraw.p, d_verts, 3 * (size_t)m.nv * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        m.verts_dirty = false;      // the device copy is the current one (the host copy is refreshed on demand: pb_scene_get_mesh_vertices)
+        m.verts_host_stale = true;
+        c->ready = false;
+    });
+}
+int pb_scene_set_bsdf_texture_device(pb_ctx *c, int bsdf, int slot, const float *d_data) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(bsdf >= 0 && bsdf < (int)c->bsdfs.size(), "Invalid BSDF id");
+        PB_ASSERT_MSG(slot >= 0 && slot < TEX_COUNT && d_data, "Invalid texture");
+        HostTexture &t = c->bsdfs[bsdf].tex[slot];
+        PB_CUDA(cudaSetDevice(c->device));
+        const size_t bytes = (size_t)t.w * t.h * t.c * sizeof(float);
+        t.d.reserve(bytes);
+        PB_CUDA(cudaMemcpyAsync(t.d.p, d_data, bytes, cudaMemcpyDeviceToDevice, c->stream));   // same resolution as set at creation / by the host setter
+        t.dirty = false;
+        c->ready = false;
+    });
+}
+int pb_scene_get_mesh_vertices(pb_ctx *c, int mesh, float *h_out) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(mesh >= 0 && mesh < (int)c->meshes.size() && h_out, "Invalid mesh id");
+        HostMesh &m = c->meshes[mesh];
+        if (m.verts_host_stale) {
+            PB_CUDA(cudaSetDevice(c->device));
+            PB_CUDA(cudaMemcpyAsync(m.verts.data(), m.d_vraw.p, 3 * (size_t)m.nv * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            PB_CUDA(cudaStreamSynchronize(c->stream));
+            m.verts_host_stale = false;
+        }
+        std::copy(m.verts.begin(), m.verts.end(), h_out);
+    });
+}
+/* importance of a secondary edge in the edge distribution: 0 = its length (the reference, scene.cpp:236), 1 = length x exterior dihedral
+ * angle (pi for boundary edges) — the alternative the reference keeps under `#if 0` (scene.cpp:230-233): flat creases are rarely silhouettes */
+int pb_scene_set_edge_importance(pb_ctx *c, int mode) {
+    return guard(c, [&] { PB_ASSERT_MSG(mode == 0 || mode == 1, "Invalid edge importance"); c->edge_importance = mode; c->ready = false; });
 }
 int pb_scene_set_mesh_uvs(pb_ctx *c, int mesh, const float *uvs) {
     return guard(c, [&] {

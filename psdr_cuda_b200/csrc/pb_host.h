@@ -66,6 +66,7 @@ struct HostMesh {
     std::vector<float> verts, uvs;
     std::vector<int> faces, uv_faces, edges, csr_off, csr_face, csr_slot;
     Mat4h raw = Mat4h::identity(), left = Mat4h::identity(), right = Mat4h::identity();
+    bool verts_host_stale = false;   // the vertices were last set from device memory (pb_scene_set_mesh_vertices_device)
     bool verts_dirty = true, topo_dirty = true, requires_grad = false, uv_requires_grad = false, uv_dirty = false;
     DevBuf d_vraw, d_faces, d_uvs, d_uv_faces, d_csr_off, d_csr_face, d_csr_slot, d_vworld, d_fcross, d_vnormal, d_face_area, d_face_cmf;
     DevBuf d_gworld, d_gnsum, d_gcorner, d_fcross_t, d_vnormal_t;   // VJP scratch: direct world-space vertex adjoint, normal-sum adjoint, per-corner adjoint
@@ -130,6 +131,7 @@ struct pb_ctx {
     bool has_bound_mesh = false;   // the last mesh is the envmap's bounding box (scene.cpp:135-180)
     // sharding / tiling
     int rank = 0, world = 1;
+    int edge_importance = 0;             // secondary-edge pmf: 0 length (reference), 1 length x dihedral angle (scene.cpp:230-233, `#if 0` there)
     int shard_mode = 0, tile_rows = 0;   // 0: every shard renders spp / world samples of every pixel; 1: image-row tiles of tile_rows rows, dealt round-robin
     void *nccl_comm = nullptr;           // pb_dist.cpp: communicator of pb_dist_init / pb_dist_adopt_comm
     bool nccl_owned = false;

@@ -61,7 +61,7 @@ void launch_primary_edge_table(cudaStream_t st, int n, const void *edge_src, con
                                unsigned char *flags, int *local, int *tile_sum, int *mesh_kept, int num_meshes, PrimEdgeRec *recs, float *pmf, float *cmf,
                                int *count_out, float *sum_out);
 void launch_secondary_edge_table(cudaStream_t st, int n, const void *edge_src, const SceneView &S, const float *const *vworld, unsigned char *flags, int *local,
-                                 int *tile_sum, SecEdgeRec *recs, float *pmf, float *cmf, int *count_out, float *sum_out);
+                                 int *tile_sum, SecEdgeRec *recs, float *pmf, float *cmf, int *count_out, float *sum_out, int importance);
 void launch_envmap_pmf(cudaStream_t st, int rx, int ry, int w, int h, const float *texel, const float *sin_theta, float *pmf);
 void launch_tri_bounds(cudaStream_t st, int n, const TriRec *tri, float *lohi);
 void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent);

@@ -14,7 +14,7 @@
 
 namespace pb {
 
-int g_sort_mode = 5;      // 5: origin cell (8x8x8, Morton) x direction octant; 0: 6-bit direction bin x 4x4x4 cells (the A/B is in profiles/r02e_*)
+int g_sort_mode = 5;      // 5: origin cell (8x8x8, Morton) x direction octant; 0: 6-bit direction bin x 4x4x4 cells (A/B: profiles/r02e_*; 16^3 cells without direction: r02m_*)
 int g_trace_kernel = 3;     // 0 first generation (k_trace_perm), 1 compact nodes, 2 compact nodes + postponed leaf, 3 persistent streaming kernel
 int g_trace_node_min = 312;  // streaming kernel: node steps continue while at least this many lanes descend
 

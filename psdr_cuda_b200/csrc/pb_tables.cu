@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_sec_edge_flags(int n, const EdgeSrc *__
 }
 __global__ void __launch_bounds__(256) k_sec_edge_write(int n, const EdgeSrc *__restrict__ es, const unsigned char *__restrict__ flags, const int *__restrict__ local,
                                                         const int *__restrict__ tile_off, const float *const *__restrict__ vworld, const TriRec *__restrict__ tri,
-                                                        const MeshRec *__restrict__ meshes, SecEdgeRec *__restrict__ recs, float *__restrict__ pmf) {
+                                                        const MeshRec *__restrict__ meshes, SecEdgeRec *__restrict__ recs, float *__restrict__ pmf, int importance) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !flags[i]) return;
     const int pos = local[i] + tile_off[i / kScanTile];
@@ -169,7 +169,12 @@ __global__ void __launch_bounds__(256) k_sec_edge_write(int n, const EdgeSrc *__
     r.d = make_float4(n1.x, n1.y, n1.z, __int_as_float(e.v1));
     r.e = make_float4(p2.x, p2.y, p2.z, 0.f);
     recs[pos] = r;
-    pmf[pos] = norm(e1);
+    float w = norm(e1);
+    if (importance == 1) {   // scene.cpp:230-233 (disabled there): length x exterior dihedral angle, pi for boundary edges
+        const float cs = fminf(fmaxf(dot(n0, n1), -1.f), 1.f);
+        w *= boundary ? kPi : acosf(cs);
+    }
+    pmf[pos] = w;
 }
 
 static void scan_flags(cudaStream_t st, int n, const unsigned char *flags, int *local, int *tile_sum, int *total) {
@@ -189,11 +194,11 @@ void launch_primary_edge_table(cudaStream_t st, int n, const void *edge_src, con
     launch_seq_cmf(st, n, pmf, cmf, sum_out, count_out);
 }
 void launch_secondary_edge_table(cudaStream_t st, int n, const void *edge_src, const SceneView &S, const float *const *vworld, unsigned char *flags, int *local,
-                                 int *tile_sum, SecEdgeRec *recs, float *pmf, float *cmf, int *count_out, float *sum_out) {
+                                 int *tile_sum, SecEdgeRec *recs, float *pmf, float *cmf, int *count_out, float *sum_out, int importance) {
     const EdgeSrc *es = static_cast<const EdgeSrc *>(edge_src);
     k_sec_edge_flags<<<nblk(n, 256), 256, 0, st>>>(n, es, S.tri, S.meshes, flags);
     scan_flags(st, n, flags, local, tile_sum, count_out);
-    k_sec_edge_write<<<nblk(n, 256), 256, 0, st>>>(n, es, flags, local, tile_sum, vworld, S.tri, S.meshes, recs, pmf);
+    k_sec_edge_write<<<nblk(n, 256), 256, 0, st>>>(n, es, flags, local, tile_sum, vworld, S.tri, S.meshes, recs, pmf, importance);
     launch_seq_cmf(st, n, pmf, cmf, sum_out, count_out);
 }
 

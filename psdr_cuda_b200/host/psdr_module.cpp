@@ -791,6 +791,28 @@ PYBIND11_MODULE(_psdr_host, m) {
                  if (!s.configured) throw std::runtime_error("Scene needs to be configured!");
                  s.check(pb_sample_boundary_segment_direct(s.ctx, n, reinterpret_cast<const float *>(d_sample3), reinterpret_cast<float *>(d_out)));
              })
+        // parameters that live on the GPU (torch leaves): device-to-device updates, no host round trip (pb_scene_set_*_device)
+        .def("_set_vertices_device", [](Scene &s, int mesh, uintptr_t d_verts) {
+                 if (!s.uploaded) throw std::runtime_error("the scene has not been configured yet");
+                 s.check(pb_scene_set_mesh_vertices_device(s.ctx, mesh, reinterpret_cast<const float *>(d_verts)));
+                 s.meshes.at(mesh)->verts_dirty = false;
+             })
+        .def("_get_vertices_device", [](Scene &s, int mesh) {
+                 auto &m = s.meshes.at(mesh);
+                 farray a(std::vector<py::ssize_t>{(py::ssize_t)m->nv(), 3});
+                 s.check(pb_scene_get_mesh_vertices(s.ctx, mesh, a.mutable_data()));
+                 std::memcpy(m->verts.data(), a.data(), m->verts.size() * sizeof(float));   // the host mirror follows, without marking it edited
+                 return a;
+             })
+        .def("_set_texture_device", [](Scene &s, int bsdf, int slot, uintptr_t d_data) {
+                 if (!s.uploaded) throw std::runtime_error("the scene has not been configured yet");
+                 s.check(pb_scene_set_bsdf_texture_device(s.ctx, bsdf, slot, reinterpret_cast<const float *>(d_data)));
+             })
+        .def("set_edge_importance", [](Scene &s, const std::string &mode) {
+                 if (mode != "length" && mode != "dihedral") throw std::runtime_error("edge importance must be \"length\" or \"dihedral\"");
+                 s.check(pb_scene_set_edge_importance(s.ctx, mode == "dihedral" ? 1 : 0));
+             })
+        .def_property_readonly("uploaded", [](const Scene &s) { return s.uploaded; })
         .def("stats_collectives", [](const Scene &s) { return (int64_t)pb_stats_collectives(s.ctx); })
         .def("set_stream", [](Scene &s, uintptr_t stream) { s.check(pb_ctx_set_stream(s.ctx, reinterpret_cast<void *>(stream))); })
         .def("stats_launches", [](const Scene &s) { return (int64_t)pb_stats_launches(s.ctx); })

@@ -802,6 +802,54 @@ def test_vertex_gradient_vector_error_estimate_meets_1e3():
     assert rel <= 1.5e-3, rel      # boundary terms: a knife-edge edge-ray pair (all-or-nothing lane) may take part
 
 
+def test_device_pointer_setters_match_the_host_setters(desc):
+    """pb_scene_set_mesh_vertices_device / pb_scene_set_bsdf_texture_device: parameters that live on the GPU update the scene device-to-device
+    (no host round trip in an optimisation loop); the result is bit-identical to the host setters'."""
+    from psdr_cuda_b200 import capi
+    opts = dict(width=48, height=48, spp=4, sppe=2, sppse=2)
+    integ = capi.make_integrator("path", max_depth=2)
+    verts = desc["meshes"][1]["verts"] + np.float32(0.21)
+    albedo = np.array([[0.3, 0.5, 0.7]], np.float32)
+    a = make_ctx(desc, opts, grads=True)
+    a.set_mesh_vertices(1, verts); a.set_bsdf_texture(0, "reflectance", albedo.reshape(1, 1, 3)); a.configure()
+    b = make_ctx(desc, opts, grads=True)
+    b.set_mesh_vertices_device(1, torch.from_numpy(verts).cuda()); b.set_bsdf_texture_device(0, "reflectance", torch.from_numpy(albedo).cuda()); b.configure()
+    assert torch.equal(a.render_c(integ), b.render_c(integ))
+    pa, _ = a.primary_edges(0); pb_, _ = b.primary_edges(0)
+    assert np.array_equal(pa.view(np.uint32), pb_.view(np.uint32))
+    assert np.array_equal(b.get_mesh_vertices(1, len(verts)), verts)
+    assert b.bvh_stats()["refits"] == 1                      # a vertex-only edit: the tree was refitted on the device
+
+
+def test_dihedral_edge_importance_is_unbiased():
+    """scene.cpp:230-233 keeps an alternative secondary-edge importance under `#if 0` (length x exterior dihedral angle); offered here as an
+    option. Both distributions are unbiased for the secondary-edge term: the same gradient projection within Monte Carlo noise."""
+    from psdr_cuda_b200 import capi, scene_io
+    pdesc = scene_io.load_scene_description(scene_path("cbox_bunny"))
+    rng = np.random.default_rng(9)
+    dLdI = torch.from_numpy(rng.uniform(0, 1, size=(32 * 32, 3)).astype(np.float32)).cuda()
+    u = np.tile(np.array([[1.0, 0.5, -0.3]], np.float32), (len(pdesc["meshes"][1]["verts"]), 1))
+    proj = {}
+    for mode in ("length", "dihedral"):
+        vals = []
+        for rep in range(4):
+            ctx = capi.Context(0)
+            ctx.load_description(pdesc, dict(width=32, height=32, spp=0, sppe=0, sppse=256))
+            ctx.grad_require(capi.PARAM_MESH_VERTICES, 1)
+            ctx.set_edge_importance(mode)
+            ctx.configure()
+            integ = capi.make_integrator("direct", bsdf_samples=1, light_samples=1)
+            for _ in range(rep + 1):
+                ctx.render_d(integ)                              # later passes continue the sampler streams: independent estimates
+            g = ctx.render_d_vjp(integ, dLdI).cpu().numpy().reshape(-1, 3)
+            vals.append(float((g.astype(np.float64) * u).sum()))
+            ctx.close()
+        proj[mode] = (np.mean(vals), np.std(vals) / np.sqrt(len(vals)))
+    (ml, sl), (md, sd) = proj["length"], proj["dihedral"]
+    assert np.isfinite([ml, md]).all() and abs(ml) > 0
+    assert abs(ml - md) <= 4 * np.hypot(sl, sd) + 0.02 * abs(ml), proj
+
+
 def test_bvh_refit_after_vertex_edits_gives_the_same_hits_and_images(desc):
     """Scene::configure after vertex-only edits refits the BVH on the device instead of rebuilding it on the host: hit records and
     images must equal those of a context that builds the tree from scratch on the moved geometry."""

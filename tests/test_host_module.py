@@ -227,6 +227,38 @@ def test_roughconductor_and_envmap_leaves_through_the_module(psdr_cuda):
 
 
 @pytest.mark.gpu
+def test_cuda_leaves_update_the_scene_without_leaving_the_device(psdr_cuda):
+    """after the first configure, registered torch leaves reach the scene device-to-device (pb_scene_set_*_device): the optimisation loop of
+    docs/inverse_diff_render.rst keeps its parameters on the GPU like the reference's Enoki arrays; host mirrors refresh when read"""
+    torch = pytest.importorskip("torch")
+    sc = psdr_cuda.Scene()
+    sc.load_file(scene_path("cbox_bunny"), False)
+    sc.opts.width, sc.opts.height, sc.opts.spp, sc.opts.sppe, sc.opts.sppse, sc.opts.log_level = 32, 32, 4, 0, 0, 0
+    verts = sc.parameter("Mesh[1]", "vertex_positions")
+    albedo = sc.parameter("BSDF[id=red]", "reflectance")
+    sc.configure()
+    integ = psdr_cuda.PathIntegrator(2)
+    before = integ.renderC(sc, 0)
+    with torch.no_grad():
+        verts += torch.tensor([3.0, 0.0, 0.0], device=verts.device)
+        albedo.copy_(torch.tensor([[0.1, 0.8, 0.1]], device=albedo.device))
+    sc.configure()                                         # device-to-device
+    after = integ.renderC(sc, 0)
+    assert not torch.equal(before, after)
+    host = np.asarray(sc.param_map["Mesh[1]"].vertex_positions)
+    assert np.allclose(host, verts.detach().cpu().numpy())
+    # the same edit through the host path gives the same image
+    sc2 = psdr_cuda.Scene()
+    sc2.load_file(scene_path("cbox_bunny"), False)
+    sc2.opts.width, sc2.opts.height, sc2.opts.spp, sc2.opts.sppe, sc2.opts.sppse, sc2.opts.log_level = 32, 32, 4, 0, 0, 0
+    sc2.param_map["Mesh[1]"].vertex_positions = verts.detach().cpu().numpy()
+    sc2.param_map["BSDF[id=red]"].reflectance.data = np.array([[0.1, 0.8, 0.1]], np.float32)
+    sc2.configure()
+    integ.renderC(sc2, 0)                                  # same position of the sampler streams as `after`
+    assert torch.allclose(integ.renderC(sc2, 0), after, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_two_renders_before_one_backward_use_their_own_samples(psdr_cuda):
     """A multi-view loss renders several images before one backward (the reference's tape differentiates each with the samples
     that produced it). Every renderD node remembers its sampler positions (pb_render_d_get_state) and restores them for its VJP:
