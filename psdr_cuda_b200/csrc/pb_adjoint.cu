@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
         if (!ev_depth0<EV>(B)) T = f3(ldg4(E.thr_in + i));
         const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
         const float3 gL = g * T, gw = gL * S_next;
-        Rng rng((uint64_t)lane, B.jump);
+        Rng rng = make_rng(P, lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         const bool geom = geom_mode(P.S) && v.active && v.bsdf && v.bsdf->type == BSDF_DIFFUSE;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
                     const TriFull t = load_tri_full(P.S, hp.tri);
                     if ((t.flags & 8) || P.S.sensor_grad) {
                         int pix0;
-                        Rng rng0((uint64_t)global_lane(P, i, pix0), P.jump0);
+                        Rng rng0 = make_rng(P, global_lane(P, i, pix0), P.jump0);
                         const float2 jit = rng0.next_2d();
                         float sx, sy;
                         lane_pixel_sample(P, pix0, jit, sx, sy);

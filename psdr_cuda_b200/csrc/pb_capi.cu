@@ -567,6 +567,22 @@ static void configure(pb_ctx *c) {
     c->retained_valid = false;
 }
 
+// seed table of the stateless sampler: (state, inc) of every lane id any of the three samplers can use, built once per lane count
+static void attach_rng_seeds(pb_ctx *c, RenderParams &P) {
+    const int64_t npix = (int64_t)c->width * c->height;
+    const int64_t need = npix * std::max(c->spp, std::max(c->sppe, c->sppse));
+    P.rng_seed = nullptr; P.rng_seed_count = 0;
+    if (need <= 0 || !c->rng_seed_table) return;
+    if (c->rng_seed_count < need) {
+        try { c->d_rng_seed.reserve((size_t)need * sizeof(ulonglong2)); }
+        catch (const Error &) { cudaGetLastError(); c->rng_seed_count = 0; return; }   // no room: the kernels hash on the fly
+        launch_rng_seed(c->stream, need, c->d_rng_seed.as<ulonglong2>());
+        c->launches++;
+        c->rng_seed_count = need;
+    }
+    P.rng_seed = c->d_rng_seed.as<ulonglong2>(); P.rng_seed_count = c->rng_seed_count;
+}
+
 struct Plan { int nbounce, nb, nl, draws; };
 static Plan make_plan(const pb_integrator &I) {
     Plan p;
@@ -778,6 +794,7 @@ static void preprocess_secondary_edges(pb_ctx *c, int sensor, const int *reso, i
     std::memset(&P, 0, sizeof(P));
     P.S = c->view; P.cam = c->sensors[sensor].rec;
     P.width = c->width; P.height = c->height; P.spp = 1; P.spp_local = 1; P.s0 = 0; P.inv_spp = 1.f;
+    attach_rng_seeds(c, P);
     for (int j = 0; j < nrounds; ++j) {
         P.jump0 = make_jump(3 * (uint64_t)j);   // a private sampler seeded with arange(N) (direct.cpp:185-186)
         for (int64_t start = 0; start < N; start += B) {
@@ -871,6 +888,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
     P.spp_local = spp_local; P.s0 = s0;
     P.tile_rows = tile_rows; P.rank = c->rank; P.world = c->world;
+    attach_rng_seeds(c, P);
     P.jump0 = make_jump(base);
     if (mode == MODE_VJP) {   // BSDF table whose textures point at their gradient segments
         // the tables of configure with their gradient pointers filled in: patched on the host copies, uploaded asynchronously (no read-back)
@@ -1578,6 +1596,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "shade_tune") == 0) pb::g_shade_tune = (int)value;
         else if (std::strcmp(key, "shade_simple") == 0) pb::g_shade_simple = (int)value;
         else if (std::strcmp(key, "l2_persist") == 0) { c->l2_persist = (int)value; set_l2_window(c); }
+        else if (std::strcmp(key, "rng_seed_table") == 0) { c->rng_seed_table = (int)value; c->rng_seed_count = 0; }
         else if (std::strcmp(key, "trace_kernel") == 0) pb::g_trace_kernel = (int)value;
         else if (std::strcmp(key, "trace_node_min") == 0) pb::g_trace_node_min = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);

@@ -340,6 +340,17 @@ void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *node
     if (num_nodes > 0) k_nodes_to_compact<<<nblk(num_nodes, 256), 256, 0, st>>>(num_nodes, nodes, out, extent);
 }
 
+// seeded PCG32 state of every lane (sampler.cpp:29-40): computed once per context, read by every kernel that draws samples
+__global__ void __launch_bounds__(256) k_rng_seed(long long n, ulonglong2 *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RngSeed s = rng_seed((uint64_t)i);
+    out[i] = make_ulonglong2(s.state, s.inc);
+}
+void launch_rng_seed(cudaStream_t st, long long n, ulonglong2 *out) {
+    if (n > 0) k_rng_seed<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, out);
+}
+
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf) {
     if (n > 0) k_build_leaf_tris<<<nblk(n, 256), 256, 0, st>>>(n, order, tri, leaf);
 }

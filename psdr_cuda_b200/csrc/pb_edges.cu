@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) k_edge_primary_rays(RenderParams P, EdgeP
     if (i >= P.n) return;
     int pix;
     const long long lane = global_lane(P, i, pix);
-    Rng rng((uint64_t)lane, P.jump0);
+    Rng rng = make_rng(P, lane, P.jump0);
     const PrimEdgeSample es = sample_primary_edge(Q, P.cam, rng.next_1d());
     const float sg = side == 0 ? 1.f : -1.f;   // side 0: ray_p (+n), side 1: ray_n (-n)
     float3 o, d;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_edge_primary_grad(RenderParams P, EdgeP
     if (i >= P.n) return;
     int pix;
     const long long lane = global_lane(P, i, pix);
-    Rng rng((uint64_t)lane, P.jump0);
+    Rng rng = make_rng(P, lane, P.jump0);
     const PrimEdgeSample es = sample_primary_edge(Q, P.cam, rng.next_1d());
     if (es.idx < 0) return;
     float *gworld = Q.mesh_gworld[es.rec.mesh];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k_edge_secondary_rays(RenderParams P, Edg
     if (i >= P.n) return;
     int pix;
     const long long lane = global_lane(P, i, pix);
-    Rng rng((uint64_t)lane, P.jump0);
+    Rng rng = make_rng(P, lane, P.jump0);
     float gp;
     const BoundarySample bss = sample_boundary_segment_direct(P.S, Q, lane_sample3(P, Q, i, rng, guide_spc, gp));
     const float3 dir = normalize(bss.p2 - bss.p0);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_edge_secondary_camera(RenderParams P, E
     if (valid) {
         int pix;
         const long long lane = global_lane(P, i, pix);
-        Rng rng((uint64_t)lane, P.jump0);
+        Rng rng = make_rng(P, lane, P.jump0);
         float gp;
         const BoundarySample bss = sample_boundary_segment_direct(P.S, Q, lane_sample3(P, Q, i, rng, guide_spc, gp));
         const Its its2 = reconstruct_its(P.S, load_hit(hits + i), p0);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
     if (hc.tri < 0) return;
     int pix;
     const long long lane = global_lane(P, i, pix);
-    Rng rng((uint64_t)lane, P.jump0);
+    Rng rng = make_rng(P, lane, P.jump0);
     float guide_pdf;
     const float3 s3 = lane_sample3(P, Q, i, rng, guide_out ? guide_spc : 0, guide_pdf);
     const BoundarySample bss = sample_boundary_segment_direct(P.S, Q, s3);

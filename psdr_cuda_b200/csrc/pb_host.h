@@ -137,6 +137,9 @@ struct pb_ctx {
     bool nccl_owned = false;
     int64_t batch = 1 << 25;   // 32 Mi lanes: large wavefronts sort into more coherent bins
     // samplers (scene.cpp:65-79): lane count the streams were seeded for and draws consumed so far
+    pb::DevBuf d_rng_seed;          // seeded PCG32 (state, inc) per lane id (16 B each), shared by the three samplers
+    int64_t rng_seed_count = 0;
+    int rng_seed_table = 1;          // debug: 0 = every kernel hashes its lane's seed on the fly (round 1)
     int64_t sampler_count[3] = {0, 0, 0};
     uint64_t sampler_offset[3] = {0, 0, 0};
     // configured device tables

@@ -30,6 +30,8 @@ struct RenderParams {
     int tile_rows, rank, world;   // pixel sharding: tile_rows > 0 and this shard owns the image-row tiles t * world + rank (tile_rows rows each); 0 = every pixel
     int n;                  // lanes in this batch
     RngJump jump0;          // stream position of the pixel jitter
+    const ulonglong2 *rng_seed;   // seeded (state, inc) per global lane id, lanes [0, rng_seed_count) (pb_ctx; nullptr / short: hash on the fly)
+    long long rng_seed_count;
 };
 
 // device buffers of one scattering event for one batch of n lanes (R = nb + nl rays per lane)
@@ -65,6 +67,7 @@ void launch_secondary_edge_table(cudaStream_t st, int n, const void *edge_src, c
 void launch_envmap_pmf(cudaStream_t st, int rx, int ry, int w, int h, const float *texel, const float *sin_theta, float *pmf);
 void launch_tri_bounds(cudaStream_t st, int n, const TriRec *tri, float *lohi);
 void launch_nodes_to_compact(cudaStream_t st, int num_nodes, const BvhNode *nodes, BvhNodeC *out, float extent);
+void launch_rng_seed(cudaStream_t st, long long n, ulonglong2 *out);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_sort_mode;       // debug: sort key (pb_sort.cu)

@@ -169,17 +169,31 @@ inline RngJump make_jump(uint64_t n) {
     return {acc_mult, acc_plus};
 }
 
+// seeded generator of stream `lane` before any draw: (state, inc) of PCG32 after Sampler::seed (sampler.cpp:29-40). It depends on the lane
+// id alone, so a context computes it once per lane (k_rng_seed) and every kernel skips the two TEA hashes (~270 of its instructions).
+struct RngSeed { uint64_t state, inc; };
+PB_HD RngSeed rng_seed(uint64_t lane) {
+    uint64_t seed_value = lane + kPCG32DefaultState;
+    uint64_t initstate = sample_tea_64(seed_value, lane), initseq = sample_tea_64(lane, seed_value);
+    RngSeed r;
+    r.inc = (initseq << 1) | 1u;
+    r.state = r.inc;                                  // state=0; step -> inc
+    r.state += initstate;
+    r.state = r.state * kPCG32Mult + r.inc;
+    return r;
+}
+
 struct Rng {
     uint64_t state, inc;
     // stream `lane` of a psdr Sampler seeded with arange(count) (sampler.cpp:29-40), advanced by `jump` draws
     PB_HD Rng(uint64_t lane, RngJump jump) {
-        uint64_t seed_value = lane + kPCG32DefaultState;
-        uint64_t initstate = sample_tea_64(seed_value, lane), initseq = sample_tea_64(lane, seed_value);
-        inc = (initseq << 1) | 1u;
-        state = inc;                                  // state=0; step -> inc
-        state += initstate;
-        state = state * kPCG32Mult + inc;
-        state = jump.A * state + inc * jump.B;
+        const RngSeed s = rng_seed(lane);
+        inc = s.inc;
+        state = jump.A * s.state + inc * jump.B;
+    }
+    PB_HD Rng(RngSeed s, RngJump jump) {
+        inc = s.inc;
+        state = jump.A * s.state + inc * jump.B;
     }
     PB_HD uint32_t next_u32() {
         uint64_t old = state;

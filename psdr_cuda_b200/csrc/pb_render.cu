@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restr
     if (i >= P.n) return;
     int pix;
     const long long lane = global_lane(P, i, pix);
-    Rng rng((uint64_t)lane, P.jump0);
+    Rng rng = make_rng(P, lane, P.jump0);
     const float2 j = rng.next_2d();
     float sx, sy;
     lane_pixel_sample(P, pix, j, sx, sy);
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
     const Vertex v = load_vertex<EV>(P, B, i, E);
     E.pos[i] = make_float4(v.its.p.x, v.its.p.y, v.its.p.z, 0.f);
     int pix_unused;
-    Rng rng((uint64_t)global_lane(P, i, pix_unused), B.jump);
+    Rng rng = make_rng(P, global_lane(P, i, pix_unused), B.jump);
     for (int j = 0; j < B.nb; ++j) {
         const float3 s3 = rng.next_3d();
         const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, v.its, s3, v.active);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
         const long long lane = global_lane(P, i, pix);
         const Vertex v = load_vertex<EV>(P, B, i, E);
         const Its &its = v.its;
-        Rng rng((uint64_t)lane, B.jump);
+        Rng rng = make_rng(P, lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         bool has_cont = false;
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;

@@ -26,6 +26,17 @@ PB_D long long global_lane(const RenderParams &P, int i, int &pix) {
     return (long long)lp * P.spp + P.s0 + s;
 }
 
+// the lane's generator at stream position `jump`: from the context's seed table when it covers the lane (one 128-bit load), else hashed
+PB_D Rng make_rng(const RenderParams &P, long long lane, RngJump jump) {
+    if (P.rng_seed && lane < P.rng_seed_count) {
+        const ulonglong2 s = __ldg(P.rng_seed + lane);
+        RngSeed r;
+        r.state = s.x; r.inc = s.y;
+        return Rng(r, jump);
+    }
+    return Rng((uint64_t)lane, jump);
+}
+
 PB_D void lane_pixel_sample(const RenderParams &P, int pix, float2 jitter, float &sx, float &sy) {
     const int x = pix % P.width, y = pix / P.width;
     sx = div_rn(add_rn((float)x, jitter.x), (float)P.width);
@@ -74,7 +85,7 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
         if (ev_ad<EV>(B)) {   // renderD: the camera hit is differentiated in solid-angle form (scene.cpp:355-376)
             int pix;
             const long long lane = global_lane(P, i, pix);
-            Rng rng((uint64_t)lane, P.jump0);
+            Rng rng = make_rng(P, lane, P.jump0);
             const float2 j = rng.next_2d();
             float sx, sy;
             lane_pixel_sample(P, pix, j, sx, sy);

@@ -54,7 +54,10 @@ def test_extension_is_loaded_and_launches_kernels(desc):
     ctx = make_ctx(desc, dict(width=16, height=16, spp=2, sppe=0, sppse=0))
     before = ctx.stats()["launches"]
     ctx.render_c(capi.make_integrator("direct"))
-    assert ctx.stats()["launches"] - before == 7          # primary, shade, sort (hist, scan, scatter), trace, resolve
+    assert ctx.stats()["launches"] - before == 8          # sampler seed table (first render only), primary, shade, sort (hist, scan, scatter), trace, resolve
+    before = ctx.stats()["launches"]
+    ctx.render_c(capi.make_integrator("direct"))
+    assert ctx.stats()["launches"] - before == 7
     maps = open("/proc/self/maps").read()
     assert "libpsdr_b200.so" in maps
 
