@@ -145,7 +145,10 @@ static void configure_sensor(HostSensor &s, int W, int H) {
 
 // all wavefront ray launches go through here: counting sort by (origin cell, direction octant) with compaction of inactive lanes,
 // then the streaming traversal kernel over the sorted stream (pb_sort.cu, pb_trace2.cuh)
-static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+// mode: SORT_CELL_OCTANT for rays that start on surfaces, SORT_DIRECTION for rays that share an origin (camera rays of the edge terms);
+// keys_ready: k_shade has left the keys in d_sort_keys
+static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, int mode = -1,
+                            bool keys_ready = false) {
     if (!c->d_active_total.p) { c->d_active_total.reserve(sizeof(unsigned long long)); cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream); }
     c->d_sort_hist.reserve(40000 * sizeof(unsigned));
     c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
@@ -153,7 +156,8 @@ static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hi
     c->d_stream_counter.reserve(sizeof(unsigned));
     launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
                         f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
-                        c->d_sort_keys.as<unsigned short>(), c->d_stream_counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1);
+                        c->d_sort_keys.as<unsigned short>(), c->d_stream_counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1,
+                        mode < 0 ? g_sort_mode : mode, keys_ready);
     c->launches += 3;
 }
 
@@ -446,6 +450,8 @@ static void configure(pb_ctx *c) {
     {   // the compact copy of the tree the wavefront traversal reads (pb_trace2.cuh)
         float extent = 0.f;
         for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(c->scene_lo[k]), std::fabs(c->scene_hi[k])));
+        for (const HostSensor &s : c->sensors)   // camera rays go through the compact nodes too: their slab-test slack scales with |o|
+            extent = std::max(extent, std::max(std::fabs(s.rec.camera_pos.x), std::max(std::fabs(s.rec.camera_pos.y), std::fabs(s.rec.camera_pos.z))));
         launch_nodes_to_compact(st, c->view.num_nodes, c->arena_nodes(), c->arena_nodes_c(), extent);
         c->launches++;
     }
@@ -583,6 +589,14 @@ static void attach_rng_seeds(pb_ctx *c, RenderParams &P) {
     P.rng_seed = c->d_rng_seed.as<ulonglong2>(); P.rng_seed_count = c->rng_seed_count;
 }
 
+// the ray sort's box and mode for k_shade, which leaves every emitted ray's key next to it (the sort then skips reading the rays)
+static void set_sort_params(const pb_ctx *c, BounceParams &B) {
+    B.sort_lo = f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]);
+    B.sort_inv_ext = f3(1.f / fmaxf(c->scene_hi[0] - c->scene_lo[0], 1e-20f), 1.f / fmaxf(c->scene_hi[1] - c->scene_lo[1], 1e-20f),
+                        1.f / fmaxf(c->scene_hi[2] - c->scene_lo[2], 1e-20f));
+    B.sort_mode = g_sort_mode;
+}
+
 struct Plan { int nbounce, nb, nl, draws; };
 static Plan make_plan(const pb_integrator &I) {
     Plan p;
@@ -664,7 +678,7 @@ static void secondary_edge_batch(pb_ctx *c, const RenderParams &P, const EdgePar
     launch_edge_secondary_rays(st, P, Q, rays, guide_spc);
     trace_wavefront(c, 2 * (int64_t)P.n, rays, hits);
     launch_edge_secondary_camera(st, P, Q, rays, hits, cam_rays, guide_spc);
-    trace_wavefront(c, (int64_t)P.n, cam_rays, cam_hits);
+    trace_wavefront(c, (int64_t)P.n, cam_rays, cam_hits, nullptr, nullptr, 7 /* SORT_DIRECTION: every ray starts at the camera */);
     if (P.S.tri_tangent) {
         RenderParams Pc = P;
         for (int ch = 0; ch < 3; ++ch) {
@@ -712,7 +726,8 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
             P.local0 = start; P.n = (int)std::min<int64_t>(B, l1 - start);
             for (int side = 0; side < 2; ++side) {   // side 0 = ray_p is evaluated first (operand order)
                 HitRec *hit0 = S.hit0.as<HitRec>();
-                launch_edge_primary_rays(st, P, Q, side, hit0);
+                launch_edge_primary_rays(st, P, Q, side, S.rays.as<RayRec>());
+                trace_wavefront(c, (int64_t)P.n, S.rays.as<RayRec>(), hit0, nullptr, nullptr, 7 /* SORT_DIRECTION */);
                 c->launches++;
                 if (field) {
                     launch_field(st, P, I.field, hit0, nullptr, S.rad.as<float4>());
@@ -723,6 +738,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         Bp.nb = plan.nb; Bp.nl = plan.nl; Bp.depth = k; Bp.last = (k == plan.nbounce - 1); Bp.carry = (I.kind == PB_INTEG_PATH);
                         Bp.hide_emitters = I.hide_emitters; Bp.ad = 0; Bp.rc_grad = 0;
                         Bp.jump = make_jump(base + 1 + (uint64_t)side * per_li + (uint64_t)k * per_event);
+                        set_sort_params(c, Bp);
                         EventBuffers E;
                         E.hit_cur = (k == 0) ? hit0 : S.hits[(k - 1) & 1].as<HitRec>();
                         E.hit_prev = nullptr;
@@ -733,8 +749,10 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.thr_in = (k == 0) ? nullptr : S.thr[k & 1].as<float4>();
                         E.thr_out = Bp.last ? nullptr : S.thr[(k + 1) & 1].as<float4>();
                         E.rad = S.rad.as<float4>();
+                        c->d_sort_keys.reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(unsigned short));
+                        E.keys = c->d_sort_keys.as<unsigned short>();
                         launch_shade(st, P, Bp, E);
-                        trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits);
+                        trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr, nullptr, -1, true);
                         launch_resolve(st, P, Bp, E, nullptr);
                         c->launches += 3;
                     }
@@ -883,6 +901,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     EventStore &S = use_retained ? c->retained : c->scratch;
     size_store(S, use_retained ? total : B, keep ? D : 2, R, B);
     if (mode == MODE_VJP) c->d_suffix.reserve((size_t)B * sizeof(float4));
+    c->d_sort_keys.reserve((size_t)B * R * sizeof(unsigned short));   // k_shade writes the sort keys of the rays it emits
     RenderParams P;
     P.S = c->view; P.cam = c->sensors[sensor].rec;
     P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
@@ -1012,6 +1031,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             if (he.env_radiance.requires_grad || he.env_scale_requires_grad || he.env_xf_requires_grad || any_geom_jvp(c)) Bp.rc_grad = 1;
         }
         Bp.jump = make_jump(base + 2 + (uint64_t)k * (3 * plan.nb + 2 * plan.nl));
+        set_sort_params(c, Bp);
     }
     size_t nev = 0, nev_edge = 0;
     for (int64_t start = 0; start < total && !(field && mode == MODE_VJP); start += B) {
@@ -1030,6 +1050,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.thr_in = (k == 0) ? nullptr : S.thr[keep ? k : (k & 1)].as<float4>() + off;
             E.thr_out = bps[k].last ? nullptr : S.thr[keep ? k + 1 : ((k + 1) & 1)].as<float4>() + off;
             E.rad = S.rad.as<float4>() + off;
+            E.keys = c->d_sort_keys.as<unsigned short>();
             return E;
         };
         if (run_forward) {
@@ -1046,7 +1067,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 const EventBuffers E = event(k);
                 launch_shade(st, P, bps[k], E);
                 cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
-                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, t0, t1);
+                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, t0, t1, -1, true);
                 launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
                 c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
             }

@@ -42,7 +42,8 @@ PB_D PrimEdgeSample sample_primary_edge(const EdgeParams &Q, const SensorRec &ca
 }
 
 // camera rays through p +- EdgeEpsilon * n, traced; lanes whose sample falls off the film are inactive (integrator.cpp:104-110)
-__global__ void __launch_bounds__(128) k_edge_primary_rays(RenderParams P, EdgeParams Q, int side, HitRec *__restrict__ hit0) {
+// (emitted as a wavefront: edge samples of neighbouring lanes are unrelated, so the rays go through the direction sort + streaming kernel)
+__global__ void __launch_bounds__(256) k_edge_primary_rays(RenderParams P, EdgeParams Q, int side, RayRec *__restrict__ rays) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     int pix;
@@ -52,8 +53,7 @@ __global__ void __launch_bounds__(128) k_edge_primary_rays(RenderParams P, EdgeP
     const float sg = side == 0 ? 1.f : -1.f;   // side 0: ray_p (+n), side 1: ray_n (-n)
     float3 o, d;
     sample_primary_ray(P.cam, es.px + sg * kEdgeEpsilon * es.rec.nx, es.py + sg * kEdgeEpsilon * es.rec.ny, o, d);
-    Hit h = trace_closest(P.S.nodes, P.S.leaf, o, d, es.idx >= 0 ? INFINITY : -1.f);
-    reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
+    store_ray(rays + i, o, d, es.idx >= 0 ? INFINITY : -1.f);
 }
 
 // adjoint of a world-space vertex: reverse mode adds it to the mesh's vertex-adjoint buffer; forward mode (the buffer then
@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(256) k_edge_secondary_eval(RenderParams P, Edg
 
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
-void launch_edge_primary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, int side, HitRec *hit0) {
-    if (P.n > 0) k_edge_primary_rays<<<nblk(P.n, 128), 128, 0, st>>>(P, Q, side, hit0);
+void launch_edge_primary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, int side, RayRec *rays) {
+    if (P.n > 0) k_edge_primary_rays<<<nblk(P.n, 256), 256, 0, st>>>(P, Q, side, rays);
 }
 void launch_edge_primary_grad(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const float4 *rad_p, const float4 *rad_n, const float *dLdI, float inv_sppe) {
     if (P.n > 0) k_edge_primary_grad<<<nblk(P.n, 256), 256, 0, st>>>(P, Q, rad_p, rad_n, dLdI, inv_sppe);

@@ -18,6 +18,8 @@ struct BounceParams {
     int ad;                 // 1: the reference's AD formulation of the primal (direct.cpp:83-95), 0: renderC's
     int rc_grad;            // adjoint only: some rough-conductor texture requires a gradient
     RngJump jump;           // stream position of this event's first draw
+    float3 sort_lo, sort_inv_ext;   // scene box of the ray sort (k_shade leaves each emitted ray's sort key in EventBuffers::keys)
+    int sort_mode;
 };
 
 struct RenderParams {
@@ -45,6 +47,7 @@ struct EventBuffers {
     const float4 *thr_in;    // [n]   throughput T_k (.w != 0: the path is dead); unused at depth 0
     float4 *thr_out;         // [n]   T_{k+1}; may be null on the last event
     float4 *rad;             // [n]   radiance accumulated so far (in/out)
+    unsigned short *keys;    // [R*n] sort keys of this event's rays, written by k_shade (or null: the sort computes them from the rays)
 };
 
 void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
@@ -77,12 +80,12 @@ extern int g_trace_kernel;    // sorted-wavefront traversal kernel: 3 persistent
 extern int g_trace_node_min;  // streaming kernel: node steps continue while at least this many lanes descend
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total = nullptr, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready);
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);
 void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI);
-void launch_edge_primary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, int side, HitRec *hit0);
+void launch_edge_primary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, int side, RayRec *rays);
 void launch_edge_primary_grad(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const float4 *rad_p, const float4 *rad_n, const float *dLdI, float inv_sppe);
 void launch_edge_secondary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, RayRec *rays, int guide_spc);
 void launch_edge_secondary_camera(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const RayRec *rays, const HitRec *hits, RayRec *cam_rays, int guide_spc);

@@ -11,6 +11,8 @@
 #include "pb_kernels.h"
 #include "pb_shade.cuh"
 #include "pb_trace.cuh"
+#include "pb_trace2.cuh"
+#include "pb_sortkey.cuh"
 #include "pb_wavefront.cuh"
 
 namespace pb {
@@ -38,7 +40,9 @@ __global__ void __launch_bounds__(128) k_primary(RenderParams P, HitRec *__restr
     lane_pixel_sample(P, pix, j, sx, sy);
     float3 o, d;
     sample_primary_ray(P.cam, sx, sy, o, d);
-    const Hit h = trace_closest(P.S.nodes, P.S.leaf, o, d, INFINITY);
+    // camera rays in lane order are coherent (the samples of a pixel are neighbours): one ray per thread over the compact nodes
+    // (their slack covers the camera positions: pb_capi.cu configure)
+    const Hit h = trace_closest_c(P.S.nodes_c, P.S.leaf, o, d, INFINITY, 0.f);
     reinterpret_cast<float4 *>(hit0)[i] = make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v);
 }
 
@@ -56,7 +60,9 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
         const float3 s3 = rng.next_3d();
         const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, v.its, s3, v.active);
         const bool a1 = v.active && bs.valid;
-        store_ray(rays_out + (size_t)j * P.n + i, v.its.p, v.its.sh.to_world(bs.wo), a1 ? INFINITY : -1.f);
+        const float3 wo_w = v.its.sh.to_world(bs.wo);
+        store_ray(rays_out + (size_t)j * P.n + i, v.its.p, wo_w, a1 ? INFINITY : -1.f);
+        if (E.keys) E.keys[(size_t)j * P.n + i] = (unsigned short)sort_key(v.its.p, a1 ? 1.f : -1.f, wo_w, B.sort_lo, B.sort_inv_ext, B.sort_mode);
     }
     for (int j = 0; j < B.nl; ++j) {
         const float2 s2 = rng.next_2d();
@@ -72,6 +78,7 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
         // contributes exactly 0 (value and derivative) whatever the ray hits: such lanes are not traced.
         const bool lit = v.its.wi.z > 0.f && dot(wo, v.its.sh.n) > 0.f;
         store_ray(rays_out + (size_t)(B.nb + j) * P.n + i, v.its.p, wo, (a1 && lit) ? fmaf(dist, 1e-5f, dist) + 2e-3f : -1.f, dist - kShadowEpsilon);
+        if (E.keys) E.keys[(size_t)(B.nb + j) * P.n + i] = (unsigned short)sort_key(v.its.p, (a1 && lit) ? 1.f : -1.f, wo, B.sort_lo, B.sort_inv_ext, B.sort_mode);
     }
 }
 

@@ -11,51 +11,32 @@
 #include "pb_kernels.h"
 #include "pb_trace.cuh"
 #include "pb_trace2.cuh"
+#include "pb_sortkey.cuh"
 
 namespace pb {
 
-int g_sort_mode = 5;      // 5: origin cell (8x8x8, Morton) x direction octant; 0: 6-bit direction bin x 4x4x4 cells (A/B: profiles/r02e_*; 16^3 cells without direction: r02m_*)
+int g_sort_mode = SORT_CELL_OCTANT;   // 5: origin cell (8x8x8, Morton) x direction octant; 0: 6-bit direction bin x 4x4x4 cells (A/B: profiles/r02e_*; 16^3 cells without direction: r02m_*)
 int g_trace_kernel = 3;     // 0 first generation (k_trace_perm), 1 compact nodes, 2 compact nodes + postponed leaf, 3 persistent streaming kernel
 int g_trace_node_min = 312;  // streaming kernel: node steps continue while at least this many lanes descend
 
-constexpr int kSortBins = 4096;   // 6 bits direction (octahedral 8x8, Morton) x 6 bits origin cell (4x4x4, Morton); finer keys measured slower
-
-__constant__ int c_sort_mode = 5;
-
-PB_D int sort_key(float4 a, float4 b, float3 lo, float3 inv_ext) {
-    if (!(a.w > 0.f)) return kSortBins;
-    if (c_sort_mode == 0) {   // 6 bits direction (octahedral 8x8, Morton) x 6 bits origin cell (4x4x4, Morton)
-        const int db = direction_bin(f3(b));
-        const int cx = min(3, max(0, (int)((a.x - lo.x) * inv_ext.x * 4.f)));
-        const int cy = min(3, max(0, (int)((a.y - lo.y) * inv_ext.y * 4.f)));
-        const int cz = min(3, max(0, (int)((a.z - lo.z) * inv_ext.z * 4.f)));
-        int cell = 0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) cell |= (((cx >> k) & 1) << (3 * k)) | (((cy >> k) & 1) << (3 * k + 1)) | (((cz >> k) & 1) << (3 * k + 2));
-        return (db << 6) | cell;
-    }
-    // 9 bits origin cell (8x8x8, Morton) x 3 bits direction octant, cell-major: a chunk of the stream starts in one small region
-    const int cx = min(7, max(0, (int)((a.x - lo.x) * inv_ext.x * 8.f)));
-    const int cy = min(7, max(0, (int)((a.y - lo.y) * inv_ext.y * 8.f)));
-    const int cz = min(7, max(0, (int)((a.z - lo.z) * inv_ext.z * 8.f)));
-    int cell = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) cell |= (((cx >> k) & 1) << (3 * k)) | (((cy >> k) & 1) << (3 * k + 1)) | (((cz >> k) & 1) << (3 * k + 2));
-    return cell << 3 | (((b.x < 0.f) ? 4 : 0) | ((b.y < 0.f) ? 2 : 0) | ((b.z < 0.f) ? 1 : 0));
-}
-
 // The histogram pass is the only one that reads the rays: it leaves each ray's 13-bit key in `keys` (2 B instead of 32 B for
-// the scatter pass to read back).
-__global__ void __launch_bounds__(1024) k_sort_hist(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, unsigned *__restrict__ hist,
+// the scatter pass to read back). rays == nullptr: the producer of the rays (k_shade) has written the keys already.
+__global__ void __launch_bounds__(1024) k_sort_hist(long long n, const RayRec *__restrict__ rays, float3 lo, float3 inv_ext, int mode, unsigned *__restrict__ hist,
                                                     unsigned short *__restrict__ keys) {
     extern __shared__ unsigned s_hist[];
     for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
-        const int key = sort_key(ldg4(rp), ldg4(rp + 1), lo, inv_ext);
-        keys[i] = (unsigned short)key;
+        int key;
+        if (rays) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+            const float4 a = ldg4(rp), b = ldg4(rp + 1);
+            key = sort_key(f3(a), a.w, f3(b), lo, inv_ext, mode);
+            keys[i] = (unsigned short)key;
+        } else {
+            key = __ldcs(keys + i);
+        }
         atomicAdd(&s_hist[key], 1u);
     }
     __syncthreads();
@@ -130,21 +111,12 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 
 // hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned; keys: n unsigned short
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1) {
+                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready) {
     if (n <= 0) return;
-    {   // debug switch (process-wide like the other pb_debug_set keys); __constant__ memory is per device, so is the record of what it holds
-        static int mode_set[64];
-        static bool init = false;
-        if (!init) { for (int &m : mode_set) m = 5; init = true; }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        int &cur = mode_set[dev & 63];
-        if (cur != g_sort_mode) { cudaMemcpyToSymbolAsync(c_sort_mode, &g_sort_mode, sizeof(int), 0, cudaMemcpyHostToDevice, st); cur = g_sort_mode; }
-    }
     const float3 inv_ext = f3(1.f / fmaxf(hi.x - lo.x, 1e-20f), 1.f / fmaxf(hi.y - lo.y, 1e-20f), 1.f / fmaxf(hi.z - lo.z, 1e-20f));
     cudaMemsetAsync(hist, 0, (kSortBins + 2) * sizeof(unsigned), st);   // hist must hold kSortBins + 2 counters
     const int cnt_bytes = (kSortBins + 1) * (int)sizeof(unsigned);
-    k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, rays, lo, inv_ext, hist, keys);
+    k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, keys_ready ? nullptr : rays, lo, inv_ext, mode, hist, keys);
     k_sort_scan<<<1, 1024, 0, st>>>(hist, active_total);
     k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
