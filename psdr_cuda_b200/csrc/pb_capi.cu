@@ -1620,6 +1620,8 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "rng_seed_table") == 0) { c->rng_seed_table = (int)value; c->rng_seed_count = 0; }
         else if (std::strcmp(key, "trace_kernel") == 0) pb::g_trace_kernel = (int)value;
         else if (std::strcmp(key, "trace_node_min") == 0) pb::g_trace_node_min = (int)value;
+        else if (std::strcmp(key, "trace_chunk") == 0) pb::g_trace_chunk = (int)value;
+        else if (std::strcmp(key, "trace_blocks") == 0) pb::g_trace_blocks = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);
     });
 }

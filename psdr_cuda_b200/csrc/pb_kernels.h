@@ -77,6 +77,7 @@ extern int g_sort_mode;       // debug: sort key (pb_sort.cu)
 extern int g_shade_simple;    // debug: 0 = never use the diffuse + area-light instantiations
 extern int g_shade_tune;      // debug: k_resolve / k_adjoint variant (0 default)
 extern int g_trace_kernel;    // sorted-wavefront traversal kernel: 3 persistent streaming kernel (default), 1 one ray per thread
+extern int g_trace_chunk, g_trace_blocks;   // debug knobs of the streaming kernel
 extern int g_trace_node_min;  // streaming kernel: node steps continue while at least this many lanes descend
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,

@@ -16,8 +16,10 @@
 namespace pb {
 
 int g_sort_mode = SORT_CELL_OCTANT;   // 5: origin cell (8x8x8, Morton) x direction octant; 0: 6-bit direction bin x 4x4x4 cells (A/B: profiles/r02e_*; 16^3 cells without direction: r02m_*)
-int g_trace_kernel = 3;     // 0 first generation (k_trace_perm), 1 compact nodes, 2 compact nodes + postponed leaf, 3 persistent streaming kernel
-int g_trace_node_min = 312;  // streaming kernel: node steps continue while at least this many lanes descend
+int g_trace_kernel = 3;     // 3 persistent streaming kernel; 1 one ray per thread over the same nodes (A/B, profiles/r02a_*)
+int g_trace_chunk = 128;    // most rays per chunk grab of the streaming kernel (128 vs 256: +1 % on 8 Mi-lane wavefronts, profiles/r02q_*)
+int g_trace_blocks = 8;     // debug: persistent blocks per SM launched (<= 8 resident)
+int g_trace_node_min = 16;  // streaming kernel: node steps continue while at least this many lanes descend (1 = plain while-while)
 
 // The histogram pass is the only one that reads the rays: it leaves each ray's 13-bit key in `keys` (2 B instead of 32 B for
 // the scatter pass to read back). rays == nullptr: the producer of the rays (k_shade) has written the keys already.
@@ -125,7 +127,8 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
     if (g_trace_kernel == 3) {
         StreamArgs A;
         A.nodes = S.nodes_c; A.leaf = S.leaf; A.n_active = hist + kSortBins + 1; A.perm = perm; A.rays = rays; A.hits = hits; A.counter = stream_counter;
-        const unsigned grid = (unsigned)std::min<long long>(nblk(n, 128), 148LL * 8);   // persistent: 8 blocks of 4 warps per SM
+        A.chunk_max = (unsigned)std::max(32, g_trace_chunk & ~31);
+        const unsigned grid = (unsigned)std::min<long long>(nblk(n, 128), 148LL * std::max(1, std::min(8, g_trace_blocks)));   // persistent: 8 blocks of 4 warps per SM
         if (g_trace_node_min == 1) k_trace_stream<1, 12, 8, 2><<<grid, 128, 0, st>>>(A);    // node steps until no lane descends (plain while-while; 40 % slower)
         else k_trace_stream<16, 12, 8, 2><<<grid, 128, 0, st>>>(A);
     } else {

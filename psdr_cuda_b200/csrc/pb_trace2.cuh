@@ -124,7 +124,7 @@ PB_D Hit trace_closest_c(const BvhNodeC *__restrict__ nodes, const LeafTri *__re
 // staged ray to every lane whose ray has terminated. Lanes are inner-node, triangle or idle lanes; the warp alternates between
 // node steps (while at least kNodeMin lanes descend) and single-triangle steps, so both instruction streams run nearly full.
 constexpr int kStreamRing = 64;      // staged rays per warp (two blocks of 32)
-constexpr unsigned kStreamChunk = 256;    // most rays per atomic grab
+constexpr unsigned kStreamChunk = 128;    // most rays per atomic grab (StreamArgs::chunk_max)
 
 PB_D void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -141,6 +141,7 @@ struct StreamArgs {
     const RayRec *rays;
     HitRec *hits;
     unsigned *counter;          // chunk cursor (zeroed before the launch)
+    unsigned chunk_max;         // most rays per grab (kStreamChunk; debug: pb_debug_set trace_chunk)
 };
 
 template <int NODE_MIN, int REFILL_MIN, int MINB, int UNROLL>
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_stream(StreamArgs A) {
             if (lane == 0) {
                 const unsigned cur = *reinterpret_cast<volatile unsigned *>(A.counter);
                 const unsigned rem = cur < n ? n - cur : 0u;
-                size = min(kStreamChunk, max(32u, (rem / (gridDim.x * 8u)) & ~31u));
+                size = min(A.chunk_max, max(32u, (rem / (gridDim.x * 8u)) & ~31u));
                 base = atomicAdd(A.counter, size);
             }
             base = __shfl_sync(full, base, 0);
