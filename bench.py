@@ -368,6 +368,7 @@ def run_ours(args):
     if cfg["grads"] == "albedo" and verify is not None and "grad_all_ones" in verify:
         e2e_grad_check = float(sum(float(hg.double().sum()) for hg in h_grads))   # sum of the 12 albedo gradients for dL/dI = 1, through the module
 
+    lanes_per_rank = W * H * SPP // max(1, world)
     total_samples = 2.0 * W * H * SPP * args.steps
     value = total_samples / (ms * 1e-3) / 1e6
     e2e_value = total_samples / (ms_e * 1e-3) / 1e6
@@ -407,7 +408,9 @@ def run_ours(args):
                              "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
                              "rays_per_launch": rays_per_launch, "ray_slots_per_launch": lanes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                              "Grays_per_s": rays_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0,
-                             "note": "BVH traversal without RT cores is bound by instruction issue, the ALU pipe and L1 (ncu: profiles/), not by HBM bytes"},
+                             "note": "BVH traversal without RT cores is bound by instruction issue, the ALU pipe and L1 (ncu: profiles/), not by HBM bytes",
+                             "overlapped": bool(lanes_per_rank <= (20 << 20)),   # short renders run two half-batches on two streams: the per-launch durations then include the other stream's kernels
+                             },
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_dLdI.numel() * 4),
                         "d2h_bytes_per_step": int((h_img_c.numel() + h_img_d.numel() + sum(g.numel() for g in h_grads)) * 4),

@@ -148,15 +148,17 @@ static void configure_sensor(HostSensor &s, int W, int H) {
 // mode: SORT_CELL_OCTANT for rays that start on surfaces, SORT_DIRECTION for rays that share an origin (camera rays of the edge terms);
 // keys_ready: k_shade has left the keys in d_sort_keys
 static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, int mode = -1,
-                            bool keys_ready = false) {
+                            bool keys_ready = false, int lane = 0) {
     if (!c->d_active_total.p) { c->d_active_total.reserve(sizeof(unsigned long long)); cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream); }
-    c->d_sort_hist.reserve(40000 * sizeof(unsigned));
-    c->d_sort_perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
-    c->d_sort_keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
-    c->d_stream_counter.reserve(sizeof(unsigned));
-    launch_trace_sorted(c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
-                        f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), c->d_sort_hist.as<unsigned>(), c->d_sort_perm.as<unsigned>(),
-                        c->d_sort_keys.as<unsigned short>(), c->d_stream_counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1,
+    DevBuf &hist = lane ? c->d_sort_hist1 : c->d_sort_hist, &perm = lane ? c->d_sort_perm1 : c->d_sort_perm, &keys = lane ? c->d_sort_keys1 : c->d_sort_keys,
+           &counter = lane ? c->d_stream_counter1 : c->d_stream_counter;
+    hist.reserve(40000 * sizeof(unsigned));
+    perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
+    keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
+    counter.reserve(sizeof(unsigned));
+    launch_trace_sorted(lane ? c->stream2 : c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
+                        f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), hist.as<unsigned>(), perm.as<unsigned>(),
+                        keys.as<unsigned short>(), counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1,
                         mode < 0 ? g_sort_mode : mode, keys_ready);
     c->launches += 3;
 }
@@ -181,6 +183,7 @@ static void set_l2_window(pb_ctx *c) {
         attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     }
     cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (c->stream2) cudaStreamSetAttribute(c->stream2, cudaStreamAttributeAccessPolicyWindow, &attr);
     cudaGetLastError();
 }
 
@@ -881,7 +884,11 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     PB_ASSERT_MSG(field || !c->emitters.empty(), "No Emitter!");
     const int64_t total = (c->spp > 0 && spp_local > 0) ? local_rows * c->width * spp_local : 0;
     const int R = std::max(1, plan.nb + plan.nl);
-    const int64_t B = std::max<int64_t>(1024, std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024));
+    // two batches in flight on two streams when the render is short (see pb_host.h); forward mode keeps one (its per-lane accumulator)
+    const bool dual = !field && !jvp && total > 2048 && (c->pipeline == 2 || (c->pipeline == 1 && total <= c->pipeline_max_lanes));
+    int64_t B = std::max<int64_t>(1024, std::min<int64_t>(c->batch, ((total + 1023) / 1024) * 1024));
+    if (dual && total <= B) B = std::max<int64_t>(1024, (((total + 1) / 2 + 1023) / 1024) * 1024);   // a single batch: split it in two
+    if (mode == MODE_VJP && c->retained_valid && c->retained_B > 0) B = c->retained_B;   // the retained records are laid out batch by batch ([ray][lane] inside a batch)
     const int D = std::max(1, plan.nbounce);
     const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (16 + 16 * R + 16));
     // which store, and whether the forward pass has to run
@@ -902,6 +909,18 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     size_store(S, use_retained ? total : B, keep ? D : 2, R, B);
     if (mode == MODE_VJP) c->d_suffix.reserve((size_t)B * sizeof(float4));
     c->d_sort_keys.reserve((size_t)B * R * sizeof(unsigned short));   // k_shade writes the sort keys of the rays it emits
+    if (dual) {   // lane 1: its own stream and per-batch buffers
+        if (!c->stream2) {
+            PB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+            PB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            PB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+            set_l2_window(c);
+        }
+        if (!use_retained) size_store(c->scratch1, B, keep ? D : 2, R, B);
+        c->d_rays1.reserve((size_t)B * R * sizeof(RayRec));
+        if (mode == MODE_VJP) c->d_suffix1.reserve((size_t)B * sizeof(float4));
+        c->d_sort_keys1.reserve((size_t)B * R * sizeof(unsigned short));
+    }
     RenderParams P;
     P.S = c->view; P.cam = c->sensors[sensor].rec;
     P.width = c->width; P.height = c->height; P.spp = c->spp; P.inv_spp = 1.f / (float)c->spp;
@@ -1034,7 +1053,19 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         set_sort_params(c, Bp);
     }
     size_t nev = 0, nev_edge = 0;
-    for (int64_t start = 0; start < total && !(field && mode == MODE_VJP); start += B) {
+    cudaStream_t const st0 = st;
+    if (dual) {   // everything enqueued so far (film clear, table uploads) precedes both lanes
+        PB_CUDA(cudaEventRecord(c->ev_fork, st0));
+        PB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    }
+    int batch_index = 0;
+    for (int64_t start = 0; start < total && !(field && mode == MODE_VJP); start += B, ++batch_index) {
+        const int lane = dual ? (batch_index & 1) : 0;
+        st = lane ? c->stream2 : st0;
+        EventStore &S = use_retained ? c->retained : (lane ? c->scratch1 : c->scratch);
+        RayRec *const lane_rays = lane ? c->d_rays1.as<RayRec>() : (use_retained ? c->retained.rays.as<RayRec>() : c->scratch.rays.as<RayRec>());
+        unsigned short *const lane_keys = lane ? c->d_sort_keys1.as<unsigned short>() : c->d_sort_keys.as<unsigned short>();
+        float4 *const lane_suffix = lane ? c->d_suffix1.as<float4>() : c->d_suffix.as<float4>();
         P.local0 = start; P.n = (int)std::min<int64_t>(B, total - start);
         const size_t off = use_retained ? (size_t)start : 0;
         HitRec *hit0 = S.hit0.as<HitRec>() + off;
@@ -1045,12 +1076,12 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.hit_prev = (k == 0 || !keep) ? nullptr : (k == 1 ? hit0 : S.hits[k - 2].as<HitRec>() + off * R);
             E.prev_pos = (k == 0) ? nullptr : S.pos[sp].as<float4>() + off;
             E.pos = S.pos[sl].as<float4>() + off;
-            E.rays = S.rays.as<RayRec>();
+            E.rays = lane_rays;
             E.hits = S.hits[sl].as<HitRec>() + off * R;
             E.thr_in = (k == 0) ? nullptr : S.thr[keep ? k : (k & 1)].as<float4>() + off;
             E.thr_out = bps[k].last ? nullptr : S.thr[keep ? k + 1 : ((k + 1) & 1)].as<float4>() + off;
             E.rad = S.rad.as<float4>() + off;
-            E.keys = c->d_sort_keys.as<unsigned short>();
+            E.keys = lane_keys;
             return E;
         };
         if (run_forward) {
@@ -1067,7 +1098,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 const EventBuffers E = event(k);
                 launch_shade(st, P, bps[k], E);
                 cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
-                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, t0, t1, -1, true);
+                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, t0, t1, -1, true, lane);
                 launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
                 c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
             }
@@ -1076,11 +1107,16 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             for (int ch = 0; ch < (jvp ? 3 : 1); ++ch) {   // forward mode: one pass per colour channel with a unit seed
                 if (jvp) { P.S.jvp_channel = ch; PB_CUDA(cudaMemsetAsync(c->d_jvp_acc.p, 0, (size_t)P.n * sizeof(float), st)); }
                 for (int k = plan.nbounce - 1; k >= 0; --k) {
-                    launch_adjoint(st, P, bps[k], event(k), c->d_suffix.as<float4>(), d_dLdI);
+                    launch_adjoint(st, P, bps[k], event(k), lane_suffix, d_dLdI);
                     c->launches++;
                 }
             }
         }
+    }
+    st = st0;
+    if (dual) {   // join: whatever follows on the context's stream (edge terms, mesh backward, the caller) sees both lanes' results
+        PB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+        PB_CUDA(cudaStreamWaitEvent(st0, c->ev_join, 0));
     }
     if (mode == MODE_VJP && (P.S.tri_grad || (jvp && any_geom_jvp(c)))) run_edge_terms(c, I, sensor, plan, P, d_dLdI, &nev_edge);
     if (mode == MODE_VJP && !jvp)   // adjoint of the envmap's from_world = inverse(left * raw) -> adjoint of `left`: g_L = -(F^T g_F F^T) R^T
@@ -1141,6 +1177,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         }
     }
     if (mode == MODE_D && use_retained) {
+        c->retained_B = B;
         c->retained_valid = true; c->retained_kind = I.kind; c->retained_nb = plan.nb; c->retained_nl = plan.nl;
         c->retained_nbounce = plan.nbounce; c->retained_sensor = sensor; c->retained_hide = I.hide_emitters;
     }
@@ -1193,6 +1230,7 @@ int pb_ctx_destroy(pb_ctx *c) {
     pb_dist_finalize(c);
     if (!c->own_stream && c->l2_persist) { c->l2_persist = 0; set_l2_window(c); }   // leave the caller's stream as it was
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1620,6 +1658,8 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "rng_seed_table") == 0) { c->rng_seed_table = (int)value; c->rng_seed_count = 0; }
         else if (std::strcmp(key, "trace_kernel") == 0) pb::g_trace_kernel = (int)value;
         else if (std::strcmp(key, "trace_node_min") == 0) pb::g_trace_node_min = (int)value;
+        else if (std::strcmp(key, "pipeline") == 0) c->pipeline = (int)value;
+        else if (std::strcmp(key, "pipeline_max_lanes") == 0) c->pipeline_max_lanes = value;
         else if (std::strcmp(key, "trace_chunk") == 0) pb::g_trace_chunk = (int)value;
         else if (std::strcmp(key, "trace_blocks") == 0) pb::g_trace_blocks = (int)value;
         else throw Error(std::string("Unknown debug key: ") + key);

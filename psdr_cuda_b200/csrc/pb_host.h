@@ -179,7 +179,17 @@ struct pb_ctx {
     std::vector<pb::GuideGrid> guides;
     uint64_t last_d_offset_e = 0, last_d_offset_s = 0;
     pb::EventStore scratch, retained;
+    // Second batch in flight (render_interior): short wavefronts (one GPU's share of a multi-GPU job) end in a tail as long as their
+    // longest ray, 10 % of a 12 M-ray launch; two half-batches on two streams fill each other's tails. Lane 0 is the context's own
+    // stream and buffers, lane 1 owns copies of everything a batch scribbles on.
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    pb::EventStore scratch1;
+    pb::DevBuf d_rays1, d_suffix1, d_sort_hist1, d_sort_perm1, d_sort_keys1, d_stream_counter1;
+    int pipeline = 1;                       // 0 never, 1 when a render has at most pipeline_max_lanes lanes, 2 always (debug)
+    int64_t pipeline_max_lanes = 20 << 20;
     int64_t retain_limit = (int64_t)64 << 30;
+    int64_t retained_B = 0;   // batch size of the render that filled the retained store (its layout depends on it)
     bool retained_valid = false;
     int retained_kind = 0, retained_nb = 0, retained_nl = 0, retained_nbounce = 0, retained_sensor = 0, retained_hide = 0;
     // replay info of the last renderD
