@@ -397,12 +397,74 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
     if (RC) rc::flush_const_tex_grad(P.S, rc_tex ? bsdf_id : -1, rc_acc, env_scale_acc, s_rc);
 }
 
+// Reflectance adjoint of one event from the linearisation the forward pass kept (EventBuffers::lin): with L_k = rho * A and
+// w_k = rho * c the event's share of dLoss/d(rho) is gL * A + gw * c and the suffix is S_k = rho * (A + c S_{k+1}) — the same sums
+// k_adjoint forms connection by connection (bsdf_eval_grad_tex), without reconstructing the connections. Diffuse scenes whose
+// only leaves are reflectance textures (no geometry, pose or uv adjoints), reverse mode.
+template <int EV>
+__global__ void __launch_bounds__(256) k_adjoint_lin(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
+    __shared__ float s_acc[kMaxConstBsdf * 3];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 acc = f3(0.f);
+    int bsdf_id = -1;
+    if (i < P.n) {
+        const float4 lin = ldg4(E.lin + i);
+        const float3 A = f3(lin);
+        const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
+        float3 Sk = f3(0.f);
+        if (A.x != 0.f || A.y != 0.f || A.z != 0.f || lin.w != 0.f) {   // (NaN compares unequal: a poisoned event is kept and poisons S_k like k_adjoint's)
+            const Vertex v = load_vertex<EV>(P, B, i, E);
+            if (v.bsdf) {
+                const TexRef &t = v.bsdf->tex[TEX_REFLECTANCE];
+                Sk = tex_eval3(t, v.its.uv) * (A + S_next * lin.w);
+                if (t.grad) {
+                    int pix;
+                    global_lane(P, i, pix);
+                    const float3 rad_final = f3(ldg4(E.rad + i));
+                    float3 g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
+                    if (!isfinite(rad_final.x)) g.x = 0.f;
+                    if (!isfinite(rad_final.y)) g.y = 0.f;
+                    if (!isfinite(rad_final.z)) g.z = 0.f;
+                    float3 T = f3(1.f);
+                    if (!ev_depth0<EV>(B)) T = f3(ldg4(E.thr_in + i));
+                    const float3 gL = g * T;
+                    const float3 gr = gL * A + gL * S_next * lin.w;
+                    if (finite3(gr)) {
+                        if (t.w == 1 && t.h == 1) {
+                            acc = gr;
+                            bsdf_id = (int)(v.bsdf - P.S.bsdfs);
+                        } else {
+                            const TexTap tap = tex_tap(t, v.its.uv);
+                            const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
+                            const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                atomicAdd(t.grad + idx[k] * 3 + 0, gr.x * w[k]);
+                                atomicAdd(t.grad + idx[k] * 3 + 1, gr.y * w[k]);
+                                atomicAdd(t.grad + idx[k] * 3 + 2, gr.z * w[k]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!ev_depth0<EV>(B)) suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
+    }
+    flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
+}
+
+int g_adjoint_lin = 1;
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI) {
     if (P.n <= 0) return;
     const unsigned g = nblk(P.n, 256);
     if (B.rc_grad) { k_adjoint<1, false, true, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
+    if (P.S.simple && g_shade_simple && g_adjoint_lin && E.lin && !P.S.tri_grad && !P.S.tri_tangent) {   // reflectance leaves only: from the kept linearisation
+        if (B.depth == 0) k_adjoint_lin<3><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
+        else k_adjoint_lin<2><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
+        return;
+    }
     if (P.S.simple && g_shade_simple) {
         if (g_shade_tune == 6) k_adjoint<3, false, false, true, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
         else if (B.depth == 0) k_adjoint<3, false, false, true, 3><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);

@@ -639,8 +639,12 @@ static EdgeParams make_edge_params(pb_ctx *c, int sensor, const GuideGrid *guide
     return Q;
 }
 
-static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t ray_lanes) {
+static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t ray_lanes, bool keep_lin = false) {
     if ((int)S.pos.size() < nslots) { S.pos.resize(nslots); S.hits.resize(nslots); }
+    if (keep_lin) {
+        if ((int)S.lin.size() < nslots) S.lin.resize(nslots);
+        for (int k = 0; k < nslots; ++k) S.lin[k].reserve((size_t)lanes * sizeof(float4));
+    }
     if ((int)S.thr.size() < nslots + 1) S.thr.resize(nslots + 1);
     S.hit0.reserve((size_t)lanes * sizeof(HitRec));
     S.rad.reserve((size_t)lanes * sizeof(float4));
@@ -754,6 +758,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.rad = S.rad.as<float4>();
                         c->d_sort_keys.reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(unsigned short));
                         E.keys = c->d_sort_keys.as<unsigned short>();
+                        E.lin = nullptr;
                         launch_shade(st, P, Bp, E);
                         trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr, nullptr, -1, true);
                         launch_resolve(st, P, Bp, E, nullptr);
@@ -890,7 +895,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     if (dual && total <= B) B = std::max<int64_t>(1024, (((total + 1) / 2 + 1023) / 1024) * 1024);   // a single batch: split it in two
     if (mode == MODE_VJP && c->retained_valid && c->retained_B > 0) B = c->retained_B;   // the retained records are laid out batch by batch ([ray][lane] inside a batch)
     const int D = std::max(1, plan.nbounce);
-    const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (16 + 16 * R + 16));
+    const bool lin = c->view.simple != 0 && g_shade_simple != 0;   // diffuse BSDFs + area emitters only: the events' reflectance linearisation is kept for k_adjoint_lin
+    const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (16 + 16 * R + 16 + (lin ? 16 : 0)));
     // which store, and whether the forward pass has to run
     bool use_retained = false, run_forward = true;
     if (mode == MODE_D && !field && !c->grad_segments.empty() && retain_bytes <= c->retain_limit) use_retained = true;
@@ -901,12 +907,12 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         }
     }
     if (use_retained && run_forward) {   // the store may not fit next to what else lives on the device: fall back to re-tracing in the VJP
-        try { size_store(c->retained, total, D, R, B); }
+        try { size_store(c->retained, total, D, R, B, lin); }
         catch (const Error &) { cudaGetLastError(); c->retained.release(); use_retained = false; }
     }
     const bool keep = use_retained || mode == MODE_VJP;   // every event has its own slot
     EventStore &S = use_retained ? c->retained : c->scratch;
-    size_store(S, use_retained ? total : B, keep ? D : 2, R, B);
+    size_store(S, use_retained ? total : B, keep ? D : 2, R, B, keep && lin);
     if (mode == MODE_VJP) c->d_suffix.reserve((size_t)B * sizeof(float4));
     c->d_sort_keys.reserve((size_t)B * R * sizeof(unsigned short));   // k_shade writes the sort keys of the rays it emits
     if (dual) {   // lane 1: its own stream and per-batch buffers
@@ -916,7 +922,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             PB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
             set_l2_window(c);
         }
-        if (!use_retained) size_store(c->scratch1, B, keep ? D : 2, R, B);
+        if (!use_retained) size_store(c->scratch1, B, keep ? D : 2, R, B, keep && lin);
         c->d_rays1.reserve((size_t)B * R * sizeof(RayRec));
         if (mode == MODE_VJP) c->d_suffix1.reserve((size_t)B * sizeof(float4));
         c->d_sort_keys1.reserve((size_t)B * R * sizeof(unsigned short));
@@ -1082,6 +1088,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.thr_out = bps[k].last ? nullptr : S.thr[keep ? k + 1 : ((k + 1) & 1)].as<float4>() + off;
             E.rad = S.rad.as<float4>() + off;
             E.keys = lane_keys;
+            E.lin = (keep && lin) ? S.lin[sl].as<float4>() + off : nullptr;
             return E;
         };
         if (run_forward) {
@@ -1654,6 +1661,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         if (std::strcmp(key, "sort_mode") == 0) pb::g_sort_mode = (int)value;
         else if (std::strcmp(key, "shade_tune") == 0) pb::g_shade_tune = (int)value;
         else if (std::strcmp(key, "shade_simple") == 0) pb::g_shade_simple = (int)value;
+        else if (std::strcmp(key, "adjoint_lin") == 0) pb::g_adjoint_lin = (int)value;
         else if (std::strcmp(key, "l2_persist") == 0) { c->l2_persist = (int)value; set_l2_window(c); }
         else if (std::strcmp(key, "rng_seed_table") == 0) { c->rng_seed_table = (int)value; c->rng_seed_count = 0; }
         else if (std::strcmp(key, "trace_kernel") == 0) pb::g_trace_kernel = (int)value;

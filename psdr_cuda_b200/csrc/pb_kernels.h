@@ -48,6 +48,8 @@ struct EventBuffers {
     float4 *thr_out;         // [n]   T_{k+1}; may be null on the last event
     float4 *rad;             // [n]   radiance accumulated so far (in/out)
     unsigned short *keys;    // [R*n] sort keys of this event's rays, written by k_shade (or null: the sort computes them from the rays)
+    float4 *lin;             // [n]   retained renders of diffuse scenes: the event's linearisation in its vertex' reflectance, (A, c) with
+                             //       L_k = rho * A and w_k = rho * c — written by k_resolve, read by k_adjoint_lin (null: not kept)
 };
 
 void launch_mesh_preprocess(cudaStream_t st, int nv, int nf, int face_offset, int mesh_id, int flags, const float *vraw, const Mat4 &to_world,
@@ -74,6 +76,7 @@ void launch_rng_seed(cudaStream_t st, long long n, ulonglong2 *out);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_sort_mode;       // debug: sort key (pb_sort.cu)
+extern int g_adjoint_lin;     // debug: 0 = reflectance adjoints through k_adjoint (connection by connection) even when the linearisation was kept
 extern int g_shade_simple;    // debug: 0 = never use the diffuse + area-light instantiations
 extern int g_shade_tune;      // debug: k_resolve / k_adjoint variant (0 default)
 extern int g_trace_kernel;    // sorted-wavefront traversal kernel: 3 persistent streaming kernel (default), 1 one ray per thread

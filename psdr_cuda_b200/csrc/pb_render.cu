@@ -98,6 +98,12 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
         Rng rng = make_rng(P, lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         bool has_cont = false;
+        // Diffuse scenes, AD formulation: L_k and w_k are linear in the vertex' reflectance, L_k = rho * A and w_k = rho * c
+        // (f = rho cos_o / pi, diffuse.cpp:25-33; pdf and MIS weight do not depend on rho). A retained render keeps (A, c): the
+        // reflectance adjoint of the event is then gL * A + gw * c (k_adjoint_lin) with no connection to reconstruct.
+        const bool keep_lin = SIMPLE && ev_ad<EV>(B) && E.lin != nullptr;
+        float3 lin_a = f3(0.f);
+        float lin_c = 0.f;
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         for (int j = 0; j < B.nb; ++j) {
             const float3 s3 = rng.next_3d();
@@ -110,14 +116,16 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             a1 = a1 && is_emitter(P.S, its1.shape);
             if (a1 || (B.carry && j == 0 && cont)) {
                 float3 bsdf_val;
-                float pdf0;
+                float pdf0, dk = 0.f;   // dk: d(bsdf_val) / d(rho)
                 if (ev_ad<EV>(B)) {   // direct.cpp:83-95
                     float3 wo = its1.p - its.p;
                     wo = wo / its1.t;
-                    bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, its.sh.to_local(wo), true);
+                    const float3 wo_l = its.sh.to_local(wo);
+                    bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, wo_l, true);
                     const float G = fabsf(dot(its1.n, -wo)) / sqr(its1.t);
                     pdf0 = bs.pdf * G;
                     bsdf_val = bsdf_val * (G / pdf0);
+                    if (keep_lin && v.bsdf && its.wi.z > 0.f && wo_l.z > 0.f) dk = (kInvPi * wo_l.z) * (G / pdf0);
                 } else {      // direct.cpp:96-106
                     const float3 d1 = its.sh.to_world(bs.wo);
                     bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, bs.wo, true);
@@ -128,9 +136,11 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
                 if (a1) {
                     float weight = inv_nb;
                     if (B.nl > 0) weight *= mis_weight(pdf0, emitter_position_pdf<SIMPLE>(P.S, its.p, its1, true));
-                    L += emitter_Le<SIMPLE>(P.S, its1, true) * bsdf_val * weight;
+                    const float3 Le = emitter_Le<SIMPLE>(P.S, its1, true);
+                    L += Le * bsdf_val * weight;
+                    if (keep_lin) lin_a += Le * (dk * weight);
                 }
-                if (B.carry && j == 0 && cont) { w_cont = bsdf_val; has_cont = true; }
+                if (B.carry && j == 0 && cont) { w_cont = bsdf_val; has_cont = true; lin_c = dk; }
             }
         }
         for (int j = 0; j < B.nl; ++j) {
@@ -152,9 +162,12 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
                 bsdf_val = bsdf_val * (G / ps.pdf);
                 float weight = inv_nl;
                 if (B.nb > 0) weight *= mis_weight(ps.pdf, pdf1);
-                L += emitter_Le<SIMPLE>(P.S, its1, true) * bsdf_val * weight;
+                const float3 Le = emitter_Le<SIMPLE>(P.S, its1, true);
+                L += Le * bsdf_val * weight;
+                if (keep_lin && v.bsdf && its.wi.z > 0.f && wo_local.z > 0.f) lin_a += Le * ((kInvPi * wo_local.z) * (G / ps.pdf) * weight);
             }
         }
+        if (keep_lin) E.lin[i] = make_float4(lin_a.x, lin_a.y, lin_a.z, lin_c);
         float3 thr = f3(1.f), rad;
         if (ev_depth0<EV>(B)) {
             rad = B.hide_emitters ? f3(0.f) : emitter_Le<SIMPLE>(P.S, its, its.valid);   // direct.cpp:51

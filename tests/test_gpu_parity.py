@@ -243,6 +243,13 @@ def test_renderD_and_albedo_vjp_vs_oracle(desc, golden):
             ref[3 * b + ch] = float((dLdI.astype(np.float64) * orc.PathIntegrator(3).renderD(osc)[1]).sum())
     assert np.linalg.norm(g - ref) <= 1e-3 * np.linalg.norm(ref)
     assert np.all(np.abs(g - ref) <= 1e-3 * np.abs(ref).max())
+    # the reflectance adjoint from the kept linearisation (k_adjoint_lin, the default here) against the connection-by-connection kernel
+    ctx.debug_set("adjoint_lin", 0)
+    try:
+        g_full = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy()
+    finally:
+        ctx.debug_set("adjoint_lin", 1)
+    assert np.allclose(g_full, g, rtol=1e-4, atol=1e-6), (g_full, g)
     # without retained event records the VJP re-traces the forward pass: same gradient
     ctx_r = make_ctx(desc, opts, grads=True)
     ctx_r.set_retain_limit(0)
@@ -328,6 +335,12 @@ def test_bitmap_texture_gradient_matches_oracle():
     g = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().reshape(tex.shape)
     ref_img, _ = orc.DirectIntegrator(1, 1).renderD(osc)
     assert_image_parity(img, ref_img)
+    ctx.debug_set("adjoint_lin", 0)   # the texel scatter of k_adjoint_lin against k_adjoint's
+    try:
+        g_full = ctx.render_d_vjp(integ, torch.from_numpy(dLdI).cuda()).cpu().numpy().reshape(tex.shape)
+    finally:
+        ctx.debug_set("adjoint_lin", 1)
+    assert np.allclose(g_full, g, rtol=1e-4, atol=1e-5 * np.abs(g).max())
     # directional derivatives for a few random texture directions
     for k in range(3):
         tdir = rng.normal(size=tex.shape).astype(np.float32)
