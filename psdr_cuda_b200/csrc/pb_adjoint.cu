@@ -413,10 +413,14 @@ __global__ void __launch_bounds__(256) k_adjoint_lin(RenderParams P, BounceParam
         const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
         float3 Sk = f3(0.f);
         if (A.x != 0.f || A.y != 0.f || A.z != 0.f || lin.w != 0.f) {   // (NaN compares unequal: a poisoned event is kept and poisons S_k like k_adjoint's)
-            const Vertex v = load_vertex<EV>(P, B, i, E);
-            if (v.bsdf) {
-                const TexRef &t = v.bsdf->tex[TEX_REFLECTANCE];
-                Sk = tex_eval3(t, v.its.uv) * (A + S_next * lin.w);
+            const float4 vc = ldg4(E.vc + i);   // the vertex record's (uv, mesh id)
+            const int shape = __float_as_int(vc.z);
+            const int bid = shape >= 0 ? P.S.meshes[shape].bsdf : -1;
+            if (bid >= 0) {
+                const BsdfRec *bsdf = P.S.bsdfs + bid;
+                const float2 uv = make_float2(vc.x, vc.y);
+                const TexRef &t = bsdf->tex[TEX_REFLECTANCE];
+                Sk = tex_eval3(t, uv) * (A + S_next * lin.w);
                 if (t.grad) {
                     int pix;
                     global_lane(P, i, pix);
@@ -432,9 +436,9 @@ __global__ void __launch_bounds__(256) k_adjoint_lin(RenderParams P, BounceParam
                     if (finite3(gr)) {
                         if (t.w == 1 && t.h == 1) {
                             acc = gr;
-                            bsdf_id = (int)(v.bsdf - P.S.bsdfs);
+                            bsdf_id = bid;
                         } else {
-                            const TexTap tap = tex_tap(t, v.its.uv);
+                            const TexTap tap = tex_tap(t, uv);
                             const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
                             const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
 #pragma unroll

@@ -640,7 +640,7 @@ static EdgeParams make_edge_params(pb_ctx *c, int sensor, const GuideGrid *guide
 }
 
 static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t ray_lanes, bool keep_lin = false) {
-    if ((int)S.pos.size() < nslots) { S.pos.resize(nslots); S.hits.resize(nslots); }
+    if ((int)S.pos.size() < nslots) { S.pos.resize(nslots); S.vb.resize(nslots); S.vc.resize(nslots); S.hits.resize(nslots); }
     if (keep_lin) {
         if ((int)S.lin.size() < nslots) S.lin.resize(nslots);
         for (int k = 0; k < nslots; ++k) S.lin[k].reserve((size_t)lanes * sizeof(float4));
@@ -649,7 +649,10 @@ static void size_store(EventStore &S, int64_t lanes, int nslots, int R, int64_t 
     S.hit0.reserve((size_t)lanes * sizeof(HitRec));
     S.rad.reserve((size_t)lanes * sizeof(float4));
     S.rays.reserve((size_t)ray_lanes * R * sizeof(RayRec));
-    for (int k = 0; k < nslots; ++k) { S.pos[k].reserve((size_t)lanes * sizeof(float4)); S.hits[k].reserve((size_t)lanes * R * sizeof(HitRec)); }
+    for (int k = 0; k < nslots; ++k) {
+        S.pos[k].reserve((size_t)lanes * sizeof(float4)); S.vb[k].reserve((size_t)lanes * sizeof(float4)); S.vc[k].reserve((size_t)lanes * sizeof(float4));
+        S.hits[k].reserve((size_t)lanes * R * sizeof(HitRec));
+    }
     for (int k = 0; k < nslots + 1; ++k) S.thr[k].reserve((size_t)lanes * sizeof(float4));
 }
 
@@ -750,7 +753,10 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.hit_cur = (k == 0) ? hit0 : S.hits[(k - 1) & 1].as<HitRec>();
                         E.hit_prev = nullptr;
                         E.prev_pos = (k == 0) ? nullptr : S.pos[(k - 1) & 1].as<float4>();
-                        E.pos = S.pos[k & 1].as<float4>();
+                        E.pos = S.pos[k & 1].as<float4>(); E.vb = S.vb[k & 1].as<float4>(); E.vc = S.vc[k & 1].as<float4>();
+                        E.next_pos = Bp.last ? nullptr : S.pos[(k + 1) & 1].as<float4>();
+                        E.next_vb = Bp.last ? nullptr : S.vb[(k + 1) & 1].as<float4>();
+                        E.next_vc = Bp.last ? nullptr : S.vc[(k + 1) & 1].as<float4>();
                         E.rays = S.rays.as<RayRec>();
                         E.hits = S.hits[k & 1].as<HitRec>();
                         E.thr_in = (k == 0) ? nullptr : S.thr[k & 1].as<float4>();
@@ -896,7 +902,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     if (mode == MODE_VJP && c->retained_valid && c->retained_B > 0) B = c->retained_B;   // the retained records are laid out batch by batch ([ray][lane] inside a batch)
     const int D = std::max(1, plan.nbounce);
     const bool lin = c->view.simple != 0 && g_shade_simple != 0;   // diffuse BSDFs + area emitters only: the events' reflectance linearisation is kept for k_adjoint_lin
-    const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (16 + 16 * R + 16 + (lin ? 16 : 0)));
+    const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (48 + 16 * R + 16 + (lin ? 16 : 0)));
     // which store, and whether the forward pass has to run
     bool use_retained = false, run_forward = true;
     if (mode == MODE_D && !field && !c->grad_segments.empty() && retain_bytes <= c->retain_limit) use_retained = true;
@@ -1081,7 +1087,11 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.hit_cur = (k == 0) ? hit0 : S.hits[sp].as<HitRec>() + off * R;
             E.hit_prev = (k == 0 || !keep) ? nullptr : (k == 1 ? hit0 : S.hits[k - 2].as<HitRec>() + off * R);
             E.prev_pos = (k == 0) ? nullptr : S.pos[sp].as<float4>() + off;
-            E.pos = S.pos[sl].as<float4>() + off;
+            E.pos = S.pos[sl].as<float4>() + off; E.vb = S.vb[sl].as<float4>() + off; E.vc = S.vc[sl].as<float4>() + off;
+            const int nsl = keep ? k + 1 : ((k + 1) & 1);
+            E.next_pos = bps[k].last ? nullptr : S.pos[nsl].as<float4>() + off;
+            E.next_vb = bps[k].last ? nullptr : S.vb[nsl].as<float4>() + off;
+            E.next_vc = bps[k].last ? nullptr : S.vc[nsl].as<float4>() + off;
             E.rays = lane_rays;
             E.hits = S.hits[sl].as<HitRec>() + off * R;
             E.thr_in = (k == 0) ? nullptr : S.thr[keep ? k : (k & 1)].as<float4>() + off;

@@ -111,8 +111,8 @@ struct GradSegment { int kind, id, slot; int64_t offset, count; };
 // per-event wavefront records, either one batch worth (scratch) or the whole shard (retained for the VJP)
 struct EventStore {
     DevBuf hit0, rad, rays;
-    std::vector<DevBuf> pos, hits, thr, lin;
-    void release() { hit0.release(); rad.release(); rays.release(); pos.clear(); hits.clear(); thr.clear(); lin.clear(); }
+    std::vector<DevBuf> pos, vb, vc, hits, thr, lin;   // per event slot: vertex record (a = pos, b, c), hits of its rays, throughput, linearisation
+    void release() { hit0.release(); rad.release(); rays.release(); pos.clear(); vb.clear(); vc.clear(); hits.clear(); thr.clear(); lin.clear(); }
 };
 
 }  // namespace pb

@@ -41,7 +41,10 @@ struct EventBuffers {
     const HitRec *hit_cur;   // [n]   hit that created this event's vertex
     const HitRec *hit_prev;  // [n]   adjoint only: hit that created the previous vertex (null at depth 0)
     const float4 *prev_pos;  // [n]   position of the previous vertex (origin of the ray that found hit_cur); unused at depth 0
-    float4 *pos;             // [n]   this vertex' position, written by k_shade
+    float4 *pos;             // [n]   this vertex' record, part a = (p, wi.x). The record (48 B: position, shading normal, local incident
+    float4 *vb, *vc;         // [n]   direction, uv, mesh id) is written by whoever reconstructs the vertex first — k_shade at the camera vertex,
+                             //       k_resolve(k) for vertex k+1 (the hit of its continuation ray) — b = (n_sh, wi.y), c = (uv, mesh id or -1, wi.z)
+    float4 *next_pos, *next_vb, *next_vc;   // [n] record of the next event's vertex, written by k_resolve (null: there is no next event)
     RayRec *rays;            // [R*n] rays of this event (scratch, ray j of lane i at j*n + i)
     HitRec *hits;            // [R*n] their hits
     const float4 *thr_in;    // [n]   throughput T_k (.w != 0: the path is dead); unused at depth 0

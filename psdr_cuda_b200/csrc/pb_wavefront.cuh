@@ -15,8 +15,17 @@ namespace pb {
 // (= RNG stream id, integrator.cpp:76) is pix*spp + s, so results do not depend on the GPU count or on the partition.
 PB_D long long global_lane(const RenderParams &P, int i, int &pix) {
     const long long li = P.local0 + i;
-    int lp = (int)(li / P.spp_local);
-    const int s = (int)(li - (long long)lp * P.spp_local);
+    const unsigned sl = (unsigned)P.spp_local;
+    int lp, s;
+    if ((sl & (sl - 1u)) == 0u) {   // the usual power-of-two sample count: shift / mask instead of the 64-bit division routine (uniform branches)
+        const int sh = 31 - __clz((int)sl);
+        lp = (int)(li >> sh); s = (int)((unsigned)li & (sl - 1u));
+    } else if (li < 0x100000000LL) {
+        const unsigned q = (unsigned)li / sl;
+        lp = (int)q; s = (int)((unsigned)li - q * sl);
+    } else {
+        lp = (int)(li / P.spp_local); s = (int)(li - (long long)lp * P.spp_local);
+    }
     if (P.tile_rows > 0) {   // local row -> global row of this shard's tiles (only the last tile of the image can be partial)
         const int lr = lp / P.width, x = lp - lr * P.width;
         const int t = lr / P.tile_rows;
@@ -106,6 +115,32 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
         v.ro = f3(ldg4(E.prev_pos + i)); v.rd = f3(0.f);
         v.its = reconstruct_its(P.S, h, v.ro);
     }
+    v.active = v.its.valid;
+    v.bsdf = its_bsdf(P.S, v.its);
+    if (P.S.emitter_env >= 0) v.active = v.active && v.bsdf != nullptr;   // direct.cpp:54-57
+    return v;
+}
+
+// Vertex record (EventBuffers::pos / vb / vc): what the event kernels need of a path vertex, written once by whoever reconstructs it
+// first and read by the kernels that would otherwise each rebuild it from the hit, the previous position and the triangle row.
+PB_D void store_vertex_rec(float4 *pa, float4 *pb, float4 *pc, int i, const Its &its, bool alive) {
+    if (alive) {
+        pa[i] = make_float4(its.p.x, its.p.y, its.p.z, its.wi.x);
+        pb[i] = make_float4(its.sh.n.x, its.sh.n.y, its.sh.n.z, its.wi.y);
+        pc[i] = make_float4(its.uv.x, its.uv.y, __int_as_float(its.shape), its.wi.z);
+    } else {   // no hit / dead path: what reconstruct_its returns for an invalid hit
+        pa[i] = make_float4(0.f, 0.f, 0.f, 0.f); pb[i] = make_float4(0.f, 0.f, 0.f, 0.f); pc[i] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+    }
+}
+PB_D Vertex load_vertex_rec(const RenderParams &P, const EventBuffers &E, int i) {
+    const float4 a = ldg4(E.pos + i), b = ldg4(E.vb + i), c = ldg4(E.vc + i);
+    Vertex v;
+    v.its.p = f3(a); v.its.wi = f3(a.w, b.w, c.w);
+    v.its.sh = Frame(f3(b));
+    v.its.uv = make_float2(c.x, c.y);
+    v.its.shape = __float_as_int(c.z); v.its.tri = -1;
+    v.its.valid = v.its.shape >= 0;
+    v.its.n = f3(0.f); v.its.t = 0.f;   // the vertex' own geometric normal / distance are not used by the event kernels
     v.active = v.its.valid;
     v.bsdf = its_bsdf(P.S, v.its);
     if (P.S.emitter_env >= 0) v.active = v.active && v.bsdf != nullptr;   // direct.cpp:54-57
