@@ -71,29 +71,54 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist,
     }
 }
 
-// Scatter with block-level aggregation: lanes rank themselves inside the block with shared-memory atomics, then one
-// global atomic per (block, non-empty bin) reserves the block's range. Rays arrive in pixel order, so the lanes in flight
-// at any moment share an origin cell and hammer ~64 counters; per-lane global atomics serialised on them.
-__global__ void __launch_bounds__(1024) k_sort_scatter(long long n, const unsigned short *__restrict__ keys, unsigned *__restrict__ cursor,
-                                                       unsigned *__restrict__ perm, HitRec *__restrict__ hits) {
+// Scatter with warp- and block-level aggregation. Rays arrive in pixel order, so the lanes in flight at any moment share an origin
+// cell and fall into a few dozen of the 4096 bins: a warp first groups its lanes by key (match.any: at most 8 octants of one cell),
+// one lane per group ranks the group inside the block with a shared-memory atomic, and one global atomic per (block, non-empty
+// bin) reserves the block's range. A block handles kScatterItems rays per thread: the zeroing / reservation sweep over the 4096
+// shared counters is paid once per 8192+ rays, and a bin's rays of one block land in consecutive slots (whole sectors).
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_sort_scatter(long long n, const unsigned short *__restrict__ keys, unsigned *__restrict__ cursor,
+                                                          unsigned *__restrict__ perm, HitRec *__restrict__ hits) {
     extern __shared__ unsigned s_cnt[];
-    for (int t = threadIdx.x; t <= kSortBins; t += blockDim.x) s_cnt[t] = 0;
+    for (int t = threadIdx.x; t <= kSortBins; t += THREADS) s_cnt[t] = 0;
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int key = kSortBins;
-    unsigned rank = 0;
-    if (i < n) {
-        key = __ldcs(keys + i);
-        if (key == kSortBins) reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);   // inactive lane: a miss
-        else rank = atomicAdd(&s_cnt[key], 1u);
+    const long long base = (long long)blockIdx.x * (THREADS * ITEMS) + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    unsigned kr[ITEMS];   // key << 16 | rank inside the block (< 65536)
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const long long i = base + (long long)k * THREADS;
+        unsigned key = kSortBins, rank = 0;
+        if (i < n) {
+            key = __ldcs(keys + i);
+            if (key == kSortBins) reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);   // inactive lane: a miss
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        if (key != kSortBins) {
+            unsigned first = 0;
+            const int leader = __ffs(grp) - 1;
+            if ((int)lane == leader) first = atomicAdd(&s_cnt[key], (unsigned)__popc(grp));
+            rank = __shfl_sync(grp, first, leader) + (unsigned)__popc(grp & lt_mask);
+        }
+        kr[k] = key << 16 | rank;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < kSortBins; t += blockDim.x) {
-        const unsigned c = s_cnt[t];
-        if (c) s_cnt[t] = atomicAdd(cursor + t, c);
+    {   // reserve the block's range of every non-empty bin: the atomics of a thread's bins are issued together
+        constexpr int PER = kSortBins / THREADS;
+        unsigned c[PER], g[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) c[k] = s_cnt[threadIdx.x + k * THREADS];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) g[k] = c[k] ? atomicAdd(cursor + threadIdx.x + k * THREADS, c[k]) : 0u;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) s_cnt[threadIdx.x + k * THREADS] = g[k];
     }
     __syncthreads();
-    if (key != kSortBins) perm[s_cnt[key] + rank] = (unsigned)i;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const unsigned key = kr[k] >> 16;
+        if (key != kSortBins) perm[s_cnt[key] + (kr[k] & 0xffffu)] = (unsigned)(base + (long long)k * THREADS);
+    }
 }
 
 // one ray per thread over the compact nodes (pb_trace2.cuh)
@@ -120,7 +145,7 @@ void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const
     const int cnt_bytes = (kSortBins + 1) * (int)sizeof(unsigned);
     k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, keys_ready ? nullptr : rays, lo, inv_ext, mode, hist, keys);
     k_sort_scan<<<1, 1024, 0, st>>>(hist, active_total);
-    k_sort_scatter<<<nblk(n, 1024), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);
+    k_sort_scatter<1024, 8><<<nblk(n, 1024 * 8), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);   // 512 x 8, 1024 x 4, 512 x 16, 256 x 16: the same within noise; 1024 x 16 / x 32: -1.5 % (profiles/r02ab_*)
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
     if (g_trace_kernel == 3) cudaMemsetAsync(stream_counter, 0, sizeof(unsigned), st);
     if (ev0) cudaEventRecord(ev0, st);   // the pair brackets the traversal kernel alone (roofline: 48 B per traced ray / this duration)
