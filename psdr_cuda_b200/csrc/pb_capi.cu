@@ -147,8 +147,9 @@ static void configure_sensor(HostSensor &s, int W, int H) {
 // then the streaming traversal kernel over the sorted stream (pb_sort.cu, pb_trace2.cuh)
 // mode: SORT_CELL_OCTANT for rays that start on surfaces, SORT_DIRECTION for rays that share an origin (camera rays of the edge terms);
 // keys_ready: k_shade has left the keys in d_sort_keys
+// sorted_inv: sorted-copy mode — `hits` receives the hits in stream order and *sorted_inv the map ray slot -> stream position
 static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hits, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, int mode = -1,
-                            bool keys_ready = false, int lane = 0) {
+                            bool keys_ready = false, int lane = 0, const unsigned **sorted_inv = nullptr) {
     if (!c->d_active_total.p) { c->d_active_total.reserve(sizeof(unsigned long long)); cudaMemsetAsync(c->d_active_total.p, 0, sizeof(unsigned long long), c->stream); }
     DevBuf &hist = lane ? c->d_sort_hist1 : c->d_sort_hist, &perm = lane ? c->d_sort_perm1 : c->d_sort_perm, &keys = lane ? c->d_sort_keys1 : c->d_sort_keys,
            &counter = lane ? c->d_stream_counter1 : c->d_stream_counter;
@@ -156,10 +157,18 @@ static void trace_wavefront(pb_ctx *c, int64_t n, const RayRec *rays, HitRec *hi
     perm.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
     keys.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned short));
     counter.reserve(sizeof(unsigned));
+    RayRec *sorted = nullptr;
+    unsigned *inv = nullptr;
+    if (sorted_inv) {
+        c->d_sorted_rays[lane].reserve((size_t)std::max<int64_t>(n, 1) * sizeof(RayRec));
+        c->d_sort_inv[lane].reserve((size_t)std::max<int64_t>(n, 1) * sizeof(unsigned));
+        sorted = c->d_sorted_rays[lane].as<RayRec>(); inv = c->d_sort_inv[lane].as<unsigned>();
+        *sorted_inv = inv;
+    }
     launch_trace_sorted(lane ? c->stream2 : c->stream, c->view, n, rays, hits, f3(c->scene_lo[0], c->scene_lo[1], c->scene_lo[2]),
                         f3(c->scene_hi[0], c->scene_hi[1], c->scene_hi[2]), hist.as<unsigned>(), perm.as<unsigned>(),
                         keys.as<unsigned short>(), counter.as<unsigned>(), c->d_active_total.as<unsigned long long>(), ev0, ev1,
-                        mode < 0 ? g_sort_mode : mode, keys_ready);
+                        mode < 0 ? g_sort_mode : mode, keys_ready, sorted, inv);
     c->launches += 3;
 }
 
@@ -764,7 +773,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.rad = S.rad.as<float4>();
                         c->d_sort_keys.reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(unsigned short));
                         E.keys = c->d_sort_keys.as<unsigned short>();
-                        E.lin = nullptr;
+                        E.lin = nullptr; E.inv = nullptr;
                         launch_shade(st, P, Bp, E);
                         trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr, nullptr, -1, true);
                         launch_resolve(st, P, Bp, E, nullptr);
@@ -903,12 +912,17 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     const int D = std::max(1, plan.nbounce);
     const bool lin = c->view.simple != 0 && g_shade_simple != 0;   // diffuse BSDFs + area emitters only: the events' reflectance linearisation is kept for k_adjoint_lin
     const int64_t retain_bytes = total * (16 + 16 + (int64_t)D * (48 + 16 * R + 16 + (lin ? 16 : 0)));
+    // every leaf is a reflectance texture of a diffuse scene, reverse mode: k_adjoint_lin runs and no kernel reads an event's hit records after its k_resolve
+    bool lin_only = lin && !jvp && g_adjoint_lin != 0;
+    for (const GradSegment &g : c->grad_segments) if (g.kind != PB_PARAM_BSDF_TEXTURE) lin_only = false;
+    const bool sorted_copy = c->sorted_copy != 0 && !field;
     // which store, and whether the forward pass has to run
     bool use_retained = false, run_forward = true;
     if (mode == MODE_D && !field && !c->grad_segments.empty() && retain_bytes <= c->retain_limit) use_retained = true;
     if (mode == MODE_VJP) {
         if (c->retained_valid && c->retained_kind == I.kind && c->retained_nb == plan.nb && c->retained_nl == plan.nl &&
-            c->retained_nbounce == plan.nbounce && c->retained_sensor == sensor && c->retained_hide == I.hide_emitters) {
+            c->retained_nbounce == plan.nbounce && c->retained_sensor == sensor && c->retained_hide == I.hide_emitters &&
+            (c->retained_hits_by_slot || lin_only)) {
             use_retained = true; run_forward = false;
         }
     }
@@ -917,6 +931,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         catch (const Error &) { cudaGetLastError(); c->retained.release(); use_retained = false; }
     }
     const bool keep = use_retained || mode == MODE_VJP;   // every event has its own slot
+    const bool hits_by_slot = keep && !lin_only;          // sorted-copy traversal: hits are un-permuted for the kernels that index them by ray slot
     EventStore &S = use_retained ? c->retained : c->scratch;
     size_store(S, use_retained ? total : B, keep ? D : 2, R, B, keep && lin);
     if (mode == MODE_VJP) c->d_suffix.reserve((size_t)B * sizeof(float4));
@@ -1099,6 +1114,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.rad = S.rad.as<float4>() + off;
             E.keys = lane_keys;
             E.lin = (keep && lin) ? S.lin[sl].as<float4>() + off : nullptr;
+            E.inv = nullptr;
             return E;
         };
         if (run_forward) {
@@ -1112,12 +1128,23 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 continue;
             }
             for (int k = 0; k < plan.nbounce; ++k) {
-                const EventBuffers E = event(k);
+                EventBuffers E = event(k);
                 launch_shade(st, P, bps[k], E);
                 cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
-                trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, t0, t1, -1, true, lane);
+                const int64_t nrays = (int64_t)P.n * (plan.nb + plan.nl);
+                if (!sorted_copy) {
+                    trace_wavefront(c, nrays, E.rays, E.hits, t0, t1, -1, true, lane);
+                } else if (hits_by_slot) {   // someone indexes this event's hits by ray slot later (k_adjoint, the next event's load_vertex): un-permute them
+                    c->d_sorted_hits[lane].reserve((size_t)nrays * sizeof(HitRec));
+                    const unsigned *inv = nullptr;
+                    trace_wavefront(c, nrays, E.rays, c->d_sorted_hits[lane].as<HitRec>(), t0, t1, -1, true, lane, &inv);
+                    launch_unpermute_hits(st, nrays, inv, c->d_sorted_hits[lane].as<HitRec>(), E.hits);
+                    c->launches++;
+                } else {                     // k_resolve is the only reader: it follows the inverse map
+                    trace_wavefront(c, nrays, E.rays, E.hits, t0, t1, -1, true, lane, &E.inv);
+                }
                 launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
-                c->launches += 3; c->last_rays += (int64_t)P.n * (plan.nb + plan.nl); c->last_trace_launches++;
+                c->launches += 3; c->last_rays += nrays; c->last_trace_launches++;
             }
         }
         if (mode == MODE_VJP) {
@@ -1195,6 +1222,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     }
     if (mode == MODE_D && use_retained) {
         c->retained_B = B;
+        c->retained_hits_by_slot = !sorted_copy || hits_by_slot;
         c->retained_valid = true; c->retained_kind = I.kind; c->retained_nb = plan.nb; c->retained_nl = plan.nl;
         c->retained_nbounce = plan.nbounce; c->retained_sensor = sensor; c->retained_hide = I.hide_emitters;
     }
@@ -1680,6 +1708,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "pipeline_max_lanes") == 0) c->pipeline_max_lanes = value;
         else if (std::strcmp(key, "trace_chunk") == 0) pb::g_trace_chunk = (int)value;
         else if (std::strcmp(key, "trace_blocks") == 0) pb::g_trace_blocks = (int)value;
+        else if (std::strcmp(key, "sorted_copy") == 0) { c->sorted_copy = (int)value; c->retained_valid = false; }
         else throw Error(std::string("Unknown debug key: ") + key);
     });
 }

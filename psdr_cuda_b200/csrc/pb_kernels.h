@@ -51,6 +51,8 @@ struct EventBuffers {
     float4 *thr_out;         // [n]   T_{k+1}; may be null on the last event
     float4 *rad;             // [n]   radiance accumulated so far (in/out)
     unsigned short *keys;    // [R*n] sort keys of this event's rays, written by k_shade (or null: the sort computes them from the rays)
+    const unsigned *inv;     // [R*n] sorted-copy traversal: `hits` is in stream order and inv[j*n + i] is the position of ray j of lane i (~0: inactive
+                             //       lane, a miss); null: hits are indexed by ray slot
     float4 *lin;             // [n]   retained renders of diffuse scenes: the event's linearisation in its vertex' reflectance, (A, c) with
                              //       L_k = rho * A and w_k = rho * c — written by k_resolve, read by k_adjoint_lin (null: not kept)
 };
@@ -87,7 +89,9 @@ extern int g_trace_chunk, g_trace_blocks;   // debug knobs of the streaming kern
 extern int g_trace_node_min;  // streaming kernel: node steps continue while at least this many lanes descend
 void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float *t_out);
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready);
+                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready,
+                         RayRec *sorted = nullptr, unsigned *inv = nullptr);
+void launch_unpermute_hits(cudaStream_t st, long long n, const unsigned *inv, const HitRec *sorted_hits, HitRec *hits);
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);

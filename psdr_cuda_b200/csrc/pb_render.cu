@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
     int pix = -1;
     float3 out = f3(0.f);
     if (in_range) {
-        if (PREFETCH) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
+        if (PREFETCH && !E.inv) prefetch_event_hits(P.S, hits, B.nb + B.nl, P.n, i);
         const long long lane = global_lane(P, i, pix);
         const Vertex v = load_vertex_rec(P, E, i);
         const Its &its = v.its;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             const float3 s3 = rng.next_3d();
             const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, its, s3, v.active);
             bool a1 = v.active && bs.valid;
-            const HitRec h1 = load_hit(hits + (size_t)j * P.n + i);
+            const HitRec h1 = event_hit(E, j, P.n, i);
             const Its its1 = reconstruct_its(P.S, h1, its.p);
             a1 = a1 && its1.valid;
             const bool cont = a1;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             const float dist_sqr = squared_norm(wo);
             const float dist = safe_sqrt(dist_sqr);
             wo = wo / dist;
-            const HitRec h1 = load_hit(hits + (size_t)(B.nb + j) * P.n + i);
+            const HitRec h1 = event_hit(E, B.nb + j, P.n, i);
             const Its its1 = reconstruct_its(P.S, h1, its.p);
             a1 = a1 && its1.valid && (its1.t > dist - kShadowEpsilon) && is_emitter(P.S, its1.shape);
             if (a1) {

@@ -76,9 +76,13 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *__restrict__ hist,
 // one lane per group ranks the group inside the block with a shared-memory atomic, and one global atomic per (block, non-empty
 // bin) reserves the block's range. A block handles kScatterItems rays per thread: the zeroing / reservation sweep over the 4096
 // shared counters is paid once per 8192+ rays, and a bin's rays of one block land in consecutive slots (whole sectors).
-template <int THREADS, int ITEMS>
+// COPY: instead of the permutation (stream position -> ray slot) the pass writes the rays themselves in stream order and the inverse map
+// (ray slot -> stream position, ~0 for an inactive lane): the traversal kernel then reads its rays and writes its hits contiguously, and the
+// consumer of the hits follows `inv`.
+template <int THREADS, int ITEMS, bool COPY>
 __global__ void __launch_bounds__(THREADS) k_sort_scatter(long long n, const unsigned short *__restrict__ keys, unsigned *__restrict__ cursor,
-                                                          unsigned *__restrict__ perm, HitRec *__restrict__ hits) {
+                                                          unsigned *__restrict__ perm, HitRec *__restrict__ hits, const RayRec *__restrict__ rays,
+                                                          RayRec *__restrict__ sorted, unsigned *__restrict__ inv) {
     extern __shared__ unsigned s_cnt[];
     for (int t = threadIdx.x; t <= kSortBins; t += THREADS) s_cnt[t] = 0;
     __syncthreads();
@@ -91,7 +95,10 @@ __global__ void __launch_bounds__(THREADS) k_sort_scatter(long long n, const uns
         unsigned key = kSortBins, rank = 0;
         if (i < n) {
             key = __ldcs(keys + i);
-            if (key == kSortBins) reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);   // inactive lane: a miss
+            if (key == kSortBins) {   // inactive lane: a miss
+                if (COPY) inv[i] = 0xffffffffu;
+                else reinterpret_cast<float4 *>(hits)[i] = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);
+            }
         }
         const unsigned grp = __match_any_sync(0xffffffffu, key);
         if (key != kSortBins) {
@@ -117,7 +124,19 @@ __global__ void __launch_bounds__(THREADS) k_sort_scatter(long long n, const uns
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const unsigned key = kr[k] >> 16;
-        if (key != kSortBins) perm[s_cnt[key] + (kr[k] & 0xffffu)] = (unsigned)(base + (long long)k * THREADS);
+        if (key != kSortBins) {
+            const unsigned pos = s_cnt[key] + (kr[k] & 0xffffu);
+            const long long i = base + (long long)k * THREADS;
+            if (COPY) {
+                const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+                const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
+                float4 *sp = reinterpret_cast<float4 *>(sorted + pos);
+                sp[0] = a; sp[1] = b;
+                inv[i] = pos;
+            } else {
+                perm[pos] = (unsigned)i;
+            }
+        }
     }
 }
 
@@ -134,24 +153,40 @@ __global__ void __launch_bounds__(128, MINB) k_trace_compact(const BvhNodeC *__r
     __stcs(reinterpret_cast<float4 *>(hits) + i, make_float4(__int_as_float(h.tri), __int_as_float(h.shape), h.u, h.v));
 }
 
+// sorted-copy mode, for consumers that index hits by ray slot: hits[i] = sorted_hits[inv[i]] (a miss where inv[i] = ~0)
+__global__ void __launch_bounds__(256) k_unpermute_hits(long long n, const unsigned *__restrict__ inv, const HitRec *__restrict__ sorted_hits, HitRec *__restrict__ hits) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned p = __ldcs(inv + i);
+    float4 h = make_float4(__int_as_float(-1), __int_as_float(-1), -1.f, -1.f);
+    if (p != 0xffffffffu) h = __ldcs(reinterpret_cast<const float4 *>(sorted_hits) + p);
+    reinterpret_cast<float4 *>(hits)[i] = h;
+}
+
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+void launch_unpermute_hits(cudaStream_t st, long long n, const unsigned *inv, const HitRec *sorted_hits, HitRec *hits) {
+    if (n > 0) k_unpermute_hits<<<nblk(n, 256), 256, 0, st>>>(n, inv, sorted_hits, hits);
+}
 
 // hist: kSortBins + 2 unsigned (zeroed here); perm: n unsigned; keys: n unsigned short
+// sorted != nullptr: sorted-copy mode (see k_sort_scatter<COPY>): `hits` receives the hits in stream order, inv[ray slot] their positions
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
-                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready) {
+                         unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready,
+                         RayRec *sorted, unsigned *inv) {
     if (n <= 0) return;
     const float3 inv_ext = f3(1.f / fmaxf(hi.x - lo.x, 1e-20f), 1.f / fmaxf(hi.y - lo.y, 1e-20f), 1.f / fmaxf(hi.z - lo.z, 1e-20f));
     cudaMemsetAsync(hist, 0, (kSortBins + 2) * sizeof(unsigned), st);   // hist must hold kSortBins + 2 counters
     const int cnt_bytes = (kSortBins + 1) * (int)sizeof(unsigned);
     k_sort_hist<<<(unsigned)std::min<long long>(nblk(n, 1024), 148), 1024, cnt_bytes, st>>>(n, keys_ready ? nullptr : rays, lo, inv_ext, mode, hist, keys);
     k_sort_scan<<<1, 1024, 0, st>>>(hist, active_total);
-    k_sort_scatter<1024, 8><<<nblk(n, 1024 * 8), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits);   // 512 x 8, 1024 x 4, 512 x 16, 256 x 16: the same within noise; 1024 x 16 / x 32: -1.5 % (profiles/r02ab_*)
+    if (sorted) k_sort_scatter<1024, 8, true><<<nblk(n, 1024 * 8), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits, rays, sorted, inv);
+    else k_sort_scatter<1024, 8, false><<<nblk(n, 1024 * 8), 1024, cnt_bytes, st>>>(n, keys, hist, perm, hits, rays, sorted, inv);   // 512 x 8, 1024 x 4, 512 x 16, 256 x 16: the same within noise; 1024 x 16 / x 32: -1.5 % (profiles/r02ab_*)
     // after the scatter the cursor of bin k has advanced to the start of bin k+1; hist[kSortBins + 1] still holds the active count
     if (g_trace_kernel == 3) cudaMemsetAsync(stream_counter, 0, sizeof(unsigned), st);
     if (ev0) cudaEventRecord(ev0, st);   // the pair brackets the traversal kernel alone (roofline: 48 B per traced ray / this duration)
     if (g_trace_kernel == 3) {
         StreamArgs A;
-        A.nodes = S.nodes_c; A.leaf = S.leaf; A.n_active = hist + kSortBins + 1; A.perm = perm; A.rays = rays; A.hits = hits; A.counter = stream_counter;
+        A.nodes = S.nodes_c; A.leaf = S.leaf; A.n_active = hist + kSortBins + 1; A.perm = sorted ? nullptr : perm; A.rays = sorted ? sorted : rays; A.hits = hits; A.counter = stream_counter;
         A.chunk_max = (unsigned)std::max(32, g_trace_chunk & ~31);
         const unsigned grid = (unsigned)std::min<long long>(nblk(n, 128), 148LL * std::max(1, std::min(8, g_trace_blocks)));   // persistent: 8 blocks of 4 warps per SM
         if (g_trace_node_min == 1) k_trace_stream<1, 12, 8, 2><<<grid, 128, 0, st>>>(A);    // node steps until no lane descends (plain while-while; 40 % slower)

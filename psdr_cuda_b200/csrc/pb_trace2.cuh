@@ -137,7 +137,7 @@ struct StreamArgs {
     const BvhNodeC *nodes;
     const LeafTri *leaf;
     const unsigned *n_active;   // device counter: rays in the sorted stream
-    const unsigned *perm;       // stream position -> ray slot
+    const unsigned *perm;       // stream position -> ray slot; null: `rays` is the sorted copy and a hit is written at its ray's stream position
     const RayRec *rays;
     HitRec *hits;
     unsigned *counter;          // chunk cursor (zeroed before the launch)
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, MINB) k_trace_stream(StreamArgs A) {
             chunk_next = base; chunk_end = min(base + size, n);
         }
         blk_cnt = min(32u, chunk_end - chunk_next);
-        if ((unsigned)lane < blk_cnt) p_src = __ldcs(A.perm + chunk_next + lane);
+        if ((unsigned)lane < blk_cnt) p_src = A.perm ? __ldcs(A.perm + chunk_next + lane) : chunk_next + lane;
         chunk_next += blk_cnt;
     };
     auto stage_block = [&]() {   // B(b): gather the block's rays into the ring, then A(b+1)

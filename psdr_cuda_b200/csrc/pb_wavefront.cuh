@@ -60,6 +60,15 @@ PB_D HitRec load_hit(const HitRec *p) {
     r.tri = __float_as_int(h.x); r.shape = __float_as_int(h.y); r.u = h.z; r.v = h.w;
     return r;
 }
+// hit of ray j of lane i of an event (EventBuffers::hits / inv)
+PB_D HitRec event_hit(const EventBuffers &E, int j, int n, int i) {
+    if (E.inv) {
+        const unsigned p = __ldg(E.inv + (size_t)j * n + i);
+        if (p == 0xffffffffu) { HitRec r; r.tri = -1; r.shape = -1; r.u = r.v = -1.f; return r; }
+        return load_hit(E.hits + p);
+    }
+    return load_hit(E.hits + (size_t)j * n + i);
+}
 PB_D void store_ray(RayRec *p, float3 o, float3 d, float tmax, float t_occ = 0.f) {
     float4 *q = reinterpret_cast<float4 *>(p);
     q[0] = make_float4(o.x, o.y, o.z, tmax);

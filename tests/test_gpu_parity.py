@@ -292,6 +292,38 @@ def test_headline_config_path5_vs_oracle(desc):
     assert np.all(np.abs(g - ref) <= 1e-3 * np.abs(ref).max()), (g, ref)
 
 
+def test_sorted_copy_traversal_gives_the_same_images_and_gradients(desc):
+    # the sorted-copy form of the ray cast (rays rewritten in stream order, hits in stream order + inverse map) against the permutation form:
+    # texture leaves only (k_resolve follows the inverse map, nothing else reads the hits) and with a vertex leaf (hits un-permuted for k_adjoint)
+    from psdr_cuda_b200 import capi
+    opts = dict(width=48, height=48, spp=8, sppe=0, sppse=0)
+    integ = capi.make_integrator("path", max_depth=4)
+    dLdI = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, size=(48 * 48, 3)).astype(np.float32)).cuda()
+    for geometry in (False, True):
+        out = []
+        for sorted_copy in (0, 1):
+            ctx = capi.Context(0)
+            ctx.load_description(desc, opts)
+            ctx.grad_require(capi.PARAM_BSDF_TEXTURE, 0, "reflectance")
+            if geometry:
+                ctx.grad_require(capi.PARAM_MESH_VERTICES, len(desc["meshes"]) - 1)
+            ctx.configure()
+            ctx.debug_set("sorted_copy", sorted_copy)
+            c = ctx.render_c(integ).cpu().numpy()
+            d = ctx.render_d(integ).cpu().numpy()
+            g = ctx.render_d_vjp(integ, dLdI).cpu().numpy()
+            ctx.set_retain_limit(0)             # and through the re-tracing VJP
+            ctx.render_d(integ)
+            g2 = ctx.render_d_vjp(integ, dLdI).cpu().numpy()
+            out.append((c, d, g, g2))
+            ctx.close()
+        (c0, d0, g0, h0), (c1, d1, g1, h1) = out
+        assert np.abs(c0 - c1).max() <= 1e-6 and np.abs(d0 - d1).max() <= 1e-6
+        scale = np.abs(g0).max()
+        assert np.allclose(g0, g1, rtol=1e-4, atol=1e-5 * scale) and np.allclose(h0, h1, rtol=1e-4, atol=1e-5 * scale)
+        assert np.abs(g0).max() > 0
+
+
 def test_path1_equals_direct11_on_the_cuda_path(desc):
     # the only pin the reference gives the PathIntegrator: depth 1 reproduces DirectIntegrator(1, 1) (direct.cpp:47-163)
     from psdr_cuda_b200 import capi
