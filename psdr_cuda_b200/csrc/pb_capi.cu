@@ -763,9 +763,6 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.hit_prev = nullptr;
                         E.prev_pos = (k == 0) ? nullptr : S.pos[(k - 1) & 1].as<float4>();
                         E.pos = S.pos[k & 1].as<float4>(); E.vb = S.vb[k & 1].as<float4>(); E.vc = S.vc[k & 1].as<float4>();
-                        E.next_pos = Bp.last ? nullptr : S.pos[(k + 1) & 1].as<float4>();
-                        E.next_vb = Bp.last ? nullptr : S.vb[(k + 1) & 1].as<float4>();
-                        E.next_vc = Bp.last ? nullptr : S.vc[(k + 1) & 1].as<float4>();
                         E.rays = S.rays.as<RayRec>();
                         E.hits = S.hits[k & 1].as<HitRec>();
                         E.thr_in = (k == 0) ? nullptr : S.thr[k & 1].as<float4>();
@@ -773,7 +770,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.rad = S.rad.as<float4>();
                         c->d_sort_keys.reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(unsigned short));
                         E.keys = c->d_sort_keys.as<unsigned short>();
-                        E.lin = nullptr; E.inv = nullptr;
+                        E.lin = nullptr; E.inv = nullptr; E.inv_cur = nullptr;
                         launch_shade(st, P, Bp, E);
                         trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr, nullptr, -1, true);
                         launch_resolve(st, P, Bp, E, nullptr);
@@ -1103,10 +1100,6 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.hit_prev = (k == 0 || !keep) ? nullptr : (k == 1 ? hit0 : S.hits[k - 2].as<HitRec>() + off * R);
             E.prev_pos = (k == 0) ? nullptr : S.pos[sp].as<float4>() + off;
             E.pos = S.pos[sl].as<float4>() + off; E.vb = S.vb[sl].as<float4>() + off; E.vc = S.vc[sl].as<float4>() + off;
-            const int nsl = keep ? k + 1 : ((k + 1) & 1);
-            E.next_pos = bps[k].last ? nullptr : S.pos[nsl].as<float4>() + off;
-            E.next_vb = bps[k].last ? nullptr : S.vb[nsl].as<float4>() + off;
-            E.next_vc = bps[k].last ? nullptr : S.vc[nsl].as<float4>() + off;
             E.rays = lane_rays;
             E.hits = S.hits[sl].as<HitRec>() + off * R;
             E.thr_in = (k == 0) ? nullptr : S.thr[keep ? k : (k & 1)].as<float4>() + off;
@@ -1114,7 +1107,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.rad = S.rad.as<float4>() + off;
             E.keys = lane_keys;
             E.lin = (keep && lin) ? S.lin[sl].as<float4>() + off : nullptr;
-            E.inv = nullptr;
+            E.inv = nullptr; E.inv_cur = nullptr;
             return E;
         };
         if (run_forward) {
@@ -1127,8 +1120,10 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 if (mode != MODE_VJP) { launch_field(st, P, I.field, hit0, d_image, nullptr); c->launches++; }
                 continue;
             }
+            const unsigned *prev_inv = nullptr;   // sorted-copy traversal: the previous event's hits are in stream order, this is their inverse map
             for (int k = 0; k < plan.nbounce; ++k) {
                 EventBuffers E = event(k);
+                E.inv_cur = prev_inv;
                 launch_shade(st, P, bps[k], E);
                 cudaEvent_t t0 = get_event(c, nev++), t1 = get_event(c, nev++);
                 const int64_t nrays = (int64_t)P.n * (plan.nb + plan.nl);
@@ -1143,6 +1138,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
                 } else {                     // k_resolve is the only reader: it follows the inverse map
                     trace_wavefront(c, nrays, E.rays, E.hits, t0, t1, -1, true, lane, &E.inv);
                 }
+                prev_inv = E.inv;
                 launch_resolve(st, P, bps[k], E, mode == MODE_VJP ? nullptr : d_image);
                 c->launches += 3; c->last_rays += nrays; c->last_trace_launches++;
             }

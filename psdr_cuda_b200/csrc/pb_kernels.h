@@ -42,15 +42,15 @@ struct EventBuffers {
     const HitRec *hit_prev;  // [n]   adjoint only: hit that created the previous vertex (null at depth 0)
     const float4 *prev_pos;  // [n]   position of the previous vertex (origin of the ray that found hit_cur); unused at depth 0
     float4 *pos;             // [n]   this vertex' record, part a = (p, wi.x). The record (48 B: position, shading normal, local incident
-    float4 *vb, *vc;         // [n]   direction, uv, mesh id) is written by whoever reconstructs the vertex first — k_shade at the camera vertex,
-                             //       k_resolve(k) for vertex k+1 (the hit of its continuation ray) — b = (n_sh, wi.y), c = (uv, mesh id or -1, wi.z)
-    float4 *next_pos, *next_vb, *next_vc;   // [n] record of the next event's vertex, written by k_resolve (null: there is no next event)
+    float4 *vb, *vc;         // [n]   direction, uv, mesh id; b = (n_sh, wi.y), c = (uv, mesh id or -1, wi.z)) is written by k_shade, which reconstructs
+                             //       the vertex from its hit, and read by k_resolve / k_adjoint_lin instead of reconstructing it again
     RayRec *rays;            // [R*n] rays of this event (scratch, ray j of lane i at j*n + i)
     HitRec *hits;            // [R*n] their hits
     const float4 *thr_in;    // [n]   throughput T_k (.w != 0: the path is dead); unused at depth 0
     float4 *thr_out;         // [n]   T_{k+1}; may be null on the last event
     float4 *rad;             // [n]   radiance accumulated so far (in/out)
     unsigned short *keys;    // [R*n] sort keys of this event's rays, written by k_shade (or null: the sort computes them from the rays)
+    const unsigned *inv_cur; // [n]   sorted-copy traversal: hit_cur is in stream order and inv_cur[i] is lane i's position (null: hit_cur is indexed by lane)
     const unsigned *inv;     // [R*n] sorted-copy traversal: `hits` is in stream order and inv[j*n + i] is the position of ray j of lane i (~0: inactive
                              //       lane, a miss); null: hits are indexed by ray slot
     float4 *lin;             // [n]   retained renders of diffuse scenes: the event's linearisation in its vertex' reflectance, (A, c) with

@@ -52,13 +52,8 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     RayRec *__restrict__ rays_out = E.rays;
-    Vertex v;
-    if (ev_depth0<EV>(B)) {   // the camera vertex is reconstructed here; later vertices were by the k_resolve that found them
-        v = load_vertex<EV>(P, B, i, E);
-        store_vertex_rec(E.pos, E.vb, E.vc, i, v.its, v.its.valid);
-    } else {
-        v = load_vertex_rec(P, E, i);
-    }
+    const Vertex v = load_vertex<EV>(P, B, i, E);
+    store_vertex_rec(E.pos, E.vb, E.vc, i, v.its, v.its.valid);   // k_resolve / k_adjoint_lin read the record instead of reconstructing the vertex again
     int pix_unused;
     Rng rng = make_rng(P, global_lane(P, i, pix_unused), B.jump);
     for (int j = 0; j < B.nb; ++j) {
@@ -103,8 +98,6 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
         Rng rng = make_rng(P, lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         bool has_cont = false;
-        float3 thr = f3(1.f);
-        if (!ev_depth0<EV>(B)) thr = f3(ldg4(E.thr_in + i));
         // Diffuse scenes, AD formulation: L_k and w_k are linear in the vertex' reflectance, L_k = rho * A and w_k = rho * c
         // (f = rho cos_o / pi, diffuse.cpp:25-33; pdf and MIS weight do not depend on rho). A retained render keeps (A, c): the
         // reflectance adjoint of the event is then gL * A + gw * c (k_adjoint_lin) with no connection to reconstruct.
@@ -149,11 +142,6 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
                 }
                 if (B.carry && j == 0 && cont) { w_cont = bsdf_val; has_cont = true; lin_c = dk; }
             }
-            if (j == 0 && E.next_pos) {   // the continuation ray's hit is the next event's vertex: leave its record (dead paths: an invalid one)
-                bool alive = has_cont;
-                if (!ev_ad<EV>(B)) { const float3 t2 = thr * w_cont; alive = alive && (t2.x != 0.f || t2.y != 0.f || t2.z != 0.f); }
-                store_vertex_rec(E.next_pos, E.next_vb, E.next_vc, i, its1, alive);
-            }
         }
         for (int j = 0; j < B.nl; ++j) {
             const float2 s2 = rng.next_2d();
@@ -180,9 +168,12 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             }
         }
         if (keep_lin) E.lin[i] = make_float4(lin_a.x, lin_a.y, lin_a.z, lin_c);
-        float3 rad;
-        if (ev_depth0<EV>(B)) rad = B.hide_emitters ? f3(0.f) : emitter_Le<SIMPLE>(P.S, its, its.valid);   // direct.cpp:51
-        else rad = f3(E.rad[i]);
+        float3 thr = f3(1.f), rad;
+        if (ev_depth0<EV>(B)) {
+            rad = B.hide_emitters ? f3(0.f) : emitter_Le<SIMPLE>(P.S, its, its.valid);   // direct.cpp:51
+        } else {
+            thr = f3(ldg4(E.thr_in + i)); rad = f3(E.rad[i]);
+        }
         rad += thr * L;
         if (B.last) out = zero_nonfinite(rad) * P.inv_spp;   // integrator.cpp:87-91
         if (E.thr_out) {

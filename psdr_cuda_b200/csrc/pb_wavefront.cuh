@@ -118,7 +118,14 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
             v.its = reconstruct_its(P.S, v.h, v.ro);
         }
     } else {
-        HitRec h = load_hit(hit_cur + i);
+        HitRec h;
+        if (E.inv_cur) {   // sorted-copy traversal: the previous event's hits are in stream order
+            const unsigned p = __ldg(E.inv_cur + i);
+            if (p == 0xffffffffu) { h.tri = -1; h.shape = -1; h.u = h.v = -1.f; }
+            else h = load_hit(hit_cur + p);
+        } else {
+            h = load_hit(hit_cur + i);
+        }
         if (ldg4(E.thr_in + i).w != 0.f) h.tri = -1;   // dead path (zero throughput or no continuation): nothing downstream can contribute
         v.h = h;
         v.ro = f3(ldg4(E.prev_pos + i)); v.rd = f3(0.f);
@@ -130,8 +137,10 @@ PB_D Vertex load_vertex(const RenderParams &P, const BounceParams &B, int i, con
     return v;
 }
 
-// Vertex record (EventBuffers::pos / vb / vc): what the event kernels need of a path vertex, written once by whoever reconstructs it
-// first and read by the kernels that would otherwise each rebuild it from the hit, the previous position and the triangle row.
+// Vertex record (EventBuffers::pos / vb / vc): what the event kernels need of a path vertex. k_shade reconstructs the vertex from its hit,
+// the previous position and the triangle row and leaves the record; k_resolve and k_adjoint_lin read it instead of rebuilding the vertex.
+// (Having k_resolve(k) write vertex k+1's record — it reconstructs that point as the end of its continuation ray — was 2 % slower: the kernel
+// is the one with no registers to spare, profiles/r02ag_*.)
 PB_D void store_vertex_rec(float4 *pa, float4 *pb, float4 *pc, int i, const Its &its, bool alive) {
     if (alive) {
         pa[i] = make_float4(its.p.x, its.p.y, its.p.z, its.wi.x);
