@@ -771,6 +771,8 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         c->d_sort_keys.reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(unsigned short));
                         E.keys = c->d_sort_keys.as<unsigned short>();
                         E.lin = nullptr; E.inv = nullptr; E.inv_cur = nullptr;
+                        c->d_conn[0].reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(float2));
+                        E.conn = c->d_conn[0].as<float2>();
                         launch_shade(st, P, Bp, E);
                         trace_wavefront(c, (int64_t)P.n * (plan.nb + plan.nl), E.rays, E.hits, nullptr, nullptr, -1, true);
                         launch_resolve(st, P, Bp, E, nullptr);
@@ -933,6 +935,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
     size_store(S, use_retained ? total : B, keep ? D : 2, R, B, keep && lin);
     if (mode == MODE_VJP) c->d_suffix.reserve((size_t)B * sizeof(float4));
     c->d_sort_keys.reserve((size_t)B * R * sizeof(unsigned short));   // k_shade writes the sort keys of the rays it emits
+    c->d_conn[0].reserve((size_t)B * R * sizeof(float2));
     if (dual) {   // lane 1: its own stream and per-batch buffers
         if (!c->stream2) {
             PB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
@@ -944,6 +947,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
         c->d_rays1.reserve((size_t)B * R * sizeof(RayRec));
         if (mode == MODE_VJP) c->d_suffix1.reserve((size_t)B * sizeof(float4));
         c->d_sort_keys1.reserve((size_t)B * R * sizeof(unsigned short));
+        c->d_conn[1].reserve((size_t)B * R * sizeof(float2));
     }
     RenderParams P;
     P.S = c->view; P.cam = c->sensors[sensor].rec;
@@ -1108,6 +1112,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.keys = lane_keys;
             E.lin = (keep && lin) ? S.lin[sl].as<float4>() + off : nullptr;
             E.inv = nullptr; E.inv_cur = nullptr;
+            E.conn = c->d_conn[lane].as<float2>();
             return E;
         };
         if (run_forward) {

@@ -49,6 +49,9 @@ struct EventBuffers {
     const float4 *thr_in;    // [n]   throughput T_k (.w != 0: the path is dead); unused at depth 0
     float4 *thr_out;         // [n]   T_{k+1}; may be null on the last event
     float4 *rad;             // [n]   radiance accumulated so far (in/out)
+    float2 *conn;            // [R*n] diffuse scenes: what k_resolve needs of the samples k_shade drew, so that it neither re-derives the sampler nor
+                             //       repeats the sampling — BSDF ray: (cos theta_o of the sampled direction, -), emitter ray: (position pdf, squared distance);
+                             //       the directions themselves are read back from `rays`
     unsigned short *keys;    // [R*n] sort keys of this event's rays, written by k_shade (or null: the sort computes them from the rays)
     const unsigned *inv_cur; // [n]   sorted-copy traversal: hit_cur is in stream order and inv_cur[i] is lane i's position (null: hit_cur is indexed by lane)
     const unsigned *inv;     // [R*n] sorted-copy traversal: `hits` is in stream order and inv[j*n + i] is the position of ray j of lane i (~0: inactive

@@ -186,6 +186,7 @@ PB_HD RngSeed rng_seed(uint64_t lane) {
 struct Rng {
     uint64_t state, inc;
     // stream `lane` of a psdr Sampler seeded with arange(count) (sampler.cpp:29-40), advanced by `jump` draws
+    PB_HD Rng() : state(0), inc(1) {}   // placeholder of a kernel instantiation that draws nothing
     PB_HD Rng(uint64_t lane, RngJump jump) {
         const RngSeed s = rng_seed(lane);
         inc = s.inc;

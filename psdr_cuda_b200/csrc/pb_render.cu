@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
         const bool a1 = v.active && bs.valid;
         const float3 wo_w = v.its.sh.to_world(bs.wo);
         store_ray(rays_out + (size_t)j * P.n + i, v.its.p, wo_w, a1 ? INFINITY : -1.f);
+        if (SIMPLE) E.conn[(size_t)j * P.n + i] = make_float2(bs.wo.z, 0.f);
         if (E.keys) E.keys[(size_t)j * P.n + i] = (unsigned short)sort_key(v.its.p, a1 ? 1.f : -1.f, wo_w, B.sort_lo, B.sort_inv_ext, B.sort_mode);
     }
     for (int j = 0; j < B.nl; ++j) {
@@ -69,8 +70,10 @@ __global__ void __launch_bounds__(256) k_shade(RenderParams P, BounceParams B, E
         const PositionSample ps = sample_emitter_position<SIMPLE>(P.S, v.its.p, s2, v.active);
         const bool a1 = v.active && ps.valid;
         float3 wo = ps.p - v.its.p;
-        const float dist = safe_sqrt(squared_norm(wo));
+        const float dist_sqr = squared_norm(wo);
+        const float dist = safe_sqrt(dist_sqr);
         wo = wo / dist;
+        if (SIMPLE) E.conn[(size_t)(B.nb + j) * P.n + i] = make_float2(ps.pdf, dist_sqr);
         // The connection is valid iff the closest hit lies beyond dist - ShadowEpsilon and is an emitter (direct.cpp:130-131):
         // nothing past the sampled point can change that, and any closer hit decides it, so the ray is bounded and
         // flagged as an occlusion query.
@@ -95,7 +98,9 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
         const long long lane = global_lane(P, i, pix);
         const Vertex v = load_vertex_rec(P, E, i);
         const Its &its = v.its;
-        Rng rng = make_rng(P, lane, B.jump);
+        // SIMPLE (diffuse + area lights): k_shade left what this kernel needs of its samples (EventBuffers::conn, directions in `rays`);
+        // otherwise the sampler is re-derived and the sampling repeated
+        Rng rng = SIMPLE ? Rng() : make_rng(P, lane, B.jump);
         float3 L = f3(0.f), w_cont = f3(0.f);
         bool has_cont = false;
         // Diffuse scenes, AD formulation: L_k and w_k are linear in the vertex' reflectance, L_k = rho * A and w_k = rho * c
@@ -106,8 +111,14 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
         float lin_c = 0.f;
         const float inv_nb = B.nb > 0 ? 1.f / (float)B.nb : 0.f, inv_nl = B.nl > 0 ? 1.f / (float)B.nl : 0.f;
         for (int j = 0; j < B.nb; ++j) {
-            const float3 s3 = rng.next_3d();
-            const BsdfSample bs = bsdf_sample<SIMPLE>(v.bsdf, its, s3, v.active);
+            BsdfSample bs;
+            if (SIMPLE) {   // diffuse.cpp:47-55: pdf = cos / pi, valid iff the incident side is the front
+                const float cos_o = v.bsdf ? __ldg(&E.conn[(size_t)j * P.n + i].x) : 0.f;
+                bs.wo = f3(0.f, 0.f, cos_o); bs.pdf = kInvPi * cos_o; bs.valid = v.bsdf && v.active && its.wi.z > 0.f;
+            } else {
+                const float3 s3 = rng.next_3d();
+                bs = bsdf_sample<SIMPLE>(v.bsdf, its, s3, v.active);
+            }
             bool a1 = v.active && bs.valid;
             const HitRec h1 = event_hit(E, j, P.n, i);
             const Its its1 = reconstruct_its(P.S, h1, its.p);
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
                     bsdf_val = bsdf_val * (G / pdf0);
                     if (keep_lin && v.bsdf && its.wi.z > 0.f && wo_l.z > 0.f) dk = (kInvPi * wo_l.z) * (G / pdf0);
                 } else {      // direct.cpp:96-106
-                    const float3 d1 = its.sh.to_world(bs.wo);
+                    const float3 d1 = SIMPLE ? f3(ldg4(reinterpret_cast<const float4 *>(E.rays + (size_t)j * P.n + i) + 1)) : its.sh.to_world(bs.wo);
                     bsdf_val = bsdf_eval<SIMPLE>(v.bsdf, its, bs.wo, true);
                     const float G = fabsf(dot(its1.n, -d1)) / sqr(its1.t);
                     pdf0 = bs.pdf * G;
@@ -144,13 +155,23 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(RenderParams P, BouncePar
             }
         }
         for (int j = 0; j < B.nl; ++j) {
-            const float2 s2 = rng.next_2d();
-            const PositionSample ps = sample_emitter_position<SIMPLE>(P.S, v.its.p, s2, v.active);
+            PositionSample ps;
+            float3 wo;
+            float dist_sqr, dist;
+            if (SIMPLE) {
+                const float2 cr = __ldg(E.conn + (size_t)(B.nb + j) * P.n + i);
+                ps.pdf = cr.x; ps.valid = v.active;
+                dist_sqr = cr.y; dist = safe_sqrt(dist_sqr);
+                wo = f3(ldg4(reinterpret_cast<const float4 *>(E.rays + (size_t)(B.nb + j) * P.n + i) + 1));
+            } else {
+                const float2 s2 = rng.next_2d();
+                ps = sample_emitter_position<SIMPLE>(P.S, v.its.p, s2, v.active);
+                wo = ps.p - its.p;
+                dist_sqr = squared_norm(wo);
+                dist = safe_sqrt(dist_sqr);
+                wo = wo / dist;
+            }
             bool a1 = v.active && ps.valid;
-            float3 wo = ps.p - its.p;
-            const float dist_sqr = squared_norm(wo);
-            const float dist = safe_sqrt(dist_sqr);
-            wo = wo / dist;
             const HitRec h1 = event_hit(E, B.nb + j, P.n, i);
             const Its its1 = reconstruct_its(P.S, h1, its.p);
             a1 = a1 && its1.valid && (its1.t > dist - kShadowEpsilon) && is_emitter(P.S, its1.shape);
