@@ -391,7 +391,7 @@ class Scene(_h.Scene):
         except ImportError:
             pass
 
-    def init_distributed(self, group=None, mode="pixels", tile_rows=8):
+    def init_distributed(self, group=None, mode="pixels", tile_rows=4):
         """one process per GPU under torch.distributed: create the library's NCCL communicator for the group's ranks (the unique id
         travels through the group), shard the scene over them. From then on renderC / renderD return the complete film and
         backward() returns the complete gradient: one collective each, enqueued by the library on the scene's stream."""
