@@ -120,6 +120,71 @@ PB_D void flush_const_tex_grad(const SceneView &S, int bsdf_id, float3 acc, floa
     }
 }
 
+// Reflectance adjoint of one lane's event from the linearisation the forward pass kept (EventBuffers::lin): with L_k = rho * A and
+// w_k = rho * c the event's share of dLoss/d(rho) is gL * A + gw * c and the suffix is S_k = rho * (A + c S_{k+1}) — the same sums
+// k_adjoint forms connection by connection (bsdf_eval_grad_tex), without reconstructing the connections.
+template <int EV>
+PB_D void adjoint_lin_lane(const RenderParams &P, const BounceParams &B, const EventBuffers &E, int i, float4 *__restrict__ suffix, const float *__restrict__ dLdI,
+                           float3 &acc, int &bsdf_id) {
+    const float4 lin = ldg4(E.lin + i);
+    const float3 A = f3(lin);
+    const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
+    float3 Sk = f3(0.f);
+    if (A.x != 0.f || A.y != 0.f || A.z != 0.f || lin.w != 0.f) {   // (NaN compares unequal: a poisoned event is kept and poisons S_k like k_adjoint's)
+        const float4 vc = ldg4(E.vc + i);   // the vertex record's (uv, mesh id)
+        const int shape = __float_as_int(vc.z);
+        const int bid = shape >= 0 ? P.S.meshes[shape].bsdf : -1;
+        if (bid >= 0) {
+            const BsdfRec *bsdf = P.S.bsdfs + bid;
+            const float2 uv = make_float2(vc.x, vc.y);
+            const TexRef &t = bsdf->tex[TEX_REFLECTANCE];
+            Sk = tex_eval3(t, uv) * (A + S_next * lin.w);
+            if (t.grad) {
+                int pix;
+                global_lane(P, i, pix);
+                const float3 rad_final = f3(ldg4(E.rad + i));
+                float3 g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
+                if (!isfinite(rad_final.x)) g.x = 0.f;
+                if (!isfinite(rad_final.y)) g.y = 0.f;
+                if (!isfinite(rad_final.z)) g.z = 0.f;
+                float3 T = f3(1.f);
+                if (!ev_depth0<EV>(B)) T = f3(ldg4(E.thr_in + i));
+                const float3 gL = g * T;
+                const float3 gr = gL * A + gL * S_next * lin.w;
+                if (finite3(gr)) {
+                    if (t.w == 1 && t.h == 1) {
+                        acc = gr;
+                        bsdf_id = bid;
+                    } else {
+                        const TexTap tap = tex_tap(t, uv);
+                        const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
+                        const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            atomicAdd(t.grad + idx[k] * 3 + 0, gr.x * w[k]);
+                            atomicAdd(t.grad + idx[k] * 3 + 1, gr.y * w[k]);
+                            atomicAdd(t.grad + idx[k] * 3 + 2, gr.z * w[k]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!ev_depth0<EV>(B)) suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
+}
+// Geometry adjoints of a diffuse scene (reverse mode): an event touches the triangle table only through its own vertex and the end points of its
+// connections. If none of them lies on a mesh whose vertices are a leaf (MeshRec::flags bit 2), the event's adjoint is the reflectance one above.
+PB_D bool event_touches_leaf_mesh(const RenderParams &P, const BounceParams &B, const EventBuffers &E, int i) {
+    auto leaf_mesh = [&](int shape) { return shape >= 0 && (P.S.meshes[shape].flags & 4) != 0; };
+    bool need = leaf_mesh(__float_as_int(__ldg(&E.vc[i].z)));
+    for (int j = 0; j < B.nb + B.nl; ++j) {
+        const int shape = __ldg(reinterpret_cast<const int *>(E.hits + (size_t)j * P.n + i) + 1);
+        // the end of a BSDF-sampled ray is the next vertex; an emitter-sampled connection only counts when it reaches an emitter
+        need = need || (leaf_mesh(shape) && (j < B.nb || P.S.meshes[shape].emitter >= 0));
+    }
+    return need;
+}
+
 // adjoint of one scattering event (texture parameters). E.thr_in: T_k; suffix: S_{k+1} in, S_k out; E.rad: the lane's
 // final forward radiance (decides which channels integrator.cpp:87 zeroed).
 // RC ("extended" events): rough-conductor texture / geometry adjoints and the environment map's radiance / scale / direction
@@ -128,7 +193,12 @@ template <int MINB, bool PREFETCH, bool RC, bool SIMPLE, int EV>
 __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
     const HitRec *__restrict__ hits = E.hits;
     __shared__ float s_acc[kMaxConstBsdf * 3];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (E.lane_list) {   // behind k_adjoint_split: the lanes whose event touches a leaf mesh (the whole block leaves together past the end of the list)
+        const unsigned cnt = __ldg(E.lane_count);
+        if (blockIdx.x * blockDim.x >= cnt) return;
+        i = (unsigned)i < cnt ? __ldg(E.lane_list + i) : P.n;
+    }
     float3 acc = f3(0.f);
     int bsdf_id = -1;
     rc::TexGrad rc_acc;
@@ -397,62 +467,39 @@ __global__ void __launch_bounds__(256, MINB) k_adjoint(RenderParams P, BouncePar
     if (RC) rc::flush_const_tex_grad(P.S, rc_tex ? bsdf_id : -1, rc_acc, env_scale_acc, s_rc);
 }
 
-// Reflectance adjoint of one event from the linearisation the forward pass kept (EventBuffers::lin): with L_k = rho * A and
-// w_k = rho * c the event's share of dLoss/d(rho) is gL * A + gw * c and the suffix is S_k = rho * (A + c S_{k+1}) — the same sums
-// k_adjoint forms connection by connection (bsdf_eval_grad_tex), without reconstructing the connections. Diffuse scenes whose
-// only leaves are reflectance textures (no geometry, pose or uv adjoints), reverse mode.
+// adjoint_lin_lane for every lane: diffuse scenes whose only leaves are reflectance textures (no geometry, pose or uv adjoints), reverse mode
 template <int EV>
 __global__ void __launch_bounds__(256) k_adjoint_lin(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI) {
     __shared__ float s_acc[kMaxConstBsdf * 3];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float3 acc = f3(0.f);
     int bsdf_id = -1;
+    if (i < P.n) adjoint_lin_lane<EV>(P, B, E, i, suffix, dLdI, acc, bsdf_id);
+    flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
+}
+
+// First half of the split geometry adjoint: a lane whose event touches no leaf mesh is finished here from the linearisation; the others are
+// listed (order is irrelevant: they only meet in atomics) for k_adjoint, which then runs on full warps of lanes that need it. In lane order a
+// warp holds 32 samples of one pixel whose deeper vertices lie anywhere: almost every warp had a few lanes on the bunny and ran the whole kernel.
+template <int EV>
+__global__ void __launch_bounds__(256) k_adjoint_split(RenderParams P, BounceParams B, EventBuffers E, float4 *__restrict__ suffix, const float *__restrict__ dLdI,
+                                                       int *__restrict__ list, unsigned *__restrict__ count) {
+    __shared__ float s_acc[kMaxConstBsdf * 3];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 acc = f3(0.f);
+    int bsdf_id = -1;
+    bool need = false;
     if (i < P.n) {
-        const float4 lin = ldg4(E.lin + i);
-        const float3 A = f3(lin);
-        const float3 S_next = B.last ? f3(0.f) : f3(suffix[i]);
-        float3 Sk = f3(0.f);
-        if (A.x != 0.f || A.y != 0.f || A.z != 0.f || lin.w != 0.f) {   // (NaN compares unequal: a poisoned event is kept and poisons S_k like k_adjoint's)
-            const float4 vc = ldg4(E.vc + i);   // the vertex record's (uv, mesh id)
-            const int shape = __float_as_int(vc.z);
-            const int bid = shape >= 0 ? P.S.meshes[shape].bsdf : -1;
-            if (bid >= 0) {
-                const BsdfRec *bsdf = P.S.bsdfs + bid;
-                const float2 uv = make_float2(vc.x, vc.y);
-                const TexRef &t = bsdf->tex[TEX_REFLECTANCE];
-                Sk = tex_eval3(t, uv) * (A + S_next * lin.w);
-                if (t.grad) {
-                    int pix;
-                    global_lane(P, i, pix);
-                    const float3 rad_final = f3(ldg4(E.rad + i));
-                    float3 g = f3(__ldg(dLdI + 3 * (size_t)pix), __ldg(dLdI + 3 * (size_t)pix + 1), __ldg(dLdI + 3 * (size_t)pix + 2)) * P.inv_spp;
-                    if (!isfinite(rad_final.x)) g.x = 0.f;
-                    if (!isfinite(rad_final.y)) g.y = 0.f;
-                    if (!isfinite(rad_final.z)) g.z = 0.f;
-                    float3 T = f3(1.f);
-                    if (!ev_depth0<EV>(B)) T = f3(ldg4(E.thr_in + i));
-                    const float3 gL = g * T;
-                    const float3 gr = gL * A + gL * S_next * lin.w;
-                    if (finite3(gr)) {
-                        if (t.w == 1 && t.h == 1) {
-                            acc = gr;
-                            bsdf_id = bid;
-                        } else {
-                            const TexTap tap = tex_tap(t, uv);
-                            const float w[4] = {tap.w0y * tap.w0x, tap.w0y * tap.w1x, tap.w1y * tap.w0x, tap.w1y * tap.w1x};
-                            const int idx[4] = {tap.idx, tap.idx + 1, tap.idx + t.w, tap.idx + t.w + 1};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                atomicAdd(t.grad + idx[k] * 3 + 0, gr.x * w[k]);
-                                atomicAdd(t.grad + idx[k] * 3 + 1, gr.y * w[k]);
-                                atomicAdd(t.grad + idx[k] * 3 + 2, gr.z * w[k]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (!ev_depth0<EV>(B)) suffix[i] = make_float4(Sk.x, Sk.y, Sk.z, 0.f);
+        need = event_touches_leaf_mesh(P, B, E, i);
+        if (!need) adjoint_lin_lane<EV>(P, B, E, i, suffix, dLdI, acc, bsdf_id);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (need) list[base + __popc(m & ((1u << lane) - 1u))] = i;
     }
     flush_const_tex_grad(P.S, bsdf_id, acc, s_acc);
 }
@@ -460,10 +507,23 @@ __global__ void __launch_bounds__(256) k_adjoint_lin(RenderParams P, BounceParam
 int g_adjoint_lin = 1;
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
-void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI) {
+void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E0, float4 *suffix, const float *dLdI,
+                    int *split_list, unsigned *split_count) {
     if (P.n <= 0) return;
     const unsigned g = nblk(P.n, 256);
+    EventBuffers E = E0;
+    E.lane_list = nullptr; E.lane_count = nullptr;
     if (B.rc_grad) { k_adjoint<1, false, true, false, -1><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI); return; }
+    if (P.S.simple && g_shade_simple && g_adjoint_lin && E.lin && P.S.tri_grad && !P.S.tri_tangent && !E.inv && split_list && split_count) {
+        // vertex leaves on some meshes of a diffuse scene: reflectance adjoint for the lanes that touch none of them, the full kernel for the rest
+        cudaMemsetAsync(split_count, 0, sizeof(unsigned), st);
+        if (B.depth == 0) k_adjoint_split<3><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI, split_list, split_count);
+        else k_adjoint_split<2><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI, split_list, split_count);
+        E.lane_list = split_list; E.lane_count = split_count;
+        if (B.depth == 0) k_adjoint<3, false, false, true, 3><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
+        else k_adjoint<3, false, false, true, 2><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
+        return;
+    }
     if (P.S.simple && g_shade_simple && g_adjoint_lin && E.lin && !P.S.tri_grad && !P.S.tri_tangent) {   // reflectance leaves only: from the kept linearisation
         if (B.depth == 0) k_adjoint_lin<3><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);
         else k_adjoint_lin<2><<<g, 256, 0, st>>>(P, B, E, suffix, dLdI);

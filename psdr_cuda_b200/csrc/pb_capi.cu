@@ -513,7 +513,7 @@ static void configure(pb_ctx *c) {
         const HostMesh &m = c->meshes[i];
         std::memset(&mr[i], 0, sizeof(MeshRec));
         mr[i].bsdf = m.bsdf; mr[i].emitter = m.emitter; mr[i].inv_total_area = m.inv_total_area;
-        mr[i].face_offset = m.face_offset; mr[i].num_faces = m.nf; mr[i].flags = m.flags & 3;
+        mr[i].face_offset = m.face_offset; mr[i].num_faces = m.nf; mr[i].flags = (m.flags & 3) | (m.requires_grad ? 4 : 0);
         mr[i].uv_faces = (m.flags & 2) ? m.d_uv_faces.as<int>() : nullptr; mr[i].uv_grad = nullptr;
     }
     c->d_meshes.upload(mr, st);
@@ -770,7 +770,7 @@ static void run_edge_terms(pb_ctx *c, const pb_integrator &I, int sensor, const 
                         E.rad = S.rad.as<float4>();
                         c->d_sort_keys.reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(unsigned short));
                         E.keys = c->d_sort_keys.as<unsigned short>();
-                        E.lin = nullptr; E.inv = nullptr; E.inv_cur = nullptr;
+                        E.lin = nullptr; E.inv = nullptr; E.inv_cur = nullptr; E.lane_list = nullptr; E.lane_count = nullptr;
                         c->d_conn[0].reserve((size_t)P.n * (plan.nb + plan.nl) * sizeof(float2));
                         E.conn = c->d_conn[0].as<float2>();
                         launch_shade(st, P, Bp, E);
@@ -1111,7 +1111,7 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             E.rad = S.rad.as<float4>() + off;
             E.keys = lane_keys;
             E.lin = (keep && lin) ? S.lin[sl].as<float4>() + off : nullptr;
-            E.inv = nullptr; E.inv_cur = nullptr;
+            E.inv = nullptr; E.inv_cur = nullptr; E.lane_list = nullptr; E.lane_count = nullptr;
             E.conn = c->d_conn[lane].as<float2>();
             return E;
         };
@@ -1152,7 +1152,8 @@ static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float
             for (int ch = 0; ch < (jvp ? 3 : 1); ++ch) {   // forward mode: one pass per colour channel with a unit seed
                 if (jvp) { P.S.jvp_channel = ch; PB_CUDA(cudaMemsetAsync(c->d_jvp_acc.p, 0, (size_t)P.n * sizeof(float), st)); }
                 for (int k = plan.nbounce - 1; k >= 0; --k) {
-                    launch_adjoint(st, P, bps[k], event(k), lane_suffix, d_dLdI);
+                    c->d_adj_list[lane].reserve((size_t)B * sizeof(int)); c->d_adj_count[lane].reserve(sizeof(unsigned));
+                    launch_adjoint(st, P, bps[k], event(k), lane_suffix, d_dLdI, c->d_adj_list[lane].as<int>(), c->d_adj_count[lane].as<unsigned>());
                     c->launches++;
                 }
             }

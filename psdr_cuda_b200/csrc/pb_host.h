@@ -188,6 +188,7 @@ struct pb_ctx {
     pb::DevBuf d_rays1, d_suffix1, d_sort_hist1, d_sort_perm1, d_sort_keys1, d_stream_counter1;
     // sorted-copy traversal (pb_sort.cu k_sort_scatter<COPY>), per lane: the rays in stream order, ray slot -> stream position, hits in stream order
     pb::DevBuf d_sorted_rays[2], d_sort_inv[2], d_sorted_hits[2];
+    pb::DevBuf d_adj_list[2], d_adj_count[2];   // lane list of the split geometry adjoint (k_adjoint_split), per lane
     pb::DevBuf d_conn[2];                // EventBuffers::conn of the batch in flight on each lane
     int sorted_copy = 0;                 // 1: the interior events trace a sorted copy of their rays (debug key sorted_copy; A/B in profiles/)
     bool retained_hits_by_slot = true;   // the retained hit records are indexed by ray slot (false: stream order — only k_adjoint_lin can use the store)

@@ -56,6 +56,8 @@ struct EventBuffers {
     const unsigned *inv_cur; // [n]   sorted-copy traversal: hit_cur is in stream order and inv_cur[i] is lane i's position (null: hit_cur is indexed by lane)
     const unsigned *inv;     // [R*n] sorted-copy traversal: `hits` is in stream order and inv[j*n + i] is the position of ray j of lane i (~0: inactive
                              //       lane, a miss); null: hits are indexed by ray slot
+    const int *lane_list;    // adjoint kernels: the lanes this launch works on (k_adjoint behind k_adjoint_split), *lane_count of them; null: all n lanes
+    const unsigned *lane_count;
     float4 *lin;             // [n]   retained renders of diffuse scenes: the event's linearisation in its vertex' reflectance, (A, c) with
                              //       L_k = rho * A and w_k = rho * c — written by k_resolve, read by k_adjoint_lin (null: not kept)
 };
@@ -98,7 +100,9 @@ void launch_unpermute_hits(cudaStream_t st, long long n, const unsigned *inv, co
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);
 void launch_resolve(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float *film);
-void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI);
+// split_list / split_count: scratch (n ints, one counter) for the lane list of the split geometry adjoint, or null
+void launch_adjoint(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E, float4 *suffix, const float *dLdI,
+                    int *split_list = nullptr, unsigned *split_count = nullptr);
 void launch_edge_primary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, int side, RayRec *rays);
 void launch_edge_primary_grad(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, const float4 *rad_p, const float4 *rad_n, const float *dLdI, float inv_sppe);
 void launch_edge_secondary_rays(cudaStream_t st, const RenderParams &P, const EdgeParams &Q, RayRec *rays, int guide_spc);

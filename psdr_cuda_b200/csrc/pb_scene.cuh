@@ -43,7 +43,7 @@ struct MeshRec {           // 48 B, per mesh
     int bsdf, emitter;     // -1 = none
     float inv_total_area;
     int face_offset, num_faces;
-    int flags;             // bit0 face normals, bit1 has uv
+    int flags;             // bit0 face normals, bit1 has uv, bit2 the vertex positions are a leaf (requires_grad)
     int pad0, pad1;
     const int *uv_faces;   // 3 uv indices per face, or nullptr
     float *uv_grad;        // VJP: gradient of Mesh.vertex_uv (2 floats per uv vertex; forward mode: its tangent), or nullptr
