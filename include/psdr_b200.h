@@ -65,8 +65,8 @@ int pb_ctx_set_shard(pb_ctx *ctx, int rank, int world);
  * bit-identical to the single-GPU image. The boundary terms are always split by lane range (integrator.cpp:98-119). */
 enum { PB_SHARD_SAMPLES = 0, PB_SHARD_PIXELS = 1 };
 int pb_ctx_set_shard_mode(pb_ctx *ctx, int mode, int tile_rows);
-/* pb_render_d keeps every event's hit records / vertex positions / throughputs of the whole shard (352 B per lane for a
- * depth-5 path) when they fit in `bytes` (default 64 GiB of the 180 GB HBM3e), so that pb_render_d_vjp runs only the
+/* pb_render_d keeps every event's hit records / vertex records / throughputs (and, for diffuse scenes, the event's linearisation in
+ * the vertex' reflectance) of the whole shard (32 + 112 B per event: 592 B per lane for a depth-5 path) when they fit in `bytes` (default 64 GiB of the 180 GB HBM3e), so that pb_render_d_vjp runs only the
  * adjoint kernels; otherwise the VJP re-traces the forward pass batch by batch. 0 disables retention. */
 int pb_ctx_set_retain_limit(pb_ctx *ctx, int64_t bytes);
 /* Run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream) instead of the context's own.

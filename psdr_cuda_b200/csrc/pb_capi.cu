@@ -856,7 +856,7 @@ static void preprocess_secondary_edges(pb_ctx *c, int sensor, const int *reso, i
 // interior term: integrator.cpp:64-95 over this shard's samples, in batches.
 //   MODE_C / MODE_D   forward render (renderC's / renderD's formulation of the primal). MODE_D additionally retains every
 //                     event's hit records, vertex positions and throughputs for the whole shard when they fit
-//                     pb_ctx_set_retain_limit (352 B per lane for a depth-5 path), so that the VJP needs no re-tracing.
+//                     pb_ctx_set_retain_limit (592 B per lane for a depth-5 path), so that the VJP needs no re-tracing.
 //   MODE_VJP          adjoint kernels in reverse event order over the retained records; if nothing was retained the
 //                     forward pass is replayed batch by batch first (same stream positions as the last renderD).
 static void render_interior(pb_ctx *c, const pb_integrator &I, int sensor, float *d_image, Mode mode, const float *d_dLdI = nullptr,
