@@ -210,9 +210,18 @@ int pb_stats_last_trace_launches(pb_ctx *ctx);
 float pb_stats_last_primary_ms(pb_ctx *ctx);
 
 /* ---- debugging / tuning hooks (not part of the reference surface) ---------------------------------------------- */
-int pb_debug_set(pb_ctx *ctx, const char *key, int64_t value);                         /* "trace_variant": 0..3 */
-int pb_debug_ray_buffer(pb_ctx *ctx, int event, void **d_rays, int64_t *bytes);
-int pb_debug_retained_rad(pb_ctx *ctx, void **d_rad, int64_t *bytes);                  /* per-lane radiance kept by pb_render_d */        /* rays kept by the last VJP batch */
+/* A/B switches behind the measurements in profiles/ (defaults in brackets). Process-wide unless noted:
+ *   "sort_mode" [5] 5 = origin cell x direction octant, 0 = round 1's direction bin x cell, 7 = direction only
+ *   "trace_kernel" [3] 3 = persistent streaming kernel, 1 = one ray per thread; "trace_node_min" [16]; "trace_chunk" [128]; "trace_blocks" [8]
+ *   "sorted_copy" [0] (per context) 1 = the ray cast works on a sorted copy of the rays and writes hits in stream order
+ *   "adjoint_lin" [1] 0 = reflectance adjoints connection by connection even when the forward pass kept the linearisation
+ *   "shade_simple" [1] 0 = never use the diffuse + area-light instantiations; "shade_tune" [0] register caps of the event kernels
+ *   "pipeline" [1] (per context) 0 = one batch at a time, 1 = two batches in flight for renders of at most "pipeline_max_lanes" lanes, 2 = always
+ *   "l2_persist" [1], "rng_seed_table" [1] (per context)
+ * Unknown keys are an error. */
+int pb_debug_set(pb_ctx *ctx, const char *key, int64_t value);
+int pb_debug_ray_buffer(pb_ctx *ctx, int event, void **d_rays, int64_t *bytes);       /* rays of the last event traced by the last batch */
+int pb_debug_retained_rad(pb_ctx *ctx, void **d_rad, int64_t *bytes);                  /* per-lane radiance kept by pb_render_d */
 
 #ifdef __cplusplus
 }
