@@ -25,7 +25,7 @@ SYMBOLS = [
     "pb_scene_add_mesh", "pb_scene_set_mesh_vertices", "pb_scene_set_mesh_uvs", "pb_scene_set_mesh_transform", "pb_scene_add_area_emitter", "pb_scene_add_envmap", "pb_scene_set_envmap_radiance", "pb_scene_set_envmap_transform", "pb_scene_num_meshes", "pb_scene_configure",
     "pb_scene_reseed", "pb_scene_num_triangles", "pb_scene_get_triangle_info", "pb_scene_mesh_num_edges", "pb_scene_mesh_get_edges",
     "pb_trace", "pb_preprocess_secondary_edges", "pb_render_c", "pb_render_c_host", "pb_render_d", "pb_grad_require", "pb_grad_num_segments", "pb_grad_segment",
-    "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
+    "pb_grad_size", "pb_render_d_vjp", "pb_render_d_jvp", "pb_stats_launches", "pb_stats_last_trace_ms", "pb_stats_last_rays", "pb_stats_last_active_rays", "pb_ctx_set_bvh_refit", "pb_ctx_set_bvh_builder", "pb_stats_bvh", "pb_stats_last_trace_launches", "pb_stats_last_primary_ms",
     "pb_debug_set", "pb_debug_ray_buffer", "pb_debug_retained_rad", "pb_render_d_get_state", "pb_render_d_set_state",
     "pb_scene_set_mesh_vertices_device", "pb_scene_set_bsdf_texture_device", "pb_scene_get_mesh_vertices", "pb_scene_set_edge_importance",
     "pb_sample_boundary_segment_direct", "pb_scene_num_primary_edges", "pb_scene_get_primary_edges", "pb_scene_num_secondary_edges", "pb_scene_get_secondary_edges", "pb_ctx_set_shard_mode", "pb_dist_available", "pb_dist_unique_id", "pb_dist_init", "pb_dist_adopt_comm", "pb_dist_finalize", "pb_allreduce_grads", "pb_allreduce_image", "pb_stats_collectives",
@@ -411,6 +411,10 @@ class Context:
 
     def set_bvh_refit(self, max_consecutive_refits):
         self._chk(lib().pb_ctx_set_bvh_refit(self.h, int(max_consecutive_refits)))
+
+    def set_bvh_builder(self, builder):
+        """0 = binned SAH on the host (default), 1 = LBVH on the device (pb_lbvh.cu)"""
+        self._chk(lib().pb_ctx_set_bvh_builder(self.h, int(builder)))
 
     def bvh_stats(self):
         b, r = C.c_int(), C.c_int()

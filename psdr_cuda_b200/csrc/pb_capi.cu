@@ -418,6 +418,24 @@ static void configure(pb_ctx *c) {
             c->launches += 1 + (int64_t)c->bvh_level_off.size() - 1;
             c->bvh_refits++; c->bvh_refit_count++;
         } else {
+        bool built = false;
+        if (c->bvh_builder == 1 && total > 64) {   // device LBVH (pb_lbvh.cu): topology on the device, boxes by the refit kernels
+            std::vector<int> lev;
+            c->d_order.reserve((size_t)total * sizeof(int));
+            if (lbvh_build(st, total, c->arena_tri(), c->scene_lo, c->scene_hi, c->d_lbvh_scratch, c->d_order.as<int>(), c->arena_nodes(), lev)) {
+                float extent = 0.f;
+                for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(c->scene_lo[k]), std::fabs(c->scene_hi[k])));
+                c->bvh_level_off = lev;
+                c->view.num_nodes = lev.back();
+                c->bvh_valid = true; c->bvh_sig = sig; c->bvh_refits = 0; c->bvh_builds++;
+                launch_build_leaf_tris(st, total, c->d_order.as<int>(), c->arena_tri(), c->arena_leaf());
+                c->d_node_boxes.reserve((size_t)c->view.num_nodes * 12 * sizeof(float));
+                launch_bvh_refit(st, c->arena_nodes(), c->d_node_boxes.as<float>(), c->arena_leaf(), c->bvh_level_off.data(), (int)c->bvh_level_off.size() - 1, extent);
+                c->launches += 4 + 2 * 96 + (int64_t)c->bvh_level_off.size();
+                built = true;
+            }
+        }
+        if (!built) {
         download_triangle_table(c);   // the binned-SAH build runs on the host (first build / topology change only)
         std::vector<float> geo(9 * (size_t)total);
         for (int t = 0; t < total; ++t)
@@ -457,6 +475,7 @@ static void configure(pb_ctx *c) {
         else launch_build_leaf_tris(st, total, c->d_order.as<int>(), c->arena_tri(), c->arena_leaf());
         c->launches += 1;
         c->view.num_nodes = (int)dn.size();
+        }
         }
     }
     {   // the compact copy of the tree the wavefront traversal reads (pb_trace2.cuh)
@@ -1710,6 +1729,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "pipeline_max_lanes") == 0) c->pipeline_max_lanes = value;
         else if (std::strcmp(key, "trace_chunk") == 0) pb::g_trace_chunk = (int)value;
         else if (std::strcmp(key, "trace_blocks") == 0) pb::g_trace_blocks = (int)value;
+        else if (std::strcmp(key, "bvh_builder") == 0) { c->bvh_builder = (int)value; c->bvh_valid = false; }   // = pb_ctx_set_bvh_builder (bench.py --debug)
         else if (std::strcmp(key, "sorted_copy") == 0) { c->sorted_copy = (int)value; c->retained_valid = false; }
         else throw Error(std::string("Unknown debug key: ") + key);
     });
@@ -1730,6 +1750,12 @@ int pb_debug_retained_rad(pb_ctx *c, void **d_rad, int64_t *bytes) {
     });
 }
 int pb_ctx_set_bvh_refit(pb_ctx *c, int max_consecutive_refits) { c->bvh_max_refits = max_consecutive_refits; return 0; }
+int pb_ctx_set_bvh_builder(pb_ctx *c, int builder) {
+    return guard(c, [&] {
+        PB_ASSERT_MSG(builder == PB_BVH_HOST_SAH || builder == PB_BVH_DEVICE_LBVH, "Unknown BVH builder");
+        c->bvh_builder = builder; c->bvh_valid = false;
+    });
+}
 int pb_stats_bvh(pb_ctx *c, int *builds, int *refits) { if (builds) *builds = c->bvh_builds; if (refits) *refits = c->bvh_refit_count; return 0; }
 int pb_ctx_set_retain_limit(pb_ctx *c, int64_t bytes) { c->retain_limit = bytes; c->retained_valid = false; return 0; }
 int pb_render_d_jvp(pb_ctx *c, const pb_integrator *I, int sensor, const float *d_tangent, float *d_dimage) {

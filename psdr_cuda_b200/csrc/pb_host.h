@@ -190,6 +190,8 @@ struct pb_ctx {
     pb::DevBuf d_sorted_rays[2], d_sort_inv[2], d_sorted_hits[2];
     pb::DevBuf d_adj_list[2], d_adj_count[2];   // lane list of the split geometry adjoint (k_adjoint_split), per lane
     pb::DevBuf d_conn[2];                // EventBuffers::conn of the batch in flight on each lane
+    int bvh_builder = 0;                 // first build of the scene BVH: 0 = binned SAH on the host (pb_bvh.cpp), 1 = LBVH on the device (pb_lbvh.cu)
+    pb::DevBuf d_lbvh_scratch;
     int sorted_copy = 0;                 // 1: the interior events trace a sorted copy of their rays (debug key sorted_copy; A/B in profiles/)
     bool retained_hits_by_slot = true;   // the retained hit records are indexed by ray slot (false: stream order — only k_adjoint_lin can use the store)
     int pipeline = 1;                       // 0 never, 1 when a render has at most pipeline_max_lanes lanes, 2 always (debug)

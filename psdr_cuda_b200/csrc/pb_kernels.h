@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "pb_scene.cuh"
 
 namespace pb {
@@ -96,6 +98,9 @@ void launch_trace(cudaStream_t st, const SceneView &S, long long n, const RayRec
 void launch_trace_sorted(cudaStream_t st, const SceneView &S, long long n, const RayRec *rays, HitRec *hits, float3 lo, float3 hi, unsigned *hist, unsigned *perm,
                          unsigned short *keys, unsigned *stream_counter, unsigned long long *active_total, cudaEvent_t ev0, cudaEvent_t ev1, int mode, bool keys_ready,
                          RayRec *sorted = nullptr, unsigned *inv = nullptr);
+struct DevBuf;
+bool lbvh_build(cudaStream_t st, int n, const TriRec *tri, const float *scene_lo, const float *scene_hi, DevBuf &scratch, int *order, BvhNode *nodes,
+                std::vector<int> &level_off);
 void launch_unpermute_hits(cudaStream_t st, long long n, const unsigned *inv, const HitRec *sorted_hits, HitRec *hits);
 void launch_primary(cudaStream_t st, const RenderParams &P, HitRec *hit0);
 void launch_shade(cudaStream_t st, const RenderParams &P, const BounceParams &B, const EventBuffers &E);

@@ -1,0 +1,147 @@
+// psdr-b200: device-side first build of the scene BVH (replaces optixAccelBuild, include/psdr/optix/optix.h:277-340, for scenes whose
+// topology changes often; the default first build is the host's binned SAH, pb_bvh.cpp, whose trees traverse faster).
+//
+// Linear BVH after Karras 2012: 30-bit Morton codes of the triangle centroids, a radix sort, one thread per inner node finds its
+// range and split from the common prefixes of neighbouring codes. Only the topology is built here: ranges of at most kLbvhLeafMax
+// sorted triangles become leaves (the leaf encoding of pb_bvh.h), the live inner nodes are renumbered breadth-first — children after
+// parents, every level a contiguous index range — and the boxes come from the same level-by-level refit kernels that follow a
+// vertex edit (pb_configure.cu). The traversal returns the exact closest hit whatever the tree looks like (ties go to the lower
+// triangle id), so hits are bit-identical to those of the SAH tree.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "pb_host.h"
+#include "pb_kernels.h"
+
+namespace pb {
+
+constexpr int kLbvhLeafMax = 4;
+
+__device__ __forceinline__ unsigned expand_bits10(unsigned v) {   // 10 bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_lbvh_morton(int n, const TriRec *__restrict__ tri, float3 lo, float3 inv_ext, unsigned *__restrict__ codes, int *__restrict__ ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *q = reinterpret_cast<const float4 *>(tri + i);
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    const float third = 1.f / 3.f;
+    const float cx = q0.x + (q1.x + q2.x) * third, cy = q0.y + (q1.y + q2.y) * third, cz = q0.z + (q1.z + q2.z) * third;
+    const unsigned ux = (unsigned)fminf(fmaxf((cx - lo.x) * inv_ext.x * 1024.f, 0.f), 1023.f);
+    const unsigned uy = (unsigned)fminf(fmaxf((cy - lo.y) * inv_ext.y * 1024.f, 0.f), 1023.f);
+    const unsigned uz = (unsigned)fminf(fmaxf((cz - lo.z) * inv_ext.z * 1024.f, 0.f), 1023.f);
+    codes[i] = (expand_bits10(ux) << 2) | (expand_bits10(uy) << 1) | expand_bits10(uz);
+    ids[i] = i;
+}
+
+// length of the common prefix of the keys (code, index) at sorted positions i and j; -1 outside the array
+__device__ __forceinline__ int lbvh_delta(const unsigned *__restrict__ codes, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned a = codes[i], b = codes[j];
+    if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);
+    return __clz(a ^ b);
+}
+
+// inner node i of the n - 1: its two child references. >= 0: inner node; < 0: leaf over sorted slots, ~((first << 3) | (count - 1))
+__global__ void k_lbvh_karras(int n, const unsigned *__restrict__ codes, int2 *__restrict__ children) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (lbvh_delta(codes, n, i, i + 1) - lbvh_delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(codes, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(codes, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lbvh_delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(codes, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if (lbvh_delta(codes, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const int cl = gamma - first + 1, cr = last - gamma;
+    int2 ch;
+    ch.x = cl <= kLbvhLeafMax ? ~((first << 3) | (cl - 1)) : gamma;
+    ch.y = cr <= kLbvhLeafMax ? ~(((gamma + 1) << 3) | (cr - 1)) : gamma + 1;
+    children[i] = ch;
+}
+
+// Breadth-first renumbering, one launch per level. lev[L] .. lev[L + 1]: new indices of level L (lev[0] = 0, lev[1] = 1: the root);
+// bfs[new index] = Karras index. The kernel of level L appends the inner children of its nodes behind lev[L + 1] and writes the
+// nodes of level L (links in the new numbering, boxes zero until the refit); k_lbvh_close_level then fixes lev[L + 2].
+__global__ void k_lbvh_level(int L, const int2 *__restrict__ children, int *__restrict__ bfs, int *__restrict__ lev, unsigned *__restrict__ counter,
+                             BvhNode *__restrict__ nodes) {
+    const int start = lev[L], end = lev[L + 1];
+    const int j = start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= end) return;
+    const int2 ch = children[bfs[j]];
+    int link[2] = {ch.x, ch.y};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+        if (link[s] >= 0) {
+            const int pos = end + (int)atomicAdd(counter, 1u);
+            bfs[pos] = link[s];
+            link[s] = pos;
+        }
+    float4 *np = reinterpret_cast<float4 *>(nodes + j);
+    np[0] = np[1] = np[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    np[3] = make_float4(__int_as_float(link[0]), __int_as_float(link[1]), 0.f, 0.f);
+}
+__global__ void k_lbvh_close_level(int L, int *__restrict__ lev, unsigned *__restrict__ counter) {
+    lev[L + 2] = lev[L + 1] + (int)*counter;
+    *counter = 0u;
+}
+
+// Builds the topology into `nodes` / `order` (order[leaf slot] = triangle id) and returns the level offsets (host) for the refit.
+// scratch grows as needed. Returns false when the tree is deeper than the level table (the caller falls back to the host builder).
+bool lbvh_build(cudaStream_t st, int n, const TriRec *tri, const float *scene_lo, const float *scene_hi, DevBuf &scratch, int *order, BvhNode *nodes,
+                std::vector<int> &level_off) {
+    constexpr int kMaxLevels = 96;
+    PB_ASSERT_MSG(n > 2 * kLbvhLeafMax, "internal: lbvh_build needs more than 8 triangles");
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr, (int *)nullptr, n, 0, 30, st);
+    const size_t o_codes = 0, o_sorted = o_codes + al((size_t)n * 4), o_ids = o_sorted + al((size_t)n * 4), o_children = o_ids + al((size_t)n * 4),
+                 o_bfs = o_children + al((size_t)n * 8), o_lev = o_bfs + al((size_t)n * 4), o_counter = o_lev + al((kMaxLevels + 2) * 4), o_cub = o_counter + 256;
+    scratch.reserve(o_cub + al(cub_bytes));
+    char *base = static_cast<char *>(scratch.p);
+    unsigned *codes = reinterpret_cast<unsigned *>(base + o_codes), *sorted = reinterpret_cast<unsigned *>(base + o_sorted);
+    int *ids = reinterpret_cast<int *>(base + o_ids), *bfs = reinterpret_cast<int *>(base + o_bfs), *lev = reinterpret_cast<int *>(base + o_lev);
+    int2 *children = reinterpret_cast<int2 *>(base + o_children);
+    unsigned *counter = reinterpret_cast<unsigned *>(base + o_counter);
+    const float3 lo = f3(scene_lo[0], scene_lo[1], scene_lo[2]);
+    const float3 inv_ext = f3(1.f / fmaxf(scene_hi[0] - scene_lo[0], 1e-20f), 1.f / fmaxf(scene_hi[1] - scene_lo[1], 1e-20f), 1.f / fmaxf(scene_hi[2] - scene_lo[2], 1e-20f));
+    const unsigned g = (unsigned)((n + 255) / 256);
+    k_lbvh_morton<<<g, 256, 0, st>>>(n, tri, lo, inv_ext, codes, ids);
+    PB_CUDA(cub::DeviceRadixSort::SortPairs(base + o_cub, cub_bytes, codes, sorted, ids, order, n, 0, 30, st));
+    k_lbvh_karras<<<g, 256, 0, st>>>(n, sorted, children);
+    const int init_lev[2] = {0, 1};
+    PB_CUDA(cudaMemsetAsync(lev, 0, (kMaxLevels + 2) * sizeof(int), st));
+    PB_CUDA(cudaMemcpyAsync(lev, init_lev, sizeof(init_lev), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    PB_CUDA(cudaMemsetAsync(bfs, 0, sizeof(int), st));   // the root is Karras node 0
+    for (int L = 0; L < kMaxLevels; ++L) {
+        k_lbvh_level<<<g, 256, 0, st>>>(L, children, bfs, lev, counter, nodes);
+        k_lbvh_close_level<<<1, 1, 0, st>>>(L, lev, counter);
+    }
+    int h_lev[kMaxLevels + 2];
+    PB_CUDA(cudaMemcpyAsync(h_lev, lev, sizeof(h_lev), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    PB_CUDA(cudaGetLastError());
+    if (h_lev[kMaxLevels + 1] != h_lev[kMaxLevels]) return false;   // the last level still had inner children
+    level_off.clear();
+    for (int L = 0; L <= kMaxLevels; ++L) {
+        level_off.push_back(h_lev[L]);
+        if (L > 0 && h_lev[L + 1] == h_lev[L]) break;   // level L is empty: h_lev[L] is the node count
+    }
+    return true;
+}
+
+}  // namespace pb

@@ -941,6 +941,54 @@ def test_bvh_refit_after_vertex_edits_gives_the_same_hits_and_images(desc):
     assert ctx.bvh_stats()["builds"] == 2
 
 
+def test_device_lbvh_first_build_gives_the_same_hits_and_refits(desc):
+    # the device-side first build (pb_lbvh.cu: Morton codes, radix sort, Karras topology, boxes by the refit kernels) against the host's
+    # binned-SAH build: the traversal returns the exact closest hit whatever the tree, so hits and images are bit-identical; a vertex
+    # edit afterwards refits the LBVH tree like any other
+    import time
+    from psdr_cuda_b200 import capi
+    opts = dict(width=64, height=64, spp=4, sppe=0, sppse=0)
+    rng = np.random.default_rng(9)
+    n = 1 << 18
+    o = rng.uniform(-150, 150, size=(n, 3)).astype(np.float32); o[:, 1] = rng.uniform(5, 380, size=n); o[:, 2] = rng.uniform(-350, 250, size=n)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays_t = torch.from_numpy(np.concatenate([o, np.full((n, 1), np.inf, np.float32), d, np.zeros((n, 1), np.float32)], axis=1).astype(np.float32)).cuda()
+    integ = capi.make_integrator("path", max_depth=3)
+    host = make_ctx(desc, opts)
+    dev = capi.Context(0)
+    dev.load_description(desc, opts)
+    dev.set_bvh_builder(1)
+    torch.cuda.synchronize(); t0 = time.time()
+    dev.configure()
+    torch.cuda.synchronize(); t_dev = time.time() - t0
+    h1, t1 = host.trace(rays_t); h2, t2 = dev.trace(rays_t)
+    assert torch.equal(h1, h2) and torch.equal(t1, t2)
+    assert torch.equal(host.render_c(integ), dev.render_c(integ))
+    assert dev.bvh_stats() == dict(builds=1, refits=0)
+    verts = desc["meshes"][1]["verts"] + rng.normal(scale=0.02, size=desc["meshes"][1]["verts"].shape).astype(np.float32)
+    for ctx in (host, dev):
+        ctx.set_mesh_vertices(1, verts)
+        ctx.configure()
+    assert dev.bvh_stats() == dict(builds=1, refits=1)
+    h1, t1 = host.trace(rays_t); h2, t2 = dev.trace(rays_t)
+    assert torch.equal(h1, h2) and torch.equal(t1, t2)
+    # a second first build (topology marked dirty) for the timing, without the one-off allocations
+    dev.set_bvh_refit(0)
+    dev.set_mesh_vertices(1, verts)
+    torch.cuda.synchronize(); t0 = time.time()
+    dev.configure()
+    torch.cuda.synchronize(); t_dev2 = time.time() - t0
+    host.set_bvh_refit(0)
+    host.set_mesh_vertices(1, verts)
+    torch.cuda.synchronize(); t0 = time.time()
+    host.configure()
+    torch.cuda.synchronize(); t_host = time.time() - t0
+    h1, _ = host.trace(rays_t); h2, _ = dev.trace(rays_t)
+    assert torch.equal(h1, h2)
+    print("configure with a first build: device LBVH %.1f ms (first %.1f) vs host SAH %.1f ms" % (1e3 * t_dev2, 1e3 * t_dev, 1e3 * t_host))
+    host.close(); dev.close()
+
+
 # ---- Sensor.to_world as a differentiable leaf (a4 in its ad flavour: camera rays, projected primary edges, secondary-edge camera ray) ----
 def _sensor_grad_case(scene, opts, kind, kw, rtol=3e-3, smooth_weights=False):
     from oracle import orc
