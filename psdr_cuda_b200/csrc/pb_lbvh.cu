@@ -1,4 +1,4 @@
-// psdr-b200: device-side first build of the scene BVH (replaces optixAccelBuild, include/psdr/optix/optix.h:277-340, for scenes whose
+// psdr-b200: device-side first build of the scene BVH (replaces optixAccelBuild, include/psdr/scene/optix.h:277-340, for scenes whose
 // topology changes often; the default first build is the host's binned SAH, pb_bvh.cpp, whose trees traverse faster).
 //
 // Linear BVH after Karras 2012: 30-bit Morton codes of the triangle centroids, a radix sort, one thread per inner node finds its
