@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the l2_fetch debug key — cudaLimitMaxL2FetchGranularity — existed only for this run; result in profiles/r02ae_*: no effect)
 mkdir -p gpurun_out
 python -m pytest tests/test_abi.py -q -x 2>&1 | tail -2 || exit 1
 timeout 900 bash scripts/bench_short.sh "--no-verify --debug l2_fetch=32" "--no-verify --debug l2_fetch=64" "--no-verify --debug l2_fetch=128" 2>&1 | tee gpurun_out/r02ad_l2_fetch.log
