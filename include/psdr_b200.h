@@ -205,7 +205,7 @@ float pb_stats_last_trace_ms(pb_ctx *ctx);
 int pb_ctx_set_bvh_refit(pb_ctx *ctx, int max_consecutive_refits);
 /* First build of the tree (and every rebuild after a topology change): PB_BVH_HOST_SAH (default) = binned SAH on the host, 40-60 ms for
  * 144 k triangles; PB_BVH_DEVICE_LBVH = Morton codes + radix sort + Karras topology on the device, boxes by the refit kernels: the whole
- * configure 7 ms, but its trees traverse ~30 % slower (6.1 vs 8.7 Grays/s on the bench) — for scenes whose topology changes every iteration.
+ * configure 4-7 ms, but its trees traverse ~27 % slower (6.4 vs 8.7 Grays/s on the bench) — for scenes whose topology changes every iteration.
  * Same hits either way. Replaces optixAccelBuild, include/psdr/scene/optix.h:277-340. */
 enum { PB_BVH_HOST_SAH = 0, PB_BVH_DEVICE_LBVH = 1 };
 int pb_ctx_set_bvh_builder(pb_ctx *ctx, int builder);

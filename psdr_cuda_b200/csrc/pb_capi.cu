@@ -1730,6 +1730,7 @@ int pb_debug_set(pb_ctx *c, const char *key, int64_t value) {
         else if (std::strcmp(key, "trace_chunk") == 0) pb::g_trace_chunk = (int)value;
         else if (std::strcmp(key, "trace_blocks") == 0) pb::g_trace_blocks = (int)value;
         else if (std::strcmp(key, "bvh_builder") == 0) { c->bvh_builder = (int)value; c->bvh_valid = false; }   // = pb_ctx_set_bvh_builder (bench.py --debug)
+        else if (std::strcmp(key, "lbvh_leaf") == 0) { pb::g_lbvh_leaf_max = (int)value; c->bvh_valid = false; }
         else if (std::strcmp(key, "sorted_copy") == 0) { c->sorted_copy = (int)value; c->retained_valid = false; }
         else throw Error(std::string("Unknown debug key: ") + key);
     });

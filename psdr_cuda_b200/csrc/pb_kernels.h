@@ -88,6 +88,7 @@ void launch_rng_seed(cudaStream_t st, long long n, ulonglong2 *out);
 void launch_build_leaf_tris(cudaStream_t st, int n, const int *order, const TriRec *tri, LeafTri *leaf);
 
 extern int g_sort_mode;       // debug: sort key (pb_sort.cu)
+extern int g_lbvh_leaf_max;
 extern int g_adjoint_lin;     // debug: 0 = reflectance adjoints through k_adjoint (connection by connection) even when the linearisation was kept
 extern int g_shade_simple;    // debug: 0 = never use the diffuse + area-light instantiations
 extern int g_shade_tune;      // debug: k_resolve / k_adjoint variant (0 default)

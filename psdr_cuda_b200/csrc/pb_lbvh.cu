@@ -2,11 +2,13 @@
 // topology changes often; the default first build is the host's binned SAH, pb_bvh.cpp, whose trees traverse faster).
 //
 // Linear BVH after Karras 2012: 30-bit Morton codes of the triangle centroids, a radix sort, one thread per inner node finds its
-// range and split from the common prefixes of neighbouring codes. Only the topology is built here: ranges of at most kLbvhLeafMax
+// range and split from the common prefixes of neighbouring codes. Only the topology is built here: ranges of at most g_lbvh_leaf_max
 // sorted triangles become leaves (the leaf encoding of pb_bvh.h), the live inner nodes are renumbered breadth-first — children after
 // parents, every level a contiguous index range — and the boxes come from the same level-by-level refit kernels that follow a
 // vertex edit (pb_configure.cu). The traversal returns the exact closest hit whatever the tree looks like (ties go to the lower
 // triangle id), so hits are bit-identical to those of the SAH tree.
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pb_host.h"
@@ -14,7 +16,7 @@
 
 namespace pb {
 
-constexpr int kLbvhLeafMax = 4;
+int g_lbvh_leaf_max = 2;   // most triangles per leaf (1..8; debug key lbvh_leaf): 8 / 4 / 2 / 1 -> 5.59 / 6.10 / 6.36 / 6.44 Grays/s on the bench (profiles/r02ar_*)
 
 __device__ __forceinline__ unsigned expand_bits10(unsigned v) {   // 10 bits -> every third bit
     v = (v * 0x00010001u) & 0xFF0000FFu;
@@ -47,7 +49,7 @@ __device__ __forceinline__ int lbvh_delta(const unsigned *__restrict__ codes, in
 }
 
 // inner node i of the n - 1: its two child references. >= 0: inner node; < 0: leaf over sorted slots, ~((first << 3) | (count - 1))
-__global__ void k_lbvh_karras(int n, const unsigned *__restrict__ codes, int2 *__restrict__ children) {
+__global__ void k_lbvh_karras(int n, int leaf_max, const unsigned *__restrict__ codes, int2 *__restrict__ children) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int d = (lbvh_delta(codes, n, i, i + 1) - lbvh_delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -68,8 +70,8 @@ __global__ void k_lbvh_karras(int n, const unsigned *__restrict__ codes, int2 *_
     const int first = min(i, j), last = max(i, j);
     const int cl = gamma - first + 1, cr = last - gamma;
     int2 ch;
-    ch.x = cl <= kLbvhLeafMax ? ~((first << 3) | (cl - 1)) : gamma;
-    ch.y = cr <= kLbvhLeafMax ? ~(((gamma + 1) << 3) | (cr - 1)) : gamma + 1;
+    ch.x = cl <= leaf_max ? ~((first << 3) | (cl - 1)) : gamma;
+    ch.y = cr <= leaf_max ? ~(((gamma + 1) << 3) | (cr - 1)) : gamma + 1;
     children[i] = ch;
 }
 
@@ -104,7 +106,8 @@ __global__ void k_lbvh_close_level(int L, int *__restrict__ lev, unsigned *__res
 bool lbvh_build(cudaStream_t st, int n, const TriRec *tri, const float *scene_lo, const float *scene_hi, DevBuf &scratch, int *order, BvhNode *nodes,
                 std::vector<int> &level_off) {
     constexpr int kMaxLevels = 96;
-    PB_ASSERT_MSG(n > 2 * kLbvhLeafMax, "internal: lbvh_build needs more than 8 triangles");
+    const int leaf_max = std::min(8, std::max(1, g_lbvh_leaf_max));
+    PB_ASSERT_MSG(n > 16, "internal: lbvh_build needs more than 16 triangles");
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr, (int *)nullptr, n, 0, 30, st);
@@ -121,7 +124,7 @@ bool lbvh_build(cudaStream_t st, int n, const TriRec *tri, const float *scene_lo
     const unsigned g = (unsigned)((n + 255) / 256);
     k_lbvh_morton<<<g, 256, 0, st>>>(n, tri, lo, inv_ext, codes, ids);
     PB_CUDA(cub::DeviceRadixSort::SortPairs(base + o_cub, cub_bytes, codes, sorted, ids, order, n, 0, 30, st));
-    k_lbvh_karras<<<g, 256, 0, st>>>(n, sorted, children);
+    k_lbvh_karras<<<g, 256, 0, st>>>(n, leaf_max, sorted, children);
     const int init_lev[2] = {0, 1};
     PB_CUDA(cudaMemsetAsync(lev, 0, (kMaxLevels + 2) * sizeof(int), st));
     PB_CUDA(cudaMemcpyAsync(lev, init_lev, sizeof(init_lev), cudaMemcpyHostToDevice, st));
