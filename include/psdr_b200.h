@@ -224,6 +224,7 @@ float pb_stats_last_primary_ms(pb_ctx *ctx);
  *   "shade_simple" [1] 0 = never use the diffuse + area-light instantiations; "shade_tune" [0] register caps of the event kernels
  *   "pipeline" [1] (per context) 0 = one batch at a time, 1 = two batches in flight for renders of at most "pipeline_max_lanes" lanes, 2 = always
  *   "l2_persist" [1], "rng_seed_table" [1] (per context)
+ *   "bvh_builder" [0] (per context) = pb_ctx_set_bvh_builder; "lbvh_leaf" [2] most triangles per leaf of the device LBVH (1..8)
  * Unknown keys are an error. */
 int pb_debug_set(pb_ctx *ctx, const char *key, int64_t value);
 int pb_debug_ray_buffer(pb_ctx *ctx, int event, void **d_rays, int64_t *bytes);       /* rays of the last event traced by the last batch */

@@ -30,6 +30,16 @@ def test_python_binding_lists_the_same_symbols(native_lib):
     assert sorted(capi.SYMBOLS) == header_symbols()
 
 
+def test_header_documents_every_debug_key():
+    # pb_debug_set's keys are the A/B switches behind profiles/: each one the library accepts is listed in the header
+    src = open(os.path.join(ROOT, "psdr_cuda_b200", "csrc", "pb_capi.cu")).read()
+    keys = set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', src))
+    assert len(keys) >= 10
+    header = open(os.path.join(ROOT, "include", "psdr_b200.h")).read()
+    for k in keys:
+        assert '"%s"' % k in header, "pb_debug_set key not documented in include/psdr_b200.h: " + k
+
+
 def test_no_cpu_fallback(native_lib):
     import torch
     if torch.cuda.is_available():
