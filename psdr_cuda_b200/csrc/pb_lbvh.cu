@@ -13,18 +13,11 @@
 
 #include "pb_host.h"
 #include "pb_kernels.h"
+#include "pb_lbvh.cuh"
 
 namespace pb {
 
 int g_lbvh_leaf_max = 2;   // most triangles per leaf (1..8; debug key lbvh_leaf): 8 / 4 / 2 / 1 -> 5.59 / 6.10 / 6.36 / 6.44 Grays/s on the bench (profiles/r02ar_*)
-
-__device__ __forceinline__ unsigned expand_bits10(unsigned v) {   // 10 bits -> every third bit
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
-}
 
 __global__ void k_lbvh_morton(int n, const TriRec *__restrict__ tri, float3 lo, float3 inv_ext, unsigned *__restrict__ codes, int *__restrict__ ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,46 +26,16 @@ __global__ void k_lbvh_morton(int n, const TriRec *__restrict__ tri, float3 lo, 
     const float4 q0 = q[0], q1 = q[1], q2 = q[2];
     const float third = 1.f / 3.f;
     const float cx = q0.x + (q1.x + q2.x) * third, cy = q0.y + (q1.y + q2.y) * third, cz = q0.z + (q1.z + q2.z) * third;
-    const unsigned ux = (unsigned)fminf(fmaxf((cx - lo.x) * inv_ext.x * 1024.f, 0.f), 1023.f);
-    const unsigned uy = (unsigned)fminf(fmaxf((cy - lo.y) * inv_ext.y * 1024.f, 0.f), 1023.f);
-    const unsigned uz = (unsigned)fminf(fmaxf((cz - lo.z) * inv_ext.z * 1024.f, 0.f), 1023.f);
-    codes[i] = (expand_bits10(ux) << 2) | (expand_bits10(uy) << 1) | expand_bits10(uz);
+    codes[i] = lbvh_morton30(cx, cy, cz, lo, inv_ext);
     ids[i] = i;
 }
 
-// length of the common prefix of the keys (code, index) at sorted positions i and j; -1 outside the array
-__device__ __forceinline__ int lbvh_delta(const unsigned *__restrict__ codes, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    const unsigned a = codes[i], b = codes[j];
-    if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);
-    return __clz(a ^ b);
-}
-
-// inner node i of the n - 1: its two child references. >= 0: inner node; < 0: leaf over sorted slots, ~((first << 3) | (count - 1))
+// inner node i of the n - 1: its two child references (pb_lbvh.cuh)
 __global__ void k_lbvh_karras(int n, int leaf_max, const unsigned *__restrict__ codes, int2 *__restrict__ children) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    const int d = (lbvh_delta(codes, n, i, i + 1) - lbvh_delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
-    const int dmin = lbvh_delta(codes, n, i, i - d);
-    int lmax = 2;
-    while (lbvh_delta(codes, n, i, i + lmax * d) > dmin) lmax *= 2;
-    int l = 0;
-    for (int t = lmax / 2; t >= 1; t /= 2)
-        if (lbvh_delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
-    const int j = i + l * d;
-    const int dnode = lbvh_delta(codes, n, i, j);
-    int s = 0, t = l;
-    do {
-        t = (t + 1) / 2;
-        if (lbvh_delta(codes, n, i, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    const int gamma = i + s * d + min(d, 0);
-    const int first = min(i, j), last = max(i, j);
-    const int cl = gamma - first + 1, cr = last - gamma;
-    int2 ch;
-    ch.x = cl <= leaf_max ? ~((first << 3) | (cl - 1)) : gamma;
-    ch.y = cr <= leaf_max ? ~(((gamma + 1) << 3) | (cr - 1)) : gamma + 1;
-    children[i] = ch;
+    const LbvhNode nd = lbvh_inner_node(codes, n, i, leaf_max);
+    children[i] = make_int2(nd.left, nd.right);
 }
 
 // Breadth-first renumbering, one launch per level. lev[L] .. lev[L + 1]: new indices of level L (lev[0] = 0, lev[1] = 1: the root);

@@ -31,3 +31,18 @@ def test_roughconductor_dual_derivatives_match_finite_differences(tmp_path):
                            os.path.join(ROOT, "tests", "native", "rc_dual_check.cu")], stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "rc_dual_check: ok" in out.stdout, out.stdout[-2000:]
+
+
+def test_device_lbvh_node_arithmetic_builds_a_valid_tree(tmp_path):
+    """csrc/pb_lbvh.cuh (Morton codes, common-prefix lengths with the index tie-break, Karras range / split search, leaf collapse), the
+    per-node arithmetic of the device LBVH build, host-compiled: 64 cases (17 .. 50 000 primitives; uniform, clustered, mostly-duplicate and
+    seven-code inputs; 1 / 2 / 4 / 8 slots per leaf) must each give a binary tree that covers every sorted slot exactly once"""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "lbvh_check")
+    subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "lbvh_check.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "lbvh_check: ok" in out.stdout, out.stdout[-2000:]
+
